@@ -1,0 +1,100 @@
+"""ctypes binding of the C-ABI shared library ``libbodyfit_b200.so``.
+
+The library holds every kernel of the product path.  There is no CPU fallback and no
+alternative backend: if the shared object is missing, or the current device is not
+sm_100, importing / calling fails loudly.  Struct layouts mirror
+``include/bodyfit_b200.h`` field by field.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libbodyfit_b200.so')
+ABI_VERSION = 4
+F_WORLD = 1
+
+_fp = C.c_void_p
+_i32 = C.c_int32
+
+
+class BfVSet(C.Structure):
+    _fields_ = [(n, _fp) for n in (
+        'Bm', 'ell_j', 'ell_w', 'jv_ptr', 'jv_vid', 'jv_w', 'kj_kind', 'kj_src', 'kj_w',
+        'dyn_src', 'dyn_w', 'tg_ptr', 'tg_k', 'tg_a', 'tg_w', 'xr_ptr', 'xr_vid', 'xr_w')] + \
+        [(n, _i32) for n in ('n', 'n_pad', 'ldn', 'nnz', 'K_out', 'n_dyn', 'n_extra', '_pad0')]
+
+
+class BfModel(C.Structure):
+    _fields_ = [(n, _fp) for n in (
+        'parents', 'depth', 'child_ptr', 'child_idx', 'Jt', 'Jd', 'pose_mean', 'hand_l', 'hand_r',
+        'gmm_mean', 'gmm_prec', 'gmm_prec_t', 'gmm_logw')] + \
+        [('full', BfVSet), ('act', BfVSet)] + \
+        [(n, _i32) for n in ('J', 'P', 'NS', 'NB', 'Kp', 'NP', 'is_smplx', 'max_depth', 'K_used',
+                             'n_gmm', '_pad0', '_pad1')]
+
+
+class BfFrames(C.Structure):
+    _fields_ = [(n, _fp) for n in (
+        'theta', 'grad', 'adam_m', 'adam_v', 'pf', 'dpf', 'A', 'dA', 'Jtr', 'dJtr', 'full_pose', 'yaw',
+        'verts', 'vposed', 'dverts', 'dvp', 'joints', 'djoints', 'kp', 'cams', 'loss', 'loss_terms', 'trace')] + \
+        [(n, C.c_double) for n in ('lr_ts', 'lr', 'beta1', 'beta2', 'eps')] + \
+        [(n, _i32) for n in ('B', 'Nv', 'ld_v', 'iter', 'flags', '_pad0')] + \
+        [(n, C.c_float) for n in ('imsize', 'constant_scale', 'sigma', 'w_pose', 'w_angle', 'w_shape')]
+
+
+class BodyfitError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Load (once) and return the shared library; raises if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise BodyfitError(
+            'CUDA extension %s is missing: run `python -c "import __graft_entry__ as g; g.build()"` '
+            '(there is no CPU fallback)' % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    L.bf_abi_version.restype = C.c_int
+    L.bf_last_error.restype = C.c_char_p
+    L.bf_check_device.restype = C.c_int
+    L.bf_sizeof.restype = C.c_int
+    L.bf_sizeof.argtypes = [C.c_int]
+    if L.bf_abi_version() != ABI_VERSION:
+        raise BodyfitError('ABI mismatch: library %d, binding %d -- rebuild' % (L.bf_abi_version(), ABI_VERSION))
+    for i, st in enumerate((BfVSet, BfModel, BfFrames)):
+        if L.bf_sizeof(i) != C.sizeof(st):
+            raise BodyfitError('struct layout mismatch for %s: C %d, ctypes %d' % (st.__name__, L.bf_sizeof(i), C.sizeof(st)))
+    pm, pf, vp, ci = C.POINTER(BfModel), C.POINTER(BfFrames), C.c_void_p, C.c_int
+    for name, extra in (('bf_pose_forward', []), ('bf_skin_forward', [ci]), ('bf_joints_forward', [ci]),
+                        ('bf_joints_backward', [ci, ci]), ('bf_keypoint_loss', [ci]), ('bf_skin_backward', [ci]),
+                        ('bf_pose_backward', [ci]), ('bf_lbs_forward', []), ('bf_lbs_backward', []),
+                        ('bf_fit_step', []), ('bf_fit_run', [ci])):
+        fn = getattr(L, name)
+        fn.restype = C.c_int
+        fn.argtypes = [pm, pf] + extra + [vp]
+    _lib = L
+    return L
+
+
+EXPORTED = ['bf_abi_version', 'bf_sizeof', 'bf_last_error', 'bf_check_device', 'bf_pose_forward', 'bf_skin_forward',
+            'bf_joints_forward', 'bf_joints_backward', 'bf_keypoint_loss', 'bf_skin_backward',
+            'bf_pose_backward', 'bf_lbs_forward', 'bf_lbs_backward', 'bf_fit_step', 'bf_fit_run']
+
+
+def check(rc, what=''):
+    if rc != 0:
+        msg = lib().bf_last_error()
+        raise BodyfitError('%s failed (%d): %s' % (what, rc, msg.decode() if msg else ''))
+
+
+def require_device():
+    """Raise unless the current CUDA device is a B200-class (sm_100) GPU."""
+    import torch
+    if not torch.cuda.is_available():
+        raise BodyfitError('no CUDA device: bodyfitting_b200 has no CPU path')
+    check(lib().bf_check_device(), 'bf_check_device')

@@ -1,0 +1,199 @@
+// C ABI of the B200 SMPLify fitting core (see include/bodyfit_b200.h).
+// Plain launchers: validate, launch on the caller's stream, report errors by return code.
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include "bf_common.cuh"
+#include "bf_pose.cuh"
+#include "bf_skin.cuh"
+#include "bf_loss.cuh"
+#include "bf_blend_tc.cuh"
+
+static thread_local char g_err[512] = "";
+
+void bf_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+static int check_model(const BfModel* m, const BfFrames* f) {
+    BF_REQUIRE(m && f, "null model / frames");
+    BF_REQUIRE(m->J > 0 && m->J <= BF_MAXJ, "J out of range");
+    BF_REQUIRE(m->NS > 0 && m->NS <= BF_MAXNS && m->NB <= m->NS, "NS/NB out of range");
+    BF_REQUIRE(m->NP == theta_layout(m->is_smplx).np && m->NP <= BF_MAXNP, "NP does not match theta layout");
+    BF_REQUIRE(m->Kp % 16 == 0 && m->Kp >= m->P + m->NS + 1, "Kp must be a multiple of 16 covering P+NS+1");
+    BF_REQUIRE(m->P == (m->J - 1) * 9, "P != 9(J-1)");
+    BF_REQUIRE(f->B > 0, "B <= 0");
+    BF_REQUIRE(f->theta, "theta is null");
+    return BF_OK;
+}
+
+static int check_vset(const BfVSet* vs, const BfFrames* f) {
+    BF_REQUIRE(vs->Bm && vs->ell_j && vs->ell_w, "vertex set tables missing");
+    BF_REQUIRE(vs->n > 0 && vs->n_pad % 32 == 0 && vs->n_pad >= vs->n && vs->ldn == 3 * vs->n_pad, "bad vertex set padding");
+    BF_REQUIRE(f->ld_v >= 3 * vs->n, "ld_v < 3n");
+    BF_REQUIRE(vs->K_out <= BF_MAXK, "too many output joints");
+    return BF_OK;
+}
+
+extern "C" {
+
+int bf_abi_version(void) { return BF_ABI_VERSION; }
+int bf_sizeof(int which) { return which == 0 ? (int)sizeof(BfVSet) : which == 1 ? (int)sizeof(BfModel) : (int)sizeof(BfFrames); }
+const char* bf_last_error(void) { return g_err; }
+
+int bf_check_device(void) {
+    int dev = 0;
+    cudaDeviceProp p;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&p, dev) != cudaSuccess) {
+        bf_set_error("bf_check_device: no CUDA device");
+        return BF_ECUDA;
+    }
+    if (p.major != 10) {
+        bf_set_error("bf_check_device: device %s is sm_%d%d; this library is sm_100a only (no fallback)", p.name, p.major, p.minor);
+        return BF_EARCH;
+    }
+    return BF_OK;
+}
+
+int bf_pose_forward(const BfModel* m, const BfFrames* f, void* stream) {
+    int rc = check_model(m, f); if (rc) return rc;
+    BF_REQUIRE(f->pf && f->A && f->Jtr, "pf/A/Jtr is null");
+    const int wpb = 4;
+    const dim3 grid((f->B + wpb - 1) / wpb), block(32 * wpb);
+    k_pose_fwd<<<grid, block, wpb * sizeof(PoseSmem), (cudaStream_t)stream>>>(*m, *f);
+    BF_LAUNCH_CHECK();
+    return BF_OK;
+}
+
+int bf_skin_forward(const BfModel* m, const BfFrames* f, int use_full, void* stream) {
+    int rc = check_model(m, f); if (rc) return rc;
+    const BfVSet* vs = use_full ? &m->full : &m->act;
+    rc = check_vset(vs, f); if (rc) return rc;
+    BF_REQUIRE(f->pf && f->A && f->verts, "pf/A/verts is null");
+    if (bf_tc_enabled() && f->B >= 128) {
+        rc = bf_skin_forward_tc(m, vs, f, (cudaStream_t)stream);
+        if (rc != 1) return rc;       // 1 = shape not supported by the tensor-core path, fall through to FFMA
+    }
+    const dim3 grid(vs->n_pad / SK_TV, (f->B + SK_TB - 1) / SK_TB), block(256);
+    k_skin_fwd<<<grid, block, 0, (cudaStream_t)stream>>>(*vs, m->J, m->Kp, f->pf, f->A, f->verts, f->vposed, f->B, f->ld_v,
+                                                           (f->flags & BF_F_WORLD) ? f->theta : nullptr, m->NP, f->constant_scale);
+    BF_LAUNCH_CHECK();
+    return BF_OK;
+}
+
+int bf_joints_forward(const BfModel* m, const BfFrames* f, int use_full, void* stream) {
+    int rc = check_model(m, f); if (rc) return rc;
+    const BfVSet* vs = use_full ? &m->full : &m->act;
+    rc = check_vset(vs, f); if (rc) return rc;
+    BF_REQUIRE(f->joints && f->Jtr && f->verts, "joints/Jtr/verts is null");
+    k_joints_fwd<<<f->B, 160, 0, (cudaStream_t)stream>>>(*m, *vs, *f);
+    BF_LAUNCH_CHECK();
+    return BF_OK;
+}
+
+int bf_joints_backward(const BfModel* m, const BfFrames* f, int use_full, int accumulate_dverts, void* stream) {
+    int rc = check_model(m, f); if (rc) return rc;
+    const BfVSet* vs = use_full ? &m->full : &m->act;
+    rc = check_vset(vs, f); if (rc) return rc;
+    BF_REQUIRE(f->dJtr && f->dverts, "dJtr/dverts is null");
+    k_joints_bwd<<<f->B, 256, 0, (cudaStream_t)stream>>>(*m, *vs, *f, accumulate_dverts);
+    BF_LAUNCH_CHECK();
+    return BF_OK;
+}
+
+int bf_keypoint_loss(const BfModel* m, const BfFrames* f, int use_full, void* stream) {
+    int rc = check_model(m, f); if (rc) return rc;
+    const BfVSet* vs = use_full ? &m->full : &m->act;
+    rc = check_vset(vs, f); if (rc) return rc;
+    BF_REQUIRE(f->kp && f->cams && f->loss && f->grad && f->dJtr && f->dverts && f->verts && f->Jtr, "loss buffers missing");
+    BF_REQUIRE(f->Nv > 0 && f->Nv <= BF_MAXVIEWS, "Nv out of range");
+    BF_REQUIRE(m->K_used <= vs->K_out, "K_used > K_out");
+    const int threads = use_full ? 256 : 160;
+    k_keypoint_loss<<<f->B, threads, 0, (cudaStream_t)stream>>>(*m, *vs, *f);
+    BF_LAUNCH_CHECK();
+    return BF_OK;
+}
+
+int bf_skin_backward(const BfModel* m, const BfFrames* f, int use_full, void* stream) {
+    int rc = check_model(m, f); if (rc) return rc;
+    const BfVSet* vs = use_full ? &m->full : &m->act;
+    rc = check_vset(vs, f); if (rc) return rc;
+    BF_REQUIRE(f->dverts && f->dvp && f->vposed && f->dA && f->dpf && f->A, "backward buffers missing");
+    BF_REQUIRE(vs->jv_ptr && vs->jv_vid && vs->jv_w, "joint->vertex lists missing");
+    cudaStream_t s = (cudaStream_t)stream;
+    {
+        const dim3 grid((vs->n + 255) / 256, (f->B + DV_FB - 1) / DV_FB);
+        k_skin_bwd_dvp<<<grid, 256, 0, s>>>(*vs, m->J, f->A, f->dverts, f->dvp, f->B, f->ld_v);
+        BF_LAUNCH_CHECK();
+    }
+    k_skin_bwd_dA<<<f->B, 256, 0, s>>>(*vs, m->J, f->dverts, f->vposed, f->dA, f->B, f->ld_v);
+    BF_LAUNCH_CHECK();
+    {
+        const dim3 grid((m->Kp + GB_T - 1) / GB_T, (f->B + GB_T - 1) / GB_T);
+        k_blend_bwd<<<grid, 256, 0, s>>>(*vs, m->Kp, f->dvp, f->dpf, f->B, f->ld_v);
+        BF_LAUNCH_CHECK();
+    }
+    return BF_OK;
+}
+
+int bf_pose_backward(const BfModel* m, const BfFrames* f, int flags, void* stream) {
+    int rc = check_model(m, f); if (rc) return rc;
+    BF_REQUIRE(f->dA && f->dJtr && f->dpf && f->grad && f->loss, "pose backward buffers missing");
+    if (flags & 1) BF_REQUIRE(m->gmm_mean && m->gmm_prec && m->gmm_prec_t && m->gmm_logw && m->n_gmm > 0, "GMM tables missing");
+    if (flags & 2) BF_REQUIRE(f->adam_m && f->adam_v, "Adam state missing");
+    // bias corrections in double on the host, exactly as torch.optim.Adam does for python-float steps
+    const double t = (double)(f->iter + 1);
+    const double bc1 = 1.0 - pow(f->beta1, t);
+    const double bc2 = 1.0 - pow(f->beta2, t);
+    AdamArgs ad;
+    ad.step_ts = (float)(f->lr_ts / bc1);
+    ad.step_lr = (float)(f->lr / bc1);
+    ad.bc2_sqrt = (float)sqrt(bc2);
+    ad.beta2 = (float)f->beta2;
+    ad.om_beta1 = (float)(1.0 - f->beta1);
+    ad.om_beta2 = (float)(1.0 - f->beta2);
+    ad.eps = (float)f->eps;
+    const int wpb = 4;
+    const dim3 grid((f->B + wpb - 1) / wpb), block(32 * wpb);
+    k_pose_bwd<<<grid, block, wpb * sizeof(PoseSmemBwd), (cudaStream_t)stream>>>(*m, *f, flags, ad);
+    BF_LAUNCH_CHECK();
+    return BF_OK;
+}
+
+int bf_lbs_forward(const BfModel* m, const BfFrames* f, void* stream) {
+    int rc = bf_pose_forward(m, f, stream); if (rc) return rc;
+    rc = bf_skin_forward(m, f, 1, stream); if (rc) return rc;
+    if (f->joints) rc = bf_joints_forward(m, f, 1, stream);
+    return rc;
+}
+
+int bf_lbs_backward(const BfModel* m, const BfFrames* f, void* stream) {
+    // f->dverts holds the incoming d(vertices) (dense); f->djoints the incoming d(joints) or NULL
+    int rc = bf_joints_backward(m, f, 1, 1, stream); if (rc) return rc;
+    rc = bf_skin_backward(m, f, 1, stream); if (rc) return rc;
+    return bf_pose_backward(m, f, 0, stream);
+}
+
+int bf_fit_step(const BfModel* m, const BfFrames* f, void* stream) {
+    int rc = bf_pose_forward(m, f, stream); if (rc) return rc;
+    rc = bf_skin_forward(m, f, 0, stream); if (rc) return rc;
+    rc = bf_keypoint_loss(m, f, 0, stream); if (rc) return rc;
+    rc = bf_skin_backward(m, f, 0, stream); if (rc) return rc;
+    return bf_pose_backward(m, f, 1 | 2 | 4, stream);
+}
+
+int bf_fit_run(const BfModel* m, const BfFrames* f, int n_iters, void* stream) {
+    BF_REQUIRE(m && f && n_iters >= 0, "bad arguments");
+    BfFrames g = *f;
+    for (int i = 0; i < n_iters; ++i) {
+        int rc = bf_fit_step(m, &g, stream); if (rc) return rc;
+        g.iter++;
+    }
+    return BF_OK;
+}
+
+}  // extern "C"

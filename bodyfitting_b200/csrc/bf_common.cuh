@@ -1,0 +1,110 @@
+// Shared helpers for the sm_100a SMPLify fitting kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/bodyfit_b200.h"
+
+#define BF_MAXJ 55          // SMPL-X kinematic tree
+#define BF_MAXNS 20         // 10 betas + 10 expression coefficients
+#define BF_MAXNP 100        // theta entries (86 / 98)
+#define BF_GMM_D 69
+
+void bf_set_error(const char* fmt, ...);
+
+#define BF_REQUIRE(cond, msg)                                   \
+    do { if (!(cond)) { bf_set_error("%s: %s", __func__, msg); return BF_EINVAL; } } while (0)
+
+#define BF_LAUNCH_CHECK()                                                              \
+    do { cudaError_t e_ = cudaGetLastError();                                          \
+         if (e_ != cudaSuccess) { bf_set_error("%s: launch failed: %s", __func__,      \
+                                               cudaGetErrorString(e_)); return BF_ECUDA; } } while (0)
+
+// theta layout (see include/bodyfit_b200.h)
+struct ThetaLayout {
+    int nbody, off_betas, off_leye, off_reye, off_lh, off_rh, np;
+};
+__host__ __device__ __forceinline__ ThetaLayout theta_layout(int is_smplx) {
+    ThetaLayout t;
+    t.nbody = is_smplx ? 63 : 69;
+    t.off_betas = 7 + t.nbody;
+    t.off_leye = t.off_betas + 10;
+    t.off_reye = t.off_leye + 3;
+    t.off_lh = t.off_reye + 3;
+    t.off_rh = t.off_lh + 6;
+    t.np = is_smplx ? t.off_rh + 6 : t.off_betas + 10;
+    return t;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// R = I + sin(a) K + (1 - cos(a)) K^2 with a = ||r + 1e-8||, K = skew(r / a)
+// (smplx.lbs.batch_rodrigues as restated in oracle/smplx_port.py).  Row-major R[9].
+__device__ __forceinline__ void rodrigues_fwd(float rx, float ry, float rz, float* R) {
+    const float ex = rx + 1e-8f, ey = ry + 1e-8f, ez = rz + 1e-8f;
+    const float a = sqrtf(ex * ex + ey * ey + ez * ez);
+    const float dx = rx / a, dy = ry / a, dz = rz / a;
+    float s, c;
+    sincosf(a, &s, &c);
+    const float oc = 1.0f - c;
+    R[0] = 1.0f + oc * (-(dy * dy + dz * dz));
+    R[1] = -s * dz + oc * (dx * dy);
+    R[2] = s * dy + oc * (dx * dz);
+    R[3] = s * dz + oc * (dx * dy);
+    R[4] = 1.0f + oc * (-(dx * dx + dz * dz));
+    R[5] = -s * dx + oc * (dy * dz);
+    R[6] = -s * dy + oc * (dx * dz);
+    R[7] = s * dx + oc * (dy * dz);
+    R[8] = 1.0f + oc * (-(dx * dx + dy * dy));
+}
+
+// Backward of exactly the composite above (matches autograd of the restatement,
+// including the epsilon placement).  G = dL/dR (row-major), out = dL/dr.
+__device__ __forceinline__ void rodrigues_bwd(float rx, float ry, float rz, const float* G, float* out) {
+    const float ex = rx + 1e-8f, ey = ry + 1e-8f, ez = rz + 1e-8f;
+    const float a = sqrtf(ex * ex + ey * ey + ez * ez);
+    const float ia = 1.0f / a;
+    const float dx = rx * ia, dy = ry * ia, dz = rz * ia;
+    float s, c;
+    sincosf(a, &s, &c);
+    const float oc = 1.0f - c;
+    // K and K^2
+    const float K[9] = {0.f, -dz, dy, dz, 0.f, -dx, -dy, dx, 0.f};
+    const float K2[9] = {-(dy * dy + dz * dz), dx * dy, dx * dz,
+                         dx * dy, -(dx * dx + dz * dz), dy * dz,
+                         dx * dz, dy * dz, -(dx * dx + dy * dy)};
+    float dLds = 0.f, dLdoc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { dLds += G[i] * K[i]; dLdoc += G[i] * K2[i]; }
+    // dL/dK = s G + oc (G K^T + K^T G)
+    float dK[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            float h = 0.f;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) h += G[i * 3 + k] * K[j * 3 + k] + K[k * 3 + i] * G[k * 3 + j];
+            dK[i * 3 + j] = s * G[i * 3 + j] + oc * h;
+        }
+    const float ddx = dK[7] - dK[5];
+    const float ddy = dK[2] - dK[6];
+    const float ddz = dK[3] - dK[1];
+    float dLda = dLds * c + dLdoc * s;
+    dLda -= (ddx * rx + ddy * ry + ddz * rz) * ia * ia;
+    out[0] = ddx * ia + dLda * ex * ia;
+    out[1] = ddy * ia + dLda * ey * ia;
+    out[2] = ddz * ia + dLda * ez * ia;
+}
+
+__device__ __forceinline__ void mat3_mul(const float* A, const float* B, float* C) {   // C = A B
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            C[r * 3 + c] = A[r * 3 + 0] * B[0 * 3 + c] + A[r * 3 + 1] * B[1 * 3 + c] + A[r * 3 + 2] * B[2 * 3 + c];
+}

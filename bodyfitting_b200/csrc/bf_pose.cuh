@@ -1,0 +1,376 @@
+// Pose kernels: one warp per frame.
+//   k_pose_fwd : theta -> full_pose, Rodrigues, pose-feature row (GEMM A operand),
+//                rest joints from betas, kinematic chain by tree level, A = rest-pose-removed
+//                transforms, posed joints, dynamic-landmark yaw row.
+//   k_pose_bwd : recompute the above in shared memory, reverse chain traversal,
+//                Rodrigues backward, PCA-hand backward, GMM / angle / shape priors and the
+//                Adam update, fused per frame.
+// Replaces smplx batch_rodrigues + batch_rigid_transform (restated in oracle/smplx_port.py),
+// smplify/prior.py:181-196, smplify/loss.py:54-61,206-217 and torch.optim.Adam
+// (smplify/smplify.py:167-174,211-213).
+#pragma once
+#include "bf_common.cuh"
+
+struct PoseSmem {
+    float th[BF_MAXNP];
+    float fp[BF_MAXJ * 3];
+    float sh[BF_MAXNS];
+    float R[BF_MAXJ * 9];
+    float Jr[BF_MAXJ * 3];
+    float GR[BF_MAXJ * 9];
+    float Gt[BF_MAXJ * 3];
+};
+struct PoseSmemBwd {
+    PoseSmem f;
+    float dGR[BF_MAXJ * 9];
+    float dGt[BF_MAXJ * 3];
+    float dJr[BF_MAXJ * 3];
+    float drel[BF_MAXJ * 3];
+    float dfp[BF_MAXJ * 3];
+    float dm[BF_GMM_D + 3];
+    float x69[BF_GMM_D + 3];
+};
+
+// Fills S for frame b (all lanes of one warp participate).
+__device__ __forceinline__ void pose_forward_warp(const BfModel& m, const float* __restrict__ theta_row,
+                                                  PoseSmem& S, int lane) {
+    const ThetaLayout L = theta_layout(m.is_smplx);
+    const int J = m.J;
+    for (int i = lane; i < L.np; i += 32) S.th[i] = theta_row[i];
+    __syncwarp();
+    // full pose
+    for (int i = lane; i < 3 * J; i += 32) {
+        float v = 0.f;
+        if (i < 3) v = S.th[4 + i];
+        else if (i < 3 + L.nbody) v = S.th[7 + (i - 3)];
+        else if (m.is_smplx) {
+            if (i < 69) v = 0.f;                                    // jaw: not optimised, stays 0
+            else if (i < 72) v = S.th[L.off_leye + (i - 69)];
+            else if (i < 75) v = S.th[L.off_reye + (i - 72)];
+            else if (i < 120) {
+                const int c0 = i - 75;
+#pragma unroll
+                for (int c = 0; c < 6; ++c) v += S.th[L.off_lh + c] * __ldg(m.hand_l + c * 45 + c0);
+            } else {
+                const int c0 = i - 120;
+#pragma unroll
+                for (int c = 0; c < 6; ++c) v += S.th[L.off_rh + c] * __ldg(m.hand_r + c * 45 + c0);
+            }
+        }
+        S.fp[i] = v + __ldg(m.pose_mean + i);
+    }
+    for (int l = lane; l < m.NS; l += 32) S.sh[l] = (l < m.NB) ? S.th[L.off_betas + l] : 0.f;
+    __syncwarp();
+    // rotations and rest joints
+    for (int j = lane; j < J; j += 32) {
+        float R[9];
+        rodrigues_fwd(S.fp[3 * j], S.fp[3 * j + 1], S.fp[3 * j + 2], R);
+#pragma unroll
+        for (int e = 0; e < 9; ++e) S.R[j * 9 + e] = R[e];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float acc = 0.f;
+            const float* jd = m.Jd + (j * 3 + c) * m.NS;
+            for (int l = 0; l < m.NS; ++l) acc += __ldg(jd + l) * S.sh[l];
+            S.Jr[j * 3 + c] = __ldg(m.Jt + j * 3 + c) + acc;
+        }
+    }
+    __syncwarp();
+    // kinematic chain, level by level (parents[j] < j, depth[parent] = depth[j] - 1)
+    for (int lev = 0; lev <= m.max_depth; ++lev) {
+        for (int j = lane; j < J; j += 32) {
+            if (__ldg(m.depth + j) != lev) continue;
+            if (lev == 0) {
+#pragma unroll
+                for (int e = 0; e < 9; ++e) S.GR[j * 9 + e] = S.R[j * 9 + e];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) S.Gt[j * 3 + c] = S.Jr[j * 3 + c];
+            } else {
+                const int p = __ldg(m.parents + j);
+                float rel[3], G[9];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) rel[c] = S.Jr[j * 3 + c] - S.Jr[p * 3 + c];
+                mat3_mul(&S.GR[p * 9], &S.R[j * 9], G);
+#pragma unroll
+                for (int e = 0; e < 9; ++e) S.GR[j * 9 + e] = G[e];
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+                    S.Gt[j * 3 + r] = S.GR[p * 9 + r * 3 + 0] * rel[0] + S.GR[p * 9 + r * 3 + 1] * rel[1] +
+                                      S.GR[p * 9 + r * 3 + 2] * rel[2] + S.Gt[p * 3 + r];
+            }
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(128) k_pose_fwd(BfModel m, BfFrames f) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    PoseSmem* all = reinterpret_cast<PoseSmem*>(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (b >= f.B) return;
+    PoseSmem& S = all[warp];
+    const int J = m.J;
+    pose_forward_warp(m, f.theta + (size_t)b * m.NP, S, lane);
+
+    // GEMM A operand row: [R_1..R_{J-1} - I | shape | 1 | 0...]
+    float* pf = f.pf + (size_t)b * m.Kp;
+    for (int i = lane; i < m.Kp; i += 32) {
+        float v = 0.f;
+        if (i < m.P) {
+            const int e = i % 9;
+            v = S.R[9 + i] - ((e == 0 || e == 4 || e == 8) ? 1.0f : 0.0f);
+        } else if (i < m.P + m.NS) v = S.sh[i - m.P];
+        else if (i == m.P + m.NS) v = 1.0f;
+        pf[i] = v;
+    }
+    // A_j = [GR_j | Gt_j - GR_j Jr_j],  posed joints = Gt
+    for (int j = lane; j < J; j += 32) {
+        float* Aj = f.A + ((size_t)b * J + j) * 12;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const float g0 = S.GR[j * 9 + r * 3], g1 = S.GR[j * 9 + r * 3 + 1], g2 = S.GR[j * 9 + r * 3 + 2];
+            Aj[r * 4 + 0] = g0; Aj[r * 4 + 1] = g1; Aj[r * 4 + 2] = g2;
+            Aj[r * 4 + 3] = S.Gt[j * 3 + r] - (g0 * S.Jr[j * 3] + g1 * S.Jr[j * 3 + 1] + g2 * S.Jr[j * 3 + 2]);
+            f.Jtr[((size_t)b * J + j) * 3 + r] = S.Gt[j * 3 + r];
+        }
+    }
+    if (f.full_pose)
+        for (int i = lane; i < 3 * J; i += 32) f.full_pose[(size_t)b * 3 * J + i] = S.fp[i];
+    // dynamic landmark row from the head yaw (smplx find_dynamic_lmk_idx_and_bcoords):
+    // rel = R0 (R3 (R6 (R9 R12))), yaw = atan2(-rel[2][0], sqrt(rel00^2 + rel10^2))
+    if (lane == 0 && f.yaw) {
+        int row = 0;
+        if (m.is_smplx) {
+            float rel[9], t[9];
+#pragma unroll
+            for (int e = 0; e < 9; ++e) rel[e] = S.R[12 * 9 + e];
+            const int chain[4] = {9, 6, 3, 0};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                mat3_mul(&S.R[chain[q] * 9], rel, t);
+#pragma unroll
+                for (int e = 0; e < 9; ++e) rel[e] = t[e];
+            }
+            const float sy = sqrtf(rel[0] * rel[0] + rel[3] * rel[3]);
+            const float ang = atan2f(-rel[6], sy);
+            float y = rintf(fminf((-ang * 180.0f) / 3.14159265358979323846f, 39.0f));
+            int yi = (int)y;
+            if (yi < 0) yi = (yi < -39) ? 78 : (39 - yi);
+            row = yi;
+        }
+        f.yaw[b] = row;
+    }
+}
+
+// flags: 1 = priors, 2 = Adam, 4 = keep grad[0:4] written by the loss kernel (else zero them)
+struct AdamArgs { float step_ts, step_lr, bc2_sqrt, beta2, om_beta1, om_beta2, eps; };
+
+__global__ void __launch_bounds__(128) k_pose_bwd(BfModel m, BfFrames f, int flags, AdamArgs ad) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    PoseSmemBwd* all = reinterpret_cast<PoseSmemBwd*>(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (b >= f.B) return;
+    PoseSmemBwd& W = all[warp];
+    PoseSmem& S = W.f;
+    const int J = m.J;
+    const ThetaLayout L = theta_layout(m.is_smplx);
+    pose_forward_warp(m, f.theta + (size_t)b * m.NP, S, lane);
+
+    // direct terms
+    for (int j = lane; j < J; j += 32) {
+        const float* dAj = f.dA + ((size_t)b * J + j) * 12;
+        const float* dJj = f.dJtr + ((size_t)b * J + j) * 3;
+        float dAt[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            dAt[r] = dAj[r * 4 + 3];
+            W.dGt[j * 3 + r] = dJj[r] + dAt[r];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) W.dGR[j * 9 + r * 3 + c] = dAj[r * 4 + c] - dAt[r] * S.Jr[j * 3 + c];
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            W.dJr[j * 3 + c] = -(S.GR[j * 9 + 0 * 3 + c] * dAt[0] + S.GR[j * 9 + 1 * 3 + c] * dAt[1] +
+                                 S.GR[j * 9 + 2 * 3 + c] * dAt[2]);
+    }
+    __syncwarp();
+    // reverse traversal: a joint gathers from its children (one level deeper, already final)
+    for (int lev = m.max_depth - 1; lev >= 0; --lev) {
+        for (int j = lane; j < J; j += 32) {
+            if (__ldg(m.depth + j) != lev) continue;
+            const int c0 = __ldg(m.child_ptr + j), c1 = __ldg(m.child_ptr + j + 1);
+            for (int q = c0; q < c1; ++q) {
+                const int ch = __ldg(m.child_idx + q);
+                float rel[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) rel[c] = S.Jr[ch * 3 + c] - S.Jr[j * 3 + c];
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    const float g0 = W.dGR[ch * 9 + r * 3], g1 = W.dGR[ch * 9 + r * 3 + 1], g2 = W.dGR[ch * 9 + r * 3 + 2];
+                    const float gt = W.dGt[ch * 3 + r];
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)   // dGR_p += dGR_c R_c^T + dGt_c (x) rel_c
+                        W.dGR[j * 9 + r * 3 + c] += g0 * S.R[ch * 9 + c * 3] + g1 * S.R[ch * 9 + c * 3 + 1] +
+                                                    g2 * S.R[ch * 9 + c * 3 + 2] + gt * rel[c];
+                    W.dGt[j * 3 + r] += gt;
+                }
+            }
+        }
+        __syncwarp();
+    }
+    // local rotation / offset gradients
+    for (int j = lane; j < J; j += 32) {
+        float dR[9], dr[3];
+        if (j == 0) {
+#pragma unroll
+            for (int e = 0; e < 9; ++e) dR[e] = W.dGR[e];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) dr[c] = W.dGt[c];
+        } else {
+            const int p = __ldg(m.parents + j);
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c)       // dR = GR_p^T dGR_j
+                    dR[r * 3 + c] = S.GR[p * 9 + 0 * 3 + r] * W.dGR[j * 9 + 0 * 3 + c] +
+                                    S.GR[p * 9 + 1 * 3 + r] * W.dGR[j * 9 + 1 * 3 + c] +
+                                    S.GR[p * 9 + 2 * 3 + r] * W.dGR[j * 9 + 2 * 3 + c];
+                dr[r] = S.GR[p * 9 + 0 * 3 + r] * W.dGt[j * 3 + 0] + S.GR[p * 9 + 1 * 3 + r] * W.dGt[j * 3 + 1] +
+                        S.GR[p * 9 + 2 * 3 + r] * W.dGt[j * 3 + 2];
+            }
+            const float* dpf = f.dpf + (size_t)b * m.Kp + (j - 1) * 9;
+#pragma unroll
+            for (int e = 0; e < 9; ++e) dR[e] += dpf[e];
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) W.drel[j * 3 + c] = dr[c];
+        float g[3];
+        rodrigues_bwd(S.fp[3 * j], S.fp[3 * j + 1], S.fp[3 * j + 2], dR, g);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) W.dfp[j * 3 + c] = g[c];
+    }
+    __syncwarp();
+    for (int j = lane; j < J; j += 32) {
+        float acc[3] = {W.drel[j * 3], W.drel[j * 3 + 1], W.drel[j * 3 + 2]};
+        const int c0 = __ldg(m.child_ptr + j), c1 = __ldg(m.child_ptr + j + 1);
+        for (int q = c0; q < c1; ++q) {
+            const int ch = __ldg(m.child_idx + q);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) acc[c] -= W.drel[ch * 3 + c];
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) W.dJr[j * 3 + c] += acc[c];
+    }
+    __syncwarp();
+
+    float* g = f.grad + (size_t)b * m.NP;
+    // betas: rest-joint path + shape rows of the blend GEMM
+    if (lane < m.NB) {
+        float acc = f.dpf[(size_t)b * m.Kp + m.P + lane];
+        for (int q = 0; q < 3 * J; ++q) acc += __ldg(m.Jd + q * m.NS + lane) * W.dJr[q];
+        g[L.off_betas + lane] = acc;
+    }
+    for (int i = lane; i < 3 + L.nbody; i += 32) g[4 + i] = W.dfp[i];      // global_orient + body_pose
+    if (m.is_smplx) {
+        if (lane < 3) { g[L.off_leye + lane] = W.dfp[69 + lane]; g[L.off_reye + lane] = W.dfp[72 + lane]; }
+        if (lane < 12) {
+            const int c = lane % 6;
+            const float* comp = (lane < 6 ? m.hand_l : m.hand_r) + c * 45;
+            const float* d = W.dfp + (lane < 6 ? 75 : 120);
+            float acc = 0.f;
+            for (int i = 0; i < 45; ++i) acc += __ldg(comp + i) * d[i];
+            g[(lane < 6 ? L.off_lh : L.off_rh) + c] = acc;
+        }
+    }
+    if (!(flags & 4) && lane < 4) g[lane] = 0.f;
+    __syncwarp();
+
+    float total = (flags & 4) ? f.loss[b] : 0.f;
+    if (flags & 1) {
+        // ---- GMM pose prior (merged likelihood, min over components) ----
+        for (int i = lane; i < BF_GMM_D; i += 32) W.x69[i] = (i < L.nbody) ? S.th[7 + i] : 0.f;
+        __syncwarp();
+        float best = 0.f; int mbest = -1;
+        for (int c = 0; c < m.n_gmm; ++c) {
+            for (int i = lane; i < BF_GMM_D; i += 32) W.dm[i] = W.x69[i] - __ldg(m.gmm_mean + c * BF_GMM_D + i);
+            __syncwarp();
+            const float* Pm = m.gmm_prec_t + (size_t)c * BF_GMM_D * BF_GMM_D;   // Pm[j][i] = P[i][j]
+            float part = 0.f;
+            for (int i = lane; i < BF_GMM_D; i += 32) {
+                float acc = 0.f;                                               // (P d)_i
+                for (int j = 0; j < BF_GMM_D; ++j) acc += __ldg(Pm + j * BF_GMM_D + i) * W.dm[j];
+                part += acc * W.dm[i];
+            }
+            const float q = warp_sum(part);
+            const float ll = 0.5f * q - __ldg(m.gmm_logw + c);
+            if (mbest < 0 || ll < best) { best = ll; mbest = c; }
+            __syncwarp();
+        }
+        for (int i = lane; i < BF_GMM_D; i += 32) W.dm[i] = W.x69[i] - __ldg(m.gmm_mean + mbest * BF_GMM_D + i);
+        __syncwarp();
+        {
+            const float* P = m.gmm_prec + (size_t)mbest * BF_GMM_D * BF_GMM_D;
+            const float* Pt = m.gmm_prec_t + (size_t)mbest * BF_GMM_D * BF_GMM_D;
+            const float wp = f.w_pose * f.w_pose;
+            for (int i = lane; i < L.nbody; i += 32) {
+                float a = 0.f, bb = 0.f;
+                for (int j = 0; j < BF_GMM_D; ++j) {
+                    a += __ldg(Pt + j * BF_GMM_D + i) * W.dm[j];   // (P d)_i
+                    bb += __ldg(P + j * BF_GMM_D + i) * W.dm[j];   // (P^T d)_i
+                }
+                g[7 + i] += wp * 0.5f * (a + bb);
+            }
+        }
+        __syncwarp();
+        const float pose_l = f.w_pose * f.w_pose * best;
+        // ---- angle prior: exp(sign * pose[idx])^2 on elbows / knees ----
+        float ang = 0.f;
+        if (lane < 4) {
+            const int idx = (lane == 0) ? 52 : (lane == 1) ? 55 : (lane == 2) ? 9 : 12;
+            const float sg = (lane == 0) ? 1.0f : -1.0f;
+            const float e = expf(S.th[7 + idx] * sg);
+            ang = e * e;
+            g[7 + idx] += f.w_angle * f.w_angle * 2.0f * ang * sg;
+        }
+        const float angle_l = f.w_angle * f.w_angle * warp_sum(ang);
+        // ---- shape prior ----
+        float sq = 0.f;
+        if (lane < m.NB) {
+            const float be = S.th[L.off_betas + lane];
+            sq = be * be;
+            g[L.off_betas + lane] += f.w_shape * f.w_shape * 2.0f * be;
+        }
+        const float shape_l = f.w_shape * f.w_shape * warp_sum(sq);
+        if (lane == 0 && f.loss_terms) {
+            f.loss_terms[b * 4 + 0] = total;
+            f.loss_terms[b * 4 + 1] = pose_l;
+            f.loss_terms[b * 4 + 2] = angle_l;
+            f.loss_terms[b * 4 + 3] = shape_l;
+        }
+        total += pose_l + angle_l + shape_l;
+    }
+    if (lane == 0) {
+        f.loss[b] = total;
+        if (f.trace) f.trace[(size_t)f.iter * f.B + b] = total;
+    }
+    __syncwarp();
+    if (flags & 2) {
+        // torch.optim.Adam (torch 2.x single-tensor path): m.lerp_(g, 1-b1); v = v*b2 + (1-b2) g g;
+        // denom = sqrt(v)/sqrt(bc2) + eps; p -= (lr/bc1) * m / denom
+        float* th = f.theta + (size_t)b * m.NP;
+        float* am = f.adam_m + (size_t)b * m.NP;
+        float* av = f.adam_v + (size_t)b * m.NP;
+        for (int i = lane; i < m.NP; i += 32) {
+            const float gi = g[i];
+            float mi = am[i], vi = av[i];
+            mi = mi + (gi - mi) * ad.om_beta1;
+            vi = vi * ad.beta2 + ad.om_beta2 * gi * gi;
+            const float denom = sqrtf(vi) / ad.bc2_sqrt + ad.eps;
+            const float step = (i < 4) ? ad.step_ts : ad.step_lr;
+            th[i] = S.th[i] + (-step) * mi / denom;
+            am[i] = mi; av[i] = vi;
+        }
+    }
+}

@@ -1,0 +1,264 @@
+// Blend-shape contraction + linear blend skinning over a vertex set, forward and backward.
+//
+//   k_skin_fwd   : v_posed[b, :] = pf[b, :] @ Bm  (shape + pose blend shapes + template in ONE
+//                  dense contraction, K = P + NS + 1), then in the epilogue, with the v_posed tile
+//                  still in registers, verts = (sum_k w_k A[b, j_k]) [v_posed; 1].
+//                  FP32 FFMA tile kernel (64 frames x 32 vertices per CTA, K chunks of 16 staged in
+//                  shared memory, double buffered).  The tcgen05 / 3xTF32 variant lives in
+//                  bf_blend_tc.cuh and shares the epilogue.
+//   k_skin_bwd_dvp : dvp = T_v[:3,:3]^T dverts            (thread per vertex, FB frames each)
+//   k_skin_bwd_dA  : dA[b,j] = sum_v w_vj dverts_v (x) [v_posed_v; 1]   (warp per (frame, joint),
+//                    gather over a CSR-by-joint list -> deterministic, no atomics)
+//   k_blend_bwd    : dpf = dvp @ Bm^T  (64x64 tiles, reduction over the vertex coordinates)
+//
+// Replaces smplx.lbs.lbs (blend_shapes, pose_offsets matmul, skinning matmul) and its autograd
+// backward; reference call sites models/smpl.py:71, smplify/smplify.py:179-187.
+#pragma once
+#include "bf_common.cuh"
+
+#define SK_TB 64      // frames per CTA
+#define SK_TV 32      // vertices per CTA
+#define SK_TN 96      // coordinates per CTA
+#define SK_KC 16      // K chunk
+#define SK_LDA 68     // padded frame stride of the transposed A tile (floats)
+
+__global__ void __launch_bounds__(256) k_skin_fwd(BfVSet vs, int J, int Kp, const float* __restrict__ pf,
+                                                  const float* __restrict__ A, float* __restrict__ verts,
+                                                  float* __restrict__ vposed, int B, int ld_v,
+                                                  const float* __restrict__ theta, int NP, float cs) {
+    __shared__ __align__(16) float As[2][SK_KC][SK_LDA];
+    __shared__ __align__(16) float Bs[2][SK_KC][SK_TN];
+    const int t = threadIdx.x;
+    const int tf = t >> 5, tv = t & 31;
+    const int b0 = blockIdx.y * SK_TB;
+    const int n0 = blockIdx.x * SK_TN;
+    const int ldn = vs.ldn;
+
+    // global -> register staging maps
+    const int ar = t >> 2, akq = (t & 3) * 4;
+    int arow = b0 + ar; if (arow >= B) arow = B - 1;
+    const float* aptr = pf + (size_t)arow * Kp + akq;
+    const int bk0 = t / 24, bc0 = (t % 24) * 4;
+    const int t2 = t + 256;
+    const int bk1 = t2 / 24, bc1 = (t2 % 24) * 4;
+    const bool has2 = t2 < (SK_KC * SK_TN / 4);
+    const float* bptr0 = vs.Bm + (size_t)bk0 * ldn + n0 + bc0;
+    const float* bptr1 = vs.Bm + (size_t)bk1 * ldn + n0 + bc1;
+
+    float acc[8][3];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { acc[i][0] = 0.f; acc[i][1] = 0.f; acc[i][2] = 0.f; }
+
+    float4 ra = *reinterpret_cast<const float4*>(aptr);
+    float4 rb0 = __ldg(reinterpret_cast<const float4*>(bptr0));
+    float4 rb1 = has2 ? __ldg(reinterpret_cast<const float4*>(bptr1)) : make_float4(0, 0, 0, 0);
+    As[0][akq + 0][ar] = ra.x; As[0][akq + 1][ar] = ra.y; As[0][akq + 2][ar] = ra.z; As[0][akq + 3][ar] = ra.w;
+    *reinterpret_cast<float4*>(&Bs[0][bk0][bc0]) = rb0;
+    if (has2) *reinterpret_cast<float4*>(&Bs[0][bk1][bc1]) = rb1;
+    __syncthreads();
+
+    const int nk = Kp / SK_KC;
+    for (int kc = 0; kc < nk; ++kc) {
+        const int cur = kc & 1;
+        if (kc + 1 < nk) {
+            const size_t ko = (size_t)(kc + 1) * SK_KC;
+            ra = *reinterpret_cast<const float4*>(aptr + ko);
+            rb0 = __ldg(reinterpret_cast<const float4*>(bptr0 + ko * ldn));
+            if (has2) rb1 = __ldg(reinterpret_cast<const float4*>(bptr1 + ko * ldn));
+        }
+#pragma unroll
+        for (int k = 0; k < SK_KC; ++k) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[cur][k][tf * 8]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[cur][k][tf * 8 + 4]);
+            const float bx = Bs[cur][k][tv * 3 + 0], by = Bs[cur][k][tv * 3 + 1], bz = Bs[cur][k][tv * 3 + 2];
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                acc[i][0] = fmaf(av[i], bx, acc[i][0]);
+                acc[i][1] = fmaf(av[i], by, acc[i][1]);
+                acc[i][2] = fmaf(av[i], bz, acc[i][2]);
+            }
+        }
+        if (kc + 1 < nk) {
+            const int nxt = cur ^ 1;
+            As[nxt][akq + 0][ar] = ra.x; As[nxt][akq + 1][ar] = ra.y; As[nxt][akq + 2][ar] = ra.z; As[nxt][akq + 3][ar] = ra.w;
+            *reinterpret_cast<float4*>(&Bs[nxt][bk0][bc0]) = rb0;
+            if (has2) *reinterpret_cast<float4*>(&Bs[nxt][bk1][bc1]) = rb1;
+        }
+        __syncthreads();
+    }
+
+    // epilogue: skinning with the v_posed micro-tile in registers
+    const int v = blockIdx.x * SK_TV + tv;
+    if (v >= vs.n) return;
+    const int nnz = vs.nnz;
+    const int32_t* ej = vs.ell_j + (size_t)v * nnz;
+    const float* ew = vs.ell_w + (size_t)v * nnz;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int b = b0 + tf * 8 + i;
+        if (b >= B) break;
+        const float px = acc[i][0], py = acc[i][1], pz = acc[i][2];
+        float T[12];
+#pragma unroll
+        for (int e = 0; e < 12; ++e) T[e] = 0.f;
+        const float* Ab = A + (size_t)b * J * 12;
+        for (int k = 0; k < nnz; ++k) {
+            const float w = __ldg(ew + k);
+            const float4* Aj = reinterpret_cast<const float4*>(Ab + __ldg(ej + k) * 12);
+            const float4 r0 = __ldg(Aj), r1 = __ldg(Aj + 1), r2 = __ldg(Aj + 2);
+            T[0] = fmaf(w, r0.x, T[0]); T[1] = fmaf(w, r0.y, T[1]); T[2] = fmaf(w, r0.z, T[2]); T[3] = fmaf(w, r0.w, T[3]);
+            T[4] = fmaf(w, r1.x, T[4]); T[5] = fmaf(w, r1.y, T[5]); T[6] = fmaf(w, r1.z, T[6]); T[7] = fmaf(w, r1.w, T[7]);
+            T[8] = fmaf(w, r2.x, T[8]); T[9] = fmaf(w, r2.y, T[9]); T[10] = fmaf(w, r2.z, T[10]); T[11] = fmaf(w, r2.w, T[11]);
+        }
+        float* o = verts + (size_t)b * ld_v + 3 * v;
+        float ox = T[0] * px + T[1] * py + T[2] * pz + T[3];
+        float oy = T[4] * px + T[5] * py + T[6] * pz + T[7];
+        float oz = T[8] * px + T[9] * py + T[10] * pz + T[11];
+        if (theta) {                      // world = (x + transl) * scale * constant_scale
+            const float* th = theta + (size_t)b * NP;
+            const float sc = __ldg(th + 3);
+            ox = (ox + __ldg(th + 0)) * sc * cs; oy = (oy + __ldg(th + 1)) * sc * cs; oz = (oz + __ldg(th + 2)) * sc * cs;
+        }
+        o[0] = ox; o[1] = oy; o[2] = oz;
+        if (vposed) {
+            float* q = vposed + (size_t)b * ld_v + 3 * v;
+            q[0] = px; q[1] = py; q[2] = pz;
+        }
+    }
+}
+
+#define DV_FB 4
+__global__ void __launch_bounds__(256) k_skin_bwd_dvp(BfVSet vs, int J, const float* __restrict__ A,
+                                                      const float* __restrict__ dverts, float* __restrict__ dvp,
+                                                      int B, int ld_v) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= vs.n) return;
+    const int nnz = vs.nnz;
+    const int32_t* ej = vs.ell_j + (size_t)v * nnz;
+    const float* ew = vs.ell_w + (size_t)v * nnz;
+    for (int i = 0; i < DV_FB; ++i) {
+        const int b = blockIdx.y * DV_FB + i;
+        if (b >= B) break;
+        const float* g = dverts + (size_t)b * ld_v + 3 * v;
+        const float gx = g[0], gy = g[1], gz = g[2];
+        float T[9];
+#pragma unroll
+        for (int e = 0; e < 9; ++e) T[e] = 0.f;
+        const float* Ab = A + (size_t)b * J * 12;
+        for (int k = 0; k < nnz; ++k) {
+            const float w = __ldg(ew + k);
+            const float4* Aj = reinterpret_cast<const float4*>(Ab + __ldg(ej + k) * 12);
+            const float4 r0 = __ldg(Aj), r1 = __ldg(Aj + 1), r2 = __ldg(Aj + 2);
+            T[0] = fmaf(w, r0.x, T[0]); T[1] = fmaf(w, r0.y, T[1]); T[2] = fmaf(w, r0.z, T[2]);
+            T[3] = fmaf(w, r1.x, T[3]); T[4] = fmaf(w, r1.y, T[4]); T[5] = fmaf(w, r1.z, T[5]);
+            T[6] = fmaf(w, r2.x, T[6]); T[7] = fmaf(w, r2.y, T[7]); T[8] = fmaf(w, r2.z, T[8]);
+        }
+        float* o = dvp + (size_t)b * ld_v + 3 * v;
+        o[0] = T[0] * gx + T[3] * gy + T[6] * gz;
+        o[1] = T[1] * gx + T[4] * gy + T[7] * gz;
+        o[2] = T[2] * gx + T[5] * gy + T[8] * gz;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_skin_bwd_dA(BfVSet vs, int J, const float* __restrict__ dverts,
+                                                     const float* __restrict__ vposed, float* __restrict__ dA,
+                                                     int B, int ld_v) {
+    const int b = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const float* g = dverts + (size_t)b * ld_v;
+    const float* x = vposed + (size_t)b * ld_v;
+    for (int j = warp; j < J; j += nw) {
+        float acc[12];
+#pragma unroll
+        for (int e = 0; e < 12; ++e) acc[e] = 0.f;
+        const int e0 = __ldg(vs.jv_ptr + j), e1 = __ldg(vs.jv_ptr + j + 1);
+        for (int e = e0 + lane; e < e1; e += 32) {
+            const int v = __ldg(vs.jv_vid + e);
+            const float w = __ldg(vs.jv_w + e);
+            const float gx = w * g[3 * v], gy = w * g[3 * v + 1], gz = w * g[3 * v + 2];
+            const float px = x[3 * v], py = x[3 * v + 1], pz = x[3 * v + 2];
+            acc[0] = fmaf(gx, px, acc[0]); acc[1] = fmaf(gx, py, acc[1]); acc[2] = fmaf(gx, pz, acc[2]); acc[3] += gx;
+            acc[4] = fmaf(gy, px, acc[4]); acc[5] = fmaf(gy, py, acc[5]); acc[6] = fmaf(gy, pz, acc[6]); acc[7] += gy;
+            acc[8] = fmaf(gz, px, acc[8]); acc[9] = fmaf(gz, py, acc[9]); acc[10] = fmaf(gz, pz, acc[10]); acc[11] += gz;
+        }
+#pragma unroll
+        for (int e = 0; e < 12; ++e) acc[e] = warp_sum(acc[e]);
+        if (lane < 12) {
+            float val = acc[0];
+#pragma unroll
+            for (int e = 1; e < 12; ++e) if (lane == e) val = acc[e];
+            dA[((size_t)b * J + j) * 12 + lane] = val;
+        }
+    }
+}
+
+#define GB_T 64
+#define GB_KC 16
+#define GB_LD 68
+// dpf[b, k] = sum_n dvp[b, n] * Bm[k, n],  n < 3 * vs.n
+__global__ void __launch_bounds__(256) k_blend_bwd(BfVSet vs, int Kp, const float* __restrict__ dvp,
+                                                   float* __restrict__ dpf, int B, int ld_v) {
+    __shared__ __align__(16) float Xs[2][GB_KC][GB_LD];
+    __shared__ __align__(16) float Ys[2][GB_KC][GB_LD];
+    const int t = threadIdx.x;
+    const int ty = t >> 4, tx = t & 15;
+    const int b0 = blockIdx.y * GB_T, k0 = blockIdx.x * GB_T;
+    const int nvalid = 3 * vs.n;
+    const int ldn = vs.ldn;
+    const int r = t >> 2, nq = (t & 3) * 4;
+    int xrow = b0 + r; if (xrow >= B) xrow = B - 1;
+    int yrow = k0 + r; if (yrow >= Kp) yrow = Kp - 1;
+    const float* xp = dvp + (size_t)xrow * ld_v + nq;
+    const float* yp = vs.Bm + (size_t)yrow * ldn + nq;
+
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    const int nchunks = (nvalid + GB_KC - 1) / GB_KC;
+    float rx[4];
+    float4 ry;
+    auto load = [&](int c) {
+        const int n = c * GB_KC + nq;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) rx[i] = (n + i < nvalid) ? xp[(size_t)c * GB_KC + i] : 0.f;
+        ry = __ldg(reinterpret_cast<const float4*>(yp + (size_t)c * GB_KC));   // ldn >= padded extent, pad columns are 0
+    };
+    auto store = [&](int buf) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) Xs[buf][nq + i][r] = rx[i];
+        Ys[buf][nq + 0][r] = ry.x; Ys[buf][nq + 1][r] = ry.y; Ys[buf][nq + 2][r] = ry.z; Ys[buf][nq + 3][r] = ry.w;
+    };
+    load(0); store(0);
+    __syncthreads();
+    for (int c = 0; c < nchunks; ++c) {
+        const int cur = c & 1;
+        if (c + 1 < nchunks) load(c + 1);
+#pragma unroll
+        for (int n = 0; n < GB_KC; ++n) {
+            const float4 xv = *reinterpret_cast<const float4*>(&Xs[cur][n][ty * 4]);
+            const float4 yv = *reinterpret_cast<const float4*>(&Ys[cur][n][tx * 4]);
+            const float xa[4] = {xv.x, xv.y, xv.z, xv.w};
+            const float ya[4] = {yv.x, yv.y, yv.z, yv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xa[i], ya[j], acc[i][j]);
+        }
+        if (c + 1 < nchunks) store(cur ^ 1);
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int b = b0 + ty * 4 + i;
+        if (b >= B) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k = k0 + tx * 4 + j;
+            if (k < Kp) dpf[(size_t)b * Kp + k] = acc[i][j];
+        }
+    }
+}

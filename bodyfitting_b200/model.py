@@ -1,0 +1,329 @@
+"""Host-side preparation of the body-model tables the kernels consume.
+
+Everything here runs once per model (numpy, fp64 where a reduction is pre-folded) and
+produces device tensors plus the ``BfModel`` struct handed to the C ABI:
+
+* ``Bm`` -- ONE blend matrix [Kp, 3 n_pad] whose rows are posedirs (P), shapedirs^T (NS) and
+  v_template (1), so that v_posed = [pose_feature | shape | 1] @ Bm is a single dense
+  contraction (smplx.lbs: blend_shapes + pose_offsets matmul + template add).
+* ``Jt`` / ``Jd`` -- J_regressor folded into the template / shape directions
+  (J_regressor @ (v_template + S beta) == Jt + Jd beta).
+* ELL skinning weights, CSR joint->vertex lists (for dA), the output-joint table
+  (chain joints, vertex picks, barycentric landmarks, yaw-dependent contour landmarks,
+  regressed extra joints) and its inverse, CSR by target, used by the atomics-free backward.
+* the *active vertex set*: the union of vertices the keypoint loss can ever touch
+  (21 picked + 51x3 static + all 79x17x3 contour candidates for SMPL-X, 11 for SMPL).
+  Gradients of the keypoint objective are exactly zero on every other vertex, so the
+  fitting loop runs blend + skinning only on this set; the full set is used for the
+  operator surface (SMPL.forward) and for the final vertices.
+
+Reference: models/smpl.py:56-83, models/utils.py:32-141, smplify/prior.py:127-174,
+smplx (un-vendored) as restated in oracle/smplx_port.py.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import constants as K
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+def load_model_data(path_or_dict, model_type=None, gender='neutral'):
+    """Accepts a dict (e.g. synthetic.make_model) or a path: a ``.npz``/``.pkl`` file, or a
+    folder laid out like the reference's ``data/`` (data/smpl/SMPL_NEUTRAL.npz ...)."""
+    if isinstance(path_or_dict, dict):
+        return path_or_dict
+    path = path_or_dict
+    if os.path.isdir(path):
+        mt = model_type or 'smpl'
+        base = os.path.basename(os.path.normpath(path))
+        folder = path if base == mt else os.path.join(path, mt)
+        cands = [os.path.join(folder, '%s_%s.%s' % (mt.upper(), g, ext))
+                 for g in (str(gender).upper(), 'NEUTRAL') for ext in ('npz', 'pkl')]
+        found = [c for c in cands if os.path.exists(c)]
+        if not found:
+            raise FileNotFoundError('no %s model file under %s (tried %s)' % (mt, path, cands))
+        path = found[0]
+    if path.endswith('.pkl'):
+        import pickle
+        with open(path, 'rb') as f:
+            d = pickle.load(f, encoding='latin1')
+        return {k: (np.asarray(v.todense()) if 'scipy.sparse' in str(type(v)) else v) for k, v in d.items()}
+    d = np.load(path, allow_pickle=True)
+    return {k: d[k] for k in d.files}
+
+
+class PreparedModel(object):
+    """numpy tables -> device tensors -> BfModel struct (kept alive by this object)."""
+
+    def __init__(self, smpl_type, data, gmm=None, J_regressor_extra=None, device='cuda', num_betas=10,
+                 num_expression=10):
+        assert smpl_type in ('smpl', 'smplx')
+        self.smpl_type = smpl_type
+        self.is_smplx = smpl_type == 'smplx'
+        self.device = torch.device(device)
+        data = load_model_data(data, smpl_type)
+        self.faces = np.asarray(data['f']).astype(np.int64)
+        vt = np.asarray(data['v_template'], dtype=np.float32)
+        V = vt.shape[0]
+        kt = np.asarray(data['kintree_table'])[0].astype(np.int64)
+        parents = kt.copy()
+        parents[0] = -1
+        J = len(parents)
+        assert all(parents[j] < j for j in range(1, J)), 'kinematic tree must be topologically sorted'
+        P = (J - 1) * 9
+        NB = num_betas
+        NS = NB + (num_expression if self.is_smplx else 0)
+        sd = np.asarray(data['shapedirs'], dtype=np.float32)[:, :, :NS]
+        assert sd.shape == (V, 3, NS), sd.shape
+        pdirs = np.asarray(data['posedirs'], dtype=np.float32)
+        PD = np.reshape(pdirs, [-1, P]).T                                   # [P, 3V]
+        Jreg = np.asarray(data['J_regressor'], dtype=np.float32)
+        W = np.asarray(data['weights'], dtype=np.float32)
+        self.V, self.J, self.P, self.NB, self.NS = V, J, P, NB, NS
+        self.Kdim = P + NS + 1
+        self.Kp = _round_up(self.Kdim, 16)
+        self.NP = 98 if self.is_smplx else 86
+        self.nbody = 63 if self.is_smplx else 69
+        self.parents = parents
+
+        depth = np.zeros(J, dtype=np.int32)
+        for j in range(1, J):
+            depth[j] = depth[parents[j]] + 1
+        child_ptr = np.zeros(J + 1, dtype=np.int32)
+        child_idx = []
+        for j in range(J):
+            ch = [c for c in range(1, J) if parents[c] == j]
+            child_idx += ch
+            child_ptr[j + 1] = len(child_idx)
+        Jt = (Jreg.astype(np.float64) @ vt.astype(np.float64)).astype(np.float32)
+        Jd = np.einsum('jv,vcl->jcl', Jreg.astype(np.float64), sd.astype(np.float64)).astype(np.float32)
+
+        pose_mean = np.zeros(3 * J, dtype=np.float32)
+        hand_l = hand_r = None
+        if self.is_smplx:
+            pose_mean[75:120] = np.asarray(data['hands_meanl'], dtype=np.float32)
+            pose_mean[120:165] = np.asarray(data['hands_meanr'], dtype=np.float32)
+            hand_l = np.asarray(data['hands_componentsl'], dtype=np.float32)[:6]
+            hand_r = np.asarray(data['hands_componentsr'], dtype=np.float32)[:6]
+
+        # ---- output joint table (pre-map list, then the reference's joint map) --------------------
+        extra_vids = np.asarray(data['extra_vids']).astype(np.int64)
+        pre = [(0, (j, 0, 0), (1.0, 0.0, 0.0)) for j in range(J)]
+        pre += [(1, (int(v), int(v), int(v)), (1.0, 0.0, 0.0)) for v in extra_vids]
+        dyn_faces = dyn_bary = None
+        xr = None
+        if self.is_smplx:
+            lf = self.faces[np.asarray(data['lmk_faces_idx']).astype(np.int64)]
+            lb = np.asarray(data['lmk_bary_coords'], dtype=np.float32)
+            pre += [(1, tuple(int(x) for x in lf[i]), tuple(float(x) for x in lb[i])) for i in range(lf.shape[0])]
+            dyn_faces = self.faces[np.asarray(data['dynamic_lmk_faces_idx']).astype(np.int64)]      # [79,17,3]
+            dyn_bary = np.asarray(data['dynamic_lmk_bary_coords'], dtype=np.float32)
+            pre += [(2, (s, 0, 0), (0.0, 0.0, 0.0)) for s in range(dyn_faces.shape[1])]
+            jmap = K.smpl_to_openpose('smplx', use_hands=True, use_face=True, use_face_contour=True,
+                                      openpose_format='coco25')
+            K_used = len(jmap)
+        else:
+            if J_regressor_extra is not None:
+                xr = np.asarray(J_regressor_extra, dtype=np.float32)
+                pre += [(3, (r, 0, 0), (0.0, 0.0, 0.0)) for r in range(xr.shape[0])]
+                jmap = np.asarray(K.SPIN_JOINT_MAP)
+            else:
+                jmap = K.smpl_to_openpose('smpl', openpose_format='coco25')
+            K_used = 25
+        self.K_used = K_used
+        self.joint_table = [pre[int(i)] for i in jmap]
+        self.K_out = len(self.joint_table)
+        self._dyn_faces, self._dyn_bary, self._xr = dyn_faces, dyn_bary, xr
+
+        # ---- GMM prior (smplify/prior.py:127-160) ------------------------------------------------
+        g = {}
+        if gmm is not None:
+            means = np.asarray(gmm['means']).astype(np.float32)
+            covs = np.asarray(gmm['covars']).astype(np.float32)
+            prec = np.stack([np.linalg.inv(c) for c in covs]).astype(np.float32)
+            sqrdets = np.array([np.sqrt(np.linalg.det(c)) for c in np.asarray(gmm['covars'])])
+            const = (2 * np.pi) ** (69 / 2.)
+            nllw = np.asarray(np.asarray(gmm['weights']) / (const * (sqrdets / sqrdets.min()))).astype(np.float32)
+            g = dict(gmm_mean=means, gmm_prec=prec, gmm_prec_t=np.ascontiguousarray(np.transpose(prec, (0, 2, 1))),
+                     gmm_logw=np.log(nllw).astype(np.float32))
+            self.n_gmm = means.shape[0]
+            assert means.shape[1] == 69
+        else:
+            self.n_gmm = 0
+
+        # ---- vertex sets -------------------------------------------------------------------------
+        Bm_rows = np.zeros((self.Kp, 3 * V), dtype=np.float32)
+        Bm_rows[:P] = PD
+        Bm_rows[P:P + NS] = sd.reshape(V * 3, NS).T
+        Bm_rows[P + NS] = vt.reshape(-1)
+        active = set()
+        for kind, src, w in self.joint_table[:K_used]:
+            if kind == 1:
+                active.update(int(s) for s, ww in zip(src, w) if ww != 0.0)
+            elif kind == 2:
+                active.update(int(x) for x in dyn_faces[:, src[0], :].reshape(-1))
+            elif kind == 3:
+                active.update(int(x) for x in np.nonzero(xr[src[0]])[0])
+        self.active_vids = np.array(sorted(active), dtype=np.int64)
+        self._host = dict(parents=parents.astype(np.int32), depth=depth, child_ptr=child_ptr,
+                          child_idx=np.array(child_idx + [0], dtype=np.int32), Jt=Jt, Jd=Jd, pose_mean=pose_mean,
+                          hand_l=hand_l, hand_r=hand_r, **g)
+        self.max_depth = int(depth.max())
+        full_h = self._build_vset(np.arange(V, dtype=np.int64), Bm_rows, W, self.joint_table)
+        act_h = self._build_vset(self.active_vids, Bm_rows, W, self.joint_table[:K_used])
+        del Bm_rows
+
+        # ---- upload ----------------------------------------------------------------------------
+        self._dev = {}
+        self.struct = _lib.BfModel()
+        for k, v in self._host.items():
+            setattr(self.struct, k, self._up('m_' + k, v))
+        self._fill_vset(self.struct.full, 'full', full_h)
+        self._fill_vset(self.struct.act, 'act', act_h)
+        for k, v in dict(J=J, P=P, NS=NS, NB=NB, Kp=self.Kp, NP=self.NP, is_smplx=int(self.is_smplx),
+                         max_depth=self.max_depth, K_used=K_used, n_gmm=self.n_gmm).items():
+            setattr(self.struct, k, v)
+        self.n_act = int(act_h['n'])
+        self.ld_act = 3 * int(act_h['n_pad'])
+        self.K_out_act = int(act_h['K_out'])
+        self._host = None
+
+    # ------------------------------------------------------------------------------------------
+    def _up(self, name, arr):
+        if arr is None:
+            return None
+        t = torch.from_numpy(np.ascontiguousarray(arr)).to(self.device)
+        self._dev[name] = t
+        return t.data_ptr()
+
+    def _fill_vset(self, vs, tag, h):
+        for k, v in h.items():
+            if isinstance(v, np.ndarray):
+                setattr(vs, k, self._up(tag + '_' + k, v))
+            else:
+                setattr(vs, k, int(v))
+
+    def _build_vset(self, vids, Bm_rows, W, table):
+        """Tables for the vertex set ``vids`` (sorted global vertex ids)."""
+        J = self.J
+        n = len(vids)
+        n_pad = _round_up(max(n, 1), 32)
+        pos = -np.ones(self.V, dtype=np.int64)
+        pos[vids] = np.arange(n)
+        cols = (3 * vids[:, None] + np.arange(3)[None]).reshape(-1)
+        Bm = np.zeros((self.Kp, 3 * n_pad), dtype=np.float32)
+        Bm[:, :3 * n] = Bm_rows[:, cols]
+        Ws = W[vids]                                                        # [n, J]
+        nnz = max(1, int((Ws != 0).sum(1).max()))
+        ell_j = np.zeros((n_pad, nnz), dtype=np.int32)
+        ell_w = np.zeros((n_pad, nnz), dtype=np.float32)
+        order = np.argsort(-(Ws != 0).astype(np.int8), axis=1, kind='stable')[:, :nnz]     # non-zeros first, joint order kept
+        ell_j[:n] = order
+        ell_w[:n] = np.take_along_axis(Ws, order, 1)
+        ell_j[:n][ell_w[:n] == 0] = 0
+        vv, jj = np.nonzero(Ws)
+        o = np.lexsort((vv, jj))
+        vv, jj = vv[o], jj[o]
+        jv_ptr = np.zeros(J + 1, dtype=np.int32)
+        np.add.at(jv_ptr, jj + 1, 1)
+        jv_ptr = np.cumsum(jv_ptr).astype(np.int32)
+        jv_vid = vv.astype(np.int32)
+        jv_w = Ws[vv, jj].astype(np.float32)
+
+        K_out = len(table)
+        kj_kind = np.zeros(K_out, dtype=np.int32)
+        kj_src = np.zeros((K_out, 3), dtype=np.int32)
+        kj_w = np.zeros((K_out, 3), dtype=np.float32)
+        entries = []                                                        # (target, k, a, w)
+        dyn_src = dyn_w = None
+        n_dyn = 0
+        if self._dyn_faces is not None:
+            n_dyn = self._dyn_faces.shape[1]
+            dyn_src = pos[self._dyn_faces].astype(np.int32)                 # [79, n_dyn, 3]
+            dyn_w = self._dyn_bary.astype(np.float32)
+        xr_ptr = xr_vid = xr_w = None
+        n_extra = 0
+        if self._xr is not None and any(kind == 3 for kind, _, _ in table):
+            n_extra = self._xr.shape[0]
+            ptr, vidl, wl = [0], [], []
+            for r in range(n_extra):
+                nzv = np.nonzero(self._xr[r])[0]
+                assert (pos[nzv] >= 0).all()
+                vidl += [int(pos[x]) for x in nzv]
+                wl += [float(self._xr[r, x]) for x in nzv]
+                ptr.append(len(vidl))
+            xr_ptr, xr_vid, xr_w = np.array(ptr, np.int32), np.array(vidl, np.int32), np.array(wl, np.float32)
+        for k, (kind, src, w) in enumerate(table):
+            kj_kind[k] = kind
+            if kind == 0:
+                kj_src[k] = (src[0], 0, 0)
+                entries.append((src[0], k, -1, 1.0))
+            elif kind == 1:
+                p = [int(pos[s]) for s in src]
+                assert min(p) >= 0, 'joint %d references a vertex outside the set' % k
+                kj_src[k] = p
+                kj_w[k] = w
+                for pi, wi in zip(p, w):
+                    if wi != 0.0:
+                        entries.append((J + pi, k, -1, float(wi)))
+            elif kind == 2:
+                s = src[0]
+                kj_src[k] = (s, 0, 0)
+                assert (dyn_src[:, s, :] >= 0).all()
+                for a in range(dyn_src.shape[0]):
+                    for i in range(3):
+                        entries.append((J + int(dyn_src[a, s, i]), k, a, float(dyn_w[a, s, i])))
+            else:
+                r = src[0]
+                kj_src[k] = (r, 0, 0)
+                for e in range(xr_ptr[r], xr_ptr[r + 1]):
+                    entries.append((J + int(xr_vid[e]), k, -1, float(xr_w[e])))
+        entries.sort(key=lambda t: (t[0], t[1], t[2]))
+        ntg = J + n
+        tg_ptr = np.zeros(ntg + 1, dtype=np.int32)
+        for t, _, _, _ in entries:
+            tg_ptr[t + 1] += 1
+        tg_ptr = np.cumsum(tg_ptr).astype(np.int32)
+        pad1 = lambda a, dt: np.array(a if len(a) else [0], dtype=dt)
+        h = dict(Bm=Bm, ell_j=ell_j, ell_w=ell_w, jv_ptr=jv_ptr, jv_vid=pad1(jv_vid, np.int32), jv_w=pad1(jv_w, np.float32),
+                 kj_kind=kj_kind, kj_src=kj_src, kj_w=kj_w, tg_ptr=tg_ptr,
+                 tg_k=pad1([e[1] for e in entries], np.int32), tg_a=pad1([e[2] for e in entries], np.int32),
+                 tg_w=pad1([e[3] for e in entries], np.float32),
+                 n=n, n_pad=n_pad, ldn=3 * n_pad, nnz=nnz, K_out=K_out, n_dyn=n_dyn, n_extra=n_extra)
+        if dyn_src is not None and any(kind == 2 for kind, _, _ in table):
+            h['dyn_src'] = np.ascontiguousarray(dyn_src)
+            h['dyn_w'] = np.ascontiguousarray(dyn_w)
+        if xr_ptr is not None:
+            h.update(xr_ptr=xr_ptr, xr_vid=xr_vid, xr_w=xr_w)
+        return h
+
+    # ------------------------------------------------------------------------------------------
+    def pack_theta(self, global_orient, body_pose, betas, transl=None, scale=None, leye=None, reye=None,
+                   lhand=None, rhand=None):
+        """Assemble [B, NP] theta rows (layout in include/bodyfit_b200.h)."""
+        B = global_orient.shape[0]
+        dev, dt = self.device, torch.float32
+        z = lambda n: torch.zeros(B, n, device=dev, dtype=dt)
+        f = lambda t, n: z(n) if t is None else t.reshape(B, n).to(device=dev, dtype=dt)
+        parts = [f(transl, 3), torch.ones(B, 1, device=dev, dtype=dt) if scale is None else f(scale, 1),
+                 f(global_orient, 3), f(body_pose, self.nbody), f(betas, 10)]
+        if self.is_smplx:
+            parts += [f(leye, 3), f(reye, 3), f(lhand, 6), f(rhand, 6)]
+        return torch.cat(parts, dim=1).contiguous()
+
+    def split_theta(self, theta):
+        nb = self.nbody
+        out = dict(transl=theta[:, 0:3], scale=theta[:, 3:4], global_orient=theta[:, 4:7],
+                   body_pose=theta[:, 7:7 + nb], betas=theta[:, 7 + nb:17 + nb])
+        if self.is_smplx:
+            o = 17 + nb
+            out.update(leye_pose=theta[:, o:o + 3], reye_pose=theta[:, o + 3:o + 6],
+                       left_hand_pose=theta[:, o + 6:o + 12], right_hand_pose=theta[:, o + 12:o + 18])
+        return out

@@ -1,0 +1,154 @@
+/*
+ * bodyfit_b200.h -- C ABI of the B200 (sm_100a) SMPLify fitting core.
+ *
+ * Every entry point is `extern "C"`, takes plain device pointers + sizes and a
+ * cudaStream_t (passed as void*), launches on that stream, never allocates and never
+ * synchronises.  Return value: 0 on success, a negative BF_E* code otherwise;
+ * bf_last_error() gives the text.  There is no CPU fallback: a device that is not
+ * compute capability 10.x is an error (BF_EARCH).
+ *
+ * Reference interfaces replaced (file:line relative to the reference repo):
+ *   bf_lbs_forward / bf_lbs_backward
+ *       models/smpl.py:69-83 SMPL.forward, smplx.SMPL/SMPLX.forward + smplx.lbs.lbs
+ *       (un-vendored, call sites models/smpl.py:71, smplify/smplify.py:179-187) and
+ *       their autograd backward.
+ *   bf_fit_step / bf_fit_run
+ *       smplify/smplify.py:177-213 (one / n iterations of the SMPLify loop:
+ *       model forward, smplify/loss.py:139-230 multiview_keypoint_loss incl.
+ *       :22-51,:132-136 projection + GMoF, smplify/prior.py:181-196 GMM prior,
+ *       loss.py:54-61 angle prior, shape L2, loss.backward(), torch.optim.Adam.step()
+ *       as configured at smplify.py:167-174).
+ *   bf_grid_* (declared in bodyfit_b200_grid.h)
+ *       thirdparty/mesh_grid/mesh_grid.cpp:129-136.
+ *
+ * All floating point data is fp32, row-major, contiguous unless a leading dimension
+ * is given.  "theta" is the per-frame optimisation vector:
+ *   [transl 3 | scale 1 | global_orient 3 | body_pose 69(smpl) or 63(smplx) | betas 10 |
+ *    (smplx only) leye 3 | reye 3 | left_hand_pca 6 | right_hand_pca 6]      NP = 86 / 98
+ */
+#ifndef BODYFIT_B200_H
+#define BODYFIT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BF_OK        0
+#define BF_EINVAL   -1   /* bad argument (null pointer, bad size)          */
+#define BF_ECUDA    -2   /* a CUDA runtime call / launch failed            */
+#define BF_EARCH    -3   /* device is not sm_100 (no fallback exists)      */
+
+#define BF_ABI_VERSION 4
+#define BF_F_WORLD 1
+
+/* A vertex set: either all V vertices of the model or the compacted "active" subset
+ * that the keypoint loss can touch.  All index tables refer to positions in this set. */
+typedef struct BfVSet {
+    const float*   Bm;        /* [Kp, ldn] blend matrix: rows 0..P-1 posedirs, P..P+NS-1 shapedirs^T, P+NS v_template, rest 0 */
+    const int32_t* ell_j;     /* [n_pad, nnz] skinning joint ids (ELL, padded with j=0,w=0) */
+    const float*   ell_w;     /* [n_pad, nnz] skinning weights */
+    const int32_t* jv_ptr;    /* [J+1] CSR by joint over (vertex, weight), for dA */
+    const int32_t* jv_vid;    /* [jv_ptr[J]] */
+    const float*   jv_w;      /* [jv_ptr[J]] */
+    const int32_t* kj_kind;   /* [K_out] 0 chain joint, 1 vertex combination, 2 dynamic landmark slot, 3 regressed extra row */
+    const int32_t* kj_src;    /* [K_out,3] chain joint id | vertex ids | slot | row */
+    const float*   kj_w;      /* [K_out,3] barycentric weights (kind 1) */
+    const int32_t* dyn_src;   /* [79,n_dyn,3] vertex ids per yaw row (or NULL) */
+    const float*   dyn_w;     /* [79,n_dyn,3] */
+    const int32_t* tg_ptr;    /* [J+n+1] CSR by target (J chain joints, then n vertices) over output joints */
+    const int32_t* tg_k;      /* output joint index */
+    const int32_t* tg_a;      /* yaw row the entry is valid for, or -1 = always */
+    const float*   tg_w;      /* weight */
+    const int32_t* xr_ptr;    /* [n_extra+1] CSR of the extra joint regressor (models/smpl.py:62-65,72) or NULL */
+    const int32_t* xr_vid;
+    const float*   xr_w;
+    int32_t n, n_pad, ldn, nnz, K_out, n_dyn, n_extra, _pad0;
+} BfVSet;
+
+typedef struct BfModel {
+    const int32_t* parents;   /* [J] */
+    const int32_t* depth;     /* [J] */
+    const int32_t* child_ptr; /* [J+1] */
+    const int32_t* child_idx; /* [J-1] */
+    const float*   Jt;        /* [J,3]     J_regressor @ v_template */
+    const float*   Jd;        /* [J,3,NS]  J_regressor @ shapedirs  */
+    const float*   pose_mean; /* [3J] */
+    const float*   hand_l;    /* [6,45] or NULL */
+    const float*   hand_r;    /* [6,45] or NULL */
+    const float*   gmm_mean;  /* [8,69] */
+    const float*   gmm_prec;  /* [8,69,69] */
+    const float*   gmm_prec_t;/* [8,69,69] transposed */
+    const float*   gmm_logw;  /* [8] log(nll_weights) */
+    BfVSet full;
+    BfVSet act;
+    int32_t J, P, NS, NB, Kp, NP, is_smplx, max_depth, K_used, n_gmm, _pad0, _pad1;
+} BfModel;
+
+/* Per-call frame buffers (all device memory, B frames). */
+typedef struct BfFrames {
+    float*       theta;      /* [B,NP] in/out */
+    float*       grad;       /* [B,NP] out */
+    float*       adam_m;     /* [B,NP] */
+    float*       adam_v;     /* [B,NP] */
+    float*       pf;         /* [B,Kp]   GEMM A operand: pose feature | shape | 1 */
+    float*       dpf;        /* [B,Kp] */
+    float*       A;          /* [B,J,12] rest-pose-removed joint transforms */
+    float*       dA;         /* [B,J,12] */
+    float*       Jtr;        /* [B,J,3]  posed joints */
+    float*       dJtr;       /* [B,J,3] */
+    float*       full_pose;  /* [B,3J] */
+    int32_t*     yaw;        /* [B] dynamic-landmark row */
+    float*       verts;      /* [B,ld_v] skinned vertices of the vertex set in use */
+    float*       vposed;     /* [B,ld_v] blended (unskinned) vertices, saved for backward */
+    float*       dverts;     /* [B,ld_v] */
+    float*       dvp;        /* [B,ld_v] */
+    float*       joints;     /* [B,K_out,3] model-space output joints (optional, may be NULL) */
+    float*       djoints;    /* [B,K_out,3] incoming joint gradient (operator backward) or NULL */
+    const float* kp;         /* [B,Nv,K_used,3] (x, y, effective weight) */
+    const float* cams;       /* [Nv,12] row-major 3x4  K @ [R|t] (world -> pixel, homogeneous) */
+    float*       loss;       /* [B] per-frame total loss of this iteration */
+    float*       loss_terms; /* [B,4] data, pose prior, angle prior, shape prior (optional) */
+    float*       trace;      /* [n_iters,B] optional per-iteration loss trace */
+    double lr_ts, lr, beta1, beta2, eps;   /* Adam hyper-parameters (python floats in the reference: smplify.py:167-174) */
+    int32_t B, Nv, ld_v, iter;
+    int32_t flags, _pad0;      /* BF_F_WORLD: skin/joints forward write (x + transl) * scale * constant_scale (smplify.py:189-190) */
+    float imsize, constant_scale, sigma, w_pose, w_angle, w_shape;
+} BfFrames;
+
+int         bf_abi_version(void);
+int         bf_sizeof(int which);                        /* 0 BfVSet, 1 BfModel, 2 BfFrames: layout check for FFI bindings */
+const char* bf_last_error(void);
+int         bf_check_device(void);                       /* BF_OK iff current device is sm_100 */
+
+/* theta -> pf, A, Jtr, full_pose, yaw */
+int bf_pose_forward(const BfModel* m, const BfFrames* f, void* stream);
+/* blend shapes + skinning over a vertex set (use_full != 0: all vertices) -> verts, vposed */
+int bf_skin_forward(const BfModel* m, const BfFrames* f, int use_full, void* stream);
+/* model-space output joints [B,K_out,3] from Jtr / verts */
+int bf_joints_forward(const BfModel* m, const BfFrames* f, int use_full, void* stream);
+/* joints gradient + optional dense dverts -> dJtr, dverts (gather by target) */
+int bf_joints_backward(const BfModel* m, const BfFrames* f, int use_full, int accumulate_dverts, void* stream);
+/* keypoint data term: loss, d/d(theta[0:4]), dJtr, dverts */
+int bf_keypoint_loss(const BfModel* m, const BfFrames* f, int use_full, void* stream);
+/* dverts -> dvp, dA, dpf */
+int bf_skin_backward(const BfModel* m, const BfFrames* f, int use_full, void* stream);
+/* dA, dJtr, dpf -> grad (theta[4:]); flags: 1 = add priors (value + grad), 2 = Adam step, 4 = keep grad[0:4] from loss kernel */
+int bf_pose_backward(const BfModel* m, const BfFrames* f, int flags, void* stream);
+
+/* LBS operator: pose_forward + skin_forward(full) + joints_forward */
+int bf_lbs_forward(const BfModel* m, const BfFrames* f, void* stream);
+/* LBS operator backward: (dverts, djoints) -> grad wrt theta */
+int bf_lbs_backward(const BfModel* m, const BfFrames* f, void* stream);
+/* one SMPLify iteration on the active vertex set; f->iter is the 0-based iteration */
+int bf_fit_step(const BfModel* m, const BfFrames* f, void* stream);
+/* n iterations starting at f->iter; if dense_last != 0 the last iteration's forward also
+ * materialises all vertices into f_full->verts (the reference returns the vertices of the
+ * last forward pass, smplify/smplify.py:217) */
+int bf_fit_run(const BfModel* m, const BfFrames* f, int n_iters, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

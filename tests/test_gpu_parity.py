@@ -1,0 +1,155 @@
+"""GPU parity tests: every stage of the CUDA path against the CPU oracle
+(oracle/fit_port.py + oracle/smplx_port.py), through the C ABI.
+
+Tolerances (BASELINE.json north_star): vertices / joints <= 1e-5 relative, per-iteration loss
+<= 1e-4 relative, final pose / betas <= 2e-3 absolute after 100 Adam iterations
+(Adam normalises gradients, so fp32 rounding differences are amplified along the trajectory;
+the fp64 oracle is used to show the CUDA path is as close to fp64 as the fp32 oracle is).
+"""
+import numpy as np
+import pytest
+import torch
+
+from util import make_port, make_scene, perturbed_params, relerr
+
+pytestmark = pytest.mark.gpu
+
+
+def _prep(assets, mt):
+    from bodyfitting_b200.model import PreparedModel
+    return PreparedModel(mt, assets(mt), gmm=assets('gmm'), J_regressor_extra=assets('jx'), device='cuda')
+
+
+def _theta(pm, p):
+    T = lambda k: None if k not in p else torch.as_tensor(p[k])
+    return pm.pack_theta(T('global_orient'), T('body_pose'), T('betas'), transl=T('global_transl'),
+                         scale=T('body_scale'), leye=T('leye_pose'), reye=T('reye_pose'),
+                         lhand=T('left_hand_pose'), rhand=T('right_hand_pose'))
+
+
+@pytest.mark.parametrize('mt', ['smpl', 'smplx'])
+def test_lbs_forward(assets, mt):
+    from bodyfitting_b200.engine import FrameBuffers
+    B = 70
+    port = make_port(assets, mt)
+    pm = _prep(assets, mt)
+    p = perturbed_params(mt, B, seed=3)
+    nv = 2
+    c2ws, Ks = __import__('bodyfitting_b200.synthetic', fromlist=['x']).make_cameras(nv)
+    K = pm.K_used
+    ev = port.loss_and_grads(p, c2ws, Ks, np.zeros((B, nv, K, 3), np.float32))
+    fb = FrameBuffers(pm, B, full=True, need_backward=False)
+    fb.t['theta'].copy_(_theta(pm, p))
+    fb.call('bf_lbs_forward')
+    torch.cuda.synchronize()
+    verts = fb.t['verts'].view(B, -1, 3).cpu().numpy()
+    joints = fb.t['joints'].cpu().numpy()
+    print(mt, 'verts rel', relerr(verts, ev['model_vertices']), 'joints rel', relerr(joints, ev['model_joints']),
+          'full_pose', relerr(fb.t['full_pose'].cpu().numpy(), ev['full_pose']))
+    assert relerr(verts, ev['model_vertices']) < 1e-5
+    assert relerr(joints, ev['model_joints']) < 1e-5
+    assert relerr(fb.t['full_pose'].cpu().numpy(), ev['full_pose']) < 1e-6
+
+
+@pytest.mark.parametrize('mt,nv', [('smpl', 4), ('smplx', 8)])
+def test_loss_and_gradients(assets, mt, nv):
+    """One evaluation of the objective on the active vertex set: per-frame loss, the four loss
+    terms and d loss / d theta against autograd of the oracle (fp32 and fp64)."""
+    from bodyfitting_b200.engine import FrameBuffers, pack_cameras, pack_keypoints
+    B = 33
+    port = make_port(assets, mt)
+    port64 = make_port(assets, mt, dtype=torch.float64)
+    pm = _prep(assets, mt)
+    sc = make_scene(port, mt, B, nv, seed=1)
+    p = perturbed_params(mt, B, seed=5)
+    ev = port.loss_and_grads(p, sc['c2ws'], sc['Ks'], sc['kp'])
+    ev64 = port64.loss_and_grads(p, sc['c2ws'], sc['Ks'], sc['kp'])
+    fb = FrameBuffers(pm, B, full=False, Nv=nv)
+    fb.t['theta'].copy_(_theta(pm, p))
+    fb.bind('kp', pack_keypoints(torch.as_tensor(sc['kp']).cuda(), mt == 'smplx'))
+    fb.bind('cams', torch.from_numpy(pack_cameras(sc['c2ws'], sc['Ks'])).cuda())
+    for fn, extra in (('bf_pose_forward', ()), ('bf_skin_forward', (0,)), ('bf_keypoint_loss', (0,)),
+                      ('bf_skin_backward', (0,)), ('bf_pose_backward', (1 | 4,))):
+        fb.call(fn, *extra)
+    torch.cuda.synchronize()
+    loss = fb.t['loss'].cpu().numpy()
+    terms = fb.t['loss_terms'].cpu().numpy()
+    print(mt, 'loss rel vs fp32 oracle', relerr(loss, ev['loss']), 'vs fp64', relerr(loss, ev64['loss']),
+          '(fp32 oracle vs fp64', relerr(ev['loss'], ev64['loss']), ')')
+    for i, k in enumerate(('reprojection_loss', 'pose_prior_loss', 'angle_prior_loss', 'shape_prior_loss')):
+        print('   term', k, relerr(terms[:, i], ev['terms'][k]))
+        assert relerr(terms[:, i], ev64['terms'][k]) < 1e-4
+    assert relerr(loss, ev64['loss']) < 1e-4
+    g = pm.split_theta(fb.t['grad']).items()
+    names = dict(transl='global_transl', scale='body_scale')
+    worst = 0.0
+    for k, gv in g:
+        ok = names.get(k, k)
+        ref64 = ev64['grads'][ok].reshape(B, -1)
+        ref32 = ev['grads'][ok].reshape(B, -1)
+        e = relerr(gv.cpu().numpy(), ref64)
+        e32 = relerr(ref32, ref64)
+        print('   grad %-16s cuda-vs-fp64 %.2e   fp32oracle-vs-fp64 %.2e   |g|max %.3e' % (k, e, e32, np.abs(ref64).max()))
+        worst = max(worst, e)
+        assert e < max(2e-4, 20 * e32), k
+    print('worst grad rel err', worst)
+
+
+@pytest.mark.parametrize('mt', ['smpl', 'smplx'])
+def test_lbs_backward_operator(assets, mt):
+    """Dense operator backward: random d(vertices), d(joints) -> d theta vs autograd of the oracle."""
+    from bodyfitting_b200.engine import FrameBuffers
+    B = 9
+    port = make_port(assets, mt, dtype=torch.float64)
+    pm = _prep(assets, mt)
+    p = perturbed_params(mt, B, seed=7)
+    rng = np.random.RandomState(0)
+    dV = rng.standard_normal((B, pm.V, 3)).astype(np.float32)
+    dJ = rng.standard_normal((B, pm.K_out, 3)).astype(np.float32)
+    pt = {k: torch.tensor(v, dtype=torch.float64, requires_grad=True) for k, v in p.items()
+          if k not in ('global_transl', 'body_scale')}
+    z = lambda *s: torch.zeros(*s, dtype=torch.float64)
+    full = dict(jaw_pose=z(B, 1, 3), leye_pose=z(B, 1, 3), reye_pose=z(B, 1, 3), left_hand_pose=z(B, 6), right_hand_pose=z(B, 6))
+    for k in list(full):
+        if k in pt:
+            full[k] = pt[k].reshape(full[k].shape)
+    full.update(global_orient=pt['global_orient'], body_pose=pt['body_pose'], betas=pt['betas'])
+    out = port.forward_model(full)
+    (out.vertices * torch.tensor(dV, dtype=torch.float64)).sum().add((out.joints * torch.tensor(dJ, dtype=torch.float64)).sum()).backward()
+    fb = FrameBuffers(pm, B, full=True)
+    fb.t['theta'].copy_(_theta(pm, {k: v for k, v in p.items() if k not in ('global_transl', 'body_scale')}))
+    fb.call('bf_lbs_forward')
+    fb.t['dverts'].copy_(torch.from_numpy(dV).view(B, -1))
+    fb.bind('djoints', torch.from_numpy(dJ).cuda().contiguous())
+    fb.call('bf_lbs_backward')
+    torch.cuda.synchronize()
+    g = pm.split_theta(fb.t['grad'])
+    for k in ('global_orient', 'body_pose', 'betas') + (('leye_pose', 'reye_pose', 'left_hand_pose', 'right_hand_pose') if mt == 'smplx' else ()):
+        e = relerr(g[k].cpu().numpy(), pt[k].grad.reshape(B, -1).numpy())
+        print(mt, 'operator grad', k, e)
+        assert e < 1e-4, k
+
+
+@pytest.mark.parametrize('mt,nv,B', [('smpl', 4, 6), ('smplx', 8, 4)])
+def test_fit_trajectory(assets, mt, nv, B):
+    """100 iterations through the drop-in SMPLify class vs the batched oracle loop."""
+    from bodyfitting_b200.smplify.smplify import SMPLify
+    port = make_port(assets, mt)
+    sc = make_scene(port, mt, B, nv, seed=2)
+    N = 100
+    ref, trace = port.fit_batched(sc['init_betas'], sc['init_pose'], sc['c2ws'], sc['Ks'], sc['kp'], num_iters=N)
+    fit = SMPLify(smpl_type=mt, num_iters=N, gender='neutral', model_data=assets(mt), gmm=assets('gmm'),
+                  J_regressor_extra=assets('jx'))
+    out = fit((sc['init_betas'], sc['init_pose']), list(sc['c2ws']), list(sc['Ks']), sc['kp'], None,
+              use_frames=list(range(nv)), imsize=512)
+    tr = fit.last_trace.cpu().numpy()
+    rel = np.abs(tr - trace) / np.abs(trace)
+    print(mt, 'loss trace max rel err', rel.max(), 'at iter', np.unravel_index(rel.argmax(), rel.shape))
+    print('   first/last loss', trace[0], trace[-1])
+    for k in ('pose', 'betas', 'global_orient', 'global_transl', 'scale', 'joints', 'vertices', 'full_pose'):
+        print('   %-14s max abs diff %.3e' % (k, np.abs(np.asarray(out[k]).reshape(B, -1) - np.asarray(ref[k]).reshape(B, -1)).max()))
+    assert rel.max() < 1e-4
+    for k in ('pose', 'betas', 'global_orient', 'global_transl', 'scale'):
+        assert np.abs(np.asarray(out[k]).reshape(B, -1) - np.asarray(ref[k]).reshape(B, -1)).max() < 2e-3, k
+    assert relerr(out['vertices'], ref['vertices']) < 1e-3
+    assert relerr(out['joints'], ref['joints']) < 1e-3
