@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""Headline benchmark: fitted frames/s (SMPL-X, 8 views, 100 iters), BASELINE.json's metric.
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun, one rank per GPU)
+  python bench.py --impl reference --steps K --warmup W    (CPU port of the reference path, rank 0 only)
+
+One *step* = one complete 100-iteration multi-view SMPLify fit of a batch of synthetic frames
+(``--frames`` per GPU, default 10,000 = BASELINE config 3; frames are independent, so ranks get
+disjoint frame ranges and no collective runs during the fit: weak scaling).
+
+  value : frames/s with inputs (keypoints, cameras, initial parameters) resident in HBM;
+          timed with CUDA events on the launching stream, max over ranks.
+  e2e   : the same through the reference-facing API ``SMPLify.__call__`` with HOST numpy
+          inputs and HOST numpy outputs (vertices included) -- pinned H2D/D2H inside the
+          timed region.
+  roofline / kernels : per-kernel CUDA-event durations of one iteration and the algorithmic
+          bytes of each kernel (DESIGN.md "Kernels"), for the dominant kernel of the step.
+  lbs_dense : all-vertex LBS operator forward / backward (BASELINE config 2) against the HBM roofline.
+  cpu_baseline : the oracle's single-frame restatement of the reference loop (oracle/fit_port.py,
+          validated bit-for-bit against the verbatim reference in the authoring container) on the
+          box's host cores, 3 frames.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+
+METRIC = 'fitted frames/s (SMPL-X, 8 views, 100 iters)'
+MT, NV, ITERS = 'smplx', 8, 100
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--frames', type=int, default=10000, help='frames per GPU')
+    ap.add_argument('--iters', type=int, default=ITERS)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-dense', action='store_true')
+    ap.add_argument('--cpu-frames', type=int, default=3)
+    return ap.parse_args()
+
+
+def peaks():
+    fn = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(fn):
+        with open(fn) as f:
+            d = json.load(f)
+        return float(d['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.idx), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, col in (('hw_slowdown', 5), ('hw_thermal_slowdown', 6), ('sw_thermal_slowdown', 7), ('sw_power_cap', 8)):
+                if len(r) > col and r[col].lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+def cpu_reference_fit(n_frames, iters, warm=1):
+    """Reference-style single-frame fits on the host cores (oracle port). Returns s/frame list."""
+    import torch
+    from bodyfitting_b200 import synthetic as syn
+    from oracle import fit_port as fp
+    from util import make_scene
+    model, gmm = syn.make_model(MT, 0), syn.make_gmm(0)
+    port = fp.FitPort(MT, model, gmm)
+    sc = make_scene(port, MT, n_frames + warm, NV, seed=11)
+    times = []
+    for f in range(n_frames + warm):
+        views = syn.keypoints_to_openpose(sc['kp'][f], MT)
+        t0 = time.perf_counter()
+        port.fit_frame(sc['init_betas'][f], sc['init_pose'][f], sc['c2ws'], sc['Ks'], views, num_iters=iters)
+        dt = time.perf_counter() - t0
+        if f >= warm:
+            times.append(dt)
+    return times, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    times, cores = cpu_reference_fit(args.steps, args.iters, warm=args.warmup)
+    fps = len(times) / sum(times)
+    line = {'impl': 'reference', 'metric': METRIC, 'value': fps, 'unit': 'frames/s', 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * sum(times) / len(times),
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'fp32', 'data': 'synthetic',
+            'config': {'workload': 'SMPL-X (10475 verts, 55 joints) 8-view 135-keypoint fit, %d Adam iterations, '
+                                   '1 frame per step (the reference fits one frame per call)' % args.iters},
+            'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
+                             'sample': '%d single-frame fits after %d warm-up, torch CPU fp32, oracle/fit_port.py '
+                                       'FitPort.fit_frame (bit-exact restatement of smplify/smplify.py:84-226)' % (args.steps, args.warmup)},
+            'e2e': {'value': fps, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+def build_workload(pm, F, seed):
+    """Synthetic scene for F frames: GT joints from the CUDA forward, 2-D detections on the host."""
+    import torch
+    from bodyfitting_b200 import synthetic as syn, _lib
+    from bodyfitting_b200.engine import FrameBuffers
+    c2ws, Ks = syn.make_cameras(NV, seed=0)
+    gt, init = syn.make_params(MT, F, seed=seed)
+    T = lambda a: torch.from_numpy(a)
+    theta_gt = pm.pack_theta(T(gt['global_orient']), T(gt['body_pose']), T(gt['betas']), transl=T(gt['transl']),
+                             scale=T(gt['scale']), leye=T(gt['leye_pose']), reye=T(gt['reye_pose']),
+                             lhand=T(gt['left_hand_pose']), rhand=T(gt['right_hand_pose']))
+    joints = torch.empty(F, pm.K_out, 3, device='cuda')
+    chunk = 2048
+    for lo in range(0, F, chunk):
+        hi = min(F, lo + chunk)
+        fb = FrameBuffers(pm, hi - lo, full=True, need_backward=False,
+                          ext=dict(theta=theta_gt[lo:hi].contiguous(), joints=joints[lo:hi]))
+        fb.struct.flags = _lib.F_WORLD
+        fb.call('bf_lbs_forward')
+    torch.cuda.synchronize()
+    kp = syn.make_keypoints(joints.cpu().numpy(), c2ws, Ks, seed=seed)
+    init_pose = np.concatenate([init['global_orient'], init['body_pose'], np.zeros((F, 6), np.float32)], 1)
+    return dict(c2ws=c2ws, Ks=Ks, kp=kp, init_pose=init_pose.astype(np.float32), init_betas=init['betas'])
+
+
+def time_events(fn, reps):
+    import torch
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+    ev[0].record()
+    for i in range(reps):
+        fn()
+        ev[i + 1].record()
+    torch.cuda.synchronize()
+    return [ev[i].elapsed_time(ev[i + 1]) for i in range(reps)]
+
+
+def kernel_breakdown(pm, sess, F, hbm_peak):
+    """Per-kernel durations of ONE fit iteration (CUDA events, mean of 20) + algorithmic bytes."""
+    fb = sess.fb
+    m = pm
+    nS3 = 3 * m.n_act
+    J, Kp, NP, K, Nv = m.J, m.Kp, m.NP, m.K_used, sess.Nv
+    bm_act = 4 * Kp * m.ld_act
+    per_frame = {   # algorithmic bytes per frame (fp32), see DESIGN.md "Kernels"
+        'k_pose_fwd': 4 * (NP + Kp + J * 12 + J * 3 + 3 * J + 1),
+        'k_skin_fwd': 4 * (Kp + J * 12 + 2 * nS3),
+        'k_keypoint_loss': 4 * (Nv * K * 3 + nS3 + J * 3 + 4 + nS3 + J * 3 + 4 + 1),
+        'k_skin_bwd_dvp': 4 * (nS3 + J * 12 + nS3),
+        'k_skin_bwd_dA': 4 * (2 * nS3 + J * 12),
+        'k_blend_bwd': 4 * (nS3 + Kp),
+        'k_pose_bwd': 4 * (NP * 7 + J * 12 + J * 3 + Kp + 2),
+    }
+    once = {'k_skin_fwd': bm_act, 'k_blend_bwd': bm_act}
+    calls = [('k_pose_fwd', lambda: fb.call('bf_pose_forward')),
+             ('k_skin_fwd', lambda: fb.call('bf_skin_forward', 0)),
+             ('k_keypoint_loss', lambda: fb.call('bf_keypoint_loss', 0)),
+             ('k_skin_bwd_dvp', lambda: fb.call('bf_skin_backward_parts', 0, 1)),
+             ('k_skin_bwd_dA', lambda: fb.call('bf_skin_backward_parts', 0, 2)),
+             ('k_blend_bwd', lambda: fb.call('bf_skin_backward_parts', 0, 4)),
+             ('k_pose_bwd', lambda: fb.call('bf_pose_backward', 1 | 4))]      # no Adam: parameters stay put
+    out = []
+    for name, fn in calls:
+        fn()
+    for name, fn in calls:
+        ms = float(np.mean(time_events(fn, 20)))
+        by = per_frame[name] * F + once.get(name, 0)
+        out.append({'kernel': name, 'ms': ms, 'bytes': by, 'gbs': by / ms / 1e6, 'frac_hbm': by / ms / 1e6 / hbm_peak})
+    return out
+
+
+def dense_lbs_bench(assets_seed, hbm_peak):
+    """BASELINE config 2: SMPL, 1024 frames, all 6890 vertices: LBS forward / backward operator."""
+    import torch
+    from bodyfitting_b200 import synthetic as syn
+    from bodyfitting_b200.engine import FrameBuffers
+    from bodyfitting_b200.model import PreparedModel
+    B = 1024
+    pm = PreparedModel('smpl', syn.make_model('smpl', assets_seed), gmm=syn.make_gmm(assets_seed),
+                       J_regressor_extra=syn.make_J_regressor_extra(seed=assets_seed), device='cuda')
+    gt, _ = syn.make_params('smpl', B, seed=5)
+    T = lambda a: torch.from_numpy(a)
+    fb = FrameBuffers(pm, B, full=True)
+    fb.t['theta'].copy_(pm.pack_theta(T(gt['global_orient']), T(gt['body_pose']), T(gt['betas'])))
+    fb.bind('djoints', torch.randn(B, pm.K_out, 3, device='cuda'))
+    fb.t['dverts'].normal_()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
+
+    def timed(fn, reps=10):
+        ts = []
+        for _ in range(reps):
+            flush.zero_()                                  # evict L2 (126 MB) between timed launches
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(); fn(); e.record(); torch.cuda.synchronize()
+            ts.append(s.elapsed_time(e))
+        return float(np.mean(ts))
+    fb.call('bf_lbs_forward'); fb.call('bf_lbs_backward')
+    V, J, Kout = pm.V, pm.J, pm.K_out
+    alg = 4 * (3 * V + 3 * Kout + 72 + 10 + 4) * B            # 83,612 B per frame
+    fwd = timed(lambda: fb.call('bf_lbs_forward'))
+    bwd = timed(lambda: fb.call('bf_lbs_backward'))
+    return {'config': 'SMPL 6890 verts, 1024 frames (BASELINE config 2), L2 flushed between launches',
+            'alg_bytes_per_frame': alg // B, 'design': 'v_posed and dv_posed are materialised (+12V B written and read each way); '
+            'achieved uses the minimal algorithmic bytes of SURVEY.md 8d',
+            'fwd_ms': fwd, 'bwd_ms': bwd, 'fwd_gbs': alg / fwd / 1e6, 'bwd_gbs': alg / bwd / 1e6,
+            'fwd_frac_hbm': alg / fwd / 1e6 / hbm_peak, 'bwd_frac_hbm': alg / bwd / 1e6 / hbm_peak}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from bodyfitting_b200 import synthetic as syn
+    from bodyfitting_b200.engine import pack_cameras, pack_keypoints
+    from bodyfitting_b200.model import PreparedModel
+    from bodyfitting_b200.smplify.smplify import SMPLify
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    F, N = args.frames, args.iters
+    hbm_peak, peak_src = peaks()
+
+    fit = SMPLify(smpl_type=MT, num_iters=N, gender='neutral', model_data=syn.make_model(MT, 0), gmm=syn.make_gmm(0))
+    pm = fit.model
+    wl = build_workload(pm, F, seed=100 + rank)            # rank r owns frames [r*F, (r+1)*F)
+    sess = fit.session(F, NV, 512, True)
+    kp_dev = pack_keypoints(torch.from_numpy(wl['kp']).cuda(), True)
+    cams = torch.from_numpy(pack_cameras(wl['c2ws'], wl['Ks'])).cuda()
+    sess.set_inputs(kp_dev, cams)
+    poses = torch.from_numpy(wl['init_pose']).cuda()
+    theta0 = pm.pack_theta(poses[:, :3], poses[:, 3:3 + pm.nbody], torch.from_numpy(wl['init_betas']).cuda())
+    gathered = torch.empty(world * F, pm.NP, device='cuda') if world > 1 else None
+
+    def step_device():
+        theta = sess.run(theta0)
+        if world > 1:                                       # final gather of the fitted parameters
+            dist.all_gather_into_tensor(gathered, theta)
+
+    host_args = ((wl['init_betas'], wl['init_pose']), list(wl['c2ws']), list(wl['Ks']), wl['kp'], None)
+
+    def step_e2e():
+        out = fit(*host_args, use_frames=list(range(NV)), imsize=512)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, sess.fb.t['theta'])
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_region(fn, K, W):
+        for _ in range(W):
+            fn()
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        s.record()
+        for _ in range(K):
+            fn()
+        e.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = s.elapsed_time(e)
+        if world > 1:
+            t = torch.tensor([ms, wall * 1e3], device='cuda', dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms, wall = float(t[0]), float(t[1]) / 1e3
+        return ms, wall
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms_dev, wall_dev = timed_region(step_device, args.steps, max(args.warmup, 3))
+    clocks = sampler.stop()
+    launches = sess.kernel_launches * args.steps
+    ms_e2e, wall_e2e = timed_region(step_e2e, args.steps, max(1, min(args.warmup, 3)))
+    h2d, d2h = fit.h2d_bytes, fit.d2h_bytes
+
+    total_frames = world * F * args.steps
+    value = total_frames / (ms_dev / 1e3)
+    e2e = total_frames / (max(ms_e2e / 1e3, wall_e2e))
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    kern = kernel_breakdown(pm, sess, F, hbm_peak)
+    dom = max(kern, key=lambda k: k['ms'])
+    iter_ms = sum(k['ms'] for k in kern)
+    line = {
+        'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
+        'warmup': max(args.warmup, 3), 'ms_per_step': ms_dev / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'fp32', 'data': 'synthetic',
+        'config': {'workload': 'SMPL-X (10475 verts, 55 joints, random-init tensors) 8-view fit of %d frames per GPU, '
+                               '135 OpenPose-layout keypoints per view, %d Adam iterations (BASELINE config 3)' % (F, N),
+                   'frames_per_gpu': F, 'views': NV, 'iters': N, 'active_vertices': int(pm.n_act),
+                   'design': 'fit loop runs blend+skinning on the %d vertices the keypoint loss can touch (exact: all other '
+                             'vertex gradients are zero); all 10475 vertices are produced once for the returned mesh' % pm.n_act,
+                   'l2': 'inputs larger than L2: %.0f MB of keypoints + %.0f MB of per-frame state per step, no flush'
+                         % (kp_dev.numel() * 4 / 1e6, F * (2 * pm.Kp + 4 * pm.ld_act + 24 * pm.J + 4 * pm.NP) * 4 / 1e6),
+                   'parallelism': 'frames sharded, %d rank(s), no collective during the fit; final all_gather of parameters' % world},
+        'clocks': clocks,
+        'e2e': {'value': e2e, 'unit': 'frames/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
+                'ms_per_step': 1e3 * max(ms_e2e / 1e3, wall_e2e) / args.steps,
+                'api': 'bodyfitting_b200.smplify.smplify.SMPLify.__call__ (numpy in, numpy out incl. vertices)'},
+        'gpu_launches': int(launches),
+        'roofline': {'bound': 'hbm', 'kernel': dom['kernel'], 'achieved': dom['gbs'], 'peak': hbm_peak, 'unit': 'GB/s',
+                     'frac': dom['frac_hbm'], 'traffic': None, 'peak_source': peak_src,
+                     'share_of_iteration': dom['ms'] / iter_ms},
+        'kernels': kern, 'iter_ms_sum_of_kernels': iter_ms,
+    }
+    if not args.no_dense:
+        try:
+            line['lbs_dense'] = dense_lbs_bench(0, hbm_peak)
+        except Exception as ex:                              # report, never hide
+            line['lbs_dense'] = {'error': repr(ex)}
+    if world > 1:
+        dist.destroy_process_group()
+    if not args.no_cpu_baseline:
+        times, cores = cpu_reference_fit(args.cpu_frames, N, warm=1)
+        line['cpu_baseline'] = {'value': len(times) / sum(times), 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
+                                'sample': '%d single-frame SMPL-X 8-view %d-iteration fits after 1 warm-up (oracle/fit_port.py '
+                                          'FitPort.fit_frame, torch CPU fp32, %d host cpus)' % (len(times), N, os.cpu_count())}
+    print(json.dumps(line))
+
+
+if __name__ == '__main__':
+    a = parse()
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -71,7 +71,7 @@ def lib():
             raise BodyfitError('struct layout mismatch for %s: C %d, ctypes %d' % (st.__name__, L.bf_sizeof(i), C.sizeof(st)))
     pm, pf, vp, ci = C.POINTER(BfModel), C.POINTER(BfFrames), C.c_void_p, C.c_int
     for name, extra in (('bf_pose_forward', []), ('bf_skin_forward', [ci]), ('bf_joints_forward', [ci]),
-                        ('bf_joints_backward', [ci, ci]), ('bf_keypoint_loss', [ci]), ('bf_skin_backward', [ci]),
+                        ('bf_joints_backward', [ci, ci]), ('bf_keypoint_loss', [ci]), ('bf_skin_backward', [ci]), ('bf_skin_backward_parts', [ci, ci]),
                         ('bf_pose_backward', [ci]), ('bf_lbs_forward', []), ('bf_lbs_backward', []),
                         ('bf_fit_step', []), ('bf_fit_run', [ci])):
         fn = getattr(L, name)
@@ -82,7 +82,7 @@ def lib():
 
 
 EXPORTED = ['bf_abi_version', 'bf_sizeof', 'bf_last_error', 'bf_check_device', 'bf_pose_forward', 'bf_skin_forward',
-            'bf_joints_forward', 'bf_joints_backward', 'bf_keypoint_loss', 'bf_skin_backward',
+            'bf_joints_forward', 'bf_joints_backward', 'bf_keypoint_loss', 'bf_skin_backward', 'bf_skin_backward_parts',
             'bf_pose_backward', 'bf_lbs_forward', 'bf_lbs_backward', 'bf_fit_step', 'bf_fit_run']
 
 

@@ -118,26 +118,33 @@ int bf_keypoint_loss(const BfModel* m, const BfFrames* f, int use_full, void* st
     return BF_OK;
 }
 
-int bf_skin_backward(const BfModel* m, const BfFrames* f, int use_full, void* stream) {
+// parts: bit0 dvp, bit1 dA, bit2 blend backward GEMM (bf_skin_backward = all three)
+int bf_skin_backward_parts(const BfModel* m, const BfFrames* f, int use_full, int parts, void* stream) {
     int rc = check_model(m, f); if (rc) return rc;
     const BfVSet* vs = use_full ? &m->full : &m->act;
     rc = check_vset(vs, f); if (rc) return rc;
     BF_REQUIRE(f->dverts && f->dvp && f->vposed && f->dA && f->dpf && f->A, "backward buffers missing");
     BF_REQUIRE(vs->jv_ptr && vs->jv_vid && vs->jv_w, "joint->vertex lists missing");
     cudaStream_t s = (cudaStream_t)stream;
-    {
+    if (parts & 1) {
         const dim3 grid((vs->n + 255) / 256, (f->B + DV_FB - 1) / DV_FB);
         k_skin_bwd_dvp<<<grid, 256, 0, s>>>(*vs, m->J, f->A, f->dverts, f->dvp, f->B, f->ld_v);
         BF_LAUNCH_CHECK();
     }
-    k_skin_bwd_dA<<<f->B, 256, 0, s>>>(*vs, m->J, f->dverts, f->vposed, f->dA, f->B, f->ld_v);
-    BF_LAUNCH_CHECK();
-    {
+    if (parts & 2) {
+        k_skin_bwd_dA<<<f->B, 256, 0, s>>>(*vs, m->J, f->dverts, f->vposed, f->dA, f->B, f->ld_v);
+        BF_LAUNCH_CHECK();
+    }
+    if (parts & 4) {
         const dim3 grid((m->Kp + GB_T - 1) / GB_T, (f->B + GB_T - 1) / GB_T);
         k_blend_bwd<<<grid, 256, 0, s>>>(*vs, m->Kp, f->dvp, f->dpf, f->B, f->ld_v);
         BF_LAUNCH_CHECK();
     }
     return BF_OK;
+}
+
+int bf_skin_backward(const BfModel* m, const BfFrames* f, int use_full, void* stream) {
+    return bf_skin_backward_parts(m, f, use_full, 7, stream);
 }
 
 int bf_pose_backward(const BfModel* m, const BfFrames* f, int flags, void* stream) {

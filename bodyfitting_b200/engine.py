@@ -108,3 +108,95 @@ def pack_keypoints(kp, use_hand_face):
             w[..., lo:hi] = c2[..., lo:hi].sum(-1, keepdim=True)
     out[..., 2] = w
     return out.contiguous()
+
+
+class FitSession(object):
+    """All device state of a B-frame fit, allocated once and reusable across calls
+    (smplify/smplify.py:84-226 for B frames in flight).
+
+    ``run(theta0)`` = N iterations on the active vertex set; the reference returns the
+    vertices / joints / full_pose of the LAST forward pass (parameters before the final
+    Adam step) next to the parameters after it (smplify.py:216-226), so the all-vertex
+    forward runs once, between iteration N-1 and N, writing world-space outputs directly.
+    """
+
+    def __init__(self, model: PreparedModel, B, Nv, num_iters, imsize=512, return_vertices=True,
+                 chunk=4096, trace=True, dense_every_iter=False):
+        self.model, self.B, self.Nv, self.N = model, int(B), int(Nv), int(num_iters)
+        assert self.N >= 1
+        dev = model.device
+        self.fb = FrameBuffers(model, B, full=False, Nv=Nv, n_trace=(self.N if trace else 0), imsize=imsize)
+        self.theta_prev = torch.empty(B, model.NP, device=dev)
+        self.verts = torch.empty(B, model.V, 3, device=dev) if return_vertices else None
+        self.joints = torch.empty(B, model.K_out, 3, device=dev)
+        self.full_pose = torch.empty(B, 3 * model.J, device=dev)
+        self.dense_every_iter = bool(dense_every_iter)
+        c = min(int(chunk), self.B)
+        scratch = dict(pf=torch.empty(c, model.Kp, device=dev), A=torch.empty(c, model.J, 12, device=dev),
+                       Jtr=torch.empty(c, model.J, 3, device=dev), yaw=torch.zeros(c, dtype=torch.int32, device=dev),
+                       loss=torch.zeros(c, device=dev))
+        if not return_vertices:
+            scratch['verts'] = torch.empty(c, 3 * model.V, device=dev)
+        self.chunks = []
+        for lo in range(0, self.B, c):
+            hi = min(self.B, lo + c)
+            ext = {k: v[:hi - lo] for k, v in scratch.items()}
+            ext.update(theta=self.theta_prev[lo:hi], joints=self.joints[lo:hi], full_pose=self.full_pose[lo:hi])
+            if return_vertices:
+                ext['verts'] = self.verts[lo:hi].view(hi - lo, -1)
+            fbf = FrameBuffers(model, hi - lo, full=True, need_backward=False, ext=ext)
+            fbf.struct.flags = _lib.F_WORLD
+            self.chunks.append(fbf)
+        self.kernel_launches = 0
+
+    def set_inputs(self, kp_packed, cams):
+        """kp_packed [B,Nv,K_used,3] (x, y, effective weight) and cams [Nv,12], device tensors."""
+        assert kp_packed.shape == (self.B, self.Nv, self.model.K_used, 3) and kp_packed.is_contiguous()
+        self.fb.bind('kp', kp_packed)
+        self.fb.bind('cams', cams)
+
+    def _dense_forward(self):
+        for fbf in self.chunks:
+            fbf.call('bf_lbs_forward')
+        return 3 * len(self.chunks)
+
+    def run(self, theta0):
+        fb, N = self.fb, self.N
+        fb.t['theta'].copy_(theta0)
+        fb.t['adam_m'].zero_()
+        fb.t['adam_v'].zero_()
+        launches = 0
+        if self.dense_every_iter:
+            # materialise all V vertices in every iteration, as the reference's model call does
+            for it in range(N - 1):
+                self.theta_prev.copy_(fb.t['theta'])
+                launches += self._dense_forward()
+                fb.struct.iter = it
+                fb.call('bf_fit_step')
+                launches += 7
+        else:
+            fb.struct.iter = 0
+            if N > 1:
+                fb.call('bf_fit_run', N - 1)
+                launches += 7 * (N - 1)
+        self.theta_prev.copy_(fb.t['theta'])
+        launches += self._dense_forward()
+        fb.struct.iter = N - 1
+        fb.call('bf_fit_step')
+        launches += 7
+        self.kernel_launches = launches
+        return fb.t['theta']
+
+    def results(self):
+        """Device tensors with the reference's result-dict keys (smplify.py:216-226)."""
+        m = self.model
+        sn = m.split_theta(self.fb.t['theta'])
+        out = {}
+        if self.verts is not None:
+            out['vertices'] = self.verts
+        out.update(joints=self.joints, pose=sn['body_pose'], betas=sn['betas'], global_orient=sn['global_orient'],
+                   global_transl=sn['transl'] * sn['scale'], scale=sn['scale'], full_pose=self.full_pose)
+        if m.is_smplx:
+            out.update(leye_pose=sn['leye_pose'], reye_pose=sn['reye_pose'],
+                       left_hand_pose=sn['left_hand_pose'], right_hand_pose=sn['right_hand_pose'])
+        return out

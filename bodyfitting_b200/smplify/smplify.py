@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from .. import constants as K
-from ..engine import FrameBuffers, pack_cameras, pack_keypoints
+from ..engine import FitSession, pack_cameras, pack_keypoints
 from ..model import PreparedModel
 from ..synthetic import openpose_to_keypoints
 
@@ -26,7 +26,7 @@ class SMPLify(object):
 
     def __init__(self, smpl_type='smpl', age='adult', step_size=1e-2, batch_size=1, num_iters=600,
                  gender='male', use_mask=False, device=torch.device('cuda'), debug=True,
-                 model_data=None, gmm=None, J_regressor_extra=None, data_root='data'):
+                 model_data=None, gmm=None, J_regressor_extra=None, data_root='data', dense_every_iter=False):
         if age != 'adult':
             raise NotImplementedError("only age='adult' is supported (kid template: smplify.py:114-115)")
         self.device = torch.device(device)
@@ -53,6 +53,8 @@ class SMPLify(object):
                                    device=self.device)
         self.smpl_faces = self.model.faces.astype(np.int32).reshape(1, -1, 3)
         self.last_trace = None
+        self.dense_every_iter = dense_every_iter
+        self._pinned = {}
         self.last_loss_terms = None
 
     # ------------------------------------------------------------------------------------------
@@ -79,65 +81,69 @@ class SMPLify(object):
             raise NotImplementedError('silhouette term (smplify/loss.py:85-130) is not part of this build')
         if use_mesh:
             raise NotImplementedError('scan term: use bodyfitting_b200.smplify.smpld (SMPL+D path)')
-        m = self.model
-        dev = self.device
-        N = int(self.num_iters)
-        assert N >= 1
+        m, dev = self.model, self.device
         init_betas, init_poses, kp = self._pack_inputs(net_output, keypoints)
         B, Nv = kp.shape[0], kp.shape[1]
         assert kp.shape[2] == m.K_used, 'expected %d keypoints per view, got %d' % (m.K_used, kp.shape[2])
         assert len(c2ws) == Nv and len(Ks) == Nv
+        sess = self.session(B, Nv, imsize, return_vertices)
 
-        fb = FrameBuffers(m, B, full=False, Nv=Nv, n_trace=N, imsize=imsize)
+        # host -> device (pinned staging so the copies are asynchronous DMA)
+        kp_dev = self._h2d('kp', kp)
+        poses_dev = self._h2d('poses', init_poses)
+        betas_dev = self._h2d('betas', init_betas)
+        cams = self._h2d('cams', torch.from_numpy(pack_cameras(c2ws, Ks)))
+        sess.set_inputs(pack_keypoints(kp_dev, self.use_hand_face), cams)
         # init: body pose / betas / global orient from the network, transl 0, scale 1, rest 0 (smplify.py:103-128)
-        theta = m.pack_theta(init_poses[:, :3].to(dev, non_blocking=True), init_poses[:, 3:3 + m.nbody].to(dev, non_blocking=True),
-                             init_betas.to(dev, non_blocking=True))
-        fb.t['theta'].copy_(theta)
-        kp_dev = pack_keypoints(kp.to(dev, non_blocking=True), self.use_hand_face)
-        cams = torch.from_numpy(pack_cameras(c2ws, Ks)).to(dev, non_blocking=True)
-        fb.bind('kp', kp_dev)
-        fb.bind('cams', cams)
-
-        if N > 1:
-            fb.call('bf_fit_run', N - 1)
-        # the reference returns vertices / joints / full_pose of the LAST forward pass (parameters
-        # before the final Adam step) together with the parameters after it (smplify.py:216-226)
-        theta_prev = fb.t['theta'].clone()
-        fb.struct.iter = N - 1
-        fb.call('bf_fit_step')
-        out = self._final_outputs(theta_prev, fb.t['theta'], return_vertices)
-        self.last_trace = fb.t['trace']
-        self.last_loss_terms = fb.t['loss_terms']
+        theta0 = m.pack_theta(poses_dev[:, :3], poses_dev[:, 3:3 + m.nbody], betas_dev)
+        sess.run(theta0)
+        out = sess.results()
+        self.last_trace = sess.fb.t.get('trace')
+        self.last_loss_terms = sess.fb.t['loss_terms']
+        self.h2d_bytes = sum(int(t.numel() * t.element_size()) for t in (kp, init_poses, init_betas, cams))
         if as_numpy:
-            out = {k: (self.cpu(v) if torch.is_tensor(v) else v) for k, v in out.items()}
+            out = self._d2h(out)
+        out['faces'] = self.smpl_faces[0]
         return out
 
-    def _final_outputs(self, theta_prev, theta, return_vertices, chunk=4096):
-        m = self.model
-        B = theta.shape[0]
-        cs = K.CONSTANT_SCALE_NO_SCAN
-        sp, sn = m.split_theta(theta_prev), m.split_theta(theta)
-        verts = torch.empty(B, m.V, 3, device=self.device) if return_vertices else None
-        joints = torch.empty(B, m.K_out, 3, device=self.device)
-        full_pose = torch.empty(B, 3 * m.J, device=self.device)
-        for lo in range(0, B, chunk):
-            hi = min(B, lo + chunk)
-            ext = dict(theta=theta_prev[lo:hi].contiguous(), joints=joints[lo:hi], full_pose=full_pose[lo:hi])
-            if return_vertices:
-                ext['verts'] = verts[lo:hi].view(hi - lo, -1)
-            full = FrameBuffers(m, hi - lo, full=True, need_backward=False, ext=ext)
-            full.call('bf_lbs_forward')
-        t, s = sp['transl'][:, None, :], sp['scale'][:, None, :]
-        out = {}
-        if return_vertices:
-            out['vertices'] = (verts + t) * s * cs
-        out.update(joints=(joints + t) * s * cs, pose=sn['body_pose'], betas=sn['betas'],
-                   global_orient=sn['global_orient'], faces=self.smpl_faces[0],
-                   global_transl=sn['transl'] * sn['scale'], scale=sn['scale'], full_pose=full_pose)
-        if self.use_hand_face:
-            out.update(leye_pose=sn['leye_pose'], reye_pose=sn['reye_pose'],
-                       left_hand_pose=sn['left_hand_pose'], right_hand_pose=sn['right_hand_pose'])
-        return out
+    # ------------------------------------------------------------------------------------------
+    def session(self, B, Nv, imsize=512, return_vertices=True):
+        key = (int(B), int(Nv), int(self.num_iters), float(imsize), bool(return_vertices))
+        if getattr(self, '_sess_key', None) != key:
+            self._sess = FitSession(self.model, B, Nv, self.num_iters, imsize=imsize,
+                                    return_vertices=return_vertices, dense_every_iter=self.dense_every_iter)
+            self._sess_key = key
+            self._pinned = {}
+        return self._sess
+
+    def _h2d(self, name, t):
+        t = t.contiguous()
+        if t.is_cuda:
+            return t
+        p = self._pinned.get(('in', name))
+        if p is None or p.shape != t.shape or p.dtype != t.dtype:
+            p = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            self._pinned[('in', name)] = p
+        p.copy_(t)
+        return p.to(self.device, non_blocking=True)
+
+    def _d2h(self, out):
+        """Device results -> numpy via pinned buffers (one async copy each, one sync); a batch
+        dimension of 1 is squeezed as the reference's ``cpu()`` does (smplify.py:252-254)."""
+        host = {}
+        nbytes = 0
+        for k, v in out.items():
+            v = v.detach()
+            p = self._pinned.get(('out', k))
+            if p is None or p.shape != v.shape:
+                p = torch.empty(v.shape, dtype=v.dtype, pin_memory=True)
+                self._pinned[('out', k)] = p
+            p.copy_(v, non_blocking=True)
+            nbytes += int(v.numel() * v.element_size())
+            host[k] = p
+        torch.cuda.current_stream().synchronize()
+        self.d2h_bytes = nbytes
+        return {k: p.squeeze(0).numpy() for k, p in host.items()}
 
     def cpu(self, tensor):
         return tensor.detach().cpu().squeeze(0).numpy()

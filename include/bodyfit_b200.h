@@ -134,6 +134,8 @@ int bf_joints_backward(const BfModel* m, const BfFrames* f, int use_full, int ac
 int bf_keypoint_loss(const BfModel* m, const BfFrames* f, int use_full, void* stream);
 /* dverts -> dvp, dA, dpf */
 int bf_skin_backward(const BfModel* m, const BfFrames* f, int use_full, void* stream);
+/* the same, one kernel at a time (profiling): parts bit0 dvp, bit1 dA, bit2 blend-backward GEMM */
+int bf_skin_backward_parts(const BfModel* m, const BfFrames* f, int use_full, int parts, void* stream);
 /* dA, dJtr, dpf -> grad (theta[4:]); flags: 1 = add priors (value + grad), 2 = Adam step, 4 = keep grad[0:4] from loss kernel */
 int bf_pose_backward(const BfModel* m, const BfFrames* f, int flags, void* stream);
 

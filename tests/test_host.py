@@ -1,0 +1,244 @@
+"""CPU tests of the host logic: model tables (checked with a numpy interpreter of the tables
+against the oracle's joints), theta packing, camera / keypoint packing, the C-ABI library's
+exported symbols and struct layouts.  No kernel is launched here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from bodyfitting_b200 import _lib, constants as C, synthetic as syn
+from bodyfitting_b200.engine import pack_cameras, pack_keypoints
+from bodyfitting_b200.model import PreparedModel
+from util import make_port, perturbed_params, relerr
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope='module')
+def prepared(assets):
+    return {mt: PreparedModel(mt, assets(mt), gmm=assets('gmm'), J_regressor_extra=assets('jx'), device='cpu')
+            for mt in ('smpl', 'smplx')}
+
+
+def _vs_tables(pm, tag):
+    return {k[len(tag) + 1:]: v.numpy() for k, v in pm._dev.items() if k.startswith(tag + '_')}
+
+
+def _interp_joints(t, K_out, yaw, Jtr, verts):
+    out = np.zeros((K_out, 3))
+    for k in range(K_out):
+        kind, src, w = t['kj_kind'][k], t['kj_src'][k], t['kj_w'][k]
+        if kind == 0:
+            out[k] = Jtr[src[0]]
+        elif kind == 1:
+            out[k] = sum(verts[src[i]] * w[i] for i in range(3))
+        elif kind == 2:
+            out[k] = sum(verts[t['dyn_src'][yaw, src[0], i]] * t['dyn_w'][yaw, src[0], i] for i in range(3))
+        else:
+            r = src[0]
+            e0, e1 = t['xr_ptr'][r], t['xr_ptr'][r + 1]
+            out[k] = (verts[t['xr_vid'][e0:e1]] * t['xr_w'][e0:e1, None]).sum(0)
+    return out
+
+
+@pytest.mark.parametrize('mt', ['smpl', 'smplx'])
+def test_joint_tables_reproduce_oracle_joints(assets, prepared, mt):
+    pm = prepared[mt]
+    port = make_port(assets, mt, dtype=torch.float64)
+    B = 3
+    p = perturbed_params(mt, B, seed=9)
+    p['global_orient'][1, 1] = 0.6           # exercise a non-zero contour-landmark row
+    p['global_orient'][2, 1] = -0.5
+    c2ws, Ks = syn.make_cameras(2)
+    ev = port.loss_and_grads(p, c2ws, Ks, np.zeros((B, 2, pm.K_used, 3), np.float32))
+    verts, joints = ev['model_vertices'], ev['model_joints']
+    full = _vs_tables(pm, 'full')
+    act = _vs_tables(pm, 'act')
+    # chain joints = the oracle's first J pre-map joints; recover them through the mapped list
+    Jtr = np.zeros((B, pm.J, 3))
+    for k, (kind, src, _) in enumerate(pm.joint_table):
+        if kind == 0:
+            Jtr[:, src[0]] = joints[:, k]
+    fp64 = torch.tensor(ev['full_pose'], dtype=torch.float64)
+    for b in range(B):
+        yaw = 0
+        if mt == 'smplx':
+            from oracle import smplx_port as sp
+            m = port.model
+            idx, _ = sp.find_dynamic_lmk_idx_and_bcoords(torch.zeros(1, pm.V, 3, dtype=torch.float64), fp64[b:b + 1],
+                                                         torch.arange(79)[:, None].expand(79, 17), m.dynamic_lmk_bary_coords,
+                                                         m.neck_kin_chain)
+            yaw = int(idx[0, 0])
+        jf = _interp_joints(full, pm.K_out, yaw, Jtr[b], verts[b])
+        assert relerr(jf, joints[b]) < 1e-6
+        ja = _interp_joints(act, pm.K_used, yaw, Jtr[b], verts[b][pm.active_vids])
+        assert relerr(ja, joints[b, :pm.K_used]) < 1e-6
+    assert pm.n_act == (11 if mt == 'smpl' else len(pm.active_vids)) and pm.n_act < 600
+
+
+@pytest.mark.parametrize('mt', ['smpl', 'smplx'])
+def test_target_lists_are_the_transpose_of_the_joint_table(prepared, mt):
+    """d(sum_k g_k . joint_k)/d(target) through tg_* equals the direct transpose, for every yaw row."""
+    pm = prepared[mt]
+    for tag, K_out, n in (('act', pm.K_used, pm.n_act), ('full', pm.K_out, pm.V)):
+        t = _vs_tables(pm, tag)
+        rng = np.random.RandomState(1)
+        g = rng.standard_normal((K_out, 3))
+        for yaw in ((0, 17, 78) if mt == 'smplx' else (0,)):
+            direct = np.zeros((pm.J + n, 3))
+            for k in range(K_out):
+                kind, src, w = t['kj_kind'][k], t['kj_src'][k], t['kj_w'][k]
+                if kind == 0:
+                    direct[src[0]] += g[k]
+                elif kind == 1:
+                    for i in range(3):
+                        direct[pm.J + src[i]] += w[i] * g[k]
+                elif kind == 2:
+                    for i in range(3):
+                        direct[pm.J + t['dyn_src'][yaw, src[0], i]] += t['dyn_w'][yaw, src[0], i] * g[k]
+                else:
+                    r = src[0]
+                    for e in range(t['xr_ptr'][r], t['xr_ptr'][r + 1]):
+                        direct[pm.J + t['xr_vid'][e]] += t['xr_w'][e] * g[k]
+            via = np.zeros_like(direct)
+            ptr = t['tg_ptr']
+            assert ptr.shape[0] == pm.J + n + 1
+            for tg in np.nonzero(np.diff(ptr))[0]:
+                for e in range(ptr[tg], ptr[tg + 1]):
+                    if t['tg_a'][e] < 0 or t['tg_a'][e] == yaw:
+                        via[tg] += t['tg_w'][e] * g[t['tg_k'][e]]
+            assert np.abs(via - direct).max() < 1e-6
+
+
+@pytest.mark.parametrize('mt', ['smpl', 'smplx'])
+def test_blend_matrix_and_folded_regressor(assets, prepared, mt):
+    pm, data = prepared[mt], assets(mt)
+    full = _vs_tables(pm, 'full')
+    Bm = full['Bm']
+    V, P, NS = pm.V, pm.P, pm.NS
+    assert Bm.shape == (pm.Kp, 3 * full['ell_j'].shape[0]) and pm.Kp % 16 == 0
+    rng = np.random.RandomState(0)
+    pf = np.zeros(pm.Kp); pf[:P] = rng.standard_normal(P) * 0.1; pf[P:P + NS] = rng.standard_normal(NS); pf[P + NS] = 1.0
+    vp = (pf @ Bm.astype(np.float64))[:3 * V].reshape(V, 3)
+    ref = data['v_template'] + np.einsum('l,vcl->vc', pf[P:P + NS], data['shapedirs'][:, :, :NS].astype(np.float64)) + \
+        (pf[:P] @ np.reshape(data['posedirs'], [-1, P]).T.astype(np.float64)).reshape(V, 3)
+    assert np.abs(vp - ref).max() < 1e-6
+    assert (Bm[:, 3 * V:] == 0).all() and (Bm[P + NS + 1:] == 0).all()
+    Jt, Jd = pm._dev['m_Jt'].numpy(), pm._dev['m_Jd'].numpy()
+    Jref = data['J_regressor'].astype(np.float64) @ (data['v_template'] + np.einsum('l,vcl->vc', pf[P:P + NS], data['shapedirs'][:, :, :NS]))
+    assert np.abs(Jt + Jd @ pf[P:P + NS] - Jref).max() < 1e-6
+    # ELL weights reproduce the dense rows; CSR by joint is their transpose
+    W = data['weights']
+    dense = np.zeros_like(W)
+    for k in range(full['ell_j'].shape[1]):
+        np.add.at(dense, (np.arange(V), full['ell_j'][:V, k]), full['ell_w'][:V, k])
+    assert np.array_equal(dense, W)
+    jv = np.zeros_like(W)
+    for j in range(pm.J):
+        e0, e1 = full['jv_ptr'][j], full['jv_ptr'][j + 1]
+        jv[full['jv_vid'][e0:e1], j] = full['jv_w'][e0:e1]
+    assert np.array_equal(jv, W)
+    act = _vs_tables(pm, 'act')
+    assert np.array_equal(act['Bm'][:, :3 * pm.n_act].reshape(pm.Kp, pm.n_act, 3), Bm[:, :3 * V].reshape(pm.Kp, V, 3)[:, pm.active_vids])
+
+
+def test_kinematic_tables(prepared):
+    for mt, depth in (('smpl', 8), ('smplx', 10)):
+        pm = prepared[mt]
+        par, dep = pm._dev['m_parents'].numpy(), pm._dev['m_depth'].numpy()
+        assert pm.max_depth == depth and dep[0] == 0 and par[0] == -1
+        assert all(dep[j] == dep[par[j]] + 1 for j in range(1, pm.J))
+        cp, ci = pm._dev['m_child_ptr'].numpy(), pm._dev['m_child_idx'].numpy()
+        for j in range(pm.J):
+            assert sorted(ci[cp[j]:cp[j + 1]]) == [c for c in range(1, pm.J) if par[c] == j]
+
+
+def test_theta_pack_roundtrip(prepared):
+    for mt in ('smpl', 'smplx'):
+        pm = prepared[mt]
+        B = 4
+        p = perturbed_params(mt, B, seed=2)
+        T = lambda k: torch.as_tensor(p[k]) if k in p else None
+        th = pm.pack_theta(T('global_orient'), T('body_pose'), T('betas'), transl=T('global_transl'), scale=T('body_scale'),
+                           leye=T('leye_pose'), reye=T('reye_pose'), lhand=T('left_hand_pose'), rhand=T('right_hand_pose'))
+        assert th.shape == (B, pm.NP) and pm.NP == (98 if mt == 'smplx' else 86)
+        s = pm.split_theta(th)
+        assert np.array_equal(s['body_pose'].numpy(), p['body_pose']) and np.array_equal(s['betas'].numpy(), p['betas'])
+        assert np.array_equal(s['scale'].numpy(), p['body_scale'])
+        if mt == 'smplx':
+            assert np.array_equal(s['right_hand_pose'].numpy(), p['right_hand_pose'])
+
+
+def test_smpl_to_openpose_tables():
+    a = C.smpl_to_openpose('smplx', use_hands=True, use_face=True, use_face_contour=True, openpose_format='coco25')
+    assert len(a) == 135 and list(a[:3]) == [55, 12, 17] and a[25] == 20 and a[29] == 66 and a[46] == 21 and a[-1] == 143
+    assert list(C.smpl_to_openpose('smpl', openpose_format='coco25')) == [24, 12, 17, 19, 21, 16, 18, 20, 0, 2, 5, 8, 1, 4, 7] + list(range(25, 35))
+    assert len(C.smpl_to_openpose('smplh', use_hands=True, openpose_format='coco19')) == 19 + 42
+    assert len(C.SPIN_JOINT_MAP) == 49 and C.SPIN_JOINT_MAP[27] == 45
+    with pytest.raises(ValueError):
+        C.smpl_to_openpose('foo')
+
+
+def test_pack_cameras_and_keypoints():
+    c2ws, Ks = syn.make_cameras(3)
+    M = pack_cameras(list(c2ws), list(Ks)).reshape(3, 3, 4)
+    X = np.array([0.1, -0.2, 0.05, 1.0])
+    for v in range(3):
+        w2c = np.linalg.inv(c2ws[v].astype(np.float64))
+        ref = Ks[v] @ (w2c[:3] @ X)
+        assert np.abs(M[v] @ X - ref).max() < 1e-4
+    kp = np.random.RandomState(0).rand(2, 3, 135, 3).astype(np.float32)
+    out = pack_keypoints(kp, True).numpy()
+    assert np.allclose(out[..., :25, 2], kp[..., :25, 2] ** 2)
+    assert np.allclose(out[..., 30, 2], (kp[..., 25:46, 2] ** 2).sum(-1))
+    assert np.allclose(out[..., 100, 2], (kp[..., 67:, 2] ** 2).sum(-1), rtol=1e-5)
+    assert np.array_equal(out[..., :2], kp[..., :2])
+
+
+def test_openpose_dict_roundtrip():
+    kp = np.random.RandomState(1).rand(8, 135, 3).astype(np.float32)
+    views = syn.keypoints_to_openpose(kp, 'smplx')
+    assert views[0]['face'].shape == (70, 3) and views[0]['hand_left'].shape == (21, 3)
+    assert np.array_equal(syn.openpose_to_keypoints(views, 'smplx'), kp)
+    views[3] = None
+    del views[4]['hand_right']
+    back = syn.openpose_to_keypoints(views, 'smplx')
+    assert (back[3] == 0).all() and (back[4, 46:67] == 0).all() and np.array_equal(back[4, :46], kp[4, :46])
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    L = _lib.lib()
+    hdr = open(os.path.join(ROOT, 'include', 'bodyfit_b200.h')).read()
+    declared = set(re.findall(r'\b(bf_[a-z0-9_]+)\s*\(', hdr))
+    assert declared, 'no declarations parsed'
+    for name in sorted(declared):
+        assert hasattr(L, name), 'symbol %s declared in the header but not exported' % name
+    assert declared == set(_lib.EXPORTED)
+    assert L.bf_abi_version() == _lib.ABI_VERSION
+    for i, st in enumerate((_lib.BfVSet, _lib.BfModel, _lib.BfFrames)):
+        assert L.bf_sizeof(i) == ctypes.sizeof(st)
+
+
+def test_no_gpu_means_loud_failure():
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    with pytest.raises(_lib.BodyfitError):
+        _lib.require_device()
+    from bodyfitting_b200.smplify.smplify import SMPLify
+    fit = SMPLify(smpl_type='smpl', num_iters=2, model_data=syn.make_model('smpl', 0), gmm=syn.make_gmm(0), device='cpu')
+    kp = np.zeros((1, 2, 25, 3), np.float32)
+    c2ws, Ks = syn.make_cameras(2)
+    with pytest.raises(_lib.BodyfitError):
+        fit((np.zeros((1, 10), np.float32), np.zeros((1, 72), np.float32)), list(c2ws), list(Ks), kp, None)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, 'bodyfitting_b200')
+    for dp, _, fns in os.walk(pkg):
+        for fn in fns:
+            if fn.endswith('.py'):
+                src = open(os.path.join(dp, fn)).read()
+                assert not re.search(r'^\s*(from|import)\s+oracle', src, re.M), fn
