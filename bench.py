@@ -164,7 +164,7 @@ def build_workload(pm, F, seed):
         hi = min(F, lo + chunk)
         fb = FrameBuffers(pm, hi - lo, full=True, need_backward=False,
                           ext=dict(theta=theta_gt[lo:hi].contiguous(), joints=joints[lo:hi]))
-        fb.struct.flags = _lib.F_WORLD
+        fb.struct.flags |= _lib.F_WORLD
         fb.call('bf_lbs_forward')
     torch.cuda.synchronize()
     kp = syn.make_keypoints(joints.cpu().numpy(), c2ws, Ks, seed=seed)

@@ -10,8 +10,9 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libbodyfit_b200.so')
-ABI_VERSION = 4
+ABI_VERSION = 6
 F_WORLD = 1
+F_TC = 2
 
 _fp = C.c_void_p
 _i32 = C.c_int32
@@ -20,7 +21,7 @@ _i32 = C.c_int32
 class BfVSet(C.Structure):
     _fields_ = [(n, _fp) for n in (
         'Bm', 'ell_j', 'ell_w', 'jv_ptr', 'jv_vid', 'jv_w', 'kj_kind', 'kj_src', 'kj_w',
-        'dyn_src', 'dyn_w', 'tg_ptr', 'tg_k', 'tg_a', 'tg_w', 'xr_ptr', 'xr_vid', 'xr_w')] + \
+        'dyn_src', 'dyn_w', 'tg_ptr', 'tg_k', 'tg_a', 'tg_w', 'xr_ptr', 'xr_vid', 'xr_w', 'Bt_hi', 'Bt_lo', 'Bm_hi', 'Bm_lo')] + \
         [(n, _i32) for n in ('n', 'n_pad', 'ldn', 'nnz', 'K_out', 'n_dyn', 'n_extra', '_pad0')]
 
 
@@ -36,7 +37,8 @@ class BfModel(C.Structure):
 class BfFrames(C.Structure):
     _fields_ = [(n, _fp) for n in (
         'theta', 'grad', 'adam_m', 'adam_v', 'pf', 'dpf', 'A', 'dA', 'Jtr', 'dJtr', 'full_pose', 'yaw',
-        'verts', 'vposed', 'dverts', 'dvp', 'joints', 'djoints', 'kp', 'cams', 'loss', 'loss_terms', 'trace')] + \
+        'verts', 'vposed', 'dverts', 'dvp', 'joints', 'djoints', 'kp', 'cams', 'loss', 'loss_terms', 'trace',
+        'pf_hi', 'pf_lo', 'dvp_hi', 'dvp_lo', 'ws')] + [('ws_floats', C.c_int64)] + \
         [(n, C.c_double) for n in ('lr_ts', 'lr', 'beta1', 'beta2', 'eps')] + \
         [(n, _i32) for n in ('B', 'Nv', 'ld_v', 'iter', 'flags', '_pad0')] + \
         [(n, C.c_float) for n in ('imsize', 'constant_scale', 'sigma', 'w_pose', 'w_angle', 'w_shape')]

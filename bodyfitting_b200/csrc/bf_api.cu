@@ -74,10 +74,7 @@ int bf_skin_forward(const BfModel* m, const BfFrames* f, int use_full, void* str
     const BfVSet* vs = use_full ? &m->full : &m->act;
     rc = check_vset(vs, f); if (rc) return rc;
     BF_REQUIRE(f->pf && f->A && f->verts, "pf/A/verts is null");
-    if (bf_tc_enabled() && f->B >= 128) {
-        rc = bf_skin_forward_tc(m, vs, f, (cudaStream_t)stream);
-        if (rc != 1) return rc;       // 1 = shape not supported by the tensor-core path, fall through to FFMA
-    }
+    if (bf_tc_ready_fwd(vs, f)) return bf_skin_forward_tc(m, vs, f, (cudaStream_t)stream);
     const dim3 grid(vs->n_pad / SK_TV, (f->B + SK_TB - 1) / SK_TB), block(256);
     k_skin_fwd<<<grid, block, 0, (cudaStream_t)stream>>>(*vs, m->J, m->Kp, f->pf, f->A, f->verts, f->vposed, f->B, f->ld_v,
                                                            (f->flags & BF_F_WORLD) ? f->theta : nullptr, m->NP, f->constant_scale);
@@ -128,14 +125,21 @@ int bf_skin_backward_parts(const BfModel* m, const BfFrames* f, int use_full, in
     cudaStream_t s = (cudaStream_t)stream;
     if (parts & 1) {
         const dim3 grid((vs->n + 255) / 256, (f->B + DV_FB - 1) / DV_FB);
-        k_skin_bwd_dvp<<<grid, 256, 0, s>>>(*vs, m->J, f->A, f->dverts, f->dvp, f->B, f->ld_v);
+        const bool tcb = bf_tc_ready_bwd(vs, f);
+        k_skin_bwd_dvp<<<grid, 256, 0, s>>>(*vs, m->J, f->A, f->dverts, f->dvp, f->B, f->ld_v,
+                                           tcb ? f->dvp_hi : nullptr, tcb ? f->dvp_lo : nullptr);
         BF_LAUNCH_CHECK();
     }
     if (parts & 2) {
         k_skin_bwd_dA<<<f->B, 256, 0, s>>>(*vs, m->J, f->dverts, f->vposed, f->dA, f->B, f->ld_v);
         BF_LAUNCH_CHECK();
     }
-    if (parts & 4) {
+    int tc_rc = 1;
+    if ((parts & 4) && bf_tc_ready_bwd(vs, f)) {
+        tc_rc = bf_blend_backward_tc(m, vs, f, s);
+        if (tc_rc < 0) return tc_rc;
+    }
+    if ((parts & 4) && tc_rc == 1) {                       // FP32 FFMA contraction (no tensor cores / no workspace)
         const dim3 grid((m->Kp + GB_T - 1) / GB_T, (f->B + GB_T - 1) / GB_T);
         k_blend_bwd<<<grid, 256, 0, s>>>(*vs, m->Kp, f->dvp, f->dpf, f->B, f->ld_v);
         BF_LAUNCH_CHECK();

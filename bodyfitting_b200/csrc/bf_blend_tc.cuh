@@ -1,6 +1,430 @@
-// Tensor-core (tcgen05, 3xTF32) variant of the blend-shape contraction -- placeholder
-// until the UMMA kernel lands; the FFMA kernel in bf_skin.cuh is the active path.
+// Tensor-core path of the blend-shape contraction (the only GEMM-shaped work of the fit):
+//
+//   k_skin_fwd_tc  : v_posed tile [128 frames x 192 coords] = pf @ Bm on tcgen05 (kind::tf32,
+//                    3xTF32 split: hi*hi + lo*hi + hi*lo, fp32 accumulate in TMEM), operands
+//                    staged by TMA (SWIZZLE_128B, K-major) through a 2-stage mbarrier pipeline,
+//                    accumulator read back with tcgen05.ld and skinned in the epilogue
+//                    (sum_k w_k A[b, j_k]) [v_posed; 1] without ever writing v_posed to HBM
+//                    unless the backward needs it.
+//   k_blend_bwd_tc : dpf tile [128 frames x <=256 k] = dvp @ Bm^T, same machinery, reduction over
+//                    the vertex coordinates.
+//
+// Warp roles (192 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA
+// issuer (one lane), warps 2..5 = epilogue (TMEM lane quarter = warp_idx % 4).
+//
+// Why 3xTF32: single TF32 (10-bit mantissa) leaves ~5e-4 relative error on the blend-shape
+// offsets, i.e. ~1e-5 of the vertex magnitude -- at the north-star tolerance (1e-5 relative on
+// vertices) and, more importantly, too coarse for the 1e-4 per-iteration loss parity through 100
+// Adam steps.  The split keeps the error at ~2^-21 per product (measured: see DESIGN.md).
 #pragma once
+#include <cuda.h>
 #include "bf_common.cuh"
-static inline bool bf_tc_enabled() { return false; }
-static inline int bf_skin_forward_tc(const BfModel*, const BfVSet*, const BfFrames*, cudaStream_t) { return 1; }
+
+#define TC_BM 128          // frames per tile (UMMA M)
+#define TC_BK 32           // fp32 elements per K chunk = one 128-byte swizzle row
+#define TC_BN1 192         // coords per tile in the forward (64 vertices)
+#define TC_STAGES 2
+#define TC_VP_LD 97        // padded row stride of the per-warp v_posed staging tile
+
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// bounded wait: a pipeline bug must trap (-> CUDA error at the caller), never hang the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const long long t0 = clock64();
+    while (!mbar_try(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) { printf("bodyfit: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x); __trap(); }
+    }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// K-major, SWIZZLE_128B operand tile: rows of 128 B, 8-row groups 1024 B apart (SBO), LBO unused (=1)
+__device__ __forceinline__ uint64_t make_desc(const void* smem_tile) {
+    const uint32_t a = smem_u32(smem_tile);
+    uint64_t d = 0;
+    d |= (uint64_t)((a >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;          // descriptor version 1 (Blackwell)
+    d |= (uint64_t)2 << 61;          // SWIZZLE_128B
+    return d;
+}
+__device__ __forceinline__ uint32_t make_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared main loop: warp 0 lane 0 streams K chunks with TMA, warp 1 lane 0 issues the MMAs.
+// Stage layout: A_hi | A_lo | B_hi | B_lo, each a [rows x 128 B] SWIZZLE_128B tile.
+struct Pipe {
+    uint8_t* stage_base;
+    uint64_t* full;
+    uint64_t* empty;
+    uint64_t* tmem_full;
+    uint32_t a_bytes, b_bytes;
+    __device__ __forceinline__ uint32_t stage_bytes() const { return 2 * a_bytes + 2 * b_bytes; }
+    __device__ __forceinline__ uint8_t* stage(int s) const { return stage_base + (size_t)s * stage_bytes(); }
+};
+
+__device__ __forceinline__ void producer(const Pipe& p, const CUtensorMap* mA_hi, const CUtensorMap* mA_lo,
+                                         const CUtensorMap* mB_hi, const CUtensorMap* mB_lo, int num_k, int rowA, int rowB,
+                                         int kc_begin = 0) {
+    for (int kc = 0; kc < num_k; ++kc) {
+        const int s = kc % TC_STAGES;
+        const uint32_t ph = (kc / TC_STAGES) & 1;
+        mbar_wait(&p.empty[s], ph ^ 1);
+        mbar_expect_tx(&p.full[s], p.stage_bytes());
+        uint8_t* st = p.stage(s);
+        const int c0 = (kc_begin + kc) * TC_BK;
+        tma_load_2d(st, mA_hi, &p.full[s], c0, rowA);
+        tma_load_2d(st + p.a_bytes, mA_lo, &p.full[s], c0, rowA);
+        tma_load_2d(st + 2 * p.a_bytes, mB_hi, &p.full[s], c0, rowB);
+        tma_load_2d(st + 2 * p.a_bytes + p.b_bytes, mB_lo, &p.full[s], c0, rowB);
+    }
+}
+
+__device__ __forceinline__ void mma_issuer(const Pipe& p, int num_k, uint32_t tmem_d, uint32_t idesc) {
+    for (int kc = 0; kc < num_k; ++kc) {
+        const int s = kc % TC_STAGES;
+        const uint32_t ph = (kc / TC_STAGES) & 1;
+        mbar_wait(&p.full[s], ph);
+        tc_fence_after();
+        uint8_t* st = p.stage(s);
+        const uint64_t a_hi = make_desc(st), a_lo = make_desc(st + p.a_bytes);
+        const uint64_t b_hi = make_desc(st + 2 * p.a_bytes), b_lo = make_desc(st + 2 * p.a_bytes + p.b_bytes);
+#pragma unroll
+        for (int k = 0; k < TC_BK / 8; ++k) {            // UMMA K = 8 tf32 = 32 B -> +2 in the 16-byte address field
+            const uint64_t o = (uint64_t)(2 * k);
+            umma_tf32(tmem_d, a_hi + o, b_hi + o, idesc, (kc | k) ? 1u : 0u);
+            umma_tf32(tmem_d, a_lo + o, b_hi + o, idesc, 1u);
+            umma_tf32(tmem_d, a_hi + o, b_lo + o, idesc, 1u);
+        }
+        umma_commit(&p.empty[s]);                        // frees the smem slot when these MMAs have read it
+    }
+    umma_commit(p.tmem_full);                            // accumulator complete
+}
+
+}  // namespace tc
+
+__global__ void __launch_bounds__(192, 1) k_skin_fwd_tc(const __grid_constant__ CUtensorMap mA_hi,
+                                                        const __grid_constant__ CUtensorMap mA_lo,
+                                                        const __grid_constant__ CUtensorMap mB_hi,
+                                                        const __grid_constant__ CUtensorMap mB_lo,
+                                                        BfVSet vs, int J, int Kp, const float* __restrict__ A,
+                                                        float* __restrict__ verts, float* __restrict__ vposed,
+                                                        int B, int ld_v, const float* __restrict__ theta, int NP, float cs) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    tc::Pipe p;
+    p.a_bytes = TC_BM * 128;
+    p.b_bytes = TC_BN1 * 128;
+    p.stage_base = base;
+    float* Vp = reinterpret_cast<float*>(base + TC_STAGES * p.stage_bytes());
+    uint64_t* bars = reinterpret_cast<uint64_t*>(Vp + 4 * 32 * TC_VP_LD);
+    p.full = bars; p.empty = bars + TC_STAGES; p.tmem_full = bars + 2 * TC_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b0 = blockIdx.y * TC_BM;
+    const int n0 = blockIdx.x * TC_BN1;
+    const int num_k = Kp / TC_BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) { tc::mbar_init(&p.full[s], 1); tc::mbar_init(&p.empty[s], 1); }
+        tc::mbar_init(p.tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(tmem_slot)), "r"(256));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_d = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) tc::producer(p, &mA_hi, &mA_lo, &mB_hi, &mB_lo, num_k, b0, n0);
+    } else if (warp == 1) {
+        if (lane == 0) tc::mma_issuer(p, num_k, tmem_d, tc::make_idesc_tf32(TC_BM, TC_BN1));
+    } else {
+        tc::mbar_wait(p.tmem_full, 0);
+        tc::tc_fence_after();
+        const int q = warp & 3;                               // TMEM lane quarter this warp may read
+        float* myVp = Vp + (warp - 2) * 32 * TC_VP_LD;
+        const int nnz = vs.nnz;
+        for (int chunk = 0; chunk < TC_BN1 / 96; ++chunk) {
+#pragma unroll 1
+            for (int part = 0; part < 3; ++part) {
+                uint32_t r[32];
+                tc::tmem_ld32(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(chunk * 96 + part * 32), r);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) myVp[lane * TC_VP_LD + part * 32 + i] = __uint_as_float(r[i]);
+            }
+            __syncwarp();
+            const int v = n0 / 3 + chunk * 32 + lane;
+            if (v < vs.n) {
+                const int32_t* ej = vs.ell_j + (size_t)v * nnz;
+                const float* ew = vs.ell_w + (size_t)v * nnz;
+                for (int fr = 0; fr < 32; ++fr) {
+                    const int b = b0 + 32 * q + fr;
+                    if (b >= B) break;
+                    const float px = myVp[fr * TC_VP_LD + 3 * lane], py = myVp[fr * TC_VP_LD + 3 * lane + 1],
+                                pz = myVp[fr * TC_VP_LD + 3 * lane + 2];
+                    float T[12];
+#pragma unroll
+                    for (int e = 0; e < 12; ++e) T[e] = 0.f;
+                    const float* Ab = A + (size_t)b * J * 12;
+                    for (int k = 0; k < nnz; ++k) {
+                        const float w = __ldg(ew + k);
+                        const float4* Aj = reinterpret_cast<const float4*>(Ab + __ldg(ej + k) * 12);
+                        const float4 r0 = __ldg(Aj), r1 = __ldg(Aj + 1), r2 = __ldg(Aj + 2);
+                        T[0] = fmaf(w, r0.x, T[0]); T[1] = fmaf(w, r0.y, T[1]); T[2] = fmaf(w, r0.z, T[2]); T[3] = fmaf(w, r0.w, T[3]);
+                        T[4] = fmaf(w, r1.x, T[4]); T[5] = fmaf(w, r1.y, T[5]); T[6] = fmaf(w, r1.z, T[6]); T[7] = fmaf(w, r1.w, T[7]);
+                        T[8] = fmaf(w, r2.x, T[8]); T[9] = fmaf(w, r2.y, T[9]); T[10] = fmaf(w, r2.z, T[10]); T[11] = fmaf(w, r2.w, T[11]);
+                    }
+                    float ox = T[0] * px + T[1] * py + T[2] * pz + T[3];
+                    float oy = T[4] * px + T[5] * py + T[6] * pz + T[7];
+                    float oz = T[8] * px + T[9] * py + T[10] * pz + T[11];
+                    if (theta) {
+                        const float* th = theta + (size_t)b * NP;
+                        const float sc = __ldg(th + 3);
+                        ox = (ox + __ldg(th + 0)) * sc * cs; oy = (oy + __ldg(th + 1)) * sc * cs; oz = (oz + __ldg(th + 2)) * sc * cs;
+                    }
+                    float* o = verts + (size_t)b * ld_v + 3 * v;
+                    o[0] = ox; o[1] = oy; o[2] = oz;
+                    if (vposed) {
+                        float* qv = vposed + (size_t)b * ld_v + 3 * v;
+                        qv[0] = px; qv[1] = py; qv[2] = pz;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(256));
+    }
+}
+
+// dpf[b, k0 + c] = sum_n dvp[b, n] Bm[k0 + c, n]; BN = columns of this CTA (multiple of 16, <= 256)
+__global__ void __launch_bounds__(192, 1) k_blend_bwd_tc(const __grid_constant__ CUtensorMap mA_hi,
+                                                         const __grid_constant__ CUtensorMap mA_lo,
+                                                         const __grid_constant__ CUtensorMap mB_hi,
+                                                         const __grid_constant__ CUtensorMap mB_lo,
+                                                         int BN, int num_k_total, int cps, int Kp,
+                                                         float* __restrict__ out, size_t split_stride, int B) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    tc::Pipe p;
+    p.a_bytes = TC_BM * 128;
+    p.b_bytes = (uint32_t)BN * 128;
+    p.stage_base = base;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base + TC_STAGES * p.stage_bytes());
+    p.full = bars; p.empty = bars + TC_STAGES; p.tmem_full = bars + 2 * TC_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b0 = blockIdx.y * TC_BM;
+    const int k0 = blockIdx.x * BN;
+    // split-K: this CTA reduces K chunks [kc_begin, kc_begin + num_k) and writes its own partial
+    // (the tensor-core accumulator truncates, so long reductions are cut and summed in fp32 RN)
+    const int kc_begin = blockIdx.z * cps;
+    const int num_k = min(cps, num_k_total - kc_begin);
+    float* dpf = out + (size_t)blockIdx.z * split_stride;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) { tc::mbar_init(&p.full[s], 1); tc::mbar_init(&p.empty[s], 1); }
+        tc::mbar_init(p.tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(tmem_slot)), "r"(256));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_d = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) tc::producer(p, &mA_hi, &mA_lo, &mB_hi, &mB_lo, num_k, b0, k0, kc_begin);
+    } else if (warp == 1) {
+        if (lane == 0) tc::mma_issuer(p, num_k, tmem_d, tc::make_idesc_tf32(TC_BM, BN));
+    } else {
+        tc::mbar_wait(p.tmem_full, 0);
+        tc::tc_fence_after();
+        const int q = warp & 3;
+        const int b = b0 + 32 * q + lane;
+        for (int c = 0; c < BN; c += 32) {
+            uint32_t r[32];
+            tc::tmem_ld32(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)c, r);
+            if (b < B) {
+                float4* o = reinterpret_cast<float4*>(dpf + (size_t)b * Kp + k0 + c);
+                const int nv = (BN - c >= 32) ? 8 : (BN - c) / 4;
+                for (int i = 0; i < nv; ++i)
+                    o[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
+                                       __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(256));
+    }
+}
+
+// dst[i] = sum_z ws[z][i], fixed order (deterministic); n is a multiple of 4 (Kp % 16 == 0)
+__global__ void __launch_bounds__(256) k_sum_partials(const float* __restrict__ ws, float* __restrict__ dst, size_t n, int S) {
+    const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i >= n) return;
+    float4 a = *reinterpret_cast<const float4*>(ws + i);
+    for (int z = 1; z < S; ++z) {
+        const float4 b = *reinterpret_cast<const float4*>(ws + (size_t)z * n + i);
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    *reinterpret_cast<float4*>(dst + i) = a;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+typedef CUresult (*bf_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                       const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                       CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static bf_encode_tiled_fn bf_get_encode() {
+    static bf_encode_tiled_fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<bf_encode_tiled_fn>(ptr);
+    }
+    return fn;
+}
+
+// [rows, cols] fp32 row-major with leading dimension ld (elements); box = 32 cols (128 B) x box_rows
+static int bf_make_map(CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+    bf_encode_tiled_fn enc = bf_get_encode();
+    if (!enc) { bf_set_error("cuTensorMapEncodeTiled not available from the driver"); return BF_ECUDA; }
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {ld * sizeof(float)};
+    cuuint32_t box[2] = {TC_BK, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { bf_set_error("cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu ld=%llu", (int)r,
+                                          (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld); return BF_ECUDA; }
+    return BF_OK;
+}
+
+static inline bool bf_tc_ready_fwd(const BfVSet* vs, const BfFrames* f) {
+    return (f->flags & BF_F_TC) && vs->Bt_hi && vs->Bt_lo && f->pf_hi && f->pf_lo;
+}
+static inline bool bf_tc_ready_bwd(const BfVSet* vs, const BfFrames* f) {
+    return (f->flags & BF_F_TC) && vs->Bm_hi && vs->Bm_lo && f->dvp_hi && f->dvp_lo;
+}
+
+static int bf_skin_forward_tc(const BfModel* m, const BfVSet* vs, const BfFrames* f, cudaStream_t s) {
+    CUtensorMap a_hi, a_lo, b_hi, b_lo;
+    int rc;
+    if ((rc = bf_make_map(&a_hi, f->pf_hi, f->B, m->Kp, m->Kp, TC_BM))) return rc;
+    if ((rc = bf_make_map(&a_lo, f->pf_lo, f->B, m->Kp, m->Kp, TC_BM))) return rc;
+    if ((rc = bf_make_map(&b_hi, vs->Bt_hi, vs->ldn, m->Kp, m->Kp, TC_BN1))) return rc;
+    if ((rc = bf_make_map(&b_lo, vs->Bt_lo, vs->ldn, m->Kp, m->Kp, TC_BN1))) return rc;
+    const size_t smem = 1024 + TC_STAGES * (2 * TC_BM * 128 + 2 * TC_BN1 * 128) + 4 * 32 * TC_VP_LD * 4 + 64;
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(k_skin_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { bf_set_error("cudaFuncSetAttribute(k_skin_fwd_tc): %s", cudaGetErrorString(e)); return BF_ECUDA; }
+        attr = true;
+    }
+    const dim3 grid((vs->ldn + TC_BN1 - 1) / TC_BN1, (f->B + TC_BM - 1) / TC_BM);
+    k_skin_fwd_tc<<<grid, 192, smem, s>>>(a_hi, a_lo, b_hi, b_lo, *vs, m->J, m->Kp, f->A, f->verts, f->vposed, f->B, f->ld_v,
+                                          (f->flags & BF_F_WORLD) ? f->theta : nullptr, m->NP, f->constant_scale);
+    BF_LAUNCH_CHECK();
+    return BF_OK;
+}
+
+static int bf_blend_backward_tc(const BfModel* m, const BfVSet* vs, const BfFrames* f, cudaStream_t s) {
+    CUtensorMap a_hi, a_lo, b_hi, b_lo;
+    int rc;
+    const int BN = m->Kp < 256 ? m->Kp : 256;
+    if (m->Kp % BN != 0) { bf_set_error("Kp=%d not tileable by %d", m->Kp, BN); return BF_EINVAL; }
+    if ((rc = bf_make_map(&a_hi, f->dvp_hi, f->B, vs->ldn, vs->ldn, TC_BM))) return rc;
+    if ((rc = bf_make_map(&a_lo, f->dvp_lo, f->B, vs->ldn, vs->ldn, TC_BM))) return rc;
+    if ((rc = bf_make_map(&b_hi, vs->Bm_hi, m->Kp, vs->ldn, vs->ldn, BN))) return rc;
+    if ((rc = bf_make_map(&b_lo, vs->Bm_lo, m->Kp, vs->ldn, vs->ldn, BN))) return rc;
+    const size_t smem = 1024 + TC_STAGES * (2 * TC_BM * 128 + 2 * (size_t)BN * 128) + 64;
+    static size_t attr = 0;
+    if (attr < smem) {
+        cudaError_t e = cudaFuncSetAttribute(k_blend_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { bf_set_error("cudaFuncSetAttribute(k_blend_bwd_tc): %s", cudaGetErrorString(e)); return BF_ECUDA; }
+        attr = smem;
+    }
+    const int num_k = vs->ldn / TC_BK;
+    const int cps = 64;                                   // <= 2048 coordinates per tensor-core accumulation run
+    const int S = (num_k + cps - 1) / cps;
+    const size_t stride = (size_t)f->B * m->Kp;
+    if (S > 1 && (!f->ws || (size_t)f->ws_floats < (size_t)S * stride)) return 1;   // caller falls back to the FFMA kernel
+    const dim3 grid(m->Kp / BN, (f->B + TC_BM - 1) / TC_BM, S);
+    k_blend_bwd_tc<<<grid, 192, smem, s>>>(a_hi, a_lo, b_hi, b_lo, BN, num_k, cps, m->Kp, S > 1 ? f->ws : f->dpf, stride, f->B);
+    BF_LAUNCH_CHECK();
+    if (S > 1) {
+        const size_t n = stride;
+        k_sum_partials<<<(unsigned)((n / 4 + 255) / 256), 256, 0, s>>>(f->ws, f->dpf, n, S);
+        BF_LAUNCH_CHECK();
+    }
+    return BF_OK;
+}

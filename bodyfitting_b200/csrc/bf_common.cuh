@@ -36,6 +36,14 @@ __host__ __device__ __forceinline__ ThetaLayout theta_layout(int is_smplx) {
     return t;
 }
 
+// round-to-nearest TF32 (10-bit mantissa, low 13 bits zero) and the exact fp32 remainder: x = hi + lo
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    hi = __uint_as_float(r);
+    lo = x - hi;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -123,6 +123,12 @@ __global__ void __launch_bounds__(128) k_pose_fwd(BfModel m, BfFrames f) {
         } else if (i < m.P + m.NS) v = S.sh[i - m.P];
         else if (i == m.P + m.NS) v = 1.0f;
         pf[i] = v;
+        if (f.pf_hi) {
+            float hi, lo;
+            split_tf32(v, hi, lo);
+            f.pf_hi[(size_t)b * m.Kp + i] = hi;
+            f.pf_lo[(size_t)b * m.Kp + i] = lo;
+        }
     }
     // A_j = [GR_j | Gt_j - GR_j Jr_j],  posed joints = Gt
     for (int j = lane; j < J; j += 32) {

@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(256) k_skin_fwd(BfVSet vs, int J, int Kp, cons
 #define DV_FB 4
 __global__ void __launch_bounds__(256) k_skin_bwd_dvp(BfVSet vs, int J, const float* __restrict__ A,
                                                       const float* __restrict__ dverts, float* __restrict__ dvp,
-                                                      int B, int ld_v) {
+                                                      int B, int ld_v, float* __restrict__ dvp_hi, float* __restrict__ dvp_lo) {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= vs.n) return;
     const int nnz = vs.nnz;
@@ -158,6 +158,11 @@ __global__ void __launch_bounds__(256) k_skin_bwd_dvp(BfVSet vs, int J, const fl
         o[0] = T[0] * gx + T[3] * gy + T[6] * gz;
         o[1] = T[1] * gx + T[4] * gy + T[7] * gz;
         o[2] = T[2] * gx + T[5] * gy + T[8] * gz;
+        if (dvp_hi) {                      // 3xTF32 operand split for the tensor-core backward GEMM
+            float* oh = dvp_hi + (size_t)b * vs.ldn + 3 * v;
+            float* ol = dvp_lo + (size_t)b * vs.ldn + 3 * v;
+            split_tf32(o[0], oh[0], ol[0]); split_tf32(o[1], oh[1], ol[1]); split_tf32(o[2], oh[2], ol[2]);
+        }
     }
 }
 

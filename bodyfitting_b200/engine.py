@@ -42,6 +42,10 @@ class FrameBuffers(object):
 
         buf('theta', B, NP, zero=True)
         buf('pf', B, Kp)
+        tc = model.tensor_cores
+        if tc:
+            buf('pf_hi', B, Kp)
+            buf('pf_lo', B, Kp)
         buf('A', B, J, 12)
         buf('Jtr', B, J, 3)
         buf('full_pose', B, 3 * J)
@@ -59,6 +63,13 @@ class FrameBuffers(object):
             buf('vposed', B, self.ld_v)
             buf('dverts', B, self.ld_v, zero=True)
             buf('dvp', B, self.ld_v)
+            if tc:                                 # 3xTF32 split of dvp, TMA-friendly padded rows, pad stays 0
+                ldn = 3 * model.n_pad_full if full else model.ld_act
+                buf('dvp_hi', B, ldn, zero=True)
+                buf('dvp_lo', B, ldn, zero=True)
+                nsplit = (ldn // 32 + 63) // 64
+                if nsplit > 1:
+                    buf('ws', nsplit, B, Kp)
             buf('loss_terms', B, 4, zero=True)
         if n_trace:
             buf('trace', n_trace, B, zero=True)
@@ -67,6 +78,8 @@ class FrameBuffers(object):
         for name, ten in t.items():
             setattr(s, name, ten.data_ptr())
         s.B, s.Nv, s.ld_v, s.iter = self.B, int(Nv), self.ld_v, 0
+        s.flags = _lib.F_TC if tc else 0
+        s.ws_floats = t['ws'].numel() if 'ws' in t else 0
         s.imsize, s.constant_scale, s.sigma = float(imsize), float(constant_scale), K.GMOF_SIGMA
         s.w_pose, s.w_angle, s.w_shape = K.POSE_PRIOR_WEIGHT, K.ANGLE_PRIOR_WEIGHT, K.SHAPE_PRIOR_WEIGHT
         s.lr_ts, s.lr = K.LR_TRANSL_SCALE, K.LR_DEFAULT
@@ -132,7 +145,8 @@ class FitSession(object):
         self.full_pose = torch.empty(B, 3 * model.J, device=dev)
         self.dense_every_iter = bool(dense_every_iter)
         c = min(int(chunk), self.B)
-        scratch = dict(pf=torch.empty(c, model.Kp, device=dev), A=torch.empty(c, model.J, 12, device=dev),
+        scratch = dict(pf=torch.empty(c, model.Kp, device=dev), pf_hi=torch.empty(c, model.Kp, device=dev),
+                       pf_lo=torch.empty(c, model.Kp, device=dev), A=torch.empty(c, model.J, 12, device=dev),
                        Jtr=torch.empty(c, model.J, 3, device=dev), yaw=torch.zeros(c, dtype=torch.int32, device=dev),
                        loss=torch.zeros(c, device=dev))
         if not return_vertices:
@@ -145,7 +159,7 @@ class FitSession(object):
             if return_vertices:
                 ext['verts'] = self.verts[lo:hi].view(hi - lo, -1)
             fbf = FrameBuffers(model, hi - lo, full=True, need_backward=False, ext=ext)
-            fbf.struct.flags = _lib.F_WORLD
+            fbf.struct.flags |= _lib.F_WORLD
             self.chunks.append(fbf)
         self.kernel_launches = 0
 

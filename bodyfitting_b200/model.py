@@ -34,6 +34,15 @@ def _round_up(x, m):
     return (x + m - 1) // m * m
 
 
+def split_tf32(x):
+    """x = hi + lo with hi the round-to-nearest TF32 value (low 13 mantissa bits zero, what
+    ``cvt.rna.tf32.f32`` produces) and lo the exact fp32 remainder: operands of the 3xTF32 GEMMs."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    u = x.view(np.uint32)
+    hi = ((u + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
+    return hi, (x - hi).astype(np.float32)
+
+
 def load_model_data(path_or_dict, model_type=None, gender='neutral'):
     """Accepts a dict (e.g. synthetic.make_model) or a path: a ``.npz``/``.pkl`` file, or a
     folder laid out like the reference's ``data/`` (data/smpl/SMPL_NEUTRAL.npz ...)."""
@@ -63,10 +72,13 @@ class PreparedModel(object):
     """numpy tables -> device tensors -> BfModel struct (kept alive by this object)."""
 
     def __init__(self, smpl_type, data, gmm=None, J_regressor_extra=None, device='cuda', num_betas=10,
-                 num_expression=10):
+                 num_expression=10, tensor_cores=None):
         assert smpl_type in ('smpl', 'smplx')
         self.smpl_type = smpl_type
         self.is_smplx = smpl_type == 'smplx'
+        if tensor_cores is None:                     # BODYFIT_TC=0 selects the FP32 FFMA contraction kernels
+            tensor_cores = os.environ.get('BODYFIT_TC', '1') != '0'
+        self.tensor_cores = bool(tensor_cores)
         self.device = torch.device(device)
         data = load_model_data(data, smpl_type)
         self.faces = np.asarray(data['f']).astype(np.int64)
@@ -191,6 +203,7 @@ class PreparedModel(object):
                          max_depth=self.max_depth, K_used=K_used, n_gmm=self.n_gmm).items():
             setattr(self.struct, k, v)
         self.n_act = int(act_h['n'])
+        self.n_pad_full = int(full_h['n_pad'])
         self.ld_act = 3 * int(act_h['n_pad'])
         self.K_out_act = int(act_h['K_out'])
         self._host = None
@@ -297,6 +310,9 @@ class PreparedModel(object):
                  tg_k=pad1([e[1] for e in entries], np.int32), tg_a=pad1([e[2] for e in entries], np.int32),
                  tg_w=pad1([e[3] for e in entries], np.float32),
                  n=n, n_pad=n_pad, ldn=3 * n_pad, nnz=nnz, K_out=K_out, n_dyn=n_dyn, n_extra=n_extra)
+        if self.tensor_cores:
+            h['Bm_hi'], h['Bm_lo'] = split_tf32(Bm)
+            h['Bt_hi'], h['Bt_lo'] = split_tf32(np.ascontiguousarray(Bm.T))
         if dyn_src is not None and any(kind == 2 for kind, _, _ in table):
             h['dyn_src'] = np.ascontiguousarray(dyn_src)
             h['dyn_w'] = np.ascontiguousarray(dyn_w)

@@ -40,8 +40,9 @@ extern "C" {
 #define BF_ECUDA    -2   /* a CUDA runtime call / launch failed            */
 #define BF_EARCH    -3   /* device is not sm_100 (no fallback exists)      */
 
-#define BF_ABI_VERSION 4
-#define BF_F_WORLD 1
+#define BF_ABI_VERSION 6
+#define BF_F_WORLD 1   /* forward outputs in world space: (x + transl) * scale * constant_scale */
+#define BF_F_TC    2   /* run the blend-shape contractions on tcgen05 tensor cores (3xTF32) */
 
 /* A vertex set: either all V vertices of the model or the compacted "active" subset
  * that the keypoint loss can touch.  All index tables refer to positions in this set. */
@@ -64,6 +65,10 @@ typedef struct BfVSet {
     const int32_t* xr_ptr;    /* [n_extra+1] CSR of the extra joint regressor (models/smpl.py:62-65,72) or NULL */
     const int32_t* xr_vid;
     const float*   xr_w;
+    const float*   Bt_hi;     /* [ldn, Kp] Bm^T split for 3xTF32: tf32-rounded part ... */
+    const float*   Bt_lo;     /* ... and the fp32 remainder (forward GEMM B operand, K-major) */
+    const float*   Bm_hi;     /* [Kp, ldn] the same split of Bm (backward GEMM B operand, K-major) */
+    const float*   Bm_lo;
     int32_t n, n_pad, ldn, nnz, K_out, n_dyn, n_extra, _pad0;
 } BfVSet;
 
@@ -111,6 +116,12 @@ typedef struct BfFrames {
     float*       loss;       /* [B] per-frame total loss of this iteration */
     float*       loss_terms; /* [B,4] data, pose prior, angle prior, shape prior (optional) */
     float*       trace;      /* [n_iters,B] optional per-iteration loss trace */
+    float*       pf_hi;      /* [B,Kp]  3xTF32 split of pf (BF_F_TC) */
+    float*       pf_lo;
+    float*       dvp_hi;     /* [B,ldn] 3xTF32 split of dvp, row stride = ldn of the vertex set, pad columns 0 */
+    float*       dvp_lo;
+    float*       ws;         /* split-K workspace of the tensor-core backward GEMM (>= ceil(ldn/2048) * B * Kp floats) or NULL */
+    int64_t      ws_floats;
     double lr_ts, lr, beta1, beta2, eps;   /* Adam hyper-parameters (python floats in the reference: smplify.py:167-174) */
     int32_t B, Nv, ld_v, iter;
     int32_t flags, _pad0;      /* BF_F_WORLD: skin/joints forward write (x + transl) * scale * constant_scale (smplify.py:189-190) */
