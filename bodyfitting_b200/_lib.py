@@ -10,7 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libbodyfit_b200.so')
-ABI_VERSION = 6
+ABI_VERSION = 8
 F_WORLD = 1
 F_TC = 2
 
@@ -21,14 +21,14 @@ _i32 = C.c_int32
 class BfVSet(C.Structure):
     _fields_ = [(n, _fp) for n in (
         'Bm', 'ell_j', 'ell_w', 'jv_ptr', 'jv_vid', 'jv_w', 'kj_kind', 'kj_src', 'kj_w',
-        'dyn_src', 'dyn_w', 'tg_ptr', 'tg_k', 'tg_a', 'tg_w', 'xr_ptr', 'xr_vid', 'xr_w', 'Bt_hi', 'Bt_lo', 'Bm_hi', 'Bm_lo')] + \
-        [(n, _i32) for n in ('n', 'n_pad', 'ldn', 'nnz', 'K_out', 'n_dyn', 'n_extra', '_pad0')]
+        'dyn_src', 'dyn_w', 'tg_ptr', 'tg_k', 'tg_a', 'tg_w', 'xr_ptr', 'xr_vid', 'xr_w', 'Bt_hi', 'Bt_lo', 'Bm_hi', 'Bm_lo', 'dyn_k', 'jv_nz')] + \
+        [(n, _i32) for n in ('n', 'n_pad', 'ldn', 'nnz', 'K_out', 'n_dyn', 'n_extra', 'n_nz')]
 
 
 class BfModel(C.Structure):
     _fields_ = [(n, _fp) for n in (
         'parents', 'depth', 'child_ptr', 'child_idx', 'Jt', 'Jd', 'pose_mean', 'hand_l', 'hand_r',
-        'gmm_mean', 'gmm_prec', 'gmm_prec_t', 'gmm_logw')] + \
+        'gmm_mean', 'gmm_psym', 'gmm_logw')] + \
         [('full', BfVSet), ('act', BfVSet)] + \
         [(n, _i32) for n in ('J', 'P', 'NS', 'NB', 'Kp', 'NP', 'is_smplx', 'max_depth', 'K_used',
                              'n_gmm', '_pad0', '_pad1')]
@@ -38,7 +38,7 @@ class BfFrames(C.Structure):
     _fields_ = [(n, _fp) for n in (
         'theta', 'grad', 'adam_m', 'adam_v', 'pf', 'dpf', 'A', 'dA', 'Jtr', 'dJtr', 'full_pose', 'yaw',
         'verts', 'vposed', 'dverts', 'dvp', 'joints', 'djoints', 'kp', 'cams', 'loss', 'loss_terms', 'trace',
-        'pf_hi', 'pf_lo', 'dvp_hi', 'dvp_lo', 'ws')] + [('ws_floats', C.c_int64)] + \
+        'pf_hi', 'pf_lo', 'dvp_hi', 'dvp_lo', 'gmm_grad', 'gmm_loss', 'ws')] + [('ws_floats', C.c_int64)] + \
         [(n, C.c_double) for n in ('lr_ts', 'lr', 'beta1', 'beta2', 'eps')] + \
         [(n, _i32) for n in ('B', 'Nv', 'ld_v', 'iter', 'flags', '_pad0')] + \
         [(n, C.c_float) for n in ('imsize', 'constant_scale', 'sigma', 'w_pose', 'w_angle', 'w_shape')]
@@ -74,7 +74,7 @@ def lib():
     pm, pf, vp, ci = C.POINTER(BfModel), C.POINTER(BfFrames), C.c_void_p, C.c_int
     for name, extra in (('bf_pose_forward', []), ('bf_skin_forward', [ci]), ('bf_joints_forward', [ci]),
                         ('bf_joints_backward', [ci, ci]), ('bf_keypoint_loss', [ci]), ('bf_skin_backward', [ci]), ('bf_skin_backward_parts', [ci, ci]),
-                        ('bf_pose_backward', [ci]), ('bf_lbs_forward', []), ('bf_lbs_backward', []),
+                        ('bf_pose_backward', [ci]), ('bf_gmm_prior', []), ('bf_frame_loss_backward', []), ('bf_lbs_forward', []), ('bf_lbs_backward', []),
                         ('bf_fit_step', []), ('bf_fit_run', [ci])):
         fn = getattr(L, name)
         fn.restype = C.c_int
@@ -85,7 +85,7 @@ def lib():
 
 EXPORTED = ['bf_abi_version', 'bf_sizeof', 'bf_last_error', 'bf_check_device', 'bf_pose_forward', 'bf_skin_forward',
             'bf_joints_forward', 'bf_joints_backward', 'bf_keypoint_loss', 'bf_skin_backward', 'bf_skin_backward_parts',
-            'bf_pose_backward', 'bf_lbs_forward', 'bf_lbs_backward', 'bf_fit_step', 'bf_fit_run']
+            'bf_pose_backward', 'bf_gmm_prior', 'bf_frame_loss_backward', 'bf_lbs_forward', 'bf_lbs_backward', 'bf_fit_step', 'bf_fit_run']
 
 
 def check(rc, what=''):

@@ -8,6 +8,8 @@
 #include "bf_pose.cuh"
 #include "bf_skin.cuh"
 #include "bf_loss.cuh"
+#include "bf_gmm.cuh"
+#include "bf_frame.cuh"
 #include "bf_blend_tc.cuh"
 
 static thread_local char g_err[512] = "";
@@ -151,10 +153,26 @@ int bf_skin_backward(const BfModel* m, const BfFrames* f, int use_full, void* st
     return bf_skin_backward_parts(m, f, use_full, 7, stream);
 }
 
+int bf_gmm_prior(const BfModel* m, const BfFrames* f, void* stream) {
+    int rc = check_model(m, f); if (rc) return rc;
+    BF_REQUIRE(m->gmm_mean && m->gmm_psym && m->gmm_logw && m->n_gmm > 0, "GMM tables missing");
+    BF_REQUIRE(f->gmm_grad && f->gmm_loss, "gmm_grad / gmm_loss is null");
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(k_gmm_prior, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GmmSmem));
+        if (e != cudaSuccess) { bf_set_error("cudaFuncSetAttribute(k_gmm_prior): %s", cudaGetErrorString(e)); return BF_ECUDA; }
+        attr = true;
+    }
+    k_gmm_prior<<<(f->B + GM_F - 1) / GM_F, GM_F * GM_PARTS, sizeof(GmmSmem), (cudaStream_t)stream>>>(*m, *f);
+    BF_LAUNCH_CHECK();
+    return BF_OK;
+}
+
 int bf_pose_backward(const BfModel* m, const BfFrames* f, int flags, void* stream) {
     int rc = check_model(m, f); if (rc) return rc;
     BF_REQUIRE(f->dA && f->dJtr && f->dpf && f->grad && f->loss, "pose backward buffers missing");
-    if (flags & 1) BF_REQUIRE(m->gmm_mean && m->gmm_prec && m->gmm_prec_t && m->gmm_logw && m->n_gmm > 0, "GMM tables missing");
+    if (flags & 1) BF_REQUIRE(f->gmm_grad && f->gmm_loss, "gmm_grad / gmm_loss missing (run bf_gmm_prior first)");
+    if (flags & 8) BF_REQUIRE((flags & 2) && f->pf && f->A && f->Jtr, "flag 8 needs the Adam step and the forward buffers");
     if (flags & 2) BF_REQUIRE(f->adam_m && f->adam_v, "Adam state missing");
     // bias corrections in double on the host, exactly as torch.optim.Adam does for python-float steps
     const double t = (double)(f->iter + 1);
@@ -189,19 +207,51 @@ int bf_lbs_backward(const BfModel* m, const BfFrames* f, void* stream) {
     return bf_pose_backward(m, f, 0, stream);
 }
 
-int bf_fit_step(const BfModel* m, const BfFrames* f, void* stream) {
-    int rc = bf_pose_forward(m, f, stream); if (rc) return rc;
+int bf_frame_loss_backward(const BfModel* m, const BfFrames* f, void* stream) {
+    int rc = check_model(m, f); if (rc) return rc;
+    const BfVSet* vs = &m->act;
+    rc = check_vset(vs, f); if (rc) return rc;
+    BF_REQUIRE(f->kp && f->cams && f->loss && f->grad && f->dJtr && f->verts && f->vposed && f->Jtr && f->A && f->dA,
+               "fused loss/backward buffers missing");
+    BF_REQUIRE(f->dvp_hi || f->dvp, "dvp (or its 3xTF32 split) missing");
+    BF_REQUIRE(f->Nv > 0 && f->Nv <= BF_MAXVIEWS, "Nv out of range");
+    BF_REQUIRE(vs->jv_ptr && vs->jv_vid && vs->jv_w && vs->jv_nz, "joint->vertex lists missing");
+    const size_t smem = sizeof(float) * (BF_MAXK * 6 + BF_MAXVIEWS * 12 + 64 + ((m->J * 12 + 15) & ~15) + 2 * (size_t)vs->ldn);
+    BF_REQUIRE(smem <= 48 * 1024, "active vertex set too large for the fused per-frame kernel");
+    BfFrames g = *f;
+    if (!bf_tc_ready_bwd(vs, f)) { g.dvp_hi = nullptr; g.dvp_lo = nullptr; }
+    k_frame_loss_bwd<<<f->B, FR_THREADS, smem, (cudaStream_t)stream>>>(*m, *vs, g);
+    BF_LAUNCH_CHECK();
+    return BF_OK;
+}
+
+static int fit_iteration(const BfModel* m, const BfFrames* f, bool with_forward, bool fuse_next, void* stream) {
+    int rc;
+    if (with_forward) { rc = bf_pose_forward(m, f, stream); if (rc) return rc; }
     rc = bf_skin_forward(m, f, 0, stream); if (rc) return rc;
-    rc = bf_keypoint_loss(m, f, 0, stream); if (rc) return rc;
-    rc = bf_skin_backward(m, f, 0, stream); if (rc) return rc;
-    return bf_pose_backward(m, f, 1 | 2 | 4, stream);
+    const size_t fused_smem = sizeof(float) * (BF_MAXK * 6 + BF_MAXVIEWS * 12 + 64 + ((m->J * 12 + 15) & ~15) + 2 * (size_t)m->act.ldn);
+    if (fused_smem <= 48 * 1024) {
+        rc = bf_frame_loss_backward(m, f, stream); if (rc) return rc;          // loss + dverts (on chip) + dvp + dA
+        rc = bf_gmm_prior(m, f, stream); if (rc) return rc;
+        rc = bf_skin_backward_parts(m, f, 0, 4, stream); if (rc) return rc;    // dpf = dvp @ Bm^T
+    } else {
+        rc = bf_keypoint_loss(m, f, 0, stream); if (rc) return rc;
+        rc = bf_gmm_prior(m, f, stream); if (rc) return rc;
+        rc = bf_skin_backward(m, f, 0, stream); if (rc) return rc;
+    }
+    return bf_pose_backward(m, f, 1 | 2 | 4 | (fuse_next ? 8 : 0), stream);
+}
+
+int bf_fit_step(const BfModel* m, const BfFrames* f, void* stream) {
+    return fit_iteration(m, f, true, false, stream);
 }
 
 int bf_fit_run(const BfModel* m, const BfFrames* f, int n_iters, void* stream) {
     BF_REQUIRE(m && f && n_iters >= 0, "bad arguments");
     BfFrames g = *f;
     for (int i = 0; i < n_iters; ++i) {
-        int rc = bf_fit_step(m, &g, stream); if (rc) return rc;
+        // the pose-backward kernel of iteration i also runs the pose forward of iteration i+1
+        int rc = fit_iteration(m, &g, i == 0, i + 1 < n_iters, stream); if (rc) return rc;
         g.iter++;
     }
     return BF_OK;

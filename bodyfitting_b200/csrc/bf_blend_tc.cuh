@@ -210,6 +210,9 @@ __global__ void __launch_bounds__(192, 1) k_skin_fwd_tc(const __grid_constant__ 
             if (v < vs.n) {
                 const int32_t* ej = vs.ell_j + (size_t)v * nnz;
                 const float* ew = vs.ell_w + (size_t)v * nnz;
+                int jo[4]; float jw[4];                      // first 4 influences in registers (SMPL / SMPL-X: nnz = 4)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { jo[k] = (k < nnz) ? __ldg(ej + k) * 12 : 0; jw[k] = (k < nnz) ? __ldg(ew + k) : 0.f; }
                 for (int fr = 0; fr < 32; ++fr) {
                     const int b = b0 + 32 * q + fr;
                     if (b >= B) break;
@@ -219,7 +222,16 @@ __global__ void __launch_bounds__(192, 1) k_skin_fwd_tc(const __grid_constant__ 
 #pragma unroll
                     for (int e = 0; e < 12; ++e) T[e] = 0.f;
                     const float* Ab = A + (size_t)b * J * 12;
-                    for (int k = 0; k < nnz; ++k) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float w = jw[k];
+                        const float4* Aj = reinterpret_cast<const float4*>(Ab + jo[k]);
+                        const float4 r0 = __ldg(Aj), r1 = __ldg(Aj + 1), r2 = __ldg(Aj + 2);
+                        T[0] = fmaf(w, r0.x, T[0]); T[1] = fmaf(w, r0.y, T[1]); T[2] = fmaf(w, r0.z, T[2]); T[3] = fmaf(w, r0.w, T[3]);
+                        T[4] = fmaf(w, r1.x, T[4]); T[5] = fmaf(w, r1.y, T[5]); T[6] = fmaf(w, r1.z, T[6]); T[7] = fmaf(w, r1.w, T[7]);
+                        T[8] = fmaf(w, r2.x, T[8]); T[9] = fmaf(w, r2.y, T[9]); T[10] = fmaf(w, r2.z, T[10]); T[11] = fmaf(w, r2.w, T[11]);
+                    }
+                    for (int k = 4; k < nnz; ++k) {
                         const float w = __ldg(ew + k);
                         const float4* Aj = reinterpret_cast<const float4*>(Ab + __ldg(ej + k) * 12);
                         const float4 r0 = __ldg(Aj), r1 = __ldg(Aj + 1), r2 = __ldg(Aj + 2);

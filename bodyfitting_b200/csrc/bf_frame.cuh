@@ -1,0 +1,220 @@
+// Fused per-frame backward of the fitting loop on the active vertex set (one CTA per frame):
+//
+//   keypoint term (joints -> world -> multi-view projection -> GMoF, smplify/loss.py:22-51,132-203)
+//   -> gradient w.r.t. transl / scale / model joints -> gather by target into d(verts) kept in
+//   SHARED memory -> skinning backward for the frame: dvp = T_v^T dverts_v (written as the 3xTF32
+//   operand split for the tensor-core blend backward) and dA[j] = sum_v w_vj dverts_v (x) [vposed_v; 1].
+//
+// Fusing the three steps keeps d(verts), v_posed and the frame's joint transforms on chip: the
+// d(verts) round trip through HBM and two launches of the unfused path (k_keypoint_loss,
+// k_skin_bwd_dvp, k_skin_bwd_dA -- still used for the all-vertex operator backward) disappear.
+#pragma once
+#include "bf_common.cuh"
+#include "bf_loss.cuh"
+
+#define FR_THREADS 256
+
+
+// sum over the 32 lanes of 16 values at once with 16 shuffles (instead of 16 x 5): after the call the
+// lane holds the total of element e = 8*bit4 + 4*bit3 + 2*bit2 + bit1 of its lane id (fixed tree).
+__device__ __forceinline__ float warp_reduce16(const float* v, int lane) {
+    float a[8], b[4], c[2];
+    bool hi = lane & 16;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float recv = __shfl_xor_sync(0xffffffffu, hi ? v[i] : v[i + 8], 16);
+        a[i] = (hi ? v[i + 8] : v[i]) + recv;
+    }
+    hi = lane & 8;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float recv = __shfl_xor_sync(0xffffffffu, hi ? a[i] : a[i + 4], 8);
+        b[i] = (hi ? a[i + 4] : a[i]) + recv;
+    }
+    hi = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float recv = __shfl_xor_sync(0xffffffffu, hi ? b[i] : b[i + 2], 4);
+        c[i] = (hi ? b[i + 2] : b[i]) + recv;
+    }
+    hi = lane & 2;
+    float d = (hi ? c[1] : c[0]) + __shfl_xor_sync(0xffffffffu, hi ? c[0] : c[1], 2);
+    d += __shfl_xor_sync(0xffffffffu, d, 1);
+    return d;
+}
+
+__global__ void __launch_bounds__(FR_THREADS) k_frame_loss_bwd(BfModel m, BfVSet vs, BfFrames f) {
+    extern __shared__ __align__(16) float sm[];
+    float* gx = sm;                               // [BF_MAXK*3] joint gradients
+    float* cam = gx + BF_MAXK * 3;                // [BF_MAXVIEWS*12]
+    float* red = cam + BF_MAXVIEWS * 12;          // [5*8]
+    float* jq = red + 64;                         // [BF_MAXK*3] joint positions + translation
+    float* As = jq + BF_MAXK * 3;                 // [J*12] this frame's joint transforms
+    float* dv = As + ((m.J * 12 + 15) & ~15);     // [3*n_pad] d(verts)
+    float* vp = dv + vs.ldn;                      // [3*n_pad] v_posed
+    const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int K = m.K_used, Nv = f.Nv, J = m.J;
+    for (int i = t; i < Nv * 12; i += FR_THREADS) cam[i] = f.cams[i];
+    for (int i = t; i < J * 12; i += FR_THREADS) As[i] = f.A[(size_t)b * J * 12 + i];
+    for (int i = t; i < 3 * vs.n; i += FR_THREADS) vp[i] = f.vposed[(size_t)b * f.ld_v + i];
+    __syncthreads();
+    const float* th = f.theta + (size_t)b * m.NP;
+    const float tx = th[0], ty = th[1], tz = th[2], sc = th[3];
+    const float cs = f.constant_scale;
+    const float coef = f.imsize / 1024.0f;
+    const float s2 = f.sigma * f.sigma;
+    const int yaw = f.yaw ? f.yaw[b] : 0;
+    const float* Jtr_b = f.Jtr + (size_t)b * J * 3;
+    const float* verts_b = f.verts + (size_t)b * f.ld_v;
+    const float invNv = 1.0f / (float)Nv;
+
+    // joint positions of this frame -> shared (model space + translation, i.e. q = x + T)
+    for (int k = t; k < K; k += FR_THREADS) {
+        float x[3];
+        joint_pos(vs, k, yaw, Jtr_b, verts_b, x);
+        jq[k * 3] = x[0] + tx; jq[k * 3 + 1] = x[1] + ty; jq[k * 3 + 2] = x[2] + tz;
+    }
+    __syncthreads();
+    // (joint, view) pairs: G lanes share a joint and split its views, then reduce over the G lanes
+    int G = 1;
+    while (G * 2 <= Nv && G < 8) G *= 2;
+    const int sub = lane & (G - 1);
+    const int jpw = 32 / G;                                  // joints per warp per pass
+    float acc5[5] = {0.f, 0.f, 0.f, 0.f, 0.f};               // loss, d/d transl (3), d/d scale
+    for (int k0 = 0; k0 < K; k0 += jpw * (FR_THREADS / 32)) {
+        const int k = k0 + warp * jpw + lane / G;
+        const bool kv = k < K;
+        const int kk = kv ? k : K - 1;
+        const float qx = jq[kk * 3], qy = jq[kk * 3 + 1], qz = jq[kk * 3 + 2];
+        const float X = qx * sc * cs, Y = qy * sc * cs, Z = qz * sc * cs;
+        float g0 = 0.f, g1 = 0.f, g2 = 0.f, ls = 0.f;
+        for (int v = sub; v < Nv; v += G) {
+            const float* kp = f.kp + (((size_t)b * Nv + v) * K + kk) * 3;
+            const float kx = kp[0], ky = kp[1], wgt = kp[2];
+            const float* M = cam + v * 12;
+            const float p0 = M[0] * X + M[1] * Y + M[2] * Z + M[3];
+            const float p1 = M[4] * X + M[5] * Y + M[6] * Z + M[7];
+            const float p2 = M[8] * X + M[9] * Y + M[10] * Z + M[11];
+            const float iz = 1.0f / p2;
+            const float u = p0 * iz, w_ = p1 * iz;
+            const float rx = (kx - u) / coef, ry = (ky - w_) / coef;
+            const float rx2 = rx * rx, ry2 = ry * ry;
+            const float dx = s2 + rx2, dy = s2 + ry2;
+            ls += wgt * ((s2 * rx2) / dx + (s2 * ry2) / dy);
+            const float du = wgt * (2.0f * s2 * s2 * rx / (dx * dx)) * (-1.0f / coef);
+            const float dw = wgt * (2.0f * s2 * s2 * ry / (dy * dy)) * (-1.0f / coef);
+            const float dp0 = du * iz, dp1 = dw * iz, dp2 = -(du * u + dw * w_) * iz;
+            g0 += M[0] * dp0 + M[4] * dp1 + M[8] * dp2;
+            g1 += M[1] * dp0 + M[5] * dp1 + M[9] * dp2;
+            g2 += M[2] * dp0 + M[6] * dp1 + M[10] * dp2;
+        }
+        for (int o = G >> 1; o > 0; o >>= 1) {               // fixed butterfly over the G view lanes
+            g0 += __shfl_xor_sync(0xffffffffu, g0, o);
+            g1 += __shfl_xor_sync(0xffffffffu, g1, o);
+            g2 += __shfl_xor_sync(0xffffffffu, g2, o);
+            ls += __shfl_xor_sync(0xffffffffu, ls, o);
+        }
+        if (kv && sub == 0) {
+            g0 *= invNv; g1 *= invNv; g2 *= invNv;
+            const float k0s = sc * cs;
+            gx[k * 3] = g0 * k0s; gx[k * 3 + 1] = g1 * k0s; gx[k * 3 + 2] = g2 * k0s;
+            acc5[0] += ls;
+            acc5[1] += g0 * k0s; acc5[2] += g1 * k0s; acc5[3] += g2 * k0s;
+            acc5[4] += (g0 * qx + g1 * qy + g2 * qz) * cs;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        const float s = warp_sum(acc5[i]);
+        if (lane == 0) red[i * 8 + warp] = s;
+    }
+    __syncthreads();                               // gx + red complete
+    if (t == 0) {
+        float tot[5];
+        for (int i = 0; i < 5; ++i) { float s = 0.f; for (int w = 0; w < FR_THREADS / 32; ++w) s += red[i * 8 + w]; tot[i] = s; }
+        f.loss[b] = tot[0] * invNv;
+        float* g = f.grad + (size_t)b * m.NP;
+        g[0] = tot[1]; g[1] = tot[2]; g[2] = tot[3]; g[3] = tot[4];
+    }
+    scatter_by_target(vs, J, K, yaw, gx, f.dJtr + (size_t)b * J * 3, dv, 0);
+    __syncthreads();
+
+    // skinning backward, vertex side: dvp = (sum_k w_k A_jk)[:3,:3]^T dverts
+    const bool split = f.dvp_hi != nullptr;
+    for (int v = t; v < vs.n; v += FR_THREADS) {
+        const int nnz = vs.nnz;
+        const int32_t* ej = vs.ell_j + (size_t)v * nnz;
+        const float* ew = vs.ell_w + (size_t)v * nnz;
+        float T[9];
+#pragma unroll
+        for (int e = 0; e < 9; ++e) T[e] = 0.f;
+        for (int k = 0; k < nnz; ++k) {
+            const float w = __ldg(ew + k);
+            const float4* Aj = reinterpret_cast<const float4*>(As + __ldg(ej + k) * 12);
+            const float4 r0 = Aj[0], r1 = Aj[1], r2 = Aj[2];
+            T[0] = fmaf(w, r0.x, T[0]); T[1] = fmaf(w, r0.y, T[1]); T[2] = fmaf(w, r0.z, T[2]);
+            T[3] = fmaf(w, r1.x, T[3]); T[4] = fmaf(w, r1.y, T[4]); T[5] = fmaf(w, r1.z, T[5]);
+            T[6] = fmaf(w, r2.x, T[6]); T[7] = fmaf(w, r2.y, T[7]); T[8] = fmaf(w, r2.z, T[8]);
+        }
+        const float gx_ = dv[3 * v], gy_ = dv[3 * v + 1], gz_ = dv[3 * v + 2];
+        const float o0 = T[0] * gx_ + T[3] * gy_ + T[6] * gz_;
+        const float o1 = T[1] * gx_ + T[4] * gy_ + T[7] * gz_;
+        const float o2 = T[2] * gx_ + T[5] * gy_ + T[8] * gz_;
+        if (split) {
+            float* oh = f.dvp_hi + (size_t)b * vs.ldn + 3 * v;
+            float* ol = f.dvp_lo + (size_t)b * vs.ldn + 3 * v;
+            split_tf32(o0, oh[0], ol[0]); split_tf32(o1, oh[1], ol[1]); split_tf32(o2, oh[2], ol[2]);
+        } else {
+            float* o = f.dvp + (size_t)b * f.ld_v + 3 * v;
+            o[0] = o0; o[1] = o1; o[2] = o2;
+        }
+    }
+    // skinning backward, joint side: dA[j] = sum_v w_vj dverts_v (x) [vposed_v; 1]
+    float* dAb = f.dA + (size_t)b * J * 12;
+    if (vs.n_nz < J)
+        for (int i = t; i < J * 12; i += FR_THREADS) dAb[i] = 0.f;
+    __syncthreads();
+    // 8 lanes per joint (skinning lists are short), 4 joints per warp at a time; the 12 (padded 16)
+    // partial sums are reduced over the 8 lanes with a multi-value butterfly: 14 shuffles per 4 joints
+    for (int jn0 = 0; jn0 < vs.n_nz; jn0 += 4 * (FR_THREADS / 32)) {
+        const int jn = jn0 + warp * 4 + (lane >> 3);
+        const bool jv_ = jn < vs.n_nz;
+        const int j = jv_ ? __ldg(vs.jv_nz + jn) : 0;
+        const int sl = lane & 7;
+        float acc[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) acc[e] = 0.f;
+        const int e0 = jv_ ? __ldg(vs.jv_ptr + j) : 0, e1 = jv_ ? __ldg(vs.jv_ptr + j + 1) : 0;
+        for (int e = e0 + sl; e < e1; e += 8) {
+            const int v = __ldg(vs.jv_vid + e);
+            const float w = __ldg(vs.jv_w + e);
+            const float gx_ = w * dv[3 * v], gy_ = w * dv[3 * v + 1], gz_ = w * dv[3 * v + 2];
+            const float px = vp[3 * v], py = vp[3 * v + 1], pz = vp[3 * v + 2];
+            acc[0] = fmaf(gx_, px, acc[0]); acc[1] = fmaf(gx_, py, acc[1]); acc[2] = fmaf(gx_, pz, acc[2]); acc[3] += gx_;
+            acc[4] = fmaf(gy_, px, acc[4]); acc[5] = fmaf(gy_, py, acc[5]); acc[6] = fmaf(gy_, pz, acc[6]); acc[7] += gy_;
+            acc[8] = fmaf(gz_, px, acc[8]); acc[9] = fmaf(gz_, py, acc[9]); acc[10] = fmaf(gz_, pz, acc[10]); acc[11] += gz_;
+        }
+        float a8[8], a4[4], a2[2];
+        bool hi = lane & 4;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float recv = __shfl_xor_sync(0xffffffffu, hi ? acc[i] : acc[i + 8], 4);
+            a8[i] = (hi ? acc[i + 8] : acc[i]) + recv;
+        }
+        hi = lane & 2;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float recv = __shfl_xor_sync(0xffffffffu, hi ? a8[i] : a8[i + 4], 2);
+            a4[i] = (hi ? a8[i + 4] : a8[i]) + recv;
+        }
+        hi = lane & 1;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const float recv = __shfl_xor_sync(0xffffffffu, hi ? a4[i] : a4[i + 2], 1);
+            a2[i] = (hi ? a4[i + 2] : a4[i]) + recv;
+        }
+        // this lane now holds elements el, el+1 of joint j
+        const int el = ((lane >> 2) & 1) * 8 + ((lane >> 1) & 1) * 4 + (lane & 1) * 2;
+        if (jv_ && el < 12) { dAb[j * 12 + el] = a2[0]; dAb[j * 12 + el + 1] = a2[1]; }
+    }
+}

@@ -1,0 +1,92 @@
+// GMM pose prior (smplify/prior.py:181-196, MaxMixturePrior.merged_log_likelihood) for all
+// frames: min over 8 components of 0.5 d^T P_m d - log(nll_w_m), d = pose69 - mu_m, and the
+// gradient of the winning component.
+//
+// 32 frames per CTA, lane = frame, 4 warps = 4 row ranges of the 69x69 precision matrix.  The
+// symmetrised precision P_sym = (P + P^T)/2 of the current component sits in shared memory
+// (double buffered, next component prefetched while computing) and every lane of a warp walks
+// the same rows in the same order, so each LDS.128 is a warp-wide broadcast feeding 4 FFMAs per
+// thread; the per-frame vector d lives in registers.  With P_sym, y = P_sym d is at once the
+// gradient (0.5 (P + P^T) d, what autograd of the reference produces) and gives the quadratic
+// form d.y = d^T P d.  The gradient of the best component so far is kept in a per-frame
+// shared-memory column (two buffers, swapped when a better component is found): no second
+// pass, no divergence.
+#pragma once
+#include "bf_common.cuh"
+
+#define GM_F 32                 // frames per CTA (lane = frame)
+#define GM_PARTS 4              // warps per CTA, each owns a range of rows
+#define GM_D BF_GMM_D           // 69
+#define GM_LD 72                // padded row length of P_sym (float4 rows, pad = 0)
+#define GM_ROWS 18              // rows per part (4 * 18 >= 69)
+
+struct GmmSmem {
+    float P[2][GM_D * GM_LD];   // double-buffered P_sym of one component
+    float g[2][GM_D][GM_F];     // gradient candidates, column per frame
+    float x[GM_D][GM_F];        // pose vector, column per frame
+    float mu[2][GM_LD];
+    float qp[GM_PARTS][GM_F];   // partial quadratic forms
+};
+
+__global__ void __launch_bounds__(GM_F * GM_PARTS) k_gmm_prior(BfModel m, BfFrames f) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    GmmSmem& S = *reinterpret_cast<GmmSmem*>(smem_raw);
+    const int t = threadIdx.x, lane = t & 31, part = t >> 5;
+    const int b = blockIdx.x * GM_F + lane;
+    const bool valid = b < f.B;
+    const int nbody = theta_layout(m.is_smplx).nbody;
+    const float* th = f.theta + (size_t)(valid ? b : f.B - 1) * m.NP + 7;
+    for (int j = part; j < GM_D; j += GM_PARTS) S.x[j][lane] = (j < nbody) ? th[j] : 0.f;
+
+    auto load_comp = [&](int c, int buf) {
+        const float4* src = reinterpret_cast<const float4*>(m.gmm_psym + (size_t)c * GM_D * GM_LD);
+        float4* dst = reinterpret_cast<float4*>(S.P[buf]);
+        for (int i = t; i < GM_D * GM_LD / 4; i += GM_F * GM_PARTS) dst[i] = __ldg(src + i);
+        if (t < GM_LD) S.mu[buf][t] = (t < GM_D) ? __ldg(m.gmm_mean + c * GM_D + t) : 0.f;
+    };
+    load_comp(0, 0);
+    __syncthreads();
+
+    const int i0 = part * GM_ROWS;
+    const int i1 = min(GM_D, i0 + GM_ROWS);
+    float best = 0.f;
+    int bi = 0;                                      // buffer holding the gradient of the best component
+    for (int c = 0; c < m.n_gmm; ++c) {
+        const int cur = c & 1;
+        if (c + 1 < m.n_gmm) load_comp(c + 1, cur ^ 1);      // prefetch into the other buffer
+        float d[GM_LD];
+#pragma unroll
+        for (int j = 0; j < GM_LD; ++j) d[j] = (j < GM_D) ? S.x[j][lane] - S.mu[cur][j] : 0.f;
+        const int cand = bi ^ 1;
+        float q = 0.f;
+        const float* Pc = S.P[cur];
+#pragma unroll 1
+        for (int i = i0; i < i1; ++i) {
+            const float4* row = reinterpret_cast<const float4*>(Pc + i * GM_LD);
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+            for (int j4 = 0; j4 < GM_LD / 4; ++j4) {
+                const float4 p = row[j4];
+                a0 = fmaf(p.x, d[4 * j4 + 0], a0);
+                a1 = fmaf(p.y, d[4 * j4 + 1], a1);
+                a2 = fmaf(p.z, d[4 * j4 + 2], a2);
+                a3 = fmaf(p.w, d[4 * j4 + 3], a3);
+            }
+            const float y = (a0 + a1) + (a2 + a3);
+            S.g[cand][i][lane] = y;
+            q = fmaf(y, S.x[i][lane] - S.mu[cur][i], q);
+        }
+        S.qp[part][lane] = q;
+        __syncthreads();
+        const float qs = (S.qp[0][lane] + S.qp[1][lane]) + (S.qp[2][lane] + S.qp[3][lane]);
+        const float ll = 0.5f * qs - __ldg(m.gmm_logw + c);
+        if (c == 0 || ll < best) { best = ll; bi = cand; }      // identical decision in all four parts
+        __syncthreads();                             // qp / P[cur] may be overwritten from here on
+    }
+    const float wp = f.w_pose * f.w_pose;
+    if (valid) {
+        if (part == 0) f.gmm_loss[b] = wp * best;
+        float* o = f.gmm_grad + (size_t)b * GM_D;
+        for (int j = part; j < GM_D; j += GM_PARTS) o[j] = wp * S.g[bi][j][lane];
+    }
+}

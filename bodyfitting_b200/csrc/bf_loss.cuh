@@ -62,8 +62,7 @@ __device__ __forceinline__ void scatter_by_target(const BfVSet& vs, int J, int K
         const int e0 = __ldg(vs.tg_ptr + tg), e1 = __ldg(vs.tg_ptr + tg + 1);
         for (int e = e0; e < e1; ++e) {
             const int k = __ldg(vs.tg_k + e);
-            const int a = __ldg(vs.tg_a + e);
-            if (k < Klim && (a < 0 || a == yaw)) {
+            if (k < Klim) {
                 const float w = __ldg(vs.tg_w + e);
                 a0 += w * gx[k * 3]; a1 += w * gx[k * 3 + 1]; a2 += w * gx[k * 3 + 2];
             }
@@ -74,6 +73,24 @@ __device__ __forceinline__ void scatter_by_target(const BfVSet& vs, int J, int K
             float* o = dverts_b + (size_t)(tg - J) * 3;
             if (accumulate) { o[0] += a0; o[1] += a1; o[2] += a2; }
             else { o[0] = a0; o[1] = a1; o[2] = a2; }
+        }
+    }
+    // contour landmarks: their three source vertices depend on the frame's yaw row, so they are
+    // added after the static gather, slot by slot in a fixed order by one warp (deterministic,
+    // the three vertices of a face are distinct)
+    if (vs.n_dyn > 0) {
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            for (int s = 0; s < vs.n_dyn; ++s) {
+                const int k = __ldg(vs.dyn_k + s);
+                if (k < Klim && threadIdx.x < 3) {
+                    const size_t e = ((size_t)yaw * vs.n_dyn + s) * 3 + threadIdx.x;
+                    const float w = __ldg(vs.dyn_w + e);
+                    float* o = dverts_b + (size_t)__ldg(vs.dyn_src + e) * 3;
+                    o[0] += w * gx[k * 3]; o[1] += w * gx[k * 3 + 1]; o[2] += w * gx[k * 3 + 2];
+                }
+                __syncwarp();
+            }
         }
     }
 }

@@ -27,17 +27,24 @@ struct PoseSmemBwd {
     float dJr[BF_MAXJ * 3];
     float drel[BF_MAXJ * 3];
     float dfp[BF_MAXJ * 3];
-    float dm[BF_GMM_D + 3];
-    float x69[BF_GMM_D + 3];
+    float thn[BF_MAXNP];
 };
 
 // Fills S for frame b (all lanes of one warp participate).
+__device__ __forceinline__ void pose_forward_from_smem(const BfModel& m, PoseSmem& S, int lane);
+
 __device__ __forceinline__ void pose_forward_warp(const BfModel& m, const float* __restrict__ theta_row,
                                                   PoseSmem& S, int lane) {
+    const int np = theta_layout(m.is_smplx).np;
+    for (int i = lane; i < np; i += 32) S.th[i] = theta_row[i];
+    __syncwarp();
+    pose_forward_from_smem(m, S, lane);
+}
+
+// theta already in S.th
+__device__ __forceinline__ void pose_forward_from_smem(const BfModel& m, PoseSmem& S, int lane) {
     const ThetaLayout L = theta_layout(m.is_smplx);
     const int J = m.J;
-    for (int i = lane; i < L.np; i += 32) S.th[i] = theta_row[i];
-    __syncwarp();
     // full pose
     for (int i = lane; i < 3 * J; i += 32) {
         float v = 0.f;
@@ -71,7 +78,7 @@ __device__ __forceinline__ void pose_forward_warp(const BfModel& m, const float*
         for (int c = 0; c < 3; ++c) {
             float acc = 0.f;
             const float* jd = m.Jd + (j * 3 + c) * m.NS;
-            for (int l = 0; l < m.NS; ++l) acc += __ldg(jd + l) * S.sh[l];
+            for (int l = 0; l < m.NB; ++l) acc += __ldg(jd + l) * S.sh[l];     // sh[l] = 0 for l >= NB (expression)
             S.Jr[j * 3 + c] = __ldg(m.Jt + j * 3 + c) + acc;
         }
     }
@@ -103,16 +110,10 @@ __device__ __forceinline__ void pose_forward_warp(const BfModel& m, const float*
     }
 }
 
-__global__ void __launch_bounds__(128) k_pose_fwd(BfModel m, BfFrames f) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    PoseSmem* all = reinterpret_cast<PoseSmem*>(smem_raw);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.x * (blockDim.x >> 5) + warp;
-    if (b >= f.B) return;
-    PoseSmem& S = all[warp];
+// forward outputs of frame b from the state in S: GEMM A operand (+ 3xTF32 split), joint transforms,
+// posed joints, full pose, contour-landmark row
+__device__ __forceinline__ void pose_write_outputs(const BfModel& m, const BfFrames& f, PoseSmem& S, int b, int lane) {
     const int J = m.J;
-    pose_forward_warp(m, f.theta + (size_t)b * m.NP, S, lane);
-
     // GEMM A operand row: [R_1..R_{J-1} - I | shape | 1 | 0...]
     float* pf = f.pf + (size_t)b * m.Kp;
     for (int i = lane; i < m.Kp; i += 32) {
@@ -169,7 +170,19 @@ __global__ void __launch_bounds__(128) k_pose_fwd(BfModel m, BfFrames f) {
     }
 }
 
-// flags: 1 = priors, 2 = Adam, 4 = keep grad[0:4] written by the loss kernel (else zero them)
+__global__ void __launch_bounds__(128) k_pose_fwd(BfModel m, BfFrames f) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    PoseSmem* all = reinterpret_cast<PoseSmem*>(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (b >= f.B) return;
+    PoseSmem& S = all[warp];
+    pose_forward_warp(m, f.theta + (size_t)b * m.NP, S, lane);
+    pose_write_outputs(m, f, S, b, lane);
+}
+
+// flags: 1 = priors, 2 = Adam, 4 = keep grad[0:4] written by the loss kernel (else zero them),
+//        8 = after the Adam step also run the NEXT iteration's pose forward (saves a launch + a theta round trip)
 struct AdamArgs { float step_ts, step_lr, bc2_sqrt, beta2, om_beta1, om_beta2, eps; };
 
 __global__ void __launch_bounds__(128) k_pose_bwd(BfModel m, BfFrames f, int flags, AdamArgs ad) {
@@ -273,10 +286,16 @@ __global__ void __launch_bounds__(128) k_pose_bwd(BfModel m, BfFrames f, int fla
 
     float* g = f.grad + (size_t)b * m.NP;
     // betas: rest-joint path + shape rows of the blend GEMM
-    if (lane < m.NB) {
-        float acc = f.dpf[(size_t)b * m.Kp + m.P + lane];
-        for (int q = 0; q < 3 * J; ++q) acc += __ldg(m.Jd + q * m.NS + lane) * W.dJr[q];
-        g[L.off_betas + lane] = acc;
+    {
+        // lanes (l, part): 3 parts split the 3J rest-joint coordinates, combined in a fixed order
+        const int l = lane % m.NB, part = lane / m.NB;
+        const int nq = 3 * J, per = (nq + 2) / 3;
+        float acc = 0.f;
+        if (part < 3)
+            for (int q = part * per; q < min(nq, (part + 1) * per); ++q) acc += __ldg(m.Jd + q * m.NS + l) * W.dJr[q];
+        const float a1 = __shfl_sync(0xffffffffu, acc, (lane + m.NB) & 31);
+        const float a2 = __shfl_sync(0xffffffffu, acc, (lane + 2 * m.NB) & 31);
+        if (lane < m.NB) g[L.off_betas + lane] = f.dpf[(size_t)b * m.Kp + m.P + lane] + ((acc + a1) + a2);
     }
     for (int i = lane; i < 3 + L.nbody; i += 32) g[4 + i] = W.dfp[i];      // global_orient + body_pose
     if (m.is_smplx) {
@@ -295,42 +314,10 @@ __global__ void __launch_bounds__(128) k_pose_bwd(BfModel m, BfFrames f, int fla
 
     float total = (flags & 4) ? f.loss[b] : 0.f;
     if (flags & 1) {
-        // ---- GMM pose prior (merged likelihood, min over components) ----
-        for (int i = lane; i < BF_GMM_D; i += 32) W.x69[i] = (i < L.nbody) ? S.th[7 + i] : 0.f;
+        // ---- GMM pose prior: value and gradient come from k_gmm_prior (bf_gmm.cuh) ----
+        for (int i = lane; i < L.nbody; i += 32) g[7 + i] += f.gmm_grad[(size_t)b * BF_GMM_D + i];
+        const float pose_l = f.gmm_loss[b];
         __syncwarp();
-        float best = 0.f; int mbest = -1;
-        for (int c = 0; c < m.n_gmm; ++c) {
-            for (int i = lane; i < BF_GMM_D; i += 32) W.dm[i] = W.x69[i] - __ldg(m.gmm_mean + c * BF_GMM_D + i);
-            __syncwarp();
-            const float* Pm = m.gmm_prec_t + (size_t)c * BF_GMM_D * BF_GMM_D;   // Pm[j][i] = P[i][j]
-            float part = 0.f;
-            for (int i = lane; i < BF_GMM_D; i += 32) {
-                float acc = 0.f;                                               // (P d)_i
-                for (int j = 0; j < BF_GMM_D; ++j) acc += __ldg(Pm + j * BF_GMM_D + i) * W.dm[j];
-                part += acc * W.dm[i];
-            }
-            const float q = warp_sum(part);
-            const float ll = 0.5f * q - __ldg(m.gmm_logw + c);
-            if (mbest < 0 || ll < best) { best = ll; mbest = c; }
-            __syncwarp();
-        }
-        for (int i = lane; i < BF_GMM_D; i += 32) W.dm[i] = W.x69[i] - __ldg(m.gmm_mean + mbest * BF_GMM_D + i);
-        __syncwarp();
-        {
-            const float* P = m.gmm_prec + (size_t)mbest * BF_GMM_D * BF_GMM_D;
-            const float* Pt = m.gmm_prec_t + (size_t)mbest * BF_GMM_D * BF_GMM_D;
-            const float wp = f.w_pose * f.w_pose;
-            for (int i = lane; i < L.nbody; i += 32) {
-                float a = 0.f, bb = 0.f;
-                for (int j = 0; j < BF_GMM_D; ++j) {
-                    a += __ldg(Pt + j * BF_GMM_D + i) * W.dm[j];   // (P d)_i
-                    bb += __ldg(P + j * BF_GMM_D + i) * W.dm[j];   // (P^T d)_i
-                }
-                g[7 + i] += wp * 0.5f * (a + bb);
-            }
-        }
-        __syncwarp();
-        const float pose_l = f.w_pose * f.w_pose * best;
         // ---- angle prior: exp(sign * pose[idx])^2 on elbows / knees ----
         float ang = 0.f;
         if (lane < 4) {
@@ -375,8 +362,17 @@ __global__ void __launch_bounds__(128) k_pose_bwd(BfModel m, BfFrames f, int fla
             vi = vi * ad.beta2 + ad.om_beta2 * gi * gi;
             const float denom = sqrtf(vi) / ad.bc2_sqrt + ad.eps;
             const float step = (i < 4) ? ad.step_ts : ad.step_lr;
-            th[i] = S.th[i] + (-step) * mi / denom;
+            const float tn = S.th[i] + (-step) * mi / denom;
+            th[i] = tn;
             am[i] = mi; av[i] = vi;
+            W.thn[i] = tn;
+        }
+        if (flags & 8) {
+            __syncwarp();
+            for (int i = lane; i < m.NP; i += 32) S.th[i] = W.thn[i];
+            __syncwarp();
+            pose_forward_from_smem(m, S, lane);
+            pose_write_outputs(m, f, S, b, lane);
         }
     }
 }

@@ -173,7 +173,13 @@ __global__ void __launch_bounds__(256) k_skin_bwd_dA(BfVSet vs, int J, const flo
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     const float* g = dverts + (size_t)b * ld_v;
     const float* x = vposed + (size_t)b * ld_v;
-    for (int j = warp; j < J; j += nw) {
+    // joints without skinned vertices in this set (most of them for the active set): zero rows
+    if (vs.n_nz < J) {
+        for (int i = threadIdx.x; i < J * 12; i += blockDim.x) dA[(size_t)b * J * 12 + i] = 0.f;
+        __syncthreads();
+    }
+    for (int jn = warp; jn < vs.n_nz; jn += nw) {
+        const int j = __ldg(vs.jv_nz + jn);
         float acc[12];
 #pragma unroll
         for (int e = 0; e < 12; ++e) acc[e] = 0.f;

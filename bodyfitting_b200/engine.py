@@ -71,6 +71,8 @@ class FrameBuffers(object):
                 if nsplit > 1:
                     buf('ws', nsplit, B, Kp)
             buf('loss_terms', B, 4, zero=True)
+            buf('gmm_grad', B, 69, zero=True)
+            buf('gmm_loss', B, zero=True)
         if n_trace:
             buf('trace', n_trace, B, zero=True)
         self.t = t
@@ -187,17 +189,17 @@ class FitSession(object):
                 launches += self._dense_forward()
                 fb.struct.iter = it
                 fb.call('bf_fit_step')
-                launches += 7
+                launches += 6
         else:
             fb.struct.iter = 0
             if N > 1:
                 fb.call('bf_fit_run', N - 1)
-                launches += 7 * (N - 1)
+                launches += 5 * (N - 1) + 1          # skin fwd, frame loss+bwd, gmm, blend bwd, pose bwd(+next fwd); pose fwd once
         self.theta_prev.copy_(fb.t['theta'])
         launches += self._dense_forward()
         fb.struct.iter = N - 1
         fb.call('bf_fit_step')
-        launches += 7
+        launches += 6
         self.kernel_launches = launches
         return fb.t['theta']
 

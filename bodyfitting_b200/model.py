@@ -163,8 +163,9 @@ class PreparedModel(object):
             sqrdets = np.array([np.sqrt(np.linalg.det(c)) for c in np.asarray(gmm['covars'])])
             const = (2 * np.pi) ** (69 / 2.)
             nllw = np.asarray(np.asarray(gmm['weights']) / (const * (sqrdets / sqrdets.min()))).astype(np.float32)
-            g = dict(gmm_mean=means, gmm_prec=prec, gmm_prec_t=np.ascontiguousarray(np.transpose(prec, (0, 2, 1))),
-                     gmm_logw=np.log(nllw).astype(np.float32))
+            psym = np.zeros((means.shape[0], 69, 72), dtype=np.float32)      # (P + P^T)/2, rows padded to 72
+            psym[:, :, :69] = (prec + np.transpose(prec, (0, 2, 1))) * np.float32(0.5)
+            g = dict(gmm_mean=means, gmm_psym=psym, gmm_logw=np.log(nllw).astype(np.float32))
             self.n_gmm = means.shape[0]
             assert means.shape[1] == 69
         else:
@@ -298,6 +299,8 @@ class PreparedModel(object):
                 kj_src[k] = (r, 0, 0)
                 for e in range(xr_ptr[r], xr_ptr[r + 1]):
                     entries.append((J + int(xr_vid[e]), k, -1, float(xr_w[e])))
+        dyn_k = [k for k, (kind, _, _) in enumerate(table) if kind == 2]
+        entries = [e for e in entries if e[2] < 0]        # contour landmarks are scattered directly from dyn_src (yaw-dependent)
         entries.sort(key=lambda t: (t[0], t[1], t[2]))
         ntg = J + n
         tg_ptr = np.zeros(ntg + 1, dtype=np.int32)
@@ -313,9 +316,16 @@ class PreparedModel(object):
         if self.tensor_cores:
             h['Bm_hi'], h['Bm_lo'] = split_tf32(Bm)
             h['Bt_hi'], h['Bt_lo'] = split_tf32(np.ascontiguousarray(Bm.T))
-        if dyn_src is not None and any(kind == 2 for kind, _, _ in table):
+        if dyn_src is not None and dyn_k:
+            assert [table[k][1][0] for k in dyn_k] == list(range(n_dyn))
             h['dyn_src'] = np.ascontiguousarray(dyn_src)
             h['dyn_w'] = np.ascontiguousarray(dyn_w)
+            h['dyn_k'] = np.array(dyn_k, dtype=np.int32)
+        else:
+            h['n_dyn'] = 0
+        nzj = np.nonzero(np.diff(jv_ptr))[0].astype(np.int32)
+        h['jv_nz'] = nzj if len(nzj) else np.zeros(1, np.int32)
+        h['n_nz'] = len(nzj)
         if xr_ptr is not None:
             h.update(xr_ptr=xr_ptr, xr_vid=xr_vid, xr_w=xr_w)
         return h

@@ -40,7 +40,7 @@ extern "C" {
 #define BF_ECUDA    -2   /* a CUDA runtime call / launch failed            */
 #define BF_EARCH    -3   /* device is not sm_100 (no fallback exists)      */
 
-#define BF_ABI_VERSION 6
+#define BF_ABI_VERSION 8
 #define BF_F_WORLD 1   /* forward outputs in world space: (x + transl) * scale * constant_scale */
 #define BF_F_TC    2   /* run the blend-shape contractions on tcgen05 tensor cores (3xTF32) */
 
@@ -69,7 +69,9 @@ typedef struct BfVSet {
     const float*   Bt_lo;     /* ... and the fp32 remainder (forward GEMM B operand, K-major) */
     const float*   Bm_hi;     /* [Kp, ldn] the same split of Bm (backward GEMM B operand, K-major) */
     const float*   Bm_lo;
-    int32_t n, n_pad, ldn, nnz, K_out, n_dyn, n_extra, _pad0;
+    const int32_t* dyn_k;     /* [n_dyn] output joint index of each contour-landmark slot */
+    const int32_t* jv_nz;     /* [n_nz] joints with a non-empty jv list */
+    int32_t n, n_pad, ldn, nnz, K_out, n_dyn, n_extra, n_nz;
 } BfVSet;
 
 typedef struct BfModel {
@@ -83,8 +85,7 @@ typedef struct BfModel {
     const float*   hand_l;    /* [6,45] or NULL */
     const float*   hand_r;    /* [6,45] or NULL */
     const float*   gmm_mean;  /* [8,69] */
-    const float*   gmm_prec;  /* [8,69,69] */
-    const float*   gmm_prec_t;/* [8,69,69] transposed */
+    const float*   gmm_psym;  /* [8,69,72] (P + P^T)/2 of each component, rows padded with zeros to 72 */
     const float*   gmm_logw;  /* [8] log(nll_weights) */
     BfVSet full;
     BfVSet act;
@@ -120,6 +121,8 @@ typedef struct BfFrames {
     float*       pf_lo;
     float*       dvp_hi;     /* [B,ldn] 3xTF32 split of dvp, row stride = ldn of the vertex set, pad columns 0 */
     float*       dvp_lo;
+    float*       gmm_grad;   /* [B,69] w_pose^2 * gradient of the GMM prior (k_gmm_prior -> k_pose_bwd) */
+    float*       gmm_loss;   /* [B]    w_pose^2 * min_m ll_m */
     float*       ws;         /* split-K workspace of the tensor-core backward GEMM (>= ceil(ldn/2048) * B * Kp floats) or NULL */
     int64_t      ws_floats;
     double lr_ts, lr, beta1, beta2, eps;   /* Adam hyper-parameters (python floats in the reference: smplify.py:167-174) */
@@ -143,11 +146,17 @@ int bf_joints_forward(const BfModel* m, const BfFrames* f, int use_full, void* s
 int bf_joints_backward(const BfModel* m, const BfFrames* f, int use_full, int accumulate_dverts, void* stream);
 /* keypoint data term: loss, d/d(theta[0:4]), dJtr, dverts */
 int bf_keypoint_loss(const BfModel* m, const BfFrames* f, int use_full, void* stream);
+/* active set only: keypoint term + its backward down to dvp, dA, dJtr, grad[0:4] in one kernel per frame
+ * (= bf_keypoint_loss + parts 1|2 of bf_skin_backward without the d(verts) round trip through HBM) */
+int bf_frame_loss_backward(const BfModel* m, const BfFrames* f, void* stream);
 /* dverts -> dvp, dA, dpf */
 int bf_skin_backward(const BfModel* m, const BfFrames* f, int use_full, void* stream);
 /* the same, one kernel at a time (profiling): parts bit0 dvp, bit1 dA, bit2 blend-backward GEMM */
 int bf_skin_backward_parts(const BfModel* m, const BfFrames* f, int use_full, int parts, void* stream);
-/* dA, dJtr, dpf -> grad (theta[4:]); flags: 1 = add priors (value + grad), 2 = Adam step, 4 = keep grad[0:4] from loss kernel */
+/* GMM pose prior of every frame -> gmm_grad, gmm_loss */
+int bf_gmm_prior(const BfModel* m, const BfFrames* f, void* stream);
+/* dA, dJtr, dpf -> grad (theta[4:]); flags: 1 = add priors (value + grad; needs bf_gmm_prior first), 2 = Adam step,
+ * 4 = keep grad[0:4] from the loss kernel, 8 = also run the next iteration's pose forward on the updated theta */
 int bf_pose_backward(const BfModel* m, const BfFrames* f, int flags, void* stream);
 
 /* LBS operator: pose_forward + skin_forward(full) + joints_forward */

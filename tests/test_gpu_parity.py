@@ -69,7 +69,7 @@ def test_loss_and_gradients(assets, mt, nv):
     fb.bind('kp', pack_keypoints(torch.as_tensor(sc['kp']).cuda(), mt == 'smplx'))
     fb.bind('cams', torch.from_numpy(pack_cameras(sc['c2ws'], sc['Ks'])).cuda())
     for fn, extra in (('bf_pose_forward', ()), ('bf_skin_forward', (0,)), ('bf_keypoint_loss', (0,)),
-                      ('bf_skin_backward', (0,)), ('bf_pose_backward', (1 | 4,))):
+                      ('bf_gmm_prior', ()), ('bf_skin_backward', (0,)), ('bf_pose_backward', (1 | 4,))):
         fb.call(fn, *extra)
     torch.cuda.synchronize()
     loss = fb.t['loss'].cpu().numpy()

@@ -106,10 +106,15 @@ def test_target_lists_are_the_transpose_of_the_joint_table(prepared, mt):
             via = np.zeros_like(direct)
             ptr = t['tg_ptr']
             assert ptr.shape[0] == pm.J + n + 1
+            assert (t['tg_a'] < 0).all()                 # static entries only; contour landmarks go through dyn_*
             for tg in np.nonzero(np.diff(ptr))[0]:
                 for e in range(ptr[tg], ptr[tg + 1]):
-                    if t['tg_a'][e] < 0 or t['tg_a'][e] == yaw:
-                        via[tg] += t['tg_w'][e] * g[t['tg_k'][e]]
+                    via[tg] += t['tg_w'][e] * g[t['tg_k'][e]]
+            if 'dyn_k' in t:
+                for s, k in enumerate(t['dyn_k']):
+                    assert t['kj_kind'][k] == 2 and t['kj_src'][k][0] == s
+                    for i in range(3):
+                        via[pm.J + t['dyn_src'][yaw, s, i]] += t['dyn_w'][yaw, s, i] * g[k]
             assert np.abs(via - direct).max() < 1e-6
 
 
