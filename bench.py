@@ -158,7 +158,7 @@ def build_workload(pm, F, seed):
     theta_gt = pm.pack_theta(T(gt['global_orient']), T(gt['body_pose']), T(gt['betas']), transl=T(gt['transl']),
                              scale=T(gt['scale']), leye=T(gt['leye_pose']), reye=T(gt['reye_pose']),
                              lhand=T(gt['left_hand_pose']), rhand=T(gt['right_hand_pose']))
-    joints = torch.empty(F, pm.K_out, 3, device='cuda')
+    joints = torch.empty(F, pm.K_full, 3, device='cuda')
     chunk = 2048
     for lo in range(0, F, chunk):
         hi = min(F, lo + chunk)
@@ -167,7 +167,7 @@ def build_workload(pm, F, seed):
         fb.struct.flags |= _lib.F_WORLD
         fb.call('bf_lbs_forward')
     torch.cuda.synchronize()
-    kp = syn.make_keypoints(joints.cpu().numpy(), c2ws, Ks, seed=seed)
+    kp = syn.make_keypoints(joints[:, :pm.K_used].cpu().numpy(), c2ws, Ks, seed=seed)
     init_pose = np.concatenate([init['global_orient'], init['body_pose'], np.zeros((F, 6), np.float32)], 1)
     return dict(c2ws=c2ws, Ks=Ks, kp=kp, init_pose=init_pose.astype(np.float32), init_betas=init['betas'])
 
@@ -230,7 +230,7 @@ def dense_lbs_bench(assets_seed, hbm_peak):
     T = lambda a: torch.from_numpy(a)
     fb = FrameBuffers(pm, B, full=True)
     fb.t['theta'].copy_(pm.pack_theta(T(gt['global_orient']), T(gt['body_pose']), T(gt['betas'])))
-    fb.bind('djoints', torch.randn(B, pm.K_out, 3, device='cuda'))
+    fb.bind('djoints', torch.randn(B, pm.K_full, 3, device='cuda'))
     fb.t['dverts'].normal_()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
 

@@ -79,6 +79,21 @@ def lib():
         fn = getattr(L, name)
         fn.restype = C.c_int
         fn.argtypes = [pm, pf] + extra + [vp]
+    fp, i32, i64, fl = C.c_void_p, C.c_int, C.c_int64, C.c_float
+    ops = {
+        'bf_op_project': [fp, fp, fp, fp, fp, i32, i32, i32, vp],
+        'bf_op_project_backward': [fp, fp, fp, fp, fp, fp, i32, i32, i32, vp],
+        'bf_op_gmof': [fp, fp, fl, i64, vp],
+        'bf_op_gmof_backward': [fp, fp, fp, fl, i64, vp],
+        'bf_op_reprojection': [fp, fp, fp, fl, fl, i32, fp, fp, vp],
+        'bf_op_keypoints_world': [fp, fp, fp, i32, i32, i32, fl, fl, fp, fp, vp],
+        'bf_op_angle_prior': [fp, i32, i32, fp, fp, vp],
+        'bf_op_gmm_pose': [pm, fp, i32, i32, i32, fl, fp, fp, vp],
+    }
+    for name, at in ops.items():
+        fn = getattr(L, name)
+        fn.restype = C.c_int
+        fn.argtypes = at
     _lib = L
     return L
 
@@ -86,6 +101,10 @@ def lib():
 EXPORTED = ['bf_abi_version', 'bf_sizeof', 'bf_last_error', 'bf_check_device', 'bf_pose_forward', 'bf_skin_forward',
             'bf_joints_forward', 'bf_joints_backward', 'bf_keypoint_loss', 'bf_skin_backward', 'bf_skin_backward_parts',
             'bf_pose_backward', 'bf_gmm_prior', 'bf_frame_loss_backward', 'bf_lbs_forward', 'bf_lbs_backward', 'bf_fit_step', 'bf_fit_run']
+
+
+EXPORTED_OPS = ['bf_op_project', 'bf_op_project_backward', 'bf_op_gmof', 'bf_op_gmof_backward', 'bf_op_reprojection',
+                'bf_op_keypoints_world', 'bf_op_angle_prior', 'bf_op_gmm_pose']
 
 
 def check(rc, what=''):

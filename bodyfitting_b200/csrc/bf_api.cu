@@ -10,6 +10,8 @@
 #include "bf_loss.cuh"
 #include "bf_gmm.cuh"
 #include "bf_frame.cuh"
+#include "bf_ops.cuh"
+#include "../../include/bodyfit_b200_ops.h"
 #include "bf_blend_tc.cuh"
 
 static thread_local char g_err[512] = "";
@@ -153,19 +155,78 @@ int bf_skin_backward(const BfModel* m, const BfFrames* f, int use_full, void* st
     return bf_skin_backward_parts(m, f, use_full, 7, stream);
 }
 
-int bf_gmm_prior(const BfModel* m, const BfFrames* f, void* stream) {
-    int rc = check_model(m, f); if (rc) return rc;
+static int launch_gmm(const BfModel* m, const float* pose, int ld, int nvalid, int B, float wp, float* grad, float* loss,
+                      cudaStream_t s) {
     BF_REQUIRE(m->gmm_mean && m->gmm_psym && m->gmm_logw && m->n_gmm > 0, "GMM tables missing");
-    BF_REQUIRE(f->gmm_grad && f->gmm_loss, "gmm_grad / gmm_loss is null");
+    BF_REQUIRE(pose && grad && loss && B > 0, "gmm buffers missing");
     static bool attr = false;
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(k_gmm_prior, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GmmSmem));
         if (e != cudaSuccess) { bf_set_error("cudaFuncSetAttribute(k_gmm_prior): %s", cudaGetErrorString(e)); return BF_ECUDA; }
         attr = true;
     }
-    k_gmm_prior<<<(f->B + GM_F - 1) / GM_F, GM_F * GM_PARTS, sizeof(GmmSmem), (cudaStream_t)stream>>>(*m, *f);
+    k_gmm_prior<<<(B + GM_F - 1) / GM_F, GM_F * GM_PARTS, sizeof(GmmSmem), s>>>(*m, pose, ld, nvalid, B, wp, grad, loss);
     BF_LAUNCH_CHECK();
     return BF_OK;
+}
+
+int bf_gmm_prior(const BfModel* m, const BfFrames* f, void* stream) {
+    int rc = check_model(m, f); if (rc) return rc;
+    BF_REQUIRE(f->gmm_grad && f->gmm_loss, "gmm_grad / gmm_loss is null");
+    return launch_gmm(m, f->theta + 7, m->NP, theta_layout(m->is_smplx).nbody, f->B, f->w_pose * f->w_pose,
+                      f->gmm_grad, f->gmm_loss, (cudaStream_t)stream);
+}
+
+// ---- stand-alone loss / prior operators (include/bodyfit_b200_ops.h) ------------------------------
+int bf_op_project(const float* pts, const float* R, const float* t, const float* K, float* uv, int B, int N, int nb, void* stream) {
+    BF_REQUIRE(pts && R && t && K && uv && B > 0 && N > 0 && (nb == 1 || nb == B), "bad arguments");
+    k_project_fwd<<<(B * N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(pts, R, t, K, uv, B, N, nb);
+    BF_LAUNCH_CHECK();
+    return BF_OK;
+}
+int bf_op_project_backward(const float* pts, const float* R, const float* t, const float* K, const float* duv, float* dpts,
+                           int B, int N, int nb, void* stream) {
+    BF_REQUIRE(pts && R && t && K && duv && dpts && B > 0 && N > 0 && (nb == 1 || nb == B), "bad arguments");
+    k_project_bwd<<<(B * N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(pts, R, t, K, duv, dpts, B, N, nb);
+    BF_LAUNCH_CHECK();
+    return BF_OK;
+}
+int bf_op_gmof(const float* x, float* y, float sigma, int64_t n, void* stream) {
+    BF_REQUIRE(x && y && n > 0, "bad arguments");
+    k_gmof_fwd<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, y, sigma, (size_t)n);
+    BF_LAUNCH_CHECK();
+    return BF_OK;
+}
+int bf_op_gmof_backward(const float* x, const float* dy, float* dx, float sigma, int64_t n, void* stream) {
+    BF_REQUIRE(x && dy && dx && n > 0, "bad arguments");
+    k_gmof_bwd<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, dy, dx, sigma, (size_t)n);
+    BF_LAUNCH_CHECK();
+    return BF_OK;
+}
+int bf_op_reprojection(const float* cord, const float* gt, const float* w, float coef, float sigma, int N, float* out,
+                       float* dcord, void* stream) {
+    BF_REQUIRE(cord && gt && w && out && dcord && N > 0, "bad arguments");
+    k_reproj<<<1, 256, 0, (cudaStream_t)stream>>>(cord, gt, w, coef, sigma, N, out, dcord);
+    BF_LAUNCH_CHECK();
+    return BF_OK;
+}
+int bf_op_keypoints_world(const float* joints, const float* kp, const float* cams, int B, int K, int Nv, float coef,
+                          float sigma, float* loss_bk, float* dJ, void* stream) {
+    BF_REQUIRE(joints && kp && cams && loss_bk && dJ && B > 0 && K > 0 && Nv > 0, "bad arguments");
+    k_kp_world<<<(B * K + 127) / 128, 128, 0, (cudaStream_t)stream>>>(joints, kp, cams, B, K, Nv, coef, sigma, loss_bk, dJ);
+    BF_LAUNCH_CHECK();
+    return BF_OK;
+}
+int bf_op_angle_prior(const float* pose, int B, int D, float* out, float* dout, void* stream) {
+    BF_REQUIRE(pose && out && dout && B > 0 && D >= 56, "bad arguments (pose needs >= 56 columns)");
+    k_angle_prior<<<(B * 4 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(pose, B, D, out, dout);
+    BF_LAUNCH_CHECK();
+    return BF_OK;
+}
+int bf_op_gmm_pose(const BfModel* m, const float* pose, int ld, int nvalid, int B, float weight, float* grad, float* loss,
+                   void* stream) {
+    BF_REQUIRE(m && nvalid > 0 && nvalid <= 69 && ld >= nvalid, "bad arguments");
+    return launch_gmm(m, pose, ld, nvalid, B, weight, grad, loss, (cudaStream_t)stream);
 }
 
 int bf_pose_backward(const BfModel* m, const BfFrames* f, int flags, void* stream) {

@@ -28,15 +28,17 @@ struct GmmSmem {
     float qp[GM_PARTS][GM_F];   // partial quadratic forms
 };
 
-__global__ void __launch_bounds__(GM_F * GM_PARTS) k_gmm_prior(BfModel m, BfFrames f) {
+// pose: row b at pose + b*ld, first nvalid entries used (the rest of the 69 are 0, smplify/loss.py:206-207)
+__global__ void __launch_bounds__(GM_F * GM_PARTS) k_gmm_prior(BfModel m, const float* __restrict__ pose, int ld, int nvalid,
+                                                                int B, float wp, float* __restrict__ gmm_grad,
+                                                                float* __restrict__ gmm_loss) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     GmmSmem& S = *reinterpret_cast<GmmSmem*>(smem_raw);
     const int t = threadIdx.x, lane = t & 31, part = t >> 5;
     const int b = blockIdx.x * GM_F + lane;
-    const bool valid = b < f.B;
-    const int nbody = theta_layout(m.is_smplx).nbody;
-    const float* th = f.theta + (size_t)(valid ? b : f.B - 1) * m.NP + 7;
-    for (int j = part; j < GM_D; j += GM_PARTS) S.x[j][lane] = (j < nbody) ? th[j] : 0.f;
+    const bool valid = b < B;
+    const float* th = pose + (size_t)(valid ? b : B - 1) * ld;
+    for (int j = part; j < GM_D; j += GM_PARTS) S.x[j][lane] = (j < nvalid) ? th[j] : 0.f;
 
     auto load_comp = [&](int c, int buf) {
         const float4* src = reinterpret_cast<const float4*>(m.gmm_psym + (size_t)c * GM_D * GM_LD);
@@ -83,10 +85,9 @@ __global__ void __launch_bounds__(GM_F * GM_PARTS) k_gmm_prior(BfModel m, BfFram
         if (c == 0 || ll < best) { best = ll; bi = cand; }      // identical decision in all four parts
         __syncthreads();                             // qp / P[cur] may be overwritten from here on
     }
-    const float wp = f.w_pose * f.w_pose;
     if (valid) {
-        if (part == 0) f.gmm_loss[b] = wp * best;
-        float* o = f.gmm_grad + (size_t)b * GM_D;
+        if (part == 0) gmm_loss[b] = wp * best;
+        float* o = gmm_grad + (size_t)b * GM_D;
         for (int j = part; j < GM_D; j += GM_PARTS) o[j] = wp * S.g[bi][j][lane];
     }
 }

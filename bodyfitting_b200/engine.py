@@ -26,7 +26,7 @@ class FrameBuffers(object):
         dev = model.device
         J, Kp, NP = model.J, model.Kp, model.NP
         self.ld_v = 3 * model.V if full else model.ld_act
-        self.K_out = model.K_out if full else model.K_out_act
+        self.K_out = model.K_full if full else model.K_out_act
         f32 = dict(device=dev, dtype=torch.float32)
         t = {}
         ext = ext or {}
@@ -143,7 +143,7 @@ class FitSession(object):
         self.fb = FrameBuffers(model, B, full=False, Nv=Nv, n_trace=(self.N if trace else 0), imsize=imsize)
         self.theta_prev = torch.empty(B, model.NP, device=dev)
         self.verts = torch.empty(B, model.V, 3, device=dev) if return_vertices else None
-        self.joints = torch.empty(B, model.K_out, 3, device=dev)
+        self.joints = torch.empty(B, model.K_full, 3, device=dev)
         self.full_pose = torch.empty(B, 3 * model.J, device=dev)
         self.dense_every_iter = bool(dense_every_iter)
         c = min(int(chunk), self.B)
@@ -210,7 +210,7 @@ class FitSession(object):
         out = {}
         if self.verts is not None:
             out['vertices'] = self.verts
-        out.update(joints=self.joints, pose=sn['body_pose'], betas=sn['betas'], global_orient=sn['global_orient'],
+        out.update(joints=self.joints[:, :m.K_out], pose=sn['body_pose'], betas=sn['betas'], global_orient=sn['global_orient'],
                    global_transl=sn['transl'] * sn['scale'], scale=sn['scale'], full_pose=self.full_pose)
         if m.is_smplx:
             out.update(leye_pose=sn['leye_pose'], reye_pose=sn['reye_pose'],

@@ -152,6 +152,10 @@ class PreparedModel(object):
         self.K_used = K_used
         self.joint_table = [pre[int(i)] for i in jmap]
         self.K_out = len(self.joint_table)
+        # SMPL wrapper also returns the 45 un-mapped smplx joints as ``joints_ori`` (models/smpl.py:73,80):
+        # appended to the all-vertex joint table so that one kernel produces (and back-propagates) both
+        self.ori_table = pre[:J + len(extra_vids)] if not self.is_smplx else []
+        self.K_full = self.K_out + len(self.ori_table)
         self._dyn_faces, self._dyn_bary, self._xr = dyn_faces, dyn_bary, xr
 
         # ---- GMM prior (smplify/prior.py:127-160) ------------------------------------------------
@@ -189,7 +193,7 @@ class PreparedModel(object):
                           child_idx=np.array(child_idx + [0], dtype=np.int32), Jt=Jt, Jd=Jd, pose_mean=pose_mean,
                           hand_l=hand_l, hand_r=hand_r, **g)
         self.max_depth = int(depth.max())
-        full_h = self._build_vset(np.arange(V, dtype=np.int64), Bm_rows, W, self.joint_table)
+        full_h = self._build_vset(np.arange(V, dtype=np.int64), Bm_rows, W, self.joint_table + self.ori_table)
         act_h = self._build_vset(self.active_vids, Bm_rows, W, self.joint_table[:K_used])
         del Bm_rows
 

@@ -1,0 +1,40 @@
+/*
+ * bodyfit_b200_ops.h -- stand-alone operators of the reference's loss / prior surface, for callers
+ * that compose the objective themselves (the fused fit loop in bodyfit_b200.h does not use them).
+ * Same conventions as bodyfit_b200.h: extern "C", device pointers, caller's stream, 0 / negative code.
+ * Every forward has its hand-written backward.  fp32, row-major, contiguous.
+ *
+ *   bf_op_project(+_backward)   smplify/loss.py:22-43   perspective_projection(points[B,N,3], rotation[nb,3,3],
+ *                               translation[nb,3], K[3,3]) -> [B,N,2], nb = 1 (broadcast) or B
+ *   bf_op_gmof(+_backward)      smplify/loss.py:45-51   sigma^2 x^2 / (sigma^2 + x^2), elementwise
+ *   bf_op_reprojection          smplify/loss.py:132-136 sum_j w_j sum_c gmof((gt - cord)/coef): value + d/dcord;
+ *                               w_j = conf_j^2 (body) or the group's sum of conf^2 ([N,1] confidences, :168-179)
+ *   bf_op_keypoints_world       smplify/loss.py:156-203 data term on world joints [B,K,3] against packed
+ *                               detections [B,Nv,K,3] = (x, y, weight) and cams [Nv,12] = K [R|t]:
+ *                               per (frame, joint) loss / Nv and d/d joints
+ *   bf_op_angle_prior           smplify/loss.py:54-61   exp(sign * pose[:, [52,55,9,12]])^2 and its derivative
+ *   bf_op_gmm_pose              smplify/prior.py:181-196 weight * min_m(0.5 d^T P_m d - log nll_w_m) on pose[B, ld]
+ *                               (first nvalid <= 69 columns used, rest 0) and its gradient [B,69]
+ */
+#ifndef BODYFIT_B200_OPS_H
+#define BODYFIT_B200_OPS_H
+#include "bodyfit_b200.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+int bf_op_project(const float* pts, const float* R, const float* t, const float* K, float* uv, int B, int N, int nb, void* stream);
+int bf_op_project_backward(const float* pts, const float* R, const float* t, const float* K, const float* duv, float* dpts,
+                           int B, int N, int nb, void* stream);
+int bf_op_gmof(const float* x, float* y, float sigma, int64_t n, void* stream);
+int bf_op_gmof_backward(const float* x, const float* dy, float* dx, float sigma, int64_t n, void* stream);
+int bf_op_reprojection(const float* cord, const float* gt, const float* w, float coef, float sigma, int N, float* out,
+                       float* dcord, void* stream);
+int bf_op_keypoints_world(const float* joints, const float* kp, const float* cams, int B, int K, int Nv, float coef,
+                          float sigma, float* loss_bk, float* dJ, void* stream);
+int bf_op_angle_prior(const float* pose, int B, int D, float* out, float* dout, void* stream);
+int bf_op_gmm_pose(const BfModel* m, const float* pose, int ld, int nvalid, int B, float weight, float* grad, float* loss,
+                   void* stream);
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,145 @@
+"""GPU parity of the operator surface (models.smpl.SMPL, smplify.loss.*, smplify.prior.*) against the
+oracle's CPU restatements, values and gradients."""
+import numpy as np
+import pytest
+import torch
+
+from bodyfitting_b200 import synthetic as syn
+from oracle import fit_port as fp
+from util import make_port, make_scene, perturbed_params, relerr
+
+pytestmark = pytest.mark.gpu
+
+
+def test_projection_gmof_reprojection_angle():
+    from bodyfitting_b200.smplify import loss as L
+    rng = np.random.RandomState(0)
+    B, N = 3, 40
+    pts = rng.randn(B, N, 3) * 0.2
+    c2ws, Ks = syn.make_cameras(1)
+    w2c = np.linalg.inv(c2ws[0].astype(np.float64))
+    R, t, K = w2c[None, :3, :3], w2c[None, :3, 3], Ks[0]
+    T = lambda a, g=False: torch.tensor(a, dtype=torch.float32, requires_grad=g)
+    p_ref = T(pts, True)
+    uv_ref = fp.project(p_ref, T(R), T(t), K)
+    p_gpu = T(pts).cuda().requires_grad_(True)
+    uv = L.perspective_projection(p_gpu, T(R).cuda(), T(t).cuda(), K)
+    assert relerr(uv.detach().cpu().numpy(), uv_ref.detach().numpy()) < 1e-5
+    wgt = rng.randn(B, N, 2).astype(np.float32)
+    (uv_ref * T(wgt)).sum().backward()
+    (uv * T(wgt).cuda()).sum().backward()
+    assert relerr(p_gpu.grad.cpu().numpy(), p_ref.grad.numpy()) < 1e-4
+    # per-frame rotation (bs,3,3)
+    Rb = np.repeat(R, B, 0)
+    tb = np.repeat(t, B, 0)
+    uv2 = L.perspective_projection(T(pts).cuda(), T(Rb).cuda(), T(tb).cuda(), torch.tensor(K).cuda())
+    assert relerr(uv2.cpu().numpy(), uv_ref.detach().numpy()) < 1e-5
+    # gmof
+    x = rng.randn(1000).astype(np.float32) * 300
+    xr, xg = T(x, True), T(x).cuda().requires_grad_(True)
+    fp.gmof(xr, 100.0).sum().backward()
+    y = L.gmof(xg, 100.0)
+    y.sum().backward()
+    assert relerr(y.detach().cpu().numpy(), fp.gmof(T(x), 100.0).numpy()) < 1e-6
+    assert relerr(xg.grad.cpu().numpy(), xr.grad.numpy()) < 1e-5
+    # reprojection_loss with [N] and [N,1] confidences (the reference's broadcast)
+    cord, gt, conf = rng.rand(21, 2) * 500, rng.rand(21, 2) * 500, rng.rand(21)
+    for shape in ((21,), (21, 1)):
+        cr, cg = T(cord, True), T(cord).cuda().requires_grad_(True)
+        ref = fp.reprojection(cr, T(gt), T(conf.reshape(shape)), 0.5, 100.0)
+        out = L.reprojection_loss(cg, T(gt).cuda(), T(conf.reshape(shape)).cuda(), 0.5, 100.0)
+        assert out.shape == ref.shape
+        assert relerr(out.detach().cpu().numpy(), ref.detach().numpy()) < 1e-5
+        ref.sum().backward(); out.sum().backward()
+        assert relerr(cg.grad.cpu().numpy(), cr.grad.numpy()) < 1e-4
+    # angle prior
+    pose = rng.randn(5, 69).astype(np.float32) * 0.3
+    pr, pg = T(pose, True), T(pose).cuda().requires_grad_(True)
+    a_ref, a = fp.angle_prior(pr), L.angle_prior(pg)
+    assert relerr(a.detach().cpu().numpy(), a_ref.detach().numpy()) < 1e-6
+    a_ref.sum().backward(); a.sum().backward()
+    assert relerr(pg.grad.cpu().numpy(), pr.grad.numpy()) < 1e-6
+
+
+def test_gmm_prior_module(assets):
+    from bodyfitting_b200.smplify.prior import MaxMixturePrior, SMPLifyAnglePrior, L2Prior, create_prior
+    gmm = assets('gmm')
+    ref = fp.GMMPrior(gmm)
+    prior = MaxMixturePrior(gmm=gmm)
+    rng = np.random.RandomState(1)
+    for D in (69, 63):
+        pose = (rng.randn(70, D) * 0.3).astype(np.float32)
+        pr = torch.tensor(np.pad(pose, ((0, 0), (0, 69 - D))), requires_grad=True)
+        pg = torch.tensor(pose).cuda().requires_grad_(True)
+        a, b = ref(pr, None), prior(pg, None)
+        assert relerr(b.detach().cpu().numpy(), a.detach().numpy()) < 1e-5
+        a.sum().backward(); b.sum().backward()
+        assert relerr(pg.grad.cpu().numpy(), pr.grad.numpy()[:, :D]) < 1e-4
+    assert isinstance(create_prior('angle'), SMPLifyAnglePrior) and isinstance(create_prior('l2'), L2Prior)
+    with pytest.raises(ValueError):
+        create_prior('nope')
+
+
+def test_smpl_module_forward_backward(assets):
+    """models.smpl.SMPL: vertices [B,6890,3], joints [B,49,3], joints_ori [B,45,3] + autograd."""
+    from bodyfitting_b200.models.smpl import SMPL
+    B = 4
+    port = make_port(assets, 'smpl', dtype=torch.float64)
+    m = SMPL(model_data=assets('smpl'), J_regressor_extra=assets('jx'))
+    p = perturbed_params('smpl', B, seed=13)
+    tr = {k: torch.tensor(p[k], dtype=torch.float64, requires_grad=True) for k in ('global_orient', 'body_pose', 'betas')}
+    tg = {k: torch.tensor(p[k]).cuda().requires_grad_(True) for k in ('global_orient', 'body_pose', 'betas')}
+    ref = port.model(**tr, return_full_pose=True)
+    out = m(**tg, return_full_pose=True)
+    assert out.vertices.shape == (B, 6890, 3) and out.joints.shape == (B, 49, 3) and out.joints_ori.shape == (B, 45, 3)
+    assert relerr(out.vertices.detach().cpu().numpy(), ref.vertices.detach().numpy()) < 1e-5
+    assert relerr(out.joints.detach().cpu().numpy(), ref.joints.detach().numpy()) < 1e-5
+    assert relerr(out.joints_ori.detach().cpu().numpy(), ref.joints_ori.detach().numpy()) < 1e-5
+    assert relerr(out.full_pose.cpu().numpy(), ref.full_pose.detach().numpy()) < 1e-6
+    rng = np.random.RandomState(2)
+    wv, wj, wo = rng.randn(B, 6890, 3), rng.randn(B, 49, 3), rng.randn(B, 45, 3)
+    Td = lambda a: torch.tensor(a, dtype=torch.float64)
+    ((ref.vertices * Td(wv)).sum() + (ref.joints * Td(wj)).sum() + (ref.joints_ori * Td(wo)).sum()).backward()
+    Tf = lambda a: torch.tensor(a, dtype=torch.float32).cuda()
+    ((out.vertices * Tf(wv)).sum() + (out.joints * Tf(wj)).sum() + (out.joints_ori * Tf(wo)).sum()).backward()
+    for k in tr:
+        assert relerr(tg[k].grad.cpu().numpy(), tr[k].grad.numpy()) < 1e-4, k
+
+
+def test_multiview_keypoint_loss_composed(assets):
+    """The stand-alone objective (SMPL-X module + loss.multiview_keypoint_loss + prior) equals the oracle's
+    reference-style objective, value and gradients, for one frame given as OpenPose dicts."""
+    from bodyfitting_b200.models.smpl import create_smplx
+    from bodyfitting_b200.smplify.loss import multiview_keypoint_loss
+    from bodyfitting_b200.smplify.prior import MaxMixturePrior
+    mt, nv = 'smplx', 8
+    port = make_port(assets, mt)
+    sc = make_scene(port, mt, 1, nv, seed=17)
+    views = syn.keypoints_to_openpose(sc['kp'][0], mt)
+    p = perturbed_params(mt, 1, seed=18)
+    # oracle
+    pr = {k: torch.tensor(v, requires_grad=True) for k, v in p.items()}
+    full = dict(pr)
+    full['jaw_pose'] = torch.zeros(1, 1, 3)
+    full['leye_pose'] = pr['leye_pose'].view(1, 1, 3); full['reye_pose'] = pr['reye_pose'].view(1, 1, 3)
+    o = port.forward_model(full)
+    jw = (o.joints + pr['global_transl']) * pr['body_scale'] * 0.3
+    w2cs = torch.inverse(torch.tensor(np.array(sc['c2ws'])))
+    ref, terms = fp.keypoint_objective(w2cs, [np.asarray(k) for k in sc['Ks']], views, jw, pr['body_pose'], pr['betas'],
+                                       port.prior, 512, True)
+    ref.backward()
+    # ours
+    pg = {k: torch.tensor(v).cuda().requires_grad_(True) for k, v in p.items()}
+    model = create_smplx(model_data=assets(mt))
+    out = model(global_orient=pg['global_orient'], body_pose=pg['body_pose'], betas=pg['betas'], leye_pose=pg['leye_pose'],
+                reye_pose=pg['reye_pose'], left_hand_pose=pg['left_hand_pose'], right_hand_pose=pg['right_hand_pose'])
+    jwg = (out.joints + pg['global_transl'][:, None]) * pg['body_scale'][:, None] * 0.3
+    prior = MaxMixturePrior(gmm=assets('gmm'))
+    tot, losses = multiview_keypoint_loss(w2cs, list(sc['Ks']), views, jwg, pg['body_pose'], pg['betas'], list(range(nv)),
+                                          prior, imsize=512, use_hand_face=True)
+    tot.backward()
+    assert relerr(float(tot), float(ref)) < 1e-5
+    for k in ('reprojection_loss', 'pose_prior_loss', 'angle_prior_loss', 'shape_prior_loss'):
+        assert relerr(losses[k], terms[k].detach().numpy()) < 1e-5, k
+    for k in p:
+        assert relerr(pg[k].grad.cpu().numpy(), pr[k].grad.numpy()) < 2e-4, k

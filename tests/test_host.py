@@ -83,7 +83,7 @@ def test_joint_tables_reproduce_oracle_joints(assets, prepared, mt):
 def test_target_lists_are_the_transpose_of_the_joint_table(prepared, mt):
     """d(sum_k g_k . joint_k)/d(target) through tg_* equals the direct transpose, for every yaw row."""
     pm = prepared[mt]
-    for tag, K_out, n in (('act', pm.K_used, pm.n_act), ('full', pm.K_out, pm.V)):
+    for tag, K_out, n in (('act', pm.K_used, pm.n_act), ('full', pm.K_full, pm.V)):
         t = _vs_tables(pm, tag)
         rng = np.random.RandomState(1)
         g = rng.standard_normal((K_out, 3))
@@ -216,12 +216,12 @@ def test_openpose_dict_roundtrip():
 
 def test_library_loads_and_exports_every_declared_symbol():
     L = _lib.lib()
-    hdr = open(os.path.join(ROOT, 'include', 'bodyfit_b200.h')).read()
-    declared = set(re.findall(r'\b(bf_[a-z0-9_]+)\s*\(', hdr))
+    hdr = open(os.path.join(ROOT, 'include', 'bodyfit_b200.h')).read() + open(os.path.join(ROOT, 'include', 'bodyfit_b200_ops.h')).read()
+    declared = set(re.findall(r'^(?:int|const char\*)\s+(bf_[a-z0-9_]+)\s*\(', hdr, re.M))
     assert declared, 'no declarations parsed'
     for name in sorted(declared):
         assert hasattr(L, name), 'symbol %s declared in the header but not exported' % name
-    assert declared == set(_lib.EXPORTED)
+    assert declared == set(_lib.EXPORTED) | set(_lib.EXPORTED_OPS)
     assert L.bf_abi_version() == _lib.ABI_VERSION
     for i, st in enumerate((_lib.BfVSet, _lib.BfModel, _lib.BfFrames)):
         assert L.bf_sizeof(i) == ctypes.sizeof(st)
