@@ -44,6 +44,19 @@ class BfFrames(C.Structure):
         [(n, C.c_float) for n in ('imsize', 'constant_scale', 'sigma', 'w_pose', 'w_angle', 'w_shape')]
 
 
+class BfGrid(C.Structure):
+    _fields_ = [(n, _fp) for n in ('verts', 'faces', 'cell_start', 'cell_tris')] + \
+        [('min', C.c_float * 3), ('step', C.c_float), ('dim', _i32 * 3), ('ncell', _i32), ('Ns', _i32), ('Fs', _i32)]
+
+
+class BfSmpld(C.Structure):
+    _fields_ = [(n, _fp) for n in ('base', 'disp', 'adam_m', 'adam_v', 'faces', 'vf_ptr', 'vf_face', 'scan_fn', 'P', 'C',
+                                   'near_faces', 'nhat', 'nlen', 'm', 'Nlen', 'dN', 'dcorner', 'partial', 'totals', 'grad',
+                                   'trace')] + \
+        [(n, C.c_double) for n in ('lr', 'beta1', 'beta2', 'eps')] + \
+        [('reg_scale', C.c_float), ('V', _i32), ('F', _i32), ('iter', _i32)]
+
+
 class BodyfitError(RuntimeError):
     pass
 
@@ -90,6 +103,13 @@ def lib():
         'bf_op_angle_prior': [fp, i32, i32, fp, fp, vp],
         'bf_op_gmm_pose': [pm, fp, i32, i32, i32, fl, fp, fp, vp],
     }
+    pg, ps = C.POINTER(BfGrid), C.POINTER(BfSmpld)
+    ops.update({
+        'bf_grid_count': [pg, fp, vp], 'bf_grid_fill': [pg, fp, vp],
+        'bf_grid_nearest': [pg, fp, i32, fp, fp, fp, vp],
+        'bf_smpld_step': [pg, ps, vp], 'bf_smpld_run': [pg, ps, i32, vp],
+        'bf_pc_loss': [pg, fp, i32, i32, i32, fl, fl, fp, fp, fp, fp, vp],
+    })
     for name, at in ops.items():
         fn = getattr(L, name)
         fn.restype = C.c_int
@@ -103,6 +123,7 @@ EXPORTED = ['bf_abi_version', 'bf_sizeof', 'bf_last_error', 'bf_check_device', '
             'bf_pose_backward', 'bf_gmm_prior', 'bf_frame_loss_backward', 'bf_lbs_forward', 'bf_lbs_backward', 'bf_fit_step', 'bf_fit_run']
 
 
+EXPORTED_GRID = ['bf_grid_count', 'bf_grid_fill', 'bf_grid_nearest', 'bf_smpld_step', 'bf_smpld_run', 'bf_pc_loss']
 EXPORTED_OPS = ['bf_op_project', 'bf_op_project_backward', 'bf_op_gmof', 'bf_op_gmof_backward', 'bf_op_reprojection',
                 'bf_op_keypoints_world', 'bf_op_angle_prior', 'bf_op_gmm_pose']
 

@@ -11,6 +11,7 @@
 #include "bf_gmm.cuh"
 #include "bf_frame.cuh"
 #include "bf_ops.cuh"
+#include "bf_grid.cuh"
 #include "../../include/bodyfit_b200_ops.h"
 #include "bf_blend_tc.cuh"
 
@@ -315,6 +316,127 @@ int bf_fit_run(const BfModel* m, const BfFrames* f, int n_iters, void* stream) {
         int rc = fit_iteration(m, &g, i == 0, i + 1 < n_iters, stream); if (rc) return rc;
         g.iter++;
     }
+    return BF_OK;
+}
+
+// ---- uniform grid / closest point / SMPL+D (include/bodyfit_b200_grid.h) ------------------------------
+static int check_grid(const BfGrid* g) {
+    BF_REQUIRE(g && g->verts && g->faces && g->cell_start, "grid tables missing");
+    BF_REQUIRE(g->step > 0.f && g->dim[0] > 0 && g->dim[1] > 0 && g->dim[2] > 0, "bad grid geometry");
+    BF_REQUIRE((long long)g->dim[0] * g->dim[1] * g->dim[2] == g->ncell, "ncell != dim product");
+    BF_REQUIRE(g->Fs > 0 && g->Ns > 0, "empty mesh");
+    return BF_OK;
+}
+
+int bf_grid_count(const BfGrid* g, int32_t* counts, void* stream) {
+    int rc = check_grid(g); if (rc) return rc;
+    BF_REQUIRE(counts, "counts is null");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (cudaMemsetAsync(counts, 0, sizeof(int32_t) * g->ncell, s) != cudaSuccess) { bf_set_error("memset failed"); return BF_ECUDA; }
+    k_grid_insert<<<(g->Fs + 255) / 256, 256, 0, s>>>(*g, counts, nullptr, nullptr);
+    BF_LAUNCH_CHECK();
+    k_grid_scan<<<1, 1024, 0, s>>>(counts, g->cell_start, g->ncell);
+    BF_LAUNCH_CHECK();
+    return BF_OK;
+}
+
+int bf_grid_fill(const BfGrid* g, int32_t* cursor, void* stream) {
+    int rc = check_grid(g); if (rc) return rc;
+    BF_REQUIRE(cursor && g->cell_tris, "cursor / cell_tris is null");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (cudaMemsetAsync(cursor, 0, sizeof(int32_t) * g->ncell, s) != cudaSuccess) { bf_set_error("memset failed"); return BF_ECUDA; }
+    k_grid_insert<<<(g->Fs + 255) / 256, 256, 0, s>>>(*g, cursor, g->cell_start, g->cell_tris);
+    BF_LAUNCH_CHECK();
+    k_grid_sort<<<(g->ncell + 255) / 256, 256, 0, s>>>(g->cell_start, g->cell_tris, g->ncell);
+    BF_LAUNCH_CHECK();
+    return BF_OK;
+}
+
+int bf_grid_nearest(const BfGrid* g, const float* points, int Q, float* near_pts, int32_t* near_faces, float* dist2, void* stream) {
+    int rc = check_grid(g); if (rc) return rc;
+    BF_REQUIRE(g->cell_tris && points && near_pts && near_faces && Q > 0, "bad arguments");
+    k_grid_nearest<<<(Q + 7) / 8, 256, 0, (cudaStream_t)stream>>>(*g, points, Q, near_pts, near_faces, dist2);
+    BF_LAUNCH_CHECK();
+    return BF_OK;
+}
+
+int bf_smpld_step(const BfGrid* g, const BfSmpld* p, void* stream) {
+    int rc = check_grid(g); if (rc) return rc;
+    BF_REQUIRE(p && p->base && p->disp && p->adam_m && p->adam_v && p->faces && p->vf_ptr && p->vf_face && p->scan_fn &&
+               p->P && p->C && p->near_faces && p->nhat && p->nlen && p->m && p->Nlen && p->dN && p->dcorner &&
+               p->partial && p->totals && p->V > 0 && p->F > 0, "SMPL+D buffers missing");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int V = p->V, F = p->F, nb = 64;
+    k_add3<<<(3 * V + 255) / 256, 256, 0, s>>>(p->base, p->disp, p->P, 3 * V);
+    BF_LAUNCH_CHECK();
+    k_face_normals<<<(F + 255) / 256, 256, 0, s>>>(p->P, p->faces, F, p->nhat, p->nlen);
+    BF_LAUNCH_CHECK();
+    k_vertex_normals<<<(V + 255) / 256, 256, 0, s>>>(p->nhat, p->vf_ptr, p->vf_face, V, p->m, p->Nlen);
+    BF_LAUNCH_CHECK();
+    k_grid_nearest<<<(V + 7) / 8, 256, 0, s>>>(*g, p->P, V, p->C, p->near_faces, nullptr);
+    BF_LAUNCH_CHECK();
+    k_smpld_partials<<<nb, 256, 0, s>>>(p->P, p->C, p->near_faces, p->scan_fn, p->m, p->faces, V, F, p->partial);
+    BF_LAUNCH_CHECK();
+    k_smpld_finish<<<1, 32, 0, s>>>(p->partial, nb, V, F, p->reg_scale, p->totals);
+    BF_LAUNCH_CHECK();
+    k_smpld_dm<<<(V + 255) / 256, 256, 0, s>>>(p->near_faces, p->scan_fn, p->m, p->faces, p->vf_ptr, p->vf_face, V, F,
+                                               p->reg_scale, p->Nlen, p->dN);
+    BF_LAUNCH_CHECK();
+    k_smpld_dface<<<(F + 255) / 256, 256, 0, s>>>(p->P, p->faces, p->nhat, p->nlen, p->dN, F, p->dcorner);
+    BF_LAUNCH_CHECK();
+    const double t = (double)(p->iter + 1);
+    const double bc1 = 1.0 - pow(p->beta1, t), bc2 = 1.0 - pow(p->beta2, t);
+    k_smpld_step<<<(V + 255) / 256, 256, 0, s>>>(p->P, p->C, p->totals, p->dcorner, p->faces, p->vf_ptr, p->vf_face, V,
+                                                 p->disp, p->adam_m, p->adam_v, p->grad, (float)(p->lr / bc1), (float)sqrt(bc2),
+                                                 (float)p->beta2, (float)(1.0 - p->beta1), (float)(1.0 - p->beta2), (float)p->eps);
+    BF_LAUNCH_CHECK();
+    if (p->trace) {
+        if (cudaMemcpyAsync(p->trace + 4 * (size_t)p->iter, p->totals, 4 * sizeof(float), cudaMemcpyDeviceToDevice, s) != cudaSuccess) {
+            bf_set_error("trace copy failed"); return BF_ECUDA;
+        }
+    }
+    return BF_OK;
+}
+
+int bf_smpld_run(const BfGrid* g, const BfSmpld* p, int n_iters, void* stream) {
+    BF_REQUIRE(g && p && n_iters >= 0, "bad arguments");
+    BfSmpld q = *p;
+    for (int i = 0; i < n_iters; ++i) {
+        int rc = bf_smpld_step(g, &q, stream); if (rc) return rc;
+        q.iter++;
+    }
+    return BF_OK;
+}
+
+__global__ void __launch_bounds__(256) k_pc_loss(const float* __restrict__ verts, const float* __restrict__ C, int V, int ld_v,
+                                                 float scale, float weight, float* __restrict__ loss, float* __restrict__ dverts) {
+    __shared__ float red[8];
+    __shared__ float tot_s;
+    const int b = blockIdx.x;
+    const float* P = verts + (size_t)b * ld_v;
+    const float* Cb = C + (size_t)b * V * 3;
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < 3 * V; i += 256) { const float d = P[i] - Cb[i]; acc += d * d; }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) { float s = 0.f; for (int w = 0; w < 8; ++w) s += red[w]; tot_s = sqrtf(s); loss[b] = tot_s * scale; }
+    __syncthreads();
+    const float k = weight * scale / tot_s;
+    float* g = dverts + (size_t)b * ld_v;
+    for (int i = threadIdx.x; i < 3 * V; i += 256) g[i] += k * (P[i] - Cb[i]);
+}
+
+int bf_pc_loss(const BfGrid* g, const float* verts, int B, int V, int ld_v, float scale, float weight,
+               float* near_pts, int32_t* near_faces, float* loss, float* dverts, void* stream) {
+    int rc = check_grid(g); if (rc) return rc;
+    BF_REQUIRE(verts && near_pts && near_faces && loss && dverts && B > 0 && V > 0 && ld_v >= 3 * V, "bad arguments");
+    BF_REQUIRE(ld_v == 3 * V, "closest-point search needs contiguous [B,V,3] vertices");
+    cudaStream_t s = (cudaStream_t)stream;
+    k_grid_nearest<<<(B * V + 7) / 8, 256, 0, s>>>(*g, verts, B * V, near_pts, near_faces, nullptr);
+    BF_LAUNCH_CHECK();
+    k_pc_loss<<<B, 256, 0, s>>>(verts, near_pts, V, ld_v, scale, weight, loss, dverts);
+    BF_LAUNCH_CHECK();
     return BF_OK;
 }
 
