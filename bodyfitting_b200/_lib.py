@@ -108,7 +108,7 @@ def lib():
         'bf_grid_count': [pg, fp, vp], 'bf_grid_fill': [pg, fp, vp],
         'bf_grid_nearest': [pg, fp, i32, fp, fp, fp, vp],
         'bf_smpld_step': [pg, ps, vp], 'bf_smpld_run': [pg, ps, i32, vp],
-        'bf_pc_loss': [pg, fp, i32, i32, i32, fl, fl, fp, fp, fp, fp, vp],
+        'bf_pc_loss': [pg, pm, pf, fl, fl, fp, fp, fp, fp, vp],
     })
     for name, at in ops.items():
         fn = getattr(L, name)

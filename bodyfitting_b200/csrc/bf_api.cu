@@ -408,34 +408,78 @@ int bf_smpld_run(const BfGrid* g, const BfSmpld* p, int n_iters, void* stream) {
     return BF_OK;
 }
 
-__global__ void __launch_bounds__(256) k_pc_loss(const float* __restrict__ verts, const float* __restrict__ C, int V, int ld_v,
-                                                 float scale, float weight, float* __restrict__ loss, float* __restrict__ dverts) {
-    __shared__ float red[8];
-    __shared__ float tot_s;
-    const int b = blockIdx.x;
-    const float* P = verts + (size_t)b * ld_v;
+// world-space copy of the skinned vertices: Pw = (v + transl) * scale * cs  (smplify/smplify.py:190)
+__global__ void k_world_points(const float* __restrict__ verts, const float* __restrict__ theta, int NP, int V, int ld_v,
+                               float cs, float* __restrict__ Pw, int B) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)B * V) return;
+    const int b = (int)(i / V), v = (int)(i % V);
+    const float* th = theta + (size_t)b * NP;
+    const float* p = verts + (size_t)b * ld_v + 3 * v;
+    const float sc = th[3];
+    Pw[3 * i] = (p[0] + th[0]) * sc * cs; Pw[3 * i + 1] = (p[1] + th[1]) * sc * cs; Pw[3 * i + 2] = (p[2] + th[2]) * sc * cs;
+}
+
+// per frame: n = |Pw - C|_F ; loss[b] += weight*scale*n ; g = weight*scale*(Pw - C)/n is d/dPw, chained to the
+// model-space vertices (x s cs), transl (sum g s cs) and scale (sum g.(v+t) cs)
+__global__ void __launch_bounds__(256) k_pc_world_bwd(const float* __restrict__ verts, const float* __restrict__ Pw,
+                                                      const float* __restrict__ C, const float* __restrict__ theta, int NP,
+                                                      int V, int ld_v, float cs, float scale, float weight,
+                                                      float* __restrict__ loss, float* __restrict__ pc_loss,
+                                                      float* __restrict__ dverts, float* __restrict__ grad) {
+    __shared__ float red[4][8];
+    __shared__ float nrm;
+    const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float* P = Pw + (size_t)b * V * 3;
     const float* Cb = C + (size_t)b * V * 3;
     float acc = 0.f;
     for (int i = threadIdx.x; i < 3 * V; i += 256) { const float d = P[i] - Cb[i]; acc += d * d; }
     acc = warp_sum(acc);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    if (lane == 0) red[0][warp] = acc;
     __syncthreads();
-    if (threadIdx.x == 0) { float s = 0.f; for (int w = 0; w < 8; ++w) s += red[w]; tot_s = sqrtf(s); loss[b] = tot_s * scale; }
+    if (threadIdx.x == 0) { float s = 0.f; for (int w = 0; w < 8; ++w) s += red[0][w]; nrm = sqrtf(s); }
     __syncthreads();
-    const float k = weight * scale / tot_s;
-    float* g = dverts + (size_t)b * ld_v;
-    for (int i = threadIdx.x; i < 3 * V; i += 256) g[i] += k * (P[i] - Cb[i]);
+    const float* th = theta + (size_t)b * NP;
+    const float sc = th[3];
+    const float k = weight * scale / nrm;
+    float g0 = 0.f, g1 = 0.f, g2 = 0.f, gs = 0.f;
+    float* dv = dverts + (size_t)b * ld_v;
+    const float* vb = verts + (size_t)b * ld_v;
+    for (int v = threadIdx.x; v < V; v += 256) {
+        float gw[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) gw[d] = k * (P[3 * v + d] - Cb[3 * v + d]);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) dv[3 * v + d] += gw[d] * sc * cs;
+        g0 += gw[0] * sc * cs; g1 += gw[1] * sc * cs; g2 += gw[2] * sc * cs;
+        gs += (gw[0] * (vb[3 * v] + th[0]) + gw[1] * (vb[3 * v + 1] + th[1]) + gw[2] * (vb[3 * v + 2] + th[2])) * cs;
+    }
+    g0 = warp_sum(g0); g1 = warp_sum(g1); g2 = warp_sum(g2); gs = warp_sum(gs);
+    __syncthreads();
+    if (lane == 0) { red[0][warp] = g0; red[1][warp] = g1; red[2][warp] = g2; red[3][warp] = gs; }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        float s = 0.f;
+        for (int w = 0; w < 8; ++w) s += red[threadIdx.x][w];
+        grad[(size_t)b * NP + threadIdx.x] += s;
+    }
+    if (threadIdx.x == 0) { loss[b] += weight * scale * nrm; if (pc_loss) pc_loss[b] = scale * nrm; }
 }
 
-int bf_pc_loss(const BfGrid* g, const float* verts, int B, int V, int ld_v, float scale, float weight,
-               float* near_pts, int32_t* near_faces, float* loss, float* dverts, void* stream) {
+int bf_pc_loss(const BfGrid* g, const BfModel* m, const BfFrames* f, float scale, float weight, float* Pw,
+               float* near_pts, int32_t* near_faces, float* pc_loss, void* stream) {
     int rc = check_grid(g); if (rc) return rc;
-    BF_REQUIRE(verts && near_pts && near_faces && loss && dverts && B > 0 && V > 0 && ld_v >= 3 * V, "bad arguments");
-    BF_REQUIRE(ld_v == 3 * V, "closest-point search needs contiguous [B,V,3] vertices");
+    rc = check_model(m, f); if (rc) return rc;
+    const int V = m->full.n;
+    BF_REQUIRE(f->verts && f->dverts && f->grad && f->loss && Pw && near_pts && near_faces && f->ld_v >= 3 * V, "bad arguments");
     cudaStream_t s = (cudaStream_t)stream;
-    k_grid_nearest<<<(B * V + 7) / 8, 256, 0, s>>>(*g, verts, B * V, near_pts, near_faces, nullptr);
+    const size_t n = (size_t)f->B * V;
+    k_world_points<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(f->verts, f->theta, m->NP, V, f->ld_v, f->constant_scale, Pw, f->B);
     BF_LAUNCH_CHECK();
-    k_pc_loss<<<B, 256, 0, s>>>(verts, near_pts, V, ld_v, scale, weight, loss, dverts);
+    k_grid_nearest<<<(unsigned)((n + 7) / 8), 256, 0, s>>>(*g, Pw, (int)n, near_pts, near_faces, nullptr);
+    BF_LAUNCH_CHECK();
+    k_pc_world_bwd<<<f->B, 256, 0, s>>>(f->verts, Pw, near_pts, f->theta, m->NP, V, f->ld_v, f->constant_scale, scale, weight,
+                                        f->loss, pc_loss, f->dverts, f->grad);
     BF_LAUNCH_CHECK();
     return BF_OK;
 }

@@ -80,7 +80,7 @@ class SMPLify(object):
         if use_mask:
             raise NotImplementedError('silhouette term (smplify/loss.py:85-130) is not part of this build')
         if use_mesh:
-            raise NotImplementedError('scan term: use bodyfitting_b200.smplify.smpld (SMPL+D path)')
+            return self._fit_to_scan(net_output, c2ws, Ks, keypoints, imsize, meshfile, displacement, as_numpy)
         m, dev = self.model, self.device
         init_betas, init_poses, kp = self._pack_inputs(net_output, keypoints)
         B, Nv = kp.shape[0], kp.shape[1]
@@ -107,6 +107,69 @@ class SMPLify(object):
         return out
 
     # ------------------------------------------------------------------------------------------
+    def _fit_to_scan(self, net_output, c2ws, Ks, keypoints, imsize, meshfile, displacement, as_numpy):
+        """``use_mesh=True`` (smplify.py:146-156,205-210,228-247): keypoint objective + 5 x point-to-scan
+        term from iteration N//3+1 on, on ALL vertices (dense backward), then the optional SMPL+D
+        displacement loop.  ``meshfile`` = path of an OBJ or a (vertices, faces) pair."""
+        import ctypes as C
+        from .. import _lib
+        from ..engine import FrameBuffers, _stream
+        from ..utils.io_utils import load_obj_mesh
+        from ..utils.mesh_grid_searcher import MeshGridSearcher
+        from .smpld import DisplacementFitter
+        m, dev, N = self.model, self.device, int(self.num_iters)
+        scan_verts, scan_faces = load_obj_mesh(meshfile) if isinstance(meshfile, str) else meshfile
+        scan_verts, scan_faces = np.asarray(scan_verts), np.asarray(scan_faces)
+        tris = scan_verts[scan_faces]
+        face_norms = np.cross(tris[:, 1] - tris[:, 0], tris[:, 2] - tris[:, 0])
+        scan_height = float((scan_verts.max(0) - scan_verts.min(0))[1])
+        constant_scale = scan_height / 1.7                                            # smplify.py:156
+        searcher = MeshGridSearcher(verts=scan_verts, faces=scan_faces, device=dev)
+        init_betas, init_poses, kp = self._pack_inputs(net_output, keypoints)
+        B, Nv = kp.shape[0], kp.shape[1]
+        fb = FrameBuffers(m, B, full=True, Nv=Nv, n_trace=N, imsize=imsize, constant_scale=constant_scale)
+        kp_dev = self._h2d('kp', kp)
+        poses_dev, betas_dev = self._h2d('poses', init_poses), self._h2d('betas', init_betas)
+        fb.bind('kp', pack_keypoints(kp_dev, self.use_hand_face))
+        fb.bind('cams', self._h2d('cams', torch.from_numpy(pack_cameras(c2ws, Ks))))
+        fb.t['theta'].copy_(m.pack_theta(poses_dev[:, :3], poses_dev[:, 3:3 + m.nbody], betas_dev))
+        Pw = torch.empty(B, m.V, 3, device=dev)
+        near = torch.empty(B, m.V, 3, device=dev)
+        near_f = torch.empty(B, m.V, dtype=torch.int32, device=dev)
+        pc = torch.zeros(B, device=dev)
+        L = _lib.lib()
+        for i in range(N):
+            fb.struct.iter = i
+            fb.call('bf_pose_forward')
+            fb.call('bf_skin_forward', 1)
+            fb.call('bf_keypoint_loss', 1)
+            if i > (N // 3):
+                _lib.check(L.bf_pc_loss(C.byref(searcher.grid), m.struct, fb.struct, float(imsize / scan_height), 5.0,
+                                        Pw.data_ptr(), near.data_ptr(), near_f.data_ptr(), pc.data_ptr(), _stream()), 'bf_pc_loss')
+            fb.call('bf_gmm_prior')
+            if i == N - 1:
+                theta_prev = fb.t['theta'].clone()
+            fb.call('bf_skin_backward', 1)
+            fb.call('bf_pose_backward', 1 | 2 | 4)
+        fb.call('bf_joints_forward', 1)                                   # joints of the last forward pass
+        sp, sn = m.split_theta(theta_prev), m.split_theta(fb.t['theta'])
+        t, s = sp['transl'][:, None, :], sp['scale'][:, None, :]
+        verts = (fb.t['verts'].view(B, m.V, 3) + t) * s * constant_scale
+        out = dict(vertices=verts, joints=(fb.t['joints'][:, :m.K_out] + t) * s * constant_scale, pose=sn['body_pose'],
+                   betas=sn['betas'], global_orient=sn['global_orient'], global_transl=sn['transl'] * sn['scale'],
+                   scale=sn['scale'], full_pose=fb.t['full_pose'])
+        self.last_trace, self.last_loss_terms, self.last_pc_loss = fb.t['trace'], fb.t['loss_terms'], pc
+        if displacement:
+            assert B == 1, 'the displacement fit takes one subject per call (smplify.py:229-247)'
+            fitter = DisplacementFitter(searcher, face_norms, m.faces, m.V, constant_scale, device=dev)
+            disp, dtrace = fitter.run(verts[0], N)
+            out['displacement'] = disp[None]
+            self.last_disp_trace = dtrace
+        if as_numpy:
+            out = {k: v.detach().cpu().squeeze(0).numpy() for k, v in out.items()}
+        out['faces'] = self.smpl_faces[0]
+        return out
+
     def session(self, B, Nv, imsize=512, return_vertices=True):
         key = (int(B), int(Nv), int(self.num_iters), float(imsize), bool(return_vertices))
         if getattr(self, '_sess_key', None) != key:

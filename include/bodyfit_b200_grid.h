@@ -9,6 +9,7 @@
 #ifndef BODYFIT_B200_GRID_H
 #define BODYFIT_B200_GRID_H
 #include <stdint.h>
+#include "bodyfit_b200.h"
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -64,10 +65,12 @@ typedef struct BfSmpld {
 int bf_smpld_step(const BfGrid* g, const BfSmpld* s, void* stream);
 int bf_smpld_run(const BfGrid* g, const BfSmpld* s, int n_iters, void* stream);
 
-/* point-to-scan term of the main loop (smplify/loss.py:233-242, smplify/smplify.py:205-206) for B frames:
- * loss[b] = |P_b - C_b|_F * scale ; dverts[b] += weight * scale * (P_b - C_b)/|P_b - C_b|_F */
-int bf_pc_loss(const BfGrid* g, const float* verts, int B, int V, int ld_v, float scale, float weight,
-               float* near_pts, int32_t* near_faces, float* loss, float* dverts, void* stream);
+/* point-to-scan term of the main loop (smplify/loss.py:233-242, smplify/smplify.py:205-206,210) for the B frames of
+ * `f` (all-vertex buffers, model-space f->verts): Pw = (verts + transl) * scale * constant_scale; closest points;
+ * pc = scale * |Pw - C|_F per frame; f->loss[b] += weight * pc; its gradient is ADDED to f->dverts (model space)
+ * and f->grad[:, 0:4] (transl, scale).  Pw, near_pts [B,V,3] and near_faces [B,V] are scratch / outputs. */
+int bf_pc_loss(const BfGrid* g, const BfModel* m, const BfFrames* f, float scale, float weight, float* Pw,
+               float* near_pts, int32_t* near_faces, float* pc_loss, void* stream);
 
 #ifdef __cplusplus
 }

@@ -288,6 +288,41 @@ class FitPort(object):
             opt.step()
         return self._result(p, out, joints, verts, False), torch.stack(trace).numpy()
 
+    # -- keypoints + point-to-scan term (use_mesh=True, smplify/smplify.py:146-156,205-210) ----------
+    def fit_batched_scan(self, init_betas, init_poses, c2ws, Ks, kp, scan_verts, scan_faces, num_iters=12, imsize=512):
+        """B frames against ONE scan; the CUDA-only mesh_grid closest point is replaced by the exact fp64
+        brute force (oracle/geometry_port.py); per frame pc = |P - C.detach()|_F / scan_height * imsize,
+        loss = body + 5 pc for i > num_iters // 3."""
+        from oracle import geometry_port as gp
+        kp = torch.as_tensor(kp, dtype=self.dtype)
+        B = kp.shape[0]
+        sv = np.asarray(scan_verts, dtype=np.float64)
+        scan_height = float((sv.max(0) - sv.min(0))[1])
+        cs = scan_height / 1.7
+        p = self._init_params(init_betas, init_poses, B)
+        w2cs = torch.inverse(torch.as_tensor(np.array(c2ws), dtype=self.dtype))
+        Kt = torch.as_tensor(np.array(Ks), dtype=self.dtype)
+        opt = self._optimizer(p)
+        trace, pcs = [], []
+        for it in range(num_iters):
+            out = self.forward_model(p)
+            joints = (out.joints + p['global_transl'].unsqueeze(1)) * p['body_scale'].unsqueeze(1) * cs
+            verts = (out.vertices + p['global_transl'].unsqueeze(1)) * p['body_scale'].unsqueeze(1) * cs
+            per_frame, _ = batched_objective(w2cs, Kt, kp, joints, p['body_pose'], p['betas'], self.prior, imsize,
+                                             self.use_hand_face)
+            if it > (num_iters // 3):
+                cp, _, _ = gp.closest_points_bruteforce(verts.detach().reshape(-1, 3).numpy(), sv, scan_faces)
+                cp = torch.as_tensor(cp.reshape(B, -1, 3), dtype=self.dtype)
+                pc = torch.sqrt(((verts - cp) ** 2).sum(dim=(1, 2))) / scan_height * imsize
+                per_frame = per_frame + 5 * pc
+                pcs.append(pc.detach().clone())
+            trace.append(per_frame.detach().clone())
+            opt.zero_grad()
+            per_frame.sum().backward()
+            opt.step()
+        res = self._result(p, out, joints, verts, False)
+        return res, torch.stack(trace).numpy(), (torch.stack(pcs).numpy() if pcs else None)
+
     # -- single evaluation: loss + grads (for kernel gradient parity) ---------------
     def loss_and_grads(self, params, c2ws, Ks, kp, imsize=512):
         kp = torch.as_tensor(kp, dtype=self.dtype)
