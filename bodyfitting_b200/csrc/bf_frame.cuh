@@ -43,7 +43,7 @@ __device__ __forceinline__ float warp_reduce16(const float* v, int lane) {
     return d;
 }
 
-__global__ void __launch_bounds__(FR_THREADS) k_frame_loss_bwd(BfModel m, BfVSet vs, BfFrames f) {
+__global__ void __launch_bounds__(FR_THREADS, 4) k_frame_loss_bwd(BfModel m, BfVSet vs, BfFrames f) {
     extern __shared__ __align__(16) float sm[];
     float* gx = sm;                               // [BF_MAXK*3] joint gradients
     float* cam = gx + BF_MAXK * 3;                // [BF_MAXVIEWS*12]
@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(FR_THREADS) k_frame_loss_bwd(BfModel m, BfVSet
     const float* th = f.theta + (size_t)b * m.NP;
     const float tx = th[0], ty = th[1], tz = th[2], sc = th[3];
     const float cs = f.constant_scale;
-    const float coef = f.imsize / 1024.0f;
+    const float icoef = 1024.0f / f.imsize;          // 1 / scale_coeff (exact for power-of-two image sizes)
     const float s2 = f.sigma * f.sigma;
     const int yaw = f.yaw ? f.yaw[b] : 0;
     const float* Jtr_b = f.Jtr + (size_t)b * J * 3;
@@ -95,14 +95,15 @@ __global__ void __launch_bounds__(FR_THREADS) k_frame_loss_bwd(BfModel m, BfVSet
             const float p0 = M[0] * X + M[1] * Y + M[2] * Z + M[3];
             const float p1 = M[4] * X + M[5] * Y + M[6] * Z + M[7];
             const float p2 = M[8] * X + M[9] * Y + M[10] * Z + M[11];
-            const float iz = 1.0f / p2;
+            // three correctly-rounded reciprocals instead of seven IEEE divisions: 1/p2, 1/(s^2+rx^2), 1/(s^2+ry^2)
+            const float iz = __frcp_rn(p2);
             const float u = p0 * iz, w_ = p1 * iz;
-            const float rx = (kx - u) / coef, ry = (ky - w_) / coef;
+            const float rx = (kx - u) * icoef, ry = (ky - w_) * icoef;
             const float rx2 = rx * rx, ry2 = ry * ry;
-            const float dx = s2 + rx2, dy = s2 + ry2;
-            ls += wgt * ((s2 * rx2) / dx + (s2 * ry2) / dy);
-            const float du = wgt * (2.0f * s2 * s2 * rx / (dx * dx)) * (-1.0f / coef);
-            const float dw = wgt * (2.0f * s2 * s2 * ry / (dy * dy)) * (-1.0f / coef);
+            const float ix = __frcp_rn(s2 + rx2), iy = __frcp_rn(s2 + ry2);
+            ls += wgt * (s2 * rx2 * ix + s2 * ry2 * iy);
+            const float du = wgt * (2.0f * s2 * s2 * rx * ix * ix) * (-icoef);
+            const float dw = wgt * (2.0f * s2 * s2 * ry * iy * iy) * (-icoef);
             const float dp0 = du * iz, dp1 = dw * iz, dp2 = -(du * u + dw * w_) * iz;
             g0 += M[0] * dp0 + M[4] * dp1 + M[8] * dp2;
             g1 += M[1] * dp0 + M[5] * dp1 + M[9] * dp2;
@@ -148,7 +149,9 @@ __global__ void __launch_bounds__(FR_THREADS) k_frame_loss_bwd(BfModel m, BfVSet
         float T[9];
 #pragma unroll
         for (int e = 0; e < 9; ++e) T[e] = 0.f;
-        for (int k = 0; k < nnz; ++k) {
+        // contour candidates not selected by this frame's yaw row carry an exactly-zero gradient
+        const bool live = dv[3 * v] != 0.f || dv[3 * v + 1] != 0.f || dv[3 * v + 2] != 0.f;
+        for (int k = 0; live && k < nnz; ++k) {
             const float w = __ldg(ew + k);
             const float4* Aj = reinterpret_cast<const float4*>(As + __ldg(ej + k) * 12);
             const float4 r0 = Aj[0], r1 = Aj[1], r2 = Aj[2];

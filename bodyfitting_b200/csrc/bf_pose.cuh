@@ -114,6 +114,11 @@ __device__ __forceinline__ void pose_forward_from_smem(const BfModel& m, PoseSme
 // posed joints, full pose, contour-landmark row
 __device__ __forceinline__ void pose_write_outputs(const BfModel& m, const BfFrames& f, PoseSmem& S, int b, int lane) {
     const int J = m.J;
+    if (f.fwd_state) {                       // [fp 3J | R 9J | Jr 3J | GR 9J] for the backward pass
+        float* st = f.fwd_state + (size_t)b * 24 * J;
+        for (int i = lane; i < 3 * J; i += 32) { st[i] = S.fp[i]; st[12 * J + i] = S.Jr[i]; }
+        for (int i = lane; i < 9 * J; i += 32) { st[3 * J + i] = S.R[i]; st[15 * J + i] = S.GR[i]; }
+    }
     // GEMM A operand row: [R_1..R_{J-1} - I | shape | 1 | 0...]
     float* pf = f.pf + (size_t)b * m.Kp;
     for (int i = lane; i < m.Kp; i += 32) {
@@ -195,7 +200,15 @@ __global__ void __launch_bounds__(128) k_pose_bwd(BfModel m, BfFrames f, int fla
     PoseSmem& S = W.f;
     const int J = m.J;
     const ThetaLayout L = theta_layout(m.is_smplx);
-    pose_forward_warp(m, f.theta + (size_t)b * m.NP, S, lane);
+    if (f.fwd_state) {                       // forward state saved by the pose forward of this iteration
+        const float* st = f.fwd_state + (size_t)b * 24 * J;
+        for (int i = lane; i < L.np; i += 32) S.th[i] = f.theta[(size_t)b * m.NP + i];
+        for (int i = lane; i < 3 * J; i += 32) { S.fp[i] = st[i]; S.Jr[i] = st[12 * J + i]; }
+        for (int i = lane; i < 9 * J; i += 32) { S.R[i] = st[3 * J + i]; S.GR[i] = st[15 * J + i]; }
+        __syncwarp();
+    } else {
+        pose_forward_warp(m, f.theta + (size_t)b * m.NP, S, lane);
+    }
 
     // direct terms
     for (int j = lane; j < J; j += 32) {

@@ -73,6 +73,7 @@ class FrameBuffers(object):
             buf('loss_terms', B, 4, zero=True)
             buf('gmm_grad', B, 69, zero=True)
             buf('gmm_loss', B, zero=True)
+            buf('fwd_state', B, 24 * J)
         if n_trace:
             buf('trace', n_trace, B, zero=True)
         self.t = t

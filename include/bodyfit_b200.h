@@ -40,7 +40,7 @@ extern "C" {
 #define BF_ECUDA    -2   /* a CUDA runtime call / launch failed            */
 #define BF_EARCH    -3   /* device is not sm_100 (no fallback exists)      */
 
-#define BF_ABI_VERSION 8
+#define BF_ABI_VERSION 9
 #define BF_F_WORLD 1   /* forward outputs in world space: (x + transl) * scale * constant_scale */
 #define BF_F_TC    2   /* run the blend-shape contractions on tcgen05 tensor cores (3xTF32) */
 
@@ -123,6 +123,8 @@ typedef struct BfFrames {
     float*       dvp_lo;
     float*       gmm_grad;   /* [B,69] w_pose^2 * gradient of the GMM prior (k_gmm_prior -> k_pose_bwd) */
     float*       gmm_loss;   /* [B]    w_pose^2 * min_m ll_m */
+    float*       fwd_state;  /* [B,24J] optional: full_pose, R, rest joints, chain rotations saved by the pose forward so the
+                                pose backward does not recompute them */
     float*       ws;         /* split-K workspace of the tensor-core backward GEMM (>= ceil(ldn/2048) * B * Kp floats) or NULL */
     int64_t      ws_floats;
     double lr_ts, lr, beta1, beta2, eps;   /* Adam hyper-parameters (python floats in the reference: smplify.py:167-174) */
