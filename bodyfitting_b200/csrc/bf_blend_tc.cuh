@@ -104,7 +104,7 @@ struct Pipe {
     uint8_t* stage_base;
     uint64_t* full;
     uint64_t* empty;
-    uint64_t* tmem_full;
+    uint64_t* tmem_full;      // one barrier (backward GEMM) or two (double-buffered forward)
     uint32_t a_bytes, b_bytes;
     __device__ __forceinline__ uint32_t stage_bytes() const { return 2 * a_bytes + 2 * b_bytes; }
     __device__ __forceinline__ uint8_t* stage(int s) const { return stage_base + (size_t)s * stage_bytes(); }
@@ -150,13 +150,17 @@ __device__ __forceinline__ void mma_issuer(const Pipe& p, int num_k, uint32_t tm
 
 }  // namespace tc
 
+// Persistent: one CTA per SM walks the (frame tile, vertex tile) list (vertex tile fastest, so that CTAs running
+// together share the same pf rows in L2).  Two TMEM accumulators: the MMA warp fills buffer (i+1)&1 while the four
+// epilogue warps skin buffer i&1.
 __global__ void __launch_bounds__(192, 1) k_skin_fwd_tc(const __grid_constant__ CUtensorMap mA_hi,
                                                         const __grid_constant__ CUtensorMap mA_lo,
                                                         const __grid_constant__ CUtensorMap mB_hi,
                                                         const __grid_constant__ CUtensorMap mB_lo,
                                                         BfVSet vs, int J, int Kp, const float* __restrict__ A,
                                                         float* __restrict__ verts, float* __restrict__ vposed,
-                                                        int B, int ld_v, const float* __restrict__ theta, int NP, float cs) {
+                                                        int B, int ld_v, const float* __restrict__ theta, int NP, float cs,
+                                                        int n_tiles_n, int n_tiles) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     tc::Pipe p;
@@ -165,103 +169,156 @@ __global__ void __launch_bounds__(192, 1) k_skin_fwd_tc(const __grid_constant__ 
     p.stage_base = base;
     float* Vp = reinterpret_cast<float*>(base + TC_STAGES * p.stage_bytes());
     uint64_t* bars = reinterpret_cast<uint64_t*>(Vp + 4 * 32 * TC_VP_LD);
-    p.full = bars; p.empty = bars + TC_STAGES; p.tmem_full = bars + 2 * TC_STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 1);
+    p.full = bars; p.empty = bars + TC_STAGES; p.tmem_full = bars + 2 * TC_STAGES;      // tmem_full[2]
+    uint64_t* tmem_empty = bars + 2 * TC_STAGES + 2;                                   // tmem_empty[2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b0 = blockIdx.y * TC_BM;
-    const int n0 = blockIdx.x * TC_BN1;
     const int num_k = Kp / TC_BK;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; ++s) { tc::mbar_init(&p.full[s], 1); tc::mbar_init(&p.empty[s], 1); }
-        tc::mbar_init(p.tmem_full, 1);
+        for (int s = 0; s < 2; ++s) { tc::mbar_init(&p.tmem_full[s], 1); tc::mbar_init(&tmem_empty[s], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(tmem_slot)), "r"(256));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(tmem_slot)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
-    const uint32_t tmem_d = *tmem_slot;
+    const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) tc::producer(p, &mA_hi, &mA_lo, &mB_hi, &mB_lo, num_k, b0, n0);
+        if (lane == 0) {
+            int it = 0;                                              // running K-chunk counter across tiles
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                const int b0 = (t / n_tiles_n) * TC_BM, n0 = (t % n_tiles_n) * TC_BN1;
+                for (int kc = 0; kc < num_k; ++kc, ++it) {
+                    const int s = it % TC_STAGES;
+                    const uint32_t ph = (it / TC_STAGES) & 1;
+                    tc::mbar_wait(&p.empty[s], ph ^ 1);
+                    tc::mbar_expect_tx(&p.full[s], p.stage_bytes());
+                    uint8_t* st = p.stage(s);
+                    tc::tma_load_2d(st, &mA_hi, &p.full[s], kc * TC_BK, b0);
+                    tc::tma_load_2d(st + p.a_bytes, &mA_lo, &p.full[s], kc * TC_BK, b0);
+                    tc::tma_load_2d(st + 2 * p.a_bytes, &mB_hi, &p.full[s], kc * TC_BK, n0);
+                    tc::tma_load_2d(st + 2 * p.a_bytes + p.b_bytes, &mB_lo, &p.full[s], kc * TC_BK, n0);
+                }
+            }
+        }
     } else if (warp == 1) {
-        if (lane == 0) tc::mma_issuer(p, num_k, tmem_d, tc::make_idesc_tf32(TC_BM, TC_BN1));
+        if (lane == 0) {
+            const uint32_t idesc = tc::make_idesc_tf32(TC_BM, TC_BN1);
+            int it = 0, i = 0;
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+                const int buf = i & 1;
+                tc::mbar_wait(&tmem_empty[buf], ((i >> 1) & 1) ^ 1);          // epilogue has drained this accumulator
+                tc::tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(buf * TC_BN1);
+                for (int kc = 0; kc < num_k; ++kc, ++it) {
+                    const int s = it % TC_STAGES;
+                    const uint32_t ph = (it / TC_STAGES) & 1;
+                    tc::mbar_wait(&p.full[s], ph);
+                    tc::tc_fence_after();
+                    uint8_t* st = p.stage(s);
+                    const uint64_t a_hi = tc::make_desc(st), a_lo = tc::make_desc(st + p.a_bytes);
+                    const uint64_t b_hi = tc::make_desc(st + 2 * p.a_bytes), b_lo = tc::make_desc(st + 2 * p.a_bytes + p.b_bytes);
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 8; ++k) {
+                        const uint64_t o = (uint64_t)(2 * k);
+                        tc::umma_tf32(tmem_d, a_hi + o, b_hi + o, idesc, (kc | k) ? 1u : 0u);
+                        tc::umma_tf32(tmem_d, a_lo + o, b_hi + o, idesc, 1u);
+                        tc::umma_tf32(tmem_d, a_hi + o, b_lo + o, idesc, 1u);
+                    }
+                    tc::umma_commit(&p.empty[s]);
+                }
+                tc::umma_commit(&p.tmem_full[buf]);
+            }
+        }
     } else {
-        tc::mbar_wait(p.tmem_full, 0);
-        tc::tc_fence_after();
         const int q = warp & 3;                               // TMEM lane quarter this warp may read
         float* myVp = Vp + (warp - 2) * 32 * TC_VP_LD;
         const int nnz = vs.nnz;
-        for (int chunk = 0; chunk < TC_BN1 / 96; ++chunk) {
+        int i = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+            const int buf = i & 1;
+            const int b0 = (t / n_tiles_n) * TC_BM, n0 = (t % n_tiles_n) * TC_BN1;
+            tc::mbar_wait(&p.tmem_full[buf], (i >> 1) & 1);
+            tc::tc_fence_after();
+            const uint32_t tmem_d = tmem_base + (uint32_t)(buf * TC_BN1);
+            for (int chunk = 0; chunk < TC_BN1 / 96; ++chunk) {
 #pragma unroll 1
-            for (int part = 0; part < 3; ++part) {
-                uint32_t r[32];
-                tc::tmem_ld32(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(chunk * 96 + part * 32), r);
+                for (int part = 0; part < 3; ++part) {
+                    uint32_t r[32];
+                    tc::tmem_ld32(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(chunk * 96 + part * 32), r);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) myVp[lane * TC_VP_LD + part * 32 + i] = __uint_as_float(r[i]);
-            }
-            __syncwarp();
-            const int v = n0 / 3 + chunk * 32 + lane;
-            if (v < vs.n) {
-                const int32_t* ej = vs.ell_j + (size_t)v * nnz;
-                const float* ew = vs.ell_w + (size_t)v * nnz;
-                int jo[4]; float jw[4];                      // first 4 influences in registers (SMPL / SMPL-X: nnz = 4)
+                    for (int e = 0; e < 32; ++e) myVp[lane * TC_VP_LD + part * 32 + e] = __uint_as_float(r[e]);
+                }
+                if (chunk == TC_BN1 / 96 - 1) {               // accumulator fully read: hand it back to the MMA warp
+                    tc::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(&tmem_empty[buf])) : "memory");
+                }
+                __syncwarp();
+                const int v = n0 / 3 + chunk * 32 + lane;
+                if (v < vs.n) {
+                    const int32_t* ej = vs.ell_j + (size_t)v * nnz;
+                    const float* ew = vs.ell_w + (size_t)v * nnz;
+                    int jo[4]; float jw[4];                      // first 4 influences in registers (SMPL / SMPL-X: nnz = 4)
 #pragma unroll
-                for (int k = 0; k < 4; ++k) { jo[k] = (k < nnz) ? __ldg(ej + k) * 12 : 0; jw[k] = (k < nnz) ? __ldg(ew + k) : 0.f; }
-                for (int fr = 0; fr < 32; ++fr) {
-                    const int b = b0 + 32 * q + fr;
-                    if (b >= B) break;
-                    const float px = myVp[fr * TC_VP_LD + 3 * lane], py = myVp[fr * TC_VP_LD + 3 * lane + 1],
-                                pz = myVp[fr * TC_VP_LD + 3 * lane + 2];
-                    float T[12];
+                    for (int k = 0; k < 4; ++k) { jo[k] = (k < nnz) ? __ldg(ej + k) * 12 : 0; jw[k] = (k < nnz) ? __ldg(ew + k) : 0.f; }
+                    for (int fr = 0; fr < 32; ++fr) {
+                        const int b = b0 + 32 * q + fr;
+                        if (b >= B) break;
+                        const float px = myVp[fr * TC_VP_LD + 3 * lane], py = myVp[fr * TC_VP_LD + 3 * lane + 1],
+                                    pz = myVp[fr * TC_VP_LD + 3 * lane + 2];
+                        float T[12];
 #pragma unroll
-                    for (int e = 0; e < 12; ++e) T[e] = 0.f;
-                    const float* Ab = A + (size_t)b * J * 12;
+                        for (int e = 0; e < 12; ++e) T[e] = 0.f;
+                        const float* Ab = A + (size_t)b * J * 12;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const float w = jw[k];
-                        const float4* Aj = reinterpret_cast<const float4*>(Ab + jo[k]);
-                        const float4 r0 = __ldg(Aj), r1 = __ldg(Aj + 1), r2 = __ldg(Aj + 2);
-                        T[0] = fmaf(w, r0.x, T[0]); T[1] = fmaf(w, r0.y, T[1]); T[2] = fmaf(w, r0.z, T[2]); T[3] = fmaf(w, r0.w, T[3]);
-                        T[4] = fmaf(w, r1.x, T[4]); T[5] = fmaf(w, r1.y, T[5]); T[6] = fmaf(w, r1.z, T[6]); T[7] = fmaf(w, r1.w, T[7]);
-                        T[8] = fmaf(w, r2.x, T[8]); T[9] = fmaf(w, r2.y, T[9]); T[10] = fmaf(w, r2.z, T[10]); T[11] = fmaf(w, r2.w, T[11]);
-                    }
-                    for (int k = 4; k < nnz; ++k) {
-                        const float w = __ldg(ew + k);
-                        const float4* Aj = reinterpret_cast<const float4*>(Ab + __ldg(ej + k) * 12);
-                        const float4 r0 = __ldg(Aj), r1 = __ldg(Aj + 1), r2 = __ldg(Aj + 2);
-                        T[0] = fmaf(w, r0.x, T[0]); T[1] = fmaf(w, r0.y, T[1]); T[2] = fmaf(w, r0.z, T[2]); T[3] = fmaf(w, r0.w, T[3]);
-                        T[4] = fmaf(w, r1.x, T[4]); T[5] = fmaf(w, r1.y, T[5]); T[6] = fmaf(w, r1.z, T[6]); T[7] = fmaf(w, r1.w, T[7]);
-                        T[8] = fmaf(w, r2.x, T[8]); T[9] = fmaf(w, r2.y, T[9]); T[10] = fmaf(w, r2.z, T[10]); T[11] = fmaf(w, r2.w, T[11]);
-                    }
-                    float ox = T[0] * px + T[1] * py + T[2] * pz + T[3];
-                    float oy = T[4] * px + T[5] * py + T[6] * pz + T[7];
-                    float oz = T[8] * px + T[9] * py + T[10] * pz + T[11];
-                    if (theta) {
-                        const float* th = theta + (size_t)b * NP;
-                        const float sc = __ldg(th + 3);
-                        ox = (ox + __ldg(th + 0)) * sc * cs; oy = (oy + __ldg(th + 1)) * sc * cs; oz = (oz + __ldg(th + 2)) * sc * cs;
-                    }
-                    float* o = verts + (size_t)b * ld_v + 3 * v;
-                    o[0] = ox; o[1] = oy; o[2] = oz;
-                    if (vposed) {
-                        float* qv = vposed + (size_t)b * ld_v + 3 * v;
-                        qv[0] = px; qv[1] = py; qv[2] = pz;
+                        for (int k = 0; k < 4; ++k) {
+                            const float w = jw[k];
+                            const float4* Aj = reinterpret_cast<const float4*>(Ab + jo[k]);
+                            const float4 r0 = __ldg(Aj), r1 = __ldg(Aj + 1), r2 = __ldg(Aj + 2);
+                            T[0] = fmaf(w, r0.x, T[0]); T[1] = fmaf(w, r0.y, T[1]); T[2] = fmaf(w, r0.z, T[2]); T[3] = fmaf(w, r0.w, T[3]);
+                            T[4] = fmaf(w, r1.x, T[4]); T[5] = fmaf(w, r1.y, T[5]); T[6] = fmaf(w, r1.z, T[6]); T[7] = fmaf(w, r1.w, T[7]);
+                            T[8] = fmaf(w, r2.x, T[8]); T[9] = fmaf(w, r2.y, T[9]); T[10] = fmaf(w, r2.z, T[10]); T[11] = fmaf(w, r2.w, T[11]);
+                        }
+                        for (int k = 4; k < nnz; ++k) {
+                            const float w = __ldg(ew + k);
+                            const float4* Aj = reinterpret_cast<const float4*>(Ab + __ldg(ej + k) * 12);
+                            const float4 r0 = __ldg(Aj), r1 = __ldg(Aj + 1), r2 = __ldg(Aj + 2);
+                            T[0] = fmaf(w, r0.x, T[0]); T[1] = fmaf(w, r0.y, T[1]); T[2] = fmaf(w, r0.z, T[2]); T[3] = fmaf(w, r0.w, T[3]);
+                            T[4] = fmaf(w, r1.x, T[4]); T[5] = fmaf(w, r1.y, T[5]); T[6] = fmaf(w, r1.z, T[6]); T[7] = fmaf(w, r1.w, T[7]);
+                            T[8] = fmaf(w, r2.x, T[8]); T[9] = fmaf(w, r2.y, T[9]); T[10] = fmaf(w, r2.z, T[10]); T[11] = fmaf(w, r2.w, T[11]);
+                        }
+                        float ox = T[0] * px + T[1] * py + T[2] * pz + T[3];
+                        float oy = T[4] * px + T[5] * py + T[6] * pz + T[7];
+                        float oz = T[8] * px + T[9] * py + T[10] * pz + T[11];
+                        if (theta) {
+                            const float* th = theta + (size_t)b * NP;
+                            const float sc = __ldg(th + 3);
+                            ox = (ox + __ldg(th + 0)) * sc * cs; oy = (oy + __ldg(th + 1)) * sc * cs; oz = (oz + __ldg(th + 2)) * sc * cs;
+                        }
+                        float* o = verts + (size_t)b * ld_v + 3 * v;
+                        o[0] = ox; o[1] = oy; o[2] = oz;
+                        if (vposed) {
+                            float* qv = vposed + (size_t)b * ld_v + 3 * v;
+                            qv[0] = px; qv[1] = py; qv[2] = pz;
+                        }
                     }
                 }
+                __syncwarp();
             }
-            __syncwarp();
         }
     }
     tc::tc_fence_before();
     __syncthreads();
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(256));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
     }
 }
 
@@ -395,16 +452,22 @@ static int bf_skin_forward_tc(const BfModel* m, const BfVSet* vs, const BfFrames
     if ((rc = bf_make_map(&a_lo, f->pf_lo, f->B, m->Kp, m->Kp, TC_BM))) return rc;
     if ((rc = bf_make_map(&b_hi, vs->Bt_hi, vs->ldn, m->Kp, m->Kp, TC_BN1))) return rc;
     if ((rc = bf_make_map(&b_lo, vs->Bt_lo, vs->ldn, m->Kp, m->Kp, TC_BN1))) return rc;
-    const size_t smem = 1024 + TC_STAGES * (2 * TC_BM * 128 + 2 * TC_BN1 * 128) + 4 * 32 * TC_VP_LD * 4 + 64;
+    const size_t smem = 1024 + TC_STAGES * (2 * TC_BM * 128 + 2 * TC_BN1 * 128) + 4 * 32 * TC_VP_LD * 4 + 128;
     static bool attr = false;
+    static int num_sms = 0;
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(k_skin_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { bf_set_error("cudaFuncSetAttribute(k_skin_fwd_tc): %s", cudaGetErrorString(e)); return BF_ECUDA; }
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
         attr = true;
     }
-    const dim3 grid((vs->ldn + TC_BN1 - 1) / TC_BN1, (f->B + TC_BM - 1) / TC_BM);
+    const int tn = (vs->ldn + TC_BN1 - 1) / TC_BN1, tm = (f->B + TC_BM - 1) / TC_BM;
+    const int tiles = tn * tm;
+    const int grid = tiles < num_sms ? tiles : num_sms;          // persistent: one CTA per SM
     k_skin_fwd_tc<<<grid, 192, smem, s>>>(a_hi, a_lo, b_hi, b_lo, *vs, m->J, m->Kp, f->A, f->verts, f->vposed, f->B, f->ld_v,
-                                          (f->flags & BF_F_WORLD) ? f->theta : nullptr, m->NP, f->constant_scale);
+                                          (f->flags & BF_F_WORLD) ? f->theta : nullptr, m->NP, f->constant_scale, tn, tiles);
     BF_LAUNCH_CHECK();
     return BF_OK;
 }
