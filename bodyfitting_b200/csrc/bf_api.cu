@@ -287,20 +287,46 @@ int bf_frame_loss_backward(const BfModel* m, const BfFrames* f, void* stream) {
     return BF_OK;
 }
 
+// The GMM prior only needs theta, so it runs on a side stream next to the blend / loss kernels of the same
+// iteration (fork after the parameters are final, join before the pose backward).  One side stream and two
+// events per device, created on first use.
+struct SideStream { cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+static SideStream* side_stream() {
+    static SideStream per_dev[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    SideStream* ss = &per_dev[dev];
+    if (!ss->s) {
+        if (cudaStreamCreateWithFlags(&ss->s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&ss->fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&ss->join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    }
+    return ss;
+}
+
 static int fit_iteration(const BfModel* m, const BfFrames* f, bool with_forward, bool fuse_next, void* stream) {
     int rc;
+    cudaStream_t main_s = (cudaStream_t)stream;
+    SideStream* ss = side_stream();
+    if (ss) {                                                     // theta of this iteration is final here
+        cudaEventRecord(ss->fork, main_s);
+        cudaStreamWaitEvent(ss->s, ss->fork, 0);
+        rc = bf_gmm_prior(m, f, ss->s); if (rc) return rc;
+        cudaEventRecord(ss->join, ss->s);
+    }
     if (with_forward) { rc = bf_pose_forward(m, f, stream); if (rc) return rc; }
     rc = bf_skin_forward(m, f, 0, stream); if (rc) return rc;
     const size_t fused_smem = sizeof(float) * (BF_MAXK * 6 + BF_MAXVIEWS * 12 + 64 + ((m->J * 12 + 15) & ~15) + 2 * (size_t)m->act.ldn);
     if (fused_smem <= 48 * 1024) {
         rc = bf_frame_loss_backward(m, f, stream); if (rc) return rc;          // loss + dverts (on chip) + dvp + dA
-        rc = bf_gmm_prior(m, f, stream); if (rc) return rc;
+        if (!ss) { rc = bf_gmm_prior(m, f, stream); if (rc) return rc; }
         rc = bf_skin_backward_parts(m, f, 0, 4, stream); if (rc) return rc;    // dpf = dvp @ Bm^T
     } else {
         rc = bf_keypoint_loss(m, f, 0, stream); if (rc) return rc;
-        rc = bf_gmm_prior(m, f, stream); if (rc) return rc;
+        if (!ss) { rc = bf_gmm_prior(m, f, stream); if (rc) return rc; }
         rc = bf_skin_backward(m, f, 0, stream); if (rc) return rc;
     }
+    if (ss) cudaStreamWaitEvent(main_s, ss->join, 0);
     return bf_pose_backward(m, f, 1 | 2 | 4 | (fuse_next ? 8 : 0), stream);
 }
 
