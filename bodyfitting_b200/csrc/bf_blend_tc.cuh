@@ -342,6 +342,7 @@ __global__ void __launch_bounds__(192, 1) k_blend_bwd_tc(const __grid_constant__
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b0 = blockIdx.y * TC_BM;
     const int k0 = blockIdx.x * BN;
+    const int tmem_cols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
     // split-K: this CTA reduces K chunks [kc_begin, kc_begin + num_k) and writes its own partial
     // (the tensor-core accumulator truncates, so long reductions are cut and summed in fp32 RN)
     const int kc_begin = blockIdx.z * cps;
@@ -354,7 +355,7 @@ __global__ void __launch_bounds__(192, 1) k_blend_bwd_tc(const __grid_constant__
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(tmem_slot)), "r"(256));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(tmem_slot)), "r"(tmem_cols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     tc::tc_fence_before();
@@ -386,7 +387,7 @@ __global__ void __launch_bounds__(192, 1) k_blend_bwd_tc(const __grid_constant__
     tc::tc_fence_before();
     __syncthreads();
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(256));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(tmem_cols));
     }
 }
 
@@ -475,8 +476,28 @@ static int bf_skin_forward_tc(const BfModel* m, const BfVSet* vs, const BfFrames
 static int bf_blend_backward_tc(const BfModel* m, const BfVSet* vs, const BfFrames* f, cudaStream_t s) {
     CUtensorMap a_hi, a_lo, b_hi, b_lo;
     int rc;
-    const int BN = m->Kp < 256 ? m->Kp : 256;
+    // column tile: the widest of 256 / 128 / 64 that divides Kp, narrowed while that shortens the critical path
+    // (waves x work per tile) -- e.g. 10,000 frames x Kp 512 gives 158 CTAs of 256 columns = 2 waves on 148 SMs,
+    // but 632 CTAs of 64 columns, two co-resident per SM, = 2.1 waves of a quarter of the work each
+    static int num_sms = 0;
+    if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); }
+    const int mt = (f->B + TC_BM - 1) / TC_BM;
+    int BN = m->Kp < 256 ? m->Kp : 256;
     if (m->Kp % BN != 0) { bf_set_error("Kp=%d not tileable by %d", m->Kp, BN); return BF_EINVAL; }
+    {
+        long best = -1;
+        const int cand[3] = {256, 128, 64};
+        for (int i = 0; i < 3; ++i) {
+            const int bn = cand[i];
+            if (bn > m->Kp || m->Kp % bn != 0) continue;
+            const size_t sm = 1024 + TC_STAGES * (2 * TC_BM * 128 + 2 * (size_t)bn * 128) + 64;
+            const int per_sm = (int)((227 * 1024) / sm) < 1 ? 1 : (int)((227 * 1024) / sm);
+            const long tiles = (long)(m->Kp / bn) * mt;
+            const long waves = (tiles + (long)num_sms * per_sm - 1) / ((long)num_sms * per_sm);
+            const long cost = waves * (bn + 96);                 // + fixed per-tile overhead (A operand, prologue)
+            if (best < 0 || cost < best) { best = cost; BN = bn; }
+        }
+    }
     if ((rc = bf_make_map(&a_hi, f->dvp_hi, f->B, vs->ldn, vs->ldn, TC_BM))) return rc;
     if ((rc = bf_make_map(&a_lo, f->dvp_lo, f->B, vs->ldn, vs->ldn, TC_BM))) return rc;
     if ((rc = bf_make_map(&b_hi, vs->Bm_hi, m->Kp, vs->ldn, vs->ldn, BN))) return rc;

@@ -26,7 +26,8 @@ class SMPLify(object):
 
     def __init__(self, smpl_type='smpl', age='adult', step_size=1e-2, batch_size=1, num_iters=600,
                  gender='male', use_mask=False, device=torch.device('cuda'), debug=True,
-                 model_data=None, gmm=None, J_regressor_extra=None, data_root='data', dense_every_iter=False):
+                 model_data=None, gmm=None, J_regressor_extra=None, data_root='data', dense_every_iter=False,
+                 pipeline_chunks=None, pipeline_min_frames=2048):
         if age != 'adult':
             raise NotImplementedError("only age='adult' is supported (kid template: smplify.py:114-115)")
         self.device = torch.device(device)
@@ -54,6 +55,10 @@ class SMPLify(object):
         self.smpl_faces = self.model.faces.astype(np.int32).reshape(1, -1, 3)
         self.last_trace = None
         self.dense_every_iter = dense_every_iter
+        if pipeline_chunks is None:
+            pipeline_chunks = int(os.environ.get('BODYFIT_PIPE', '1'))
+        self.pipeline_chunks = max(1, int(pipeline_chunks))
+        self.pipeline_min_frames = int(pipeline_min_frames)
         self._pinned = {}
         self.last_loss_terms = None
 
@@ -86,6 +91,9 @@ class SMPLify(object):
         B, Nv = kp.shape[0], kp.shape[1]
         assert kp.shape[2] == m.K_used, 'expected %d keypoints per view, got %d' % (m.K_used, kp.shape[2])
         assert len(c2ws) == Nv and len(Ks) == Nv
+        n_chunks = self.pipeline_chunks if (as_numpy and B >= self.pipeline_min_frames * self.pipeline_chunks) else 1
+        if n_chunks > 1:
+            return self._call_pipelined(init_betas, init_poses, kp, c2ws, Ks, imsize, return_vertices, n_chunks)
         sess = self.session(B, Nv, imsize, return_vertices)
 
         # host -> device (pinned staging so the copies are asynchronous DMA)
@@ -105,6 +113,74 @@ class SMPLify(object):
             out = self._d2h(out)
         out['faces'] = self.smpl_faces[0]
         return out
+
+    def _call_pipelined(self, init_betas, init_poses, kp, c2ws, Ks, imsize, return_vertices, n_chunks):
+        """Large batches: the frames are fitted in ``n_chunks`` consecutive chunks with two sets of device
+        buffers, so that the device->host copy of chunk i (1.2 GB of vertices per 10k SMPL-X frames) runs on a
+        copy stream while chunk i+1 is being fitted.  Frames are independent, so the results are bit-identical
+        to the single-batch path."""
+        from ..sharding import frame_range
+        m, dev = self.model, self.device
+        B, Nv = kp.shape[0], kp.shape[1]
+        ranges = [frame_range(B, c, n_chunks) for c in range(n_chunks)]
+        cmax = max(hi - lo for lo, hi in ranges)
+        key = ('pipe', cmax, int(Nv), int(self.num_iters), float(imsize), bool(return_vertices))
+        if getattr(self, '_pipe_key', None) != key:
+            self._pipe = [dict() for _ in range(2)]
+            self._pipe_key = key
+            self._pipe_stream = torch.cuda.Stream(device=dev)
+            self._pinned = {}
+        cams = self._h2d('cams', torch.from_numpy(pack_cameras(c2ws, Ks)))
+        main = torch.cuda.current_stream()
+        host, copied = {}, [None, None]
+        nbytes = 0
+        traces, terms = [], []
+        for ci, (lo, hi) in enumerate(ranges):
+            slot = self._pipe[ci % 2]
+            n = hi - lo
+            if slot.get('n') != n:
+                slot['sess'] = FitSession(m, n, Nv, self.num_iters, imsize=imsize, return_vertices=return_vertices,
+                                          dense_every_iter=self.dense_every_iter)
+                slot['n'] = n
+            sess = slot['sess']
+            if copied[ci % 2] is not None:
+                main.wait_event(copied[ci % 2])               # the previous copy out of these buffers has finished
+            kp_dev = self._h2d(('kp', ci % 2), kp[lo:hi])
+            poses_dev = self._h2d(('poses', ci % 2), init_poses[lo:hi])
+            betas_dev = self._h2d(('betas', ci % 2), init_betas[lo:hi])
+            sess.set_inputs(pack_keypoints(kp_dev, self.use_hand_face), cams)
+            sess.run(m.pack_theta(poses_dev[:, :3], poses_dev[:, 3:3 + m.nbody], betas_dev))
+            out = sess.results()
+            out = {k: (v if v.is_contiguous() else v.contiguous()) for k, v in out.items()}
+            done = torch.cuda.Event()
+            done.record(main)
+            with torch.cuda.stream(self._pipe_stream):
+                self._pipe_stream.wait_event(done)
+                for k, v in out.items():
+                    if k not in host:
+                        pk = ('out', k)
+                        p = self._pinned.get(pk)
+                        if p is None or p.shape != (B,) + tuple(v.shape[1:]):
+                            p = torch.empty((B,) + tuple(v.shape[1:]), dtype=v.dtype, pin_memory=True)
+                            self._pinned[pk] = p
+                        host[k] = p
+                    host[k][lo:hi].copy_(v, non_blocking=True)
+                    v.record_stream(self._pipe_stream)
+                    nbytes += int(v.numel() * v.element_size())
+                ev = torch.cuda.Event()
+                ev.record(self._pipe_stream)
+                copied[ci % 2] = ev
+            traces.append(sess.fb.t.get('trace'))
+            terms.append(sess.fb.t['loss_terms'])
+        self._pipe_stream.synchronize()
+        main.synchronize()
+        self.last_trace = torch.cat([t.clone() for t in traces], dim=1) if n_chunks <= 2 and traces[0] is not None else traces[-1]
+        self.last_loss_terms = terms[-1]
+        self.h2d_bytes = sum(int(t.numel() * t.element_size()) for t in (kp, init_poses, init_betas, cams))
+        self.d2h_bytes = nbytes
+        res = {k: p.squeeze(0).numpy() for k, p in host.items()}
+        res['faces'] = self.smpl_faces[0]
+        return res
 
     # ------------------------------------------------------------------------------------------
     def _fit_to_scan(self, net_output, c2ws, Ks, keypoints, imsize, meshfile, displacement, as_numpy):
@@ -187,8 +263,15 @@ class SMPLify(object):
         if p is None or p.shape != t.shape or p.dtype != t.dtype:
             p = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
             self._pinned[('in', name)] = p
+        ev = self._pinned.get(('ev', name))
+        if ev is not None:
+            ev.synchronize()                                   # the previous DMA out of this staging buffer is done
         p.copy_(t)
-        return p.to(self.device, non_blocking=True)
+        d = p.to(self.device, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self._pinned[('ev', name)] = ev
+        return d
 
     def _d2h(self, out):
         """Device results -> numpy via pinned buffers (one async copy each, one sync); a batch

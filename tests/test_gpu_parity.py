@@ -223,3 +223,21 @@ def test_edge_cases_single_frame_single_view_and_all_missing(assets):
     one = fit((sc['init_betas'][:1], sc['init_pose'][:1]), list(sc['c2ws']), list(sc['Ks']), sc['kp'][:1], None, imsize=512)
     assert one['vertices'].shape == (6890, 3) and one['pose'].shape == (69,)             # batch dim squeezed
     assert np.array_equal(one['pose'], np.array(out['pose'])[0]) is False or True
+
+
+def test_pipelined_chunks_equal_single_batch(assets):
+    """Large batches are fitted in chunks whose device->host copies overlap the next chunk's fit; frames are
+    independent, so every output is bit-identical to the single-batch call (ragged chunk sizes included)."""
+    from bodyfitting_b200.smplify.smplify import SMPLify
+    mt, nv, B, N = 'smplx', 8, 11, 8
+    port = make_port(assets, mt)
+    sc = make_scene(port, mt, B, nv, seed=33)
+    outs = []
+    for chunks in (1, 2, 3):
+        fit = SMPLify(smpl_type=mt, num_iters=N, gender='neutral', model_data=assets(mt), gmm=assets('gmm'),
+                      pipeline_chunks=chunks, pipeline_min_frames=1)
+        o = fit((sc['init_betas'], sc['init_pose']), list(sc['c2ws']), list(sc['Ks']), sc['kp'], None, imsize=512)
+        outs.append({k: np.array(v) for k, v in o.items()})
+    for o in outs[1:]:
+        for k in ('pose', 'betas', 'global_orient', 'global_transl', 'scale', 'vertices', 'joints', 'full_pose'):
+            assert np.array_equal(outs[0][k], o[k]), k
