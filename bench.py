@@ -61,6 +61,19 @@ def peaks():
     return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
+def measured_traffic(kernel, frames):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed `ncu --set full` capture
+    (profiles/r1_traffic.json, taken at 10,000 frames); None if this kernel / size was not captured."""
+    fn = os.path.join(ROOT, 'profiles', 'r1_traffic.json')
+    if not os.path.exists(fn):
+        return None
+    with open(fn) as f:
+        d = json.load(f).get(kernel)
+    if not d or d.get('frames') != frames:
+        return None
+    return d['dram_bytes_read'] + d['dram_bytes_write']
+
+
 class ClockSampler(object):
     """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
     Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
@@ -356,7 +369,7 @@ def run_ours(args):
                 'api': 'bodyfitting_b200.smplify.smplify.SMPLify.__call__ (numpy in, numpy out incl. vertices)'},
         'gpu_launches': int(launches),
         'roofline': {'bound': 'hbm', 'kernel': dom['kernel'], 'achieved': dom['gbs'], 'peak': hbm_peak, 'unit': 'GB/s',
-                     'frac': dom['frac_hbm'], 'traffic': None, 'peak_source': peak_src,
+                     'frac': dom['frac_hbm'], 'traffic': measured_traffic(dom['kernel'], F), 'peak_source': peak_src,
                      'share_of_iteration': dom['ms'] / iter_ms},
         'kernels': kern, 'iter_ms_sum_of_kernels': iter_ms,
     }
