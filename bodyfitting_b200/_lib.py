@@ -10,7 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libbodyfit_b200.so')
-ABI_VERSION = 9
+ABI_VERSION = 11
 F_WORLD = 1
 F_TC = 2
 
@@ -38,10 +38,10 @@ class BfFrames(C.Structure):
     _fields_ = [(n, _fp) for n in (
         'theta', 'grad', 'adam_m', 'adam_v', 'pf', 'dpf', 'A', 'dA', 'Jtr', 'dJtr', 'full_pose', 'yaw',
         'verts', 'vposed', 'dverts', 'dvp', 'joints', 'djoints', 'kp', 'cams', 'loss', 'loss_terms', 'trace',
-        'pf_hi', 'pf_lo', 'dvp_hi', 'dvp_lo', 'gmm_grad', 'gmm_loss', 'fwd_state', 'ws')] + [('ws_floats', C.c_int64)] + \
+        'pf_hi', 'pf_lo', 'dvp_hi', 'dvp_lo', 'gmm_grad', 'gmm_loss', 'tgrad', 'tloss', 'halo_prev', 'halo_next', 'fwd_state', 'ws')] + [('ws_floats', C.c_int64)] + \
         [(n, C.c_double) for n in ('lr_ts', 'lr', 'beta1', 'beta2', 'eps')] + \
         [(n, _i32) for n in ('B', 'Nv', 'ld_v', 'iter', 'flags', '_pad0')] + \
-        [(n, C.c_float) for n in ('imsize', 'constant_scale', 'sigma', 'w_pose', 'w_angle', 'w_shape')]
+        [(n, C.c_float) for n in ('imsize', 'constant_scale', 'sigma', 'w_pose', 'w_angle', 'w_shape', 'w_temporal', '_padf')]
 
 
 class BfGrid(C.Structure):
@@ -87,7 +87,7 @@ def lib():
     pm, pf, vp, ci = C.POINTER(BfModel), C.POINTER(BfFrames), C.c_void_p, C.c_int
     for name, extra in (('bf_pose_forward', []), ('bf_skin_forward', [ci]), ('bf_joints_forward', [ci]),
                         ('bf_joints_backward', [ci, ci]), ('bf_keypoint_loss', [ci]), ('bf_skin_backward', [ci]), ('bf_skin_backward_parts', [ci, ci]),
-                        ('bf_pose_backward', [ci]), ('bf_gmm_prior', []), ('bf_frame_loss_backward', []), ('bf_lbs_forward', []), ('bf_lbs_backward', []),
+                        ('bf_pose_backward', [ci]), ('bf_gmm_prior', []), ('bf_temporal_prior', []), ('bf_fit_iteration', [ci, ci]), ('bf_frame_loss_backward', []), ('bf_lbs_forward', []), ('bf_lbs_backward', []),
                         ('bf_fit_step', []), ('bf_fit_run', [ci])):
         fn = getattr(L, name)
         fn.restype = C.c_int
@@ -120,7 +120,7 @@ def lib():
 
 EXPORTED = ['bf_abi_version', 'bf_sizeof', 'bf_last_error', 'bf_check_device', 'bf_pose_forward', 'bf_skin_forward',
             'bf_joints_forward', 'bf_joints_backward', 'bf_keypoint_loss', 'bf_skin_backward', 'bf_skin_backward_parts',
-            'bf_pose_backward', 'bf_gmm_prior', 'bf_frame_loss_backward', 'bf_lbs_forward', 'bf_lbs_backward', 'bf_fit_step', 'bf_fit_run']
+            'bf_pose_backward', 'bf_gmm_prior', 'bf_temporal_prior', 'bf_fit_iteration', 'bf_frame_loss_backward', 'bf_lbs_forward', 'bf_lbs_backward', 'bf_fit_step', 'bf_fit_run']
 
 
 EXPORTED_GRID = ['bf_grid_count', 'bf_grid_fill', 'bf_grid_nearest', 'bf_smpld_step', 'bf_smpld_run', 'bf_pc_loss']

@@ -171,6 +171,39 @@ static int launch_gmm(const BfModel* m, const float* pose, int ld, int nvalid, i
     return BF_OK;
 }
 
+// temporal smoothness: one warp per frame
+__global__ void __launch_bounds__(128) k_temporal(BfModel m, BfFrames f) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * 4 + warp;
+    if (b >= f.B) return;
+    const int nb = theta_layout(m.is_smplx).nbody;
+    const float* cur = f.theta + (size_t)b * m.NP;
+    const float* prev = b > 0 ? cur - m.NP : f.halo_prev;
+    const float* next = b + 1 < f.B ? cur + m.NP : f.halo_next;
+    const float w = f.w_temporal;
+    float acc = 0.f;
+    for (int i = lane; i < m.NP; i += 32) {
+        const bool used = i < 3 || (i >= 4 && i < 7 + nb);           // transl, global_orient, body_pose
+        float g = 0.f;
+        if (used) {
+            const float x = cur[i];
+            if (prev) { const float d = x - prev[i]; acc += d * d; g += 2.0f * w * d; }
+            if (next) g += 2.0f * w * (x - next[i]);
+        }
+        f.tgrad[(size_t)b * m.NP + i] = g;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) f.tloss[b] = w * acc;
+}
+
+int bf_temporal_prior(const BfModel* m, const BfFrames* f, void* stream) {
+    int rc = check_model(m, f); if (rc) return rc;
+    BF_REQUIRE(f->tgrad && f->tloss, "tgrad / tloss is null");
+    k_temporal<<<(f->B + 3) / 4, 128, 0, (cudaStream_t)stream>>>(*m, *f);
+    BF_LAUNCH_CHECK();
+    return BF_OK;
+}
+
 int bf_gmm_prior(const BfModel* m, const BfFrames* f, void* stream) {
     int rc = check_model(m, f); if (rc) return rc;
     BF_REQUIRE(f->gmm_grad && f->gmm_loss, "gmm_grad / gmm_loss is null");
@@ -314,6 +347,7 @@ static int fit_iteration(const BfModel* m, const BfFrames* f, bool with_forward,
         rc = bf_gmm_prior(m, f, ss->s); if (rc) return rc;
         cudaEventRecord(ss->join, ss->s);
     }
+    if (f->tgrad && f->w_temporal > 0.f) { rc = bf_temporal_prior(m, f, stream); if (rc) return rc; }
     if (with_forward) { rc = bf_pose_forward(m, f, stream); if (rc) return rc; }
     rc = bf_skin_forward(m, f, 0, stream); if (rc) return rc;
     const size_t fused_smem = sizeof(float) * (BF_MAXK * 6 + BF_MAXVIEWS * 12 + 64 + ((m->J * 12 + 15) & ~15) + 2 * (size_t)m->act.ldn);
@@ -332,6 +366,11 @@ static int fit_iteration(const BfModel* m, const BfFrames* f, bool with_forward,
 
 int bf_fit_step(const BfModel* m, const BfFrames* f, void* stream) {
     return fit_iteration(m, f, true, false, stream);
+}
+
+int bf_fit_iteration(const BfModel* m, const BfFrames* f, int with_forward, int fuse_next, void* stream) {
+    BF_REQUIRE(m && f, "bad arguments");
+    return fit_iteration(m, f, with_forward != 0, fuse_next != 0, stream);
 }
 
 int bf_fit_run(const BfModel* m, const BfFrames* f, int n_iters, void* stream) {

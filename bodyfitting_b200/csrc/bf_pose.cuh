@@ -331,6 +331,13 @@ __global__ void __launch_bounds__(128) k_pose_bwd(BfModel m, BfFrames f, int fla
         for (int i = lane; i < L.nbody; i += 32) g[7 + i] += f.gmm_grad[(size_t)b * BF_GMM_D + i];
         const float pose_l = f.gmm_loss[b];
         __syncwarp();
+        // ---- temporal smoothness (optional, bf_temporal_prior) ----
+        float temp_l = 0.f;
+        if (f.tgrad) {
+            for (int i = lane; i < m.NP; i += 32) g[i] += f.tgrad[(size_t)b * m.NP + i];
+            temp_l = f.tloss[b];
+            __syncwarp();
+        }
         // ---- angle prior: exp(sign * pose[idx])^2 on elbows / knees ----
         float ang = 0.f;
         if (lane < 4) {
@@ -355,7 +362,7 @@ __global__ void __launch_bounds__(128) k_pose_bwd(BfModel m, BfFrames f, int fla
             f.loss_terms[b * 4 + 2] = angle_l;
             f.loss_terms[b * 4 + 3] = shape_l;
         }
-        total += pose_l + angle_l + shape_l;
+        total += pose_l + angle_l + shape_l + temp_l;
     }
     if (lane == 0) {
         f.loss[b] = total;

@@ -20,7 +20,7 @@ class FrameBuffers(object):
     else the active set).  Owns the ``BfFrames`` struct passed to the library."""
 
     def __init__(self, model: PreparedModel, B, full=False, Nv=0, need_backward=True, n_trace=0,
-                 imsize=512.0, constant_scale=K.CONSTANT_SCALE_NO_SCAN, ext=None):
+                 imsize=512.0, constant_scale=K.CONSTANT_SCALE_NO_SCAN, ext=None, temporal_weight=0.0):
         _lib.require_device()
         self.model, self.B, self.full = model, int(B), bool(full)
         dev = model.device
@@ -74,6 +74,9 @@ class FrameBuffers(object):
             buf('gmm_grad', B, 69, zero=True)
             buf('gmm_loss', B, zero=True)
             buf('fwd_state', B, 24 * J)
+            if temporal_weight > 0:
+                buf('tgrad', B, NP, zero=True)
+                buf('tloss', B, zero=True)
         if n_trace:
             buf('trace', n_trace, B, zero=True)
         self.t = t
@@ -87,6 +90,7 @@ class FrameBuffers(object):
         s.w_pose, s.w_angle, s.w_shape = K.POSE_PRIOR_WEIGHT, K.ANGLE_PRIOR_WEIGHT, K.SHAPE_PRIOR_WEIGHT
         s.lr_ts, s.lr = K.LR_TRANSL_SCALE, K.LR_DEFAULT
         s.beta1, s.beta2, s.eps = K.ADAM_BETAS[0], K.ADAM_BETAS[1], K.ADAM_EPS
+        s.w_temporal = float(temporal_weight)
         self.struct = s
 
     def bind(self, name, tensor):
@@ -137,11 +141,15 @@ class FitSession(object):
     """
 
     def __init__(self, model: PreparedModel, B, Nv, num_iters, imsize=512, return_vertices=True,
-                 chunk=4096, trace=True, dense_every_iter=False):
+                 chunk=4096, trace=True, dense_every_iter=False, temporal_weight=0.0, halo_exchange=None):
         self.model, self.B, self.Nv, self.N = model, int(B), int(Nv), int(num_iters)
         assert self.N >= 1
         dev = model.device
-        self.fb = FrameBuffers(model, B, full=False, Nv=Nv, n_trace=(self.N if trace else 0), imsize=imsize)
+        self.fb = FrameBuffers(model, B, full=False, Nv=Nv, n_trace=(self.N if trace else 0), imsize=imsize,
+                               temporal_weight=temporal_weight)
+        # halo_exchange(first_row, last_row) -> (prev_row | None, next_row | None): boundary frames of the
+        # neighbouring ranks, called before every iteration when the temporal term couples frames across shards
+        self.halo_exchange = halo_exchange if temporal_weight > 0 else None
         self.theta_prev = torch.empty(B, model.NP, device=dev)
         self.verts = torch.empty(B, model.V, 3, device=dev) if return_vertices else None
         self.joints = torch.empty(B, model.K_full, 3, device=dev)
@@ -172,6 +180,12 @@ class FitSession(object):
         self.fb.bind('kp', kp_packed)
         self.fb.bind('cams', cams)
 
+    def _exchange(self):
+        th = self.fb.t['theta']
+        prev, nxt = self.halo_exchange(th[0], th[-1])
+        self.fb.bind('halo_prev', prev)
+        self.fb.bind('halo_next', nxt)
+
     def _dense_forward(self):
         for fbf in self.chunks:
             fbf.call('bf_lbs_forward')
@@ -191,6 +205,12 @@ class FitSession(object):
                 fb.struct.iter = it
                 fb.call('bf_fit_step')
                 launches += 6
+        elif self.halo_exchange is not None:
+            for it in range(N - 1):
+                self._exchange()
+                fb.struct.iter = it
+                fb.call('bf_fit_iteration', 1 if it == 0 else 0, 1)
+                launches += 6
         else:
             fb.struct.iter = 0
             if N > 1:
@@ -199,6 +219,8 @@ class FitSession(object):
         self.theta_prev.copy_(fb.t['theta'])
         launches += self._dense_forward()
         fb.struct.iter = N - 1
+        if self.halo_exchange is not None:
+            self._exchange()
         fb.call('bf_fit_step')
         launches += 6
         self.kernel_launches = launches

@@ -16,6 +16,26 @@ def frame_range(n_frames, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def exchange_halo(first_row, last_row, group=None):
+    """Boundary-frame halo exchange of the temporal term: every rank sends its first frame's parameter row to
+    rank-1 and its last to rank+1 and receives theirs.  Returns (prev_row | None, next_row | None); None at the
+    two ends of the sequence.  NCCL send/recv on GPU tensors (NVLink within a box), gloo on CPU tensors."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return None, None
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    first, last = first_row.contiguous(), last_row.contiguous()
+    prev = torch.empty_like(first) if rank > 0 else None
+    nxt = torch.empty_like(last) if rank + 1 < world else None
+    ops = []
+    if rank > 0:
+        ops += [dist.P2POp(dist.isend, first, rank - 1, group), dist.P2POp(dist.irecv, prev, rank - 1, group)]
+    if rank + 1 < world:
+        ops += [dist.P2POp(dist.isend, last, rank + 1, group), dist.P2POp(dist.irecv, nxt, rank + 1, group)]
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+    return prev, nxt
+
+
 def gather_frames(local, n_frames, group=None):
     """All-gather per-frame rows [n_local, ...] from every rank into [n_frames, ...] in frame order.
     Ragged ranges are padded to the largest shard for the collective and trimmed afterwards."""

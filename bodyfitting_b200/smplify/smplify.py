@@ -27,7 +27,7 @@ class SMPLify(object):
     def __init__(self, smpl_type='smpl', age='adult', step_size=1e-2, batch_size=1, num_iters=600,
                  gender='male', use_mask=False, device=torch.device('cuda'), debug=True,
                  model_data=None, gmm=None, J_regressor_extra=None, data_root='data', dense_every_iter=False,
-                 pipeline_chunks=None, pipeline_min_frames=2048):
+                 pipeline_chunks=None, pipeline_min_frames=2048, temporal_weight=0.0, halo_exchange=None):
         if age != 'adult':
             raise NotImplementedError("only age='adult' is supported (kid template: smplify.py:114-115)")
         self.device = torch.device(device)
@@ -55,6 +55,8 @@ class SMPLify(object):
         self.smpl_faces = self.model.faces.astype(np.int32).reshape(1, -1, 3)
         self.last_trace = None
         self.dense_every_iter = dense_every_iter
+        # temporal smoothness between consecutive frames of the batch (not in the reference; BASELINE config 4)
+        self.temporal_weight, self.halo_exchange = float(temporal_weight), halo_exchange
         if pipeline_chunks is None:
             pipeline_chunks = int(os.environ.get('BODYFIT_PIPE', '1'))
         self.pipeline_chunks = max(1, int(pipeline_chunks))
@@ -92,6 +94,8 @@ class SMPLify(object):
         assert kp.shape[2] == m.K_used, 'expected %d keypoints per view, got %d' % (m.K_used, kp.shape[2])
         assert len(c2ws) == Nv and len(Ks) == Nv
         n_chunks = self.pipeline_chunks if (as_numpy and B >= self.pipeline_min_frames * self.pipeline_chunks) else 1
+        if self.temporal_weight > 0:
+            n_chunks = 1                                       # frames are coupled: no independent chunks
         if n_chunks > 1:
             return self._call_pipelined(init_betas, init_poses, kp, c2ws, Ks, imsize, return_vertices, n_chunks)
         sess = self.session(B, Nv, imsize, return_vertices)
@@ -250,7 +254,8 @@ class SMPLify(object):
         key = (int(B), int(Nv), int(self.num_iters), float(imsize), bool(return_vertices))
         if getattr(self, '_sess_key', None) != key:
             self._sess = FitSession(self.model, B, Nv, self.num_iters, imsize=imsize,
-                                    return_vertices=return_vertices, dense_every_iter=self.dense_every_iter)
+                                    return_vertices=return_vertices, dense_every_iter=self.dense_every_iter,
+                                    temporal_weight=self.temporal_weight, halo_exchange=self.halo_exchange)
             self._sess_key = key
             self._pinned = {}
         return self._sess

@@ -40,7 +40,7 @@ extern "C" {
 #define BF_ECUDA    -2   /* a CUDA runtime call / launch failed            */
 #define BF_EARCH    -3   /* device is not sm_100 (no fallback exists)      */
 
-#define BF_ABI_VERSION 9
+#define BF_ABI_VERSION 11
 #define BF_F_WORLD 1   /* forward outputs in world space: (x + transl) * scale * constant_scale */
 #define BF_F_TC    2   /* run the blend-shape contractions on tcgen05 tensor cores (3xTF32) */
 
@@ -123,6 +123,10 @@ typedef struct BfFrames {
     float*       dvp_lo;
     float*       gmm_grad;   /* [B,69] w_pose^2 * gradient of the GMM prior (k_gmm_prior -> k_pose_bwd) */
     float*       gmm_loss;   /* [B]    w_pose^2 * min_m ll_m */
+    float*       tgrad;      /* [B,NP] gradient of the temporal smoothness term (bf_temporal_prior -> k_pose_bwd), or NULL */
+    float*       tloss;      /* [B]    its per-frame value */
+    const float* halo_prev;  /* [NP] theta of the frame before this shard's first frame (previous rank), NULL at the sequence start */
+    const float* halo_next;  /* [NP] theta of the frame after this shard's last frame (next rank), NULL at the sequence end */
     float*       fwd_state;  /* [B,24J] optional: full_pose, R, rest joints, chain rotations saved by the pose forward so the
                                 pose backward does not recompute them */
     float*       ws;         /* split-K workspace of the tensor-core backward GEMM (>= ceil(ldn/2048) * B * Kp floats) or NULL */
@@ -131,6 +135,7 @@ typedef struct BfFrames {
     int32_t B, Nv, ld_v, iter;
     int32_t flags, _pad0;      /* BF_F_WORLD: skin/joints forward write (x + transl) * scale * constant_scale (smplify.py:189-190) */
     float imsize, constant_scale, sigma, w_pose, w_angle, w_shape;
+    float w_temporal, _padf;   /* weight of the temporal term (0 = off; not part of the reference) */
 } BfFrames;
 
 int         bf_abi_version(void);
@@ -155,6 +160,14 @@ int bf_frame_loss_backward(const BfModel* m, const BfFrames* f, void* stream);
 int bf_skin_backward(const BfModel* m, const BfFrames* f, int use_full, void* stream);
 /* the same, one kernel at a time (profiling): parts bit0 dvp, bit1 dA, bit2 blend-backward GEMM */
 int bf_skin_backward_parts(const BfModel* m, const BfFrames* f, int use_full, int parts, void* stream);
+/* temporal smoothness between consecutive frames of a sequence (NOT in the reference; BASELINE config 4):
+ *   L = w_temporal * sum_f |p_f - p_{f-1}|^2,  p = (transl, global_orient, body_pose);
+ * frame f is charged the edge (f-1, f); tgrad[f] = 2 w (2 p_f - p_{f-1} - p_{f+1}) with the shard's outer
+ * neighbours taken from halo_prev / halo_next (exchanged between ranks before every iteration) */
+int bf_temporal_prior(const BfModel* m, const BfFrames* f, void* stream);
+/* one fit iteration with explicit control: with_forward = run the pose forward first, fuse_next = let the pose
+ * backward also run the next iteration's pose forward (bf_fit_step = (1, 0)) */
+int bf_fit_iteration(const BfModel* m, const BfFrames* f, int with_forward, int fuse_next, void* stream);
 /* GMM pose prior of every frame -> gmm_grad, gmm_loss */
 int bf_gmm_prior(const BfModel* m, const BfFrames* f, void* stream);
 /* dA, dJtr, dpf -> grad (theta[4:]); flags: 1 = add priors (value + grad; needs bf_gmm_prior first), 2 = Adam step,

@@ -267,7 +267,8 @@ class FitPort(object):
         return self._result(p, out, joints, verts, True), trace
 
     # -- B frames at once ---------------------------------------------------------
-    def fit_batched(self, init_betas, init_poses, c2ws, Ks, kp, num_iters=100, imsize=512, hook=None):
+    def fit_batched(self, init_betas, init_poses, c2ws, Ks, kp, num_iters=100, imsize=512, hook=None,
+                    temporal_weight=0.0):
         kp = torch.as_tensor(kp, dtype=self.dtype)
         B = kp.shape[0]
         p = self._init_params(init_betas, init_poses, B)
@@ -280,6 +281,11 @@ class FitPort(object):
             joints, verts = self.world(out, p)
             per_frame, _ = batched_objective(w2cs, Kt, kp, joints, p['body_pose'], p['betas'], self.prior,
                                              imsize, self.use_hand_face)
+            if temporal_weight > 0 and B > 1:
+                # builder-defined sequence term (BASELINE config 4, not in the reference): frame f pays the edge (f-1, f)
+                pvec = torch.cat([p['global_transl'], p['global_orient'], p['body_pose']], dim=1)
+                edge = temporal_weight * ((pvec[1:] - pvec[:-1]) ** 2).sum(dim=1)
+                per_frame = per_frame + torch.cat([edge.new_zeros(1), edge])
             trace.append(per_frame.detach().clone())
             opt.zero_grad()
             per_frame.sum().backward()

