@@ -113,3 +113,32 @@ def test_nearest_points_vs_reference_kernel():
           % ((dour - dref).min(), (dour - dref).max(), (np.abs(dour - dref) < 1e-5).mean()))
     assert (dour <= dref + 1e-5).all()
     assert (np.abs(dour - dref) < 1e-5).mean() > 0.9
+
+
+def test_full_size_scan_properties():
+    """BASELINE config 5 size (100k-vertex / 200k-face scan, 10,475 queries): size-independent properties --
+    the returned point lies on the returned face, realises the returned distance, is never farther than the
+    nearest scan vertex, and projecting twice is idempotent."""
+    from bodyfitting_b200.utils.mesh_grid_searcher import MeshGridSearcher
+    v, f = syn.make_template(100000, 9)
+    v = (v * 0.6).astype(np.float32); f = f.astype(np.int32)
+    body, _ = syn.make_template(10475, 0)
+    q = (body * 0.6 * 1.03 + np.random.RandomState(1).randn(*body.shape) * 0.005).astype(np.float32)
+    s = MeshGridSearcher(v, f)
+    qd = torch.from_numpy(q).cuda()
+    pts, faces, d2 = s.nearest_points(qd, return_dist2=True)
+    assert int(s.cell_start[-1]) == s.cell_tris.shape[0] and faces.min() >= 0 and faces.max() < len(f)
+    vd = torch.from_numpy(v).cuda()
+    nn = torch.cat([torch.cdist(qd[i:i + 1024], vd).min(1)[0] for i in range(0, len(q), 1024)])
+    assert bool((d2.sqrt() <= nn + 1e-6).all())                       # a vertex of the mesh is a candidate
+    assert float((torch.norm(pts - qd, dim=1) - d2.sqrt()).abs().max()) < 1e-6
+    tri = vd[torch.from_numpy(f).cuda().long()[faces.long()]]          # [Q,3,3]
+    n = torch.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0], dim=1)
+    n = n / n.norm(dim=1, keepdim=True)
+    assert float(((pts - tri[:, 0]) * n).sum(1).abs().max()) < 1e-5   # in the plane of the face
+    # barycentric coordinates within [0,1]
+    A = torch.stack([tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0]], dim=2)            # [Q,3,2]
+    uv = torch.linalg.lstsq(A, (pts - tri[:, 0]).unsqueeze(2)).solution.squeeze(2)
+    assert float(uv.min()) > -1e-3 and float(uv.sum(1).max()) < 1 + 1e-3
+    pts2, _, d22 = s.nearest_points(pts, return_dist2=True)
+    assert float(d22.max()) < 1e-9                                     # already on the surface

@@ -1,0 +1,43 @@
+"""Closest-point kernel on BASELINE config 5 sizes: 100k-vertex scan (200k faces), 10,475 queries.
+Times bf_grid_nearest and the grid build, and -- when oracle/_ref was built -- the reference's own
+mesh_grid kernel compiled for sm_100a on the same GPU (the on-box bar for this path)."""
+import glob, importlib.util, json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np, torch
+from bodyfitting_b200 import synthetic as syn
+from bodyfitting_b200.utils.mesh_grid_searcher import MeshGridSearcher
+
+def ev_time(fn, reps=20):
+    fn(); torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(); fn(); e.record(); torch.cuda.synchronize(); ts.append(s.elapsed_time(e))
+    return float(np.median(ts))
+
+v, f = syn.make_template(100000, 9)
+v = (v * 0.6).astype(np.float32); f = f.astype(np.int32)
+body, _ = syn.make_template(10475, 0)
+rng = np.random.RandomState(0)
+q = (body * 0.6 * 1.02 + rng.randn(*body.shape) * 0.004).astype(np.float32)
+t0 = time.perf_counter(); s = MeshGridSearcher(v, f); torch.cuda.synchronize(); build_ms = 1e3 * (time.perf_counter() - t0)
+qd = torch.from_numpy(q).cuda()
+ours = ev_time(lambda: s.nearest_points(qd))
+pts, faces, d2 = s.nearest_points(qd, return_dist2=True)
+out = {'scan_verts': len(v), 'scan_faces': len(f), 'queries': len(q), 'cells': s.num[3], 'grid_build_ms_incl_alloc': build_ms,
+       'ours_ms': ours, 'ours_mqueries_per_s': len(q) / ours / 1e3}
+so = glob.glob(os.path.join(ROOT, 'oracle', '_ref', 'mesh_grid*.so'))
+if so:
+    spec = importlib.util.spec_from_file_location('mesh_grid', so[0]); mg = importlib.util.module_from_spec(spec); spec.loader.exec_module(mg)
+    verts, fa = torch.from_numpy(v).cuda(), torch.from_numpy(f).cuda()
+    num = torch.tensor(s.num, dtype=torch.int32).cuda(); minmax = torch.from_numpy(np.asarray(s.minmax, np.float32)).cuda()
+    tri_num = torch.zeros(s.num[3], dtype=torch.int32).cuda(); tri_idx = torch.zeros(1, dtype=torch.int32).cuda()
+    t0 = time.perf_counter(); mg.insert_grid_surface(verts, fa, minmax, num, s.step, tri_num, tri_idx); torch.cuda.synchronize()
+    out['reference_grid_build_ms'] = 1e3 * (time.perf_counter() - t0)
+    nf = torch.zeros(len(q), dtype=torch.int32).cuda(); co = torch.zeros(len(q), 3).cuda(); npts = torch.zeros(len(q), 3).cuda()
+    ref = ev_time(lambda: mg.search_nearest_point(qd, verts, fa, tri_num, tri_idx, num, minmax, s.step, nf, npts, co))
+    dref = torch.norm(npts - qd, dim=1)
+    out.update(reference_ms=ref, speedup_vs_reference_kernel=ref / ours,
+               max_abs_dist_diff=float((dref - d2.sqrt()).abs().max()), ours_never_worse=bool((d2.sqrt() <= dref + 1e-6).all()))
+print(json.dumps(out))
