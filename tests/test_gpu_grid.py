@@ -129,7 +129,7 @@ def test_full_size_scan_properties():
     pts, faces, d2 = s.nearest_points(qd, return_dist2=True)
     assert int(s.cell_start[-1]) == s.cell_tris.shape[0] and faces.min() >= 0 and faces.max() < len(f)
     vd = torch.from_numpy(v).cuda()
-    nn = torch.cat([torch.cdist(qd[i:i + 1024], vd).min(1)[0] for i in range(0, len(q), 1024)])
+    nn = torch.cat([torch.cdist(qd[i:i + 1024], vd, compute_mode='donot_use_mm_for_euclid_dist').min(1)[0] for i in range(0, len(q), 1024)])
     assert bool((d2.sqrt() <= nn + 1e-6).all())                       # a vertex of the mesh is a candidate
     assert float((torch.norm(pts - qd, dim=1) - d2.sqrt()).abs().max()) < 1e-6
     tri = vd[torch.from_numpy(f).cuda().long()[faces.long()]]          # [Q,3,3]

@@ -21,6 +21,8 @@ v = (v * 0.6).astype(np.float32); f = f.astype(np.int32)
 body, _ = syn.make_template(10475, 0)
 rng = np.random.RandomState(0)
 q = (body * 0.6 * 1.02 + rng.randn(*body.shape) * 0.004).astype(np.float32)
+MeshGridSearcher(v[:3000], f[:10])                       # warm-up (library load, allocator)
+torch.cuda.synchronize()
 t0 = time.perf_counter(); s = MeshGridSearcher(v, f); torch.cuda.synchronize(); build_ms = 1e3 * (time.perf_counter() - t0)
 qd = torch.from_numpy(q).cuda()
 ours = ev_time(lambda: s.nearest_points(qd))
