@@ -248,3 +248,51 @@ def test_product_never_imports_oracle():
             if fn.endswith('.py'):
                 src = open(os.path.join(dp, fn)).read()
                 assert not re.search(r'^\s*(from|import)\s+oracle', src, re.M), fn
+
+
+def test_openpose_json_and_obj_formats(tmp_path):
+    """load_openpose on an OpenPose-1.3 style file (25x3 body, confidences may exceed 1, empty hand arrays, a second
+    weaker person), OBJ writer/reader round trip, parameter .npy schema."""
+    import json
+    from bodyfitting_b200.smplify.body_fitting import write_result
+    from bodyfitting_b200.utils.io_utils import load_obj_mesh, load_openpose, save_obj_mesh
+    rng = np.random.RandomState(0)
+    body = np.concatenate([rng.rand(25, 2) * 500, rng.rand(25, 1) * 3.5], 1)
+    hand = np.concatenate([rng.rand(21, 2) * 500, rng.rand(21, 1)], 1)
+    doc = {'version': 1.3, 'people': [
+        {'person_id': [-1], 'pose_keypoints_2d': (body * 0.1).reshape(-1).tolist(), 'face_keypoints_2d': [],
+         'hand_left_keypoints_2d': [], 'hand_right_keypoints_2d': []},
+        {'person_id': [-1], 'pose_keypoints_2d': body.reshape(-1).tolist(), 'face_keypoints_2d': np.zeros(210).tolist(),
+         'hand_left_keypoints_2d': hand.reshape(-1).tolist(), 'hand_right_keypoints_2d': [], 'pose_keypoints_3d': []}]}
+    fn = tmp_path / 'f_keypoints.json'
+    fn.write_text(json.dumps(doc))
+    d = load_openpose(str(fn))
+    assert set(d) == {'pose', 'hand_left'} and d['pose'].shape == (25, 3) and d['hand_left'].shape == (21, 3)
+    assert np.allclose(d['pose'], body)                      # the stronger person; all-zero face dropped
+    assert len(load_openpose(str(fn), only_one=False)) == 2
+    (tmp_path / 'empty.json').write_text(json.dumps({'people': []}))
+    assert load_openpose(str(tmp_path / 'empty.json')) is None
+    v = rng.rand(10, 3); f = rng.randint(0, 10, (6, 3))
+    write_result(str(tmp_path / 'out'), 'smpl', dict(vertices=v, faces=f, pose=np.zeros(69)))
+    v2, f2 = load_obj_mesh(str(tmp_path / 'out' / 'smpl.obj'))
+    assert np.abs(v2 - v).max() < 1e-4 and np.array_equal(f2, f)
+    back = np.load(str(tmp_path / 'out' / 'smpl_parameter.npy'), allow_pickle=True).item()
+    assert set(back) == {'vertices', 'faces', 'pose'}
+    (tmp_path / 'quad.obj').write_text('v 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nvn 0 0 1\nf 1/1/1 2/1/1 3/1/1 4/1/1\n')
+    _, fq = load_obj_mesh(str(tmp_path / 'quad.obj'))
+    assert fq.tolist() == [[0, 1, 2], [0, 2, 3]]
+
+
+def test_rotation_matrix_to_axis_angle():
+    from scipy.spatial.transform import Rotation as Rot
+    from bodyfitting_b200.utils.geometry import convert_hom_to_angle, rotation_matrix_to_angle_axis
+    rng = np.random.RandomState(3)
+    rv = rng.randn(200, 3) * 1.2
+    rv[0] = 0.0                                              # identity (the reference patches a NaN here)
+    rv[1] = [np.pi - 1e-4, 0, 0]                             # near pi
+    R = torch.tensor(Rot.from_rotvec(rv).as_matrix(), dtype=torch.float64)
+    out = rotation_matrix_to_angle_axis(R).numpy()
+    ref = Rot.from_matrix(R.numpy()).as_rotvec()
+    assert np.abs(out - ref).max() < 1e-8 and (out[0] == 0).all()
+    pose = convert_hom_to_angle(R[:48].reshape(2, 24, 3, 3).float(), 2)
+    assert pose.shape == (2, 72) and np.abs(pose.numpy().reshape(-1, 3) - ref[:48]).max() < 1e-5
