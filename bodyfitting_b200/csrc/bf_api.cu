@@ -322,25 +322,30 @@ int bf_frame_loss_backward(const BfModel* m, const BfFrames* f, void* stream) {
 
 // The GMM prior only needs theta, so it runs on a side stream next to the blend / loss kernels of the same
 // iteration (fork after the parameters are final, join before the pose backward).  One side stream and two
-// events per device, created on first use.
-struct SideStream { cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
-static SideStream* side_stream() {
-    static SideStream per_dev[64];
+// events per (device, stream), created on first use.
+struct SideStream { cudaStream_t main = nullptr; cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, join = nullptr; int dev = -1; };
+// one side stream (+ two events) per (device, caller stream), created on first use
+static SideStream* side_stream(cudaStream_t main_s) {
+    static SideStream table[256];
+    static int used = 0;
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-    SideStream* ss = &per_dev[dev];
-    if (!ss->s) {
-        if (cudaStreamCreateWithFlags(&ss->s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-        if (cudaEventCreateWithFlags(&ss->fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-        if (cudaEventCreateWithFlags(&ss->join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-    }
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    for (int i = 0; i < used; ++i)
+        if (table[i].dev == dev && table[i].main == main_s) return &table[i];
+    if (used >= 256) return nullptr;
+    SideStream* ss = &table[used];
+    if (cudaStreamCreateWithFlags(&ss->s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&ss->fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&ss->join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    ss->dev = dev; ss->main = main_s;
+    ++used;
     return ss;
 }
 
 static int fit_iteration(const BfModel* m, const BfFrames* f, bool with_forward, bool fuse_next, void* stream) {
     int rc;
     cudaStream_t main_s = (cudaStream_t)stream;
-    SideStream* ss = side_stream();
+    SideStream* ss = side_stream(main_s);
     if (ss) {                                                     // theta of this iteration is final here
         cudaEventRecord(ss->fork, main_s);
         cudaStreamWaitEvent(ss->s, ss->fork, 0);
