@@ -205,16 +205,25 @@ def kernel_breakdown(pm, sess, F, hbm_peak):
     bm_act = 4 * Kp * m.ld_act
     per_frame = {   # algorithmic bytes per frame (fp32), see DESIGN.md "Kernels"
         'k_pose_fwd': 4 * (NP + Kp * (3 if m.tensor_cores else 1) + J * 12 + J * 3 + 3 * J + 1),
-        'k_skin_fwd': 4 * (Kp + J * 12 + 2 * nS3),
-        'k_frame_loss_bwd': 4 * (Nv * K * 3 + 2 * nS3 + J * 3 + J * 12 + 4 + (2 if m.tensor_cores else 1) * nS3 + J * 12 + J * 3 + 4 + 1),
+        # tensor-core mode: the GEMM kernel only blends (pf -> v_posed) and the per-frame kernel skins its live vertices
+        # from v_posed; FFMA mode: blend + skinning fused (v_posed and verts written, both read by the per-frame kernel)
+        'k_skin_fwd': 4 * (Kp + nS3) if m.tensor_cores else 4 * (Kp + J * 12 + 2 * nS3),
+        'k_frame_loss_bwd': 4 * (Nv * K * 3 + (1 if m.tensor_cores else 2) * nS3 + J * 3 + J * 12 + 4 + (2 if m.tensor_cores else 1) * nS3 + J * 12 + J * 3 + 4 + 1),
         'k_blend_bwd': 4 * (nS3 + Kp),
         'k_gmm_prior': 4 * (NP + 69 + 1),
         'k_pose_bwd': 4 * (NP * 7 + J * 12 + J * 3 + Kp + 2 + 70) + 4 * (Kp * (3 if m.tensor_cores else 1) + J * 12 + J * 3 + 3 * J + 1),
     }
     once = {'k_skin_fwd': bm_act, 'k_blend_bwd': bm_act}
+    from bodyfitting_b200 import _lib
+
+    def frame_kernel():
+        if m.tensor_cores:
+            fb.struct.flags |= _lib.F_SKIN_FUSED
+        fb.call('bf_frame_loss_backward')
+        fb.struct.flags &= ~_lib.F_SKIN_FUSED
     calls = [('k_pose_fwd', lambda: fb.call('bf_pose_forward')),
-             ('k_skin_fwd', lambda: fb.call('bf_skin_forward', 0)),
-             ('k_frame_loss_bwd', lambda: fb.call('bf_frame_loss_backward')),
+             ('k_skin_fwd', lambda: fb.call('bf_blend_forward' if m.tensor_cores else 'bf_skin_forward', 0)),
+             ('k_frame_loss_bwd', frame_kernel),
              ('k_blend_bwd', lambda: fb.call('bf_skin_backward_parts', 0, 4)),
              ('k_gmm_prior', lambda: fb.call('bf_gmm_prior')),
              ('k_pose_bwd', lambda: fb.call('bf_pose_backward', 1 | 2 | 4 | 8))]   # incl. Adam + next iteration's pose forward

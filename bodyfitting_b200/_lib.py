@@ -9,10 +9,11 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libbodyfit_b200.so')
-ABI_VERSION = 11
+LIB_PATH = os.environ.get('BODYFIT_LIB') or os.path.join(_HERE, 'libbodyfit_b200.so')   # BODYFIT_LIB: A/B builds of the same ABI
+ABI_VERSION = 12
 F_WORLD = 1
 F_TC = 2
+F_SKIN_FUSED = 4
 
 _fp = C.c_void_p
 _i32 = C.c_int32
@@ -21,8 +22,9 @@ _i32 = C.c_int32
 class BfVSet(C.Structure):
     _fields_ = [(n, _fp) for n in (
         'Bm', 'ell_j', 'ell_w', 'jv_ptr', 'jv_vid', 'jv_w', 'kj_kind', 'kj_src', 'kj_w',
-        'dyn_src', 'dyn_w', 'tg_ptr', 'tg_k', 'tg_a', 'tg_w', 'xr_ptr', 'xr_vid', 'xr_w', 'Bt_hi', 'Bt_lo', 'Bm_hi', 'Bm_lo', 'dyn_k', 'jv_nz')] + \
-        [(n, _i32) for n in ('n', 'n_pad', 'ldn', 'nnz', 'K_out', 'n_dyn', 'n_extra', 'n_nz')]
+        'dyn_src', 'dyn_w', 'tg_ptr', 'tg_k', 'tg_a', 'tg_w', 'xr_ptr', 'xr_vid', 'xr_w', 'Bt_hi', 'Bt_lo', 'Bm_hi', 'Bm_lo', 'dyn_k', 'jv_nz',
+        'lv_n', 'lv_vid', 'lt_ptr', 'lt_k', 'lt_w', 'lj_ptr', 'lj_vid', 'lj_w')] + \
+        [(n, _i32) for n in ('n', 'n_pad', 'ldn', 'nnz', 'K_out', 'n_dyn', 'n_extra', 'n_nz', 'lmax', 'n_rows')]
 
 
 class BfModel(C.Structure):
@@ -38,7 +40,7 @@ class BfFrames(C.Structure):
     _fields_ = [(n, _fp) for n in (
         'theta', 'grad', 'adam_m', 'adam_v', 'pf', 'dpf', 'A', 'dA', 'Jtr', 'dJtr', 'full_pose', 'yaw',
         'verts', 'vposed', 'dverts', 'dvp', 'joints', 'djoints', 'kp', 'cams', 'loss', 'loss_terms', 'trace',
-        'pf_hi', 'pf_lo', 'dvp_hi', 'dvp_lo', 'gmm_grad', 'gmm_loss', 'tgrad', 'tloss', 'halo_prev', 'halo_next', 'fwd_state', 'ws')] + [('ws_floats', C.c_int64)] + \
+        'pf_hi', 'pf_lo', 'dvp_hi', 'dvp_lo', 'gmm_grad', 'gmm_loss', 'tgrad', 'tloss', 'halo_prev', 'halo_next', 'fwd_state', 'A_T', 'ws')] + [('ws_floats', C.c_int64)] + \
         [(n, C.c_double) for n in ('lr_ts', 'lr', 'beta1', 'beta2', 'eps')] + \
         [(n, _i32) for n in ('B', 'Nv', 'ld_v', 'iter', 'flags', '_pad0')] + \
         [(n, C.c_float) for n in ('imsize', 'constant_scale', 'sigma', 'w_pose', 'w_angle', 'w_shape', 'w_temporal', '_padf')]
@@ -85,7 +87,7 @@ def lib():
         if L.bf_sizeof(i) != C.sizeof(st):
             raise BodyfitError('struct layout mismatch for %s: C %d, ctypes %d' % (st.__name__, L.bf_sizeof(i), C.sizeof(st)))
     pm, pf, vp, ci = C.POINTER(BfModel), C.POINTER(BfFrames), C.c_void_p, C.c_int
-    for name, extra in (('bf_pose_forward', []), ('bf_skin_forward', [ci]), ('bf_joints_forward', [ci]),
+    for name, extra in (('bf_pose_forward', []), ('bf_skin_forward', [ci]), ('bf_blend_forward', [ci]), ('bf_joints_forward', [ci]),
                         ('bf_joints_backward', [ci, ci]), ('bf_keypoint_loss', [ci]), ('bf_skin_backward', [ci]), ('bf_skin_backward_parts', [ci, ci]),
                         ('bf_pose_backward', [ci]), ('bf_gmm_prior', []), ('bf_temporal_prior', []), ('bf_fit_iteration', [ci, ci]), ('bf_frame_loss_backward', []), ('bf_lbs_forward', []), ('bf_lbs_backward', []),
                         ('bf_fit_step', []), ('bf_fit_run', [ci])):
@@ -118,7 +120,7 @@ def lib():
     return L
 
 
-EXPORTED = ['bf_abi_version', 'bf_sizeof', 'bf_last_error', 'bf_check_device', 'bf_pose_forward', 'bf_skin_forward',
+EXPORTED = ['bf_abi_version', 'bf_sizeof', 'bf_last_error', 'bf_check_device', 'bf_pose_forward', 'bf_skin_forward', 'bf_blend_forward',
             'bf_joints_forward', 'bf_joints_backward', 'bf_keypoint_loss', 'bf_skin_backward', 'bf_skin_backward_parts',
             'bf_pose_backward', 'bf_gmm_prior', 'bf_temporal_prior', 'bf_fit_iteration', 'bf_frame_loss_backward', 'bf_lbs_forward', 'bf_lbs_backward', 'bf_fit_step', 'bf_fit_run']
 

@@ -87,6 +87,15 @@ int bf_skin_forward(const BfModel* m, const BfFrames* f, int use_full, void* str
     return BF_OK;
 }
 
+int bf_blend_forward(const BfModel* m, const BfFrames* f, int use_full, void* stream) {
+    int rc = check_model(m, f); if (rc) return rc;
+    const BfVSet* vs = use_full ? &m->full : &m->act;
+    rc = check_vset(vs, f); if (rc) return rc;
+    BF_REQUIRE(f->vposed, "vposed is null");
+    BF_REQUIRE((f->flags & BF_F_TC) && vs->Bt_hi && vs->Bt_lo && f->pf_hi && f->pf_lo, "bf_blend_forward needs the tensor-core operands (BF_F_TC)");
+    return bf_skin_forward_tc(m, vs, f, (cudaStream_t)stream, true);
+}
+
 int bf_joints_forward(const BfModel* m, const BfFrames* f, int use_full, void* stream) {
     int rc = check_model(m, f); if (rc) return rc;
     const BfVSet* vs = use_full ? &m->full : &m->act;
@@ -306,8 +315,12 @@ int bf_frame_loss_backward(const BfModel* m, const BfFrames* f, void* stream) {
     int rc = check_model(m, f); if (rc) return rc;
     const BfVSet* vs = &m->act;
     rc = check_vset(vs, f); if (rc) return rc;
-    BF_REQUIRE(f->kp && f->cams && f->loss && f->grad && f->dJtr && f->verts && f->vposed && f->Jtr && f->A && f->dA,
+    const int skin_here = (f->flags & BF_F_SKIN_FUSED) ? 1 : 0;
+    BF_REQUIRE(f->kp && f->cams && f->loss && f->grad && f->dJtr && (skin_here || f->verts) && f->vposed && f->Jtr && f->A && f->dA,
                "fused loss/backward buffers missing");
+    BF_REQUIRE(vs->lv_n && vs->lv_vid && vs->lt_ptr && vs->lt_k && vs->lt_w && vs->lj_ptr && vs->lj_vid && vs->lj_w && vs->lmax > 0 &&
+               vs->n_rows > 0, "live-vertex lists of the active set missing");
+    BF_REQUIRE(f->ld_v % 4 == 0 && vs->ldn % 4 == 0, "ld_v / ldn must be multiples of 4 floats");
     BF_REQUIRE(f->dvp_hi || f->dvp, "dvp (or its 3xTF32 split) missing");
     BF_REQUIRE(f->Nv > 0 && f->Nv <= BF_MAXVIEWS, "Nv out of range");
     BF_REQUIRE(vs->jv_ptr && vs->jv_vid && vs->jv_w && vs->jv_nz, "joint->vertex lists missing");
@@ -315,7 +328,7 @@ int bf_frame_loss_backward(const BfModel* m, const BfFrames* f, void* stream) {
     BF_REQUIRE(smem <= 48 * 1024, "active vertex set too large for the fused per-frame kernel");
     BfFrames g = *f;
     if (!bf_tc_ready_bwd(vs, f)) { g.dvp_hi = nullptr; g.dvp_lo = nullptr; }
-    k_frame_loss_bwd<<<f->B, FR_THREADS, smem, (cudaStream_t)stream>>>(*m, *vs, g);
+    k_frame_loss_bwd<<<f->B, FR_THREADS, smem, (cudaStream_t)stream>>>(*m, *vs, g, skin_here);
     BF_LAUNCH_CHECK();
     return BF_OK;
 }
@@ -354,10 +367,16 @@ static int fit_iteration(const BfModel* m, const BfFrames* f, bool with_forward,
     }
     if (f->tgrad && f->w_temporal > 0.f) { rc = bf_temporal_prior(m, f, stream); if (rc) return rc; }
     if (with_forward) { rc = bf_pose_forward(m, f, stream); if (rc) return rc; }
-    rc = bf_skin_forward(m, f, 0, stream); if (rc) return rc;
     const size_t fused_smem = sizeof(float) * (BF_MAXK * 6 + BF_MAXVIEWS * 12 + 64 + ((m->J * 12 + 15) & ~15) + 2 * (size_t)m->act.ldn);
-    if (fused_smem <= 48 * 1024) {
-        rc = bf_frame_loss_backward(m, f, stream); if (rc) return rc;          // loss + dverts (on chip) + dvp + dA
+    const bool fused = fused_smem <= 48 * 1024 && m->act.lv_n;
+    // tensor-core path of the fused loop: the GEMM only blends (v_posed); the per-frame kernel skins its live vertices
+    const bool blend_only = fused && bf_tc_ready_fwd(&m->act, f) && f->vposed && !(f->flags & BF_F_WORLD);
+    if (blend_only) { rc = bf_blend_forward(m, f, 0, stream); if (rc) return rc; }
+    else { rc = bf_skin_forward(m, f, 0, stream); if (rc) return rc; }
+    if (fused) {
+        BfFrames g = *f;
+        if (blend_only) g.flags |= BF_F_SKIN_FUSED;
+        rc = bf_frame_loss_backward(m, &g, stream); if (rc) return rc;          // skin + loss + dverts (on chip) + dvp + dA
         if (!ss) { rc = bf_gmm_prior(m, f, stream); if (rc) return rc; }
         rc = bf_skin_backward_parts(m, f, 0, 4, stream); if (rc) return rc;    // dpf = dvp @ Bm^T
     } else {

@@ -21,10 +21,14 @@
 #include "bf_common.cuh"
 
 #define TC_BM 128          // frames per tile (UMMA M)
-#define TC_BK 32           // fp32 elements per K chunk = one 128-byte swizzle row
+#ifndef TC_BK
+#define TC_BK 16           // fp32 elements per K chunk = one swizzle row (16 -> SWIZZLE_64B, 32 -> SWIZZLE_128B)
+#endif
+#define TC_ROWB (TC_BK * 4)   // bytes per operand row of one K chunk
 #define TC_BN1 192         // coords per tile in the forward (64 vertices)
-#define TC_STAGES 2
-#define TC_VP_LD 97        // padded row stride of the per-warp v_posed staging tile
+#ifndef TC_STAGES
+#define TC_STAGES (TC_BK == 16 ? 4 : 2)   // the same 160 KB of operand staging, but up to three chunks in flight instead of one
+#endif
 
 namespace tc {
 
@@ -63,15 +67,15 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// K-major, SWIZZLE_128B operand tile: rows of 128 B, 8-row groups 1024 B apart (SBO), LBO unused (=1)
+// K-major swizzled operand tile: rows of TC_ROWB bytes (= the swizzle span), 8-row groups 8 * TC_ROWB apart (SBO), LBO unused (=1)
 __device__ __forceinline__ uint64_t make_desc(const void* smem_tile) {
     const uint32_t a = smem_u32(smem_tile);
     uint64_t d = 0;
     d |= (uint64_t)((a >> 4) & 0x3FFF);
     d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)((8 * TC_ROWB) >> 4) << 32;
     d |= (uint64_t)1 << 46;          // descriptor version 1 (Blackwell)
-    d |= (uint64_t)2 << 61;          // SWIZZLE_128B
+    d |= (uint64_t)(TC_BK == 32 ? 2 : 4) << 61;          // layout type: SWIZZLE_128B = 2, SWIZZLE_64B = 4
     return d;
 }
 __device__ __forceinline__ uint32_t make_idesc_tf32(int M, int N) {
@@ -99,7 +103,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
 }
 
 // Shared main loop: warp 0 lane 0 streams K chunks with TMA, warp 1 lane 0 issues the MMAs.
-// Stage layout: A_hi | A_lo | B_hi | B_lo, each a [rows x 128 B] SWIZZLE_128B tile.
+// Stage layout: A_hi | A_lo | B_hi | B_lo, each a [rows x TC_ROWB] swizzled tile.
 struct Pipe {
     uint8_t* stage_base;
     uint64_t* full;
@@ -151,24 +155,68 @@ __device__ __forceinline__ void mma_issuer(const Pipe& p, int num_k, uint32_t tm
 }  // namespace tc
 
 // Persistent: one CTA per SM walks the (frame tile, vertex tile) list (vertex tile fastest, so that CTAs running
-// together share the same pf rows in L2).  Two TMEM accumulators: the MMA warp fills buffer (i+1)&1 while the four
+// together share the same pf rows in L2).  Two TMEM accumulators: the MMA warp fills buffer (i+1)&1 while the eight
 // epilogue warps skin buffer i&1.
-__global__ void __launch_bounds__(192, 1) k_skin_fwd_tc(const __grid_constant__ CUtensorMap mA_hi,
-                                                        const __grid_constant__ CUtensorMap mA_lo,
-                                                        const __grid_constant__ CUtensorMap mB_hi,
-                                                        const __grid_constant__ CUtensorMap mB_lo,
-                                                        BfVSet vs, int J, int Kp, const float* __restrict__ A,
-                                                        float* __restrict__ verts, float* __restrict__ vposed,
-                                                        int B, int ld_v, const float* __restrict__ theta, int NP, float cs,
-                                                        int n_tiles_n, int n_tiles) {
+//
+// Epilogue mapping: LANE = FRAME, which is the accumulator's own TMEM layout (lane = row of D), so v_posed comes
+// out of tcgen05.ld already where it is needed.  The skinning influences (joint, weight) of a vertex are then
+// warp-uniform, and the joint transforms are read from the frame-minor copy AT[(j*3 + r)][b] (float4 rows): one
+// LDG.128 of the warp covers 32 consecutive frames of the same joint row = 512 contiguous bytes = the minimum of
+// four L1 wavefronts, whatever the joint pattern of the model (the frame-major A[b][j] gather costs one wavefront
+// per distinct cache line: ~22 per load on a model with scattered influences, measured as the limiter before).
+// Skinned vertices are transposed through a small per-warp shared tile so that the global stores are row-contiguous.
+// Warps 2..9: TMEM lane quarter q = warp % 4, vertex half h = (warp - 2) / 4 of the 64-vertex tile, two passes of
+// 16 vertices (48 accumulator columns) each.
+#define TC_EPI_WARPS 8
+#define TC_ST_LD 33        // row stride (floats) of the per-warp [48 coords][32 frames] staging tile
+#define TC_ST_FLOATS (48 * TC_ST_LD)
+
+namespace tc {
+// 48 consecutive accumulator columns of this warp's 32 lanes -> registers (one wait for the three loads)
+__device__ __forceinline__ void tmem_ld48(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%48];\n"
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%49];\n"
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47}, [%50];\n"
+        "tcgen05.wait::ld.sync.aligned;\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]),
+          "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]),
+          "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47])
+        : "r"(taddr), "r"(taddr + 16u), "r"(taddr + 32u)
+        : "memory");
+}
+
+// staging tile [48 coords][32 frames] -> rows of `dst` (row stride ld floats), `ncols` valid coords, `nrows` valid frames
+__device__ __forceinline__ void store_rows48(const float* st, float* __restrict__ dst, size_t ld, int ncols, int nrows, int lane) {
+#pragma unroll 4
+    for (int rp = 0; rp < 16; ++rp) {                     // 2 rows x 48 coords = 96 elements = 3 warp-wide stores
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+            const int idx = lane + 32 * s, hi = idx >= 48;
+            const int fr = 2 * rp + hi, c = idx - 48 * hi;
+            if (fr < nrows && c < ncols) dst[(size_t)fr * ld + c] = st[c * TC_ST_LD + fr];
+        }
+    }
+}
+}  // namespace tc
+
+__global__ void __launch_bounds__(64 + 32 * TC_EPI_WARPS, 1)
+k_skin_fwd_tc(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CUtensorMap mA_lo,
+              const __grid_constant__ CUtensorMap mB_hi, const __grid_constant__ CUtensorMap mB_lo,
+              BfVSet vs, int J, int Kp, const float4* __restrict__ AT, float* __restrict__ verts,
+              float* __restrict__ vposed, int B, int ld_v, const float* __restrict__ theta, int NP, float cs,
+              int n_tiles_n, int n_tiles) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     tc::Pipe p;
-    p.a_bytes = TC_BM * 128;
-    p.b_bytes = TC_BN1 * 128;
+    p.a_bytes = TC_BM * TC_ROWB;
+    p.b_bytes = TC_BN1 * TC_ROWB;
     p.stage_base = base;
-    float* Vp = reinterpret_cast<float*>(base + TC_STAGES * p.stage_bytes());
-    uint64_t* bars = reinterpret_cast<uint64_t*>(Vp + 4 * 32 * TC_VP_LD);
+    float* St = reinterpret_cast<float*>(base + TC_STAGES * p.stage_bytes());
+    uint64_t* bars = reinterpret_cast<uint64_t*>(St + TC_EPI_WARPS * TC_ST_FLOATS);
     p.full = bars; p.empty = bars + TC_STAGES; p.tmem_full = bars + 2 * TC_STAGES;      // tmem_full[2]
     uint64_t* tmem_empty = bars + 2 * TC_STAGES + 2;                                   // tmem_empty[2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 4);
@@ -178,7 +226,7 @@ __global__ void __launch_bounds__(192, 1) k_skin_fwd_tc(const __grid_constant__ 
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; ++s) { tc::mbar_init(&p.full[s], 1); tc::mbar_init(&p.empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { tc::mbar_init(&p.tmem_full[s], 1); tc::mbar_init(&tmem_empty[s], 4); }
+        for (int s = 0; s < 2; ++s) { tc::mbar_init(&p.tmem_full[s], 1); tc::mbar_init(&tmem_empty[s], TC_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -239,77 +287,98 @@ __global__ void __launch_bounds__(192, 1) k_skin_fwd_tc(const __grid_constant__ 
         }
     } else {
         const int q = warp & 3;                               // TMEM lane quarter this warp may read
-        float* myVp = Vp + (warp - 2) * 32 * TC_VP_LD;
+        const int h = (warp - 2) >> 2;                        // which 32 vertices of the 64-vertex tile
+        float* st = St + (warp - 2) * TC_ST_FLOATS;
         const int nnz = vs.nnz;
+        const size_t Bz = (size_t)B;
         int i = 0;
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
             const int buf = i & 1;
-            const int b0 = (t / n_tiles_n) * TC_BM, n0 = (t % n_tiles_n) * TC_BN1;
+            const int b0 = (t / n_tiles_n) * TC_BM + 32 * q, n0 = (t % n_tiles_n) * TC_BN1;
+            const int b = b0 + lane;
+            const int bl = b < B ? b : B - 1;                 // rows past the batch compute on a valid frame, never stored
+            const int nrows = min(32, B - b0);
+            float t0 = 0.f, t1 = 0.f, t2 = 0.f, sc = 1.f;
+            if (theta) {                                      // world = (x + transl) * scale * cs (smplify.py:190)
+                const float* th = theta + (size_t)bl * NP;
+                t0 = __ldg(th); t1 = __ldg(th + 1); t2 = __ldg(th + 2); sc = __ldg(th + 3);
+            }
             tc::mbar_wait(&p.tmem_full[buf], (i >> 1) & 1);
             tc::tc_fence_after();
-            const uint32_t tmem_d = tmem_base + (uint32_t)(buf * TC_BN1);
-            for (int chunk = 0; chunk < TC_BN1 / 96; ++chunk) {
+            const uint32_t tmem_d = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * TC_BN1 + h * 96);
+            const float4* ATb = AT + bl;
 #pragma unroll 1
-                for (int part = 0; part < 3; ++part) {
-                    uint32_t r[32];
-                    tc::tmem_ld32(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(chunk * 96 + part * 32), r);
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) myVp[lane * TC_VP_LD + part * 32 + e] = __uint_as_float(r[e]);
-                }
-                if (chunk == TC_BN1 / 96 - 1) {               // accumulator fully read: hand it back to the MMA warp
+            for (int pass = 0; pass < 2; ++pass) {
+                uint32_t r[48];
+                tc::tmem_ld48(tmem_d + (uint32_t)(pass * 48), r);
+                if (pass == 1) {                              // accumulator half fully read: hand it back to the MMA warp
                     tc::tc_fence_before();
                     __syncwarp();
                     if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(&tmem_empty[buf])) : "memory");
                 }
-                __syncwarp();
-                const int v = n0 / 3 + chunk * 32 + lane;
-                if (v < vs.n) {
+                const int vbase = n0 / 3 + h * 32 + pass * 16;
+                if (vbase >= vs.n) continue;                  // warp-uniform: pad vertices of the last tile
+                if (AT == nullptr) {                          // blend only: v_posed rows (the per-frame kernel skins what it needs)
+#pragma unroll
+                    for (int c = 0; c < 48; ++c) st[c * TC_ST_LD + lane] = __uint_as_float(r[c]);
+                    __syncwarp();
+                    tc::store_rows48(st, vposed + (size_t)b0 * ld_v + 3 * vbase, (size_t)ld_v, 3 * min(16, vs.n - vbase), nrows, lane);
+                    __syncwarp();
+                    continue;
+                }
+#pragma unroll
+                for (int vi = 0; vi < 16; ++vi) {
+                    const int v = min(vbase + vi, vs.n - 1);  // warp-uniform (clamped pad vertices are not stored)
+                    const float px = __uint_as_float(r[3 * vi]), py = __uint_as_float(r[3 * vi + 1]), pz = __uint_as_float(r[3 * vi + 2]);
+                    float T[12];
+#pragma unroll
+                    for (int e = 0; e < 12; ++e) T[e] = 0.f;
                     const int32_t* ej = vs.ell_j + (size_t)v * nnz;
                     const float* ew = vs.ell_w + (size_t)v * nnz;
-                    int jo[4]; float jw[4];                      // first 4 influences in registers (SMPL / SMPL-X: nnz = 4)
+                    int jo[4]; float jw[4];
+                    if (nnz == 4) {                           // SMPL / SMPL-X: one 16-byte uniform load each
+                        const int4 j4 = __ldg(reinterpret_cast<const int4*>(ej));
+                        const float4 w4 = __ldg(reinterpret_cast<const float4*>(ew));
+                        jo[0] = j4.x; jo[1] = j4.y; jo[2] = j4.z; jo[3] = j4.w;
+                        jw[0] = w4.x; jw[1] = w4.y; jw[2] = w4.z; jw[3] = w4.w;
+                    } else {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) { jo[k] = (k < nnz) ? __ldg(ej + k) * 12 : 0; jw[k] = (k < nnz) ? __ldg(ew + k) : 0.f; }
-                    for (int fr = 0; fr < 32; ++fr) {
-                        const int b = b0 + 32 * q + fr;
-                        if (b >= B) break;
-                        const float px = myVp[fr * TC_VP_LD + 3 * lane], py = myVp[fr * TC_VP_LD + 3 * lane + 1],
-                                    pz = myVp[fr * TC_VP_LD + 3 * lane + 2];
-                        float T[12];
-#pragma unroll
-                        for (int e = 0; e < 12; ++e) T[e] = 0.f;
-                        const float* Ab = A + (size_t)b * J * 12;
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const float w = jw[k];
-                            const float4* Aj = reinterpret_cast<const float4*>(Ab + jo[k]);
-                            const float4 r0 = __ldg(Aj), r1 = __ldg(Aj + 1), r2 = __ldg(Aj + 2);
-                            T[0] = fmaf(w, r0.x, T[0]); T[1] = fmaf(w, r0.y, T[1]); T[2] = fmaf(w, r0.z, T[2]); T[3] = fmaf(w, r0.w, T[3]);
-                            T[4] = fmaf(w, r1.x, T[4]); T[5] = fmaf(w, r1.y, T[5]); T[6] = fmaf(w, r1.z, T[6]); T[7] = fmaf(w, r1.w, T[7]);
-                            T[8] = fmaf(w, r2.x, T[8]); T[9] = fmaf(w, r2.y, T[9]); T[10] = fmaf(w, r2.z, T[10]); T[11] = fmaf(w, r2.w, T[11]);
-                        }
-                        for (int k = 4; k < nnz; ++k) {
-                            const float w = __ldg(ew + k);
-                            const float4* Aj = reinterpret_cast<const float4*>(Ab + __ldg(ej + k) * 12);
-                            const float4 r0 = __ldg(Aj), r1 = __ldg(Aj + 1), r2 = __ldg(Aj + 2);
-                            T[0] = fmaf(w, r0.x, T[0]); T[1] = fmaf(w, r0.y, T[1]); T[2] = fmaf(w, r0.z, T[2]); T[3] = fmaf(w, r0.w, T[3]);
-                            T[4] = fmaf(w, r1.x, T[4]); T[5] = fmaf(w, r1.y, T[5]); T[6] = fmaf(w, r1.z, T[6]); T[7] = fmaf(w, r1.w, T[7]);
-                            T[8] = fmaf(w, r2.x, T[8]); T[9] = fmaf(w, r2.y, T[9]); T[10] = fmaf(w, r2.z, T[10]); T[11] = fmaf(w, r2.w, T[11]);
-                        }
-                        float ox = T[0] * px + T[1] * py + T[2] * pz + T[3];
-                        float oy = T[4] * px + T[5] * py + T[6] * pz + T[7];
-                        float oz = T[8] * px + T[9] * py + T[10] * pz + T[11];
-                        if (theta) {
-                            const float* th = theta + (size_t)b * NP;
-                            const float sc = __ldg(th + 3);
-                            ox = (ox + __ldg(th + 0)) * sc * cs; oy = (oy + __ldg(th + 1)) * sc * cs; oz = (oz + __ldg(th + 2)) * sc * cs;
-                        }
-                        float* o = verts + (size_t)b * ld_v + 3 * v;
-                        o[0] = ox; o[1] = oy; o[2] = oz;
-                        if (vposed) {
-                            float* qv = vposed + (size_t)b * ld_v + 3 * v;
-                            qv[0] = px; qv[1] = py; qv[2] = pz;
-                        }
+                        for (int k = 0; k < 4; ++k) { jo[k] = (k < nnz) ? __ldg(ej + k) : 0; jw[k] = (k < nnz) ? __ldg(ew + k) : 0.f; }
                     }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float w = jw[k];
+                        const float4* Aj = ATb + (size_t)(jo[k] * 3) * Bz;
+                        const float4 r0 = __ldg(Aj), r1 = __ldg(Aj + Bz), r2 = __ldg(Aj + 2 * Bz);
+                        T[0] = fmaf(w, r0.x, T[0]); T[1] = fmaf(w, r0.y, T[1]); T[2] = fmaf(w, r0.z, T[2]); T[3] = fmaf(w, r0.w, T[3]);
+                        T[4] = fmaf(w, r1.x, T[4]); T[5] = fmaf(w, r1.y, T[5]); T[6] = fmaf(w, r1.z, T[6]); T[7] = fmaf(w, r1.w, T[7]);
+                        T[8] = fmaf(w, r2.x, T[8]); T[9] = fmaf(w, r2.y, T[9]); T[10] = fmaf(w, r2.z, T[10]); T[11] = fmaf(w, r2.w, T[11]);
+                    }
+                    for (int k = 4; k < nnz; ++k) {
+                        const float w = __ldg(ew + k);
+                        const float4* Aj = ATb + (size_t)(__ldg(ej + k) * 3) * Bz;
+                        const float4 r0 = __ldg(Aj), r1 = __ldg(Aj + Bz), r2 = __ldg(Aj + 2 * Bz);
+                        T[0] = fmaf(w, r0.x, T[0]); T[1] = fmaf(w, r0.y, T[1]); T[2] = fmaf(w, r0.z, T[2]); T[3] = fmaf(w, r0.w, T[3]);
+                        T[4] = fmaf(w, r1.x, T[4]); T[5] = fmaf(w, r1.y, T[5]); T[6] = fmaf(w, r1.z, T[6]); T[7] = fmaf(w, r1.w, T[7]);
+                        T[8] = fmaf(w, r2.x, T[8]); T[9] = fmaf(w, r2.y, T[9]); T[10] = fmaf(w, r2.z, T[10]); T[11] = fmaf(w, r2.w, T[11]);
+                    }
+                    float ox = T[0] * px + T[1] * py + T[2] * pz + T[3];
+                    float oy = T[4] * px + T[5] * py + T[6] * pz + T[7];
+                    float oz = T[8] * px + T[9] * py + T[10] * pz + T[11];
+                    if (theta) { ox = (ox + t0) * sc * cs; oy = (oy + t1) * sc * cs; oz = (oz + t2) * sc * cs; }
+                    st[(3 * vi) * TC_ST_LD + lane] = ox;
+                    st[(3 * vi + 1) * TC_ST_LD + lane] = oy;
+                    st[(3 * vi + 2) * TC_ST_LD + lane] = oz;
+                }
+                __syncwarp();
+                const int ncols = 3 * min(16, vs.n - vbase);
+                tc::store_rows48(st, verts + (size_t)b0 * ld_v + 3 * vbase, (size_t)ld_v, ncols, nrows, lane);
+                if (vposed) {
+                    __syncwarp();
+#pragma unroll
+                    for (int c = 0; c < 48; ++c) st[c * TC_ST_LD + lane] = __uint_as_float(r[c]);
+                    __syncwarp();
+                    tc::store_rows48(st, vposed + (size_t)b0 * ld_v + 3 * vbase, (size_t)ld_v, ncols, nrows, lane);
                 }
                 __syncwarp();
             }
@@ -332,8 +401,8 @@ __global__ void __launch_bounds__(192, 1) k_blend_bwd_tc(const __grid_constant__
     extern __shared__ uint8_t smem_raw[];
     uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     tc::Pipe p;
-    p.a_bytes = TC_BM * 128;
-    p.b_bytes = (uint32_t)BN * 128;
+    p.a_bytes = TC_BM * TC_ROWB;
+    p.b_bytes = (uint32_t)BN * TC_ROWB;
     p.stage_base = base;
     uint64_t* bars = reinterpret_cast<uint64_t*>(base + TC_STAGES * p.stage_bytes());
     p.full = bars; p.empty = bars + TC_STAGES; p.tmem_full = bars + 2 * TC_STAGES;
@@ -423,7 +492,7 @@ static bf_encode_tiled_fn bf_get_encode() {
     return fn;
 }
 
-// [rows, cols] fp32 row-major with leading dimension ld (elements); box = 32 cols (128 B) x box_rows
+// [rows, cols] fp32 row-major with leading dimension ld (elements); box = TC_BK cols (one swizzle row) x box_rows
 static int bf_make_map(CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
     bf_encode_tiled_fn enc = bf_get_encode();
     if (!enc) { bf_set_error("cuTensorMapEncodeTiled not available from the driver"); return BF_ECUDA; }
@@ -432,7 +501,7 @@ static int bf_make_map(CUtensorMap* m, const float* base, uint64_t rows, uint64_
     cuuint32_t box[2] = {TC_BK, box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, TC_BK == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { bf_set_error("cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu ld=%llu", (int)r,
                                           (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld); return BF_ECUDA; }
@@ -440,20 +509,21 @@ static int bf_make_map(CUtensorMap* m, const float* base, uint64_t rows, uint64_
 }
 
 static inline bool bf_tc_ready_fwd(const BfVSet* vs, const BfFrames* f) {
-    return (f->flags & BF_F_TC) && vs->Bt_hi && vs->Bt_lo && f->pf_hi && f->pf_lo;
+    return (f->flags & BF_F_TC) && vs->Bt_hi && vs->Bt_lo && f->pf_hi && f->pf_lo && f->A_T;
 }
 static inline bool bf_tc_ready_bwd(const BfVSet* vs, const BfFrames* f) {
     return (f->flags & BF_F_TC) && vs->Bm_hi && vs->Bm_lo && f->dvp_hi && f->dvp_lo;
 }
 
-static int bf_skin_forward_tc(const BfModel* m, const BfVSet* vs, const BfFrames* f, cudaStream_t s) {
+// blend_only: write v_posed only (no skinning, f->verts untouched)
+static int bf_skin_forward_tc(const BfModel* m, const BfVSet* vs, const BfFrames* f, cudaStream_t s, bool blend_only = false) {
     CUtensorMap a_hi, a_lo, b_hi, b_lo;
     int rc;
     if ((rc = bf_make_map(&a_hi, f->pf_hi, f->B, m->Kp, m->Kp, TC_BM))) return rc;
     if ((rc = bf_make_map(&a_lo, f->pf_lo, f->B, m->Kp, m->Kp, TC_BM))) return rc;
     if ((rc = bf_make_map(&b_hi, vs->Bt_hi, vs->ldn, m->Kp, m->Kp, TC_BN1))) return rc;
     if ((rc = bf_make_map(&b_lo, vs->Bt_lo, vs->ldn, m->Kp, m->Kp, TC_BN1))) return rc;
-    const size_t smem = 1024 + TC_STAGES * (2 * TC_BM * 128 + 2 * TC_BN1 * 128) + 4 * 32 * TC_VP_LD * 4 + 128;
+    const size_t smem = 1024 + TC_STAGES * (2 * TC_BM * TC_ROWB + 2 * TC_BN1 * TC_ROWB) + TC_EPI_WARPS * TC_ST_FLOATS * 4 + 128;
     static bool attr = false;
     static int num_sms = 0;
     if (!attr) {
@@ -467,7 +537,8 @@ static int bf_skin_forward_tc(const BfModel* m, const BfVSet* vs, const BfFrames
     const int tn = (vs->ldn + TC_BN1 - 1) / TC_BN1, tm = (f->B + TC_BM - 1) / TC_BM;
     const int tiles = tn * tm;
     const int grid = tiles < num_sms ? tiles : num_sms;          // persistent: one CTA per SM
-    k_skin_fwd_tc<<<grid, 192, smem, s>>>(a_hi, a_lo, b_hi, b_lo, *vs, m->J, m->Kp, f->A, f->verts, f->vposed, f->B, f->ld_v,
+    k_skin_fwd_tc<<<grid, 64 + 32 * TC_EPI_WARPS, smem, s>>>(a_hi, a_lo, b_hi, b_lo, *vs, m->J, m->Kp,
+                                          blend_only ? nullptr : reinterpret_cast<const float4*>(f->A_T), f->verts, f->vposed, f->B, f->ld_v,
                                           (f->flags & BF_F_WORLD) ? f->theta : nullptr, m->NP, f->constant_scale, tn, tiles);
     BF_LAUNCH_CHECK();
     return BF_OK;
@@ -490,7 +561,7 @@ static int bf_blend_backward_tc(const BfModel* m, const BfVSet* vs, const BfFram
         for (int i = 0; i < 3; ++i) {
             const int bn = cand[i];
             if (bn > m->Kp || m->Kp % bn != 0) continue;
-            const size_t sm = 1024 + TC_STAGES * (2 * TC_BM * 128 + 2 * (size_t)bn * 128) + 64;
+            const size_t sm = 1024 + TC_STAGES * (2 * TC_BM * TC_ROWB + 2 * (size_t)bn * TC_ROWB) + 64;
             const int per_sm = (int)((227 * 1024) / sm) < 1 ? 1 : (int)((227 * 1024) / sm);
             const long tiles = (long)(m->Kp / bn) * mt;
             const long waves = (tiles + (long)num_sms * per_sm - 1) / ((long)num_sms * per_sm);
@@ -502,7 +573,7 @@ static int bf_blend_backward_tc(const BfModel* m, const BfVSet* vs, const BfFram
     if ((rc = bf_make_map(&a_lo, f->dvp_lo, f->B, vs->ldn, vs->ldn, TC_BM))) return rc;
     if ((rc = bf_make_map(&b_hi, vs->Bm_hi, m->Kp, vs->ldn, vs->ldn, BN))) return rc;
     if ((rc = bf_make_map(&b_lo, vs->Bm_lo, m->Kp, vs->ldn, vs->ldn, BN))) return rc;
-    const size_t smem = 1024 + TC_STAGES * (2 * TC_BM * 128 + 2 * (size_t)BN * 128) + 64;
+    const size_t smem = 1024 + TC_STAGES * (2 * TC_BM * TC_ROWB + 2 * (size_t)BN * TC_ROWB) + 64;
     static size_t attr = 0;
     if (attr < smem) {
         cudaError_t e = cudaFuncSetAttribute(k_blend_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -510,7 +581,7 @@ static int bf_blend_backward_tc(const BfModel* m, const BfVSet* vs, const BfFram
         attr = smem;
     }
     const int num_k = vs->ldn / TC_BK;
-    const int cps = 64;                                   // <= 2048 coordinates per tensor-core accumulation run
+    const int cps = 2048 / TC_BK;                         // <= 2048 coordinates per tensor-core accumulation run
     const int S = (num_k + cps - 1) / cps;
     const size_t stride = (size_t)f->B * m->Kp;
     if (S > 1 && (!f->ws || (size_t)f->ws_floats < (size_t)S * stride)) return 1;   // caller falls back to the FFMA kernel

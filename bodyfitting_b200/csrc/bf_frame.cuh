@@ -43,35 +43,95 @@ __device__ __forceinline__ float warp_reduce16(const float* v, int lane) {
     return d;
 }
 
-__global__ void __launch_bounds__(FR_THREADS, 4) k_frame_loss_bwd(BfModel m, BfVSet vs, BfFrames f) {
+// T = sum_k w_k A[j_k] for vertex v (rows of A in shared memory); NR = 12 (forward) or 9 (rotation part, backward)
+template <int NC>
+__device__ __forceinline__ void blend_transform(const BfVSet& vs, const float* As, int v, float (&T)[3 * NC]) {
+    const int nnz = vs.nnz;
+    const int32_t* ej = vs.ell_j + (size_t)v * nnz;
+    const float* ew = vs.ell_w + (size_t)v * nnz;
+#pragma unroll
+    for (int e = 0; e < 3 * NC; ++e) T[e] = 0.f;
+    for (int k = 0; k < nnz; ++k) {
+        const float w = __ldg(ew + k);
+        const float4* Aj = reinterpret_cast<const float4*>(As + __ldg(ej + k) * 12);
+        const float4 r0 = Aj[0], r1 = Aj[1], r2 = Aj[2];
+        T[0] = fmaf(w, r0.x, T[0]); T[1] = fmaf(w, r0.y, T[1]); T[2] = fmaf(w, r0.z, T[2]);
+        T[NC] = fmaf(w, r1.x, T[NC]); T[NC + 1] = fmaf(w, r1.y, T[NC + 1]); T[NC + 2] = fmaf(w, r1.z, T[NC + 2]);
+        T[2 * NC] = fmaf(w, r2.x, T[2 * NC]); T[2 * NC + 1] = fmaf(w, r2.y, T[2 * NC + 1]); T[2 * NC + 2] = fmaf(w, r2.z, T[2 * NC + 2]);
+        if (NC == 4) { T[3] = fmaf(w, r0.w, T[3]); T[7] = fmaf(w, r1.w, T[7]); T[11] = fmaf(w, r2.w, T[11]); }
+    }
+}
+
+// Work is restricted to the frame's LIVE vertices: the static picks / landmarks plus the 17 x 3 contour vertices of
+// the frame's yaw row (vs.lv_* / lt_* / lj_*, built per row on the host).  Every other vertex of the active set has
+// an exactly-zero gradient for this frame, so it is neither skinned nor back-propagated; its dvp entries are zeroed.
+// skin_here != 0: v_posed comes from the blend GEMM and the live vertices are skinned in this kernel (f.verts unused).
+__global__ void __launch_bounds__(FR_THREADS, 4) k_frame_loss_bwd(BfModel m, BfVSet vs, BfFrames f, int skin_here) {
     extern __shared__ __align__(16) float sm[];
     float* gx = sm;                               // [BF_MAXK*3] joint gradients
     float* cam = gx + BF_MAXK * 3;                // [BF_MAXVIEWS*12]
     float* red = cam + BF_MAXVIEWS * 12;          // [5*8]
     float* jq = red + 64;                         // [BF_MAXK*3] joint positions + translation
     float* As = jq + BF_MAXK * 3;                 // [J*12] this frame's joint transforms
-    float* dv = As + ((m.J * 12 + 15) & ~15);     // [3*n_pad] d(verts)
+    float* dv = As + ((m.J * 12 + 15) & ~15);     // [3*n_pad] skinned vertices, later d(verts)
     float* vp = dv + vs.ldn;                      // [3*n_pad] v_posed
     const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int K = m.K_used, Nv = f.Nv, J = m.J;
+    const int yaw = f.yaw ? f.yaw[b] : 0;
+    const int row = vs.n_rows > 1 ? yaw : 0;
+    const int L = __ldg(vs.lv_n + row);
+    const int32_t* lv = vs.lv_vid + (size_t)row * vs.lmax;
     for (int i = t; i < Nv * 12; i += FR_THREADS) cam[i] = f.cams[i];
-    for (int i = t; i < J * 12; i += FR_THREADS) As[i] = f.A[(size_t)b * J * 12 + i];
-    for (int i = t; i < 3 * vs.n; i += FR_THREADS) vp[i] = f.vposed[(size_t)b * f.ld_v + i];
+    {
+        const float4* src = reinterpret_cast<const float4*>(f.A + (size_t)b * J * 12);
+        for (int i = t; i < J * 3; i += FR_THREADS) reinterpret_cast<float4*>(As)[i] = src[i];
+        const float4* vsrc = reinterpret_cast<const float4*>(f.vposed + (size_t)b * f.ld_v);     // ld_v % 4 == 0 (checked on the host)
+        for (int i = t; i < (3 * vs.n + 3) / 4; i += FR_THREADS) reinterpret_cast<float4*>(vp)[i] = vsrc[i];
+        if (!skin_here) {
+            const float4* wsrc = reinterpret_cast<const float4*>(f.verts + (size_t)b * f.ld_v);
+            for (int i = t; i < (3 * vs.n + 3) / 4; i += FR_THREADS) reinterpret_cast<float4*>(dv)[i] = wsrc[i];
+        }
+    }
+    // clear this frame's d(v_posed) rows: only live vertices are written below (a vertex live on another yaw row in an
+    // earlier iteration must read as zero in the blend backward GEMM)
+    const bool split = f.dvp_hi != nullptr;
+    {
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int n4 = (3 * vs.n + 3) / 4;
+        if (split) {
+            float4* oh = reinterpret_cast<float4*>(f.dvp_hi + (size_t)b * vs.ldn);
+            float4* ol = reinterpret_cast<float4*>(f.dvp_lo + (size_t)b * vs.ldn);
+            for (int i = t; i < n4; i += FR_THREADS) { oh[i] = z; ol[i] = z; }
+        } else {
+            float4* o = reinterpret_cast<float4*>(f.dvp + (size_t)b * f.ld_v);
+            for (int i = t; i < n4; i += FR_THREADS) o[i] = z;
+        }
+    }
     __syncthreads();
     const float* th = f.theta + (size_t)b * m.NP;
     const float tx = th[0], ty = th[1], tz = th[2], sc = th[3];
     const float cs = f.constant_scale;
     const float icoef = 1024.0f / f.imsize;          // 1 / scale_coeff (exact for power-of-two image sizes)
     const float s2 = f.sigma * f.sigma;
-    const int yaw = f.yaw ? f.yaw[b] : 0;
     const float* Jtr_b = f.Jtr + (size_t)b * J * 3;
-    const float* verts_b = f.verts + (size_t)b * f.ld_v;
     const float invNv = 1.0f / (float)Nv;
 
+    if (skin_here) {                                 // skin the live vertices: verts = (sum_k w_k A_jk) [v_posed; 1]
+        for (int i = t; i < L; i += FR_THREADS) {
+            const int v = __ldg(lv + i);
+            float T[12];
+            blend_transform<4>(vs, As, v, T);
+            const float px = vp[3 * v], py = vp[3 * v + 1], pz = vp[3 * v + 2];
+            dv[3 * v] = T[0] * px + T[1] * py + T[2] * pz + T[3];
+            dv[3 * v + 1] = T[4] * px + T[5] * py + T[6] * pz + T[7];
+            dv[3 * v + 2] = T[8] * px + T[9] * py + T[10] * pz + T[11];
+        }
+        __syncthreads();
+    }
     // joint positions of this frame -> shared (model space + translation, i.e. q = x + T)
     for (int k = t; k < K; k += FR_THREADS) {
         float x[3];
-        joint_pos(vs, k, yaw, Jtr_b, verts_b, x);
+        joint_pos(vs, k, yaw, Jtr_b, dv, x);
         jq[k * 3] = x[0] + tx; jq[k * 3 + 1] = x[1] + ty; jq[k * 3 + 2] = x[2] + tz;
     }
     __syncthreads();
@@ -129,7 +189,7 @@ __global__ void __launch_bounds__(FR_THREADS, 4) k_frame_loss_bwd(BfModel m, BfV
         const float s = warp_sum(acc5[i]);
         if (lane == 0) red[i * 8 + warp] = s;
     }
-    __syncthreads();                               // gx + red complete
+    __syncthreads();                               // gx + red complete; skinned vertices (dv) no longer needed
     if (t == 0) {
         float tot[5];
         for (int i = 0; i < 5; ++i) { float s = 0.f; for (int w = 0; w < FR_THREADS / 32; ++w) s += red[i * 8 + w]; tot[i] = s; }
@@ -137,28 +197,36 @@ __global__ void __launch_bounds__(FR_THREADS, 4) k_frame_loss_bwd(BfModel m, BfV
         float* g = f.grad + (size_t)b * m.NP;
         g[0] = tot[1]; g[1] = tot[2]; g[2] = tot[3]; g[3] = tot[4];
     }
-    scatter_by_target(vs, J, K, yaw, gx, f.dJtr + (size_t)b * J * 3, dv, 0);
+    // joint gradients -> chain joints (static gather by target) and live vertices (per-row gather lists)
+    float* dJtr_b = f.dJtr + (size_t)b * J * 3;
+    const int32_t* ltp = vs.lt_ptr + (size_t)row * (vs.lmax + 1);
+    for (int i = t; i < J + L; i += FR_THREADS) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+        if (i < J) {
+            const int e0 = __ldg(vs.tg_ptr + i), e1 = __ldg(vs.tg_ptr + i + 1);
+            for (int e = e0; e < e1; ++e) {
+                const int k = __ldg(vs.tg_k + e);
+                if (k < K) { const float w = __ldg(vs.tg_w + e); a0 += w * gx[k * 3]; a1 += w * gx[k * 3 + 1]; a2 += w * gx[k * 3 + 2]; }
+            }
+            dJtr_b[i * 3] = a0; dJtr_b[i * 3 + 1] = a1; dJtr_b[i * 3 + 2] = a2;
+        } else {
+            const int li = i - J;
+            const int e0 = __ldg(ltp + li), e1 = __ldg(ltp + li + 1);
+            for (int e = e0; e < e1; ++e) {
+                const int k = __ldg(vs.lt_k + e);
+                if (k < K) { const float w = __ldg(vs.lt_w + e); a0 += w * gx[k * 3]; a1 += w * gx[k * 3 + 1]; a2 += w * gx[k * 3 + 2]; }
+            }
+            const int v = __ldg(lv + li);
+            dv[3 * v] = a0; dv[3 * v + 1] = a1; dv[3 * v + 2] = a2;
+        }
+    }
     __syncthreads();
 
-    // skinning backward, vertex side: dvp = (sum_k w_k A_jk)[:3,:3]^T dverts
-    const bool split = f.dvp_hi != nullptr;
-    for (int v = t; v < vs.n; v += FR_THREADS) {
-        const int nnz = vs.nnz;
-        const int32_t* ej = vs.ell_j + (size_t)v * nnz;
-        const float* ew = vs.ell_w + (size_t)v * nnz;
+    // skinning backward, vertex side (live vertices): dvp = (sum_k w_k A_jk)[:3,:3]^T dverts
+    for (int i = t; i < L; i += FR_THREADS) {
+        const int v = __ldg(lv + i);
         float T[9];
-#pragma unroll
-        for (int e = 0; e < 9; ++e) T[e] = 0.f;
-        // contour candidates not selected by this frame's yaw row carry an exactly-zero gradient
-        const bool live = dv[3 * v] != 0.f || dv[3 * v + 1] != 0.f || dv[3 * v + 2] != 0.f;
-        for (int k = 0; live && k < nnz; ++k) {
-            const float w = __ldg(ew + k);
-            const float4* Aj = reinterpret_cast<const float4*>(As + __ldg(ej + k) * 12);
-            const float4 r0 = Aj[0], r1 = Aj[1], r2 = Aj[2];
-            T[0] = fmaf(w, r0.x, T[0]); T[1] = fmaf(w, r0.y, T[1]); T[2] = fmaf(w, r0.z, T[2]);
-            T[3] = fmaf(w, r1.x, T[3]); T[4] = fmaf(w, r1.y, T[4]); T[5] = fmaf(w, r1.z, T[5]);
-            T[6] = fmaf(w, r2.x, T[6]); T[7] = fmaf(w, r2.y, T[7]); T[8] = fmaf(w, r2.z, T[8]);
-        }
+        blend_transform<3>(vs, As, v, T);
         const float gx_ = dv[3 * v], gy_ = dv[3 * v + 1], gz_ = dv[3 * v + 2];
         const float o0 = T[0] * gx_ + T[3] * gy_ + T[6] * gz_;
         const float o1 = T[1] * gx_ + T[4] * gy_ + T[7] * gz_;
@@ -172,13 +240,14 @@ __global__ void __launch_bounds__(FR_THREADS, 4) k_frame_loss_bwd(BfModel m, BfV
             o[0] = o0; o[1] = o1; o[2] = o2;
         }
     }
-    // skinning backward, joint side: dA[j] = sum_v w_vj dverts_v (x) [vposed_v; 1]
+    // skinning backward, joint side: dA[j] = sum_{live v} w_vj dverts_v (x) [vposed_v; 1]
     float* dAb = f.dA + (size_t)b * J * 12;
     if (vs.n_nz < J)
         for (int i = t; i < J * 12; i += FR_THREADS) dAb[i] = 0.f;
     __syncthreads();
     // 8 lanes per joint (skinning lists are short), 4 joints per warp at a time; the 12 (padded 16)
     // partial sums are reduced over the 8 lanes with a multi-value butterfly: 14 shuffles per 4 joints
+    const int32_t* ljp = vs.lj_ptr + (size_t)row * (vs.n_nz + 1);
     for (int jn0 = 0; jn0 < vs.n_nz; jn0 += 4 * (FR_THREADS / 32)) {
         const int jn = jn0 + warp * 4 + (lane >> 3);
         const bool jv_ = jn < vs.n_nz;
@@ -187,10 +256,10 @@ __global__ void __launch_bounds__(FR_THREADS, 4) k_frame_loss_bwd(BfModel m, BfV
         float acc[16];
 #pragma unroll
         for (int e = 0; e < 16; ++e) acc[e] = 0.f;
-        const int e0 = jv_ ? __ldg(vs.jv_ptr + j) : 0, e1 = jv_ ? __ldg(vs.jv_ptr + j + 1) : 0;
+        const int e0 = jv_ ? __ldg(ljp + jn) : 0, e1 = jv_ ? __ldg(ljp + jn + 1) : 0;
         for (int e = e0 + sl; e < e1; e += 8) {
-            const int v = __ldg(vs.jv_vid + e);
-            const float w = __ldg(vs.jv_w + e);
+            const int v = __ldg(vs.lj_vid + e);
+            const float w = __ldg(vs.lj_w + e);
             const float gx_ = w * dv[3 * v], gy_ = w * dv[3 * v + 1], gz_ = w * dv[3 * v + 2];
             const float px = vp[3 * v], py = vp[3 * v + 1], pz = vp[3 * v + 2];
             acc[0] = fmaf(gx_, px, acc[0]); acc[1] = fmaf(gx_, py, acc[1]); acc[2] = fmaf(gx_, pz, acc[2]); acc[3] += gx_;

@@ -137,13 +137,15 @@ __device__ __forceinline__ void pose_write_outputs(const BfModel& m, const BfFra
         }
     }
     // A_j = [GR_j | Gt_j - GR_j Jr_j],  posed joints = Gt
+    float4* At = reinterpret_cast<float4*>(f.A_T);     // frame-minor copy for the lane = frame skinning epilogue (bf_blend_tc.cuh)
     for (int j = lane; j < J; j += 32) {
-        float* Aj = f.A + ((size_t)b * J + j) * 12;
+        float4* Aj = reinterpret_cast<float4*>(f.A + ((size_t)b * J + j) * 12);
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
             const float g0 = S.GR[j * 9 + r * 3], g1 = S.GR[j * 9 + r * 3 + 1], g2 = S.GR[j * 9 + r * 3 + 2];
-            Aj[r * 4 + 0] = g0; Aj[r * 4 + 1] = g1; Aj[r * 4 + 2] = g2;
-            Aj[r * 4 + 3] = S.Gt[j * 3 + r] - (g0 * S.Jr[j * 3] + g1 * S.Jr[j * 3 + 1] + g2 * S.Jr[j * 3 + 2]);
+            const float4 row = make_float4(g0, g1, g2, S.Gt[j * 3 + r] - (g0 * S.Jr[j * 3] + g1 * S.Jr[j * 3 + 1] + g2 * S.Jr[j * 3 + 2]));
+            Aj[r] = row;
+            if (At) At[(size_t)(j * 3 + r) * f.B + b] = row;
             f.Jtr[((size_t)b * J + j) * 3 + r] = S.Gt[j * 3 + r];
         }
     }

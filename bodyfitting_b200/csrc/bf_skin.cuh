@@ -273,3 +273,99 @@ __global__ void __launch_bounds__(256) k_blend_bwd(BfVSet vs, int Kp, const floa
         }
     }
 }
+
+// ---------------------------------------------------------------------------------------------
+// k_skin_rows : verts = (sum_k w_k A[b, j_k]) [v_posed; 1] for 32 frames x a slab of vertices per CTA, with the
+// joint transforms of the 32 frames resident in SHARED memory in frame-minor order As[(j*3 + r)][frame] (float4 rows).
+//
+// Why this shape: skinning gathers 4 x 48 B of transforms per vertex and frame -- 16x the 12 B it writes.  Gathered
+// from L2 that traffic bounds the kernel far below the HBM roofline (measured: the GEMM-epilogue version of this step
+// ran at ~37 us per 128x64 tile whatever the GEMM depth), so the transforms have to be on chip, and they are reused by
+// every vertex of the sweep.  LANE = FRAME: the influences (joint, weight) of a vertex are warp-uniform and one
+// LDS.128 of the warp reads 32 consecutive frames of one transform row -- conflict-free for any skinning pattern.
+// v_posed / verts rows are transposed through a per-warp [48 coords][32 frames] tile so that global accesses are
+// row-contiguous.  In place (verts == vposed) is allowed: a warp reads its 16-vertex segment completely before it
+// writes it.
+#define SR_WARPS 16
+#define SR_LD 33
+__global__ void __launch_bounds__(32 * SR_WARPS, 1)
+k_skin_rows(BfVSet vs, int J, const float* __restrict__ A, const float* vposed, float* verts, int B, int ld_v,
+            const float* __restrict__ theta, int NP, float cs, int chunks_per_slab) {
+    extern __shared__ __align__(16) float sm_sr[];
+    float4* As = reinterpret_cast<float4*>(sm_sr);                          // [3J][32]
+    float* st = sm_sr + (size_t)3 * J * 32 * 4 + (threadIdx.x >> 5) * (48 * SR_LD);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b0 = blockIdx.x * 32;
+    const int nrows = min(32, B - b0);
+    {   // A[b][j][r] (float4) -> As[j*3 + r][frame]; global reads are contiguous per frame
+        const float4* src = reinterpret_cast<const float4*>(A);
+        const int n = 3 * J;
+        for (int i = threadIdx.x; i < 32 * n; i += blockDim.x) {
+            const int fl = i / n, jr = i - fl * n;
+            const int b = min(b0 + fl, B - 1);
+            As[jr * 32 + fl] = __ldg(src + (size_t)b * n + jr);
+        }
+    }
+    const int bl = min(b0 + lane, B - 1);
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f, sc = 1.f;
+    if (theta) {                                                            // world = (x + transl) * scale * cs
+        const float* th = theta + (size_t)bl * NP;
+        t0 = __ldg(th); t1 = __ldg(th + 1); t2 = __ldg(th + 2); sc = __ldg(th + 3);
+    }
+    __syncthreads();
+    const int nnz = vs.nnz;
+    const int n_chunks = (vs.n + 15) >> 4;
+    const int c_end = min(n_chunks, (int)(blockIdx.y + 1) * chunks_per_slab);
+    for (int ch = blockIdx.y * chunks_per_slab + warp; ch < c_end; ch += SR_WARPS) {
+        const int vbase = ch << 4;
+        const int ncols = 3 * min(16, vs.n - vbase);
+        const float* src = vposed + (size_t)b0 * ld_v + 3 * vbase;
+        float* dst = verts + (size_t)b0 * ld_v + 3 * vbase;
+        // rows -> tile (2 rows x 48 coords per three warp-wide loads)
+#pragma unroll 4
+        for (int rp = 0; rp < 16; ++rp) {
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+                const int idx = lane + 32 * s, hi = idx >= 48;
+                const int fr = 2 * rp + hi, c = idx - 48 * hi;
+                if (fr < nrows && c < ncols) st[c * SR_LD + fr] = src[(size_t)fr * ld_v + c];
+            }
+        }
+        __syncwarp();
+#pragma unroll 4
+        for (int vi = 0; vi < 16; ++vi) {
+            const int v = min(vbase + vi, vs.n - 1);                         // warp-uniform; clamped pad vertices are not stored
+            const int32_t* ej = vs.ell_j + (size_t)v * nnz;
+            const float* ew = vs.ell_w + (size_t)v * nnz;
+            float T[12];
+#pragma unroll
+            for (int e = 0; e < 12; ++e) T[e] = 0.f;
+            for (int k = 0; k < nnz; ++k) {
+                const float w = __ldg(ew + k);
+                const float4* Aj = As + (size_t)(__ldg(ej + k) * 3) * 32 + lane;
+                const float4 r0 = Aj[0], r1 = Aj[32], r2 = Aj[64];
+                T[0] = fmaf(w, r0.x, T[0]); T[1] = fmaf(w, r0.y, T[1]); T[2] = fmaf(w, r0.z, T[2]); T[3] = fmaf(w, r0.w, T[3]);
+                T[4] = fmaf(w, r1.x, T[4]); T[5] = fmaf(w, r1.y, T[5]); T[6] = fmaf(w, r1.z, T[6]); T[7] = fmaf(w, r1.w, T[7]);
+                T[8] = fmaf(w, r2.x, T[8]); T[9] = fmaf(w, r2.y, T[9]); T[10] = fmaf(w, r2.z, T[10]); T[11] = fmaf(w, r2.w, T[11]);
+            }
+            float* q = st + (3 * vi) * SR_LD + lane;
+            const float px = q[0], py = q[SR_LD], pz = q[2 * SR_LD];
+            float ox = T[0] * px + T[1] * py + T[2] * pz + T[3];
+            float oy = T[4] * px + T[5] * py + T[6] * pz + T[7];
+            float oz = T[8] * px + T[9] * py + T[10] * pz + T[11];
+            if (theta) { ox = (ox + t0) * sc * cs; oy = (oy + t1) * sc * cs; oz = (oz + t2) * sc * cs; }
+            q[0] = ox; q[SR_LD] = oy; q[2 * SR_LD] = oz;
+        }
+        __syncwarp();
+#pragma unroll 4
+        for (int rp = 0; rp < 16; ++rp) {
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+                const int idx = lane + 32 * s, hi = idx >= 48;
+                const int fr = 2 * rp + hi, c = idx - 48 * hi;
+                if (fr < nrows && c < ncols) dst[(size_t)fr * ld_v + c] = st[c * SR_LD + fr];
+            }
+        }
+        __syncwarp();
+    }
+}

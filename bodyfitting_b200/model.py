@@ -194,7 +194,7 @@ class PreparedModel(object):
                           hand_l=hand_l, hand_r=hand_r, **g)
         self.max_depth = int(depth.max())
         full_h = self._build_vset(np.arange(V, dtype=np.int64), Bm_rows, W, self.joint_table + self.ori_table)
-        act_h = self._build_vset(self.active_vids, Bm_rows, W, self.joint_table[:K_used])
+        act_h = self._build_vset(self.active_vids, Bm_rows, W, self.joint_table[:K_used], build_live=True)
         del Bm_rows
 
         # ---- upload ----------------------------------------------------------------------------
@@ -228,7 +228,7 @@ class PreparedModel(object):
             else:
                 setattr(vs, k, int(v))
 
-    def _build_vset(self, vids, Bm_rows, W, table):
+    def _build_vset(self, vids, Bm_rows, W, table, build_live=False):
         """Tables for the vertex set ``vids`` (sorted global vertex ids)."""
         J = self.J
         n = len(vids)
@@ -330,9 +330,59 @@ class PreparedModel(object):
         nzj = np.nonzero(np.diff(jv_ptr))[0].astype(np.int32)
         h['jv_nz'] = nzj if len(nzj) else np.zeros(1, np.int32)
         h['n_nz'] = len(nzj)
+        if build_live:
+            h.update(self._build_live_tables(J, n, entries, dyn_src if h['n_dyn'] else None, dyn_w, dyn_k, Ws, nzj))
         if xr_ptr is not None:
             h.update(xr_ptr=xr_ptr, xr_vid=xr_vid, xr_w=xr_w)
         return h
+
+    @staticmethod
+    def _build_live_tables(J, n, entries, dyn_src, dyn_w, dyn_k, Ws, nzj):
+        """Per contour row (79 yaw rows for SMPL-X, one row otherwise): the vertices of the set that carry a
+        non-zero keypoint gradient for a frame on that row (static picks / landmarks + the 17 x 3 contour vertices
+        of the row), the keypoint-gradient gather lists of those vertices (static entries first, then the contour
+        entries in slot order -- the accumulation order of the unfused kernels) and the joint->vertex skinning lists
+        restricted to them.  The fused per-frame kernel walks only these lists (k_frame_loss_bwd)."""
+        rows = dyn_src.shape[0] if dyn_src is not None else 1
+        static = {}
+        for t, k, a, w in entries:                                          # already sorted by (target, k)
+            if t >= J:
+                static.setdefault(t - J, []).append((k, w))
+        per_row = []
+        for a in range(rows):
+            ent = {v: list(e) for v, e in static.items()}
+            if dyn_src is not None:
+                for s_, k in enumerate(dyn_k):
+                    for i in range(3):
+                        ent.setdefault(int(dyn_src[a, s_, i]), []).append((k, float(dyn_w[a, s_, i])))
+            per_row.append(ent)
+        lmax = _round_up(max(len(e) for e in per_row), 32)
+        lv_n = np.zeros(rows, np.int32)
+        lv_vid = np.zeros((rows, lmax), np.int32)
+        lt_ptr = np.zeros((rows, lmax + 1), np.int32)
+        lt_k, lt_w = [], []
+        nnzj = max(1, len(nzj))
+        lj_ptr = np.zeros((rows, nnzj + 1), np.int32)
+        lj_vid, lj_w = [], []
+        for a, ent in enumerate(per_row):
+            live = sorted(ent)
+            lv_n[a] = len(live)
+            lv_vid[a, :len(live)] = live
+            for i, v in enumerate(live):
+                lt_ptr[a, i] = len(lt_k)
+                lt_k += [k for k, _ in ent[v]]
+                lt_w += [w for _, w in ent[v]]
+            lt_ptr[a, len(live):] = len(lt_k)
+            sub = Ws[live]                                                  # [L, J]
+            for jn, j in enumerate(nzj):
+                lj_ptr[a, jn] = len(lj_vid)
+                nzv = np.nonzero(sub[:, j])[0]
+                lj_vid += [live[x] for x in nzv]
+                lj_w += [float(sub[x, j]) for x in nzv]
+            lj_ptr[a, len(nzj):] = len(lj_vid)
+        pad1 = lambda x, dt: np.array(x if len(x) else [0], dtype=dt)
+        return dict(lv_n=lv_n, lv_vid=lv_vid, lt_ptr=lt_ptr, lt_k=pad1(lt_k, np.int32), lt_w=pad1(lt_w, np.float32),
+                    lj_ptr=lj_ptr, lj_vid=pad1(lj_vid, np.int32), lj_w=pad1(lj_w, np.float32), lmax=lmax, n_rows=rows)
 
     # ------------------------------------------------------------------------------------------
     def pack_theta(self, global_orient, body_pose, betas, transl=None, scale=None, leye=None, reye=None,

@@ -40,9 +40,10 @@ extern "C" {
 #define BF_ECUDA    -2   /* a CUDA runtime call / launch failed            */
 #define BF_EARCH    -3   /* device is not sm_100 (no fallback exists)      */
 
-#define BF_ABI_VERSION 11
+#define BF_ABI_VERSION 12
 #define BF_F_WORLD 1   /* forward outputs in world space: (x + transl) * scale * constant_scale */
 #define BF_F_TC    2   /* run the blend-shape contractions on tcgen05 tensor cores (3xTF32) */
+#define BF_F_SKIN_FUSED 4  /* bf_frame_loss_backward skins the frame's live vertices itself from vposed (after bf_blend_forward) */
 
 /* A vertex set: either all V vertices of the model or the compacted "active" subset
  * that the keypoint loss can touch.  All index tables refer to positions in this set. */
@@ -71,7 +72,17 @@ typedef struct BfVSet {
     const float*   Bm_lo;
     const int32_t* dyn_k;     /* [n_dyn] output joint index of each contour-landmark slot */
     const int32_t* jv_nz;     /* [n_nz] joints with a non-empty jv list */
-    int32_t n, n_pad, ldn, nnz, K_out, n_dyn, n_extra, n_nz;
+    /* "live" lists of the active set, one row per contour (yaw) row -- n_rows = 79 for SMPL-X, 1 otherwise; NULL for the
+     * full set.  A frame on row a has non-zero keypoint gradients only on lv_vid[a][0..lv_n[a]) */
+    const int32_t* lv_n;      /* [n_rows] */
+    const int32_t* lv_vid;    /* [n_rows, lmax] positions in this set, ascending */
+    const int32_t* lt_ptr;    /* [n_rows, lmax+1] absolute offsets into lt_k / lt_w: gradient gather list of live vertex i */
+    const int32_t* lt_k;      /* output joint index */
+    const float*   lt_w;      /* weight (static entries first, then contour entries in slot order) */
+    const int32_t* lj_ptr;    /* [n_rows, n_nz+1] absolute offsets: skinning list of joint jv_nz[jn] restricted to live vertices */
+    const int32_t* lj_vid;
+    const float*   lj_w;
+    int32_t n, n_pad, ldn, nnz, K_out, n_dyn, n_extra, n_nz, lmax, n_rows;
 } BfVSet;
 
 typedef struct BfModel {
@@ -129,6 +140,9 @@ typedef struct BfFrames {
     const float* halo_next;  /* [NP] theta of the frame after this shard's last frame (next rank), NULL at the sequence end */
     float*       fwd_state;  /* [B,24J] optional: full_pose, R, rest joints, chain rotations saved by the pose forward so the
                                 pose backward does not recompute them */
+    float*       A_T;        /* [3J, B, 4] frame-minor copy of A (row r of joint j, 32 consecutive frames = 512 contiguous bytes):
+                                the tensor-core skinning epilogue reads it with lane = frame (fully coalesced); written by the
+                                pose forward next to A; required by BF_F_TC */
     float*       ws;         /* split-K workspace of the tensor-core backward GEMM (>= ceil(ldn/2048) * B * Kp floats) or NULL */
     int64_t      ws_floats;
     double lr_ts, lr, beta1, beta2, eps;   /* Adam hyper-parameters (python floats in the reference: smplify.py:167-174) */
@@ -145,6 +159,8 @@ int         bf_check_device(void);                       /* BF_OK iff current de
 
 /* theta -> pf, A, Jtr, full_pose, yaw */
 int bf_pose_forward(const BfModel* m, const BfFrames* f, void* stream);
+/* blend shapes only (tensor-core path): pf @ Bm -> vposed; the fused per-frame kernel of the fit skins the live vertices itself */
+int bf_blend_forward(const BfModel* m, const BfFrames* f, int use_full, void* stream);
 /* blend shapes + skinning over a vertex set (use_full != 0: all vertices) -> verts, vposed */
 int bf_skin_forward(const BfModel* m, const BfFrames* f, int use_full, void* stream);
 /* model-space output joints [B,K_out,3] from Jtr / verts */
