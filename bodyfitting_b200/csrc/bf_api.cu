@@ -79,7 +79,14 @@ int bf_skin_forward(const BfModel* m, const BfFrames* f, int use_full, void* str
     const BfVSet* vs = use_full ? &m->full : &m->act;
     rc = check_vset(vs, f); if (rc) return rc;
     BF_REQUIRE(f->pf && f->A && f->verts, "pf/A/verts is null");
-    if (bf_tc_ready_fwd(vs, f)) return bf_skin_forward_tc(m, vs, f, (cudaStream_t)stream);
+    if (bf_tc_ready_fwd(vs, f)) {
+        // tensor cores blend (v_posed), then the row kernel skins with the joint transforms resident in shared memory;
+        // without a v_posed buffer (inference) the blend goes to f->verts and is skinned in place
+        float* vp = f->vposed ? f->vposed : f->verts;
+        rc = bf_blend_forward_tc(m, vs, f, vp, (cudaStream_t)stream); if (rc) return rc;
+        return bf_launch_skin_rows(0, vs, m->J, f->A, vp, f->verts, nullptr, nullptr, f->B, f->ld_v, 0,
+                                   (f->flags & BF_F_WORLD) ? f->theta : nullptr, m->NP, f->constant_scale, (cudaStream_t)stream);
+    }
     const dim3 grid(vs->n_pad / SK_TV, (f->B + SK_TB - 1) / SK_TB), block(256);
     k_skin_fwd<<<grid, block, 0, (cudaStream_t)stream>>>(*vs, m->J, m->Kp, f->pf, f->A, f->verts, f->vposed, f->B, f->ld_v,
                                                            (f->flags & BF_F_WORLD) ? f->theta : nullptr, m->NP, f->constant_scale);
@@ -93,7 +100,7 @@ int bf_blend_forward(const BfModel* m, const BfFrames* f, int use_full, void* st
     rc = check_vset(vs, f); if (rc) return rc;
     BF_REQUIRE(f->vposed, "vposed is null");
     BF_REQUIRE((f->flags & BF_F_TC) && vs->Bt_hi && vs->Bt_lo && f->pf_hi && f->pf_lo, "bf_blend_forward needs the tensor-core operands (BF_F_TC)");
-    return bf_skin_forward_tc(m, vs, f, (cudaStream_t)stream, true);
+    return bf_blend_forward_tc(m, vs, f, f->vposed, (cudaStream_t)stream);
 }
 
 int bf_joints_forward(const BfModel* m, const BfFrames* f, int use_full, void* stream) {
@@ -137,9 +144,14 @@ int bf_skin_backward_parts(const BfModel* m, const BfFrames* f, int use_full, in
     BF_REQUIRE(f->dverts && f->dvp && f->vposed && f->dA && f->dpf && f->A, "backward buffers missing");
     BF_REQUIRE(vs->jv_ptr && vs->jv_vid && vs->jv_w, "joint->vertex lists missing");
     cudaStream_t s = (cudaStream_t)stream;
-    if (parts & 1) {
+    if ((parts & 1) && bf_tc_ready_bwd(vs, f)) {
+        // tensor-core mode: only the 3xTF32 split of dvp is consumed (by the blend backward GEMM)
+        rc = bf_launch_skin_rows(1, vs, m->J, f->A, f->dverts, nullptr, f->dvp_hi, f->dvp_lo, f->B, f->ld_v, vs->ldn,
+                                 nullptr, m->NP, 0.f, s);
+        if (rc) return rc;
+    } else if (parts & 1) {
         const dim3 grid((vs->n + 255) / 256, (f->B + DV_FB - 1) / DV_FB);
-        const bool tcb = bf_tc_ready_bwd(vs, f);
+        const bool tcb = false;
         k_skin_bwd_dvp<<<grid, 256, 0, s>>>(*vs, m->J, f->A, f->dverts, f->dvp, f->B, f->ld_v,
                                            tcb ? f->dvp_hi : nullptr, tcb ? f->dvp_lo : nullptr);
         BF_LAUNCH_CHECK();
@@ -445,6 +457,22 @@ int bf_grid_nearest(const BfGrid* g, const float* points, int Q, float* near_pts
     int rc = check_grid(g); if (rc) return rc;
     BF_REQUIRE(g->cell_tris && points && near_pts && near_faces && Q > 0, "bad arguments");
     k_grid_nearest<<<(Q + 7) / 8, 256, 0, (cudaStream_t)stream>>>(*g, points, Q, near_pts, near_faces, dist2);
+    BF_LAUNCH_CHECK();
+    return BF_OK;
+}
+
+int bf_grid_inside(const BfGrid* g, const float* points, int Q, float* signs, void* stream) {
+    int rc = check_grid(g); if (rc) return rc;
+    BF_REQUIRE(g->cell_tris && points && signs && Q > 0, "bad arguments");
+    k_grid_inside<<<(Q + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*g, points, Q, signs);
+    BF_LAUNCH_CHECK();
+    return BF_OK;
+}
+
+int bf_grid_intersects_any(const BfGrid* g, const float* origins, const float* directions, int Q, uint8_t* hit, void* stream) {
+    int rc = check_grid(g); if (rc) return rc;
+    BF_REQUIRE(g->cell_tris && origins && directions && hit && Q > 0, "bad arguments");
+    k_grid_ray_any<<<(Q + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*g, origins, directions, Q, hit);
     BF_LAUNCH_CHECK();
     return BF_OK;
 }

@@ -1,16 +1,20 @@
 // Tensor-core path of the blend-shape contraction (the only GEMM-shaped work of the fit):
 //
-//   k_skin_fwd_tc  : v_posed tile [128 frames x 192 coords] = pf @ Bm on tcgen05 (kind::tf32,
+//   k_blend_fwd_tc : v_posed tile [128 frames x 192 coords] = pf @ Bm on tcgen05 (kind::tf32,
 //                    3xTF32 split: hi*hi + lo*hi + hi*lo, fp32 accumulate in TMEM), operands
-//                    staged by TMA (SWIZZLE_128B, K-major) through a 2-stage mbarrier pipeline,
-//                    accumulator read back with tcgen05.ld and skinned in the epilogue
-//                    (sum_k w_k A[b, j_k]) [v_posed; 1] without ever writing v_posed to HBM
-//                    unless the backward needs it.
+//                    staged by TMA (swizzled, K-major) through a 4-stage mbarrier pipeline,
+//                    persistent CTAs with two TMEM accumulators (MMA of tile i+1 overlaps the
+//                    read-out of tile i), accumulator read back with tcgen05.ld and written as
+//                    row-contiguous v_posed.  Skinning is NOT done here: it gathers 192 B of joint
+//                    transforms per vertex and frame, which bound a fused epilogue at ~37 us per
+//                    tile whatever the GEMM depth (L2 gather); the fit's per-frame kernel skins its
+//                    live vertices from shared memory instead (bf_frame.cuh) and the all-vertex
+//                    operator uses k_skin_rows (bf_skin.cuh, transforms resident in shared memory).
 //   k_blend_bwd_tc : dpf tile [128 frames x <=256 k] = dvp @ Bm^T, same machinery, reduction over
 //                    the vertex coordinates.
 //
-// Warp roles (192 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA
-// issuer (one lane), warps 2..5 = epilogue (TMEM lane quarter = warp_idx % 4).
+// Warp roles: warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA issuer (one lane),
+// warps 2.. = epilogue (TMEM lane quarter = warp_idx % 4).
 //
 // Why 3xTF32: single TF32 (10-bit mantissa) leaves ~5e-4 relative error on the blend-shape
 // offsets, i.e. ~1e-5 of the vertex magnitude -- at the north-star tolerance (1e-5 relative on
@@ -154,19 +158,24 @@ __device__ __forceinline__ void mma_issuer(const Pipe& p, int num_k, uint32_t tm
 
 }  // namespace tc
 
-// Persistent: one CTA per SM walks the (frame tile, vertex tile) list (vertex tile fastest, so that CTAs running
-// together share the same pf rows in L2).  Two TMEM accumulators: the MMA warp fills buffer (i+1)&1 while the eight
-// epilogue warps skin buffer i&1.
-//
-// Epilogue mapping: LANE = FRAME, which is the accumulator's own TMEM layout (lane = row of D), so v_posed comes
-// out of tcgen05.ld already where it is needed.  The skinning influences (joint, weight) of a vertex are then
-// warp-uniform, and the joint transforms are read from the frame-minor copy AT[(j*3 + r)][b] (float4 rows): one
-// LDG.128 of the warp covers 32 consecutive frames of the same joint row = 512 contiguous bytes = the minimum of
-// four L1 wavefronts, whatever the joint pattern of the model (the frame-major A[b][j] gather costs one wavefront
-// per distinct cache line: ~22 per load on a model with scattered influences, measured as the limiter before).
-// Skinned vertices are transposed through a small per-warp shared tile so that the global stores are row-contiguous.
-// Warps 2..9: TMEM lane quarter q = warp % 4, vertex half h = (warp - 2) / 4 of the 64-vertex tile, two passes of
-// 16 vertices (48 accumulator columns) each.
+// Persistent: one CTA per SM walks the (frame tile, vertex tile) list.  Two TMEM accumulators: the MMA warp fills
+// buffer (i+1)&1 while the eight epilogue warps drain buffer i&1.  Epilogue warps 2..9: TMEM lane quarter
+// q = warp % 4 (lane = frame row of the tile), vertex half h = (warp - 2) / 4 of the 64-vertex tile, two passes of
+// 16 vertices (48 accumulator columns), transposed through a per-warp shared tile so that the global stores are
+// row-contiguous (192 B per frame row).
+#define TC_BAND 64         // frame tiles per band of the tile order
+// Tile order: bands of TC_BAND frame tiles; inside a band the frame tile runs fastest, then the vertex tile.  The CTAs
+// that run together then share a few model-matrix tiles (each read from DRAM once per band and re-used from L2 by the
+// whole band) while the band's pose-feature rows (<= 64 x 128 frames x Kp x 8 B = 33 MB at Kp = 512) stay L2-resident.
+// (Vertex-tile-fastest order streamed the whole 128 MB SMPL-X model matrix once per frame tile: 4 GB of DRAM reads
+// for a 10,000-frame all-vertex forward.)
+__device__ __forceinline__ void tc_tile_coords(int t, int tm, int tn, int& fm, int& vn) {
+    const int per_band = TC_BAND * tn;
+    const int band = t / per_band, rem = t - band * per_band;
+    const int bs = min(TC_BAND, tm - band * TC_BAND);
+    vn = rem / bs;
+    fm = band * TC_BAND + (rem - vn * bs);
+}
 #define TC_EPI_WARPS 8
 #define TC_ST_LD 33        // row stride (floats) of the per-warp [48 coords][32 frames] staging tile
 #define TC_ST_FLOATS (48 * TC_ST_LD)
@@ -204,11 +213,9 @@ __device__ __forceinline__ void store_rows48(const float* st, float* __restrict_
 }  // namespace tc
 
 __global__ void __launch_bounds__(64 + 32 * TC_EPI_WARPS, 1)
-k_skin_fwd_tc(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CUtensorMap mA_lo,
-              const __grid_constant__ CUtensorMap mB_hi, const __grid_constant__ CUtensorMap mB_lo,
-              BfVSet vs, int J, int Kp, const float4* __restrict__ AT, float* __restrict__ verts,
-              float* __restrict__ vposed, int B, int ld_v, const float* __restrict__ theta, int NP, float cs,
-              int n_tiles_n, int n_tiles) {
+k_blend_fwd_tc(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CUtensorMap mA_lo,
+               const __grid_constant__ CUtensorMap mB_hi, const __grid_constant__ CUtensorMap mB_lo,
+               int n_verts, int Kp, float* __restrict__ vposed, int B, int ld_v, int n_tiles_m, int n_tiles_n, int n_tiles) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     tc::Pipe p;
@@ -242,7 +249,9 @@ k_skin_fwd_tc(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__
         if (lane == 0) {
             int it = 0;                                              // running K-chunk counter across tiles
             for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-                const int b0 = (t / n_tiles_n) * TC_BM, n0 = (t % n_tiles_n) * TC_BN1;
+                int fm, vn;
+                tc_tile_coords(t, n_tiles_m, n_tiles_n, fm, vn);
+                const int b0 = fm * TC_BM, n0 = vn * TC_BN1;
                 for (int kc = 0; kc < num_k; ++kc, ++it) {
                     const int s = it % TC_STAGES;
                     const uint32_t ph = (it / TC_STAGES) & 1;
@@ -289,24 +298,16 @@ k_skin_fwd_tc(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__
         const int q = warp & 3;                               // TMEM lane quarter this warp may read
         const int h = (warp - 2) >> 2;                        // which 32 vertices of the 64-vertex tile
         float* st = St + (warp - 2) * TC_ST_FLOATS;
-        const int nnz = vs.nnz;
-        const size_t Bz = (size_t)B;
         int i = 0;
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
             const int buf = i & 1;
-            const int b0 = (t / n_tiles_n) * TC_BM + 32 * q, n0 = (t % n_tiles_n) * TC_BN1;
-            const int b = b0 + lane;
-            const int bl = b < B ? b : B - 1;                 // rows past the batch compute on a valid frame, never stored
+            int fm, vn;
+            tc_tile_coords(t, n_tiles_m, n_tiles_n, fm, vn);
+            const int b0 = fm * TC_BM + 32 * q, n0 = vn * TC_BN1;
             const int nrows = min(32, B - b0);
-            float t0 = 0.f, t1 = 0.f, t2 = 0.f, sc = 1.f;
-            if (theta) {                                      // world = (x + transl) * scale * cs (smplify.py:190)
-                const float* th = theta + (size_t)bl * NP;
-                t0 = __ldg(th); t1 = __ldg(th + 1); t2 = __ldg(th + 2); sc = __ldg(th + 3);
-            }
             tc::mbar_wait(&p.tmem_full[buf], (i >> 1) & 1);
             tc::tc_fence_after();
             const uint32_t tmem_d = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * TC_BN1 + h * 96);
-            const float4* ATb = AT + bl;
 #pragma unroll 1
             for (int pass = 0; pass < 2; ++pass) {
                 uint32_t r[48];
@@ -317,69 +318,11 @@ k_skin_fwd_tc(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__
                     if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(&tmem_empty[buf])) : "memory");
                 }
                 const int vbase = n0 / 3 + h * 32 + pass * 16;
-                if (vbase >= vs.n) continue;                  // warp-uniform: pad vertices of the last tile
-                if (AT == nullptr) {                          // blend only: v_posed rows (the per-frame kernel skins what it needs)
+                if (vbase >= n_verts || nrows <= 0) continue; // warp-uniform: pad vertices / pad frames of the last tiles
 #pragma unroll
-                    for (int c = 0; c < 48; ++c) st[c * TC_ST_LD + lane] = __uint_as_float(r[c]);
-                    __syncwarp();
-                    tc::store_rows48(st, vposed + (size_t)b0 * ld_v + 3 * vbase, (size_t)ld_v, 3 * min(16, vs.n - vbase), nrows, lane);
-                    __syncwarp();
-                    continue;
-                }
-#pragma unroll
-                for (int vi = 0; vi < 16; ++vi) {
-                    const int v = min(vbase + vi, vs.n - 1);  // warp-uniform (clamped pad vertices are not stored)
-                    const float px = __uint_as_float(r[3 * vi]), py = __uint_as_float(r[3 * vi + 1]), pz = __uint_as_float(r[3 * vi + 2]);
-                    float T[12];
-#pragma unroll
-                    for (int e = 0; e < 12; ++e) T[e] = 0.f;
-                    const int32_t* ej = vs.ell_j + (size_t)v * nnz;
-                    const float* ew = vs.ell_w + (size_t)v * nnz;
-                    int jo[4]; float jw[4];
-                    if (nnz == 4) {                           // SMPL / SMPL-X: one 16-byte uniform load each
-                        const int4 j4 = __ldg(reinterpret_cast<const int4*>(ej));
-                        const float4 w4 = __ldg(reinterpret_cast<const float4*>(ew));
-                        jo[0] = j4.x; jo[1] = j4.y; jo[2] = j4.z; jo[3] = j4.w;
-                        jw[0] = w4.x; jw[1] = w4.y; jw[2] = w4.z; jw[3] = w4.w;
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) { jo[k] = (k < nnz) ? __ldg(ej + k) : 0; jw[k] = (k < nnz) ? __ldg(ew + k) : 0.f; }
-                    }
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const float w = jw[k];
-                        const float4* Aj = ATb + (size_t)(jo[k] * 3) * Bz;
-                        const float4 r0 = __ldg(Aj), r1 = __ldg(Aj + Bz), r2 = __ldg(Aj + 2 * Bz);
-                        T[0] = fmaf(w, r0.x, T[0]); T[1] = fmaf(w, r0.y, T[1]); T[2] = fmaf(w, r0.z, T[2]); T[3] = fmaf(w, r0.w, T[3]);
-                        T[4] = fmaf(w, r1.x, T[4]); T[5] = fmaf(w, r1.y, T[5]); T[6] = fmaf(w, r1.z, T[6]); T[7] = fmaf(w, r1.w, T[7]);
-                        T[8] = fmaf(w, r2.x, T[8]); T[9] = fmaf(w, r2.y, T[9]); T[10] = fmaf(w, r2.z, T[10]); T[11] = fmaf(w, r2.w, T[11]);
-                    }
-                    for (int k = 4; k < nnz; ++k) {
-                        const float w = __ldg(ew + k);
-                        const float4* Aj = ATb + (size_t)(__ldg(ej + k) * 3) * Bz;
-                        const float4 r0 = __ldg(Aj), r1 = __ldg(Aj + Bz), r2 = __ldg(Aj + 2 * Bz);
-                        T[0] = fmaf(w, r0.x, T[0]); T[1] = fmaf(w, r0.y, T[1]); T[2] = fmaf(w, r0.z, T[2]); T[3] = fmaf(w, r0.w, T[3]);
-                        T[4] = fmaf(w, r1.x, T[4]); T[5] = fmaf(w, r1.y, T[5]); T[6] = fmaf(w, r1.z, T[6]); T[7] = fmaf(w, r1.w, T[7]);
-                        T[8] = fmaf(w, r2.x, T[8]); T[9] = fmaf(w, r2.y, T[9]); T[10] = fmaf(w, r2.z, T[10]); T[11] = fmaf(w, r2.w, T[11]);
-                    }
-                    float ox = T[0] * px + T[1] * py + T[2] * pz + T[3];
-                    float oy = T[4] * px + T[5] * py + T[6] * pz + T[7];
-                    float oz = T[8] * px + T[9] * py + T[10] * pz + T[11];
-                    if (theta) { ox = (ox + t0) * sc * cs; oy = (oy + t1) * sc * cs; oz = (oz + t2) * sc * cs; }
-                    st[(3 * vi) * TC_ST_LD + lane] = ox;
-                    st[(3 * vi + 1) * TC_ST_LD + lane] = oy;
-                    st[(3 * vi + 2) * TC_ST_LD + lane] = oz;
-                }
+                for (int c = 0; c < 48; ++c) st[c * TC_ST_LD + lane] = __uint_as_float(r[c]);
                 __syncwarp();
-                const int ncols = 3 * min(16, vs.n - vbase);
-                tc::store_rows48(st, verts + (size_t)b0 * ld_v + 3 * vbase, (size_t)ld_v, ncols, nrows, lane);
-                if (vposed) {
-                    __syncwarp();
-#pragma unroll
-                    for (int c = 0; c < 48; ++c) st[c * TC_ST_LD + lane] = __uint_as_float(r[c]);
-                    __syncwarp();
-                    tc::store_rows48(st, vposed + (size_t)b0 * ld_v + 3 * vbase, (size_t)ld_v, ncols, nrows, lane);
-                }
+                tc::store_rows48(st, vposed + (size_t)b0 * ld_v + 3 * vbase, (size_t)ld_v, 3 * min(16, n_verts - vbase), nrows, lane);
                 __syncwarp();
             }
         }
@@ -509,14 +452,14 @@ static int bf_make_map(CUtensorMap* m, const float* base, uint64_t rows, uint64_
 }
 
 static inline bool bf_tc_ready_fwd(const BfVSet* vs, const BfFrames* f) {
-    return (f->flags & BF_F_TC) && vs->Bt_hi && vs->Bt_lo && f->pf_hi && f->pf_lo && f->A_T;
+    return (f->flags & BF_F_TC) && vs->Bt_hi && vs->Bt_lo && f->pf_hi && f->pf_lo;
 }
 static inline bool bf_tc_ready_bwd(const BfVSet* vs, const BfFrames* f) {
     return (f->flags & BF_F_TC) && vs->Bm_hi && vs->Bm_lo && f->dvp_hi && f->dvp_lo;
 }
 
-// blend_only: write v_posed only (no skinning, f->verts untouched)
-static int bf_skin_forward_tc(const BfModel* m, const BfVSet* vs, const BfFrames* f, cudaStream_t s, bool blend_only = false) {
+// v_posed[B, ld_v] = pf @ Bm on the tensor cores (dst = f->vposed, or any [B, ld_v] buffer)
+static int bf_blend_forward_tc(const BfModel* m, const BfVSet* vs, const BfFrames* f, float* dst, cudaStream_t s) {
     CUtensorMap a_hi, a_lo, b_hi, b_lo;
     int rc;
     if ((rc = bf_make_map(&a_hi, f->pf_hi, f->B, m->Kp, m->Kp, TC_BM))) return rc;
@@ -527,8 +470,8 @@ static int bf_skin_forward_tc(const BfModel* m, const BfVSet* vs, const BfFrames
     static bool attr = false;
     static int num_sms = 0;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(k_skin_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) { bf_set_error("cudaFuncSetAttribute(k_skin_fwd_tc): %s", cudaGetErrorString(e)); return BF_ECUDA; }
+        cudaError_t e = cudaFuncSetAttribute(k_blend_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { bf_set_error("cudaFuncSetAttribute(k_blend_fwd_tc): %s", cudaGetErrorString(e)); return BF_ECUDA; }
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -537,9 +480,7 @@ static int bf_skin_forward_tc(const BfModel* m, const BfVSet* vs, const BfFrames
     const int tn = (vs->ldn + TC_BN1 - 1) / TC_BN1, tm = (f->B + TC_BM - 1) / TC_BM;
     const int tiles = tn * tm;
     const int grid = tiles < num_sms ? tiles : num_sms;          // persistent: one CTA per SM
-    k_skin_fwd_tc<<<grid, 64 + 32 * TC_EPI_WARPS, smem, s>>>(a_hi, a_lo, b_hi, b_lo, *vs, m->J, m->Kp,
-                                          blend_only ? nullptr : reinterpret_cast<const float4*>(f->A_T), f->verts, f->vposed, f->B, f->ld_v,
-                                          (f->flags & BF_F_WORLD) ? f->theta : nullptr, m->NP, f->constant_scale, tn, tiles);
+    k_blend_fwd_tc<<<grid, 64 + 32 * TC_EPI_WARPS, smem, s>>>(a_hi, a_lo, b_hi, b_lo, vs->n, m->Kp, dst, f->B, f->ld_v, tm, tn, tiles);
     BF_LAUNCH_CHECK();
     return BF_OK;
 }

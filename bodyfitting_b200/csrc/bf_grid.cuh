@@ -389,3 +389,131 @@ __global__ void k_add3(const float* __restrict__ a, const float* __restrict__ b,
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) o[i] = a[i] + b[i];
 }
+
+// ---- inside / ray queries on the same grid (utils/mesh_grid_searcher.py:86-99) ----------------------------
+// 2-D orientation of p against the directed edge a -> b in the plane (u, w); the edge is evaluated in a canonical
+// direction (lower vertex id first) so that the two triangles sharing it see exactly the same number -> no ray
+// can slip between them or be counted twice (watertight crossing parity).
+__device__ __forceinline__ float edge_fn(const float* va, const float* vb, int ia, int ib, float pu, float pw, int u, int w) {
+    const bool sw = ia > ib;
+    const float* a = sw ? vb : va;
+    const float* b = sw ? va : vb;
+    const float e = (b[u] - a[u]) * (pw - a[w]) - (b[w] - a[w]) * (pu - a[u]);
+    return sw ? -e : e;
+}
+
+// Inside test by crossing parity along an axis ray (the reference marches the same kind of ray through its grid and
+// counts distinct triangles, mesh_grid_kernel.cu:568-650): the axis / direction with the fewest cells to the grid
+// border is taken, every triangle listed in the cells on the way is tested in the projection plane, and a crossing
+// is charged to the ONE cell that contains it (so a triangle listed in several cells of the column is counted once;
+// the reference keeps a 16-entry visited list instead).  +1 inside, -1 outside (also outside the grid box).
+__global__ void __launch_bounds__(128) k_grid_inside(BfGrid g, const float* __restrict__ points, int Q, float* __restrict__ signs) {
+    const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= Q) return;
+    const float p[3] = {points[3 * qi], points[3 * qi + 1], points[3 * qi + 2]};
+    int c[3];
+    int best_d = 0, best_n = 0x7fffffff;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const float x = (p[d] - g.min[d]) / g.step;
+        if (!(x >= 0.f) || x >= (float)g.dim[d]) { signs[qi] = -1.0f; return; }
+        c[d] = (int)x;
+        if (c[d] < best_n) { best_n = c[d]; best_d = 2 * d; }                                  // towards the lower border
+        if (g.dim[d] - 1 - c[d] < best_n) { best_n = g.dim[d] - 1 - c[d]; best_d = 2 * d + 1; } // towards the upper border
+    }
+    const int ax = best_d >> 1, u = (ax + 1) % 3, w = (ax + 2) % 3;
+    const int dir = (best_d & 1) ? 1 : -1;
+    int crossings = 0;
+    int cc[3] = {c[0], c[1], c[2]};
+    for (int s = 0; s <= best_n; ++s, cc[ax] += dir) {
+        const int cell = (cc[0] * g.dim[1] + cc[1]) * g.dim[2] + cc[2];
+        const int e0 = __ldg(g.cell_start + cell), e1 = __ldg(g.cell_start + cell + 1);
+        for (int i = e0; i < e1; ++i) {
+            const int f = __ldg(g.cell_tris + i);
+            const int ia = __ldg(g.faces + 3 * f), ib = __ldg(g.faces + 3 * f + 1), ic = __ldg(g.faces + 3 * f + 2);
+            const float* a = g.verts + 3 * ia;
+            const float* b = g.verts + 3 * ib;
+            const float* cv = g.verts + 3 * ic;
+            const float e_ab = edge_fn(a, b, ia, ib, p[u], p[w], u, w);
+            const float e_bc = edge_fn(b, cv, ib, ic, p[u], p[w], u, w);
+            const float e_ca = edge_fn(cv, a, ic, ia, p[u], p[w], u, w);
+            // inside the projected triangle (either winding); an exactly-zero edge value belongs to the positive side
+            const bool pos = e_ab >= 0.f && e_bc >= 0.f && e_ca >= 0.f;
+            const bool neg = e_ab < 0.f && e_bc < 0.f && e_ca < 0.f;
+            if (!pos && !neg) continue;
+            const float area = e_ab + e_bc + e_ca;
+            if (area == 0.f) continue;                                         // degenerate in projection
+            // crossing coordinate along the axis (barycentric interpolation: weights e_bc -> a, e_ca -> b, e_ab -> c)
+            const float t = (e_bc * a[ax] + e_ca * b[ax] + e_ab * cv[ax]) / area;
+            if (dir > 0 ? !(t > p[ax]) : !(t < p[ax])) continue;
+            int ct = (int)floorf((t - g.min[ax]) / g.step);
+            ct = min(max(ct, 0), g.dim[ax] - 1);
+            if (dir > 0) ct = max(ct, c[ax]); else ct = min(ct, c[ax]);       // never before the query's own cell
+            if (ct == cc[ax]) ++crossings;
+        }
+    }
+    signs[qi] = (crossings & 1) ? 1.0f : -1.0f;
+}
+
+// Ray / triangle (Moeller-Trumbore), hit iff barycentrics >= -eps and t >= -eps (one-directional ray that includes
+// its origin, as mesh_grid_kernel.cu:742-781 with both_direction = false)
+__device__ __forceinline__ bool ray_hits_triangle(const float* o, const float* d, const float* a, const float* b, const float* c) {
+    const float e1[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]}, e2[3] = {c[0] - a[0], c[1] - a[1], c[2] - a[2]};
+    const float pv[3] = {d[1] * e2[2] - d[2] * e2[1], d[2] * e2[0] - d[0] * e2[2], d[0] * e2[1] - d[1] * e2[0]};
+    const float det = e1[0] * pv[0] + e1[1] * pv[1] + e1[2] * pv[2];
+    if (fabsf(det) <= 1e-20f) return false;                                   // parallel to the triangle's plane
+    const float inv = 1.0f / det;
+    const float tv[3] = {o[0] - a[0], o[1] - a[1], o[2] - a[2]};
+    const float bu = (tv[0] * pv[0] + tv[1] * pv[1] + tv[2] * pv[2]) * inv;
+    const float qv[3] = {tv[1] * e1[2] - tv[2] * e1[1], tv[2] * e1[0] - tv[0] * e1[2], tv[0] * e1[1] - tv[1] * e1[0]};
+    const float bv = (d[0] * qv[0] + d[1] * qv[1] + d[2] * qv[2]) * inv;
+    const float t = (e2[0] * qv[0] + e2[1] * qv[1] + e2[2] * qv[2]) * inv;
+    const float eps = 1e-6f;
+    return bu >= -eps && bv >= -eps && bu + bv <= 1.0f + eps && t >= -eps;
+}
+
+// intersects_any: 3-D DDA through the grid from the ray's entry point; the first cell holding a hit ends the walk
+__global__ void __launch_bounds__(128) k_grid_ray_any(BfGrid g, const float* __restrict__ origins, const float* __restrict__ dirs,
+                                                      int Q, uint8_t* __restrict__ hit) {
+    const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= Q) return;
+    const float o[3] = {origins[3 * qi], origins[3 * qi + 1], origins[3 * qi + 2]};
+    const float d[3] = {dirs[3 * qi], dirs[3 * qi + 1], dirs[3 * qi + 2]};
+    hit[qi] = 0;
+    if (d[0] * d[0] + d[1] * d[1] + d[2] * d[2] < 1e-9f) return;               // degenerate direction (:1052-1055)
+    // clip the ray to the grid box: t in [t0, t1]
+    float t0 = 0.f, t1 = 3.0e38f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float lo = g.min[k], hi = g.min[k] + g.step * (float)g.dim[k];
+        if (d[k] == 0.f) { if (o[k] < lo || o[k] > hi) return; continue; }
+        const float inv = 1.0f / d[k];
+        float ta = (lo - o[k]) * inv, tb = (hi - o[k]) * inv;
+        if (ta > tb) { const float s = ta; ta = tb; tb = s; }
+        t0 = fmaxf(t0, ta); t1 = fminf(t1, tb);
+    }
+    if (t0 > t1) return;
+    int c[3], stp[3];
+    float tmax[3], tdel[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float x = (o[k] + t0 * d[k] - g.min[k]) / g.step;
+        c[k] = min(max((int)floorf(x), 0), g.dim[k] - 1);
+        if (d[k] > 0.f) { stp[k] = 1; tdel[k] = g.step / d[k]; tmax[k] = (g.min[k] + g.step * (float)(c[k] + 1) - o[k]) / d[k]; }
+        else if (d[k] < 0.f) { stp[k] = -1; tdel[k] = -g.step / d[k]; tmax[k] = (g.min[k] + g.step * (float)c[k] - o[k]) / d[k]; }
+        else { stp[k] = 0; tdel[k] = 3.0e38f; tmax[k] = 3.0e38f; }
+    }
+    for (int guard = g.dim[0] + g.dim[1] + g.dim[2] + 3; guard > 0; --guard) {
+        const int cell = (c[0] * g.dim[1] + c[1]) * g.dim[2] + c[2];
+        const int e0 = __ldg(g.cell_start + cell), e1 = __ldg(g.cell_start + cell + 1);
+        for (int i = e0; i < e1; ++i) {
+            const int f = __ldg(g.cell_tris + i);
+            if (ray_hits_triangle(o, d, g.verts + 3 * __ldg(g.faces + 3 * f), g.verts + 3 * __ldg(g.faces + 3 * f + 1),
+                                  g.verts + 3 * __ldg(g.faces + 3 * f + 2))) { hit[qi] = 1; return; }
+        }
+        const int k = tmax[0] <= tmax[1] ? (tmax[0] <= tmax[2] ? 0 : 2) : (tmax[1] <= tmax[2] ? 1 : 2);
+        c[k] += stp[k];
+        if (stp[k] == 0 || c[k] < 0 || c[k] >= g.dim[k]) return;
+        tmax[k] += tdel[k];
+    }
+}

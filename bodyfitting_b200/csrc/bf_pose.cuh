@@ -20,14 +20,14 @@ struct PoseSmem {
     float GR[BF_MAXJ * 9];
     float Gt[BF_MAXJ * 3];
 };
+// Backward scratch.  Three more per-joint arrays live in forward slots that are dead by then (smaller footprint ->
+// five CTAs of four frames per SM instead of four): d(rel) in f.Gt (the backward never reads the posed joints), d(full
+// pose) in f.fp (each lane overwrites exactly the three angles it has just consumed) and the updated theta in f.th.
 struct PoseSmemBwd {
     PoseSmem f;
     float dGR[BF_MAXJ * 9];
     float dGt[BF_MAXJ * 3];
     float dJr[BF_MAXJ * 3];
-    float drel[BF_MAXJ * 3];
-    float dfp[BF_MAXJ * 3];
-    float thn[BF_MAXNP];
 };
 
 // Fills S for frame b (all lanes of one warp participate).
@@ -137,7 +137,6 @@ __device__ __forceinline__ void pose_write_outputs(const BfModel& m, const BfFra
         }
     }
     // A_j = [GR_j | Gt_j - GR_j Jr_j],  posed joints = Gt
-    float4* At = reinterpret_cast<float4*>(f.A_T);     // frame-minor copy for the lane = frame skinning epilogue (bf_blend_tc.cuh)
     for (int j = lane; j < J; j += 32) {
         float4* Aj = reinterpret_cast<float4*>(f.A + ((size_t)b * J + j) * 12);
 #pragma unroll
@@ -145,7 +144,6 @@ __device__ __forceinline__ void pose_write_outputs(const BfModel& m, const BfFra
             const float g0 = S.GR[j * 9 + r * 3], g1 = S.GR[j * 9 + r * 3 + 1], g2 = S.GR[j * 9 + r * 3 + 2];
             const float4 row = make_float4(g0, g1, g2, S.Gt[j * 3 + r] - (g0 * S.Jr[j * 3] + g1 * S.Jr[j * 3 + 1] + g2 * S.Jr[j * 3 + 2]));
             Aj[r] = row;
-            if (At) At[(size_t)(j * 3 + r) * f.B + b] = row;
             f.Jtr[((size_t)b * J + j) * 3 + r] = S.Gt[j * 3 + r];
         }
     }
@@ -200,6 +198,8 @@ __global__ void __launch_bounds__(128) k_pose_bwd(BfModel m, BfFrames f, int fla
     if (b >= f.B) return;
     PoseSmemBwd& W = all[warp];
     PoseSmem& S = W.f;
+    float* const drel = S.Gt;
+    float* const dfp = S.fp;
     const int J = m.J;
     const ThetaLayout L = theta_layout(m.is_smplx);
     if (f.fwd_state) {                       // forward state saved by the pose forward of this iteration
@@ -235,22 +235,33 @@ __global__ void __launch_bounds__(128) k_pose_bwd(BfModel m, BfFrames f, int fla
         for (int j = lane; j < J; j += 32) {
             if (__ldg(m.depth + j) != lev) continue;
             const int c0 = __ldg(m.child_ptr + j), c1 = __ldg(m.child_ptr + j + 1);
+            if (c0 == c1) continue;
+            float aR[9], aT[3], pj[3];                 // the parent's sums stay in registers across its children
+#pragma unroll
+            for (int e = 0; e < 9; ++e) aR[e] = W.dGR[j * 9 + e];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { aT[c] = W.dGt[j * 3 + c]; pj[c] = S.Jr[j * 3 + c]; }
             for (int q = c0; q < c1; ++q) {
                 const int ch = __ldg(m.child_idx + q);
-                float rel[3];
+                float rel[3], Rc[9];
 #pragma unroll
-                for (int c = 0; c < 3; ++c) rel[c] = S.Jr[ch * 3 + c] - S.Jr[j * 3 + c];
+                for (int c = 0; c < 3; ++c) rel[c] = S.Jr[ch * 3 + c] - pj[c];
+#pragma unroll
+                for (int e = 0; e < 9; ++e) Rc[e] = S.R[ch * 9 + e];
 #pragma unroll
                 for (int r = 0; r < 3; ++r) {
                     const float g0 = W.dGR[ch * 9 + r * 3], g1 = W.dGR[ch * 9 + r * 3 + 1], g2 = W.dGR[ch * 9 + r * 3 + 2];
                     const float gt = W.dGt[ch * 3 + r];
 #pragma unroll
                     for (int c = 0; c < 3; ++c)   // dGR_p += dGR_c R_c^T + dGt_c (x) rel_c
-                        W.dGR[j * 9 + r * 3 + c] += g0 * S.R[ch * 9 + c * 3] + g1 * S.R[ch * 9 + c * 3 + 1] +
-                                                    g2 * S.R[ch * 9 + c * 3 + 2] + gt * rel[c];
-                    W.dGt[j * 3 + r] += gt;
+                        aR[r * 3 + c] += g0 * Rc[c * 3] + g1 * Rc[c * 3 + 1] + g2 * Rc[c * 3 + 2] + gt * rel[c];
+                    aT[r] += gt;
                 }
             }
+#pragma unroll
+            for (int e = 0; e < 9; ++e) W.dGR[j * 9 + e] = aR[e];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) W.dGt[j * 3 + c] = aT[c];
         }
         __syncwarp();
     }
@@ -279,20 +290,20 @@ __global__ void __launch_bounds__(128) k_pose_bwd(BfModel m, BfFrames f, int fla
             for (int e = 0; e < 9; ++e) dR[e] += dpf[e];
         }
 #pragma unroll
-        for (int c = 0; c < 3; ++c) W.drel[j * 3 + c] = dr[c];
+        for (int c = 0; c < 3; ++c) drel[j * 3 + c] = dr[c];
         float g[3];
         rodrigues_bwd(S.fp[3 * j], S.fp[3 * j + 1], S.fp[3 * j + 2], dR, g);
 #pragma unroll
-        for (int c = 0; c < 3; ++c) W.dfp[j * 3 + c] = g[c];
+        for (int c = 0; c < 3; ++c) dfp[j * 3 + c] = g[c];
     }
     __syncwarp();
     for (int j = lane; j < J; j += 32) {
-        float acc[3] = {W.drel[j * 3], W.drel[j * 3 + 1], W.drel[j * 3 + 2]};
+        float acc[3] = {drel[j * 3], drel[j * 3 + 1], drel[j * 3 + 2]};
         const int c0 = __ldg(m.child_ptr + j), c1 = __ldg(m.child_ptr + j + 1);
         for (int q = c0; q < c1; ++q) {
             const int ch = __ldg(m.child_idx + q);
 #pragma unroll
-            for (int c = 0; c < 3; ++c) acc[c] -= W.drel[ch * 3 + c];
+            for (int c = 0; c < 3; ++c) acc[c] -= drel[ch * 3 + c];
         }
 #pragma unroll
         for (int c = 0; c < 3; ++c) W.dJr[j * 3 + c] += acc[c];
@@ -312,13 +323,13 @@ __global__ void __launch_bounds__(128) k_pose_bwd(BfModel m, BfFrames f, int fla
         const float a2 = __shfl_sync(0xffffffffu, acc, (lane + 2 * m.NB) & 31);
         if (lane < m.NB) g[L.off_betas + lane] = f.dpf[(size_t)b * m.Kp + m.P + lane] + ((acc + a1) + a2);
     }
-    for (int i = lane; i < 3 + L.nbody; i += 32) g[4 + i] = W.dfp[i];      // global_orient + body_pose
+    for (int i = lane; i < 3 + L.nbody; i += 32) g[4 + i] = dfp[i];      // global_orient + body_pose
     if (m.is_smplx) {
-        if (lane < 3) { g[L.off_leye + lane] = W.dfp[69 + lane]; g[L.off_reye + lane] = W.dfp[72 + lane]; }
+        if (lane < 3) { g[L.off_leye + lane] = dfp[69 + lane]; g[L.off_reye + lane] = dfp[72 + lane]; }
         if (lane < 12) {
             const int c = lane % 6;
             const float* comp = (lane < 6 ? m.hand_l : m.hand_r) + c * 45;
-            const float* d = W.dfp + (lane < 6 ? 75 : 120);
+            const float* d = dfp + (lane < 6 ? 75 : 120);
             float acc = 0.f;
             for (int i = 0; i < 45; ++i) acc += __ldg(comp + i) * d[i];
             g[(lane < 6 ? L.off_lh : L.off_rh) + c] = acc;
@@ -387,11 +398,9 @@ __global__ void __launch_bounds__(128) k_pose_bwd(BfModel m, BfFrames f, int fla
             const float tn = S.th[i] + (-step) * mi / denom;
             th[i] = tn;
             am[i] = mi; av[i] = vi;
-            W.thn[i] = tn;
+            S.th[i] = tn;
         }
         if (flags & 8) {
-            __syncwarp();
-            for (int i = lane; i < m.NP; i += 32) S.th[i] = W.thn[i];
             __syncwarp();
             pose_forward_from_smem(m, S, lane);
             pose_write_outputs(m, f, S, b, lane);

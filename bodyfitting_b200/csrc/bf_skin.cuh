@@ -288,27 +288,33 @@ __global__ void __launch_bounds__(256) k_blend_bwd(BfVSet vs, int Kp, const floa
 // writes it.
 #define SR_WARPS 16
 #define SR_LD 33
+#define SR_TILE (48 * SR_LD + 128)     // per-warp floats: [48 coords][32 frames] tile + the chunk's ELL rows (16 x (4 joints | 4 weights))
+
+// MODE 0: forward  verts = T [v_posed; 1]  (optionally -> world space)
+// MODE 1: backward dvp   = T[:3,:3]^T dverts, written as the 3xTF32 split (out_hi / out_lo, row stride ld_out) and / or plain
+template <int MODE>
 __global__ void __launch_bounds__(32 * SR_WARPS, 1)
-k_skin_rows(BfVSet vs, int J, const float* __restrict__ A, const float* vposed, float* verts, int B, int ld_v,
-            const float* __restrict__ theta, int NP, float cs, int chunks_per_slab) {
+k_skin_rows(BfVSet vs, int J, const float* __restrict__ A, const float* in, float* out, float* out_hi, float* out_lo,
+            int B, int ld_v, int ld_out, const float* __restrict__ theta, int NP, float cs, int chunks_per_slab) {
     extern __shared__ __align__(16) float sm_sr[];
     float4* As = reinterpret_cast<float4*>(sm_sr);                          // [3J][32]
-    float* st = sm_sr + (size_t)3 * J * 32 * 4 + (threadIdx.x >> 5) * (48 * SR_LD);
+    float* st = sm_sr + (size_t)3 * J * 32 * 4 + (threadIdx.x >> 5) * SR_TILE;
+    float* ell = st + 48 * SR_LD;                                           // 16B-aligned: 48*33*4 = 6336 = 16 * 396
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b0 = blockIdx.x * 32;
     const int nrows = min(32, B - b0);
-    {   // A[b][j][r] (float4) -> As[j*3 + r][frame]; global reads are contiguous per frame
+    {   // A[b][j][r] (float4) -> As[j*3 + r][frame]: consecutive threads take consecutive frames (conflict-free stores)
         const float4* src = reinterpret_cast<const float4*>(A);
         const int n = 3 * J;
         for (int i = threadIdx.x; i < 32 * n; i += blockDim.x) {
-            const int fl = i / n, jr = i - fl * n;
+            const int jr = i >> 5, fl = i & 31;
             const int b = min(b0 + fl, B - 1);
-            As[jr * 32 + fl] = __ldg(src + (size_t)b * n + jr);
+            As[i] = __ldg(src + (size_t)b * n + jr);
         }
     }
     const int bl = min(b0 + lane, B - 1);
     float t0 = 0.f, t1 = 0.f, t2 = 0.f, sc = 1.f;
-    if (theta) {                                                            // world = (x + transl) * scale * cs
+    if (MODE == 0 && theta) {                                               // world = (x + transl) * scale * cs
         const float* th = theta + (size_t)bl * NP;
         t0 = __ldg(th); t1 = __ldg(th + 1); t2 = __ldg(th + 2); sc = __ldg(th + 3);
     }
@@ -319,10 +325,15 @@ k_skin_rows(BfVSet vs, int J, const float* __restrict__ A, const float* vposed, 
     for (int ch = blockIdx.y * chunks_per_slab + warp; ch < c_end; ch += SR_WARPS) {
         const int vbase = ch << 4;
         const int ncols = 3 * min(16, vs.n - vbase);
-        const float* src = vposed + (size_t)b0 * ld_v + 3 * vbase;
-        float* dst = verts + (size_t)b0 * ld_v + 3 * vbase;
+        const float* src = in + (size_t)b0 * ld_v + 3 * vbase;
+        if (nnz == 4) {                                                      // the chunk's influences -> shared (one 16-byte load per lane)
+            const int vi = lane & 15;
+            const int v = min(vbase + vi, vs.n - 1);
+            if (lane < 16) reinterpret_cast<int4*>(ell)[vi] = __ldg(reinterpret_cast<const int4*>(vs.ell_j) + v);
+            else reinterpret_cast<float4*>(ell)[16 + vi] = __ldg(reinterpret_cast<const float4*>(vs.ell_w) + v);
+        }
         // rows -> tile (2 rows x 48 coords per three warp-wide loads)
-#pragma unroll 4
+#pragma unroll 8
         for (int rp = 0; rp < 16; ++rp) {
 #pragma unroll
             for (int s = 0; s < 3; ++s) {
@@ -332,28 +343,54 @@ k_skin_rows(BfVSet vs, int J, const float* __restrict__ A, const float* vposed, 
             }
         }
         __syncwarp();
-#pragma unroll 4
+#pragma unroll 2
         for (int vi = 0; vi < 16; ++vi) {
-            const int v = min(vbase + vi, vs.n - 1);                         // warp-uniform; clamped pad vertices are not stored
-            const int32_t* ej = vs.ell_j + (size_t)v * nnz;
-            const float* ew = vs.ell_w + (size_t)v * nnz;
-            float T[12];
+            constexpr int NC = MODE == 0 ? 4 : 3;
+            float T[3 * NC];
 #pragma unroll
-            for (int e = 0; e < 12; ++e) T[e] = 0.f;
-            for (int k = 0; k < nnz; ++k) {
-                const float w = __ldg(ew + k);
-                const float4* Aj = As + (size_t)(__ldg(ej + k) * 3) * 32 + lane;
-                const float4 r0 = Aj[0], r1 = Aj[32], r2 = Aj[64];
-                T[0] = fmaf(w, r0.x, T[0]); T[1] = fmaf(w, r0.y, T[1]); T[2] = fmaf(w, r0.z, T[2]); T[3] = fmaf(w, r0.w, T[3]);
-                T[4] = fmaf(w, r1.x, T[4]); T[5] = fmaf(w, r1.y, T[5]); T[6] = fmaf(w, r1.z, T[6]); T[7] = fmaf(w, r1.w, T[7]);
-                T[8] = fmaf(w, r2.x, T[8]); T[9] = fmaf(w, r2.y, T[9]); T[10] = fmaf(w, r2.z, T[10]); T[11] = fmaf(w, r2.w, T[11]);
+            for (int e = 0; e < 3 * NC; ++e) T[e] = 0.f;
+            if (nnz == 4) {
+                const int4 j4 = reinterpret_cast<const int4*>(ell)[vi];
+                const float4 w4 = reinterpret_cast<const float4*>(ell)[16 + vi];
+                const int jj[4] = {j4.x, j4.y, j4.z, j4.w};
+                const float ww[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float w = ww[k];
+                    const float4* Aj = As + jj[k] * 96 + lane;
+                    const float4 r0 = Aj[0], r1 = Aj[32], r2 = Aj[64];
+                    T[0] = fmaf(w, r0.x, T[0]); T[1] = fmaf(w, r0.y, T[1]); T[2] = fmaf(w, r0.z, T[2]);
+                    T[NC] = fmaf(w, r1.x, T[NC]); T[NC + 1] = fmaf(w, r1.y, T[NC + 1]); T[NC + 2] = fmaf(w, r1.z, T[NC + 2]);
+                    T[2 * NC] = fmaf(w, r2.x, T[2 * NC]); T[2 * NC + 1] = fmaf(w, r2.y, T[2 * NC + 1]); T[2 * NC + 2] = fmaf(w, r2.z, T[2 * NC + 2]);
+                    if (NC == 4) { T[3] = fmaf(w, r0.w, T[3]); T[7] = fmaf(w, r1.w, T[7]); T[11] = fmaf(w, r2.w, T[11]); }
+                }
+            } else {
+                const int v = min(vbase + vi, vs.n - 1);                     // warp-uniform; clamped pad vertices are not stored
+                const int32_t* ej = vs.ell_j + (size_t)v * nnz;
+                const float* ew = vs.ell_w + (size_t)v * nnz;
+                for (int k = 0; k < nnz; ++k) {
+                    const float w = __ldg(ew + k);
+                    const float4* Aj = As + __ldg(ej + k) * 96 + lane;
+                    const float4 r0 = Aj[0], r1 = Aj[32], r2 = Aj[64];
+                    T[0] = fmaf(w, r0.x, T[0]); T[1] = fmaf(w, r0.y, T[1]); T[2] = fmaf(w, r0.z, T[2]);
+                    T[NC] = fmaf(w, r1.x, T[NC]); T[NC + 1] = fmaf(w, r1.y, T[NC + 1]); T[NC + 2] = fmaf(w, r1.z, T[NC + 2]);
+                    T[2 * NC] = fmaf(w, r2.x, T[2 * NC]); T[2 * NC + 1] = fmaf(w, r2.y, T[2 * NC + 1]); T[2 * NC + 2] = fmaf(w, r2.z, T[2 * NC + 2]);
+                    if (NC == 4) { T[3] = fmaf(w, r0.w, T[3]); T[7] = fmaf(w, r1.w, T[7]); T[11] = fmaf(w, r2.w, T[11]); }
+                }
             }
             float* q = st + (3 * vi) * SR_LD + lane;
             const float px = q[0], py = q[SR_LD], pz = q[2 * SR_LD];
-            float ox = T[0] * px + T[1] * py + T[2] * pz + T[3];
-            float oy = T[4] * px + T[5] * py + T[6] * pz + T[7];
-            float oz = T[8] * px + T[9] * py + T[10] * pz + T[11];
-            if (theta) { ox = (ox + t0) * sc * cs; oy = (oy + t1) * sc * cs; oz = (oz + t2) * sc * cs; }
+            float ox, oy, oz;
+            if (MODE == 0) {
+                ox = T[0] * px + T[1] * py + T[2] * pz + T[3];
+                oy = T[4] * px + T[5] * py + T[6] * pz + T[7];
+                oz = T[8] * px + T[9] * py + T[10] * pz + T[11];
+                if (theta) { ox = (ox + t0) * sc * cs; oy = (oy + t1) * sc * cs; oz = (oz + t2) * sc * cs; }
+            } else {
+                ox = T[0] * px + T[3] * py + T[6] * pz;
+                oy = T[1] * px + T[4] * py + T[7] * pz;
+                oz = T[2] * px + T[5] * py + T[8] * pz;
+            }
             q[0] = ox; q[SR_LD] = oy; q[2 * SR_LD] = oz;
         }
         __syncwarp();
@@ -363,9 +400,45 @@ k_skin_rows(BfVSet vs, int J, const float* __restrict__ A, const float* vposed, 
             for (int s = 0; s < 3; ++s) {
                 const int idx = lane + 32 * s, hi = idx >= 48;
                 const int fr = 2 * rp + hi, c = idx - 48 * hi;
-                if (fr < nrows && c < ncols) dst[(size_t)fr * ld_v + c] = st[c * SR_LD + fr];
+                if (fr < nrows && c < ncols) {
+                    const float val = st[c * SR_LD + fr];
+                    if (out) out[(size_t)(b0 + fr) * ld_v + 3 * vbase + c] = val;
+                    if (MODE == 1 && out_hi) {
+                        float h_, l_;
+                        split_tf32(val, h_, l_);
+                        const size_t o = (size_t)(b0 + fr) * ld_out + 3 * vbase + c;
+                        out_hi[o] = h_; out_lo[o] = l_;
+                    }
+                }
             }
         }
         __syncwarp();
     }
+}
+
+static int bf_launch_skin_rows(int mode, const BfVSet* vs, int J, const float* A, const float* in, float* out, float* out_hi,
+                               float* out_lo, int B, int ld_v, int ld_out, const float* theta, int NP, float cs, cudaStream_t s) {
+    const size_t smem = sizeof(float) * ((size_t)3 * J * 32 * 4 + (size_t)SR_WARPS * SR_TILE);
+    static size_t attr[2] = {0, 0};
+    if (attr[mode] < smem) {
+        cudaError_t e = mode == 0 ? cudaFuncSetAttribute(k_skin_rows<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                  : cudaFuncSetAttribute(k_skin_rows<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { bf_set_error("cudaFuncSetAttribute(k_skin_rows): %s", cudaGetErrorString(e)); return BF_ECUDA; }
+        attr[mode] = smem;
+    }
+    static int num_sms = 0;
+    if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); }
+    // 32 frames per CTA (one CTA per SM); the vertex range is cut into slabs only while that is needed to fill the SMs:
+    // at most two full rounds of CTAs, each slab at least one 16-vertex chunk per warp
+    const int groups = (B + 31) / 32, n_chunks = (vs->n + 15) / 16;
+    int slabs = (2 * num_sms) / groups;
+    const int max_slabs = (n_chunks + SR_WARPS - 1) / SR_WARPS;
+    if (slabs > max_slabs) slabs = max_slabs;
+    if (slabs < 1) slabs = 1;
+    const int cps = (n_chunks + slabs - 1) / slabs;
+    const dim3 grid(groups, (n_chunks + cps - 1) / cps);
+    if (mode == 0) k_skin_rows<0><<<grid, 32 * SR_WARPS, smem, s>>>(*vs, J, A, in, out, out_hi, out_lo, B, ld_v, ld_out, theta, NP, cs, cps);
+    else k_skin_rows<1><<<grid, 32 * SR_WARPS, smem, s>>>(*vs, J, A, in, out, out_hi, out_lo, B, ld_v, ld_out, theta, NP, cs, cps);
+    BF_LAUNCH_CHECK();
+    return BF_OK;
 }

@@ -47,8 +47,6 @@ class FrameBuffers(object):
             buf('pf_hi', B, Kp)
             buf('pf_lo', B, Kp)
         buf('A', B, J, 12)
-        if tc:
-            buf('A_T', 3 * J * B * 4)                  # frame-minor copy of A, leading dimension = B of this struct
         buf('Jtr', B, J, 3)
         buf('full_pose', B, 3 * J)
         buf('yaw', B, dtype=torch.int32, zero=True)
@@ -160,7 +158,6 @@ class FitSession(object):
         c = min(int(chunk), self.B)
         scratch = dict(pf=torch.empty(c, model.Kp, device=dev), pf_hi=torch.empty(c, model.Kp, device=dev),
                        pf_lo=torch.empty(c, model.Kp, device=dev), A=torch.empty(c, model.J, 12, device=dev),
-                       A_T=torch.empty(3 * model.J * c * 4, device=dev),
                        Jtr=torch.empty(c, model.J, 3, device=dev), yaw=torch.zeros(c, dtype=torch.int32, device=dev),
                        loss=torch.zeros(c, device=dev))
         if not return_vertices:
@@ -168,7 +165,7 @@ class FitSession(object):
         self.chunks = []
         for lo in range(0, self.B, c):
             hi = min(self.B, lo + c)
-            ext = {k: (v if k == 'A_T' else v[:hi - lo]) for k, v in scratch.items()}
+            ext = {k: v[:hi - lo] for k, v in scratch.items()}
             ext.update(theta=self.theta_prev[lo:hi], joints=self.joints[lo:hi], full_pose=self.full_pose[lo:hi])
             if return_vertices:
                 ext['verts'] = self.verts[lo:hi].view(hi - lo, -1)

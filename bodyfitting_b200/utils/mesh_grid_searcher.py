@@ -1,7 +1,6 @@
 """``MeshGridSearcher`` -- same interface as the reference's ``utils/mesh_grid_searcher.py:51-84``
-(``set_mesh``, ``nearest_points`` -> (points [Q,3] f32, face ids [Q] i32)) on the B200 grid kernels
-(include/bodyfit_b200_grid.h).  ``inside_mesh`` / ``intersects_any`` (unused by the fitting path,
-SURVEY.md 8f rank 4) are not provided."""
+(``set_mesh``, ``nearest_points`` -> (points [Q,3] f32, face ids [Q] i32), ``inside_mesh`` -> signs [Q] f32,
+``intersects_any`` -> bool [Q]; :51-99) on the B200 grid kernels (include/bodyfit_b200_grid.h)."""
 import ctypes as C
 
 import numpy as np
@@ -65,3 +64,23 @@ class MeshGridSearcher(object):
                                               near_faces.data_ptr(), d2.data_ptr() if return_dist2 else None, _stream()),
                    'bf_grid_nearest')
         return (near_pts, near_faces, d2) if return_dist2 else (near_pts, near_faces)
+
+    def inside_mesh(self, points):
+        """+1 for query points inside the closed mesh, -1 outside (reference: mesh_grid_searcher.py:86-91)."""
+        points = points.to(self.device).float().reshape(-1, 3).contiguous()
+        Q = points.shape[0]
+        signs = torch.empty(Q, dtype=torch.float32, device=self.device)
+        _lib.check(_lib.lib().bf_grid_inside(C.byref(self.grid), points.detach().data_ptr(), Q, signs.data_ptr(), _stream()),
+                   'bf_grid_inside')
+        return signs
+
+    def intersects_any(self, origins, directions):
+        """bool [Q]: does the ray origin + t * direction (t >= 0) meet the mesh (reference: mesh_grid_searcher.py:93-99)."""
+        origins = origins.to(self.device).float().reshape(-1, 3).contiguous()
+        directions = directions.to(self.device).float().reshape(-1, 3).contiguous()
+        assert origins.shape == directions.shape
+        Q = origins.shape[0]
+        hit = torch.empty(Q, dtype=torch.uint8, device=self.device)
+        _lib.check(_lib.lib().bf_grid_intersects_any(C.byref(self.grid), origins.detach().data_ptr(), directions.detach().data_ptr(),
+                                                     Q, hit.data_ptr(), _stream()), 'bf_grid_intersects_any')
+        return hit.bool()

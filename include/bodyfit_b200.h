@@ -140,9 +140,6 @@ typedef struct BfFrames {
     const float* halo_next;  /* [NP] theta of the frame after this shard's last frame (next rank), NULL at the sequence end */
     float*       fwd_state;  /* [B,24J] optional: full_pose, R, rest joints, chain rotations saved by the pose forward so the
                                 pose backward does not recompute them */
-    float*       A_T;        /* [3J, B, 4] frame-minor copy of A (row r of joint j, 32 consecutive frames = 512 contiguous bytes):
-                                the tensor-core skinning epilogue reads it with lane = frame (fully coalesced); written by the
-                                pose forward next to A; required by BF_F_TC */
     float*       ws;         /* split-K workspace of the tensor-core backward GEMM (>= ceil(ldn/2048) * B * Kp floats) or NULL */
     int64_t      ws_floats;
     double lr_ts, lr, beta1, beta2, eps;   /* Adam hyper-parameters (python floats in the reference: smplify.py:167-174) */

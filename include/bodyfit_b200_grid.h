@@ -32,6 +32,13 @@ int bf_grid_fill(const BfGrid* g, int32_t* cursor, void* stream);
 /* closest point of every query: near_pts[Q,3], near_faces[Q] (-1 if the mesh is empty), dist2[Q] (optional) */
 int bf_grid_nearest(const BfGrid* g, const float* points, int Q, float* near_pts, int32_t* near_faces, float* dist2, void* stream);
 
+/* inside test (utils/mesh_grid_searcher.py:86-91, native search_inside_mesh): signs[Q] = +1 inside the closed mesh, -1 outside
+ * (crossing parity of an axis ray towards the nearest grid border; points outside the grid box are outside) */
+int bf_grid_inside(const BfGrid* g, const float* points, int Q, float* signs, void* stream);
+/* ray queries (utils/mesh_grid_searcher.py:93-99, native search_intersect): hit[Q] = 1 iff the ray origin + t * direction,
+ * t >= 0, meets any triangle; a zero direction never hits */
+int bf_grid_intersects_any(const BfGrid* g, const float* origins, const float* directions, int Q, uint8_t* hit, void* stream);
+
 /* SMPL+D displacement step (smplify/smplify.py:236-245) for one subject, body mesh with V vertices / F faces:
  *   P = base + disp; normals; closest points (computed ONCE, the reference searches twice: loss.py:239,267);
  *   loss = |P - C|_F + (mean(1 - <scan_fn[closest], n_v>) + laplacian(n)) * reg_scale; backward; Adam on disp.
