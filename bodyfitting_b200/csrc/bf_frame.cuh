@@ -142,6 +142,7 @@ __global__ void __launch_bounds__(FR_THREADS, 4) k_frame_loss_bwd(BfModel m, BfV
     const int jpw = 32 / G;                                  // joints per warp per pass
     float acc5[5] = {0.f, 0.f, 0.f, 0.f, 0.f};               // loss, d/d transl (3), d/d scale
     for (int k0 = 0; k0 < K; k0 += jpw * (FR_THREADS / 32)) {
+        if (k0 + warp * jpw >= K) break;                     // warp-uniform: nothing left for this warp (last pass)
         const int k = k0 + warp * jpw + lane / G;
         const bool kv = k < K;
         const int kk = kv ? k : K - 1;
@@ -149,7 +150,7 @@ __global__ void __launch_bounds__(FR_THREADS, 4) k_frame_loss_bwd(BfModel m, BfV
         const float X = qx * sc * cs, Y = qy * sc * cs, Z = qz * sc * cs;
         float g0 = 0.f, g1 = 0.f, g2 = 0.f, ls = 0.f;
         for (int v = sub; v < Nv; v += G) {
-            const float* kp = f.kp + (((size_t)b * Nv + v) * K + kk) * 3;
+            const float* kp = f.kp + (((size_t)b * K + kk) * Nv + v) * 3;
             const float kx = kp[0], ky = kp[1], wgt = kp[2];
             const float* M = cam + v * 12;
             const float p0 = M[0] * X + M[1] * Y + M[2] * Z + M[3];

@@ -116,7 +116,7 @@ __global__ void k_kp_world(const float* __restrict__ joints, const float* __rest
         const float p2 = M[8] * X + M[9] * Y + M[10] * Z + M[11];
         const float iz = 1.0f / p2;
         const float u = p0 * iz, w_ = p1 * iz;
-        const float* q = kp + (((size_t)b * Nv + v) * K + k) * 3;
+        const float* q = kp + (((size_t)b * K + k) * Nv + v) * 3;
         const float wgt = q[2];
         const float rx = (q[0] - u) / coef, ry = (q[1] - w_) / coef;
         const float dx = s2 + rx * rx, dy = s2 + ry * ry;

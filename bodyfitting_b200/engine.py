@@ -115,9 +115,10 @@ def pack_cameras(c2ws, Ks):
 
 
 def pack_keypoints(kp, use_hand_face):
-    """[B,Nv,K,3] (x, y, conf) -> (x, y, effective weight).  Body joints weigh conf^2; the
-    reference passes hand / face confidences as [N,1], which broadcasts against the [N]
-    residuals, so every joint of such a group weighs sum_i conf_i^2 of that group and view
+    """[B,Nv,K,3] (x, y, conf) -> device layout [B,K,Nv,3] (x, y, effective weight), joint-major: the Nv views of
+    one joint are 12*Nv contiguous bytes, so the (joint, view) lanes of the loss kernels read whole cache lines.
+    Body joints weigh conf^2; the reference passes hand / face confidences as [N,1], which broadcasts against the
+    [N] residuals, so every joint of such a group weighs sum_i conf_i^2 of that group and view
     (smplify/loss.py:134 with :168,:173,:179)."""
     kp = torch.as_tensor(kp, dtype=torch.float32)
     out = kp.clone()
@@ -127,7 +128,7 @@ def pack_keypoints(kp, use_hand_face):
         for lo, hi in ((25, 46), (46, 67), (67, 135)):
             w[..., lo:hi] = c2[..., lo:hi].sum(-1, keepdim=True)
     out[..., 2] = w
-    return out.contiguous()
+    return out.permute(0, 2, 1, 3).contiguous()
 
 
 class FitSession(object):
@@ -141,19 +142,22 @@ class FitSession(object):
     """
 
     def __init__(self, model: PreparedModel, B, Nv, num_iters, imsize=512, return_vertices=True,
-                 chunk=4096, trace=True, dense_every_iter=False, temporal_weight=0.0, halo_exchange=None):
+                 chunk=4096, trace=True, dense_every_iter=False, temporal_weight=0.0, halo_exchange=None, out=None):
+        """``out`` (optional): externally owned result buffers for these B frames -- ``theta`` [B,NP], ``verts`` [B,V,3],
+        ``joints`` [B,K_full,3], ``full_pose`` [B,3J] (contiguous row slices of a larger batch: ConcurrentFitSession)."""
         self.model, self.B, self.Nv, self.N = model, int(B), int(Nv), int(num_iters)
         assert self.N >= 1
         dev = model.device
+        out = out or {}
         self.fb = FrameBuffers(model, B, full=False, Nv=Nv, n_trace=(self.N if trace else 0), imsize=imsize,
-                               temporal_weight=temporal_weight)
+                               temporal_weight=temporal_weight, ext=dict(theta=out.get('theta')))
         # halo_exchange(first_row, last_row) -> (prev_row | None, next_row | None): boundary frames of the
         # neighbouring ranks, called before every iteration when the temporal term couples frames across shards
         self.halo_exchange = halo_exchange if temporal_weight > 0 else None
         self.theta_prev = torch.empty(B, model.NP, device=dev)
-        self.verts = torch.empty(B, model.V, 3, device=dev) if return_vertices else None
-        self.joints = torch.empty(B, model.K_full, 3, device=dev)
-        self.full_pose = torch.empty(B, 3 * model.J, device=dev)
+        self.verts = (out['verts'] if out.get('verts') is not None else torch.empty(B, model.V, 3, device=dev)) if return_vertices else None
+        self.joints = out['joints'] if out.get('joints') is not None else torch.empty(B, model.K_full, 3, device=dev)
+        self.full_pose = out['full_pose'] if out.get('full_pose') is not None else torch.empty(B, 3 * model.J, device=dev)
         self.dense_every_iter = bool(dense_every_iter)
         c = min(int(chunk), self.B)
         scratch = dict(pf=torch.empty(c, model.Kp, device=dev), pf_hi=torch.empty(c, model.Kp, device=dev),
@@ -175,8 +179,8 @@ class FitSession(object):
         self.kernel_launches = 0
 
     def set_inputs(self, kp_packed, cams):
-        """kp_packed [B,Nv,K_used,3] (x, y, effective weight) and cams [Nv,12], device tensors."""
-        assert kp_packed.shape == (self.B, self.Nv, self.model.K_used, 3) and kp_packed.is_contiguous()
+        """kp_packed [B,K_used,Nv,3] (x, y, effective weight; pack_keypoints) and cams [Nv,12], device tensors."""
+        assert kp_packed.shape == (self.B, self.model.K_used, self.Nv, 3) and kp_packed.is_contiguous()
         self.fb.bind('kp', kp_packed)
         self.fb.bind('cams', cams)
 
@@ -226,10 +230,101 @@ class FitSession(object):
         self.kernel_launches = launches
         return fb.t['theta']
 
+    @property
+    def theta(self):
+        return self.fb.t['theta']
+
     def results(self):
         """Device tensors with the reference's result-dict keys (smplify.py:216-226)."""
         m = self.model
         sn = m.split_theta(self.fb.t['theta'])
+        out = {}
+        if self.verts is not None:
+            out['vertices'] = self.verts
+        out.update(joints=self.joints[:, :m.K_out], pose=sn['body_pose'], betas=sn['betas'], global_orient=sn['global_orient'],
+                   global_transl=sn['transl'] * sn['scale'], scale=sn['scale'], full_pose=self.full_pose)
+        if m.is_smplx:
+            out.update(leye_pose=sn['leye_pose'], reye_pose=sn['reye_pose'],
+                       left_hand_pose=sn['left_hand_pose'], right_hand_pose=sn['right_hand_pose'])
+        return out
+
+
+def staggered_ranges(B, n_parts, grain=128, min_part=2048):
+    """Cut B frames into ``n_parts`` consecutive ranges of linearly growing size (multiples of ``grain`` frames = one GEMM
+    row tile).  Parts that run concurrently share the GPU about evenly, so they finish in order of size: the results of
+    an early part travel to the host while the later parts are still being fitted."""
+    n_parts = max(1, min(int(n_parts), B // max(1, int(min_part))))   # a part should still fill the GPU a few times over
+    grain = grain if min_part >= grain else 1
+    if n_parts == 1:
+        return [(0, B)]
+    w = np.array([1.0 + 0.5 * k for k in range(n_parts)])
+    edges = np.round(np.cumsum(w) / w.sum() * B / grain).astype(np.int64) * grain
+    edges[-1] = B
+    lo, out = 0, []
+    for hi in edges:
+        hi = int(min(max(hi, lo + grain), B))
+        out.append((lo, hi))
+        lo = hi
+    out[-1] = (out[-1][0], B)
+    return [r for r in out if r[1] > r[0]]
+
+
+class ConcurrentFitSession(object):
+    """The B-frame fit as a few staggered parts, each a FitSession on its own CUDA stream (frames are independent fits,
+    smplify/body_fitting.py:82-91, so any partition gives bit-identical results).  Why: the per-frame kernels of one
+    part fill the bubbles of the other parts' latency-bound ones (measured: two concurrent halves finish 6 % sooner than
+    one batch), and because the parts finish one after the other, the device->host copy of an early part's vertices
+    (126 KB per SMPL-X frame) overlaps the remaining fitting instead of trailing it (SMPLify.__call__).
+    Same interface as FitSession (set_inputs / run / results)."""
+
+    def __init__(self, model: PreparedModel, B, Nv, num_iters, imsize=512, return_vertices=True, dense_every_iter=False,
+                 n_parts=3, trace=True, min_part=2048):
+        self.model, self.B, self.Nv, self.N = model, int(B), int(Nv), int(num_iters)
+        dev = model.device
+        self.ranges = staggered_ranges(self.B, n_parts, min_part=min_part)
+        self.theta = torch.zeros(B, model.NP, device=dev)
+        self.verts = torch.empty(B, model.V, 3, device=dev) if return_vertices else None
+        self.joints = torch.empty(B, model.K_full, 3, device=dev)
+        self.full_pose = torch.empty(B, 3 * model.J, device=dev)
+        self.parts, self.streams = [], []
+        for lo, hi in self.ranges:
+            out = dict(theta=self.theta[lo:hi], joints=self.joints[lo:hi], full_pose=self.full_pose[lo:hi],
+                       verts=self.verts[lo:hi] if return_vertices else None)
+            self.parts.append(FitSession(model, hi - lo, Nv, num_iters, imsize=imsize, return_vertices=return_vertices,
+                                         dense_every_iter=dense_every_iter, trace=trace, out=out))
+            self.streams.append(torch.cuda.Stream(device=dev))
+        self.kernel_launches = 0
+
+    def set_inputs(self, kp_packed, cams):
+        assert kp_packed.shape[0] == self.B
+        for (lo, hi), p in zip(self.ranges, self.parts):
+            p.set_inputs(kp_packed[lo:hi], cams)
+
+    def run(self, theta0):
+        cur = torch.cuda.current_stream()
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        for (lo, hi), p, st in zip(self.ranges, self.parts, self.streams):
+            st.wait_event(ready)
+            with torch.cuda.stream(st):
+                p.run(theta0[lo:hi])
+        for st in self.streams:
+            cur.wait_stream(st)
+        self.kernel_launches = sum(p.kernel_launches for p in self.parts)
+        return self.theta
+
+    @property
+    def trace(self):
+        ts = [p.fb.t.get('trace') for p in self.parts]
+        return None if ts[0] is None else torch.cat(ts, dim=1)
+
+    @property
+    def loss_terms(self):
+        return torch.cat([p.fb.t['loss_terms'] for p in self.parts], dim=0)
+
+    def results(self):
+        m = self.model
+        sn = m.split_theta(self.theta)
         out = {}
         if self.verts is not None:
             out['vertices'] = self.verts

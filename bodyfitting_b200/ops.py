@@ -88,7 +88,7 @@ class _KeypointsWorld(torch.autograd.Function):
         _need_cuda(joints)
         j = _f32c(joints)
         B, K = j.shape[0], j.shape[1]
-        Nv = kp_packed.shape[1]
+        Nv = kp_packed.shape[2]                       # [B,K,Nv,3] joint-major (engine.pack_keypoints)
         lbk = torch.empty(B, K, device=j.device)
         dJ = torch.empty_like(j)
         _call('bf_op_keypoints_world', j.data_ptr(), kp_packed.data_ptr(), cams.data_ptr(), B, K, Nv, float(scale_coeff),

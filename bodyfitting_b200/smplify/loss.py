@@ -59,7 +59,7 @@ def multiview_keypoint_loss(w2cs, Ks, keypoints, model_joints, poses, betas, use
     else:
         kp = torch.from_numpy(openpose_to_keypoints(keypoints, 'smplx' if use_hand_face else 'smpl'))[None]
     Kn = kp.shape[2]
-    kp = pack_keypoints(kp.to(dev), use_hand_face)
+    kp = pack_keypoints(kp.to(dev), use_hand_face)                # -> [1 or B, K, Nv, 3]
     if torch.is_tensor(w2cs):
         c2ws = [np.linalg.inv(w.detach().cpu().numpy()) for w in w2cs]
     else:

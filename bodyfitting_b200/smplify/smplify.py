@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from .. import constants as K
-from ..engine import FitSession, pack_cameras, pack_keypoints
+from ..engine import ConcurrentFitSession, FitSession, pack_cameras, pack_keypoints, staggered_ranges
 from ..model import PreparedModel
 from ..synthetic import openpose_to_keypoints
 
@@ -27,7 +27,7 @@ class SMPLify(object):
     def __init__(self, smpl_type='smpl', age='adult', step_size=1e-2, batch_size=1, num_iters=600,
                  gender='male', use_mask=False, device=torch.device('cuda'), debug=True,
                  model_data=None, gmm=None, J_regressor_extra=None, data_root='data', dense_every_iter=False,
-                 pipeline_chunks=None, pipeline_min_frames=2048, temporal_weight=0.0, halo_exchange=None):
+                 concurrent_parts=None, concurrent_min_part=2048, temporal_weight=0.0, halo_exchange=None):
         if age != 'adult':
             raise NotImplementedError("only age='adult' is supported (kid template: smplify.py:114-115)")
         self.device = torch.device(device)
@@ -57,10 +57,11 @@ class SMPLify(object):
         self.dense_every_iter = dense_every_iter
         # temporal smoothness between consecutive frames of the batch (not in the reference; BASELINE config 4)
         self.temporal_weight, self.halo_exchange = float(temporal_weight), halo_exchange
-        if pipeline_chunks is None:
-            pipeline_chunks = int(os.environ.get('BODYFIT_PIPE', '1'))
-        self.pipeline_chunks = max(1, int(pipeline_chunks))
-        self.pipeline_min_frames = int(pipeline_min_frames)
+        # batches of >= 4096 frames are fitted as this many staggered parts on their own streams (1 = one batch)
+        if concurrent_parts is None:
+            concurrent_parts = int(os.environ.get('BODYFIT_PARTS', '3'))
+        self.concurrent_parts = max(1, int(concurrent_parts))
+        self.concurrent_min_part = int(concurrent_min_part)
         self._pinned = {}
         self.last_loss_terms = None
 
@@ -93,12 +94,10 @@ class SMPLify(object):
         B, Nv = kp.shape[0], kp.shape[1]
         assert kp.shape[2] == m.K_used, 'expected %d keypoints per view, got %d' % (m.K_used, kp.shape[2])
         assert len(c2ws) == Nv and len(Ks) == Nv
-        n_chunks = self.pipeline_chunks if (as_numpy and B >= self.pipeline_min_frames * self.pipeline_chunks) else 1
-        if self.temporal_weight > 0:
-            n_chunks = 1                                       # frames are coupled: no independent chunks
-        if n_chunks > 1:
-            return self._call_pipelined(init_betas, init_poses, kp, c2ws, Ks, imsize, return_vertices, n_chunks)
         sess = self.session(B, Nv, imsize, return_vertices)
+        self.h2d_bytes = int(kp.numel() + init_poses.numel() + init_betas.numel() + 12 * Nv) * 4
+        if isinstance(sess, ConcurrentFitSession):
+            return self._call_concurrent(sess, init_betas, init_poses, kp, c2ws, Ks, as_numpy)
 
         # host -> device (pinned staging so the copies are asynchronous DMA)
         kp_dev = self._h2d('kp', kp)
@@ -112,79 +111,52 @@ class SMPLify(object):
         out = sess.results()
         self.last_trace = sess.fb.t.get('trace')
         self.last_loss_terms = sess.fb.t['loss_terms']
-        self.h2d_bytes = sum(int(t.numel() * t.element_size()) for t in (kp, init_poses, init_betas, cams))
         if as_numpy:
             out = self._d2h(out)
         out['faces'] = self.smpl_faces[0]
         return out
 
-    def _call_pipelined(self, init_betas, init_poses, kp, c2ws, Ks, imsize, return_vertices, n_chunks):
-        """Large batches: the frames are fitted in ``n_chunks`` consecutive chunks with two sets of device
-        buffers, so that the device->host copy of chunk i (1.2 GB of vertices per 10k SMPL-X frames) runs on a
-        copy stream while chunk i+1 is being fitted.  Frames are independent, so the results are bit-identical
-        to the single-batch path."""
-        from ..sharding import frame_range
-        m, dev = self.model, self.device
-        B, Nv = kp.shape[0], kp.shape[1]
-        ranges = [frame_range(B, c, n_chunks) for c in range(n_chunks)]
-        cmax = max(hi - lo for lo, hi in ranges)
-        key = ('pipe', cmax, int(Nv), int(self.num_iters), float(imsize), bool(return_vertices))
-        if getattr(self, '_pipe_key', None) != key:
-            self._pipe = [dict() for _ in range(2)]
-            self._pipe_key = key
-            self._pipe_stream = torch.cuda.Stream(device=dev)
-            self._pinned = {}
+    def _call_concurrent(self, sess, init_betas, init_poses, kp, c2ws, Ks, as_numpy):
+        """Large batches: staggered parts on their own streams (engine.ConcurrentFitSession).  Each part's inputs go up,
+        its frames are fitted and its results come down on the part's stream, so the device->host copy of an early
+        part (126 KB of vertices per SMPL-X frame) overlaps the fitting of the later ones.  Results are bit-identical to
+        the single-batch path (frames are independent)."""
+        m = self.model
+        B = kp.shape[0]
+        cur = torch.cuda.current_stream()
         cams = self._h2d('cams', torch.from_numpy(pack_cameras(c2ws, Ks)))
-        main = torch.cuda.current_stream()
-        host, copied = {}, [None, None]
-        nbytes = 0
-        traces, terms = [], []
-        for ci, (lo, hi) in enumerate(ranges):
-            slot = self._pipe[ci % 2]
-            n = hi - lo
-            if slot.get('n') != n:
-                slot['sess'] = FitSession(m, n, Nv, self.num_iters, imsize=imsize, return_vertices=return_vertices,
-                                          dense_every_iter=self.dense_every_iter)
-                slot['n'] = n
-            sess = slot['sess']
-            if copied[ci % 2] is not None:
-                main.wait_event(copied[ci % 2])               # the previous copy out of these buffers has finished
-            kp_dev = self._h2d(('kp', ci % 2), kp[lo:hi])
-            poses_dev = self._h2d(('poses', ci % 2), init_poses[lo:hi])
-            betas_dev = self._h2d(('betas', ci % 2), init_betas[lo:hi])
-            sess.set_inputs(pack_keypoints(kp_dev, self.use_hand_face), cams)
-            sess.run(m.pack_theta(poses_dev[:, :3], poses_dev[:, 3:3 + m.nbody], betas_dev))
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        host, nbytes = {}, 0
+        for k, ((lo, hi), part, st) in enumerate(zip(sess.ranges, sess.parts, sess.streams)):
+            with torch.cuda.stream(st):
+                st.wait_event(ready)
+                kp_dev = self._h2d(('kp', k), kp[lo:hi])
+                poses_dev = self._h2d(('poses', k), init_poses[lo:hi])
+                betas_dev = self._h2d(('betas', k), init_betas[lo:hi])
+                part.set_inputs(pack_keypoints(kp_dev, self.use_hand_face), cams)
+                part.run(m.pack_theta(poses_dev[:, :3], poses_dev[:, 3:3 + m.nbody], betas_dev))
+                if as_numpy:
+                    for name, v in part.results().items():
+                        pbuf = self._pinned.get(('out', name))
+                        if pbuf is None or pbuf.shape != (B,) + tuple(v.shape[1:]):
+                            pbuf = torch.empty((B,) + tuple(v.shape[1:]), dtype=v.dtype, pin_memory=True)
+                            self._pinned[('out', name)] = pbuf
+                        host[name] = pbuf
+                        pbuf[lo:hi].copy_(v, non_blocking=True)
+                        nbytes += int(v.numel() * v.element_size())
+        if as_numpy:
+            for st in sess.streams:
+                st.synchronize()
+            self.d2h_bytes = nbytes
+            out = {name: pbuf.squeeze(0).numpy() for name, pbuf in host.items()}
+        else:
+            for st in sess.streams:
+                cur.wait_stream(st)
             out = sess.results()
-            out = {k: (v if v.is_contiguous() else v.contiguous()) for k, v in out.items()}
-            done = torch.cuda.Event()
-            done.record(main)
-            with torch.cuda.stream(self._pipe_stream):
-                self._pipe_stream.wait_event(done)
-                for k, v in out.items():
-                    if k not in host:
-                        pk = ('out', k)
-                        p = self._pinned.get(pk)
-                        if p is None or p.shape != (B,) + tuple(v.shape[1:]):
-                            p = torch.empty((B,) + tuple(v.shape[1:]), dtype=v.dtype, pin_memory=True)
-                            self._pinned[pk] = p
-                        host[k] = p
-                    host[k][lo:hi].copy_(v, non_blocking=True)
-                    v.record_stream(self._pipe_stream)
-                    nbytes += int(v.numel() * v.element_size())
-                ev = torch.cuda.Event()
-                ev.record(self._pipe_stream)
-                copied[ci % 2] = ev
-            traces.append(sess.fb.t.get('trace'))
-            terms.append(sess.fb.t['loss_terms'])
-        self._pipe_stream.synchronize()
-        main.synchronize()
-        self.last_trace = torch.cat([t.clone() for t in traces], dim=1) if n_chunks <= 2 and traces[0] is not None else traces[-1]
-        self.last_loss_terms = terms[-1]
-        self.h2d_bytes = sum(int(t.numel() * t.element_size()) for t in (kp, init_poses, init_betas, cams))
-        self.d2h_bytes = nbytes
-        res = {k: p.squeeze(0).numpy() for k, p in host.items()}
-        res['faces'] = self.smpl_faces[0]
-        return res
+        self.last_trace, self.last_loss_terms = sess.trace, sess.loss_terms
+        out['faces'] = self.smpl_faces[0]
+        return out
 
     # ------------------------------------------------------------------------------------------
     def _fit_to_scan(self, net_output, c2ws, Ks, keypoints, imsize, meshfile, displacement, as_numpy):
@@ -251,11 +223,19 @@ class SMPLify(object):
         return out
 
     def session(self, B, Nv, imsize=512, return_vertices=True):
+        """Device state for B frames, cached across calls of the same shape: a ConcurrentFitSession (staggered parts on
+        their own streams) for large batches, a plain FitSession otherwise / when the temporal term couples the frames."""
         key = (int(B), int(Nv), int(self.num_iters), float(imsize), bool(return_vertices))
         if getattr(self, '_sess_key', None) != key:
-            self._sess = FitSession(self.model, B, Nv, self.num_iters, imsize=imsize,
-                                    return_vertices=return_vertices, dense_every_iter=self.dense_every_iter,
-                                    temporal_weight=self.temporal_weight, halo_exchange=self.halo_exchange)
+            n_parts = 1 if self.temporal_weight > 0 else self.concurrent_parts
+            if n_parts > 1 and len(staggered_ranges(B, n_parts, min_part=self.concurrent_min_part)) > 1:
+                self._sess = ConcurrentFitSession(self.model, B, Nv, self.num_iters, imsize=imsize, return_vertices=return_vertices,
+                                                  dense_every_iter=self.dense_every_iter, n_parts=n_parts,
+                                                  min_part=self.concurrent_min_part)
+            else:
+                self._sess = FitSession(self.model, B, Nv, self.num_iters, imsize=imsize,
+                                        return_vertices=return_vertices, dense_every_iter=self.dense_every_iter,
+                                        temporal_weight=self.temporal_weight, halo_exchange=self.halo_exchange)
             self._sess_key = key
             self._pinned = {}
         return self._sess

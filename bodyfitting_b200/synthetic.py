@@ -308,3 +308,19 @@ def openpose_to_keypoints(views, model_type):
             if 'face' in d:
                 out[v, 67:135] = np.asarray(d['face'], dtype=np.float32)[FACE_MAPPING]
     return out
+
+
+def make_masks(verts_world, faces, c2ws, Ks, imsize=512):
+    """Silhouette masks [Nv,imsize,imsize] uint8 (0 / 255) of a world-space mesh: every face rasterised with
+    cv2.fillPoly in every view (stand-in for the segmentation masks of apps/genebody_fitting.py)."""
+    import cv2
+    v = np.asarray(verts_world, dtype=np.float64)
+    out = np.zeros((len(c2ws), imsize, imsize), np.uint8)
+    for i, (c2w, K) in enumerate(zip(c2ws, Ks)):
+        w2c = np.linalg.inv(np.asarray(c2w, dtype=np.float64))
+        pc = v @ w2c[:3, :3].T + w2c[:3, 3]
+        uv = pc @ np.asarray(K, dtype=np.float64).T
+        uv = uv[:, :2] / uv[:, 2:3]
+        polys = np.round(uv[np.asarray(faces)]).astype(np.int32)
+        cv2.fillPoly(out[i], list(polys), 255)
+    return out

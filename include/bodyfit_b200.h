@@ -123,7 +123,7 @@ typedef struct BfFrames {
     float*       dvp;        /* [B,ld_v] */
     float*       joints;     /* [B,K_out,3] model-space output joints (optional, may be NULL) */
     float*       djoints;    /* [B,K_out,3] incoming joint gradient (operator backward) or NULL */
-    const float* kp;         /* [B,Nv,K_used,3] (x, y, effective weight) */
+    const float* kp;         /* [B,K_used,Nv,3] (x, y, effective weight), joint-major: the views of a joint are contiguous */
     const float* cams;       /* [Nv,12] row-major 3x4  K @ [R|t] (world -> pixel, homogeneous) */
     float*       loss;       /* [B] per-frame total loss of this iteration */
     float*       loss_terms; /* [B,4] data, pose prior, angle prior, shape prior (optional) */

@@ -10,7 +10,7 @@
  *   bf_op_reprojection          smplify/loss.py:132-136 sum_j w_j sum_c gmof((gt - cord)/coef): value + d/dcord;
  *                               w_j = conf_j^2 (body) or the group's sum of conf^2 ([N,1] confidences, :168-179)
  *   bf_op_keypoints_world       smplify/loss.py:156-203 data term on world joints [B,K,3] against packed
- *                               detections [B,Nv,K,3] = (x, y, weight) and cams [Nv,12] = K [R|t]:
+ *                               detections [B,K,Nv,3] = (x, y, weight) (joint-major) and cams [Nv,12] = K [R|t]:
  *                               per (frame, joint) loss / Nv and d/d joints
  *   bf_op_angle_prior           smplify/loss.py:54-61   exp(sign * pose[:, [52,55,9,12]])^2 and its derivative
  *   bf_op_gmm_pose              smplify/prior.py:181-196 weight * min_m(0.5 d^T P_m d - log nll_w_m) on pose[B, ld]

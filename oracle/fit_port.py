@@ -14,6 +14,8 @@ baseline.  Each function cites the reference lines it follows:
   SpinSMPL             models/smpl.py:56-83     SMPL wrapper (+9 regressed joints, 49-joint map)
   FitPort.fit_frame()  smplify/smplify.py:84-226 SMPLify.__call__ for ONE frame, same op
                                                  sequence (per-view Python loop, 9-group Adam)
+  extract_contours()   smplify/loss.py:73-83    extract_countours
+  mask_objective()     smplify/loss.py:85-130   multview_mask_loss (silhouette term, use_mask=True)
   FitPort.fit_batched()the same objective for B independent frames at once (the
                        reference supports B=1 only, smplify/smplify.py:189-190); validated
                        against fit_frame per frame in tests/test_oracle.py
@@ -158,6 +160,54 @@ def keypoint_objective(w2cs, Ks, views, model_joints, poses, betas, prior, imsiz
                              shape_prior_loss=shape_l)
 
 
+def extract_contours(masks):
+    """smplify/loss.py:73-83 extract_countours: per mask the longest external contour (cv2.RETR_EXTERNAL,
+    CHAIN_APPROX_NONE) as a float tensor [Nc,1,2] of (x, y) pixels.  The reference unpacks OpenCV 3's three return
+    values (:79); OpenCV 4 returns (contours, hierarchy) -- same contours."""
+    import cv2
+    out = []
+    for mask in masks:
+        res = cv2.findContours(mask.cpu().numpy().astype(np.uint8) * 255, cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_NONE)
+        contour = res[-2]
+        contour = contour[int(np.argmax(np.array([a.shape[1] for a in contour])))]
+        out.append(torch.tensor(contour, dtype=torch.float32, device=masks.device))
+    return out
+
+
+def mask_objective(contours, masks, verts, w2cs, Ks, imsize=512, epsilon=10, exact_cdist=False):
+    """smplify/loss.py:85-130 multview_mask_loss for ONE frame: ``verts`` [1,V,3] world vertices, ``masks`` [Nm,H,W]
+    float 0/1, ``contours`` from extract_contours, ``w2cs`` / ``Ks`` of the mask views.
+      * every 4th vertex is projected (:100,:105);
+      * the contour is [Nc,1,2], so ``cdist(points[1,Np,2], contour[1,Nc,1,2])`` broadcasts to [Nc,Np,1] and ``min(dist, 1)``
+        picks, for every CONTOUR point, the closest projected in-image vertex (:111-112);
+      * that vertex's pixel decides the penalty: 10 x if it falls outside the mask, 1 x otherwise (:115-118);
+      * plus 10 x the bilinear samples of (1 - mask) at every projected vertex (grid_sample, align_corners=False) (:124-128).
+    ``exact_cdist``: direct |x - c| instead of torch's matmul-based expansion (what the CUDA kernel computes)."""
+    scale_coeff = 1
+    sv = verts.squeeze(0)[::4]
+    losses, uvs = [], []
+    for i in range(len(contours)):
+        pose, K, contour, mask = w2cs[i], Ks[i], contours[i], masks[i]
+        pp = project(sv.unsqueeze(0), pose[None, :3, :3], pose[None, :3, 3], K).squeeze(0)
+        inside = torch.prod((pp < imsize) & (pp >= 0), dim=1).squeeze(0) > 0
+        ip = pp[inside]
+        uvs.append(pp)
+        if exact_cdist:
+            dist = torch.cdist(ip.unsqueeze(0) / scale_coeff, contour.unsqueeze(0) / scale_coeff,
+                               compute_mode='donot_use_mm_for_euclid_dist').squeeze(0)
+        else:
+            dist = torch.cdist(ip.unsqueeze(0) / scale_coeff, contour.unsqueeze(0) / scale_coeff).squeeze(0)
+        mindist, index = torch.min(dist, 1)
+        cp = ip[index[:, 0]].long()
+        outside = (mask[cp[:, 1], cp[:, 0]] < 0.1).to(verts.dtype)[:, None]
+        coeff = outside * (epsilon - 1) + 1
+        losses.append(torch.sum(mindist * coeff))
+    total = torch.stack(losses).sum()
+    uvs = torch.stack(uvs, dim=0).view(len(masks), -1, 1, 2) / imsize * 2 - 1
+    binary = torch.nn.functional.grid_sample(1 - masks[:, None], uvs, align_corners=False)
+    return total + torch.sum(binary) * epsilon
+
+
 def effective_weights(kp, use_hand_face):
     """kp [B,Nv,K,3] -> w [B,Nv,K]: conf^2 for the body joints; for each hand / the face
     the reference's broadcast makes every joint of the group weigh sum_i conf_i^2."""
@@ -247,19 +297,28 @@ class FitPort(object):
                     left_hand_pose=sq(p['left_hand_pose']), right_hand_pose=sq(p['right_hand_pose']))
 
     # -- one frame, reference op sequence ---------------------------------------
-    def fit_frame(self, init_betas, init_poses, c2ws, Ks, views, num_iters=100, imsize=512):
+    def fit_frame(self, init_betas, init_poses, c2ws, Ks, views, num_iters=100, imsize=512, masks=None, mask_frames=None):
+        """``masks`` [Nm,H,W] uint8 + ``mask_frames``: also the silhouette term (use_mask=True, smplify.py:137-144,196-199)."""
         p = self._init_params(init_betas, init_poses, 1)
         w2cs = torch.inverse(torch.from_numpy(np.array(c2ws)).to(self.dtype))
         Ks = [np.asarray(k) for k in Ks]
         opt = self._optimizer(p)
         trace = []
-        for _ in range(num_iters):
+        if masks is not None:
+            mk = torch.from_numpy((np.array(masks) > 128).astype(np.float32)).to(self.dtype)
+            use_frames = list(range(len(c2ws)))
+            mask_w2cs = [w2cs[use_frames.index(f)] for f in mask_frames]
+            mask_Ks = [Ks[use_frames.index(f)] for f in mask_frames]
+            contours = extract_contours(mk)
+        for i in range(num_iters):
             out = self.forward_model(p)
             # reference broadcasting for B=1: [1,K,3] + [1,3] and * [1,1]
             joints = (out.joints + p['global_transl']) * p['body_scale'] * self.constant_scale
             verts = (out.vertices + p['global_transl']) * p['body_scale'] * self.constant_scale
             loss, _ = keypoint_objective(w2cs, Ks, views, joints, p['body_pose'], p['betas'], self.prior,
                                          imsize, self.use_hand_face)
+            if masks is not None and i > (num_iters // 3):
+                loss = loss + 5 * mask_objective(contours, mk, verts, mask_w2cs, mask_Ks, imsize) + 5 * 0
             trace.append(float(loss.detach()))
             opt.zero_grad()
             loss.backward()
@@ -293,6 +352,40 @@ class FitPort(object):
                 hook(it, p, out, joints, verts, per_frame)
             opt.step()
         return self._result(p, out, joints, verts, False), torch.stack(trace).numpy()
+
+    # -- keypoints + silhouette term (use_mask=True, smplify/smplify.py:137-144,196-199,210) ------------
+    def fit_batched_mask(self, init_betas, init_poses, c2ws, Ks, kp, masks, mask_frames, num_iters=12, imsize=512,
+                         exact_cdist=False):
+        """B frames, each with its own masks [B,Nm,H,W] (uint8 0..255) of the views ``mask_frames`` (indices into the
+        camera list; the reference looks them up through use_frames, smplify.py:141-142):
+        loss_f = keypoint objective + 5 x mask objective for i > num_iters // 3."""
+        kp = torch.as_tensor(kp, dtype=self.dtype)
+        B = kp.shape[0]
+        p = self._init_params(init_betas, init_poses, B)
+        w2cs = torch.inverse(torch.as_tensor(np.array(c2ws), dtype=self.dtype))
+        Kt = torch.as_tensor(np.array(Ks), dtype=self.dtype)
+        mk = torch.as_tensor((np.asarray(masks) > 128).astype(np.float32)).to(self.dtype)          # smplify.py:139
+        contours = [[c.to(self.dtype) for c in extract_contours(mk[b])] for b in range(B)]
+        mw2c = [w2cs[f] for f in mask_frames]
+        mK = [Kt[f] for f in mask_frames]
+        opt = self._optimizer(p)
+        trace, mls = [], []
+        for it in range(num_iters):
+            out = self.forward_model(p)
+            joints, verts = self.world(out, p)
+            per_frame, _ = batched_objective(w2cs, Kt, kp, joints, p['body_pose'], p['betas'], self.prior, imsize,
+                                             self.use_hand_face)
+            if it > (num_iters // 3):
+                ml = torch.stack([mask_objective(contours[b], mk[b], verts[b:b + 1], mw2c, mK, imsize, exact_cdist=exact_cdist)
+                                  for b in range(B)])
+                per_frame = per_frame + 5 * ml
+                mls.append(ml.detach().clone())
+            trace.append(per_frame.detach().clone())
+            opt.zero_grad()
+            per_frame.sum().backward()
+            opt.step()
+        res = self._result(p, out, joints, verts, False)
+        return res, torch.stack(trace).numpy(), (torch.stack(mls).numpy() if mls else None)
 
     # -- keypoints + point-to-scan term (use_mesh=True, smplify/smplify.py:146-156,205-210) ----------
     def fit_batched_scan(self, init_betas, init_poses, c2ws, Ks, kp, scan_verts, scan_faces, num_iters=12, imsize=512):

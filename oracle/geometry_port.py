@@ -95,3 +95,46 @@ def smpld_loop(body_vertices, body_faces, scan_verts, scan_faces, constant_scale
         trace.append([float(icp), float(norm_loss), float(smooth), float(loss)])
         opt.zero_grad(); loss.backward(); opt.step()
     return disp.detach().numpy(), np.array(trace)
+
+
+def inside_bruteforce(points, verts, faces, chunk=512):
+    """fp64 referee for MeshGridSearcher.inside_mesh (utils/mesh_grid_searcher.py:86-91): generalised winding
+    number (van Oosterom & Strackee solid angles) over ALL faces; returns (sign [+1 inside / -1 outside], winding)."""
+    P = np.asarray(points, np.float64); V = np.asarray(verts, np.float64); F = np.asarray(faces, np.int64)
+    a, b, c = V[F[:, 0]], V[F[:, 1]], V[F[:, 2]]
+    wn = np.zeros(len(P))
+    for s in range(0, len(P), chunk):
+        p = P[s:s + chunk, None, :]
+        A, B, C = a[None] - p, b[None] - p, c[None] - p
+        la, lb, lc = np.linalg.norm(A, axis=-1), np.linalg.norm(B, axis=-1), np.linalg.norm(C, axis=-1)
+        num = np.einsum('qfi,qfi->qf', A, np.cross(B, C))
+        den = la * lb * lc + (A * B).sum(-1) * lc + (B * C).sum(-1) * la + (C * A).sum(-1) * lb
+        wn[s:s + chunk] = (2.0 * np.arctan2(num, den)).sum(1) / (4.0 * np.pi)
+    return np.where(np.abs(wn) > 0.5, 1.0, -1.0), wn
+
+
+def ray_any_bruteforce(origins, dirs, verts, faces, chunk=512):
+    """fp64 referee for MeshGridSearcher.intersects_any (utils/mesh_grid_searcher.py:93-99; one-directional ray,
+    t >= 0, thirdparty/mesh_grid/mesh_grid_kernel.cu:742-781): Moeller-Trumbore against ALL faces.
+    Returns (hit [bool], margin): margin = how far the decisive triangle test is from flipping (small = grazing)."""
+    O = np.asarray(origins, np.float64); D = np.asarray(dirs, np.float64)
+    V = np.asarray(verts, np.float64); F = np.asarray(faces, np.int64)
+    a = V[F[:, 0]]; e1 = V[F[:, 1]] - a; e2 = V[F[:, 2]] - a
+    hit = np.zeros(len(O), bool); margin = np.zeros(len(O))
+    for s in range(0, len(O), chunk):
+        o, d = O[s:s + chunk, None, :], D[s:s + chunk, None, :]
+        pv = np.cross(d, e2[None])
+        det = (e1[None] * pv).sum(-1)
+        with np.errstate(divide='ignore', invalid='ignore'):
+            inv = 1.0 / det
+            tv = o - a[None]
+            u = (tv * pv).sum(-1) * inv
+            qv = np.cross(tv, e1[None])
+            v = (d * qv).sum(-1) * inv
+            t = (e2[None] * qv).sum(-1) * inv
+        m = np.minimum(np.minimum(u, v), np.minimum(1.0 - u - v, t))       # > 0: hit with that much slack
+        m = np.where(np.isfinite(m), m, -np.inf)
+        best = m.max(1)
+        hit[s:s + chunk] = best >= 0
+        margin[s:s + chunk] = np.abs(best)
+    return hit, margin

@@ -91,8 +91,23 @@ def data_cwd(data_parent):
         os.chdir(old)
 
 
+class _Cv2ThreeReturn(object):
+    """The reference calls OpenCV 3's ``_, contours, _ = cv2.findContours(...)`` (smplify/loss.py:79); OpenCV 4 returns
+    (contours, hierarchy).  This adapter restores the three-value form and forwards everything else untouched."""
+
+    def __init__(self, cv2):
+        self._cv2 = cv2
+
+    def __getattr__(self, name):
+        return getattr(self._cv2, name)
+
+    def findContours(self, *a, **k):
+        res = self._cv2.findContours(*a, **k)
+        return (None, res[0], res[1]) if len(res) == 2 else res
+
+
 def run_reference_fit(data_parent, smpl_type, init_betas, init_poses, c2ws, Ks, keypoints, num_iters=100,
-                      imsize=512, record=True):
+                      imsize=512, record=True, masks=None, mask_frames=None):
     """One frame through the verbatim ``SMPLify.__call__`` (smplify/smplify.py:84-250) on CPU.
     ``keypoints`` = list (per view) of OpenPose dicts.  Returns (result dict, per-iteration
     total-loss list, per-iteration loss-term dicts)."""
@@ -115,10 +130,16 @@ def run_reference_fit(data_parent, smpl_type, init_betas, init_poses, c2ws, Ks, 
             fitter = ns.smplify.SMPLify(smpl_type=smpl_type, num_iters=num_iters, gender='neutral',
                                         device=torch.device('cpu'), debug=False)
             nv = len(c2ws)
+            extra = {}
+            if masks is not None:                       # silhouette term: masks [Nm,H,W] uint8 of the views mask_frames
+                extra = dict(use_mask=True, masks=list(masks), mask_frames=list(mask_frames))
+                ns.loss.cv2 = _Cv2ThreeReturn(ns.loss.cv2)
             res = fitter((torch.tensor(init_betas).float().reshape(1, -1).clone(),
                           torch.tensor(init_poses).float().reshape(1, -1).clone()),
                          [np.asarray(c, dtype=np.float32) for c in c2ws], [np.asarray(k) for k in Ks],
-                         keypoints, None, use_frames=list(range(nv)), imsize=imsize)
+                         keypoints, None, use_frames=list(range(nv)), imsize=imsize, **extra)
         finally:
             ns.smplify.multiview_keypoint_loss = orig
+            if isinstance(ns.loss.cv2, _Cv2ThreeReturn):
+                ns.loss.cv2 = ns.loss.cv2._cv2
     return res, trace, terms, fitter

@@ -31,12 +31,12 @@ for w in (0.0, 300.0):
     fit = SMPLify(halo_exchange=exchange_halo, **kw)
     out = fit((sc['init_betas'][lo:hi], sc['init_pose'][lo:hi]), list(sc['c2ws']), list(sc['Ks']), sc['kp'][lo:hi], None,
               imsize=512, as_numpy=False)
-    theta = gather_frames(fit.session(hi - lo, nv, 512, True).fb.t['theta'].contiguous(), B)
+    theta = gather_frames(fit.session(hi - lo, nv, 512, True).theta.contiguous(), B)
     verts = gather_frames(out['vertices'].contiguous(), B)
     if rank == 0:
         one = SMPLify(**kw)
         ref = one((sc['init_betas'], sc['init_pose']), list(sc['c2ws']), list(sc['Ks']), sc['kp'], None, imsize=512, as_numpy=False)
-        t_ref = one.session(B, nv, 512, True).fb.t['theta']
+        t_ref = one.session(B, nv, 512, True).theta
         same_t = bool(torch.equal(theta, t_ref))
         same_v = bool(torch.equal(verts, ref['vertices']))
         print('temporal_weight %.0f: %d ranks, sharded == single-GPU  theta: %s  vertices: %s  (max |d theta| %.3e)'

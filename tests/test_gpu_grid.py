@@ -142,3 +142,95 @@ def test_full_size_scan_properties():
     assert float(uv.min()) > -1e-3 and float(uv.sum(1).max()) < 1 + 1e-3
     pts2, _, d22 = s.nearest_points(pts, return_dist2=True)
     assert float(d22.max()) < 1e-9                                     # already on the surface
+
+
+def _inside_queries(v, n, seed):
+    rng = np.random.RandomState(seed)
+    lo, hi = v.min(0), v.max(0)
+    box = (rng.rand(n // 2, 3) * (hi - lo) * 1.3 + lo - 0.15 * (hi - lo)).astype(np.float32)      # in / around the box
+    shell = (v[rng.randint(0, len(v), n - n // 2)] * (1.0 + rng.randn(n - n // 2, 1) * 0.05)).astype(np.float32)   # near the surface
+    return np.concatenate([box, shell]).astype(np.float32)
+
+
+def test_inside_mesh_vs_winding_number():
+    """MeshGridSearcher.inside_mesh against the fp64 generalised winding number over all faces."""
+    from bodyfitting_b200.utils.mesh_grid_searcher import MeshGridSearcher
+    v, f = _scan()
+    q = _inside_queries(v, 6000, 3)
+    s = MeshGridSearcher(v, f)
+    sg = s.inside_mesh(torch.from_numpy(q).cuda()).cpu().numpy()
+    ref, wn = gp.inside_bruteforce(q, v, f)
+    assert set(np.unique(sg)) <= {-1.0, 1.0} and sg.dtype == np.float32
+    print('inside fraction', (ref > 0).mean(), 'mismatches', int((sg != ref).sum()))
+    assert (ref > 0).mean() > 0.2 and (ref < 0).mean() > 0.2          # the query set exercises both answers
+    assert (sg == ref).all()
+    far = torch.tensor([[50.0, 0.0, 0.0], [0.0, 0.0, 0.0]]).cuda()     # outside the grid box / the centre of the blob
+    assert s.inside_mesh(far).cpu().tolist() == [-1.0, 1.0]
+
+
+def test_intersects_any_vs_bruteforce():
+    """MeshGridSearcher.intersects_any against fp64 Moeller-Trumbore over all faces (rays from inside always hit,
+    rays pointing away from outside never do, random rays agree except for grazing cases)."""
+    from bodyfitting_b200.utils.mesh_grid_searcher import MeshGridSearcher
+    v, f = _scan()
+    rng = np.random.RandomState(4)
+    s = MeshGridSearcher(v, f)
+    lo, hi = v.min(0), v.max(0)
+    n = 4000
+    o = (rng.rand(n, 3) * (hi - lo) * 2.0 + lo - 0.5 * (hi - lo)).astype(np.float32)
+    d = rng.randn(n, 3).astype(np.float32)
+    d[:50] *= 1e-3                                                      # short direction vectors are still rays
+    hit = s.intersects_any(torch.from_numpy(o).cuda(), torch.from_numpy(d).cuda()).cpu().numpy()
+    ref, margin = gp.ray_any_bruteforce(o, d, v, f)
+    bad = hit != ref
+    print('hit fraction', ref.mean(), 'mismatches', int(bad.sum()), 'their margins', margin[bad])
+    assert hit.dtype == np.bool_ and 0.05 < ref.mean() < 0.95
+    assert (margin[bad] < 1e-4).all() and bad.sum() <= 4                 # only grazing rays may differ (fp32 vs fp64)
+    # from the centre every direction hits; from far outside pointing away nothing does; a zero direction never hits
+    c = np.zeros((256, 3), np.float32)
+    dd = rng.randn(256, 3).astype(np.float32)
+    assert bool(s.intersects_any(torch.from_numpy(c).cuda(), torch.from_numpy(dd).cuda()).all())
+    out = (dd / np.linalg.norm(dd, axis=1, keepdims=True) * 5.0).astype(np.float32)
+    assert not bool(s.intersects_any(torch.from_numpy(out).cuda(), torch.from_numpy(dd).cuda()).any())
+    assert bool(s.intersects_any(torch.from_numpy(out).cuda(), torch.from_numpy(-dd).cuda()).all())
+    assert not bool(s.intersects_any(torch.from_numpy(c).cuda(), torch.zeros(256, 3).cuda()).any())
+
+
+def test_inside_and_rays_vs_reference_kernel():
+    """The reference's own search_inside_mesh / search_intersect (oracle/_ref) on the same grid: identical answers away
+    from the surface / for non-grazing rays."""
+    mg = _load_reference_mesh_grid()
+    if mg is None:
+        pytest.skip('oracle/_ref not built')
+    from bodyfitting_b200.utils.mesh_grid_searcher import MeshGridSearcher
+    v, f = _scan()
+    s = MeshGridSearcher(v, f)
+    verts, faces = torch.from_numpy(v).cuda(), torch.from_numpy(f).cuda()
+    num = torch.tensor(s.num, dtype=torch.int32).cuda()
+    minmax = torch.from_numpy(np.asarray(s.minmax, dtype=np.float32)).cuda()
+    tri_num = torch.zeros(s.num[3], dtype=torch.int32).cuda()
+    tri_idx = torch.zeros(1, dtype=torch.int32).cuda()
+    mg.insert_grid_surface(verts, faces, minmax, num, s.step, tri_num, tri_idx)
+    q = _inside_queries(v, 4000, 6)
+    qd = torch.from_numpy(q).cuda()
+    signs = torch.zeros(len(q)).cuda()
+    mg.search_inside_mesh(qd, verts, faces, tri_num, tri_idx, num, minmax, s.step, signs)
+    torch.cuda.synchronize()
+    ours = s.inside_mesh(qd)
+    _, wn = gp.inside_bruteforce(q, v, f)
+    agree = (ours == signs).float().mean().item()
+    print('inside: agreement with the reference kernel %.4f' % agree)
+    assert agree > 0.995                                                 # the reference's 16-entry visited list / edge rules may differ
+    assert bool((ours.cpu().numpy() == np.where(np.abs(wn) > 0.5, 1.0, -1.0)).all())      # and where they differ we hold the exact answer
+    rng = np.random.RandomState(8)
+    lo, hi = v.min(0), v.max(0)
+    o = (rng.rand(4000, 3) * (hi - lo) * 2.0 + lo - 0.5 * (hi - lo)).astype(np.float32)
+    d = rng.randn(4000, 3).astype(np.float32)
+    od, dd = torch.from_numpy(o).cuda(), torch.from_numpy(d).cuda()
+    rhit = torch.zeros(len(o), dtype=torch.bool).cuda()
+    mg.search_intersect(od, dd, verts, faces, tri_num, tri_idx, num, minmax, s.step, rhit)
+    torch.cuda.synchronize()
+    ohit = s.intersects_any(od, dd)
+    agree = (ohit == rhit).float().mean().item()
+    print('rays: agreement with the reference kernel %.4f' % agree)
+    assert agree > 0.995

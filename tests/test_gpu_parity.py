@@ -225,19 +225,27 @@ def test_edge_cases_single_frame_single_view_and_all_missing(assets):
     assert np.array_equal(one['pose'], np.array(out['pose'])[0]) is False or True
 
 
-def test_pipelined_chunks_equal_single_batch(assets):
-    """Large batches are fitted in chunks whose device->host copies overlap the next chunk's fit; frames are
-    independent, so every output is bit-identical to the single-batch call (ragged chunk sizes included)."""
+def test_concurrent_parts_equal_single_batch(assets):
+    """Large batches are fitted as staggered parts on their own streams, each part's device->host copy overlapping the
+    later parts' fit; frames are independent, so every output is bit-identical to the single-batch call (ragged part
+    sizes included), for host (numpy) and device results."""
+    from bodyfitting_b200.engine import ConcurrentFitSession, staggered_ranges
     from bodyfitting_b200.smplify.smplify import SMPLify
+    assert [h - l for l, h in staggered_ranges(10000, 3)] == [2176, 3328, 4496]
+    assert staggered_ranges(1250, 3) == [(0, 1250)] and staggered_ranges(11, 3, min_part=1) == [(0, 2), (2, 6), (6, 11)]
     mt, nv, B, N = 'smplx', 8, 11, 8
     port = make_port(assets, mt)
     sc = make_scene(port, mt, B, nv, seed=33)
     outs = []
-    for chunks in (1, 2, 3):
+    for parts in (1, 2, 3):
         fit = SMPLify(smpl_type=mt, num_iters=N, gender='neutral', model_data=assets(mt), gmm=assets('gmm'),
-                      pipeline_chunks=chunks, pipeline_min_frames=1)
+                      concurrent_parts=parts, concurrent_min_part=1)
         o = fit((sc['init_betas'], sc['init_pose']), list(sc['c2ws']), list(sc['Ks']), sc['kp'], None, imsize=512)
+        assert isinstance(fit.session(B, nv, 512, True), ConcurrentFitSession) == (parts > 1)
         outs.append({k: np.array(v) for k, v in o.items()})
+        assert fit.last_trace.shape == (N, B)
+        od = fit((sc['init_betas'], sc['init_pose']), list(sc['c2ws']), list(sc['Ks']), sc['kp'], None, imsize=512, as_numpy=False)
+        assert np.array_equal(od['vertices'].cpu().numpy(), outs[-1]['vertices'])
     for o in outs[1:]:
         for k in ('pose', 'betas', 'global_orient', 'global_transl', 'scale', 'vertices', 'joints', 'full_pose'):
             assert np.array_equal(outs[0][k], o[k]), k

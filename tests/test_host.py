@@ -196,7 +196,9 @@ def test_pack_cameras_and_keypoints():
         ref = Ks[v] @ (w2c[:3] @ X)
         assert np.abs(M[v] @ X - ref).max() < 1e-4
     kp = np.random.RandomState(0).rand(2, 3, 135, 3).astype(np.float32)
-    out = pack_keypoints(kp, True).numpy()
+    out = pack_keypoints(kp, True)
+    assert out.shape == (2, 135, 3, 3) and out.is_contiguous()         # device layout is joint-major [B,K,Nv,3]
+    out = out.permute(0, 2, 1, 3).numpy()
     assert np.allclose(out[..., :25, 2], kp[..., :25, 2] ** 2)
     assert np.allclose(out[..., 30, 2], (kp[..., 25:46, 2] ** 2).sum(-1))
     assert np.allclose(out[..., 100, 2], (kp[..., 67:, 2] ** 2).sum(-1), rtol=1e-5)

@@ -9,7 +9,7 @@ import torch
 
 from bodyfitting_b200 import synthetic as syn
 from oracle import fit_port as fp, ref_harness as rh, smplx_port as sp
-from util import make_port, make_scene, relerr
+from util import gt_param_dict, make_port, make_scene, relerr
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 
@@ -50,6 +50,36 @@ def test_port_bit_exact_vs_verbatim_reference(assets, tmp_path, mt, nv):
     assert np.array_equal(np.asarray(trace), np.asarray(trp))
     for k in ('pose', 'betas', 'global_orient', 'global_transl', 'scale', 'joints', 'vertices', 'full_pose'):
         assert np.array_equal(res[k], resp[k]), k
+
+
+@pytest.mark.skipif(not rh.available(), reason='/root/reference not present (GPU box)')
+def test_mask_term_port_bit_exact_vs_verbatim_reference(assets, tmp_path):
+    """Silhouette term (use_mask=True, smplify/loss.py:73-130): the restatement run for one frame equals the verbatim
+    reference bit for bit (cv2.findContours adapted to OpenCV 4's return arity in the harness)."""
+    mt, nv, N = 'smpl', 4, 10
+    syn.write_data_dir(str(tmp_path / 'data'), seed=0, model_types=(mt,))
+    port = make_port(assets, mt)
+    sc = make_scene(port, mt, 1, nv, seed=12)
+    ev = port.loss_and_grads(gt_param_dict(sc['gt'], mt), sc['c2ws'], sc['Ks'], np.zeros((1, nv, 25, 3), np.float32))
+    mask_frames = [1, 3]
+    masks = syn.make_masks(ev['vertices'][0], port.faces, sc['c2ws'], sc['Ks'])[mask_frames]
+    views = syn.keypoints_to_openpose(sc['kp'][0], mt)
+    res, trace, terms, _ = rh.run_reference_fit(str(tmp_path), mt, sc['init_betas'][0], sc['init_pose'][0], sc['c2ws'],
+                                                sc['Ks'], views, num_iters=N, masks=masks, mask_frames=mask_frames)
+    resp, trp = port.fit_frame(sc['init_betas'][0], sc['init_pose'][0], sc['c2ws'], sc['Ks'], views, num_iters=N,
+                               masks=masks, mask_frames=mask_frames)
+    for k in ('pose', 'betas', 'global_orient', 'global_transl', 'scale', 'joints', 'vertices', 'full_pose'):
+        assert np.array_equal(res[k], resp[k]), k
+    # the harness records the keypoint objective alone; the port's trace includes 5 x the mask term from iteration N//3+1 on
+    assert np.array_equal(np.asarray(trace[:N // 3 + 1]), np.asarray(trp[:N // 3 + 1]))
+    assert all(t > 2 * r for t, r in zip(trp[N // 3 + 1:], trace[N // 3 + 1:]))
+    # batched restatement (what the GPU tests compare against): same first iterations of the mask phase; afterwards the
+    # objective's argmin / inside-outside switches make trajectories sensitive to the last bit
+    resb, trb, mls = port.fit_batched_mask(sc['init_betas'][:1], sc['init_pose'][:1], sc['c2ws'], sc['Ks'], sc['kp'][:1],
+                                           masks[None], mask_frames, num_iters=N)
+    assert mls is not None and (mls > 0).all()
+    assert relerr(trb[:N // 3 + 2, 0], np.asarray(trp[:N // 3 + 2])) < 1e-5
+    assert relerr(trb[:N // 3 + 3, 0], np.asarray(trp[:N // 3 + 3])) < 1e-3
 
 
 @pytest.mark.parametrize('mt,nv', [('smpl', 4), ('smplx', 8)])

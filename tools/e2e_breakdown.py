@@ -9,7 +9,7 @@ from bodyfitting_b200.engine import pack_cameras, pack_keypoints
 from bodyfitting_b200.smplify.smplify import SMPLify
 
 F = 10000
-fit = SMPLify(smpl_type='smplx', num_iters=100, gender='neutral', model_data=syn.make_model('smplx', 0), gmm=syn.make_gmm(0), pipeline_chunks=1)
+fit = SMPLify(smpl_type='smplx', num_iters=100, gender='neutral', model_data=syn.make_model('smplx', 0), gmm=syn.make_gmm(0), concurrent_parts=1)
 pm = fit.model
 wl = bench.build_workload(pm, F, seed=100)
 args = ((wl['init_betas'], wl['init_pose']), list(wl['c2ws']), list(wl['Ks']), wl['kp'], None)

@@ -19,7 +19,7 @@ ap.add_argument('--frames', type=int, default=10000)
 ap.add_argument('--iters', type=int, default=3)
 ap.add_argument('--dense', action='store_true', help='also run the SMPL 1024-frame dense LBS operator fwd/bwd')
 a = ap.parse_args()
-fit = SMPLify(smpl_type='smplx', num_iters=a.iters, gender='neutral', model_data=syn.make_model('smplx', 0), gmm=syn.make_gmm(0))
+fit = SMPLify(smpl_type='smplx', num_iters=a.iters, gender='neutral', model_data=syn.make_model('smplx', 0), gmm=syn.make_gmm(0), concurrent_parts=1)
 pm = fit.model
 wl = bench.build_workload(pm, a.frames, seed=100)
 sess = fit.session(a.frames, 8, 512, True)
