@@ -59,6 +59,12 @@ class BfSmpld(C.Structure):
         [('reg_scale', C.c_float), ('V', _i32), ('F', _i32), ('iter', _i32)]
 
 
+class BfMask(C.Structure):
+    _fields_ = [(n, _fp) for n in ('masks', 'cams', 'contour', 'cptr', 'cown', 'uv', 'near_q', 'cdist', 'cw', 'dPw', 'part',
+                                   'mask_loss')] + \
+        [(n, _i32) for n in ('Nm', 'H', 'W', 'Nq', 'stride', 'total')] + [('imsize', C.c_float), ('epsilon', C.c_float)]
+
+
 class BodyfitError(RuntimeError):
     pass
 
@@ -83,7 +89,7 @@ def lib():
     L.bf_sizeof.argtypes = [C.c_int]
     if L.bf_abi_version() != ABI_VERSION:
         raise BodyfitError('ABI mismatch: library %d, binding %d -- rebuild' % (L.bf_abi_version(), ABI_VERSION))
-    for i, st in enumerate((BfVSet, BfModel, BfFrames)):
+    for i, st in enumerate((BfVSet, BfModel, BfFrames, BfGrid, BfSmpld, BfMask)):
         if L.bf_sizeof(i) != C.sizeof(st):
             raise BodyfitError('struct layout mismatch for %s: C %d, ctypes %d' % (st.__name__, L.bf_sizeof(i), C.sizeof(st)))
     pm, pf, vp, ci = C.POINTER(BfModel), C.POINTER(BfFrames), C.c_void_p, C.c_int
@@ -112,6 +118,7 @@ def lib():
         'bf_grid_inside': [pg, fp, i32, fp, vp], 'bf_grid_intersects_any': [pg, fp, fp, i32, fp, vp],
         'bf_smpld_step': [pg, ps, vp], 'bf_smpld_run': [pg, ps, i32, vp],
         'bf_pc_loss': [pg, pm, pf, fl, fl, fp, fp, fp, fp, vp],
+        'bf_mask_loss': [pm, pf, C.POINTER(BfMask), fl, vp],
     })
     for name, at in ops.items():
         fn = getattr(L, name)
@@ -127,6 +134,7 @@ EXPORTED = ['bf_abi_version', 'bf_sizeof', 'bf_last_error', 'bf_check_device', '
 
 
 EXPORTED_GRID = ['bf_grid_count', 'bf_grid_fill', 'bf_grid_nearest', 'bf_grid_inside', 'bf_grid_intersects_any', 'bf_smpld_step', 'bf_smpld_run', 'bf_pc_loss']
+EXPORTED_MASK = ['bf_mask_loss']
 EXPORTED_OPS = ['bf_op_project', 'bf_op_project_backward', 'bf_op_gmof', 'bf_op_gmof_backward', 'bf_op_reprojection',
                 'bf_op_keypoints_world', 'bf_op_angle_prior', 'bf_op_gmm_pose']
 

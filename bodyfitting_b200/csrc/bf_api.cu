@@ -12,6 +12,7 @@
 #include "bf_frame.cuh"
 #include "bf_ops.cuh"
 #include "bf_grid.cuh"
+#include "bf_mask.cuh"
 #include "../../include/bodyfit_b200_ops.h"
 #include "bf_blend_tc.cuh"
 
@@ -47,7 +48,17 @@ static int check_vset(const BfVSet* vs, const BfFrames* f) {
 extern "C" {
 
 int bf_abi_version(void) { return BF_ABI_VERSION; }
-int bf_sizeof(int which) { return which == 0 ? (int)sizeof(BfVSet) : which == 1 ? (int)sizeof(BfModel) : (int)sizeof(BfFrames); }
+int bf_sizeof(int which) {
+    switch (which) {
+        case 0: return (int)sizeof(BfVSet);
+        case 1: return (int)sizeof(BfModel);
+        case 2: return (int)sizeof(BfFrames);
+        case 3: return (int)sizeof(BfGrid);
+        case 4: return (int)sizeof(BfSmpld);
+        case 5: return (int)sizeof(BfMask);
+        default: return -1;
+    }
+}
 const char* bf_last_error(void) { return g_err; }
 
 int bf_check_device(void) {
@@ -581,6 +592,29 @@ __global__ void __launch_bounds__(256) k_pc_world_bwd(const float* __restrict__ 
         grad[(size_t)b * NP + threadIdx.x] += s;
     }
     if (threadIdx.x == 0) { loss[b] += weight * scale * nrm; if (pc_loss) pc_loss[b] = scale * nrm; }
+}
+
+int bf_mask_loss(const BfModel* m, const BfFrames* f, const BfMask* k, float weight, void* stream) {
+    int rc = check_model(m, f); if (rc) return rc;
+    const int V = m->full.n;
+    BF_REQUIRE(k && k->masks && k->cams && k->contour && k->cptr && k->cown && k->uv && k->near_q && k->cdist && k->cw && k->dPw &&
+               k->part, "mask buffers missing");
+    BF_REQUIRE(k->Nm > 0 && k->H > 0 && k->W > 0 && k->stride > 0 && k->Nq == (V + k->stride - 1) / k->stride && k->total >= 0 &&
+               k->imsize > 0.f, "bad mask geometry");
+    BF_REQUIRE(f->verts && f->dverts && f->grad && f->loss && f->ld_v >= 3 * V, "all-vertex frame buffers missing");
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t n = (size_t)f->B * k->Nm * k->Nq;
+    k_mask_project<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(*f, *k, m->NP);
+    BF_LAUNCH_CHECK();
+    if (k->total > 0) {
+        k_mask_nearest<<<(k->total + 7) / 8, 256, 0, s>>>(*k, k->total);
+        BF_LAUNCH_CHECK();
+    }
+    k_mask_vertex<<<(unsigned)(((size_t)f->B * k->Nq + 127) / 128), 128, 0, s>>>(*f, *k, m->NP);
+    BF_LAUNCH_CHECK();
+    k_mask_finish<<<f->B, 256, 0, s>>>(*f, *k, m->NP, weight);
+    BF_LAUNCH_CHECK();
+    return BF_OK;
 }
 
 int bf_pc_loss(const BfGrid* g, const BfModel* m, const BfFrames* f, float scale, float weight, float* Pw,

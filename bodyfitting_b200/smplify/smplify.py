@@ -7,7 +7,8 @@ Extensions over the reference (which supports one frame per call, smplify.py:189
 [B,Nv,K,3] array in model joint order -- each frame being an independent fit with its
 own Adam state, exactly as B separate reference calls.
 
-Not implemented here (SURVEY.md 8f "next" rows): ``use_mask`` (silhouette term).
+``use_mask=True`` (silhouette term) and ``use_mesh=True`` (point-to-scan term, SMPL+D) run the all-vertex loop
+(``_fit_dense``); the keypoint-only objective runs the fused active-set loop.
 """
 import os
 import pickle
@@ -85,10 +86,10 @@ class SMPLify(object):
     def __call__(self, net_output, c2ws, Ks, keypoints, output_folder=None, use_mask=False, masks=None,
                  use_frames=[0], mask_frames=[0], keyframe=6, imsize=512, use_mesh=False, meshfile=None,
                  displacement=False, return_vertices=True, as_numpy=True):
-        if use_mask:
-            raise NotImplementedError('silhouette term (smplify/loss.py:85-130) is not part of this build')
-        if use_mesh:
-            return self._fit_to_scan(net_output, c2ws, Ks, keypoints, imsize, meshfile, displacement, as_numpy)
+        if use_mask or use_mesh:
+            return self._fit_dense(net_output, c2ws, Ks, keypoints, imsize, as_numpy, use_mesh=use_mesh, meshfile=meshfile,
+                                   displacement=displacement, use_mask=use_mask, masks=masks, use_frames=use_frames,
+                                   mask_frames=mask_frames)
         m, dev = self.model, self.device
         init_betas, init_poses, kp = self._pack_inputs(net_output, keypoints)
         B, Nv = kp.shape[0], kp.shape[1]
@@ -159,36 +160,51 @@ class SMPLify(object):
         return out
 
     # ------------------------------------------------------------------------------------------
-    def _fit_to_scan(self, net_output, c2ws, Ks, keypoints, imsize, meshfile, displacement, as_numpy):
-        """``use_mesh=True`` (smplify.py:146-156,205-210,228-247): keypoint objective + 5 x point-to-scan
-        term from iteration N//3+1 on, on ALL vertices (dense backward), then the optional SMPL+D
-        displacement loop.  ``meshfile`` = path of an OBJ or a (vertices, faces) pair."""
+    def _fit_dense(self, net_output, c2ws, Ks, keypoints, imsize, as_numpy, use_mesh=False, meshfile=None, displacement=False,
+                   use_mask=False, masks=None, use_frames=None, mask_frames=None):
+        """The objectives that need ALL vertices in every iteration (dense LBS backward):
+        ``use_mesh=True`` (smplify.py:146-156,205-210,228-247): keypoints + 5 x point-to-scan term from iteration N//3+1 on,
+        then the optional SMPL+D displacement loop; ``meshfile`` = path of an OBJ or a (vertices, faces) pair;
+        ``use_mask=True`` (smplify.py:137-144,196-199,210): keypoints + 5 x silhouette term from iteration N//3+1 on;
+        ``masks`` = [Nm,H,W] (one frame) or [B,Nm,H,W] uint8 images of the views ``mask_frames`` (ids looked up in
+        ``use_frames``, the ids of the cameras passed in, :141-142)."""
         import ctypes as C
         from .. import _lib
         from ..engine import FrameBuffers, _stream
-        from ..utils.io_utils import load_obj_mesh
-        from ..utils.mesh_grid_searcher import MeshGridSearcher
-        from .smpld import DisplacementFitter
         m, dev, N = self.model, self.device, int(self.num_iters)
-        scan_verts, scan_faces = load_obj_mesh(meshfile) if isinstance(meshfile, str) else meshfile
-        scan_verts, scan_faces = np.asarray(scan_verts), np.asarray(scan_faces)
-        tris = scan_verts[scan_faces]
-        face_norms = np.cross(tris[:, 1] - tris[:, 0], tris[:, 2] - tris[:, 0])
-        scan_height = float((scan_verts.max(0) - scan_verts.min(0))[1])
-        constant_scale = scan_height / 1.7                                            # smplify.py:156
-        searcher = MeshGridSearcher(verts=scan_verts, faces=scan_faces, device=dev)
         init_betas, init_poses, kp = self._pack_inputs(net_output, keypoints)
         B, Nv = kp.shape[0], kp.shape[1]
+        constant_scale = K.CONSTANT_SCALE_NO_SCAN
+        searcher = scan_height = None
+        if use_mesh:
+            from ..utils.io_utils import load_obj_mesh
+            from ..utils.mesh_grid_searcher import MeshGridSearcher
+            scan_verts, scan_faces = load_obj_mesh(meshfile) if isinstance(meshfile, str) else meshfile
+            scan_verts, scan_faces = np.asarray(scan_verts), np.asarray(scan_faces)
+            tris = scan_verts[scan_faces]
+            face_norms = np.cross(tris[:, 1] - tris[:, 0], tris[:, 2] - tris[:, 0])
+            scan_height = float((scan_verts.max(0) - scan_verts.min(0))[1])
+            constant_scale = scan_height / 1.7                                            # smplify.py:156
+            searcher = MeshGridSearcher(verts=scan_verts, faces=scan_faces, device=dev)
         fb = FrameBuffers(m, B, full=True, Nv=Nv, n_trace=N, imsize=imsize, constant_scale=constant_scale)
         kp_dev = self._h2d('kp', kp)
         poses_dev, betas_dev = self._h2d('poses', init_poses), self._h2d('betas', init_betas)
         fb.bind('kp', pack_keypoints(kp_dev, self.use_hand_face))
-        fb.bind('cams', self._h2d('cams', torch.from_numpy(pack_cameras(c2ws, Ks))))
+        cams_np = pack_cameras(c2ws, Ks)
+        fb.bind('cams', self._h2d('cams', torch.from_numpy(cams_np)))
         fb.t['theta'].copy_(m.pack_theta(poses_dev[:, :3], poses_dev[:, 3:3 + m.nbody], betas_dev))
-        Pw = torch.empty(B, m.V, 3, device=dev)
-        near = torch.empty(B, m.V, 3, device=dev)
-        near_f = torch.empty(B, m.V, dtype=torch.int32, device=dev)
-        pc = torch.zeros(B, device=dev)
+        sil = None
+        if use_mask:
+            from .mask import SilhouetteTerm
+            use_frames = list(use_frames) if use_frames is not None and len(use_frames) == Nv else list(range(Nv))
+            idx = [use_frames.index(f) for f in mask_frames]
+            sil = SilhouetteTerm(m, masks, cams_np[idx], imsize=imsize, device=dev)
+            assert sil.B == B, 'masks for %d frames, parameters for %d' % (sil.B, B)
+        if use_mesh:
+            Pw = torch.empty(B, m.V, 3, device=dev)
+            near = torch.empty(B, m.V, 3, device=dev)
+            near_f = torch.empty(B, m.V, dtype=torch.int32, device=dev)
+            pc = torch.zeros(B, device=dev)
         L = _lib.lib()
         for i in range(N):
             fb.struct.iter = i
@@ -196,8 +212,11 @@ class SMPLify(object):
             fb.call('bf_skin_forward', 1)
             fb.call('bf_keypoint_loss', 1)
             if i > (N // 3):
-                _lib.check(L.bf_pc_loss(C.byref(searcher.grid), m.struct, fb.struct, float(imsize / scan_height), 5.0,
-                                        Pw.data_ptr(), near.data_ptr(), near_f.data_ptr(), pc.data_ptr(), _stream()), 'bf_pc_loss')
+                if sil is not None:
+                    sil.add(fb, 5.0)
+                if use_mesh:
+                    _lib.check(L.bf_pc_loss(C.byref(searcher.grid), m.struct, fb.struct, float(imsize / scan_height), 5.0,
+                                            Pw.data_ptr(), near.data_ptr(), near_f.data_ptr(), pc.data_ptr(), _stream()), 'bf_pc_loss')
             fb.call('bf_gmm_prior')
             if i == N - 1:
                 theta_prev = fb.t['theta'].clone()
@@ -210,9 +229,16 @@ class SMPLify(object):
         out = dict(vertices=verts, joints=(fb.t['joints'][:, :m.K_out] + t) * s * constant_scale, pose=sn['body_pose'],
                    betas=sn['betas'], global_orient=sn['global_orient'], global_transl=sn['transl'] * sn['scale'],
                    scale=sn['scale'], full_pose=fb.t['full_pose'])
-        self.last_trace, self.last_loss_terms, self.last_pc_loss = fb.t['trace'], fb.t['loss_terms'], pc
+        if m.is_smplx:
+            out.update(leye_pose=sn['leye_pose'], reye_pose=sn['reye_pose'],
+                       left_hand_pose=sn['left_hand_pose'], right_hand_pose=sn['right_hand_pose'])
+        self.last_trace, self.last_loss_terms = fb.t['trace'], fb.t['loss_terms']
+        self.last_pc_loss = pc if use_mesh else None
+        self.last_mask_loss = sil.mask_loss if sil is not None else None
         if displacement:
+            assert use_mesh, 'the displacement fit needs a scan (use_mesh=True)'
             assert B == 1, 'the displacement fit takes one subject per call (smplify.py:229-247)'
+            from .smpld import DisplacementFitter
             fitter = DisplacementFitter(searcher, face_norms, m.faces, m.V, constant_scale, device=dev)
             disp, dtrace = fitter.run(verts[0], N)
             out['displacement'] = disp[None]

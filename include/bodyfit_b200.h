@@ -150,7 +150,7 @@ typedef struct BfFrames {
 } BfFrames;
 
 int         bf_abi_version(void);
-int         bf_sizeof(int which);                        /* 0 BfVSet, 1 BfModel, 2 BfFrames: layout check for FFI bindings */
+int         bf_sizeof(int which);                        /* 0 BfVSet, 1 BfModel, 2 BfFrames, 3 BfGrid, 4 BfSmpld, 5 BfMask: layout check for FFI bindings */
 const char* bf_last_error(void);
 int         bf_check_device(void);                       /* BF_OK iff current device is sm_100 */
 

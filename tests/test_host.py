@@ -219,15 +219,15 @@ def test_openpose_dict_roundtrip():
 def test_library_loads_and_exports_every_declared_symbol():
     L = _lib.lib()
     hdr = open(os.path.join(ROOT, 'include', 'bodyfit_b200.h')).read() + open(os.path.join(ROOT, 'include', 'bodyfit_b200_ops.h')).read() + \
-        open(os.path.join(ROOT, 'include', 'bodyfit_b200_grid.h')).read()
+        open(os.path.join(ROOT, 'include', 'bodyfit_b200_grid.h')).read() + open(os.path.join(ROOT, 'include', 'bodyfit_b200_mask.h')).read()
     declared = set(re.findall(r'^(?:int|const char\*)\s+(bf_[a-z0-9_]+)\s*\(', hdr, re.M))
     assert declared, 'no declarations parsed'
     for name in sorted(declared):
         assert hasattr(L, name), 'symbol %s declared in the header but not exported' % name
-    assert declared == set(_lib.EXPORTED) | set(_lib.EXPORTED_OPS) | set(_lib.EXPORTED_GRID)
+    assert declared == set(_lib.EXPORTED) | set(_lib.EXPORTED_OPS) | set(_lib.EXPORTED_GRID) | set(_lib.EXPORTED_MASK)
     assert L.bf_abi_version() == _lib.ABI_VERSION
-    for i, st in enumerate((_lib.BfVSet, _lib.BfModel, _lib.BfFrames)):
-        assert L.bf_sizeof(i) == ctypes.sizeof(st)
+    for i, st in enumerate((_lib.BfVSet, _lib.BfModel, _lib.BfFrames, _lib.BfGrid, _lib.BfSmpld, _lib.BfMask)):
+        assert L.bf_sizeof(i) == ctypes.sizeof(st), st.__name__
 
 
 def test_no_gpu_means_loud_failure():
