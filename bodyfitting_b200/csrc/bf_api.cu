@@ -239,6 +239,22 @@ int bf_temporal_prior(const BfModel* m, const BfFrames* f, void* stream) {
 int bf_gmm_prior(const BfModel* m, const BfFrames* f, void* stream) {
     int rc = check_model(m, f); if (rc) return rc;
     BF_REQUIRE(f->gmm_grad && f->gmm_loss, "gmm_grad / gmm_loss is null");
+    if ((f->flags & BF_F_TC) && m->gmm_bt_hi && m->gmm_bt_lo && f->gmm_ws && (m->n_gmm * GM_LD) % TC_BN1 == 0) {
+        // tensor-core form: pack [pose | 1] -> one 3xTF32 GEMM against [P_sym,m | -P_sym,m mu_m] -> per-frame select
+        BF_REQUIRE(m->gmm_mean && m->gmm_logw && m->n_gmm > 0, "GMM tables missing");
+        cudaStream_t s = (cudaStream_t)stream;
+        const int ny = m->n_gmm * GM_LD, nb = theta_layout(m->is_smplx).nbody;
+        float* Y = f->gmm_ws;
+        float* x_hi = f->gmm_ws + (size_t)f->B * ny;
+        float* x_lo = x_hi + (size_t)f->B * GM_KG;
+        const float wp = f->w_pose * f->w_pose;
+        k_gmm_pack<<<(unsigned)(((size_t)f->B * GM_KG + 255) / 256), 256, 0, s>>>(f->theta + 7, m->NP, nb, f->B, x_hi, x_lo);
+        BF_LAUNCH_CHECK();
+        rc = bf_gemm_forward_tc(x_hi, x_lo, m->gmm_bt_hi, m->gmm_bt_lo, f->B, GM_KG, ny, ny / 3, Y, ny, s); if (rc) return rc;
+        k_gmm_select<<<(f->B + 3) / 4, 128, 0, s>>>(*m, f->theta + 7, m->NP, nb, f->B, Y, ny, wp, f->gmm_grad, f->gmm_loss);
+        BF_LAUNCH_CHECK();
+        return BF_OK;
+    }
     return launch_gmm(m, f->theta + 7, m->NP, theta_layout(m->is_smplx).nbody, f->B, f->w_pose * f->w_pose,
                       f->gmm_grad, f->gmm_loss, (cudaStream_t)stream);
 }

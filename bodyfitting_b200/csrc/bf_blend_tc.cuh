@@ -458,14 +458,17 @@ static inline bool bf_tc_ready_bwd(const BfVSet* vs, const BfFrames* f) {
     return (f->flags & BF_F_TC) && vs->Bm_hi && vs->Bm_lo && f->dvp_hi && f->dvp_lo;
 }
 
-// v_posed[B, ld_v] = pf @ Bm on the tensor cores (dst = f->vposed, or any [B, ld_v] buffer)
-static int bf_blend_forward_tc(const BfModel* m, const BfVSet* vs, const BfFrames* f, float* dst, cudaStream_t s) {
+// dst[B, ld_dst] (first 3 * n_verts columns) = A[B, Kp] @ Bt[ldn, Kp]^T on the tensor cores, operands pre-split for 3xTF32.
+// Used for the blend shapes (A = pose features, Bt = blend matrix) and for the GMM prior (A = [pose | 1], Bt = precisions).
+static int bf_gemm_forward_tc(const float* a_hi_p, const float* a_lo_p, const float* bt_hi_p, const float* bt_lo_p, int B, int Kp,
+                              int ldn, int n_verts, float* dst, int ld_dst, cudaStream_t s) {
     CUtensorMap a_hi, a_lo, b_hi, b_lo;
     int rc;
-    if ((rc = bf_make_map(&a_hi, f->pf_hi, f->B, m->Kp, m->Kp, TC_BM))) return rc;
-    if ((rc = bf_make_map(&a_lo, f->pf_lo, f->B, m->Kp, m->Kp, TC_BM))) return rc;
-    if ((rc = bf_make_map(&b_hi, vs->Bt_hi, vs->ldn, m->Kp, m->Kp, TC_BN1))) return rc;
-    if ((rc = bf_make_map(&b_lo, vs->Bt_lo, vs->ldn, m->Kp, m->Kp, TC_BN1))) return rc;
+    if (Kp % TC_BK != 0 || ldn % 3 != 0) { bf_set_error("bf_gemm_forward_tc: Kp=%d / ldn=%d not tileable", Kp, ldn); return BF_EINVAL; }
+    if ((rc = bf_make_map(&a_hi, a_hi_p, B, Kp, Kp, TC_BM))) return rc;
+    if ((rc = bf_make_map(&a_lo, a_lo_p, B, Kp, Kp, TC_BM))) return rc;
+    if ((rc = bf_make_map(&b_hi, bt_hi_p, ldn, Kp, Kp, TC_BN1))) return rc;
+    if ((rc = bf_make_map(&b_lo, bt_lo_p, ldn, Kp, Kp, TC_BN1))) return rc;
     const size_t smem = 1024 + TC_STAGES * (2 * TC_BM * TC_ROWB + 2 * TC_BN1 * TC_ROWB) + TC_EPI_WARPS * TC_ST_FLOATS * 4 + 128;
     static bool attr = false;
     static int num_sms = 0;
@@ -477,12 +480,17 @@ static int bf_blend_forward_tc(const BfModel* m, const BfVSet* vs, const BfFrame
         cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
         attr = true;
     }
-    const int tn = (vs->ldn + TC_BN1 - 1) / TC_BN1, tm = (f->B + TC_BM - 1) / TC_BM;
+    const int tn = (ldn + TC_BN1 - 1) / TC_BN1, tm = (B + TC_BM - 1) / TC_BM;
     const int tiles = tn * tm;
     const int grid = tiles < num_sms ? tiles : num_sms;          // persistent: one CTA per SM
-    k_blend_fwd_tc<<<grid, 64 + 32 * TC_EPI_WARPS, smem, s>>>(a_hi, a_lo, b_hi, b_lo, vs->n, m->Kp, dst, f->B, f->ld_v, tm, tn, tiles);
+    k_blend_fwd_tc<<<grid, 64 + 32 * TC_EPI_WARPS, smem, s>>>(a_hi, a_lo, b_hi, b_lo, n_verts, Kp, dst, B, ld_dst, tm, tn, tiles);
     BF_LAUNCH_CHECK();
     return BF_OK;
+}
+
+// v_posed[B, ld_v] = pf @ Bm (dst = f->vposed, or any [B, ld_v] buffer)
+static int bf_blend_forward_tc(const BfModel* m, const BfVSet* vs, const BfFrames* f, float* dst, cudaStream_t s) {
+    return bf_gemm_forward_tc(f->pf_hi, f->pf_lo, vs->Bt_hi, vs->Bt_lo, f->B, m->Kp, vs->ldn, vs->n, dst, f->ld_v, s);
 }
 
 static int bf_blend_backward_tc(const BfModel* m, const BfVSet* vs, const BfFrames* f, cudaStream_t s) {

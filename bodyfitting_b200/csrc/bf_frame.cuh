@@ -135,55 +135,57 @@ __global__ void __launch_bounds__(FR_THREADS, 4) k_frame_loss_bwd(BfModel m, BfV
         jq[k * 3] = x[0] + tx; jq[k * 3 + 1] = x[1] + ty; jq[k * 3 + 2] = x[2] + tz;
     }
     __syncthreads();
-    // (joint, view) pairs: G lanes share a joint and split its views, then reduce over the G lanes
-    int G = 1;
-    while (G * 2 <= Nv && G < 8) G *= 2;
-    const int sub = lane & (G - 1);
-    const int jpw = 32 / G;                                  // joints per warp per pass
+    // one thread per joint, its views in sequence: no cross-lane reduction, world coordinates computed once per joint,
+    // and the joint-major keypoint rows ([B,K,Nv,3]) are read as 16-byte vectors, four views at a time
     float acc5[5] = {0.f, 0.f, 0.f, 0.f, 0.f};               // loss, d/d transl (3), d/d scale
-    for (int k0 = 0; k0 < K; k0 += jpw * (FR_THREADS / 32)) {
-        if (k0 + warp * jpw >= K) break;                     // warp-uniform: nothing left for this warp (last pass)
-        const int k = k0 + warp * jpw + lane / G;
-        const bool kv = k < K;
-        const int kk = kv ? k : K - 1;
-        const float qx = jq[kk * 3], qy = jq[kk * 3 + 1], qz = jq[kk * 3 + 2];
+    const bool vec4 = (Nv & 3) == 0;
+    for (int k = t; k < K; k += FR_THREADS) {
+        const float qx = jq[k * 3], qy = jq[k * 3 + 1], qz = jq[k * 3 + 2];
         const float X = qx * sc * cs, Y = qy * sc * cs, Z = qz * sc * cs;
         float g0 = 0.f, g1 = 0.f, g2 = 0.f, ls = 0.f;
-        for (int v = sub; v < Nv; v += G) {
-            const float* kp = f.kp + (((size_t)b * K + kk) * Nv + v) * 3;
-            const float kx = kp[0], ky = kp[1], wgt = kp[2];
-            const float* M = cam + v * 12;
-            const float p0 = M[0] * X + M[1] * Y + M[2] * Z + M[3];
-            const float p1 = M[4] * X + M[5] * Y + M[6] * Z + M[7];
-            const float p2 = M[8] * X + M[9] * Y + M[10] * Z + M[11];
-            // three correctly-rounded reciprocals instead of seven IEEE divisions: 1/p2, 1/(s^2+rx^2), 1/(s^2+ry^2)
-            const float iz = __frcp_rn(p2);
-            const float u = p0 * iz, w_ = p1 * iz;
-            const float rx = (kx - u) * icoef, ry = (ky - w_) * icoef;
-            const float rx2 = rx * rx, ry2 = ry * ry;
-            const float ix = __frcp_rn(s2 + rx2), iy = __frcp_rn(s2 + ry2);
-            ls += wgt * (s2 * rx2 * ix + s2 * ry2 * iy);
-            const float du = wgt * (2.0f * s2 * s2 * rx * ix * ix) * (-icoef);
-            const float dw = wgt * (2.0f * s2 * s2 * ry * iy * iy) * (-icoef);
-            const float dp0 = du * iz, dp1 = dw * iz, dp2 = -(du * u + dw * w_) * iz;
-            g0 += M[0] * dp0 + M[4] * dp1 + M[8] * dp2;
-            g1 += M[1] * dp0 + M[5] * dp1 + M[9] * dp2;
-            g2 += M[2] * dp0 + M[6] * dp1 + M[10] * dp2;
+        const float* kpr = f.kp + ((size_t)b * K + k) * Nv * 3;
+        for (int v0 = 0; v0 < Nv; v0 += 4) {
+            float kv[12];
+            if (vec4) {
+                const float4* p4 = reinterpret_cast<const float4*>(kpr + v0 * 3);
+                const float4 a = p4[0], bq = p4[1], c = p4[2];
+                kv[0] = a.x; kv[1] = a.y; kv[2] = a.z; kv[3] = a.w; kv[4] = bq.x; kv[5] = bq.y; kv[6] = bq.z; kv[7] = bq.w;
+                kv[8] = c.x; kv[9] = c.y; kv[10] = c.z; kv[11] = c.w;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 12; ++i) kv[i] = (v0 * 3 + i < Nv * 3) ? kpr[v0 * 3 + i] : 0.f;
+            }
+#pragma unroll
+            for (int u4 = 0; u4 < 4; ++u4) {
+                const int v = v0 + u4;
+                if (v >= Nv) break;
+                const float kx = kv[3 * u4], ky = kv[3 * u4 + 1], wgt = kv[3 * u4 + 2];
+                const float4* M4 = reinterpret_cast<const float4*>(cam + v * 12);
+                const float4 m0 = M4[0], m1 = M4[1], m2 = M4[2];
+                const float p0 = m0.x * X + m0.y * Y + m0.z * Z + m0.w;
+                const float p1 = m1.x * X + m1.y * Y + m1.z * Z + m1.w;
+                const float p2 = m2.x * X + m2.y * Y + m2.z * Z + m2.w;
+                // three correctly-rounded reciprocals instead of seven IEEE divisions: 1/p2, 1/(s^2+rx^2), 1/(s^2+ry^2)
+                const float iz = __frcp_rn(p2);
+                const float u = p0 * iz, w_ = p1 * iz;
+                const float rx = (kx - u) * icoef, ry = (ky - w_) * icoef;
+                const float rx2 = rx * rx, ry2 = ry * ry;
+                const float ix = __frcp_rn(s2 + rx2), iy = __frcp_rn(s2 + ry2);
+                ls += wgt * (s2 * rx2 * ix + s2 * ry2 * iy);
+                const float du = wgt * (2.0f * s2 * s2 * rx * ix * ix) * (-icoef);
+                const float dw = wgt * (2.0f * s2 * s2 * ry * iy * iy) * (-icoef);
+                const float dp0 = du * iz, dp1 = dw * iz, dp2 = -(du * u + dw * w_) * iz;
+                g0 += m0.x * dp0 + m1.x * dp1 + m2.x * dp2;
+                g1 += m0.y * dp0 + m1.y * dp1 + m2.y * dp2;
+                g2 += m0.z * dp0 + m1.z * dp1 + m2.z * dp2;
+            }
         }
-        for (int o = G >> 1; o > 0; o >>= 1) {               // fixed butterfly over the G view lanes
-            g0 += __shfl_xor_sync(0xffffffffu, g0, o);
-            g1 += __shfl_xor_sync(0xffffffffu, g1, o);
-            g2 += __shfl_xor_sync(0xffffffffu, g2, o);
-            ls += __shfl_xor_sync(0xffffffffu, ls, o);
-        }
-        if (kv && sub == 0) {
-            g0 *= invNv; g1 *= invNv; g2 *= invNv;
-            const float k0s = sc * cs;
-            gx[k * 3] = g0 * k0s; gx[k * 3 + 1] = g1 * k0s; gx[k * 3 + 2] = g2 * k0s;
-            acc5[0] += ls;
-            acc5[1] += g0 * k0s; acc5[2] += g1 * k0s; acc5[3] += g2 * k0s;
-            acc5[4] += (g0 * qx + g1 * qy + g2 * qz) * cs;
-        }
+        g0 *= invNv; g1 *= invNv; g2 *= invNv;
+        const float k0s = sc * cs;
+        gx[k * 3] = g0 * k0s; gx[k * 3 + 1] = g1 * k0s; gx[k * 3 + 2] = g2 * k0s;
+        acc5[0] += ls;
+        acc5[1] += g0 * k0s; acc5[2] += g1 * k0s; acc5[3] += g2 * k0s;
+        acc5[4] += (g0 * qx + g1 * qy + g2 * qz) * cs;
     }
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
@@ -246,19 +248,21 @@ __global__ void __launch_bounds__(FR_THREADS, 4) k_frame_loss_bwd(BfModel m, BfV
     if (vs.n_nz < J)
         for (int i = t; i < J * 12; i += FR_THREADS) dAb[i] = 0.f;
     __syncthreads();
-    // 8 lanes per joint (skinning lists are short), 4 joints per warp at a time; the 12 (padded 16)
-    // partial sums are reduced over the 8 lanes with a multi-value butterfly: 14 shuffles per 4 joints
+    // 4 lanes per joint (the live skinning lists are short), 8 joints per warp at a time; the 12 (padded 16) partial sums
+    // are reduced over the 4 lanes with a multi-value butterfly (8 + 4 shuffles), after which lane l of the group holds
+    // elements 4l .. 4l+3 = one row of dA[j] -> one 16-byte store
     const int32_t* ljp = vs.lj_ptr + (size_t)row * (vs.n_nz + 1);
-    for (int jn0 = 0; jn0 < vs.n_nz; jn0 += 4 * (FR_THREADS / 32)) {
-        const int jn = jn0 + warp * 4 + (lane >> 3);
+    for (int jn0 = 0; jn0 < vs.n_nz; jn0 += 8 * (FR_THREADS / 32)) {
+        if (jn0 + warp * 8 >= vs.n_nz) break;                  // warp-uniform
+        const int jn = jn0 + warp * 8 + (lane >> 2);
         const bool jv_ = jn < vs.n_nz;
         const int j = jv_ ? __ldg(vs.jv_nz + jn) : 0;
-        const int sl = lane & 7;
+        const int sl = lane & 3;
         float acc[16];
 #pragma unroll
         for (int e = 0; e < 16; ++e) acc[e] = 0.f;
         const int e0 = jv_ ? __ldg(ljp + jn) : 0, e1 = jv_ ? __ldg(ljp + jn + 1) : 0;
-        for (int e = e0 + sl; e < e1; e += 8) {
+        for (int e = e0 + sl; e < e1; e += 4) {
             const int v = __ldg(vs.lj_vid + e);
             const float w = __ldg(vs.lj_w + e);
             const float gx_ = w * dv[3 * v], gy_ = w * dv[3 * v + 1], gz_ = w * dv[3 * v + 2];
@@ -267,27 +271,20 @@ __global__ void __launch_bounds__(FR_THREADS, 4) k_frame_loss_bwd(BfModel m, BfV
             acc[4] = fmaf(gy_, px, acc[4]); acc[5] = fmaf(gy_, py, acc[5]); acc[6] = fmaf(gy_, pz, acc[6]); acc[7] += gy_;
             acc[8] = fmaf(gz_, px, acc[8]); acc[9] = fmaf(gz_, py, acc[9]); acc[10] = fmaf(gz_, pz, acc[10]); acc[11] += gz_;
         }
-        float a8[8], a4[4], a2[2];
-        bool hi = lane & 4;
+        float a8[8], a4[4];
+        bool hi = lane & 2;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const float recv = __shfl_xor_sync(0xffffffffu, hi ? acc[i] : acc[i + 8], 4);
+            const float recv = __shfl_xor_sync(0xffffffffu, hi ? acc[i] : acc[i + 8], 2);
             a8[i] = (hi ? acc[i + 8] : acc[i]) + recv;
-        }
-        hi = lane & 2;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float recv = __shfl_xor_sync(0xffffffffu, hi ? a8[i] : a8[i + 4], 2);
-            a4[i] = (hi ? a8[i + 4] : a8[i]) + recv;
         }
         hi = lane & 1;
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const float recv = __shfl_xor_sync(0xffffffffu, hi ? a4[i] : a4[i + 2], 1);
-            a2[i] = (hi ? a4[i + 2] : a4[i]) + recv;
+        for (int i = 0; i < 4; ++i) {
+            const float recv = __shfl_xor_sync(0xffffffffu, hi ? a8[i] : a8[i + 4], 1);
+            a4[i] = (hi ? a8[i + 4] : a8[i]) + recv;
         }
-        // this lane now holds elements el, el+1 of joint j
-        const int el = ((lane >> 2) & 1) * 8 + ((lane >> 1) & 1) * 4 + (lane & 1) * 2;
-        if (jv_ && el < 12) { dAb[j * 12 + el] = a2[0]; dAb[j * 12 + el + 1] = a2[1]; }
+        // this lane now holds elements 4*sl .. 4*sl+3 of joint j (sl = 3: the padding)
+        if (jv_ && sl < 3) *reinterpret_cast<float4*>(dAb + j * 12 + 4 * sl) = make_float4(a4[0], a4[1], a4[2], a4[3]);
     }
 }

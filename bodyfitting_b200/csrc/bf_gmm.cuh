@@ -91,3 +91,57 @@ __global__ void __launch_bounds__(GM_F * GM_PARTS) k_gmm_prior(BfModel m, const 
         for (int j = part; j < GM_D; j += GM_PARTS) o[j] = wp * S.g[bi][j][lane];
     }
 }
+
+
+// ---- tensor-core form (BF_F_TC): y_m = P_sym,m (x - mu_m) for all components is ONE GEMM -------------------------
+//   [pose69 | 1 | 0 ...] (K = 80)  @  [P_sym,m | -P_sym,m mu_m | 0]  ->  Y [B, n_gmm * 72]
+// run by the blend GEMM kernel (k_blend_fwd_tc, 3xTF32), between a pack kernel (operand rows, hi/lo split) and a select
+// kernel (quadratic forms d.y, arg-min, gradient of the winner).  39.7k FFMA per frame move to the tensor pipe, which is
+// idle while the per-frame loss kernel of the same iteration runs on the main stream.
+#define GM_KG 80
+
+__global__ void __launch_bounds__(256) k_gmm_pack(const float* __restrict__ pose, int ld, int nvalid, int B,
+                                                  float* __restrict__ x_hi, float* __restrict__ x_lo) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)B * GM_KG) return;
+    const int b = (int)(i / GM_KG), j = (int)(i % GM_KG);
+    const float v = j < nvalid ? pose[(size_t)b * ld + j] : (j == GM_D ? 1.0f : 0.0f);
+    float hi, lo;
+    split_tf32(v, hi, lo);
+    x_hi[i] = hi; x_lo[i] = lo;
+}
+
+// one warp per frame: q_m = (x - mu_m) . y_m, ll_m = q_m / 2 - log w_m, first minimum wins (prior.py:188-196)
+__global__ void __launch_bounds__(128) k_gmm_select(BfModel m, const float* __restrict__ pose, int ld, int nvalid, int B,
+                                                    const float* __restrict__ Y, int ldy, float wp,
+                                                    float* __restrict__ gmm_grad, float* __restrict__ gmm_loss) {
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= B) return;
+    float x[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const int i = lane + 32 * r;
+        x[r] = i < nvalid ? pose[(size_t)b * ld + i] : 0.f;
+    }
+    const float* y = Y + (size_t)b * ldy;
+    float best = 0.f;
+    int bc = 0;
+    for (int c = 0; c < m.n_gmm; ++c) {
+        float q = 0.f;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const int i = lane + 32 * r;
+            if (i < GM_D) q = fmaf(x[r] - __ldg(m.gmm_mean + c * GM_D + i), y[c * GM_LD + i], q);
+        }
+        q = warp_sum(q);
+        const float ll = 0.5f * q - __ldg(m.gmm_logw + c);
+        if (c == 0 || ll < best) { best = ll; bc = c; }
+    }
+    if (lane == 0) gmm_loss[b] = wp * best;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const int i = lane + 32 * r;
+        if (i < GM_D) gmm_grad[(size_t)b * GM_D + i] = wp * y[bc * GM_LD + i];
+    }
+}

@@ -170,6 +170,14 @@ class PreparedModel(object):
             psym = np.zeros((means.shape[0], 69, 72), dtype=np.float32)      # (P + P^T)/2, rows padded to 72
             psym[:, :, :69] = (prec + np.transpose(prec, (0, 2, 1))) * np.float32(0.5)
             g = dict(gmm_mean=means, gmm_psym=psym, gmm_logw=np.log(nllw).astype(np.float32))
+            if self.tensor_cores and means.shape[0] * 72 % 192 == 0:
+                # tensor-core form of the prior: y_m = P_sym,m (x - mu_m) for all components at once is ONE GEMM
+                # [pose69 | 1 | 0..] (K = 80) @ [P_sym,m | -P_sym,m mu_m] -> [B, n_gmm * 72]; K-major operand, 3xTF32 split
+                bt = np.zeros((means.shape[0] * 72, 80), dtype=np.float32)
+                for c in range(means.shape[0]):
+                    bt[c * 72:c * 72 + 69, :69] = psym[c, :, :69]
+                    bt[c * 72:c * 72 + 69, 69] = -(psym[c, :, :69].astype(np.float64) @ means[c].astype(np.float64)).astype(np.float32)
+                g['gmm_bt_hi'], g['gmm_bt_lo'] = split_tf32(bt)
             self.n_gmm = means.shape[0]
             assert means.shape[1] == 69
         else:

@@ -58,9 +58,9 @@ class SMPLify(object):
         self.dense_every_iter = dense_every_iter
         # temporal smoothness between consecutive frames of the batch (not in the reference; BASELINE config 4)
         self.temporal_weight, self.halo_exchange = float(temporal_weight), halo_exchange
-        # batches of >= 4096 frames are fitted as this many staggered parts on their own streams (1 = one batch)
+        # batches of >= 4096 frames are fitted as up to this many staggered parts on their own streams (1 = one batch)
         if concurrent_parts is None:
-            concurrent_parts = int(os.environ.get('BODYFIT_PARTS', '3'))
+            concurrent_parts = int(os.environ.get('BODYFIT_PARTS', '4'))
         self.concurrent_parts = max(1, int(concurrent_parts))
         self.concurrent_min_part = int(concurrent_min_part)
         self._pinned = {}
@@ -129,7 +129,8 @@ class SMPLify(object):
         ready = torch.cuda.Event()
         ready.record(cur)
         host, nbytes = {}, 0
-        for k, ((lo, hi), part, st) in enumerate(zip(sess.ranges, sess.parts, sess.streams)):
+        streams = sess.prio_streams                            # decreasing priority: parts finish in launch order
+        for k, ((lo, hi), part, st) in enumerate(zip(sess.ranges, sess.parts, streams)):
             with torch.cuda.stream(st):
                 st.wait_event(ready)
                 kp_dev = self._h2d(('kp', k), kp[lo:hi])
@@ -147,12 +148,12 @@ class SMPLify(object):
                         pbuf[lo:hi].copy_(v, non_blocking=True)
                         nbytes += int(v.numel() * v.element_size())
         if as_numpy:
-            for st in sess.streams:
+            for st in streams:
                 st.synchronize()
             self.d2h_bytes = nbytes
             out = {name: pbuf.squeeze(0).numpy() for name, pbuf in host.items()}
         else:
-            for st in sess.streams:
+            for st in streams:
                 cur.wait_stream(st)
             out = sess.results()
         self.last_trace, self.last_loss_terms = sess.trace, sess.loss_terms

@@ -40,7 +40,7 @@ extern "C" {
 #define BF_ECUDA    -2   /* a CUDA runtime call / launch failed            */
 #define BF_EARCH    -3   /* device is not sm_100 (no fallback exists)      */
 
-#define BF_ABI_VERSION 12
+#define BF_ABI_VERSION 13
 #define BF_F_WORLD 1   /* forward outputs in world space: (x + transl) * scale * constant_scale */
 #define BF_F_TC    2   /* run the blend-shape contractions on tcgen05 tensor cores (3xTF32) */
 #define BF_F_SKIN_FUSED 4  /* bf_frame_loss_backward skins the frame's live vertices itself from vposed (after bf_blend_forward) */
@@ -98,6 +98,8 @@ typedef struct BfModel {
     const float*   gmm_mean;  /* [8,69] */
     const float*   gmm_psym;  /* [8,69,72] (P + P^T)/2 of each component, rows padded with zeros to 72 */
     const float*   gmm_logw;  /* [8] log(nll_weights) */
+    const float*   gmm_bt_hi; /* [n_gmm*72, 80] K-major [P_sym,m | -P_sym,m mu_m | 0], 3xTF32 split: the prior as one tcgen05 GEMM (or NULL) */
+    const float*   gmm_bt_lo;
     BfVSet full;
     BfVSet act;
     int32_t J, P, NS, NB, Kp, NP, is_smplx, max_depth, K_used, n_gmm, _pad0, _pad1;
@@ -140,6 +142,7 @@ typedef struct BfFrames {
     const float* halo_next;  /* [NP] theta of the frame after this shard's last frame (next rank), NULL at the sequence end */
     float*       fwd_state;  /* [B,24J] optional: full_pose, R, rest joints, chain rotations saved by the pose forward so the
                                 pose backward does not recompute them */
+    float*       gmm_ws;     /* [B, n_gmm*72 + 160] workspace of the tensor-core GMM prior (y of every component | [pose|1] hi | lo), or NULL */
     float*       ws;         /* split-K workspace of the tensor-core backward GEMM (>= ceil(ldn/2048) * B * Kp floats) or NULL */
     int64_t      ws_floats;
     double lr_ts, lr, beta1, beta2, eps;   /* Adam hyper-parameters (python floats in the reference: smplify.py:167-174) */

@@ -231,8 +231,8 @@ def test_concurrent_parts_equal_single_batch(assets):
     sizes included), for host (numpy) and device results."""
     from bodyfitting_b200.engine import ConcurrentFitSession, staggered_ranges
     from bodyfitting_b200.smplify.smplify import SMPLify
-    assert [h - l for l, h in staggered_ranges(10000, 3)] == [2176, 3328, 4496]
-    assert staggered_ranges(1250, 3) == [(0, 1250)] and staggered_ranges(11, 3, min_part=1) == [(0, 2), (2, 6), (6, 11)]
+    assert [h - l for l, h in staggered_ranges(10000, 3)] == [4480, 3328, 2192]
+    assert staggered_ranges(1250, 3) == [(0, 1250)] and staggered_ranges(11, 3, min_part=1) == [(0, 5), (5, 9), (9, 11)]
     mt, nv, B, N = 'smplx', 8, 11, 8
     port = make_port(assets, mt)
     sc = make_scene(port, mt, B, nv, seed=33)
