@@ -22,6 +22,7 @@
 // Adam steps.  The split keeps the error at ~2^-21 per product (measured: see DESIGN.md).
 #pragma once
 #include <cuda.h>
+#include <stdlib.h>
 #include "bf_common.cuh"
 
 #define TC_BM 128          // frames per tile (UMMA M)
@@ -496,27 +497,22 @@ static int bf_blend_forward_tc(const BfModel* m, const BfVSet* vs, const BfFrame
 static int bf_blend_backward_tc(const BfModel* m, const BfVSet* vs, const BfFrames* f, cudaStream_t s) {
     CUtensorMap a_hi, a_lo, b_hi, b_lo;
     int rc;
-    // column tile: the widest of 256 / 128 / 64 that divides Kp, narrowed while that shortens the critical path
-    // (waves x work per tile) -- e.g. 10,000 frames x Kp 512 gives 158 CTAs of 256 columns = 2 waves on 148 SMs,
-    // but 632 CTAs of 64 columns, two co-resident per SM, = 2.1 waves of a quarter of the work each
+    // column tile: the widest of 256 / 128 / 64 that divides Kp (else Kp itself).  The kernel streams its operands from L2
+    // and every column tile re-reads the whole dvp row block, so the widest tile wins even when it leaves a partial last
+    // wave: measured on 10,000 frames x Kp 512, 64 / 128 / 256 columns = 0.134 / 0.123 / 0.109 ms (158 CTAs on 148 SMs).
     static int num_sms = 0;
     if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); }
-    const int mt = (f->B + TC_BM - 1) / TC_BM;
     int BN = m->Kp < 256 ? m->Kp : 256;
-    if (m->Kp % BN != 0) { bf_set_error("Kp=%d not tileable by %d", m->Kp, BN); return BF_EINVAL; }
     {
-        long best = -1;
         const int cand[3] = {256, 128, 64};
-        for (int i = 0; i < 3; ++i) {
-            const int bn = cand[i];
-            if (bn > m->Kp || m->Kp % bn != 0) continue;
-            const size_t sm = 1024 + TC_STAGES * (2 * TC_BM * TC_ROWB + 2 * (size_t)bn * TC_ROWB) + 64;
-            const int per_sm = (int)((227 * 1024) / sm) < 1 ? 1 : (int)((227 * 1024) / sm);
-            const long tiles = (long)(m->Kp / bn) * mt;
-            const long waves = (tiles + (long)num_sms * per_sm - 1) / ((long)num_sms * per_sm);
-            const long cost = waves * (bn + 96);                 // + fixed per-tile overhead (A operand, prologue)
-            if (best < 0 || cost < best) { best = cost; BN = bn; }
-        }
+        for (int i = 0; i < 3; ++i)
+            if (cand[i] <= m->Kp && m->Kp % cand[i] == 0) { BN = cand[i]; break; }
+    }
+    if (m->Kp % BN != 0 || BN % 16 != 0) { bf_set_error("Kp=%d not tileable by %d", m->Kp, BN); return BF_EINVAL; }
+    {
+        static int forced = -1;                           // BODYFIT_BWD_BN=64|128|256: tile-width experiments
+        if (forced < 0) { const char* e = getenv("BODYFIT_BWD_BN"); forced = e ? atoi(e) : 0; }
+        if (forced > 0 && forced <= m->Kp && m->Kp % forced == 0 && forced % 16 == 0 && forced <= 256) BN = forced;
     }
     if ((rc = bf_make_map(&a_hi, f->dvp_hi, f->B, vs->ldn, vs->ldn, TC_BM))) return rc;
     if ((rc = bf_make_map(&a_lo, f->dvp_lo, f->B, vs->ldn, vs->ldn, TC_BM))) return rc;

@@ -43,6 +43,14 @@ __device__ __forceinline__ float warp_reduce16(const float* v, int lane) {
     return d;
 }
 
+// 1 / x: hardware approximation (1 ulp) + one Newton step -> within 1 ulp of the correctly rounded value, 3 instructions
+// and no slow path (__frcp_rn costs ~8 instructions and a call for special operands; the loss loop needs 3 per (joint, view))
+__device__ __forceinline__ float rcp_nr(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return fmaf(r, fmaf(-x, r, 1.0f), r);
+}
+
 // T = sum_k w_k A[j_k] for vertex v (rows of A in shared memory); NR = 12 (forward) or 9 (rotation part, backward)
 template <int NC>
 __device__ __forceinline__ void blend_transform(const BfVSet& vs, const float* As, int v, float (&T)[3 * NC]) {
@@ -165,12 +173,12 @@ __global__ void __launch_bounds__(FR_THREADS, 4) k_frame_loss_bwd(BfModel m, BfV
                 const float p0 = m0.x * X + m0.y * Y + m0.z * Z + m0.w;
                 const float p1 = m1.x * X + m1.y * Y + m1.z * Z + m1.w;
                 const float p2 = m2.x * X + m2.y * Y + m2.z * Z + m2.w;
-                // three correctly-rounded reciprocals instead of seven IEEE divisions: 1/p2, 1/(s^2+rx^2), 1/(s^2+ry^2)
-                const float iz = __frcp_rn(p2);
+                // three reciprocals instead of seven IEEE divisions: 1/p2, 1/(s^2+rx^2), 1/(s^2+ry^2)
+                const float iz = rcp_nr(p2);
                 const float u = p0 * iz, w_ = p1 * iz;
                 const float rx = (kx - u) * icoef, ry = (ky - w_) * icoef;
                 const float rx2 = rx * rx, ry2 = ry * ry;
-                const float ix = __frcp_rn(s2 + rx2), iy = __frcp_rn(s2 + ry2);
+                const float ix = rcp_nr(s2 + rx2), iy = rcp_nr(s2 + ry2);
                 ls += wgt * (s2 * rx2 * ix + s2 * ry2 * iy);
                 const float du = wgt * (2.0f * s2 * s2 * rx * ix * ix) * (-icoef);
                 const float dw = wgt * (2.0f * s2 * s2 * ry * iy * iy) * (-icoef);

@@ -118,6 +118,67 @@ def test_target_lists_are_the_transpose_of_the_joint_table(prepared, mt):
             assert np.abs(via - direct).max() < 1e-6
 
 
+def test_gmm_gemm_operand(prepared):
+    """The tensor-core form of the GMM prior: [pose | 1 | 0] @ [P_sym,m | -P_sym,m mu_m | 0]^T == P_sym,m (pose - mu_m)."""
+    pm = prepared['smplx']
+    bt = (pm._dev['m_gmm_bt_hi'] + pm._dev['m_gmm_bt_lo']).numpy().astype(np.float64)
+    hi = pm._dev['m_gmm_bt_hi'].numpy()
+    assert bt.shape == (pm.n_gmm * 72, 80) and ((hi.view(np.uint32) & 0x1FFF) == 0).all()     # hi parts are TF32 values
+    psym, mu = pm._dev['m_gmm_psym'].numpy().astype(np.float64), pm._dev['m_gmm_mean'].numpy().astype(np.float64)
+    x = np.random.RandomState(2).standard_normal(69) * 0.3
+    a = np.zeros(80); a[:69] = x; a[69] = 1.0
+    y = bt @ a
+    for c in range(pm.n_gmm):
+        ref = psym[c, :, :69] @ (x - mu[c])
+        assert np.abs(y[c * 72:c * 72 + 69] - ref).max() < 1e-5 * max(1.0, np.abs(ref).max())
+        assert not y[c * 72 + 69:c * 72 + 72].any()
+
+
+@pytest.mark.parametrize('mt', ['smpl', 'smplx'])
+def test_live_vertex_tables(assets, prepared, mt):
+    """Per contour row: the live list is exactly the set of active vertices with a non-zero keypoint gradient, its gather
+    lists reproduce the transposed joint table (static entries, then contour entries in slot order), and the restricted
+    joint->vertex lists are the skinning weights of the live vertices."""
+    pm = prepared[mt]
+    t = _vs_tables(pm, 'act')
+    W = assets(mt)['weights'][pm.active_vids]
+    rows, lmax, n_nz = t['lv_n'].shape[0], t['lv_vid'].shape[1], len(t['jv_nz'])
+    assert rows == (79 if mt == 'smplx' else 1) and pm.struct.act.lmax == lmax and pm.struct.act.n_rows == rows
+    rng = np.random.RandomState(3)
+    g = rng.standard_normal((pm.K_used, 3))
+    for a in ((0, 11, 40, 78) if mt == 'smplx' else (0,)):
+        direct = np.zeros((pm.n_act, 3))
+        for k in range(pm.K_used):
+            kind, src, w = t['kj_kind'][k], t['kj_src'][k], t['kj_w'][k]
+            if kind == 1:
+                for i in range(3):
+                    direct[src[i]] += w[i] * g[k]
+            elif kind == 2:
+                for i in range(3):
+                    direct[t['dyn_src'][a, src[0], i]] += t['dyn_w'][a, src[0], i] * g[k]
+            elif kind == 3:
+                for e in range(t['xr_ptr'][src[0]], t['xr_ptr'][src[0] + 1]):
+                    direct[t['xr_vid'][e]] += t['xr_w'][e] * g[k]
+        L = int(t['lv_n'][a])
+        live = t['lv_vid'][a, :L]
+        assert (np.diff(live) > 0).all() and L <= lmax
+        touched = set(np.nonzero(np.abs(direct).sum(1))[0])
+        assert touched <= set(live.tolist())                 # every vertex with a gradient is live
+        via = np.zeros_like(direct)
+        for i, v in enumerate(live):
+            for e in range(t['lt_ptr'][a, i], t['lt_ptr'][a, i + 1]):
+                via[v] += t['lt_w'][e] * g[t['lt_k'][e]]
+        assert np.abs(via - direct).max() < 1e-6
+        sub = np.zeros((pm.n_act, pm.J))
+        for jn, j in enumerate(t['jv_nz']):
+            for e in range(t['lj_ptr'][a, jn], t['lj_ptr'][a, jn + 1]):
+                sub[t['lj_vid'][e], j] = t['lj_w'][e]
+        ref = np.zeros_like(sub)
+        ref[live] = W[live]
+        assert np.array_equal(sub, ref.astype(np.float32))
+        assert t['lj_ptr'].shape == (rows, n_nz + 1)
+
+
 @pytest.mark.parametrize('mt', ['smpl', 'smplx'])
 def test_blend_matrix_and_folded_regressor(assets, prepared, mt):
     pm, data = prepared[mt], assets(mt)
