@@ -195,7 +195,7 @@ class FitSession(object):
     def _dense_forward(self):
         for fbf in self.chunks:
             fbf.call('bf_lbs_forward')
-        return 3 * len(self.chunks)
+        return (4 if self.model.tensor_cores else 3) * len(self.chunks)     # pose, blend GEMM (+ row skinning), joints
 
     def run(self, theta0):
         fb, N = self.fb, self.N
@@ -203,6 +203,9 @@ class FitSession(object):
         fb.t['adam_m'].zero_()
         fb.t['adam_v'].zero_()
         launches = 0
+        # kernels of one iteration: blend GEMM, per-frame loss/backward, GMM prior (pack + GEMM + select on tensor cores,
+        # one FFMA kernel otherwise), blend backward GEMM, pose backward (+ next pose forward); + temporal term if on
+        per_it = 4 + (3 if 'gmm_ws' in fb.t else 1) + (1 if 'tgrad' in fb.t else 0)
         if self.dense_every_iter:
             # materialise all V vertices in every iteration, as the reference's model call does
             for it in range(N - 1):
@@ -210,25 +213,25 @@ class FitSession(object):
                 launches += self._dense_forward()
                 fb.struct.iter = it
                 fb.call('bf_fit_step')
-                launches += 6
+                launches += per_it + 1
         elif self.halo_exchange is not None:
             for it in range(N - 1):
                 self._exchange()
                 fb.struct.iter = it
                 fb.call('bf_fit_iteration', 1 if it == 0 else 0, 1)
-                launches += 6
+                launches += per_it + (1 if it == 0 else 0)
         else:
             fb.struct.iter = 0
             if N > 1:
                 fb.call('bf_fit_run', N - 1)
-                launches += 5 * (N - 1) + 1          # skin fwd, frame loss+bwd, gmm, blend bwd, pose bwd(+next fwd); pose fwd once
+                launches += per_it * (N - 1) + 1     # + the pose forward of the first iteration
         self.theta_prev.copy_(fb.t['theta'])
         launches += self._dense_forward()
         fb.struct.iter = N - 1
         if self.halo_exchange is not None:
             self._exchange()
         fb.call('bf_fit_step')
-        launches += 6
+        launches += per_it + 1
         self.kernel_launches = launches
         return fb.t['theta']
 
