@@ -18,7 +18,7 @@ disjoint frame ranges and no collective runs during the fit: weak scaling).
   lbs_dense : all-vertex LBS operator forward / backward (BASELINE config 2) against the HBM roofline.
   cpu_baseline : the oracle's single-frame restatement of the reference loop (oracle/fit_port.py,
           validated bit-for-bit against the verbatim reference in the authoring container) on the
-          box's host cores, 3 frames.
+          box's host cores, 8 frames (about 10 s).
 """
 import argparse
 import json
@@ -48,7 +48,7 @@ def parse():
     ap.add_argument('--iters', type=int, default=ITERS)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-dense', action='store_true')
-    ap.add_argument('--cpu-frames', type=int, default=3)
+    ap.add_argument('--cpu-frames', type=int, default=8)
     return ap.parse_args()
 
 

@@ -316,3 +316,35 @@ def test_sequence_driver_reads_openpose_files_and_writes_reference_outputs(asset
              use_frames=list(range(nv)), output_folder=str(tmp_path / 'single'), net_output=(sc['init_betas'][:1], sc['init_pose'][:1]),
              imsize=512)
     assert np.array_equal(one['pose'], direct['pose'][0])
+
+
+def test_full_size_batch_properties(assets):
+    """BASELINE config 3 size (SMPL-X, 8 views, 10,000 frames; 30 iterations here): size-independent properties --
+    every frame of the big batch (fitted as concurrent parts) equals the same frame fitted in a small batch bit for bit
+    (frames are independent fits), identical frames get identical results wherever they sit in the batch, the
+    objective decreases, and everything stays finite."""
+    import bench
+    from bodyfitting_b200.engine import ConcurrentFitSession
+    from bodyfitting_b200.smplify.smplify import SMPLify
+    mt, nv, B, N = 'smplx', 8, 10000, 30
+    fit = SMPLify(smpl_type=mt, num_iters=N, gender='neutral', model_data=assets(mt), gmm=assets('gmm'))
+    wl = bench.build_workload(fit.model, B, seed=7)
+    kp, pose, betas = wl['kp'].copy(), wl['init_pose'].copy(), wl['init_betas'].copy()
+    dup = [(17, 9000), (4095, 4096), (0, 9999)]                           # the same frame at two positions (different parts)
+    for a, b in dup:
+        kp[b], pose[b], betas[b] = kp[a], pose[a], betas[a]
+    args = (list(wl['c2ws']), list(wl['Ks']))
+    out = fit((betas, pose), *args, kp, None, imsize=512)
+    assert isinstance(fit.session(B, nv, 512, True), ConcurrentFitSession)
+    tr = fit.last_trace.cpu().numpy()
+    assert tr.shape == (N, B) and np.isfinite(tr).all() and all(np.isfinite(np.asarray(v)).all() for v in out.values())
+    print('frames whose objective decreased: %.4f, mean objective %.4g -> %.4g' % ((tr[-1] < tr[0]).mean(), tr[0].mean(), tr[-1].mean()))
+    assert (tr[-1] < tr[0]).mean() > 0.9 and tr[-1].mean() < 0.7 * tr[0].mean()       # the fit makes progress on (almost) every frame
+    for a, b in dup:
+        for k in ('pose', 'betas', 'global_orient', 'global_transl', 'scale', 'vertices', 'joints'):
+            assert np.array_equal(out[k][a], out[k][b]), (k, a, b)
+    pick = [0, 17, 2175, 2176, 5503, 5504, 8575, 8576, 9999]             # around the part boundaries
+    small = SMPLify(smpl_type=mt, num_iters=N, gender='neutral', model_data=assets(mt), gmm=assets('gmm'))
+    ref = small((betas[pick], pose[pick]), *args, kp[pick], None, imsize=512)
+    for k in ('pose', 'betas', 'global_orient', 'global_transl', 'scale', 'vertices', 'joints', 'full_pose'):
+        assert np.array_equal(np.asarray(out[k])[pick], np.asarray(ref[k])), k
