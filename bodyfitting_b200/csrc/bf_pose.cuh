@@ -121,6 +121,7 @@ __device__ __forceinline__ void pose_write_outputs(const BfModel& m, const BfFra
     }
     // GEMM A operand row: [R_1..R_{J-1} - I | shape | 1 | 0...]
     float* pf = f.pf + (size_t)b * m.Kp;
+    const bool tc_only = (f.flags & BF_F_TC) && f.pf_hi && f.pf_lo;
     for (int i = lane; i < m.Kp; i += 32) {
         float v = 0.f;
         if (i < m.P) {
@@ -128,7 +129,7 @@ __device__ __forceinline__ void pose_write_outputs(const BfModel& m, const BfFra
             v = S.R[9 + i] - ((e == 0 || e == 4 || e == 8) ? 1.0f : 0.0f);
         } else if (i < m.P + m.NS) v = S.sh[i - m.P];
         else if (i == m.P + m.NS) v = 1.0f;
-        pf[i] = v;
+        if (!tc_only) pf[i] = v;                     // the unsplit row is read by the FFMA contraction only
         if (f.pf_hi) {
             float hi, lo;
             split_tf32(v, hi, lo);
