@@ -350,6 +350,12 @@ int bf_lbs_backward(const BfModel* m, const BfFrames* f, void* stream) {
     return bf_pose_backward(m, f, 0, stream);
 }
 
+// shared memory of k_frame_loss_bwd: joint gradients + positions, cameras, reduction scratch, the frame's transforms,
+// skinned vertices / d(verts), v_posed, and the live vertices' outer products
+static size_t bf_frame_smem(const BfModel* m, const BfVSet* vs) {
+    return sizeof(float) * (BF_MAXK * 6 + BF_MAXVIEWS * 12 + 64 + ((m->J * 12 + 15) & ~15) + 2 * (size_t)vs->ldn + 12 * (size_t)vs->lmax);
+}
+
 int bf_frame_loss_backward(const BfModel* m, const BfFrames* f, void* stream) {
     int rc = check_model(m, f); if (rc) return rc;
     const BfVSet* vs = &m->act;
@@ -363,7 +369,7 @@ int bf_frame_loss_backward(const BfModel* m, const BfFrames* f, void* stream) {
     BF_REQUIRE(f->dvp_hi || f->dvp, "dvp (or its 3xTF32 split) missing");
     BF_REQUIRE(f->Nv > 0 && f->Nv <= BF_MAXVIEWS, "Nv out of range");
     BF_REQUIRE(vs->jv_ptr && vs->jv_vid && vs->jv_w && vs->jv_nz, "joint->vertex lists missing");
-    const size_t smem = sizeof(float) * (BF_MAXK * 6 + BF_MAXVIEWS * 12 + 64 + ((m->J * 12 + 15) & ~15) + 2 * (size_t)vs->ldn);
+    const size_t smem = bf_frame_smem(m, vs);
     BF_REQUIRE(smem <= 48 * 1024, "active vertex set too large for the fused per-frame kernel");
     BfFrames g = *f;
     if (!bf_tc_ready_bwd(vs, f)) { g.dvp_hi = nullptr; g.dvp_lo = nullptr; }
@@ -406,7 +412,7 @@ static int fit_iteration(const BfModel* m, const BfFrames* f, bool with_forward,
     }
     if (f->tgrad && f->w_temporal > 0.f) { rc = bf_temporal_prior(m, f, stream); if (rc) return rc; }
     if (with_forward) { rc = bf_pose_forward(m, f, stream); if (rc) return rc; }
-    const size_t fused_smem = sizeof(float) * (BF_MAXK * 6 + BF_MAXVIEWS * 12 + 64 + ((m->J * 12 + 15) & ~15) + 2 * (size_t)m->act.ldn);
+    const size_t fused_smem = bf_frame_smem(m, &m->act);
     const bool fused = fused_smem <= 48 * 1024 && m->act.lv_n;
     // tensor-core path of the fused loop: the GEMM only blends (v_posed); the per-frame kernel skins its live vertices
     const bool blend_only = fused && bf_tc_ready_fwd(&m->act, f) && f->vposed && !(f->flags & BF_F_WORLD);

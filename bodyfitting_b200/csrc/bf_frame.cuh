@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(FR_THREADS, 4) k_frame_loss_bwd(BfModel m, BfV
     float* As = jq + BF_MAXK * 3;                 // [J*12] this frame's joint transforms
     float* dv = As + ((m.J * 12 + 15) & ~15);     // [3*n_pad] skinned vertices, later d(verts)
     float* vp = dv + vs.ldn;                      // [3*n_pad] v_posed
+    float4* outb = reinterpret_cast<float4*>(vp + vs.ldn);      // [lmax*3] d(verts) (x) [v_posed; 1] of every live vertex
     const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int K = m.K_used, Nv = f.Nv, J = m.J;
     const int yaw = f.yaw ? f.yaw[b] : 0;
@@ -133,6 +134,10 @@ __global__ void __launch_bounds__(FR_THREADS, 4) k_frame_loss_bwd(BfModel m, BfV
             dv[3 * v] = T[0] * px + T[1] * py + T[2] * pz + T[3];
             dv[3 * v + 1] = T[4] * px + T[5] * py + T[6] * pz + T[7];
             dv[3 * v + 2] = T[8] * px + T[9] * py + T[10] * pz + T[11];
+            // keep the blended transform for the backward (same thread, same slot; overwritten there by the outer product)
+            outb[3 * i] = make_float4(T[0], T[1], T[2], T[3]);
+            outb[3 * i + 1] = make_float4(T[4], T[5], T[6], T[7]);
+            outb[3 * i + 2] = make_float4(T[8], T[9], T[10], T[11]);
         }
         __syncthreads();
     }
@@ -237,7 +242,12 @@ __global__ void __launch_bounds__(FR_THREADS, 4) k_frame_loss_bwd(BfModel m, BfV
     for (int i = t; i < L; i += FR_THREADS) {
         const int v = __ldg(lv + i);
         float T[9];
-        blend_transform<3>(vs, As, v, T);
+        if (skin_here) {                               // blended transform saved by the forward skinning above
+            const float4 r0 = outb[3 * i], r1 = outb[3 * i + 1], r2 = outb[3 * i + 2];
+            T[0] = r0.x; T[1] = r0.y; T[2] = r0.z; T[3] = r1.x; T[4] = r1.y; T[5] = r1.z; T[6] = r2.x; T[7] = r2.y; T[8] = r2.z;
+        } else {
+            blend_transform<3>(vs, As, v, T);
+        }
         const float gx_ = dv[3 * v], gy_ = dv[3 * v + 1], gz_ = dv[3 * v + 2];
         const float o0 = T[0] * gx_ + T[3] * gy_ + T[6] * gz_;
         const float o1 = T[1] * gx_ + T[4] * gy_ + T[7] * gz_;
@@ -250,6 +260,11 @@ __global__ void __launch_bounds__(FR_THREADS, 4) k_frame_loss_bwd(BfModel m, BfV
             float* o = f.dvp + (size_t)b * f.ld_v + 3 * v;
             o[0] = o0; o[1] = o1; o[2] = o2;
         }
+        // the vertex's outer product, once; the joint side below only scales and adds it
+        const float px = vp[3 * v], py = vp[3 * v + 1], pz = vp[3 * v + 2];
+        outb[3 * i] = make_float4(gx_ * px, gx_ * py, gx_ * pz, gx_);
+        outb[3 * i + 1] = make_float4(gy_ * px, gy_ * py, gy_ * pz, gy_);
+        outb[3 * i + 2] = make_float4(gz_ * px, gz_ * py, gz_ * pz, gz_);
     }
     // skinning backward, joint side: dA[j] = sum_{live v} w_vj dverts_v (x) [vposed_v; 1]
     float* dAb = f.dA + (size_t)b * J * 12;
@@ -271,13 +286,12 @@ __global__ void __launch_bounds__(FR_THREADS, 4) k_frame_loss_bwd(BfModel m, BfV
         for (int e = 0; e < 16; ++e) acc[e] = 0.f;
         const int e0 = jv_ ? __ldg(ljp + jn) : 0, e1 = jv_ ? __ldg(ljp + jn + 1) : 0;
         for (int e = e0 + sl; e < e1; e += 4) {
-            const int v = __ldg(vs.lj_vid + e);
+            const float4* o = outb + 3 * __ldg(vs.lj_vid + e);          // lj_vid: index into the row's live list
             const float w = __ldg(vs.lj_w + e);
-            const float gx_ = w * dv[3 * v], gy_ = w * dv[3 * v + 1], gz_ = w * dv[3 * v + 2];
-            const float px = vp[3 * v], py = vp[3 * v + 1], pz = vp[3 * v + 2];
-            acc[0] = fmaf(gx_, px, acc[0]); acc[1] = fmaf(gx_, py, acc[1]); acc[2] = fmaf(gx_, pz, acc[2]); acc[3] += gx_;
-            acc[4] = fmaf(gy_, px, acc[4]); acc[5] = fmaf(gy_, py, acc[5]); acc[6] = fmaf(gy_, pz, acc[6]); acc[7] += gy_;
-            acc[8] = fmaf(gz_, px, acc[8]); acc[9] = fmaf(gz_, py, acc[9]); acc[10] = fmaf(gz_, pz, acc[10]); acc[11] += gz_;
+            const float4 o0 = o[0], o1 = o[1], o2 = o[2];
+            acc[0] = fmaf(w, o0.x, acc[0]); acc[1] = fmaf(w, o0.y, acc[1]); acc[2] = fmaf(w, o0.z, acc[2]); acc[3] = fmaf(w, o0.w, acc[3]);
+            acc[4] = fmaf(w, o1.x, acc[4]); acc[5] = fmaf(w, o1.y, acc[5]); acc[6] = fmaf(w, o1.z, acc[6]); acc[7] = fmaf(w, o1.w, acc[7]);
+            acc[8] = fmaf(w, o2.x, acc[8]); acc[9] = fmaf(w, o2.y, acc[9]); acc[10] = fmaf(w, o2.z, acc[10]); acc[11] = fmaf(w, o2.w, acc[11]);
         }
         float a8[8], a4[4];
         bool hi = lane & 2;

@@ -385,7 +385,7 @@ class PreparedModel(object):
             for jn, j in enumerate(nzj):
                 lj_ptr[a, jn] = len(lj_vid)
                 nzv = np.nonzero(sub[:, j])[0]
-                lj_vid += [live[x] for x in nzv]
+                lj_vid += [int(x) for x in nzv]                             # index into this row's live list
                 lj_w += [float(sub[x, j]) for x in nzv]
             lj_ptr[a, len(nzj):] = len(lj_vid)
         pad1 = lambda x, dt: np.array(x if len(x) else [0], dtype=dt)

@@ -80,7 +80,7 @@ typedef struct BfVSet {
     const int32_t* lt_k;      /* output joint index */
     const float*   lt_w;      /* weight (static entries first, then contour entries in slot order) */
     const int32_t* lj_ptr;    /* [n_rows, n_nz+1] absolute offsets: skinning list of joint jv_nz[jn] restricted to live vertices */
-    const int32_t* lj_vid;
+    const int32_t* lj_vid;    /* index into the row's live list (lv_vid[a][.]) */
     const float*   lj_w;
     int32_t n, n_pad, ldn, nnz, K_out, n_dyn, n_extra, n_nz, lmax, n_rows;
 } BfVSet;

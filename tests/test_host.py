@@ -172,7 +172,7 @@ def test_live_vertex_tables(assets, prepared, mt):
         sub = np.zeros((pm.n_act, pm.J))
         for jn, j in enumerate(t['jv_nz']):
             for e in range(t['lj_ptr'][a, jn], t['lj_ptr'][a, jn + 1]):
-                sub[t['lj_vid'][e], j] = t['lj_w'][e]
+                sub[live[t['lj_vid'][e]], j] = t['lj_w'][e]          # lj_vid indexes the row's live list
         ref = np.zeros_like(sub)
         ref[live] = W[live]
         assert np.array_equal(sub, ref.astype(np.float32))
