@@ -74,7 +74,7 @@ __device__ __forceinline__ void blend_transform(const BfVSet& vs, const float* A
 // the frame's yaw row (vs.lv_* / lt_* / lj_*, built per row on the host).  Every other vertex of the active set has
 // an exactly-zero gradient for this frame, so it is neither skinned nor back-propagated; its dvp entries are zeroed.
 // skin_here != 0: v_posed comes from the blend GEMM and the live vertices are skinned in this kernel (f.verts unused).
-__global__ void __launch_bounds__(FR_THREADS, 4) k_frame_loss_bwd(BfModel m, BfVSet vs, BfFrames f, int skin_here) {
+__global__ void __launch_bounds__(FR_THREADS, 5) k_frame_loss_bwd(BfModel m, BfVSet vs, BfFrames f, int skin_here) {
     extern __shared__ __align__(16) float sm[];
     float* gx = sm;                               // [BF_MAXK*3] joint gradients
     float* cam = gx + BF_MAXK * 3;                // [BF_MAXVIEWS*12]
