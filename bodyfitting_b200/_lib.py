@@ -10,7 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('BODYFIT_LIB') or os.path.join(_HERE, 'libbodyfit_b200.so')   # BODYFIT_LIB: A/B builds of the same ABI
-ABI_VERSION = 13
+ABI_VERSION = 14
 F_WORLD = 1
 F_TC = 2
 F_SKIN_FUSED = 4
@@ -29,7 +29,7 @@ class BfVSet(C.Structure):
 
 class BfModel(C.Structure):
     _fields_ = [(n, _fp) for n in (
-        'parents', 'depth', 'child_ptr', 'child_idx', 'Jt', 'Jd', 'pose_mean', 'hand_l', 'hand_r',
+        'parents', 'depth', 'lvl_ptr', 'lvl_j', 'child_ptr', 'child_idx', 'Jt', 'Jd', 'pose_mean', 'hand_l', 'hand_r',
         'gmm_mean', 'gmm_psym', 'gmm_logw', 'gmm_bt_hi', 'gmm_bt_lo')] + \
         [('full', BfVSet), ('act', BfVSet)] + \
         [(n, _i32) for n in ('J', 'P', 'NS', 'NB', 'Kp', 'NP', 'is_smplx', 'max_depth', 'K_used',

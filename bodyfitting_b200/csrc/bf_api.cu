@@ -32,6 +32,7 @@ static int check_model(const BfModel* m, const BfFrames* f) {
     BF_REQUIRE(m->NP == theta_layout(m->is_smplx).np && m->NP <= BF_MAXNP, "NP does not match theta layout");
     BF_REQUIRE(m->Kp % 16 == 0 && m->Kp >= m->P + m->NS + 1, "Kp must be a multiple of 16 covering P+NS+1");
     BF_REQUIRE(m->P == (m->J - 1) * 9, "P != 9(J-1)");
+    BF_REQUIRE(m->parents && m->lvl_ptr && m->lvl_j && m->child_ptr && m->child_idx, "kinematic tree tables missing");
     BF_REQUIRE(f->B > 0, "B <= 0");
     BF_REQUIRE(f->theta, "theta is null");
     return BF_OK;

@@ -85,8 +85,8 @@ __device__ __forceinline__ void pose_forward_from_smem(const BfModel& m, PoseSme
     __syncwarp();
     // kinematic chain, level by level (parents[j] < j, depth[parent] = depth[j] - 1)
     for (int lev = 0; lev <= m.max_depth; ++lev) {
-        for (int j = lane; j < J; j += 32) {
-            if (__ldg(m.depth + j) != lev) continue;
+        for (int idx = __ldg(m.lvl_ptr + lev) + lane; idx < __ldg(m.lvl_ptr + lev + 1); idx += 32) {
+            const int j = __ldg(m.lvl_j + idx);
             if (lev == 0) {
 #pragma unroll
                 for (int e = 0; e < 9; ++e) S.GR[j * 9 + e] = S.R[j * 9 + e];
@@ -233,8 +233,8 @@ __global__ void __launch_bounds__(128) k_pose_bwd(BfModel m, BfFrames f, int fla
     __syncwarp();
     // reverse traversal: a joint gathers from its children (one level deeper, already final)
     for (int lev = m.max_depth - 1; lev >= 0; --lev) {
-        for (int j = lane; j < J; j += 32) {
-            if (__ldg(m.depth + j) != lev) continue;
+        for (int idx = __ldg(m.lvl_ptr + lev) + lane; idx < __ldg(m.lvl_ptr + lev + 1); idx += 32) {
+            const int j = __ldg(m.lvl_j + idx);
             const int c0 = __ldg(m.child_ptr + j), c1 = __ldg(m.child_ptr + j + 1);
             if (c0 == c1) continue;
             float aR[9], aT[3], pj[3];                 // the parent's sums stay in registers across its children

@@ -197,7 +197,12 @@ class PreparedModel(object):
             elif kind == 3:
                 active.update(int(x) for x in np.nonzero(xr[src[0]])[0])
         self.active_vids = np.array(sorted(active), dtype=np.int64)
-        self._host = dict(parents=parents.astype(np.int32), depth=depth, child_ptr=child_ptr,
+        # joints grouped by tree level: the chain kernels walk one level at a time with lane = joint of that level
+        lvl_j = np.argsort(depth, kind='stable').astype(np.int32)
+        lvl_ptr = np.zeros(int(depth.max()) + 2, dtype=np.int32)
+        np.add.at(lvl_ptr, depth + 1, 1)
+        lvl_ptr = np.cumsum(lvl_ptr).astype(np.int32)
+        self._host = dict(parents=parents.astype(np.int32), depth=depth, lvl_ptr=lvl_ptr, lvl_j=lvl_j, child_ptr=child_ptr,
                           child_idx=np.array(child_idx + [0], dtype=np.int32), Jt=Jt, Jd=Jd, pose_mean=pose_mean,
                           hand_l=hand_l, hand_r=hand_r, **g)
         self.max_depth = int(depth.max())

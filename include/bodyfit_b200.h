@@ -40,7 +40,7 @@ extern "C" {
 #define BF_ECUDA    -2   /* a CUDA runtime call / launch failed            */
 #define BF_EARCH    -3   /* device is not sm_100 (no fallback exists)      */
 
-#define BF_ABI_VERSION 13
+#define BF_ABI_VERSION 14
 #define BF_F_WORLD 1   /* forward outputs in world space: (x + transl) * scale * constant_scale */
 #define BF_F_TC    2   /* run the blend-shape contractions on tcgen05 tensor cores (3xTF32) */
 #define BF_F_SKIN_FUSED 4  /* bf_frame_loss_backward skins the frame's live vertices itself from vposed (after bf_blend_forward) */
@@ -88,6 +88,8 @@ typedef struct BfVSet {
 typedef struct BfModel {
     const int32_t* parents;   /* [J] */
     const int32_t* depth;     /* [J] */
+    const int32_t* lvl_ptr;   /* [max_depth+2] CSR over lvl_j: joints of tree level d are lvl_j[lvl_ptr[d] .. lvl_ptr[d+1]) */
+    const int32_t* lvl_j;     /* [J] joints sorted by depth (stable) */
     const int32_t* child_ptr; /* [J+1] */
     const int32_t* child_idx; /* [J-1] */
     const float*   Jt;        /* [J,3]     J_regressor @ v_template */

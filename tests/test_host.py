@@ -216,6 +216,9 @@ def test_kinematic_tables(prepared):
         pm = prepared[mt]
         par, dep = pm._dev['m_parents'].numpy(), pm._dev['m_depth'].numpy()
         assert pm.max_depth == depth and dep[0] == 0 and par[0] == -1
+        lp, lj = pm._dev['m_lvl_ptr'].numpy(), pm._dev['m_lvl_j'].numpy()
+        assert lp[0] == 0 and lp[-1] == pm.J and sorted(lj.tolist()) == list(range(pm.J))
+        assert all((dep[lj[lp[d]:lp[d + 1]]] == d).all() for d in range(depth + 1))
         assert all(dep[j] == dep[par[j]] + 1 for j in range(1, pm.J))
         cp, ci = pm._dev['m_child_ptr'].numpy(), pm._dev['m_child_idx'].numpy()
         for j in range(pm.J):
