@@ -1,47 +1,21 @@
-// Fused per-frame backward of the fitting loop on the active vertex set (one CTA per frame):
+// Fused per-frame kernel of the fitting loop on the active vertex set (one CTA per frame):
 //
-//   keypoint term (joints -> world -> multi-view projection -> GMoF, smplify/loss.py:22-51,132-203)
-//   -> gradient w.r.t. transl / scale / model joints -> gather by target into d(verts) kept in
-//   SHARED memory -> skinning backward for the frame: dvp = T_v^T dverts_v (written as the 3xTF32
-//   operand split for the tensor-core blend backward) and dA[j] = sum_v w_vj dverts_v (x) [vposed_v; 1].
+//   stage the frame's joint transforms A[b] and blended vertices v_posed (from the blend GEMM) in SHARED memory
+//   -> LBS skinning of the frame's LIVE vertices (static picks / landmarks + the contour vertices of its yaw row)
+//   -> output joints (chain joints, picked vertices, barycentric landmarks, contour landmarks)
+//   -> keypoint term: world -> multi-view projection -> GMoF (smplify/loss.py:22-51,132-203), one thread per joint
+//      walking its views, keypoints read as 16-byte vectors from the joint-major layout
+//   -> gradient w.r.t. transl / scale / model joints -> gather by target into d(verts) (shared memory)
+//   -> skinning backward: dvp = T_v^T dverts_v (written as the 3xTF32 operand split for the tensor-core blend
+//      backward) and dA[j] = sum_v w_vj dverts_v (x) [vposed_v; 1] (per-vertex outer products staged once).
 //
-// Fusing the three steps keeps d(verts), v_posed and the frame's joint transforms on chip: the
-// d(verts) round trip through HBM and two launches of the unfused path (k_keypoint_loss,
-// k_skin_bwd_dvp, k_skin_bwd_dA -- still used for the all-vertex operator backward) disappear.
+// Skinned vertices, d(verts), the blended transforms and the outer products never leave the chip; the unfused path
+// (k_keypoint_loss, k_skin_rows, k_skin_bwd_dA) serves the all-vertex loop (silhouette / scan terms, operator surface).
 #pragma once
 #include "bf_common.cuh"
 #include "bf_loss.cuh"
 
 #define FR_THREADS 256
-
-
-// sum over the 32 lanes of 16 values at once with 16 shuffles (instead of 16 x 5): after the call the
-// lane holds the total of element e = 8*bit4 + 4*bit3 + 2*bit2 + bit1 of its lane id (fixed tree).
-__device__ __forceinline__ float warp_reduce16(const float* v, int lane) {
-    float a[8], b[4], c[2];
-    bool hi = lane & 16;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const float recv = __shfl_xor_sync(0xffffffffu, hi ? v[i] : v[i + 8], 16);
-        a[i] = (hi ? v[i + 8] : v[i]) + recv;
-    }
-    hi = lane & 8;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float recv = __shfl_xor_sync(0xffffffffu, hi ? a[i] : a[i + 4], 8);
-        b[i] = (hi ? a[i + 4] : a[i]) + recv;
-    }
-    hi = lane & 4;
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const float recv = __shfl_xor_sync(0xffffffffu, hi ? b[i] : b[i + 2], 4);
-        c[i] = (hi ? b[i + 2] : b[i]) + recv;
-    }
-    hi = lane & 2;
-    float d = (hi ? c[1] : c[0]) + __shfl_xor_sync(0xffffffffu, hi ? c[0] : c[1], 2);
-    d += __shfl_xor_sync(0xffffffffu, d, 1);
-    return d;
-}
 
 // 1 / x: hardware approximation (1 ulp) + one Newton step -> within 1 ulp of the correctly rounded value, 3 instructions
 // and no slow path (__frcp_rn costs ~8 instructions and a call for special operands; the loss loop needs 3 per (joint, view))
@@ -51,7 +25,7 @@ __device__ __forceinline__ float rcp_nr(float x) {
     return fmaf(r, fmaf(-x, r, 1.0f), r);
 }
 
-// T = sum_k w_k A[j_k] for vertex v (rows of A in shared memory); NR = 12 (forward) or 9 (rotation part, backward)
+// T = sum_k w_k A[j_k] for vertex v (rows of A in shared memory); NC = 4: full 3x4 rows (forward), 3: rotation part (backward)
 template <int NC>
 __device__ __forceinline__ void blend_transform(const BfVSet& vs, const float* As, int v, float (&T)[3 * NC]) {
     const int nnz = vs.nnz;
