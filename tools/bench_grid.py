@@ -1,5 +1,5 @@
-"""Closest-point kernel on BASELINE config 5 sizes: 100k-vertex scan (200k faces), 10,475 queries.
-Times bf_grid_nearest and the grid build, and -- when oracle/_ref was built -- the reference's own
+"""Grid kernels on BASELINE config 5 sizes: 100k-vertex scan (200k faces), 10,475 closest-point queries, 100k inside / ray
+queries.  Times bf_grid_nearest / bf_grid_inside / bf_grid_intersects_any and the grid build, and -- when oracle/_ref was built -- the reference's own
 mesh_grid kernel compiled for sm_100a on the same GPU (the on-box bar for this path)."""
 import glob, importlib.util, json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -42,4 +42,19 @@ if so:
     dref = torch.norm(npts - qd, dim=1)
     out.update(reference_ms=ref, speedup_vs_reference_kernel=ref / ours,
                max_abs_dist_diff=float((dref - d2.sqrt()).abs().max()), ours_never_worse=bool((d2.sqrt() <= dref + 1e-6).all()))
+# inside test / ray queries on the same grid: 100k queries in and around the scan
+n = 100000
+lo, hi = v.min(0), v.max(0)
+qi = torch.from_numpy((rng.rand(n, 3) * (hi - lo) * 1.3 + lo - 0.15 * (hi - lo)).astype(np.float32)).cuda()
+ro = torch.from_numpy((rng.rand(n, 3) * (hi - lo) * 2.0 + lo - 0.5 * (hi - lo)).astype(np.float32)).cuda()
+rd = torch.from_numpy(rng.randn(n, 3).astype(np.float32)).cuda()
+out['inside_queries'] = n
+out['inside_ms'] = ev_time(lambda: s.inside_mesh(qi))
+out['rays_ms'] = ev_time(lambda: s.intersects_any(ro, rd))
+if so:
+    signs = torch.zeros(n).cuda(); hit = torch.zeros(n, dtype=torch.bool).cuda()
+    out['reference_inside_ms'] = ev_time(lambda: mg.search_inside_mesh(qi, verts, fa, tri_num, tri_idx, num, minmax, s.step, signs), reps=5)
+    out['reference_rays_ms'] = ev_time(lambda: mg.search_intersect(ro, rd, verts, fa, tri_num, tri_idx, num, minmax, s.step, hit), reps=5)
+    out['inside_agreement'] = float((s.inside_mesh(qi) == signs).float().mean())
+    out['rays_agreement'] = float((s.intersects_any(ro, rd) == hit).float().mean())
 print(json.dumps(out))
