@@ -276,6 +276,30 @@ def dense_lbs_bench(assets_seed, hbm_peak):
             'fwd_frac_hbm': alg / fwd / 1e6 / hbm_peak, 'bwd_frac_hbm': alg / bwd / 1e6 / hbm_peak}
 
 
+def config2_fit_bench():
+    """BASELINE config 2 as a fit: SMPL, 1024 frames, 4 views, 25 keypoints, 100 iterations on one GPU (device-resident)."""
+    import torch
+    from bodyfitting_b200 import synthetic as syn
+    from bodyfitting_b200.engine import FitSession, pack_cameras, pack_keypoints
+    from bodyfitting_b200.model import PreparedModel
+    B, nv, N = 1024, 4, 100
+    pm = PreparedModel('smpl', syn.make_model('smpl', 0), gmm=syn.make_gmm(0),
+                       J_regressor_extra=syn.make_J_regressor_extra(seed=0), device='cuda')
+    gt, init = syn.make_params('smpl', B, seed=9)
+    c2ws, Ks = syn.make_cameras(nv, seed=0)
+    rng = np.random.RandomState(9)
+    kp = np.concatenate([rng.rand(B, nv, 25, 2).astype(np.float32) * 512, rng.rand(B, nv, 25, 1).astype(np.float32)], -1)
+    sess = FitSession(pm, B, nv, N)
+    sess.set_inputs(pack_keypoints(torch.from_numpy(kp).cuda(), False), torch.from_numpy(pack_cameras(c2ws, Ks)).cuda())
+    T = lambda a: torch.from_numpy(a).cuda()
+    theta0 = pm.pack_theta(T(init['global_orient']), T(init['body_pose']), T(init['betas']))
+    for _ in range(3):
+        sess.run(theta0)
+    ms = float(np.median(time_events(lambda: sess.run(theta0), 5)))
+    return {'config': 'SMPL 6890 verts, 1024 frames, 4 views x 25 keypoints, 100 iterations (BASELINE config 2), one batch, one stream',
+            'ms_per_fit': ms, 'frames_per_s': B / ms * 1e3, 'active_vertices': int(pm.n_act)}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -394,6 +418,10 @@ def run_ours(args):
             line['lbs_dense'] = dense_lbs_bench(0, hbm_peak)
         except Exception as ex:                              # report, never hide
             line['lbs_dense'] = {'error': repr(ex)}
+        try:
+            line['config2_fit'] = config2_fit_bench()
+        except Exception as ex:
+            line['config2_fit'] = {'error': repr(ex)}
     if world > 1:
         dist.destroy_process_group()
     if not args.no_cpu_baseline:

@@ -148,6 +148,29 @@ int bf_keypoint_loss(const BfModel* m, const BfFrames* f, int use_full, void* st
     return BF_OK;
 }
 
+// Side streams (+ fork / join events) per (device, caller stream, slot), created on first use.
+//   slot 0: the GMM prior of a fit iteration only needs theta, so it runs next to the blend / loss kernels (fork after the
+//           parameters are final, join before the pose backward);
+//   slot 1: in the all-vertex backward, dA (gathers per joint, no shared memory) runs next to dvp (row kernel) -- both
+//           only read d(verts).
+struct SideStream { cudaStream_t main = nullptr; cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, join = nullptr; int dev = -1, slot = 0; };
+static SideStream* side_stream(cudaStream_t main_s, int slot = 0) {
+    static SideStream table[512];
+    static int used = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    for (int i = 0; i < used; ++i)
+        if (table[i].dev == dev && table[i].main == main_s && table[i].slot == slot) return &table[i];
+    if (used >= 512) return nullptr;
+    SideStream* ss = &table[used];
+    if (cudaStreamCreateWithFlags(&ss->s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&ss->fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&ss->join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    ss->dev = dev; ss->main = main_s; ss->slot = slot;
+    ++used;
+    return ss;
+}
+
 // parts: bit0 dvp, bit1 dA, bit2 blend backward GEMM (bf_skin_backward = all three)
 int bf_skin_backward_parts(const BfModel* m, const BfFrames* f, int use_full, int parts, void* stream) {
     int rc = check_model(m, f); if (rc) return rc;
@@ -156,6 +179,14 @@ int bf_skin_backward_parts(const BfModel* m, const BfFrames* f, int use_full, in
     BF_REQUIRE(f->dverts && f->dvp && f->vposed && f->dA && f->dpf && f->A, "backward buffers missing");
     BF_REQUIRE(vs->jv_ptr && vs->jv_vid && vs->jv_w, "joint->vertex lists missing");
     cudaStream_t s = (cudaStream_t)stream;
+    SideStream* s2 = ((parts & 3) == 3) ? side_stream(s, 1) : nullptr;
+    if (s2) {                                              // dA next to dvp: both only read d(verts)
+        cudaEventRecord(s2->fork, s);
+        cudaStreamWaitEvent(s2->s, s2->fork, 0);
+        k_skin_bwd_dA<<<f->B, 256, 0, s2->s>>>(*vs, m->J, f->dverts, f->vposed, f->dA, f->B, f->ld_v);
+        BF_LAUNCH_CHECK();
+        cudaEventRecord(s2->join, s2->s);
+    }
     if ((parts & 1) && bf_tc_ready_bwd(vs, f)) {
         // tensor-core mode: only the 3xTF32 split of dvp is consumed (by the blend backward GEMM)
         rc = bf_launch_skin_rows(1, vs, m->J, f->A, f->dverts, nullptr, f->dvp_hi, f->dvp_lo, f->B, f->ld_v, vs->ldn,
@@ -168,7 +199,7 @@ int bf_skin_backward_parts(const BfModel* m, const BfFrames* f, int use_full, in
                                            tcb ? f->dvp_hi : nullptr, tcb ? f->dvp_lo : nullptr);
         BF_LAUNCH_CHECK();
     }
-    if (parts & 2) {
+    if ((parts & 2) && !s2) {
         k_skin_bwd_dA<<<f->B, 256, 0, s>>>(*vs, m->J, f->dverts, f->vposed, f->dA, f->B, f->ld_v);
         BF_LAUNCH_CHECK();
     }
@@ -182,6 +213,7 @@ int bf_skin_backward_parts(const BfModel* m, const BfFrames* f, int use_full, in
         k_blend_bwd<<<grid, 256, 0, s>>>(*vs, m->Kp, f->dvp, f->dpf, f->B, f->ld_v);
         BF_LAUNCH_CHECK();
     }
+    if (s2) cudaStreamWaitEvent(s, s2->join, 0);
     return BF_OK;
 }
 
@@ -377,28 +409,6 @@ int bf_frame_loss_backward(const BfModel* m, const BfFrames* f, void* stream) {
     k_frame_loss_bwd<<<f->B, FR_THREADS, smem, (cudaStream_t)stream>>>(*m, *vs, g, skin_here);
     BF_LAUNCH_CHECK();
     return BF_OK;
-}
-
-// The GMM prior only needs theta, so it runs on a side stream next to the blend / loss kernels of the same
-// iteration (fork after the parameters are final, join before the pose backward).  One side stream and two
-// events per (device, stream), created on first use.
-struct SideStream { cudaStream_t main = nullptr; cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, join = nullptr; int dev = -1; };
-// one side stream (+ two events) per (device, caller stream), created on first use
-static SideStream* side_stream(cudaStream_t main_s) {
-    static SideStream table[256];
-    static int used = 0;
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
-    for (int i = 0; i < used; ++i)
-        if (table[i].dev == dev && table[i].main == main_s) return &table[i];
-    if (used >= 256) return nullptr;
-    SideStream* ss = &table[used];
-    if (cudaStreamCreateWithFlags(&ss->s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-    if (cudaEventCreateWithFlags(&ss->fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-    if (cudaEventCreateWithFlags(&ss->join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-    ss->dev = dev; ss->main = main_s;
-    ++used;
-    return ss;
 }
 
 static int fit_iteration(const BfModel* m, const BfFrames* f, bool with_forward, bool fuse_next, void* stream) {
