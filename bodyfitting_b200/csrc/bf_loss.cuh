@@ -60,6 +60,7 @@ __device__ __forceinline__ void scatter_by_target(const BfVSet& vs, int J, int K
     for (int tg = threadIdx.x; tg < ntg; tg += blockDim.x) {
         float a0 = 0.f, a1 = 0.f, a2 = 0.f;
         const int e0 = __ldg(vs.tg_ptr + tg), e1 = __ldg(vs.tg_ptr + tg + 1);
+        if (accumulate && e0 == e1 && tg >= J) continue;     // nothing to add to this vertex: leave its row untouched
         for (int e = e0; e < e1; ++e) {
             const int k = __ldg(vs.tg_k + e);
             if (k < Klim) {

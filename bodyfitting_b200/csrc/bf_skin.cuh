@@ -322,6 +322,11 @@ k_skin_rows(BfVSet vs, int J, const float* __restrict__ A, const float* in, floa
     const int nnz = vs.nnz;
     const int n_chunks = (vs.n + 15) >> 4;
     const int c_end = min(n_chunks, (int)(blockIdx.y + 1) * chunks_per_slab);
+    // this lane's three (row-of-the-pair, coord) slots of a 2-row x 48-coord step: global / tile offsets
+    const int hi1 = lane >= 16, c1 = lane + 32 - 48 * hi1;
+    const size_t g_off0 = (size_t)lane, g_off1 = (size_t)hi1 * ld_v + c1, g_off2 = (size_t)ld_v + lane + 16;
+    const size_t h_off0 = (size_t)lane, h_off1 = (size_t)hi1 * ld_out + c1, h_off2 = (size_t)ld_out + lane + 16;
+    const int s_off0 = lane * SR_LD, s_off1 = c1 * SR_LD + hi1, s_off2 = (lane + 16) * SR_LD + 1;
     for (int ch = blockIdx.y * chunks_per_slab + warp; ch < c_end; ch += SR_WARPS) {
         const int vbase = ch << 4;
         const int ncols = 3 * min(16, vs.n - vbase);
@@ -332,14 +337,25 @@ k_skin_rows(BfVSet vs, int J, const float* __restrict__ A, const float* in, floa
             if (lane < 16) reinterpret_cast<int4*>(ell)[vi] = __ldg(reinterpret_cast<const int4*>(vs.ell_j) + v);
             else reinterpret_cast<float4*>(ell)[16 + vi] = __ldg(reinterpret_cast<const float4*>(vs.ell_w) + v);
         }
-        // rows -> tile (2 rows x 48 coords per three warp-wide loads)
+        // rows -> tile: 2 rows x 48 coords per three warp-wide loads; the lane's three (row, coord) slots are fixed, so a
+        // full chunk is just pointer increments
+        const bool full_chunk = nrows == 32 && ncols == 48;
+        if (full_chunk) {
+            const float* p = src;
 #pragma unroll 8
-        for (int rp = 0; rp < 16; ++rp) {
+            for (int rp = 0; rp < 16; ++rp, p += 2 * (size_t)ld_v) {
+                const float x0 = p[g_off0], x1 = p[g_off1], x2 = p[g_off2];
+                st[s_off0 + 2 * rp] = x0; st[s_off1 + 2 * rp] = x1; st[s_off2 + 2 * rp] = x2;
+            }
+        } else {
+#pragma unroll 4
+            for (int rp = 0; rp < 16; ++rp) {
 #pragma unroll
-            for (int s = 0; s < 3; ++s) {
-                const int idx = lane + 32 * s, hi = idx >= 48;
-                const int fr = 2 * rp + hi, c = idx - 48 * hi;
-                if (fr < nrows && c < ncols) st[c * SR_LD + fr] = src[(size_t)fr * ld_v + c];
+                for (int s = 0; s < 3; ++s) {
+                    const int idx = lane + 32 * s, hi = idx >= 48;
+                    const int fr = 2 * rp + hi, c = idx - 48 * hi;
+                    if (fr < nrows && c < ncols) st[c * SR_LD + fr] = src[(size_t)fr * ld_v + c];
+                }
             }
         }
         __syncwarp();
@@ -394,20 +410,42 @@ k_skin_rows(BfVSet vs, int J, const float* __restrict__ A, const float* in, floa
             q[0] = ox; q[SR_LD] = oy; q[2 * SR_LD] = oz;
         }
         __syncwarp();
+        if (full_chunk) {
+            if (out) {
+                float* p = out + (size_t)b0 * ld_v + 3 * vbase;
+#pragma unroll 8
+                for (int rp = 0; rp < 16; ++rp, p += 2 * (size_t)ld_v) {
+                    p[g_off0] = st[s_off0 + 2 * rp]; p[g_off1] = st[s_off1 + 2 * rp]; p[g_off2] = st[s_off2 + 2 * rp];
+                }
+            }
+            if (MODE == 1 && out_hi) {
+                const size_t base = (size_t)b0 * ld_out + 3 * vbase;
+                float* ph = out_hi + base;
+                float* pl = out_lo + base;
+#pragma unroll 8
+                for (int rp = 0; rp < 16; ++rp, ph += 2 * (size_t)ld_out, pl += 2 * (size_t)ld_out) {
+                    float h_, l_;
+                    split_tf32(st[s_off0 + 2 * rp], h_, l_); ph[h_off0] = h_; pl[h_off0] = l_;
+                    split_tf32(st[s_off1 + 2 * rp], h_, l_); ph[h_off1] = h_; pl[h_off1] = l_;
+                    split_tf32(st[s_off2 + 2 * rp], h_, l_); ph[h_off2] = h_; pl[h_off2] = l_;
+                }
+            }
+        } else {
 #pragma unroll 4
-        for (int rp = 0; rp < 16; ++rp) {
+            for (int rp = 0; rp < 16; ++rp) {
 #pragma unroll
-            for (int s = 0; s < 3; ++s) {
-                const int idx = lane + 32 * s, hi = idx >= 48;
-                const int fr = 2 * rp + hi, c = idx - 48 * hi;
-                if (fr < nrows && c < ncols) {
-                    const float val = st[c * SR_LD + fr];
-                    if (out) out[(size_t)(b0 + fr) * ld_v + 3 * vbase + c] = val;
-                    if (MODE == 1 && out_hi) {
-                        float h_, l_;
-                        split_tf32(val, h_, l_);
-                        const size_t o = (size_t)(b0 + fr) * ld_out + 3 * vbase + c;
-                        out_hi[o] = h_; out_lo[o] = l_;
+                for (int s = 0; s < 3; ++s) {
+                    const int idx = lane + 32 * s, hi = idx >= 48;
+                    const int fr = 2 * rp + hi, c = idx - 48 * hi;
+                    if (fr < nrows && c < ncols) {
+                        const float val = st[c * SR_LD + fr];
+                        if (out) out[(size_t)(b0 + fr) * ld_v + 3 * vbase + c] = val;
+                        if (MODE == 1 && out_hi) {
+                            float h_, l_;
+                            split_tf32(val, h_, l_);
+                            const size_t o = (size_t)(b0 + fr) * ld_out + 3 * vbase + c;
+                            out_hi[o] = h_; out_lo[o] = l_;
+                        }
                     }
                 }
             }
