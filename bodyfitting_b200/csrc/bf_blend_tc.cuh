@@ -199,10 +199,24 @@ __device__ __forceinline__ void tmem_ld48(uint32_t taddr, uint32_t* r) {
         : "memory");
 }
 
-// staging tile [48 coords][32 frames] -> rows of `dst` (row stride ld floats), `ncols` valid coords, `nrows` valid frames
+// staging tile [48 coords][32 frames] -> rows of `dst` (row stride ld floats), `ncols` valid coords, `nrows` valid frames.
+// 2 rows x 48 coords = 96 elements = 3 warp-wide stores per step; a lane's three (row-of-the-pair, coord) slots are fixed,
+// so a full tile is walked with pointer increments only.
 __device__ __forceinline__ void store_rows48(const float* st, float* __restrict__ dst, size_t ld, int ncols, int nrows, int lane) {
+    if (nrows == 32 && ncols == 48) {
+        const int hi1 = lane >= 16, c1 = lane + 32 - 48 * hi1;
+        const size_t g0 = (size_t)lane, g1 = (size_t)hi1 * ld + c1, g2 = ld + lane + 16;
+        const float* s0 = st + lane * TC_ST_LD;
+        const float* s1 = st + c1 * TC_ST_LD + hi1;
+        const float* s2 = st + (lane + 16) * TC_ST_LD + 1;
+#pragma unroll 8
+        for (int rp = 0; rp < 16; ++rp, dst += 2 * ld) {
+            dst[g0] = s0[2 * rp]; dst[g1] = s1[2 * rp]; dst[g2] = s2[2 * rp];
+        }
+        return;
+    }
 #pragma unroll 4
-    for (int rp = 0; rp < 16; ++rp) {                     // 2 rows x 48 coords = 96 elements = 3 warp-wide stores
+    for (int rp = 0; rp < 16; ++rp) {
 #pragma unroll
         for (int s = 0; s < 3; ++s) {
             const int idx = lane + 32 * s, hi = idx >= 48;
