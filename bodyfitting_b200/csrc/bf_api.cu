@@ -385,8 +385,16 @@ int bf_lbs_backward(const BfModel* m, const BfFrames* f, void* stream) {
 
 // shared memory of k_frame_loss_bwd: joint gradients + positions, cameras, reduction scratch, the frame's transforms,
 // skinned vertices / d(verts), v_posed, and the live vertices' outer products
-static size_t bf_frame_smem(const BfModel* m, const BfVSet* vs) {
-    return sizeof(float) * (BF_MAXK * 6 + BF_MAXVIEWS * 12 + 64 + ((m->J * 12 + 15) & ~15) + 2 * (size_t)vs->ldn + 12 * (size_t)vs->lmax);
+static size_t bf_frame_smem(const BfModel* m, const BfVSet* vs, int Nv, int tma) {
+    return sizeof(float) * (size_t)frame_smem_layout(m->K_used, Nv, m->J, vs->ldn, vs->lmax, tma).total;
+}
+// The bulk-copy (TMA) staging of the per-frame kernel needs 16-byte aligned, 16-byte granular keypoint rows and room for
+// them in shared memory; otherwise the plain-load variant runs.  BODYFIT_FRAME_TMA=0 forces the latter (A/B timing).
+static bool bf_frame_use_tma(const BfModel* m, const BfVSet* vs, const BfFrames* f) {
+    static int env = -1;
+    if (env < 0) { const char* e = getenv("BODYFIT_FRAME_TMA"); env = e ? atoi(e) : 1; }
+    return env != 0 && (m->K_used * f->Nv) % 4 == 0 && ((uintptr_t)f->kp & 15) == 0 && ((uintptr_t)f->A & 15) == 0 &&
+           ((uintptr_t)f->vposed & 15) == 0 && bf_frame_smem(m, vs, f->Nv, 1) <= 48 * 1024;
 }
 
 int bf_frame_loss_backward(const BfModel* m, const BfFrames* f, void* stream) {
@@ -402,11 +410,13 @@ int bf_frame_loss_backward(const BfModel* m, const BfFrames* f, void* stream) {
     BF_REQUIRE(f->dvp_hi || f->dvp, "dvp (or its 3xTF32 split) missing");
     BF_REQUIRE(f->Nv > 0 && f->Nv <= BF_MAXVIEWS, "Nv out of range");
     BF_REQUIRE(vs->jv_ptr && vs->jv_vid && vs->jv_w && vs->jv_nz, "joint->vertex lists missing");
-    const size_t smem = bf_frame_smem(m, vs);
+    const bool tma = bf_frame_use_tma(m, vs, f);
+    const size_t smem = bf_frame_smem(m, vs, f->Nv, tma);
     BF_REQUIRE(smem <= 48 * 1024, "active vertex set too large for the fused per-frame kernel");
     BfFrames g = *f;
     if (!bf_tc_ready_bwd(vs, f)) { g.dvp_hi = nullptr; g.dvp_lo = nullptr; }
-    k_frame_loss_bwd<<<f->B, FR_THREADS, smem, (cudaStream_t)stream>>>(*m, *vs, g, skin_here);
+    if (tma) k_frame_loss_bwd<1><<<f->B, FR_THREADS, smem, (cudaStream_t)stream>>>(*m, *vs, g, skin_here);
+    else k_frame_loss_bwd<0><<<f->B, FR_THREADS, smem, (cudaStream_t)stream>>>(*m, *vs, g, skin_here);
     BF_LAUNCH_CHECK();
     return BF_OK;
 }
@@ -423,7 +433,7 @@ static int fit_iteration(const BfModel* m, const BfFrames* f, bool with_forward,
     }
     if (f->tgrad && f->w_temporal > 0.f) { rc = bf_temporal_prior(m, f, stream); if (rc) return rc; }
     if (with_forward) { rc = bf_pose_forward(m, f, stream); if (rc) return rc; }
-    const size_t fused_smem = bf_frame_smem(m, &m->act);
+    const size_t fused_smem = bf_frame_smem(m, &m->act, f->Nv, 0);
     const bool fused = fused_smem <= 48 * 1024 && m->act.lv_n;
     // tensor-core path of the fused loop: the GEMM only blends (v_posed); the per-frame kernel skins its live vertices
     const bool blend_only = fused && bf_tc_ready_fwd(&m->act, f) && f->vposed && !(f->flags & BF_F_WORLD);

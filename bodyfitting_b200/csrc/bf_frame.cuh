@@ -17,6 +17,34 @@
 
 #define FR_THREADS 256
 
+// Dynamic shared-memory layout of k_frame_loss_bwd (float offsets, every region 16-byte aligned); host and device use the
+// same function.  TMA = 1 adds the frame's keypoint row and two mbarriers.
+struct FrameSmem {
+    int gx, cam, red, jq, As, dv, vp, outb, kp, bars, total;       // total in floats
+};
+__host__ __device__ __forceinline__ FrameSmem frame_smem_layout(int K, int Nv, int J, int ldn, int lmax, int tma) {
+    FrameSmem L;
+    const int K3 = (3 * K + 3) & ~3;
+    L.gx = 0;                                   // [K*3] joint gradients
+    L.cam = L.gx + K3;                          // [Nv*12]
+    L.red = L.cam + Nv * 12;                    // [5*8]
+    L.jq = L.red + 64;                          // [K*3] joint positions + translation
+    L.As = L.jq + K3;                           // [J*12] this frame's joint transforms
+    L.dv = L.As + ((J * 12 + 15) & ~15);        // [ldn] skinned vertices, later d(verts)
+    L.vp = L.dv + ldn;                          // [ldn] v_posed
+    L.outb = L.vp + ldn;                        // [lmax*12] blended transforms, later d(verts) (x) [v_posed; 1]
+    L.kp = L.outb + 12 * lmax;                  // [K*Nv*3] keypoint row (TMA only)
+    L.bars = L.kp + (tma ? ((K * Nv * 3 + 3) & ~3) : 0);
+    L.total = L.bars + (tma ? 4 : 0);
+    return L;
+}
+
+// wait for a bulk copy: bounded spin, trap instead of hanging the GPU if the copy never lands
+__device__ __forceinline__ void fr_wait(uint64_t* bar) {
+    int spins = 0;
+    while (!tc::mbar_try(bar, 0)) { if (++spins > (1 << 26)) __trap(); }
+}
+
 // 1 / x: hardware approximation (1 ulp) + one Newton step -> within 1 ulp of the correctly rounded value, 3 instructions
 // and no slow path (__frcp_rn costs ~8 instructions and a call for special operands; the loss loop needs 3 per (joint, view))
 __device__ __forceinline__ float rcp_nr(float x) {
@@ -27,52 +55,82 @@ __device__ __forceinline__ float rcp_nr(float x) {
 
 // T = sum_k w_k A[j_k] for vertex v (rows of A in shared memory); NC = 4: full 3x4 rows (forward), 3: rotation part (backward)
 template <int NC>
+__device__ __forceinline__ void blend_accum(const float* As, int j, float w, float (&T)[3 * NC]) {
+    const float4* Aj = reinterpret_cast<const float4*>(As + j * 12);
+    const float4 r0 = Aj[0], r1 = Aj[1], r2 = Aj[2];
+    T[0] = fmaf(w, r0.x, T[0]); T[1] = fmaf(w, r0.y, T[1]); T[2] = fmaf(w, r0.z, T[2]);
+    T[NC] = fmaf(w, r1.x, T[NC]); T[NC + 1] = fmaf(w, r1.y, T[NC + 1]); T[NC + 2] = fmaf(w, r1.z, T[NC + 2]);
+    T[2 * NC] = fmaf(w, r2.x, T[2 * NC]); T[2 * NC + 1] = fmaf(w, r2.y, T[2 * NC + 1]); T[2 * NC + 2] = fmaf(w, r2.z, T[2 * NC + 2]);
+    if (NC == 4) { T[3] = fmaf(w, r0.w, T[3]); T[7] = fmaf(w, r1.w, T[7]); T[11] = fmaf(w, r2.w, T[11]); }
+}
+template <int NC>
 __device__ __forceinline__ void blend_transform(const BfVSet& vs, const float* As, int v, float (&T)[3 * NC]) {
     const int nnz = vs.nnz;
-    const int32_t* ej = vs.ell_j + (size_t)v * nnz;
-    const float* ew = vs.ell_w + (size_t)v * nnz;
 #pragma unroll
     for (int e = 0; e < 3 * NC; ++e) T[e] = 0.f;
-    for (int k = 0; k < nnz; ++k) {
-        const float w = __ldg(ew + k);
-        const float4* Aj = reinterpret_cast<const float4*>(As + __ldg(ej + k) * 12);
-        const float4 r0 = Aj[0], r1 = Aj[1], r2 = Aj[2];
-        T[0] = fmaf(w, r0.x, T[0]); T[1] = fmaf(w, r0.y, T[1]); T[2] = fmaf(w, r0.z, T[2]);
-        T[NC] = fmaf(w, r1.x, T[NC]); T[NC + 1] = fmaf(w, r1.y, T[NC + 1]); T[NC + 2] = fmaf(w, r1.z, T[NC + 2]);
-        T[2 * NC] = fmaf(w, r2.x, T[2 * NC]); T[2 * NC + 1] = fmaf(w, r2.y, T[2 * NC + 1]); T[2 * NC + 2] = fmaf(w, r2.z, T[2 * NC + 2]);
-        if (NC == 4) { T[3] = fmaf(w, r0.w, T[3]); T[7] = fmaf(w, r1.w, T[7]); T[11] = fmaf(w, r2.w, T[11]); }
+    if (nnz == 4) {                                   // the usual skinning width: one 16-byte load each for joints and weights
+        const int4 j4 = __ldg(reinterpret_cast<const int4*>(vs.ell_j) + v);
+        const float4 w4 = __ldg(reinterpret_cast<const float4*>(vs.ell_w) + v);
+        blend_accum<NC>(As, j4.x, w4.x, T); blend_accum<NC>(As, j4.y, w4.y, T);
+        blend_accum<NC>(As, j4.z, w4.z, T); blend_accum<NC>(As, j4.w, w4.w, T);
+        return;
     }
+    const int32_t* ej = vs.ell_j + (size_t)v * nnz;
+    const float* ew = vs.ell_w + (size_t)v * nnz;
+    for (int k = 0; k < nnz; ++k) blend_accum<NC>(As, __ldg(ej + k), __ldg(ew + k), T);
 }
 
 // Work is restricted to the frame's LIVE vertices: the static picks / landmarks plus the 17 x 3 contour vertices of
 // the frame's yaw row (vs.lv_* / lt_* / lj_*, built per row on the host).  Every other vertex of the active set has
 // an exactly-zero gradient for this frame, so it is neither skinned nor back-propagated; its dvp entries are zeroed.
 // skin_here != 0: v_posed comes from the blend GEMM and the live vertices are skinned in this kernel (f.verts unused).
+// TMA = 1: the frame's transforms, v_posed row and keypoint row (J*48 + 12*n + 12*K*Nv bytes, each one contiguous in
+// HBM) are fetched by three bulk copies issued by one thread at kernel entry; the keypoints land while the vertices are
+// being skinned, so the loss loop reads them from shared memory instead of waiting on HBM.
+template <int TMA>
 __global__ void __launch_bounds__(FR_THREADS, 5) k_frame_loss_bwd(BfModel m, BfVSet vs, BfFrames f, int skin_here) {
     extern __shared__ __align__(16) float sm[];
-    float* gx = sm;                               // [BF_MAXK*3] joint gradients
-    float* cam = gx + BF_MAXK * 3;                // [BF_MAXVIEWS*12]
-    float* red = cam + BF_MAXVIEWS * 12;          // [5*8]
-    float* jq = red + 64;                         // [BF_MAXK*3] joint positions + translation
-    float* As = jq + BF_MAXK * 3;                 // [J*12] this frame's joint transforms
-    float* dv = As + ((m.J * 12 + 15) & ~15);     // [3*n_pad] skinned vertices, later d(verts)
-    float* vp = dv + vs.ldn;                      // [3*n_pad] v_posed
-    float4* outb = reinterpret_cast<float4*>(vp + vs.ldn);      // [lmax*3] d(verts) (x) [v_posed; 1] of every live vertex
     const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int K = m.K_used, Nv = f.Nv, J = m.J;
+    const FrameSmem SL = frame_smem_layout(K, Nv, J, vs.ldn, vs.lmax, TMA);
+    float* gx = sm + SL.gx;
+    float* cam = sm + SL.cam;
+    float* red = sm + SL.red;
+    float* jq = sm + SL.jq;
+    float* As = sm + SL.As;
+    float* dv = sm + SL.dv;
+    float* vp = sm + SL.vp;
+    float4* outb = reinterpret_cast<float4*>(sm + SL.outb);
+    const float* kps = sm + SL.kp;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + SL.bars);
+    const int n4 = (3 * vs.n + 3) / 4;                                  // float4s of a v_posed row; ld_v % 4 == 0 (checked on the host)
+    if (TMA && t == 0) {
+        tc::mbar_init(&bars[0], 1);
+        tc::mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        const uint32_t a_bytes = (uint32_t)J * 48u, v_bytes = (uint32_t)n4 * 16u, k_bytes = (uint32_t)(K * Nv) * 12u;
+        tc::mbar_expect_tx(&bars[0], a_bytes + v_bytes);
+        tc::bulk_g2s(As, f.A + (size_t)b * J * 12, a_bytes, &bars[0]);
+        tc::bulk_g2s(vp, f.vposed + (size_t)b * f.ld_v, v_bytes, &bars[0]);
+        tc::mbar_expect_tx(&bars[1], k_bytes);
+        tc::bulk_g2s(sm + SL.kp, f.kp + (size_t)b * K * Nv * 3, k_bytes, &bars[1]);
+    }
     const int yaw = f.yaw ? f.yaw[b] : 0;
     const int row = vs.n_rows > 1 ? yaw : 0;
     const int L = __ldg(vs.lv_n + row);
     const int32_t* lv = vs.lv_vid + (size_t)row * vs.lmax;
     for (int i = t; i < Nv * 12; i += FR_THREADS) cam[i] = f.cams[i];
     {
-        const float4* src = reinterpret_cast<const float4*>(f.A + (size_t)b * J * 12);
-        for (int i = t; i < J * 3; i += FR_THREADS) reinterpret_cast<float4*>(As)[i] = src[i];
-        const float4* vsrc = reinterpret_cast<const float4*>(f.vposed + (size_t)b * f.ld_v);     // ld_v % 4 == 0 (checked on the host)
-        for (int i = t; i < (3 * vs.n + 3) / 4; i += FR_THREADS) reinterpret_cast<float4*>(vp)[i] = vsrc[i];
+        if (!TMA) {
+            const float4* src = reinterpret_cast<const float4*>(f.A + (size_t)b * J * 12);
+            for (int i = t; i < J * 3; i += FR_THREADS) reinterpret_cast<float4*>(As)[i] = src[i];
+            const float4* vsrc = reinterpret_cast<const float4*>(f.vposed + (size_t)b * f.ld_v);
+            for (int i = t; i < n4; i += FR_THREADS) reinterpret_cast<float4*>(vp)[i] = vsrc[i];
+        }
         if (!skin_here) {
             const float4* wsrc = reinterpret_cast<const float4*>(f.verts + (size_t)b * f.ld_v);
-            for (int i = t; i < (3 * vs.n + 3) / 4; i += FR_THREADS) reinterpret_cast<float4*>(dv)[i] = wsrc[i];
+            for (int i = t; i < n4; i += FR_THREADS) reinterpret_cast<float4*>(dv)[i] = wsrc[i];
         }
     }
     // clear this frame's d(v_posed) rows: only live vertices are written below (a vertex live on another yaw row in an
@@ -80,7 +138,6 @@ __global__ void __launch_bounds__(FR_THREADS, 5) k_frame_loss_bwd(BfModel m, BfV
     const bool split = f.dvp_hi != nullptr;
     {
         const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        const int n4 = (3 * vs.n + 3) / 4;
         if (split) {
             float4* oh = reinterpret_cast<float4*>(f.dvp_hi + (size_t)b * vs.ldn);
             float4* ol = reinterpret_cast<float4*>(f.dvp_lo + (size_t)b * vs.ldn);
@@ -91,6 +148,7 @@ __global__ void __launch_bounds__(FR_THREADS, 5) k_frame_loss_bwd(BfModel m, BfV
         }
     }
     __syncthreads();
+    if (TMA) fr_wait(&bars[0]);                      // transforms + v_posed have landed
     const float* th = f.theta + (size_t)b * m.NP;
     const float tx = th[0], ty = th[1], tz = th[2], sc = th[3];
     const float cs = f.constant_scale;
@@ -126,11 +184,12 @@ __global__ void __launch_bounds__(FR_THREADS, 5) k_frame_loss_bwd(BfModel m, BfV
     // and the joint-major keypoint rows ([B,K,Nv,3]) are read as 16-byte vectors, four views at a time
     float acc5[5] = {0.f, 0.f, 0.f, 0.f, 0.f};               // loss, d/d transl (3), d/d scale
     const bool vec4 = (Nv & 3) == 0;
+    if (TMA) fr_wait(&bars[1]);                      // keypoint row (in flight since kernel entry)
     for (int k = t; k < K; k += FR_THREADS) {
         const float qx = jq[k * 3], qy = jq[k * 3 + 1], qz = jq[k * 3 + 2];
         const float X = qx * sc * cs, Y = qy * sc * cs, Z = qz * sc * cs;
         float g0 = 0.f, g1 = 0.f, g2 = 0.f, ls = 0.f;
-        const float* kpr = f.kp + ((size_t)b * K + k) * Nv * 3;
+        const float* kpr = TMA ? kps + k * Nv * 3 : f.kp + ((size_t)b * K + k) * Nv * 3;
         for (int v0 = 0; v0 < Nv; v0 += 4) {
             float kv[12];
             if (vec4) {
