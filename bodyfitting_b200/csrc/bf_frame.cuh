@@ -20,7 +20,7 @@
 // Dynamic shared-memory layout of k_frame_loss_bwd (float offsets, every region 16-byte aligned); host and device use the
 // same function.  TMA = 1 adds the frame's keypoint row and two mbarriers.
 struct FrameSmem {
-    int gx, cam, red, jq, As, dv, vp, outb, kp, bars, total;       // total in floats
+    int gx, cam, red, As, dv, vp, outb, kp, bars, total;       // total in floats
 };
 __host__ __device__ __forceinline__ FrameSmem frame_smem_layout(int K, int Nv, int J, int ldn, int lmax, int tma) {
     FrameSmem L;
@@ -28,8 +28,7 @@ __host__ __device__ __forceinline__ FrameSmem frame_smem_layout(int K, int Nv, i
     L.gx = 0;                                   // [K*3] joint gradients
     L.cam = L.gx + K3;                          // [Nv*12]
     L.red = L.cam + Nv * 12;                    // [5*8]
-    L.jq = L.red + 64;                          // [K*3] joint positions + translation
-    L.As = L.jq + K3;                           // [J*12] this frame's joint transforms
+    L.As = L.red + 64;                          // [J*12] this frame's joint transforms
     L.dv = L.As + ((J * 12 + 15) & ~15);        // [ldn] skinned vertices, later d(verts)
     L.vp = L.dv + ldn;                          // [ldn] v_posed
     L.outb = L.vp + ldn;                        // [lmax*12] blended transforms, later d(verts) (x) [v_posed; 1]
@@ -96,7 +95,6 @@ __global__ void __launch_bounds__(FR_THREADS, 5) k_frame_loss_bwd(BfModel m, BfV
     float* gx = sm + SL.gx;
     float* cam = sm + SL.cam;
     float* red = sm + SL.red;
-    float* jq = sm + SL.jq;
     float* As = sm + SL.As;
     float* dv = sm + SL.dv;
     float* vp = sm + SL.vp;
@@ -173,20 +171,15 @@ __global__ void __launch_bounds__(FR_THREADS, 5) k_frame_loss_bwd(BfModel m, BfV
         }
         __syncthreads();
     }
-    // joint positions of this frame -> shared (model space + translation, i.e. q = x + T)
-    for (int k = t; k < K; k += FR_THREADS) {
-        float x[3];
-        joint_pos(vs, k, yaw, Jtr_b, dv, x);
-        jq[k * 3] = x[0] + tx; jq[k * 3 + 1] = x[1] + ty; jq[k * 3 + 2] = x[2] + tz;
-    }
-    __syncthreads();
     // one thread per joint, its views in sequence: no cross-lane reduction, world coordinates computed once per joint,
     // and the joint-major keypoint rows ([B,K,Nv,3]) are read as 16-byte vectors, four views at a time
     float acc5[5] = {0.f, 0.f, 0.f, 0.f, 0.f};               // loss, d/d transl (3), d/d scale
     const bool vec4 = (Nv & 3) == 0;
     if (TMA) fr_wait(&bars[1]);                      // keypoint row (in flight since kernel entry)
     for (int k = t; k < K; k += FR_THREADS) {
-        const float qx = jq[k * 3], qy = jq[k * 3 + 1], qz = jq[k * 3 + 2];
+        float x[3];                                  // joint position (model space) + translation: q = x + T
+        joint_pos(vs, k, yaw, Jtr_b, dv, x);
+        const float qx = x[0] + tx, qy = x[1] + ty, qz = x[2] + tz;
         const float X = qx * sc * cs, Y = qy * sc * cs, Z = qz * sc * cs;
         float g0 = 0.f, g1 = 0.f, g2 = 0.f, ls = 0.f;
         const float* kpr = TMA ? kps + k * Nv * 3 : f.kp + ((size_t)b * K + k) * Nv * 3;

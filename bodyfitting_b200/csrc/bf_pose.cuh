@@ -11,23 +11,28 @@
 #pragma once
 #include "bf_common.cuh"
 
-struct PoseSmem {
+// fp | R | Jr | GR are contiguous and 16-byte aligned, in the order of a saved forward-state row ([fp 3J | R 9J | Jr 3J |
+// GR 9J], pose_write_outputs): for J == BF_MAXJ the backward fetches the row with ONE bulk copy.
+struct __align__(16) PoseSmem {
     float th[BF_MAXNP];
-    float fp[BF_MAXJ * 3];
     float sh[BF_MAXNS];
+    float fp[BF_MAXJ * 3];
     float R[BF_MAXJ * 9];
     float Jr[BF_MAXJ * 3];
     float GR[BF_MAXJ * 9];
     float Gt[BF_MAXJ * 3];
 };
+static_assert((BF_MAXNP + BF_MAXNS) % 4 == 0, "PoseSmem::fp must be 16-byte aligned");
 // Backward scratch.  Three more per-joint arrays live in forward slots that are dead by then (smaller footprint ->
 // five CTAs of four frames per SM instead of four): d(rel) in f.Gt (the backward never reads the posed joints), d(full
 // pose) in f.fp (each lane overwrites exactly the three angles it has just consumed) and the updated theta in f.th.
-struct PoseSmemBwd {
+struct __align__(16) PoseSmemBwd {
     PoseSmem f;
     float dGR[BF_MAXJ * 9];
     float dGt[BF_MAXJ * 3];
     float dJr[BF_MAXJ * 3];
+    float g[BF_MAXNP];            // gradient row: assembled on chip, written to f.grad once
+    uint64_t bar;                 // mbarrier of the forward-state bulk copy
 };
 
 // Fills S for frame b (all lanes of one warp participate).
@@ -203,25 +208,77 @@ __global__ void __launch_bounds__(128) k_pose_bwd(BfModel m, BfFrames f, int fla
     float* const dfp = S.fp;
     const int J = m.J;
     const ThetaLayout L = theta_layout(m.is_smplx);
+    // ---- everything this frame reads from HBM is requested up front: the saved forward state by bulk copy (TMA), the
+    // loss kernel's dA / dJtr rows, the Adam moments and the GMM gradient into registers; nothing below waits on HBM again
+    // (J == BF_MAXJ: the row is one contiguous block of PoseSmem; smaller skeletons take the plain loops below)
+    const bool use_bulk = f.fwd_state && J == BF_MAXJ && ((uintptr_t)f.fwd_state & 15) == 0;
+    if (use_bulk) {
+        if (lane == 0) {
+            tc::mbar_init(&W.bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            const float* st = f.fwd_state + (size_t)b * 24 * J;
+            tc::mbar_expect_tx(&W.bar, (uint32_t)(96 * J));
+            tc::bulk_g2s(S.fp, st, (uint32_t)(96 * J), &W.bar);
+        }
+    }
+    float4 dA_r[2][3];
+    float dJ_r[2][3];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        const int j = lane + 32 * s;
+        if (j < J) {
+            const float4* dAj = reinterpret_cast<const float4*>(f.dA + ((size_t)b * J + j) * 12);
+            const float* dJj = f.dJtr + ((size_t)b * J + j) * 3;
+            dA_r[s][0] = dAj[0]; dA_r[s][1] = dAj[1]; dA_r[s][2] = dAj[2];
+            dJ_r[s][0] = dJj[0]; dJ_r[s][1] = dJj[1]; dJ_r[s][2] = dJj[2];
+        }
+    }
+    float am_r[4], av_r[4], gg_r[3];
+    if (flags & 2) {
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            const int i = lane + 32 * s;
+            if (i < m.NP) { am_r[s] = f.adam_m[(size_t)b * m.NP + i]; av_r[s] = f.adam_v[(size_t)b * m.NP + i]; }
+        }
+    }
+    if (flags & 1) {
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+            const int i = lane + 32 * s;
+            gg_r[s] = i < L.nbody ? f.gmm_grad[(size_t)b * BF_GMM_D + i] : 0.f;
+        }
+    }
+    float* const g = W.g;
+    if (lane < 4) g[lane] = (flags & 4) ? f.grad[(size_t)b * m.NP + lane] : 0.f;
     if (f.fwd_state) {                       // forward state saved by the pose forward of this iteration
-        const float* st = f.fwd_state + (size_t)b * 24 * J;
         for (int i = lane; i < L.np; i += 32) S.th[i] = f.theta[(size_t)b * m.NP + i];
-        for (int i = lane; i < 3 * J; i += 32) { S.fp[i] = st[i]; S.Jr[i] = st[12 * J + i]; }
-        for (int i = lane; i < 9 * J; i += 32) { S.R[i] = st[3 * J + i]; S.GR[i] = st[15 * J + i]; }
+        if (use_bulk) {
+            __syncwarp();                    // the barrier init (lane 0) is visible to the whole warp
+            int spins = 0;
+            while (!tc::mbar_try(&W.bar, 0)) { if (++spins > (1 << 26)) __trap(); }
+        } else {
+            const float* st = f.fwd_state + (size_t)b * 24 * J;
+            for (int i = lane; i < 3 * J; i += 32) { S.fp[i] = st[i]; S.Jr[i] = st[12 * J + i]; }
+            for (int i = lane; i < 9 * J; i += 32) { S.R[i] = st[3 * J + i]; S.GR[i] = st[15 * J + i]; }
+        }
         __syncwarp();
     } else {
         pose_forward_warp(m, f.theta + (size_t)b * m.NP, S, lane);
     }
 
     // direct terms
-    for (int j = lane; j < J; j += 32) {
-        const float* dAj = f.dA + ((size_t)b * J + j) * 12;
-        const float* dJj = f.dJtr + ((size_t)b * J + j) * 3;
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        const int j = lane + 32 * s;
+        if (j >= J) break;
+        const float dAj[12] = {dA_r[s][0].x, dA_r[s][0].y, dA_r[s][0].z, dA_r[s][0].w, dA_r[s][1].x, dA_r[s][1].y, dA_r[s][1].z, dA_r[s][1].w,
+                               dA_r[s][2].x, dA_r[s][2].y, dA_r[s][2].z, dA_r[s][2].w};
         float dAt[3];
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
             dAt[r] = dAj[r * 4 + 3];
-            W.dGt[j * 3 + r] = dJj[r] + dAt[r];
+            W.dGt[j * 3 + r] = dJ_r[s][r] + dAt[r];
 #pragma unroll
             for (int c = 0; c < 3; ++c) W.dGR[j * 9 + r * 3 + c] = dAj[r * 4 + c] - dAt[r] * S.Jr[j * 3 + c];
         }
@@ -311,15 +368,17 @@ __global__ void __launch_bounds__(128) k_pose_bwd(BfModel m, BfFrames f, int fla
     }
     __syncwarp();
 
-    float* g = f.grad + (size_t)b * m.NP;
     // betas: rest-joint path + shape rows of the blend GEMM
     {
         // lanes (l, part): 3 parts split the 3J rest-joint coordinates, combined in a fixed order
         const int l = lane % m.NB, part = lane / m.NB;
         const int nq = 3 * J, per = (nq + 2) / 3;
         float acc = 0.f;
-        if (part < 3)
-            for (int q = part * per; q < min(nq, (part + 1) * per); ++q) acc += __ldg(m.Jd + q * m.NS + l) * W.dJr[q];
+        if (part < 3) {
+            const int q1 = min(nq, (part + 1) * per);
+#pragma unroll 5
+            for (int q = part * per; q < q1; ++q) acc += __ldg(m.Jd + q * m.NS + l) * W.dJr[q];
+        }
         const float a1 = __shfl_sync(0xffffffffu, acc, (lane + m.NB) & 31);
         const float a2 = __shfl_sync(0xffffffffu, acc, (lane + 2 * m.NB) & 31);
         if (lane < m.NB) g[L.off_betas + lane] = f.dpf[(size_t)b * m.Kp + m.P + lane] + ((acc + a1) + a2);
@@ -332,17 +391,21 @@ __global__ void __launch_bounds__(128) k_pose_bwd(BfModel m, BfFrames f, int fla
             const float* comp = (lane < 6 ? m.hand_l : m.hand_r) + c * 45;
             const float* d = dfp + (lane < 6 ? 75 : 120);
             float acc = 0.f;
+#pragma unroll 9
             for (int i = 0; i < 45; ++i) acc += __ldg(comp + i) * d[i];
             g[(lane < 6 ? L.off_lh : L.off_rh) + c] = acc;
         }
     }
-    if (!(flags & 4) && lane < 4) g[lane] = 0.f;
     __syncwarp();
 
     float total = (flags & 4) ? f.loss[b] : 0.f;
     if (flags & 1) {
         // ---- GMM pose prior: value and gradient come from k_gmm_prior (bf_gmm.cuh) ----
-        for (int i = lane; i < L.nbody; i += 32) g[7 + i] += f.gmm_grad[(size_t)b * BF_GMM_D + i];
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+            const int i = lane + 32 * s;
+            if (i < L.nbody) g[7 + i] += gg_r[s];
+        }
         const float pose_l = f.gmm_loss[b];
         __syncwarp();
         // ---- temporal smoothness (optional, bf_temporal_prior) ----
@@ -383,15 +446,19 @@ __global__ void __launch_bounds__(128) k_pose_bwd(BfModel m, BfFrames f, int fla
         if (f.trace) f.trace[(size_t)f.iter * f.B + b] = total;
     }
     __syncwarp();
+    for (int i = lane; i < m.NP; i += 32) f.grad[(size_t)b * m.NP + i] = g[i];
     if (flags & 2) {
         // torch.optim.Adam (torch 2.x single-tensor path): m.lerp_(g, 1-b1); v = v*b2 + (1-b2) g g;
         // denom = sqrt(v)/sqrt(bc2) + eps; p -= (lr/bc1) * m / denom
         float* th = f.theta + (size_t)b * m.NP;
         float* am = f.adam_m + (size_t)b * m.NP;
         float* av = f.adam_v + (size_t)b * m.NP;
-        for (int i = lane; i < m.NP; i += 32) {
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            const int i = lane + 32 * s;
+            if (i >= m.NP) break;
             const float gi = g[i];
-            float mi = am[i], vi = av[i];
+            float mi = am_r[s], vi = av_r[s];              // loaded at kernel entry
             mi = mi + (gi - mi) * ad.om_beta1;
             vi = vi * ad.beta2 + ad.om_beta2 * gi * gi;
             const float denom = sqrtf(vi) / ad.bc2_sqrt + ad.eps;
