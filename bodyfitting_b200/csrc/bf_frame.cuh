@@ -226,46 +226,45 @@ __global__ void __launch_bounds__(FR_THREADS, 5) k_frame_loss_bwd(BfModel m, BfV
         acc5[1] += g0 * k0s; acc5[2] += g1 * k0s; acc5[3] += g2 * k0s;
         acc5[4] += (g0 * qx + g1 * qy + g2 * qz) * cs;
     }
+    const int nwk = (K + 31) >> 5;                   // warps that own joints; the others hold zeros
+    if (warp < nwk) {
 #pragma unroll
-    for (int i = 0; i < 5; ++i) {
-        const float s = warp_sum(acc5[i]);
-        if (lane == 0) red[i * 8 + warp] = s;
+        for (int i = 0; i < 5; ++i) {
+            const float s = warp_sum(acc5[i]);
+            if (lane == 0) red[i * 8 + warp] = s;
+        }
     }
-    __syncthreads();                               // gx + red complete; skinned vertices (dv) no longer needed
+    __syncthreads();                               // gx + red complete
     if (t == 0) {
         float tot[5];
-        for (int i = 0; i < 5; ++i) { float s = 0.f; for (int w = 0; w < FR_THREADS / 32; ++w) s += red[i * 8 + w]; tot[i] = s; }
+        for (int i = 0; i < 5; ++i) { float s = 0.f; for (int w = 0; w < nwk; ++w) s += red[i * 8 + w]; tot[i] = s; }
         f.loss[b] = tot[0] * invNv;
         float* g = f.grad + (size_t)b * m.NP;
         g[0] = tot[1]; g[1] = tot[2]; g[2] = tot[3]; g[3] = tot[4];
     }
-    // joint gradients -> chain joints (static gather by target) and live vertices (per-row gather lists)
+    // joint gradients -> chain joints (static gather by target; the threads at the top of the block, idle below)
     float* dJtr_b = f.dJtr + (size_t)b * J * 3;
-    const int32_t* ltp = vs.lt_ptr + (size_t)row * (vs.lmax + 1);
-    for (int i = t; i < J + L; i += FR_THREADS) {
+    for (int i = FR_THREADS - 1 - t; i < J; i += FR_THREADS) {
         float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-        if (i < J) {
-            const int e0 = __ldg(vs.tg_ptr + i), e1 = __ldg(vs.tg_ptr + i + 1);
-            for (int e = e0; e < e1; ++e) {
-                const int k = __ldg(vs.tg_k + e);
-                if (k < K) { const float w = __ldg(vs.tg_w + e); a0 += w * gx[k * 3]; a1 += w * gx[k * 3 + 1]; a2 += w * gx[k * 3 + 2]; }
-            }
-            dJtr_b[i * 3] = a0; dJtr_b[i * 3 + 1] = a1; dJtr_b[i * 3 + 2] = a2;
-        } else {
-            const int li = i - J;
-            const int e0 = __ldg(ltp + li), e1 = __ldg(ltp + li + 1);
+        const int e0 = __ldg(vs.tg_ptr + i), e1 = __ldg(vs.tg_ptr + i + 1);
+        for (int e = e0; e < e1; ++e) {
+            const int k = __ldg(vs.tg_k + e);
+            if (k < K) { const float w = __ldg(vs.tg_w + e); a0 += w * gx[k * 3]; a1 += w * gx[k * 3 + 1]; a2 += w * gx[k * 3 + 2]; }
+        }
+        dJtr_b[i * 3] = a0; dJtr_b[i * 3 + 1] = a1; dJtr_b[i * 3 + 2] = a2;
+    }
+    // live vertices: gather d(vertex) from the joints it feeds (per-row lists) and back-propagate it through the skinning
+    // right away -- d(verts) stays in registers: dvp = (sum_k w_k A_jk)[:3,:3]^T dverts
+    const int32_t* ltp = vs.lt_ptr + (size_t)row * (vs.lmax + 1);
+    for (int i = t; i < L; i += FR_THREADS) {
+        float gx_ = 0.f, gy_ = 0.f, gz_ = 0.f;
+        {
+            const int e0 = __ldg(ltp + i), e1 = __ldg(ltp + i + 1);
             for (int e = e0; e < e1; ++e) {
                 const int k = __ldg(vs.lt_k + e);
-                if (k < K) { const float w = __ldg(vs.lt_w + e); a0 += w * gx[k * 3]; a1 += w * gx[k * 3 + 1]; a2 += w * gx[k * 3 + 2]; }
+                if (k < K) { const float w = __ldg(vs.lt_w + e); gx_ += w * gx[k * 3]; gy_ += w * gx[k * 3 + 1]; gz_ += w * gx[k * 3 + 2]; }
             }
-            const int v = __ldg(lv + li);
-            dv[3 * v] = a0; dv[3 * v + 1] = a1; dv[3 * v + 2] = a2;
         }
-    }
-    __syncthreads();
-
-    // skinning backward, vertex side (live vertices): dvp = (sum_k w_k A_jk)[:3,:3]^T dverts
-    for (int i = t; i < L; i += FR_THREADS) {
         const int v = __ldg(lv + i);
         float T[9];
         if (skin_here) {                               // blended transform saved by the forward skinning above
@@ -274,7 +273,6 @@ __global__ void __launch_bounds__(FR_THREADS, 5) k_frame_loss_bwd(BfModel m, BfV
         } else {
             blend_transform<3>(vs, As, v, T);
         }
-        const float gx_ = dv[3 * v], gy_ = dv[3 * v + 1], gz_ = dv[3 * v + 2];
         const float o0 = T[0] * gx_ + T[3] * gy_ + T[6] * gz_;
         const float o1 = T[1] * gx_ + T[4] * gy_ + T[7] * gz_;
         const float o2 = T[2] * gx_ + T[5] * gy_ + T[8] * gz_;
