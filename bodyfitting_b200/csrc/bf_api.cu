@@ -362,7 +362,9 @@ int bf_pose_backward(const BfModel* m, const BfFrames* f, int flags, void* strea
     ad.om_beta1 = (float)(1.0 - f->beta1);
     ad.om_beta2 = (float)(1.0 - f->beta2);
     ad.eps = (float)f->eps;
-    const int wpb = 4;
+    // frames (warps) per CTA: shared memory bounds the residency (8.4 KB per frame + 1 KB per CTA): 4 -> 24, 2 -> 26 warps / SM
+    static int wpb = 0;
+    if (!wpb) { const char* e = getenv("BODYFIT_POSE_WPB"); wpb = e ? atoi(e) : 2; if (wpb < 1 || wpb > 4) wpb = 2; }
     const dim3 grid((f->B + wpb - 1) / wpb), block(32 * wpb);
     k_pose_bwd<<<grid, block, wpb * sizeof(PoseSmemBwd), (cudaStream_t)stream>>>(*m, *f, flags, ad);
     BF_LAUNCH_CHECK();

@@ -515,10 +515,25 @@ static int bf_blend_backward_tc(const BfModel* m, const BfVSet* vs, const BfFram
         attr = smem;
     }
     const int num_k = vs->ldn / TC_BK;
-    const int cps = 2048 / TC_BK;                         // <= 2048 coordinates per tensor-core accumulation run
-    const int S = (num_k + cps - 1) / cps;
     const size_t stride = (size_t)f->B * m->Kp;
+    // split-K: at most 2048 coordinates per tensor-core accumulation run (accuracy, see above); when the (frame tile x
+    // column tile) grid alone leaves SMs idle -- the all-vertex backward of a ~1000-frame batch has 8 tiles and a 20k-long
+    // reduction -- the reduction is cut further, into as many runs as fill the SMs once (workspace permitting)
+    int cps = 2048 / TC_BK;
+    int S = (num_k + cps - 1) / cps;
     if (S > 1 && (!f->ws || (size_t)f->ws_floats < (size_t)S * stride)) return 1;   // caller falls back to the FFMA kernel
+    {
+        const int tiles = (m->Kp / BN) * ((f->B + TC_BM - 1) / TC_BM);
+        int S_fill = num_sms / tiles;
+        if (S_fill > num_k) S_fill = num_k;
+        static int fill_env = -1;                         // BODYFIT_BWD_FILL=0: accuracy-only split (A/B timing)
+        if (fill_env < 0) { const char* e = getenv("BODYFIT_BWD_FILL"); fill_env = e ? atoi(e) : 1; }
+        if (!fill_env) S_fill = 0;
+        if (S_fill > S && f->ws && (size_t)f->ws_floats >= (size_t)S_fill * stride) {
+            cps = (num_k + S_fill - 1) / S_fill;
+            S = (num_k + cps - 1) / cps;
+        }
+    }
     const dim3 grid(m->Kp / BN, (f->B + TC_BM - 1) / TC_BM, S);
     k_blend_bwd_tc<<<grid, 192, smem, s>>>(a_hi, a_lo, b_hi, b_lo, BN, num_k, cps, m->Kp, S > 1 ? f->ws : f->dpf, stride, f->B);
     BF_LAUNCH_CHECK();

@@ -23,17 +23,17 @@ struct __align__(16) PoseSmem {
     float Gt[BF_MAXJ * 3];
 };
 static_assert((BF_MAXNP + BF_MAXNS) % 4 == 0, "PoseSmem::fp must be 16-byte aligned");
-// Backward scratch.  Three more per-joint arrays live in forward slots that are dead by then (smaller footprint ->
-// five CTAs of four frames per SM instead of four): d(rel) in f.Gt (the backward never reads the posed joints), d(full
-// pose) in f.fp (each lane overwrites exactly the three angles it has just consumed) and the updated theta in f.th.
+// Backward scratch.  Everything else the backward needs lives in forward slots that are dead by then (smaller footprint ->
+// six CTAs of four frames per SM): d(posed joints) and later d(rel) in f.Gt (the backward never reads the posed joints),
+// d(full pose) in f.fp (each lane overwrites exactly the three angles it has just consumed), the updated theta in f.th, and --
+// once the reverse chain traversal is done with the local rotations -- the gradient row in f.R[0:NP] and d(rest joints) in
+// f.R[128:128+3J] (until then each lane keeps the d(rest joints) of its own joints in registers).
 struct __align__(16) PoseSmemBwd {
     PoseSmem f;
     float dGR[BF_MAXJ * 9];
-    float dGt[BF_MAXJ * 3];
-    float dJr[BF_MAXJ * 3];
-    float g[BF_MAXNP];            // gradient row: assembled on chip, written to f.grad once
     uint64_t bar;                 // mbarrier of the forward-state bulk copy
 };
+static_assert(BF_MAXNP <= 128 && 128 + BF_MAXJ * 3 <= BF_MAXJ * 9, "gradient row / d(rest joints) must fit into PoseSmem::R");
 
 // Fills S for frame b (all lanes of one warp participate).
 __device__ __forceinline__ void pose_forward_from_smem(const BfModel& m, PoseSmem& S, int lane);
@@ -79,12 +79,29 @@ __device__ __forceinline__ void pose_forward_from_smem(const BfModel& m, PoseSme
         rodrigues_fwd(S.fp[3 * j], S.fp[3 * j + 1], S.fp[3 * j + 2], R);
 #pragma unroll
         for (int e = 0; e < 9; ++e) S.R[j * 9 + e] = R[e];
+        if (m.NB == 10 && (m.NS & 3) == 0) {          // the usual 10 betas: three vector loads per regressor row
+            float sh[10];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            float acc = 0.f;
-            const float* jd = m.Jd + (j * 3 + c) * m.NS;
-            for (int l = 0; l < m.NB; ++l) acc += __ldg(jd + l) * S.sh[l];     // sh[l] = 0 for l >= NB (expression)
-            S.Jr[j * 3 + c] = __ldg(m.Jt + j * 3 + c) + acc;
+            for (int l = 0; l < 10; ++l) sh[l] = S.sh[l];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float* jd = m.Jd + (j * 3 + c) * m.NS;
+                const float4 a = __ldg(reinterpret_cast<const float4*>(jd)), q = __ldg(reinterpret_cast<const float4*>(jd) + 1);
+                const float2 r = __ldg(reinterpret_cast<const float2*>(jd) + 4);
+                float acc = 0.f;                       // same order as the scalar loop below
+                acc += a.x * sh[0]; acc += a.y * sh[1]; acc += a.z * sh[2]; acc += a.w * sh[3];
+                acc += q.x * sh[4]; acc += q.y * sh[5]; acc += q.z * sh[6]; acc += q.w * sh[7];
+                acc += r.x * sh[8]; acc += r.y * sh[9];
+                S.Jr[j * 3 + c] = __ldg(m.Jt + j * 3 + c) + acc;
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                float acc = 0.f;
+                const float* jd = m.Jd + (j * 3 + c) * m.NS;
+                for (int l = 0; l < m.NB; ++l) acc += __ldg(jd + l) * S.sh[l];     // sh[l] = 0 for l >= NB (expression)
+                S.Jr[j * 3 + c] = __ldg(m.Jt + j * 3 + c) + acc;
+            }
         }
     }
     __syncwarp();
@@ -249,8 +266,9 @@ __global__ void __launch_bounds__(128) k_pose_bwd(BfModel m, BfFrames f, int fla
             gg_r[s] = i < L.nbody ? f.gmm_grad[(size_t)b * BF_GMM_D + i] : 0.f;
         }
     }
-    float* const g = W.g;
-    if (lane < 4) g[lane] = (flags & 4) ? f.grad[(size_t)b * m.NP + lane] : 0.f;
+    float* const g = S.R;                    // gradient row: live from the betas phase on (S.R is dead by then)
+    float* const dJr_s = S.R + 128;          // d(rest joints), same
+    const float g_ts = (lane < 4 && (flags & 4)) ? f.grad[(size_t)b * m.NP + lane] : 0.f;     // d/d(transl, scale) from the loss kernel
     if (f.fwd_state) {                       // forward state saved by the pose forward of this iteration
         for (int i = lane; i < L.np; i += 32) S.th[i] = f.theta[(size_t)b * m.NP + i];
         if (use_bulk) {
@@ -268,6 +286,7 @@ __global__ void __launch_bounds__(128) k_pose_bwd(BfModel m, BfFrames f, int fla
     }
 
     // direct terms
+    float dJr_r[2][3];
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
         const int j = lane + 32 * s;
@@ -278,14 +297,14 @@ __global__ void __launch_bounds__(128) k_pose_bwd(BfModel m, BfFrames f, int fla
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
             dAt[r] = dAj[r * 4 + 3];
-            W.dGt[j * 3 + r] = dJ_r[s][r] + dAt[r];
+            S.Gt[j * 3 + r] = dJ_r[s][r] + dAt[r];
 #pragma unroll
             for (int c = 0; c < 3; ++c) W.dGR[j * 9 + r * 3 + c] = dAj[r * 4 + c] - dAt[r] * S.Jr[j * 3 + c];
         }
 #pragma unroll
         for (int c = 0; c < 3; ++c)
-            W.dJr[j * 3 + c] = -(S.GR[j * 9 + 0 * 3 + c] * dAt[0] + S.GR[j * 9 + 1 * 3 + c] * dAt[1] +
-                                 S.GR[j * 9 + 2 * 3 + c] * dAt[2]);
+            dJr_r[s][c] = -(S.GR[j * 9 + 0 * 3 + c] * dAt[0] + S.GR[j * 9 + 1 * 3 + c] * dAt[1] +
+                            S.GR[j * 9 + 2 * 3 + c] * dAt[2]);
     }
     __syncwarp();
     // reverse traversal: a joint gathers from its children (one level deeper, already final)
@@ -298,7 +317,7 @@ __global__ void __launch_bounds__(128) k_pose_bwd(BfModel m, BfFrames f, int fla
 #pragma unroll
             for (int e = 0; e < 9; ++e) aR[e] = W.dGR[j * 9 + e];
 #pragma unroll
-            for (int c = 0; c < 3; ++c) { aT[c] = W.dGt[j * 3 + c]; pj[c] = S.Jr[j * 3 + c]; }
+            for (int c = 0; c < 3; ++c) { aT[c] = S.Gt[j * 3 + c]; pj[c] = S.Jr[j * 3 + c]; }
             for (int q = c0; q < c1; ++q) {
                 const int ch = __ldg(m.child_idx + q);
                 float rel[3], Rc[9];
@@ -309,7 +328,7 @@ __global__ void __launch_bounds__(128) k_pose_bwd(BfModel m, BfFrames f, int fla
 #pragma unroll
                 for (int r = 0; r < 3; ++r) {
                     const float g0 = W.dGR[ch * 9 + r * 3], g1 = W.dGR[ch * 9 + r * 3 + 1], g2 = W.dGR[ch * 9 + r * 3 + 2];
-                    const float gt = W.dGt[ch * 3 + r];
+                    const float gt = S.Gt[ch * 3 + r];
 #pragma unroll
                     for (int c = 0; c < 3; ++c)   // dGR_p += dGR_c R_c^T + dGt_c (x) rel_c
                         aR[r * 3 + c] += g0 * Rc[c * 3] + g1 * Rc[c * 3 + 1] + g2 * Rc[c * 3 + 2] + gt * rel[c];
@@ -319,7 +338,7 @@ __global__ void __launch_bounds__(128) k_pose_bwd(BfModel m, BfFrames f, int fla
 #pragma unroll
             for (int e = 0; e < 9; ++e) W.dGR[j * 9 + e] = aR[e];
 #pragma unroll
-            for (int c = 0; c < 3; ++c) W.dGt[j * 3 + c] = aT[c];
+            for (int c = 0; c < 3; ++c) S.Gt[j * 3 + c] = aT[c];
         }
         __syncwarp();
     }
@@ -330,7 +349,7 @@ __global__ void __launch_bounds__(128) k_pose_bwd(BfModel m, BfFrames f, int fla
 #pragma unroll
             for (int e = 0; e < 9; ++e) dR[e] = W.dGR[e];
 #pragma unroll
-            for (int c = 0; c < 3; ++c) dr[c] = W.dGt[c];
+            for (int c = 0; c < 3; ++c) dr[c] = S.Gt[c];
         } else {
             const int p = __ldg(m.parents + j);
 #pragma unroll
@@ -340,8 +359,8 @@ __global__ void __launch_bounds__(128) k_pose_bwd(BfModel m, BfFrames f, int fla
                     dR[r * 3 + c] = S.GR[p * 9 + 0 * 3 + r] * W.dGR[j * 9 + 0 * 3 + c] +
                                     S.GR[p * 9 + 1 * 3 + r] * W.dGR[j * 9 + 1 * 3 + c] +
                                     S.GR[p * 9 + 2 * 3 + r] * W.dGR[j * 9 + 2 * 3 + c];
-                dr[r] = S.GR[p * 9 + 0 * 3 + r] * W.dGt[j * 3 + 0] + S.GR[p * 9 + 1 * 3 + r] * W.dGt[j * 3 + 1] +
-                        S.GR[p * 9 + 2 * 3 + r] * W.dGt[j * 3 + 2];
+                dr[r] = S.GR[p * 9 + 0 * 3 + r] * S.Gt[j * 3 + 0] + S.GR[p * 9 + 1 * 3 + r] * S.Gt[j * 3 + 1] +
+                        S.GR[p * 9 + 2 * 3 + r] * S.Gt[j * 3 + 2];
             }
             const float* dpf = f.dpf + (size_t)b * m.Kp + (j - 1) * 9;
 #pragma unroll
@@ -355,7 +374,10 @@ __global__ void __launch_bounds__(128) k_pose_bwd(BfModel m, BfFrames f, int fla
         for (int c = 0; c < 3; ++c) dfp[j * 3 + c] = g[c];
     }
     __syncwarp();
-    for (int j = lane; j < J; j += 32) {
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        const int j = lane + 32 * s;
+        if (j >= J) break;
         float acc[3] = {drel[j * 3], drel[j * 3 + 1], drel[j * 3 + 2]};
         const int c0 = __ldg(m.child_ptr + j), c1 = __ldg(m.child_ptr + j + 1);
         for (int q = c0; q < c1; ++q) {
@@ -364,8 +386,9 @@ __global__ void __launch_bounds__(128) k_pose_bwd(BfModel m, BfFrames f, int fla
             for (int c = 0; c < 3; ++c) acc[c] -= drel[ch * 3 + c];
         }
 #pragma unroll
-        for (int c = 0; c < 3; ++c) W.dJr[j * 3 + c] += acc[c];
+        for (int c = 0; c < 3; ++c) dJr_s[j * 3 + c] = dJr_r[s][c] + acc[c];
     }
+    if (lane < 4) g[lane] = g_ts;
     __syncwarp();
 
     // betas: rest-joint path + shape rows of the blend GEMM
@@ -377,7 +400,7 @@ __global__ void __launch_bounds__(128) k_pose_bwd(BfModel m, BfFrames f, int fla
         if (part < 3) {
             const int q1 = min(nq, (part + 1) * per);
 #pragma unroll 5
-            for (int q = part * per; q < q1; ++q) acc += __ldg(m.Jd + q * m.NS + l) * W.dJr[q];
+            for (int q = part * per; q < q1; ++q) acc += __ldg(m.Jd + q * m.NS + l) * dJr_s[q];
         }
         const float a1 = __shfl_sync(0xffffffffu, acc, (lane + m.NB) & 31);
         const float a2 = __shfl_sync(0xffffffffu, acc, (lane + 2 * m.NB) & 31);

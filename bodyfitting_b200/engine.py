@@ -67,9 +67,12 @@ class FrameBuffers(object):
                 ldn = 3 * model.n_pad_full if full else model.ld_act
                 buf('dvp_hi', B, ldn, zero=True)
                 buf('dvp_lo', B, ldn, zero=True)
-                nsplit = (ldn // 32 + 63) // 64
+                nsplit = (ldn // 32 + 63) // 64          # accuracy: <= 2048 coordinates per accumulation run
                 if nsplit > 1:
-                    buf('ws', nsplit, B, Kp)
+                    # + room to cut the reduction further when the tile grid alone would leave SMs idle (small batches)
+                    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+                    tiles = ((B + 127) // 128) * max(1, Kp // 256)
+                    buf('ws', max(nsplit, min(64, sms // tiles)), B, Kp)
             buf('loss_terms', B, 4, zero=True)
             if tc and model.n_gmm and model.n_gmm * 72 % 192 == 0:
                 buf('gmm_ws', B, model.n_gmm * 72 + 160)
