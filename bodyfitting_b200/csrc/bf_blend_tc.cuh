@@ -526,8 +526,11 @@ static int bf_blend_backward_tc(const BfModel* m, const BfVSet* vs, const BfFram
         const int tiles = (m->Kp / BN) * ((f->B + TC_BM - 1) / TC_BM);
         int S_fill = num_sms / tiles;
         if (S_fill > num_k) S_fill = num_k;
-        static int fill_env = -1;                         // BODYFIT_BWD_FILL=0: accuracy-only split (A/B timing)
-        if (fill_env < 0) { const char* e = getenv("BODYFIT_BWD_FILL"); fill_env = e ? atoi(e) : 1; }
+        // Off by default: the GEMM alone gets faster (SMPL x 1024 frames: 100 -> 77 us) but the all-vertex backward as a whole
+        // slower (327 -> 341 us) -- its 144 large-shared-memory CTAs crowd out the dA gather kernel that runs next to it on the
+        // side stream, which is the longer of the two.  BODYFIT_BWD_FILL=1 enables it.
+        static int fill_env = -1;
+        if (fill_env < 0) { const char* e = getenv("BODYFIT_BWD_FILL"); fill_env = e ? atoi(e) : 0; }
         if (!fill_env) S_fill = 0;
         if (S_fill > S && f->ws && (size_t)f->ws_floats >= (size_t)S_fill * stride) {
             cps = (num_k + S_fill - 1) / S_fill;
