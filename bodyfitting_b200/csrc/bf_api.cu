@@ -15,6 +15,7 @@
 #include "bf_mask.cuh"
 #include "../../include/bodyfit_b200_ops.h"
 #include "bf_blend_tc.cuh"
+#include "bf_blend_tc2.cuh"
 
 static thread_local char g_err[512] = "";
 

@@ -94,12 +94,13 @@ struct Pipe {
     __device__ __forceinline__ uint8_t* stage(int s) const { return stage_base + (size_t)s * stage_bytes(); }
 };
 
+template <int NS>
 __device__ __forceinline__ void producer(const Pipe& p, const CUtensorMap* mA_hi, const CUtensorMap* mA_lo,
                                          const CUtensorMap* mB_hi, const CUtensorMap* mB_lo, int num_k, int rowA, int rowB,
                                          int kc_begin = 0) {
     for (int kc = 0; kc < num_k; ++kc) {
-        const int s = kc % TC_STAGES;
-        const uint32_t ph = (kc / TC_STAGES) & 1;
+        const int s = kc % NS;
+        const uint32_t ph = (kc / NS) & 1;
         mbar_wait(&p.empty[s], ph ^ 1);
         mbar_expect_tx(&p.full[s], p.stage_bytes());
         uint8_t* st = p.stage(s);
@@ -111,10 +112,11 @@ __device__ __forceinline__ void producer(const Pipe& p, const CUtensorMap* mA_hi
     }
 }
 
+template <int NS>
 __device__ __forceinline__ void mma_issuer(const Pipe& p, int num_k, uint32_t tmem_d, uint32_t idesc) {
     for (int kc = 0; kc < num_k; ++kc) {
-        const int s = kc % TC_STAGES;
-        const uint32_t ph = (kc / TC_STAGES) & 1;
+        const int s = kc % NS;
+        const uint32_t ph = (kc / NS) & 1;
         mbar_wait(&p.full[s], ph);
         tc_fence_after();
         uint8_t* st = p.stage(s);
@@ -324,7 +326,10 @@ k_blend_fwd_tc(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant_
     }
 }
 
-// dpf[b, k0 + c] = sum_n dvp[b, n] Bm[k0 + c, n]; BN = columns of this CTA (multiple of 16, <= 256)
+// dpf[b, k0 + c] = sum_n dvp[b, n] Bm[k0 + c, n]; BN = columns of this CTA (multiple of 16, <= 256); NS = pipeline stages
+// (4: one CTA per SM; 2 with BN <= 128: 67 KB and 128 TMEM columns per CTA, so three CTAs share an SM and a grid a little
+// larger than the SM count does not leave a nearly empty second wave)
+template <int NS>
 __global__ void __launch_bounds__(192, 1) k_blend_bwd_tc(const __grid_constant__ CUtensorMap mA_hi,
                                                          const __grid_constant__ CUtensorMap mA_lo,
                                                          const __grid_constant__ CUtensorMap mB_hi,
@@ -337,9 +342,9 @@ __global__ void __launch_bounds__(192, 1) k_blend_bwd_tc(const __grid_constant__
     p.a_bytes = TC_BM * TC_ROWB;
     p.b_bytes = (uint32_t)BN * TC_ROWB;
     p.stage_base = base;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(base + TC_STAGES * p.stage_bytes());
-    p.full = bars; p.empty = bars + TC_STAGES; p.tmem_full = bars + 2 * TC_STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 1);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base + NS * p.stage_bytes());
+    p.full = bars; p.empty = bars + NS; p.tmem_full = bars + 2 * NS;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b0 = blockIdx.y * TC_BM;
@@ -352,7 +357,7 @@ __global__ void __launch_bounds__(192, 1) k_blend_bwd_tc(const __grid_constant__
     float* dpf = out + (size_t)blockIdx.z * split_stride;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) { tc::mbar_init(&p.full[s], 1); tc::mbar_init(&p.empty[s], 1); }
+        for (int s = 0; s < NS; ++s) { tc::mbar_init(&p.full[s], 1); tc::mbar_init(&p.empty[s], 1); }
         tc::mbar_init(p.tmem_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -366,9 +371,9 @@ __global__ void __launch_bounds__(192, 1) k_blend_bwd_tc(const __grid_constant__
     const uint32_t tmem_d = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) tc::producer(p, &mA_hi, &mA_lo, &mB_hi, &mB_lo, num_k, b0, k0, kc_begin);
+        if (lane == 0) tc::producer<NS>(p, &mA_hi, &mA_lo, &mB_hi, &mB_lo, num_k, b0, k0, kc_begin);
     } else if (warp == 1) {
-        if (lane == 0) tc::mma_issuer(p, num_k, tmem_d, tc::make_idesc_tf32(TC_BM, BN));
+        if (lane == 0) tc::mma_issuer<NS>(p, num_k, tmem_d, tc::make_idesc_tf32(TC_BM, BN));
     } else {
         tc::mbar_wait(p.tmem_full, 0);
         tc::tc_fence_after();
@@ -479,7 +484,11 @@ static int bf_gemm_forward_tc(const float* a_hi_p, const float* a_lo_p, const fl
 }
 
 // v_posed[B, ld_v] = pf @ Bm (dst = f->vposed, or any [B, ld_v] buffer)
+static int bf_gemm_forward_tc2(const float* a_hi_p, const float* a_lo_p, const float* bt_hi_p, const float* bt_lo_p, int B, int Kp,
+                               int ldn, int n_verts, float* dst, int ld_dst, cudaStream_t s);      // bf_blend_tc2.cuh
 static int bf_blend_forward_tc(const BfModel* m, const BfVSet* vs, const BfFrames* f, float* dst, cudaStream_t s) {
+    const int rc2 = bf_gemm_forward_tc2(f->pf_hi, f->pf_lo, vs->Bt_hi, vs->Bt_lo, f->B, m->Kp, vs->ldn, vs->n, dst, f->ld_v, s);
+    if (rc2 != 1) return rc2;                              // CTA-pair kernel ran (or failed loudly); 1 = not applicable
     return bf_gemm_forward_tc(f->pf_hi, f->pf_lo, vs->Bt_hi, vs->Bt_lo, f->B, m->Kp, vs->ldn, vs->n, dst, f->ld_v, s);
 }
 
@@ -507,12 +516,20 @@ static int bf_blend_backward_tc(const BfModel* m, const BfVSet* vs, const BfFram
     if ((rc = bf_make_map(&a_lo, f->dvp_lo, f->B, vs->ldn, vs->ldn, TC_BM))) return rc;
     if ((rc = bf_make_map(&b_hi, vs->Bm_hi, m->Kp, vs->ldn, vs->ldn, BN))) return rc;
     if ((rc = bf_make_map(&b_lo, vs->Bm_lo, m->Kp, vs->ldn, vs->ldn, BN))) return rc;
-    const size_t smem = 1024 + TC_STAGES * (2 * TC_BM * TC_ROWB + 2 * (size_t)BN * TC_ROWB) + 64;
-    static size_t attr = 0;
-    if (attr < smem) {
-        cudaError_t e = cudaFuncSetAttribute(k_blend_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // pipeline depth: TC_STAGES with one CTA per SM, or 2 stages with narrow tiles so that three CTAs share an SM
+    int NS = TC_STAGES;
+    {
+        static int st_env = -1;                           // BODYFIT_BWD_STAGES=2|4: experiments
+        if (st_env < 0) { const char* e = getenv("BODYFIT_BWD_STAGES"); st_env = e ? atoi(e) : 0; }
+        if (st_env == 2 && BN <= 128) NS = 2;
+    }
+    const size_t smem = 1024 + NS * (2 * TC_BM * TC_ROWB + 2 * (size_t)BN * TC_ROWB) + 64;
+    static size_t attr[2] = {0, 0};
+    if (attr[NS == 2] < smem) {
+        cudaError_t e = NS == 2 ? cudaFuncSetAttribute(k_blend_bwd_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                : cudaFuncSetAttribute(k_blend_bwd_tc<TC_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { bf_set_error("cudaFuncSetAttribute(k_blend_bwd_tc): %s", cudaGetErrorString(e)); return BF_ECUDA; }
-        attr = smem;
+        attr[NS == 2] = smem;
     }
     const int num_k = vs->ldn / TC_BK;
     const size_t stride = (size_t)f->B * m->Kp;
@@ -538,7 +555,8 @@ static int bf_blend_backward_tc(const BfModel* m, const BfVSet* vs, const BfFram
         }
     }
     const dim3 grid(m->Kp / BN, (f->B + TC_BM - 1) / TC_BM, S);
-    k_blend_bwd_tc<<<grid, 192, smem, s>>>(a_hi, a_lo, b_hi, b_lo, BN, num_k, cps, m->Kp, S > 1 ? f->ws : f->dpf, stride, f->B);
+    if (NS == 2) k_blend_bwd_tc<2><<<grid, 192, smem, s>>>(a_hi, a_lo, b_hi, b_lo, BN, num_k, cps, m->Kp, S > 1 ? f->ws : f->dpf, stride, f->B);
+    else k_blend_bwd_tc<TC_STAGES><<<grid, 192, smem, s>>>(a_hi, a_lo, b_hi, b_lo, BN, num_k, cps, m->Kp, S > 1 ? f->ws : f->dpf, stride, f->B);
     BF_LAUNCH_CHECK();
     if (S > 1) {
         const size_t n = stride;

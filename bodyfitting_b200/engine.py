@@ -257,7 +257,7 @@ class FitSession(object):
         return out
 
 
-def staggered_ranges(B, n_parts, grain=128, min_part=2048, lead=0):
+def staggered_ranges(B, n_parts, grain=128, min_part=2048, lead=0, taper=0.5):
     """``lead`` > 0: a small first part of that many frames in front of the staggered ones -- its inputs are staged and
     uploaded quickly, so the GPU starts working while the host is still staging the large parts (end-to-end path only).
 
@@ -266,13 +266,13 @@ def staggered_ranges(B, n_parts, grain=128, min_part=2048, lead=0):
     parts travel to the host while the later parts are still being fitted and the last -- exposed -- copy is the smallest."""
     lead = (int(lead) // grain) * grain if min_part >= grain else int(lead)
     if lead > 0 and n_parts > 1 and B - lead >= 2 * min_part:
-        rest = staggered_ranges(B - lead, n_parts, grain=grain, min_part=min_part)
+        rest = staggered_ranges(B - lead, n_parts, grain=grain, min_part=min_part, taper=taper)
         return [(0, lead)] + [(lo + lead, hi + lead) for lo, hi in rest]
     n_parts = max(1, min(int(n_parts), B // max(1, int(min_part))))   # a part should still fill the GPU a few times over
     grain = grain if min_part >= grain else 1
     if n_parts == 1:
         return [(0, B)]
-    w = np.array([1.0 + 0.5 * k for k in range(n_parts)])[::-1]
+    w = np.array([1.0 + float(taper) * k for k in range(n_parts)])[::-1]     # sizes shrink linearly; the last part weighs 1
     edges = np.round(np.cumsum(w) / w.sum() * B / grain).astype(np.int64) * grain
     edges[-1] = B
     lo, out = 0, []
@@ -295,10 +295,10 @@ class ConcurrentFitSession(object):
     Same interface as FitSession (set_inputs / run / results)."""
 
     def __init__(self, model: PreparedModel, B, Nv, num_iters, imsize=512, return_vertices=True, dense_every_iter=False,
-                 n_parts=4, trace=True, min_part=2048, lead=0):
+                 n_parts=4, trace=True, min_part=2048, lead=0, taper=0.5):
         self.model, self.B, self.Nv, self.N = model, int(B), int(Nv), int(num_iters)
         dev = model.device
-        self.ranges = staggered_ranges(self.B, n_parts, min_part=min_part, lead=lead)
+        self.ranges = staggered_ranges(self.B, n_parts, min_part=min_part, lead=lead, taper=taper)
         self.theta = torch.zeros(B, model.NP, device=dev)
         self.verts = torch.empty(B, model.V, 3, device=dev) if return_vertices else None
         self.joints = torch.empty(B, model.K_full, 3, device=dev)

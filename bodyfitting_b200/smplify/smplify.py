@@ -64,6 +64,7 @@ class SMPLify(object):
         self.concurrent_parts = max(1, int(concurrent_parts))
         self.concurrent_min_part = int(os.environ.get('BODYFIT_MIN_PART', concurrent_min_part))
         self.concurrent_lead = int(os.environ.get('BODYFIT_LEAD', '0'))
+        self.concurrent_taper = float(os.environ.get('BODYFIT_TAPER', '0.5'))
         self._pinned = {}
         self.last_loss_terms = None
 
@@ -259,7 +260,8 @@ class SMPLify(object):
             if n_parts > 1 and len(staggered_ranges(B, n_parts, min_part=self.concurrent_min_part)) > 1:
                 self._sess = ConcurrentFitSession(self.model, B, Nv, self.num_iters, imsize=imsize, return_vertices=return_vertices,
                                                   dense_every_iter=self.dense_every_iter, n_parts=n_parts,
-                                                  min_part=self.concurrent_min_part, lead=self.concurrent_lead)
+                                                  min_part=self.concurrent_min_part, lead=self.concurrent_lead,
+                                                  taper=self.concurrent_taper)
             else:
                 self._sess = FitSession(self.model, B, Nv, self.num_iters, imsize=imsize,
                                         return_vertices=return_vertices, dense_every_iter=self.dense_every_iter,

@@ -27,9 +27,9 @@ for _ in range(3):
     t2 = time.perf_counter(); pin.copy_(src); t3 = time.perf_counter()
 print('pinned alloc %.1f ms; host->pinned staging of %.0f MB: %.1f ms (%.1f GB/s)' % (1e3 * (t1 - t0), src.numel() * 4 / 1e6, 1e3 * (t3 - t2), src.numel() * 4 / (t3 - t2) / 1e9))
 
-configs = [(4, 2048, 0), (4, 2048, 512), (4, 2048, 1024), (5, 1024, 0), (5, 1024, 512), (6, 1024, 512), (6, 1024, 1024), (8, 512, 512)]
-for parts, min_part, lead in configs:
-    fit.concurrent_parts, fit.concurrent_min_part, fit.concurrent_lead = parts, min_part, lead
+configs = [(4, 2048, 0, 0.5), (4, 2048, 0, 1.0), (4, 2048, 0, 1.5), (4, 2048, 0, 2.5), (3, 2048, 0, 1.0), (3, 2048, 0, 2.0), (5, 1024, 0, 1.5), (4, 2048, 0, 0.5)]
+for parts, min_part, lead, taper in configs:
+    fit.concurrent_parts, fit.concurrent_min_part, fit.concurrent_lead, fit.concurrent_taper = parts, min_part, lead, taper
     fit._sess_key = None
     for _ in range(2):
         fit(*args, imsize=512)
@@ -44,6 +44,6 @@ for parts, min_part, lead in configs:
     for _ in range(4):
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record(); sess.run(theta0); e.record(); torch.cuda.synchronize(); td.append(s.elapsed_time(e))
-    print('parts %d min_part %d lead %d -> ranges %s | e2e %.2f ms (%.1fk frames/s) | device %.2f ms'
-          % (parts, min_part, lead, [hi - lo for lo, hi in getattr(sess, 'ranges', [(0, F)])], 1e3 * float(np.median(ts)),
+    print('parts %d min_part %d lead %d taper %.1f -> ranges %s | e2e %.2f ms (%.1fk frames/s) | device %.2f ms'
+          % (parts, min_part, lead, taper, [hi - lo for lo, hi in getattr(sess, 'ranges', [(0, F)])], 1e3 * float(np.median(ts)),
              F / float(np.median(ts)) / 1e3, float(np.median(td[1:]))), flush=True)
