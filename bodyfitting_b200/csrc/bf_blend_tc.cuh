@@ -521,7 +521,7 @@ static int bf_blend_backward_tc(const BfModel* m, const BfVSet* vs, const BfFram
     {
         static int st_env = -1;                           // BODYFIT_BWD_STAGES=2|4: experiments
         if (st_env < 0) { const char* e = getenv("BODYFIT_BWD_STAGES"); st_env = e ? atoi(e) : 0; }
-        if (st_env == 2 && BN <= 128) NS = 2;
+        if (st_env == 2) NS = 2;                        // measured: slower in the full fit at either width
     }
     const size_t smem = 1024 + NS * (2 * TC_BM * TC_ROWB + 2 * (size_t)BN * TC_ROWB) + 64;
     static size_t attr[2] = {0, 0};

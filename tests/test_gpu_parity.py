@@ -6,6 +6,8 @@ Tolerances (BASELINE.json north_star): vertices / joints <= 1e-5 relative, per-i
 (Adam normalises gradients, so fp32 rounding differences are amplified along the trajectory;
 the fp64 oracle is used to show the CUDA path is as close to fp64 as the fp32 oracle is).
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -348,3 +350,25 @@ def test_full_size_batch_properties(assets):
     ref = small((betas[pick], pose[pick]), *args, kp[pick], None, imsize=512)
     for k in ('pose', 'betas', 'global_orient', 'global_transl', 'scale', 'vertices', 'joints', 'full_pose'):
         assert np.array_equal(np.asarray(out[k])[pick], np.asarray(ref[k])), k
+
+
+@pytest.mark.gpu
+def test_cta_pair_blend_gemm_matches_fp64_and_single_cta():
+    """The cta_group::2 forward blend GEMM (BODYFIT_TC2=1, read once per process -> run in a child process): same maximum
+    error vs an fp64 contraction as the single-CTA kernel on the same inputs, no unwritten outputs, four batch shapes
+    (incl. one below the 256-frame pair tile, which must fall back to the single-CTA kernel)."""
+    import re, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    errs = {}
+    for flag in ('0', '1'):
+        env = dict(os.environ, BODYFIT_TC2=flag)
+        out = subprocess.run([sys.executable, os.path.join(root, 'tools', 'check_tc2.py')], env=env, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        rows = re.findall(r'B=(\d+) full=(\d)  max \|err\| ([0-9.e+-]+) .*nan (\d+)', out.stdout)
+        assert len(rows) == 4, out.stdout
+        for B, full, err, nan in rows:
+            assert int(nan) == 0 and float(err) < 1e-6, (flag, B, full, err, nan)
+            errs[(flag, B, full)] = float(err)
+    for (flag, B, full), e in errs.items():
+        if flag == '1':
+            assert e == errs[('0', B, full)], 'pair kernel differs from the single-CTA kernel'

@@ -362,3 +362,23 @@ def test_rotation_matrix_to_axis_angle():
     assert np.abs(out - ref).max() < 1e-8 and (out[0] == 0).all()
     pose = convert_hom_to_angle(R[:48].reshape(2, 24, 3, 3).float(), 2)
     assert pose.shape == (2, 72) and np.abs(pose.numpy().reshape(-1, 3) - ref[:48]).max() < 1e-5
+
+
+def test_staggered_ranges_partition_properties():
+    """Part layout of large batches (engine.staggered_ranges): a partition of [0, B) into consecutive ranges of
+    non-increasing size, GEMM-tile aligned, for every taper / lead setting."""
+    from bodyfitting_b200.engine import staggered_ranges
+    for B in (1, 100, 2047, 4096, 10000, 16384, 100001):
+        for n_parts in (1, 2, 4, 6):
+            for taper in (0.0, 0.5, 1.5):
+                for lead in (0, 512):
+                    rs = staggered_ranges(B, n_parts, taper=taper, lead=lead)
+                    assert rs[0][0] == 0 and rs[-1][1] == B
+                    assert all(rs[i][1] == rs[i + 1][0] for i in range(len(rs) - 1))
+                    assert all(hi > lo for lo, hi in rs)
+                    body = rs[1:] if (lead and len(rs) > 1 and rs[0][1] == lead) else rs
+                    sizes = [hi - lo for lo, hi in body]
+                    assert all(sizes[i] >= sizes[i + 1] - 128 for i in range(len(sizes) - 1))
+                    assert all(lo % 128 == 0 for lo, _ in rs)
+                    assert len(rs) <= n_parts + (1 if lead else 0)
+    assert staggered_ranges(10000, 4) == [(0, 3584), (3584, 6400), (6400, 8576), (8576, 10000)]
