@@ -292,8 +292,10 @@ __global__ void __launch_bounds__(FR_THREADS, 5) k_frame_loss_bwd(BfModel m, BfV
     }
     // skinning backward, joint side: dA[j] = sum_{live v} w_vj dverts_v (x) [vposed_v; 1]
     float* dAb = f.dA + (size_t)b * J * 12;
-    if (vs.n_nz < J)
-        for (int i = t; i < J * 12; i += FR_THREADS) dAb[i] = 0.f;
+    if (vs.n_nz < J) {                                 // joints without live vertices keep zero rows (16-byte stores)
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = t; i < J * 3; i += FR_THREADS) reinterpret_cast<float4*>(dAb)[i] = z;
+    }
     __syncthreads();
     // 4 lanes per joint (the live skinning lists are short), 8 joints per warp at a time; the 12 (padded 16) partial sums
     // are reduced over the 4 lanes with a multi-value butterfly (8 + 4 shuffles), after which lane l of the group holds

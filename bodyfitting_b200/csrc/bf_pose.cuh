@@ -399,7 +399,7 @@ __global__ void __launch_bounds__(128) k_pose_bwd(BfModel m, BfFrames f, int fla
         float acc = 0.f;
         if (part < 3) {
             const int q1 = min(nq, (part + 1) * per);
-#pragma unroll 5
+#pragma unroll 11
             for (int q = part * per; q < q1; ++q) acc += __ldg(m.Jd + q * m.NS + l) * dJr_s[q];
         }
         const float a1 = __shfl_sync(0xffffffffu, acc, (lane + m.NB) & 31);
@@ -414,7 +414,7 @@ __global__ void __launch_bounds__(128) k_pose_bwd(BfModel m, BfFrames f, int fla
             const float* comp = (lane < 6 ? m.hand_l : m.hand_r) + c * 45;
             const float* d = dfp + (lane < 6 ? 75 : 120);
             float acc = 0.f;
-#pragma unroll 9
+#pragma unroll 15
             for (int i = 0; i < 45; ++i) acc += __ldg(comp + i) * d[i];
             g[(lane < 6 ? L.off_lh : L.off_rh) + c] = acc;
         }
