@@ -42,3 +42,19 @@ for name, p in (('initial poses', init), ('ground-truth poses', gt)):
         nvert = np.mean([len(set().union(*[live[a] for a in r])) for r in rows])
         print('%-19s %-14s: %.1f rows and %.0f of %d active vertices per 128-frame tile (%.0f %% of the GEMM columns)'
               % (name, order, nrows, nvert, pm.n_act, 100.0 * nvert / pm.n_act))
+
+# structure of the contour candidates: how well a row's vertices cluster when the contour vertices are ordered by the first row
+# that uses them (the column order a per-tile block list would want)
+static = set.intersection(*live)
+contour = [l - static for l in live]
+allc = set().union(*contour)
+first = {}
+for a, c in enumerate(contour):
+    for v in c:
+        first.setdefault(v, a)
+pos = {v: i for i, v in enumerate(sorted(allc, key=lambda v: (first[v], v)))}
+blocks = [len({pos[v] // 16 for v in c}) for c in contour]
+overlap = [len(contour[a] & contour[a + 1]) for a in range(len(contour) - 1)]
+print('%d static + %d contour vertices; adjacent rows share %.1f of %.1f contour vertices; in first-use order a row touches '
+      '%.1f (max %d) of %d 16-vertex blocks' % (len(static), len(allc), np.mean(overlap), np.mean([len(c) for c in contour]),
+                                                 np.mean(blocks), max(blocks), (len(allc) + 15) // 16))
