@@ -4,23 +4,31 @@
   python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun, one rank per GPU)
   python bench.py --impl reference --steps K --warmup W    (CPU port of the reference path, rank 0 only)
 
-One *step* = one complete 100-iteration multi-view SMPLify fit of a batch of synthetic frames
-(``--frames`` per GPU, default 10,000 = BASELINE config 3; frames are independent, so ranks get
-disjoint frame ranges and no collective runs during the fit: weak scaling).
+One *step* = one complete 100-iteration multi-view SMPLify fit of ONE synthetic sequence of ``--frames`` frames
+(default 10,000 = BASELINE config 3).  STRONG scaling: the sequence is cut into contiguous frame ranges, one per rank
+(``sharding.frame_range``); frames are independent fits, so no collective runs during the fit and one all_gather of the
+fitted parameters ends the step.  ``--scaling weak`` gives every rank its own ``--frames`` frames instead (reported as the
+extra key ``weak`` at N>1 in the default run).
 
-  value : frames/s with inputs (keypoints, cameras, initial parameters) resident in HBM;
-          timed with CUDA events on the launching stream, max over ranks.
-  e2e   : the same through the reference-facing API ``SMPLify.__call__`` with HOST numpy
-          inputs and HOST numpy outputs (vertices included) -- pinned H2D/D2H inside the
-          timed region.
-  roofline / kernels : per-kernel CUDA-event durations of one iteration and the algorithmic
-          bytes of each kernel (DESIGN.md "Kernels"), for the dominant kernel of the step.
+  value : frames/s with inputs (keypoints, cameras, initial parameters) resident in HBM; every step is timed with its
+          own CUDA-event pair on the launching stream, L2 flushed (a 256 MB fill) between steps, summed over the K steps
+          after a barrier, max over ranks.
+  e2e   : the same through the reference-facing API ``SMPLify.__call__`` with HOST (page-locked numpy) inputs and HOST
+          numpy outputs (vertices included) -- H2D / D2H inside the timed region.
+  roofline / kernels : per-kernel CUDA-event durations of one iteration and the algorithmic bytes of each kernel
+          (DESIGN.md "Kernels"), for the dominant kernel of the step.
   lbs_dense : all-vertex LBS operator forward / backward (BASELINE config 2) against the HBM roofline.
-  cpu_baseline : the oracle's single-frame restatement of the reference loop (oracle/fit_port.py,
-          validated bit-for-bit against the verbatim reference in the authoring container) on the
-          box's host cores, 8 frames (about 10 s).
+  config4 : the same sequence with the temporal smoothness term; boundary rows cross GPUs by in-kernel NVLink stores
+          (sharding.HaloLink) -- frames/s, halo cost per iteration, host-driven NCCL fallback beside it.
+  config5 : SMPL+D scan path: uniform-grid build + closest-point search on 100k-vertex scans, subjects round-robin over
+          the ranks; the reference's own mesh_grid kernel (oracle/_ref, compiled for sm_100a) timed on the same GPU.
+  cpu_baseline : the oracle's single-frame restatement of the reference loop (oracle/fit_port.py, validated bit-for-bit
+          against the verbatim reference in the authoring container) on the box's host cores; gpu_eager_baseline: the same
+          eager op sequence on the B200 (the reference's default device) -- both reported, neither is the target.
 """
 import argparse
+import glob
+import importlib.util
 import json
 import os
 import subprocess
@@ -36,6 +44,7 @@ sys.path.insert(0, os.path.join(ROOT, 'tests'))
 
 METRIC = 'fitted frames/s (SMPL-X, 8 views, 100 iters)'
 MT, NV, ITERS = 'smplx', 8, 100
+TEMPORAL_W = 300.0
 
 
 def parse():
@@ -44,10 +53,12 @@ def parse():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--frames', type=int, default=10000, help='frames per GPU')
+    ap.add_argument('--frames', type=int, default=10000, help='frames of the sequence (strong) / per GPU (weak)')
+    ap.add_argument('--scaling', default='strong', choices=['strong', 'weak'])
     ap.add_argument('--iters', type=int, default=ITERS)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-dense', action='store_true')
+    ap.add_argument('--no-extras', action='store_true', help='skip config4 / config5 / weak / GPU-eager legs')
     ap.add_argument('--cpu-frames', type=int, default=8)
     return ap.parse_args()
 
@@ -63,15 +74,16 @@ def peaks():
 
 def measured_traffic(kernel, frames):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed `ncu --set full` capture
-    (profiles/r1_traffic.json, taken at 10,000 frames); None if this kernel / size was not captured."""
-    fn = os.path.join(ROOT, 'profiles', 'r1_traffic.json')
-    if not os.path.exists(fn):
-        return None
-    with open(fn) as f:
-        d = json.load(f).get(kernel)
-    if not d or d.get('frames') != frames:
-        return None
-    return d['dram_bytes_read'] + d['dram_bytes_write']
+    (profiles/r2_traffic.json, else r1_traffic.json; taken at 10,000 frames); None if this kernel / size was not captured."""
+    for name in ('r2_traffic.json', 'r1_traffic.json'):
+        fn = os.path.join(ROOT, 'profiles', name)
+        if not os.path.exists(fn):
+            continue
+        with open(fn) as f:
+            d = json.load(f).get(kernel)
+        if d and d.get('frames') == frames:
+            return d['dram_bytes_read'] + d['dram_bytes_write']
+    return None
 
 
 class ClockSampler(object):
@@ -120,24 +132,43 @@ class ClockSampler(object):
 
 
 # ---------------------------------------------------------------------------------------------
-def cpu_reference_fit(n_frames, iters, warm=1):
-    """Reference-style single-frame fits on the host cores (oracle port). Returns s/frame list."""
+def host_threads(share=1):
+    """torchrun exports OMP_NUM_THREADS=1; the CPU legs use every core this process may run on (1/share of them when
+    ``share`` ranks work side by side)."""
+    import torch
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    torch.set_num_threads(max(1, n // max(1, share)))
+    return torch.get_num_threads()
+
+
+def cpu_reference_fit(n_frames, iters, warm=1, device='cpu'):
+    """Reference-style single-frame fits (oracle port): on the host cores, or eagerly on the GPU. Returns s/frame list."""
     import torch
     from bodyfitting_b200 import synthetic as syn
     from oracle import fit_port as fp
     from util import make_scene
+    cores = host_threads()
     model, gmm = syn.make_model(MT, 0), syn.make_gmm(0)
     port = fp.FitPort(MT, model, gmm)
     sc = make_scene(port, MT, n_frames + warm, NV, seed=11)
+    if device != 'cpu':
+        port = fp.FitPort(MT, model, gmm, device=device)
     times = []
     for f in range(n_frames + warm):
         views = syn.keypoints_to_openpose(sc['kp'][f], MT)
+        if device != 'cpu':
+            torch.cuda.synchronize()
         t0 = time.perf_counter()
         port.fit_frame(sc['init_betas'][f], sc['init_pose'][f], sc['c2ws'], sc['Ks'], views, num_iters=iters)
+        if device != 'cpu':
+            torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         if f >= warm:
             times.append(dt)
-    return times, torch.get_num_threads()
+    return times, cores
 
 
 def run_reference(args):
@@ -148,7 +179,7 @@ def run_reference(args):
     fps = len(times) / sum(times)
     line = {'impl': 'reference', 'metric': METRIC, 'value': fps, 'unit': 'frames/s', 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * sum(times) / len(times),
-            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'fp32', 'data': 'synthetic',
+            'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'fp32', 'data': 'synthetic',
             'config': {'workload': 'SMPL-X (10475 verts, 55 joints) 8-view 135-keypoint fit, %d Adam iterations, '
                                    '1 frame per step (the reference fits one frame per call)' % args.iters},
             'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
@@ -160,29 +191,37 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------
-def build_workload(pm, F, seed):
-    """Synthetic scene for F frames: GT joints from the CUDA forward, 2-D detections on the host."""
+def build_workload(pm, F, seed, lo=0, hi=None):
+    """Frames [lo, hi) of the synthetic F-frame scene ``seed``: GT joints from the CUDA forward, 2-D detections on the
+    host.  Every rank draws the whole sequence's parameters (cheap) and keeps its own range, so the sequence does not
+    depend on how it is sharded."""
     import torch
     from bodyfitting_b200 import synthetic as syn, _lib
     from bodyfitting_b200.engine import FrameBuffers
+    hi = F if hi is None else hi
     c2ws, Ks = syn.make_cameras(NV, seed=0)
     gt, init = syn.make_params(MT, F, seed=seed)
-    T = lambda a: torch.from_numpy(a)
+    gt = {k: v[lo:hi] for k, v in gt.items()}
+    init = {k: v[lo:hi] for k, v in init.items()}
+    n = hi - lo
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a))
     theta_gt = pm.pack_theta(T(gt['global_orient']), T(gt['body_pose']), T(gt['betas']), transl=T(gt['transl']),
                              scale=T(gt['scale']), leye=T(gt['leye_pose']), reye=T(gt['reye_pose']),
                              lhand=T(gt['left_hand_pose']), rhand=T(gt['right_hand_pose']))
-    joints = torch.empty(F, pm.K_full, 3, device='cuda')
+    joints = torch.empty(n, pm.K_full, 3, device='cuda')
     chunk = 2048
-    for lo in range(0, F, chunk):
-        hi = min(F, lo + chunk)
-        fb = FrameBuffers(pm, hi - lo, full=True, need_backward=False,
-                          ext=dict(theta=theta_gt[lo:hi].contiguous(), joints=joints[lo:hi]))
+    for a in range(0, n, chunk):
+        b = min(n, a + chunk)
+        fb = FrameBuffers(pm, b - a, full=True, need_backward=False,
+                          ext=dict(theta=theta_gt[a:b].contiguous(), joints=joints[a:b]))
         fb.struct.flags |= _lib.F_WORLD
         fb.call('bf_lbs_forward')
     torch.cuda.synchronize()
-    kp = syn.make_keypoints(joints[:, :pm.K_used].cpu().numpy(), c2ws, Ks, seed=seed)
-    init_pose = np.concatenate([init['global_orient'], init['body_pose'], np.zeros((F, 6), np.float32)], 1)
-    return dict(c2ws=c2ws, Ks=Ks, kp=kp, init_pose=init_pose.astype(np.float32), init_betas=init['betas'])
+    # detections: the noise stream is drawn per frame index so that a shard sees the frames of the whole sequence
+    kp = syn.make_keypoints(joints[:, :pm.K_used].cpu().numpy(), c2ws, Ks, seed=seed + 7919 * lo)
+    init_pose = np.concatenate([init['global_orient'], init['body_pose'], np.zeros((n, 6), np.float32)], 1)
+    return dict(c2ws=c2ws, Ks=Ks, kp=kp, init_pose=np.ascontiguousarray(init_pose.astype(np.float32)),
+                init_betas=np.ascontiguousarray(init['betas']))
 
 
 def time_events(fn, reps):
@@ -296,16 +335,87 @@ def config2_fit_bench():
     for _ in range(3):
         sess.run(theta0)
     ms = float(np.median(time_events(lambda: sess.run(theta0), 5)))
-    return {'config': 'SMPL 6890 verts, 1024 frames, 4 views x 25 keypoints, 100 iterations (BASELINE config 2), one batch, one stream',
+    return {'config': 'SMPL 6890 verts, 1024 frames, 4 views x 25 keypoints, 100 iterations (BASELINE config 2), one batch, '
+                      'one CUDA graph' if sess.use_graph else 'one stream',
             'ms_per_fit': ms, 'frames_per_s': B / ms * 1e3, 'active_vertices': int(pm.n_act)}
+
+
+def config5_bench(rank, world, n_subjects=8, searches=100):
+    """BASELINE config 5 (SMPL+D scan path): per subject a 100k-vertex / 200k-face scan -> uniform-grid build, then
+    ``searches`` closest-point searches of the 10,475 SMPL-X vertices (what the displacement loop does once per
+    iteration).  Subjects round-robin over the ranks, no collective.  Rank 0 also times the reference's own mesh_grid
+    kernel (oracle/_ref, compiled for sm_100a) on the first subject."""
+    import torch
+    from bodyfitting_b200 import synthetic as syn
+    from bodyfitting_b200.utils.mesh_grid_searcher import MeshGridSearcher
+    mine = list(range(rank, n_subjects, world))
+    body, _ = syn.make_template(10475, 0)
+    scans = {}
+    for s in mine:
+        v, f = syn.make_template(100000, 9 + s)
+        scans[s] = ((v * 0.6).astype(np.float32), f.astype(np.int32))
+    rng = np.random.RandomState(0)
+    q = torch.from_numpy((body * 0.6 * 1.02 + rng.randn(*body.shape) * 0.004).astype(np.float32)).cuda()
+    MeshGridSearcher(scans[mine[0]][0][:3000], scans[mine[0]][1][:10]) if mine else None      # warm-up
+    torch.cuda.synchronize()
+    build_ms, search_ms = [], []
+    t_all = time.perf_counter()
+    for s in mine:
+        v, f = scans[s]
+        vd, fd = torch.from_numpy(v).cuda(), torch.from_numpy(f).cuda()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        g = MeshGridSearcher(vd, fd)
+        torch.cuda.synchronize()
+        build_ms.append(1e3 * (time.perf_counter() - t0))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(searches):
+            g.nearest_points(q)
+        e1.record()
+        torch.cuda.synchronize()
+        search_ms.append(e0.elapsed_time(e1) / searches)
+    wall = time.perf_counter() - t_all
+    out = {'subjects': n_subjects, 'subjects_this_rank': len(mine), 'scan_verts': 100000, 'scan_faces': 200000, 'queries': 10475,
+           'searches_per_subject': searches, 'grid_build_ms': float(np.mean(build_ms)) if build_ms else None,
+           'nearest_ms': float(np.mean(search_ms)) if search_ms else None, 'rank_wall_s': wall}
+    so = glob.glob(os.path.join(ROOT, 'oracle', '_ref', 'mesh_grid*.so'))
+    if rank == 0 and so and mine:
+        try:
+            spec = importlib.util.spec_from_file_location('mesh_grid', so[0])
+            mg = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mg)
+            v, f = scans[mine[0]]
+            g = MeshGridSearcher(v, f)
+            verts, fa = torch.from_numpy(v).cuda(), torch.from_numpy(f).cuda()
+            num = torch.tensor(g.num, dtype=torch.int32).cuda()
+            minmax = torch.from_numpy(np.asarray(g.minmax, np.float32)).cuda()
+            tri_num = torch.zeros(g.num[3], dtype=torch.int32).cuda()
+            tri_idx = torch.zeros(1, dtype=torch.int32).cuda()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            mg.insert_grid_surface(verts, fa, minmax, num, g.step, tri_num, tri_idx)
+            torch.cuda.synchronize()
+            out['reference_kernel_grid_build_ms'] = 1e3 * (time.perf_counter() - t0)
+            nf = torch.zeros(len(q), dtype=torch.int32).cuda()
+            co, npts = torch.zeros(len(q), 3).cuda(), torch.zeros(len(q), 3).cuda()
+            fn = lambda: mg.search_nearest_point(q, verts, fa, tri_num, tri_idx, num, minmax, g.step, nf, npts, co)
+            fn()
+            out['reference_kernel_nearest_ms'] = float(np.median(time_events(fn, 5)))
+            out['nearest_speedup_vs_reference_kernel'] = out['reference_kernel_nearest_ms'] / out['nearest_ms']
+        except Exception as ex:
+            out['reference_kernel'] = 'failed: %r' % (ex,)
+    elif rank == 0:
+        out['reference_kernel'] = 'oracle/_ref not built'
+    return out
 
 
 def run_ours(args):
     import torch
     import torch.distributed as dist
     from bodyfitting_b200 import synthetic as syn
-    from bodyfitting_b200.engine import pack_cameras, pack_keypoints
-    from bodyfitting_b200.model import PreparedModel
+    from bodyfitting_b200.engine import FitSession
+    from bodyfitting_b200.sharding import HaloLink, exchange_halo, frame_range
     from bodyfitting_b200.smplify.smplify import SMPLify
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -326,32 +436,10 @@ def run_ours(args):
             sys.stdout.flush()
             os.dup2(saved_fd, 1)
             os.close(saved_fd)
-    F, N = args.frames, args.iters
+    host_threads(world)                                     # pinned staging / numpy of this rank may use its share of the cores
+    N = args.iters
     hbm_peak, peak_src = peaks()
-
-    fit = SMPLify(smpl_type=MT, num_iters=N, gender='neutral', model_data=syn.make_model(MT, 0), gmm=syn.make_gmm(0))
-    pm = fit.model
-    wl = build_workload(pm, F, seed=100 + rank)            # rank r owns frames [r*F, (r+1)*F)
-    sess = fit.session(F, NV, 512, True)
-    kp_dev = pack_keypoints(torch.from_numpy(wl['kp']).cuda(), True)
-    cams = torch.from_numpy(pack_cameras(wl['c2ws'], wl['Ks'])).cuda()
-    sess.set_inputs(kp_dev, cams)
-    poses = torch.from_numpy(wl['init_pose']).cuda()
-    theta0 = pm.pack_theta(poses[:, :3], poses[:, 3:3 + pm.nbody], torch.from_numpy(wl['init_betas']).cuda())
-    gathered = torch.empty(world * F, pm.NP, device='cuda') if world > 1 else None
-
-    def step_device():
-        theta = sess.run(theta0)
-        if world > 1:                                       # final gather of the fitted parameters
-            dist.all_gather_into_tensor(gathered, theta)
-
-    host_args = ((wl['init_betas'], wl['init_pose']), list(wl['c2ws']), list(wl['Ks']), wl['kp'], None)
-
-    def step_e2e():
-        out = fit(*host_args, use_frames=list(range(NV)), imsize=512)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, sess.theta)
-        return out
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
 
     def barrier():
         if world > 1:
@@ -359,23 +447,69 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def timed_region(fn, K, W):
+        """W untimed steps, barrier, K steps each bracketed by its own event pair with an L2 flush in front (not timed),
+        barrier; the step times are summed per rank and the MAX over ranks is returned (plus the wall-clock maximum)."""
         for _ in range(W):
             fn()
         barrier()
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0 = time.perf_counter()
-        s.record()
-        for _ in range(K):
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        wall = 0.0
+        for s, e in ev:
+            flush.zero_()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            s.record()
             fn()
-        e.record()
+            e.record()
+            torch.cuda.synchronize()
+            wall += time.perf_counter() - t0
         barrier()
-        wall = time.perf_counter() - t0
-        ms = s.elapsed_time(e)
+        ms = sum(s.elapsed_time(e) for s, e in ev)
         if world > 1:
             t = torch.tensor([ms, wall * 1e3], device='cuda', dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms, wall = float(t[0]), float(t[1]) / 1e3
         return ms, wall
+
+    def make_leg(F_total, lo, hi, temporal=0.0, halo=None, halo_exchange=None):
+        """A fitter + device-resident session + pinned host inputs for frames [lo, hi) of the F_total-frame sequence."""
+        fit = SMPLify(smpl_type=MT, num_iters=N, gender='neutral', model_data=model_data, gmm=gmm, temporal_weight=temporal,
+                      halo=halo, halo_exchange=halo_exchange)
+        wl = build_workload(fit.model, F_total, 100, lo, hi)
+        pin = {k: torch.from_numpy(wl[k]).pin_memory() for k in ('kp', 'init_pose', 'init_betas')}
+        from bodyfitting_b200.engine import pack_cameras
+        sess = fit.session(hi - lo, NV, 512, True)
+        cams = torch.from_numpy(pack_cameras(wl['c2ws'], wl['Ks'])).cuda()
+        sess.load_inputs(pin['kp'].cuda(), cams, pin['init_pose'].cuda(), pin['init_betas'].cuda())
+        torch.cuda.synchronize()
+        host_args = ((pin['init_betas'].numpy(), pin['init_pose'].numpy()), list(wl['c2ws']), list(wl['Ks']), pin['kp'].numpy(), None)
+        return fit, sess, host_args, pin
+
+    model_data, gmm = syn.make_model(MT, 0), syn.make_gmm(0)
+    if args.scaling == 'strong':
+        F_total = args.frames
+        lo, hi = frame_range(F_total, rank, world)
+    else:
+        F_total = args.frames * world
+        lo, hi = rank * args.frames, (rank + 1) * args.frames
+    F = hi - lo
+    fit, sess, host_args, pin = make_leg(F_total, lo, hi)
+    pm = fit.model
+    from bodyfitting_b200.sharding import gather_frames
+
+    def run_sess(s):
+        return s.run()
+
+    def step_device():
+        theta = run_sess(sess)
+        if world > 1:                                       # final gather of the fitted parameters
+            gather_frames(theta, F_total)
+
+    def step_e2e():
+        out = fit(*host_args, use_frames=list(range(NV)), imsize=512)
+        if world > 1:
+            gather_frames(sess.theta, F_total)
+        return out
 
     sampler = ClockSampler(local)
     sampler.start()
@@ -384,47 +518,104 @@ def run_ours(args):
     launches = sess.kernel_launches * args.steps
     ms_e2e, wall_e2e = timed_region(step_e2e, args.steps, max(1, min(args.warmup, 3)))
     h2d, d2h = fit.h2d_bytes, fit.d2h_bytes
+    if world > 1:
+        t = torch.tensor([h2d, d2h, launches], device='cuda', dtype=torch.float64)
+        dist.all_reduce(t)
+        h2d, d2h, launches = (int(x) for x in t.tolist())
 
-    total_frames = world * F * args.steps
-    value = total_frames / (ms_dev / 1e3)
-    e2e = total_frames / (max(ms_e2e / 1e3, wall_e2e))
+    frames_done = F_total * args.steps
+    value = frames_done / (ms_dev / 1e3)
+    e2e = frames_done / (max(ms_e2e / 1e3, wall_e2e))
+    extras = {}
+
+    # ---- config 4: temporal term, boundary rows by in-kernel NVLink stores -------------------------------------------
+    if not args.no_extras:
+        try:
+            link = HaloLink()
+            fit_t, sess_t, _, _ = make_leg(F_total, lo, hi, temporal=TEMPORAL_W, halo=link)
+            k4 = max(2, min(args.steps, 5))
+            ms_t, _ = timed_region(lambda: run_sess(sess_t), k4, 2)
+            c4 = {'workload': 'config 3 + temporal smoothness term (weight %.0f) coupling consecutive frames; %d-frame sequence over '
+                              '%d rank(s)' % (TEMPORAL_W, F_total, world), 'halo': 'in-kernel NVLink peer stores + flag (HaloLink)' if world > 1 else 'none (one rank)',
+                  'frames_per_s': F_total * k4 / (ms_t / 1e3), 'ms_per_fit': ms_t / k4, 'graph': bool(sess_t.use_graph)}
+            if world > 1:
+                # the same shards without the link (every shard its own sequence): the difference is what the halo costs
+                fit_u, sess_u, _, _ = make_leg(F_total, lo, hi, temporal=TEMPORAL_W)
+                ms_u, _ = timed_region(lambda: run_sess(sess_u), k4, 2)
+                c4['ms_per_fit_without_halo'] = ms_u / k4
+                c4['halo_us_per_iteration'] = 1e3 * (ms_t - ms_u) / k4 / N
+                fit_h, sess_h, _, _ = make_leg(F_total, lo, hi, temporal=TEMPORAL_W, halo_exchange=exchange_halo)
+                ms_h, _ = timed_region(lambda: run_sess(sess_h), 2, 1)
+                c4['host_nccl_fallback_ms_per_fit'] = ms_h / 2
+                c4['host_nccl_fallback_halo_us_per_iteration'] = 1e3 * (ms_h / 2 - ms_u / k4) / N
+                del fit_u, sess_u, fit_h, sess_h
+            extras['config4'] = c4
+            del fit_t, sess_t
+        except Exception as ex:                              # report, never hide
+            extras['config4'] = {'error': repr(ex)}
+        try:
+            c5 = config5_bench(rank, world)
+            if world > 1:
+                t = torch.tensor([c5['rank_wall_s']], device='cuda', dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                c5['wall_s_max_over_ranks'] = float(t[0])
+            else:
+                c5['wall_s_max_over_ranks'] = c5['rank_wall_s']
+            c5['subjects_per_s'] = c5['subjects'] / c5['wall_s_max_over_ranks']
+            extras['config5'] = c5
+        except Exception as ex:
+            extras['config5'] = {'error': repr(ex)}
+        if world > 1 and args.scaling == 'strong':
+            try:                                             # weak scaling beside it: --frames frames on EVERY rank
+                fit_w, sess_w, _, _ = make_leg(args.frames * world, rank * args.frames, (rank + 1) * args.frames)
+                ms_w, _ = timed_region(lambda: run_sess(sess_w), 3, 2)
+                extras['weak'] = {'frames_per_gpu': args.frames, 'value': args.frames * world * 3 / (ms_w / 1e3), 'unit': 'frames/s',
+                                  'ms_per_step': ms_w / 3}
+                del fit_w, sess_w
+            except Exception as ex:
+                extras['weak'] = {'error': repr(ex)}
+
     if rank != 0:
         if world > 1:
+            dist.barrier()
             dist.destroy_process_group()
         return
-    from bodyfitting_b200.engine import FitSession
-    plain = FitSession(pm, F, NV, N)                        # one batch on one stream: per-kernel times of one iteration
-    plain.set_inputs(kp_dev, cams)
-    plain.run(theta0)
+    plain = FitSession(pm, F, NV, N, graph=False)           # one batch on one stream: per-kernel times of one iteration
+    plain.load_inputs(pin['kp'].cuda(), torch.zeros(NV, 12, device='cuda'), pin['init_pose'].cuda(), pin['init_betas'].cuda())
+    plain.cams.copy_(sess.parts[0].cams if hasattr(sess, 'parts') else sess.cams)
+    plain.run()
     kern = kernel_breakdown(pm, plain, F, hbm_peak)
-    dom = max(kern, key=lambda k: k['ms'])
     iter_ms = sum(k['ms'] * k['launches_per_iteration'] for k in kern)
     dom = max(kern, key=lambda k: k['ms'] * k['launches_per_iteration'])
+    kp_mb = F * pm.K_used * NV * 12 / 1e6
+    state_mb = F * (2 * pm.Kp + 4 * pm.ld_act + 24 * pm.J + 4 * pm.NP) * 4 / 1e6
     line = {
         'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
-        'warmup': max(args.warmup, 3), 'ms_per_step': ms_dev / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'warmup': max(args.warmup, 3), 'ms_per_step': ms_dev / args.steps, 'higher_is_better': True, 'scaling': args.scaling,
         'vs_baseline': None, 'dtype': 'fp32', 'data': 'synthetic',
-        'config': {'workload': 'SMPL-X (10475 verts, 55 joints, random-init tensors) 8-view fit of %d frames per GPU, '
-                               '135 OpenPose-layout keypoints per view, %d Adam iterations (BASELINE config 3)' % (F, N),
-                   'frames_per_gpu': F, 'views': NV, 'iters': N, 'active_vertices': int(pm.n_act),
+        'config': {'workload': 'SMPL-X (10475 verts, 55 joints, random-init tensors) 8-view fit of ONE %d-frame sequence, '
+                               '135 OpenPose-layout keypoints per view, %d Adam iterations (BASELINE config 3), frame-sharded over '
+                               '%d GPU(s)' % (F_total, N, world),
+                   'frames_total': F_total, 'frames_per_gpu': F, 'views': NV, 'iters': N, 'active_vertices': int(pm.n_act),
                    'design': 'fit loop runs blend+skinning on the %d vertices the keypoint loss can touch (exact: all other '
                              'vertex gradients are zero); all 10475 vertices are produced once for the returned mesh' % pm.n_act,
-                   'l2': 'inputs larger than L2: %.0f MB of keypoints + %.0f MB of per-frame state per step, no flush'
-                         % (kp_dev.numel() * 4 / 1e6, F * (2 * pm.Kp + 4 * pm.ld_act + 24 * pm.J + 4 * pm.NP) * 4 / 1e6),
+                   'l2': 'L2 flushed (256 MB fill) before every timed step; per step %.0f MB of keypoints + %.0f MB of '
+                         'per-frame state per rank' % (kp_mb, state_mb),
                    'parallelism': 'frames sharded, %d rank(s), no collective during the fit; final all_gather of parameters' % world,
-                   'streams': 'per GPU the batch runs as %s staggered parts on their own CUDA streams (bit-identical results); '
-                              'kernels[] / roofline are timed on one 10,000-frame batch on one stream'
+                   'streams': 'per GPU the shard runs as %d part(s), each ONE CUDA graph (N iterations + all-vertex forward) on '
+                              'its own stream (bit-identical results); kernels[] / roofline are timed on one batch on one stream'
                               % (len(getattr(sess, 'ranges', [0])))},
         'clocks': clocks,
         'e2e': {'value': e2e, 'unit': 'frames/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
                 'ms_per_step': 1e3 * max(ms_e2e / 1e3, wall_e2e) / args.steps,
-                'api': 'bodyfitting_b200.smplify.smplify.SMPLify.__call__ (numpy in, numpy out incl. vertices)'},
+                'api': 'bodyfitting_b200.smplify.smplify.SMPLify.__call__ (page-locked numpy in, numpy out incl. vertices)'},
         'gpu_launches': int(launches),
         'roofline': {'bound': 'hbm', 'kernel': dom['kernel'], 'achieved': dom['gbs'], 'peak': hbm_peak, 'unit': 'GB/s',
                      'frac': dom['frac_hbm'], 'traffic': measured_traffic(dom['kernel'], F), 'peak_source': peak_src,
                      'share_of_iteration': dom['ms'] / iter_ms},
         'kernels': kern, 'iter_ms_sum_of_kernels': iter_ms,
     }
+    line.update(extras)
     if not args.no_dense:
         try:
             line['lbs_dense'] = dense_lbs_bench(0, hbm_peak)
@@ -435,8 +626,17 @@ def run_ours(args):
         except Exception as ex:
             line['config2_fit'] = {'error': repr(ex)}
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
-    if not args.no_cpu_baseline:
+    if world == 1 and not args.no_extras:
+        try:
+            times, _ = cpu_reference_fit(2, N, warm=1, device='cuda')
+            line['gpu_eager_baseline'] = {'value': len(times) / sum(times), 'unit': 'frames/s', 'kind': 'port on device=cuda',
+                                          'sample': '2 single-frame SMPL-X 8-view %d-iteration fits after 1 warm-up: the reference\'s '
+                                                    'eager torch op sequence (oracle/fit_port.py) on the B200 -- launch-bound, not the target' % N}
+        except Exception as ex:
+            line['gpu_eager_baseline'] = {'error': repr(ex)}
+    if world == 1 and not args.no_cpu_baseline:
         times, cores = cpu_reference_fit(args.cpu_frames, N, warm=1)
         line['cpu_baseline'] = {'value': len(times) / sum(times), 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
                                 'sample': '%d single-frame SMPL-X 8-view %d-iteration fits after 1 warm-up (oracle/fit_port.py '

@@ -10,7 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('BODYFIT_LIB') or os.path.join(_HERE, 'libbodyfit_b200.so')   # BODYFIT_LIB: A/B builds of the same ABI
-ABI_VERSION = 14
+ABI_VERSION = 15
 F_WORLD = 1
 F_TC = 2
 F_SKIN_FUSED = 4
@@ -40,9 +40,9 @@ class BfFrames(C.Structure):
     _fields_ = [(n, _fp) for n in (
         'theta', 'grad', 'adam_m', 'adam_v', 'pf', 'dpf', 'A', 'dA', 'Jtr', 'dJtr', 'full_pose', 'yaw',
         'verts', 'vposed', 'dverts', 'dvp', 'joints', 'djoints', 'kp', 'cams', 'loss', 'loss_terms', 'trace',
-        'pf_hi', 'pf_lo', 'dvp_hi', 'dvp_lo', 'gmm_grad', 'gmm_loss', 'tgrad', 'tloss', 'halo_prev', 'halo_next', 'fwd_state', 'gmm_ws', 'ws')] + [('ws_floats', C.c_int64)] + \
+        'pf_hi', 'pf_lo', 'dvp_hi', 'dvp_lo', 'gmm_grad', 'gmm_loss', 'tgrad', 'tloss', 'halo_prev', 'halo_next', 'halo_buf', 'halo_peer_prev', 'halo_peer_next', 'fwd_state', 'gmm_ws', 'ws')] + [('ws_floats', C.c_int64)] + \
         [(n, C.c_double) for n in ('lr_ts', 'lr', 'beta1', 'beta2', 'eps')] + \
-        [(n, _i32) for n in ('B', 'Nv', 'ld_v', 'iter', 'flags', '_pad0')] + \
+        [(n, _i32) for n in ('B', 'Nv', 'ld_v', 'iter', 'flags', 'halo_iters')] + \
         [(n, C.c_float) for n in ('imsize', 'constant_scale', 'sigma', 'w_pose', 'w_angle', 'w_shape', 'w_temporal', '_padf')]
 
 
@@ -96,7 +96,7 @@ def lib():
     for name, extra in (('bf_pose_forward', []), ('bf_skin_forward', [ci]), ('bf_blend_forward', [ci]), ('bf_joints_forward', [ci]),
                         ('bf_joints_backward', [ci, ci]), ('bf_keypoint_loss', [ci]), ('bf_skin_backward', [ci]), ('bf_skin_backward_parts', [ci, ci]),
                         ('bf_pose_backward', [ci]), ('bf_gmm_prior', []), ('bf_temporal_prior', []), ('bf_fit_iteration', [ci, ci]), ('bf_frame_loss_backward', []), ('bf_lbs_forward', []), ('bf_lbs_backward', []),
-                        ('bf_fit_step', []), ('bf_fit_run', [ci])):
+                        ('bf_fit_step', []), ('bf_fit_run', [ci]), ('bf_halo_begin', [ci])):
         fn = getattr(L, name)
         fn.restype = C.c_int
         fn.argtypes = [pm, pf] + extra + [vp]
@@ -111,6 +111,15 @@ def lib():
         'bf_op_angle_prior': [fp, i32, i32, fp, fp, vp],
         'bf_op_gmm_pose': [pm, fp, i32, i32, i32, fl, fp, fp, vp],
     }
+    ops.update({
+        'bf_pack_keypoints': [fp, fp, i32, i32, i32, i32, vp],
+        'bf_init_theta': [pm, fp, i32, fp, fp, i32, vp],
+        'bf_halo_alloc': [C.POINTER(C.c_void_p), fp], 'bf_halo_open': [fp, C.POINTER(C.c_void_p)],
+        'bf_halo_close': [fp], 'bf_halo_free': [fp],
+    })
+    for name in ('bf_halo_bytes', 'bf_halo_handle_bytes'):
+        getattr(L, name).restype = C.c_int
+        getattr(L, name).argtypes = []
     pg, ps = C.POINTER(BfGrid), C.POINTER(BfSmpld)
     ops.update({
         'bf_grid_count': [pg, fp, vp], 'bf_grid_fill': [pg, fp, vp],
@@ -130,7 +139,9 @@ def lib():
 
 EXPORTED = ['bf_abi_version', 'bf_sizeof', 'bf_last_error', 'bf_check_device', 'bf_pose_forward', 'bf_skin_forward', 'bf_blend_forward',
             'bf_joints_forward', 'bf_joints_backward', 'bf_keypoint_loss', 'bf_skin_backward', 'bf_skin_backward_parts',
-            'bf_pose_backward', 'bf_gmm_prior', 'bf_temporal_prior', 'bf_fit_iteration', 'bf_frame_loss_backward', 'bf_lbs_forward', 'bf_lbs_backward', 'bf_fit_step', 'bf_fit_run']
+            'bf_pose_backward', 'bf_gmm_prior', 'bf_temporal_prior', 'bf_fit_iteration', 'bf_frame_loss_backward', 'bf_lbs_forward', 'bf_lbs_backward', 'bf_fit_step', 'bf_fit_run',
+            'bf_pack_keypoints', 'bf_init_theta', 'bf_halo_bytes', 'bf_halo_handle_bytes', 'bf_halo_alloc', 'bf_halo_open',
+            'bf_halo_close', 'bf_halo_free', 'bf_halo_begin']
 
 
 EXPORTED_GRID = ['bf_grid_count', 'bf_grid_fill', 'bf_grid_nearest', 'bf_grid_inside', 'bf_grid_intersects_any', 'bf_smpld_step', 'bf_smpld_run', 'bf_pc_loss']

@@ -71,3 +71,15 @@ def smpl_to_openpose(model_type='smplx', use_hands=True, use_face=True, use_face
         start = 76 if n == 25 else 70
         out += list(range(start, start + 51 + 17 * int(bool(use_face_contour))))
     return np.array(out, dtype=np.int32)
+
+
+# Vertex ids of the 21 vertex-picked joints (smplx.vertex_ids: nose, reye, leye, rear, lear, LBigToe, LSmallToe, LHeel,
+# RBigToe, RSmallToe, RHeel, left thumb / index / middle / ring / pinky tips, right ...), in vertex_joint_selector order.
+# The official model files do not carry them (smplx hard-codes the table), so the loader falls back to these.
+EXTRA_VIDS = {
+    'smpl': [332, 6260, 2800, 4071, 583, 3216, 3226, 3387, 6617, 6624, 6787,
+             2746, 2319, 2445, 2556, 2673, 6191, 5782, 5905, 6016, 6133],
+    'smplx': [9120, 9929, 9448, 616, 6, 5770, 5780, 8846, 8463, 8474, 8635,
+              5361, 4933, 5058, 5169, 5286, 8079, 7669, 7794, 7905, 8022],
+}
+SHAPE_SPACE_DIM = 300          # official SMPL-X files: shapedirs [V,3,400] = 300 shape + 100 expression directions

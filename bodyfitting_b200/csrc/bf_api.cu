@@ -16,6 +16,7 @@
 #include "../../include/bodyfit_b200_ops.h"
 #include "bf_blend_tc.cuh"
 #include "bf_blend_tc2.cuh"
+#include "bf_pack.cuh"
 
 static thread_local char g_err[512] = "";
 
@@ -78,6 +79,7 @@ int bf_check_device(void) {
 }
 
 int bf_pose_forward(const BfModel* m, const BfFrames* f, void* stream) {
+    BF_NVTX();
     int rc = check_model(m, f); if (rc) return rc;
     BF_REQUIRE(f->pf && f->A && f->Jtr, "pf/A/Jtr is null");
     const int wpb = 4;
@@ -88,6 +90,7 @@ int bf_pose_forward(const BfModel* m, const BfFrames* f, void* stream) {
 }
 
 int bf_skin_forward(const BfModel* m, const BfFrames* f, int use_full, void* stream) {
+    BF_NVTX();
     int rc = check_model(m, f); if (rc) return rc;
     const BfVSet* vs = use_full ? &m->full : &m->act;
     rc = check_vset(vs, f); if (rc) return rc;
@@ -108,6 +111,7 @@ int bf_skin_forward(const BfModel* m, const BfFrames* f, int use_full, void* str
 }
 
 int bf_blend_forward(const BfModel* m, const BfFrames* f, int use_full, void* stream) {
+    BF_NVTX();
     int rc = check_model(m, f); if (rc) return rc;
     const BfVSet* vs = use_full ? &m->full : &m->act;
     rc = check_vset(vs, f); if (rc) return rc;
@@ -117,6 +121,7 @@ int bf_blend_forward(const BfModel* m, const BfFrames* f, int use_full, void* st
 }
 
 int bf_joints_forward(const BfModel* m, const BfFrames* f, int use_full, void* stream) {
+    BF_NVTX();
     int rc = check_model(m, f); if (rc) return rc;
     const BfVSet* vs = use_full ? &m->full : &m->act;
     rc = check_vset(vs, f); if (rc) return rc;
@@ -127,6 +132,7 @@ int bf_joints_forward(const BfModel* m, const BfFrames* f, int use_full, void* s
 }
 
 int bf_joints_backward(const BfModel* m, const BfFrames* f, int use_full, int accumulate_dverts, void* stream) {
+    BF_NVTX();
     int rc = check_model(m, f); if (rc) return rc;
     const BfVSet* vs = use_full ? &m->full : &m->act;
     rc = check_vset(vs, f); if (rc) return rc;
@@ -137,6 +143,7 @@ int bf_joints_backward(const BfModel* m, const BfFrames* f, int use_full, int ac
 }
 
 int bf_keypoint_loss(const BfModel* m, const BfFrames* f, int use_full, void* stream) {
+    BF_NVTX();
     int rc = check_model(m, f); if (rc) return rc;
     const BfVSet* vs = use_full ? &m->full : &m->act;
     rc = check_vset(vs, f); if (rc) return rc;
@@ -160,6 +167,7 @@ static SideStream* side_stream(cudaStream_t main_s, int slot = 0) {
     static int used = 0;
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> lk(g_bf_mu);
     for (int i = 0; i < used; ++i)
         if (table[i].dev == dev && table[i].main == main_s && table[i].slot == slot) return &table[i];
     if (used >= 512) return nullptr;
@@ -174,6 +182,7 @@ static SideStream* side_stream(cudaStream_t main_s, int slot = 0) {
 
 // parts: bit0 dvp, bit1 dA, bit2 blend backward GEMM (bf_skin_backward = all three)
 int bf_skin_backward_parts(const BfModel* m, const BfFrames* f, int use_full, int parts, void* stream) {
+    BF_NVTX();
     int rc = check_model(m, f); if (rc) return rc;
     const BfVSet* vs = use_full ? &m->full : &m->act;
     rc = check_vset(vs, f); if (rc) return rc;
@@ -226,18 +235,16 @@ static int launch_gmm(const BfModel* m, const float* pose, int ld, int nvalid, i
                       cudaStream_t s) {
     BF_REQUIRE(m->gmm_mean && m->gmm_psym && m->gmm_logw && m->n_gmm > 0, "GMM tables missing");
     BF_REQUIRE(pose && grad && loss && B > 0, "gmm buffers missing");
-    static bool attr = false;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(k_gmm_prior, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GmmSmem));
-        if (e != cudaSuccess) { bf_set_error("cudaFuncSetAttribute(k_gmm_prior): %s", cudaGetErrorString(e)); return BF_ECUDA; }
-        attr = true;
-    }
+    static size_t attr[BF_MAXDEV] = {0};
+    { const int rc = bf_ensure_smem(k_gmm_prior, sizeof(GmmSmem), attr, "k_gmm_prior"); if (rc) return rc; }
     k_gmm_prior<<<(B + GM_F - 1) / GM_F, GM_F * GM_PARTS, sizeof(GmmSmem), s>>>(*m, pose, ld, nvalid, B, wp, grad, loss);
     BF_LAUNCH_CHECK();
     return BF_OK;
 }
 
-// temporal smoothness: one warp per frame
+// temporal smoothness: one warp per frame.  The shard's outer neighbours come either from halo_prev / halo_next (rows the
+// host exchanged before the launch) or, with the NVLink halo (f.halo_buf, bf_pack.cuh), from the local slots the neighbouring
+// ranks' optimiser kernels wrote: the two boundary warps wait for the tick of this iteration.
 __global__ void __launch_bounds__(128) k_temporal(BfModel m, BfFrames f) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x * 4 + warp;
@@ -246,6 +253,18 @@ __global__ void __launch_bounds__(128) k_temporal(BfModel m, BfFrames f) {
     const float* cur = f.theta + (size_t)b * m.NP;
     const float* prev = b > 0 ? cur - m.NP : f.halo_prev;
     const float* next = b + 1 < f.B ? cur + m.NP : f.halo_next;
+    if (f.halo_buf && (b == 0 || b + 1 == f.B)) {
+        const uint32_t tick = *reinterpret_cast<const uint32_t*>(f.halo_buf + BF_HALO_EPOCH) + (uint32_t)f.iter;
+        const uint32_t* flags = reinterpret_cast<const uint32_t*>(f.halo_buf + BF_HALO_FLAGS);
+        if (b == 0 && f.halo_peer_prev) {
+            halo_wait(flags + (tick & 1u), tick);
+            prev = f.halo_buf + BF_HALO_PREV + (tick & 1u) * BF_HALO_ROW;
+        }
+        if (b + 1 == f.B && f.halo_peer_next) {
+            halo_wait(flags + 2 + (tick & 1u), tick);
+            next = f.halo_buf + BF_HALO_NEXT + (tick & 1u) * BF_HALO_ROW;
+        }
+    }
     const float w = f.w_temporal;
     float acc = 0.f;
     for (int i = lane; i < m.NP; i += 32) {
@@ -253,8 +272,8 @@ __global__ void __launch_bounds__(128) k_temporal(BfModel m, BfFrames f) {
         float g = 0.f;
         if (used) {
             const float x = cur[i];
-            if (prev) { const float d = x - prev[i]; acc += d * d; g += 2.0f * w * d; }
-            if (next) g += 2.0f * w * (x - next[i]);
+            if (prev) { const float d = x - __ldcv(prev + i); acc += d * d; g += 2.0f * w * d; }
+            if (next) g += 2.0f * w * (x - __ldcv(next + i));
         }
         f.tgrad[(size_t)b * m.NP + i] = g;
     }
@@ -263,6 +282,7 @@ __global__ void __launch_bounds__(128) k_temporal(BfModel m, BfFrames f) {
 }
 
 int bf_temporal_prior(const BfModel* m, const BfFrames* f, void* stream) {
+    BF_NVTX();
     int rc = check_model(m, f); if (rc) return rc;
     BF_REQUIRE(f->tgrad && f->tloss, "tgrad / tloss is null");
     k_temporal<<<(f->B + 3) / 4, 128, 0, (cudaStream_t)stream>>>(*m, *f);
@@ -271,6 +291,7 @@ int bf_temporal_prior(const BfModel* m, const BfFrames* f, void* stream) {
 }
 
 int bf_gmm_prior(const BfModel* m, const BfFrames* f, void* stream) {
+    BF_NVTX();
     int rc = check_model(m, f); if (rc) return rc;
     BF_REQUIRE(f->gmm_grad && f->gmm_loss, "gmm_grad / gmm_loss is null");
     if ((f->flags & BF_F_TC) && m->gmm_bt_hi && m->gmm_bt_lo && f->gmm_ws && (m->n_gmm * GM_LD) % TC_BN1 == 0) {
@@ -346,6 +367,7 @@ int bf_op_gmm_pose(const BfModel* m, const float* pose, int ld, int nvalid, int 
 }
 
 int bf_pose_backward(const BfModel* m, const BfFrames* f, int flags, void* stream) {
+    BF_NVTX();
     int rc = check_model(m, f); if (rc) return rc;
     BF_REQUIRE(f->dA && f->dJtr && f->dpf && f->grad && f->loss, "pose backward buffers missing");
     if (flags & 1) BF_REQUIRE(f->gmm_grad && f->gmm_loss, "gmm_grad / gmm_loss missing (run bf_gmm_prior first)");
@@ -373,6 +395,7 @@ int bf_pose_backward(const BfModel* m, const BfFrames* f, int flags, void* strea
 }
 
 int bf_lbs_forward(const BfModel* m, const BfFrames* f, void* stream) {
+    BF_NVTX();
     int rc = bf_pose_forward(m, f, stream); if (rc) return rc;
     rc = bf_skin_forward(m, f, 1, stream); if (rc) return rc;
     if (f->joints) rc = bf_joints_forward(m, f, 1, stream);
@@ -380,6 +403,7 @@ int bf_lbs_forward(const BfModel* m, const BfFrames* f, void* stream) {
 }
 
 int bf_lbs_backward(const BfModel* m, const BfFrames* f, void* stream) {
+    BF_NVTX();
     // f->dverts holds the incoming d(vertices) (dense); f->djoints the incoming d(joints) or NULL
     int rc = bf_joints_backward(m, f, 1, 1, stream); if (rc) return rc;
     rc = bf_skin_backward(m, f, 1, stream); if (rc) return rc;
@@ -401,6 +425,7 @@ static bool bf_frame_use_tma(const BfModel* m, const BfVSet* vs, const BfFrames*
 }
 
 int bf_frame_loss_backward(const BfModel* m, const BfFrames* f, void* stream) {
+    BF_NVTX();
     int rc = check_model(m, f); if (rc) return rc;
     const BfVSet* vs = &m->act;
     rc = check_vset(vs, f); if (rc) return rc;
@@ -454,19 +479,23 @@ static int fit_iteration(const BfModel* m, const BfFrames* f, bool with_forward,
         rc = bf_skin_backward(m, f, 0, stream); if (rc) return rc;
     }
     if (ss) cudaStreamWaitEvent(main_s, ss->join, 0);
-    return bf_pose_backward(m, f, 1 | 2 | 4 | (fuse_next ? 8 : 0), stream);
+    const int push = (f->halo_buf && f->tgrad && f->w_temporal > 0.f && f->iter + 1 < f->halo_iters) ? 16 : 0;
+    return bf_pose_backward(m, f, 1 | 2 | 4 | (fuse_next ? 8 : 0) | push, stream);
 }
 
 int bf_fit_step(const BfModel* m, const BfFrames* f, void* stream) {
+    BF_NVTX();
     return fit_iteration(m, f, true, false, stream);
 }
 
 int bf_fit_iteration(const BfModel* m, const BfFrames* f, int with_forward, int fuse_next, void* stream) {
+    BF_NVTX();
     BF_REQUIRE(m && f, "bad arguments");
     return fit_iteration(m, f, with_forward != 0, fuse_next != 0, stream);
 }
 
 int bf_fit_run(const BfModel* m, const BfFrames* f, int n_iters, void* stream) {
+    BF_NVTX();
     BF_REQUIRE(m && f && n_iters >= 0, "bad arguments");
     BfFrames g = *f;
     for (int i = 0; i < n_iters; ++i) {
@@ -474,6 +503,74 @@ int bf_fit_run(const BfModel* m, const BfFrames* f, int n_iters, void* stream) {
         int rc = fit_iteration(m, &g, i == 0, i + 1 < n_iters, stream); if (rc) return rc;
         g.iter++;
     }
+    return BF_OK;
+}
+
+// ---- input packing ------------------------------------------------------------------------------------------
+int bf_pack_keypoints(const float* kp_raw, float* kp_packed, int B, int Nv, int K, int hand_face, void* stream) {
+    BF_NVTX();
+    BF_REQUIRE(kp_raw && kp_packed && B > 0 && Nv > 0 && K > 0, "bad arguments");
+    BF_REQUIRE(!hand_face || K > 67, "hand / face groups need the SMPL-X joint layout (K > 67)");
+    const size_t smem = sizeof(float) * (((size_t)Nv * K * 3 + 3) / 4 * 4 + (size_t)Nv * PK_MAXG);
+    BF_REQUIRE(smem <= 48 * 1024, "Nv * K too large for one frame per CTA");
+    k_pack_keypoints<<<B, 256, smem, (cudaStream_t)stream>>>(kp_raw, kp_packed, B, Nv, K, hand_face);
+    BF_LAUNCH_CHECK();
+    return BF_OK;
+}
+
+int bf_init_theta(const BfModel* m, const float* poses, int ld_poses, const float* betas, float* theta, int B, void* stream) {
+    BF_NVTX();
+    BF_REQUIRE(m && poses && betas && theta && B > 0, "bad arguments");
+    const int nb = theta_layout(m->is_smplx).nbody;
+    BF_REQUIRE(ld_poses >= 3 + nb, "poses need global_orient + body_pose columns");
+    const size_t n = (size_t)B * m->NP;
+    k_init_theta<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(poses, ld_poses, betas, theta, B, m->NP, nb);
+    BF_LAUNCH_CHECK();
+    return BF_OK;
+}
+
+// ---- NVLink halo of the temporal term (bf_pack.cuh) --------------------------------------------------------------
+int bf_halo_bytes(void) { return (int)(BF_HALO_FLOATS * sizeof(float)); }
+int bf_halo_handle_bytes(void) { return (int)sizeof(cudaIpcMemHandle_t); }
+
+int bf_halo_alloc(void** buf, void* ipc_handle_out) {
+    BF_REQUIRE(buf, "buf is null");
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, BF_HALO_FLOATS * sizeof(float));
+    if (e != cudaSuccess) { bf_set_error("bf_halo_alloc: cudaMalloc: %s", cudaGetErrorString(e)); return BF_ECUDA; }
+    cudaMemset(p, 0, BF_HALO_FLOATS * sizeof(float));
+    cudaDeviceSynchronize();
+    if (ipc_handle_out) {
+        cudaIpcMemHandle_t h;
+        e = cudaIpcGetMemHandle(&h, p);
+        if (e != cudaSuccess) { cudaFree(p); bf_set_error("bf_halo_alloc: cudaIpcGetMemHandle: %s", cudaGetErrorString(e)); return BF_ECUDA; }
+        memcpy(ipc_handle_out, &h, sizeof(h));
+    }
+    *buf = p;
+    return BF_OK;
+}
+int bf_halo_open(const void* ipc_handle, void** peer_buf) {
+    BF_REQUIRE(ipc_handle && peer_buf, "bad arguments");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, ipc_handle, sizeof(h));
+    cudaError_t e = cudaIpcOpenMemHandle(peer_buf, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { bf_set_error("bf_halo_open: cudaIpcOpenMemHandle: %s", cudaGetErrorString(e)); return BF_ECUDA; }
+    return BF_OK;
+}
+int bf_halo_close(void* peer_buf) {
+    if (peer_buf && cudaIpcCloseMemHandle(peer_buf) != cudaSuccess) { bf_set_error("bf_halo_close failed"); return BF_ECUDA; }
+    return BF_OK;
+}
+int bf_halo_free(void* buf) {
+    if (buf && cudaFree(buf) != cudaSuccess) { bf_set_error("bf_halo_free failed"); return BF_ECUDA; }
+    return BF_OK;
+}
+int bf_halo_begin(const BfModel* m, const BfFrames* f, int n_iters, void* stream) {
+    BF_NVTX();
+    int rc = check_model(m, f); if (rc) return rc;
+    BF_REQUIRE(f->halo_buf && n_iters > 0, "halo buffer missing");
+    k_halo_begin<<<1, 64, 0, (cudaStream_t)stream>>>(*f, m->NP, n_iters);
+    BF_LAUNCH_CHECK();
     return BF_OK;
 }
 
@@ -487,6 +584,7 @@ static int check_grid(const BfGrid* g) {
 }
 
 int bf_grid_count(const BfGrid* g, int32_t* counts, void* stream) {
+    BF_NVTX();
     int rc = check_grid(g); if (rc) return rc;
     BF_REQUIRE(counts, "counts is null");
     cudaStream_t s = (cudaStream_t)stream;
@@ -499,6 +597,7 @@ int bf_grid_count(const BfGrid* g, int32_t* counts, void* stream) {
 }
 
 int bf_grid_fill(const BfGrid* g, int32_t* cursor, void* stream) {
+    BF_NVTX();
     int rc = check_grid(g); if (rc) return rc;
     BF_REQUIRE(cursor && g->cell_tris, "cursor / cell_tris is null");
     cudaStream_t s = (cudaStream_t)stream;
@@ -511,6 +610,7 @@ int bf_grid_fill(const BfGrid* g, int32_t* cursor, void* stream) {
 }
 
 int bf_grid_nearest(const BfGrid* g, const float* points, int Q, float* near_pts, int32_t* near_faces, float* dist2, void* stream) {
+    BF_NVTX();
     int rc = check_grid(g); if (rc) return rc;
     BF_REQUIRE(g->cell_tris && points && near_pts && near_faces && Q > 0, "bad arguments");
     k_grid_nearest<<<(Q + 7) / 8, 256, 0, (cudaStream_t)stream>>>(*g, points, Q, near_pts, near_faces, dist2);
@@ -519,6 +619,7 @@ int bf_grid_nearest(const BfGrid* g, const float* points, int Q, float* near_pts
 }
 
 int bf_grid_inside(const BfGrid* g, const float* points, int Q, float* signs, void* stream) {
+    BF_NVTX();
     int rc = check_grid(g); if (rc) return rc;
     BF_REQUIRE(g->cell_tris && points && signs && Q > 0, "bad arguments");
     k_grid_inside<<<(Q + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*g, points, Q, signs);
@@ -527,6 +628,7 @@ int bf_grid_inside(const BfGrid* g, const float* points, int Q, float* signs, vo
 }
 
 int bf_grid_intersects_any(const BfGrid* g, const float* origins, const float* directions, int Q, uint8_t* hit, void* stream) {
+    BF_NVTX();
     int rc = check_grid(g); if (rc) return rc;
     BF_REQUIRE(g->cell_tris && origins && directions && hit && Q > 0, "bad arguments");
     k_grid_ray_any<<<(Q + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*g, origins, directions, Q, hit);
@@ -535,6 +637,7 @@ int bf_grid_intersects_any(const BfGrid* g, const float* origins, const float* d
 }
 
 int bf_smpld_step(const BfGrid* g, const BfSmpld* p, void* stream) {
+    BF_NVTX();
     int rc = check_grid(g); if (rc) return rc;
     BF_REQUIRE(p && p->base && p->disp && p->adam_m && p->adam_v && p->faces && p->vf_ptr && p->vf_face && p->scan_fn &&
                p->P && p->C && p->near_faces && p->nhat && p->nlen && p->m && p->Nlen && p->dN && p->dcorner &&
@@ -573,6 +676,7 @@ int bf_smpld_step(const BfGrid* g, const BfSmpld* p, void* stream) {
 }
 
 int bf_smpld_run(const BfGrid* g, const BfSmpld* p, int n_iters, void* stream) {
+    BF_NVTX();
     BF_REQUIRE(g && p && n_iters >= 0, "bad arguments");
     BfSmpld q = *p;
     for (int i = 0; i < n_iters; ++i) {
@@ -641,6 +745,7 @@ __global__ void __launch_bounds__(256) k_pc_world_bwd(const float* __restrict__ 
 }
 
 int bf_mask_loss(const BfModel* m, const BfFrames* f, const BfMask* k, float weight, void* stream) {
+    BF_NVTX();
     int rc = check_model(m, f); if (rc) return rc;
     const int V = m->full.n;
     BF_REQUIRE(k && k->masks && k->cams && k->contour && k->cptr && k->cown && k->uv && k->near_q && k->cdist && k->cw && k->dPw &&
@@ -665,6 +770,7 @@ int bf_mask_loss(const BfModel* m, const BfFrames* f, const BfMask* k, float wei
 
 int bf_pc_loss(const BfGrid* g, const BfModel* m, const BfFrames* f, float scale, float weight, float* Pw,
                float* near_pts, int32_t* near_faces, float* pc_loss, void* stream) {
+    BF_NVTX();
     int rc = check_grid(g); if (rc) return rc;
     rc = check_model(m, f); if (rc) return rc;
     const int V = m->full.n;

@@ -430,8 +430,36 @@ static bf_encode_tiled_fn bf_get_encode() {
     return fn;
 }
 
+// Tensor maps describe (address, shape, box) only, so one encoded for a buffer stays valid for as long as the same view of
+// the same address is used: the per-iteration launches of a fit re-use them from this table instead of calling the
+// driver twelve times per iteration (the operands of a session never move).
+struct BfMapKey { const void* base; uint64_t rows, cols, ld; uint32_t box_rows; int dev; };
+struct BfMapEntry { BfMapKey k; CUtensorMap map; };
+#define BF_MAP_CACHE 512
+static BfMapEntry g_map_cache[BF_MAP_CACHE];
+static int g_map_used = 0;
+
+static int bf_make_map_uncached(CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
 // [rows, cols] fp32 row-major with leading dimension ld (elements); box = TC_BK cols (one swizzle row) x box_rows
 static int bf_make_map(CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+    const int dev = bf_cur_dev();
+    std::lock_guard<std::mutex> lk(g_bf_mu);
+    for (int i = 0; i < g_map_used; ++i) {
+        const BfMapKey& k = g_map_cache[i].k;
+        if (k.base == base && k.rows == rows && k.cols == cols && k.ld == ld && k.box_rows == box_rows && k.dev == dev) {
+            *m = g_map_cache[i].map;
+            return BF_OK;
+        }
+    }
+    const int rc = bf_make_map_uncached(m, base, rows, cols, ld, box_rows);
+    if (rc) return rc;
+    if (g_map_used == BF_MAP_CACHE) g_map_used = 0;            // full: start over (entries are only a cache)
+    g_map_cache[g_map_used].k = BfMapKey{base, rows, cols, ld, box_rows, dev};
+    g_map_cache[g_map_used].map = *m;
+    ++g_map_used;
+    return BF_OK;
+}
+static int bf_make_map_uncached(CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
     bf_encode_tiled_fn enc = bf_get_encode();
     if (!enc) { bf_set_error("cuTensorMapEncodeTiled not available from the driver"); return BF_ECUDA; }
     cuuint64_t dims[2] = {cols, rows};
@@ -465,16 +493,9 @@ static int bf_gemm_forward_tc(const float* a_hi_p, const float* a_lo_p, const fl
     if ((rc = bf_make_map(&b_hi, bt_hi_p, ldn, Kp, Kp, TC_BN1))) return rc;
     if ((rc = bf_make_map(&b_lo, bt_lo_p, ldn, Kp, Kp, TC_BN1))) return rc;
     const size_t smem = 1024 + TC_STAGES * (2 * TC_BM * TC_ROWB + 2 * TC_BN1 * TC_ROWB) + TC_EPI_WARPS * TC_ST_FLOATS * 4 + 128;
-    static bool attr = false;
-    static int num_sms = 0;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(k_blend_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) { bf_set_error("cudaFuncSetAttribute(k_blend_fwd_tc): %s", cudaGetErrorString(e)); return BF_ECUDA; }
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-        attr = true;
-    }
+    static size_t attr[BF_MAXDEV] = {0};
+    if ((rc = bf_ensure_smem(k_blend_fwd_tc, smem, attr, "k_blend_fwd_tc"))) return rc;
+    const int num_sms = bf_num_sms();
     const int tn = (ldn + TC_BN1 - 1) / TC_BN1, tm = (B + TC_BM - 1) / TC_BM;
     const int tiles = tn * tm;
     const int grid = tiles < num_sms ? tiles : num_sms;          // persistent: one CTA per SM
@@ -498,8 +519,7 @@ static int bf_blend_backward_tc(const BfModel* m, const BfVSet* vs, const BfFram
     // column tile: the widest of 256 / 128 / 64 that divides Kp (else Kp itself).  The kernel streams its operands from L2
     // and every column tile re-reads the whole dvp row block, so the widest tile wins even when it leaves a partial last
     // wave: measured on 10,000 frames x Kp 512, 64 / 128 / 256 columns = 0.134 / 0.123 / 0.109 ms (158 CTAs on 148 SMs).
-    static int num_sms = 0;
-    if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); }
+    const int num_sms = bf_num_sms();
     int BN = m->Kp < 256 ? m->Kp : 256;
     {
         const int cand[3] = {256, 128, 64};
@@ -507,6 +527,13 @@ static int bf_blend_backward_tc(const BfModel* m, const BfVSet* vs, const BfFram
             if (cand[i] <= m->Kp && m->Kp % cand[i] == 0) { BN = cand[i]; break; }
     }
     if (m->Kp % BN != 0 || BN % 16 != 0) { bf_set_error("Kp=%d not tileable by %d", m->Kp, BN); return BF_EINVAL; }
+    // Small batches (a shard of a strong-scaled sequence: 1,250 frames x Kp 512 = 20 tiles of 256 columns on 148 SMs): narrower
+    // column tiles until the grid covers at least half of the SMs.  Every output element still accumulates its K products
+    // in the same order, so the result does not depend on the tile width (bit-identical across batch sizes, tested).
+    if (vs->ldn / TC_BK <= 2048 / TC_BK) {                 // single accumulation run only (the all-vertex backward is split-K)
+        const int mt = (f->B + TC_BM - 1) / TC_BM;
+        while (BN > 64 && (m->Kp / BN) * mt * 2 < num_sms && m->Kp % (BN / 2) == 0 && (BN / 2) % 16 == 0) BN /= 2;
+    }
     {
         static int forced = -1;                           // BODYFIT_BWD_BN=64|128|256: tile-width experiments
         if (forced < 0) { const char* e = getenv("BODYFIT_BWD_BN"); forced = e ? atoi(e) : 0; }
@@ -524,13 +551,9 @@ static int bf_blend_backward_tc(const BfModel* m, const BfVSet* vs, const BfFram
         if (st_env == 2) NS = 2;                        // measured: slower in the full fit at either width
     }
     const size_t smem = 1024 + NS * (2 * TC_BM * TC_ROWB + 2 * (size_t)BN * TC_ROWB) + 64;
-    static size_t attr[2] = {0, 0};
-    if (attr[NS == 2] < smem) {
-        cudaError_t e = NS == 2 ? cudaFuncSetAttribute(k_blend_bwd_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                                : cudaFuncSetAttribute(k_blend_bwd_tc<TC_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) { bf_set_error("cudaFuncSetAttribute(k_blend_bwd_tc): %s", cudaGetErrorString(e)); return BF_ECUDA; }
-        attr[NS == 2] = smem;
-    }
+    static size_t attr[2][BF_MAXDEV] = {{0}};
+    if ((rc = NS == 2 ? bf_ensure_smem(k_blend_bwd_tc<2>, smem, attr[1], "k_blend_bwd_tc<2>")
+                      : bf_ensure_smem(k_blend_bwd_tc<TC_STAGES>, smem, attr[0], "k_blend_bwd_tc"))) return rc;
     const int num_k = vs->ldn / TC_BK;
     const size_t stride = (size_t)f->B * m->Kp;
     // split-K: at most 2048 coordinates per tensor-core accumulation run (accuracy, see above); when the (frame tile x
@@ -545,7 +568,8 @@ static int bf_blend_backward_tc(const BfModel* m, const BfVSet* vs, const BfFram
         if (S_fill > num_k) S_fill = num_k;
         // Off by default: the GEMM alone gets faster (SMPL x 1024 frames: 100 -> 77 us) but the all-vertex backward as a whole
         // slower (327 -> 341 us) -- its 144 large-shared-memory CTAs crowd out the dA gather kernel that runs next to it on the
-        // side stream, which is the longer of the two.  BODYFIT_BWD_FILL=1 enables it.
+        // side stream, which is the longer of the two; and a batch-size dependent split would make results depend on the
+        // batch size in the last bit.  BODYFIT_BWD_FILL=1 enables it.
         static int fill_env = -1;
         if (fill_env < 0) { const char* e = getenv("BODYFIT_BWD_FILL"); fill_env = e ? atoi(e) : 0; }
         if (!fill_env) S_fill = 0;

@@ -205,16 +205,9 @@ static int bf_gemm_forward_tc2(const float* a_hi_p, const float* a_lo_p, const f
     if ((rc = bf_make_map(&b_hi, bt_hi_p, ldn, Kp, Kp, TC_BN1 / 2))) return rc;
     if ((rc = bf_make_map(&b_lo, bt_lo_p, ldn, Kp, Kp, TC_BN1 / 2))) return rc;
     const size_t smem = 1024 + (size_t)TC2_STAGES * (2 * TC_BM * TC_ROWB + 2 * (TC_BN1 / 2) * TC_ROWB) + TC_EPI_WARPS * TC_ST_FLOATS * 4 + 256;
-    static bool attr = false;
-    static int num_sms = 0;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(k_blend_fwd_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) { bf_set_error("cudaFuncSetAttribute(k_blend_fwd_tc2): %s", cudaGetErrorString(e)); return BF_ECUDA; }
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-        attr = true;
-    }
+    static size_t attr[BF_MAXDEV] = {0};
+    if ((rc = bf_ensure_smem(k_blend_fwd_tc2, smem, attr, "k_blend_fwd_tc2"))) return rc;
+    const int num_sms = bf_num_sms();
     const int tn = (ldn + TC_BN1 - 1) / TC_BN1, tm = (B + 2 * TC_BM - 1) / (2 * TC_BM);
     const int tiles = tn * tm;
     int clusters = num_sms / 2;

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <mutex>
+#include <nvtx3/nvToolsExt.h>
 #include "../../include/bodyfit_b200.h"
 
 #define BF_MAXJ 55          // SMPL-X kinematic tree
@@ -11,6 +13,42 @@
 #define BF_GMM_D 69
 
 void bf_set_error(const char* fmt, ...);
+
+// ---- per-device host state ------------------------------------------------------------------------------------
+// Kernel attributes (opt-in shared memory) and the SM count belong to a DEVICE, not to the process: every cache below is
+// indexed by the current device, and the slow paths (first use on a device, side-stream / tensor-map tables) take one
+// process-wide mutex, so two host threads driving two GPUs (or the same one) do not race.
+#define BF_MAXDEV 32
+static std::mutex g_bf_mu;
+static inline int bf_cur_dev() { int d = 0; cudaGetDevice(&d); return (d >= 0 && d < BF_MAXDEV) ? d : 0; }
+static inline int bf_num_sms() {
+    static int sms[BF_MAXDEV] = {0};
+    const int d = bf_cur_dev();
+    if (!sms[d]) {
+        std::lock_guard<std::mutex> lk(g_bf_mu);
+        int n = 0;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d);
+        sms[d] = n > 0 ? n : 1;
+    }
+    return sms[d];
+}
+// opt a kernel into `smem` bytes of dynamic shared memory on the current device (once per device and size)
+template <typename F>
+static inline int bf_ensure_smem(F* fn, size_t smem, size_t* cache /* [BF_MAXDEV] */, const char* what) {
+    const int d = bf_cur_dev();
+    if (cache[d] >= smem) return BF_OK;
+    std::lock_guard<std::mutex> lk(g_bf_mu);
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { bf_set_error("cudaFuncSetAttribute(%s, %zu): %s", what, smem, cudaGetErrorString(e)); return BF_ECUDA; }
+    cache[d] = smem;
+    return BF_OK;
+}
+// NVTX range around every C-ABI entry point (visible in nsys / ncu --nvtx; a no-op without an attached tool)
+struct BfRange {
+    explicit BfRange(const char* name) { nvtxRangePushA(name); }
+    ~BfRange() { nvtxRangePop(); }
+};
+#define BF_NVTX() BfRange bf_nvtx_range_(__func__)
 
 #define BF_REQUIRE(cond, msg)                                   \
     do { if (!(cond)) { bf_set_error("%s: %s", __func__, msg); return BF_EINVAL; } } while (0)

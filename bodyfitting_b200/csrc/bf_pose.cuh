@@ -10,6 +10,7 @@
 // (smplify/smplify.py:167-174,211-213).
 #pragma once
 #include "bf_common.cuh"
+#include "bf_pack.cuh"
 
 // fp | R | Jr | GR are contiguous and 16-byte aligned, in the order of a saved forward-state row ([fp 3J | R 9J | Jr 3J |
 // GR 9J], pose_write_outputs): for J == BF_MAXJ the backward fetches the row with ONE bulk copy.
@@ -210,7 +211,9 @@ __global__ void __launch_bounds__(128) k_pose_fwd(BfModel m, BfFrames f) {
 }
 
 // flags: 1 = priors, 2 = Adam, 4 = keep grad[0:4] written by the loss kernel (else zero them),
-//        8 = after the Adam step also run the NEXT iteration's pose forward (saves a launch + a theta round trip)
+//        8 = after the Adam step also run the NEXT iteration's pose forward (saves a launch + a theta round trip),
+//        16 = NVLink halo: the first / last frame of the shard store their updated theta row into the neighbouring
+//             ranks' halo buffers and raise the flag of the next iteration's tick (bf_pack.cuh)
 struct AdamArgs { float step_ts, step_lr, bc2_sqrt, beta2, om_beta1, om_beta2, eps; };
 
 __global__ void __launch_bounds__(128) k_pose_bwd(BfModel m, BfFrames f, int flags, AdamArgs ad) {
@@ -490,6 +493,12 @@ __global__ void __launch_bounds__(128) k_pose_bwd(BfModel m, BfFrames f, int fla
             th[i] = tn;
             am[i] = mi; av[i] = vi;
             S.th[i] = tn;
+        }
+        if ((flags & 16) && f.halo_buf && (b == 0 || b + 1 == f.B)) {
+            __syncwarp();
+            const uint32_t tick = *reinterpret_cast<const uint32_t*>(f.halo_buf + BF_HALO_EPOCH) + (uint32_t)f.iter + 1u;
+            if (b == 0 && f.halo_peer_prev) halo_push_row(S.th, m.NP, f.halo_peer_prev, BF_HALO_NEXT, tick, lane);
+            if (b + 1 == f.B && f.halo_peer_next) halo_push_row(S.th, m.NP, f.halo_peer_next, BF_HALO_PREV, tick, lane);
         }
         if (flags & 8) {
             __syncwarp();

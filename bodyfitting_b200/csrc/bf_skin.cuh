@@ -457,15 +457,13 @@ k_skin_rows(BfVSet vs, int J, const float* __restrict__ A, const float* in, floa
 static int bf_launch_skin_rows(int mode, const BfVSet* vs, int J, const float* A, const float* in, float* out, float* out_hi,
                                float* out_lo, int B, int ld_v, int ld_out, const float* theta, int NP, float cs, cudaStream_t s) {
     const size_t smem = sizeof(float) * ((size_t)3 * J * 32 * 4 + (size_t)SR_WARPS * SR_TILE);
-    static size_t attr[2] = {0, 0};
-    if (attr[mode] < smem) {
-        cudaError_t e = mode == 0 ? cudaFuncSetAttribute(k_skin_rows<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                                  : cudaFuncSetAttribute(k_skin_rows<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) { bf_set_error("cudaFuncSetAttribute(k_skin_rows): %s", cudaGetErrorString(e)); return BF_ECUDA; }
-        attr[mode] = smem;
+    static size_t attr[2][BF_MAXDEV] = {{0}};
+    {
+        const int rc = mode == 0 ? bf_ensure_smem(k_skin_rows<0>, smem, attr[0], "k_skin_rows<0>")
+                                 : bf_ensure_smem(k_skin_rows<1>, smem, attr[1], "k_skin_rows<1>");
+        if (rc) return rc;
     }
-    static int num_sms = 0;
-    if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); }
+    const int num_sms = bf_num_sms();
     // 32 frames per CTA (one CTA per SM); the vertex range is cut into slabs only while that is needed to fill the SMs:
     // at most two full rounds of CTAs, each slab at least one 16-vertex chunk per warp
     const int groups = (B + 31) / 32, n_chunks = (vs->n + 15) / 16;

@@ -3,6 +3,8 @@
 Torch is used for device memory, the current stream and autograd plumbing only; every
 arithmetic step of the path is a kernel in ``libbodyfit_b200.so``.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -69,7 +71,7 @@ class FrameBuffers(object):
                 buf('dvp_lo', B, ldn, zero=True)
                 nsplit = (ldn // 32 + 63) // 64          # accuracy: <= 2048 coordinates per accumulation run
                 if nsplit > 1:
-                    # + room to cut the reduction further when the tile grid alone would leave SMs idle (small batches)
+                    # + room to cut the reduction further when the tile grid alone would leave SMs idle (BODYFIT_BWD_FILL=1)
                     sms = torch.cuda.get_device_properties(dev).multi_processor_count
                     tiles = ((B + 127) // 128) * max(1, Kp // 256)
                     buf('ws', max(nsplit, min(64, sms // tiles)), B, Kp)
@@ -147,18 +149,36 @@ class FitSession(object):
     """
 
     def __init__(self, model: PreparedModel, B, Nv, num_iters, imsize=512, return_vertices=True,
-                 chunk=4096, trace=True, dense_every_iter=False, temporal_weight=0.0, halo_exchange=None, out=None):
+                 chunk=4096, trace=True, dense_every_iter=False, temporal_weight=0.0, halo_exchange=None, out=None,
+                 halo=None, graph=None):
         """``out`` (optional): externally owned result buffers for these B frames -- ``theta`` [B,NP], ``verts`` [B,V,3],
-        ``joints`` [B,K_full,3], ``full_pose`` [B,3J] (contiguous row slices of a larger batch: ConcurrentFitSession)."""
+        ``joints`` [B,K_full,3], ``full_pose`` [B,3J] (contiguous row slices of a larger batch: ConcurrentFitSession).
+        ``halo``: a sharding.HaloLink -- boundary rows of the temporal term travel by in-kernel NVLink stores (graph-capturable);
+        ``halo_exchange``: the host-driven fallback (a callable, one NCCL send/recv pair per iteration).
+        ``graph``: capture the whole run (N iterations + the all-vertex forward) in ONE CUDA graph on first use and replay it
+        afterwards (default on; BODYFIT_GRAPH=0 or a host halo callback turn it off).  Inputs live in session-owned static
+        buffers (``kp``, ``cams``, ``theta0``), so the captured pointers never change."""
         self.model, self.B, self.Nv, self.N = model, int(B), int(Nv), int(num_iters)
         assert self.N >= 1
         dev = model.device
         out = out or {}
         self.fb = FrameBuffers(model, B, full=False, Nv=Nv, n_trace=(self.N if trace else 0), imsize=imsize,
                                temporal_weight=temporal_weight, ext=dict(theta=out.get('theta')))
+        # static inputs of the captured run
+        self.kp = torch.zeros(B, model.K_used, Nv, 3, device=dev)
+        self.cams = torch.zeros(Nv, 12, device=dev)
+        self.theta0 = torch.zeros(B, model.NP, device=dev)
+        self.fb.bind('kp', self.kp)
+        self.fb.bind('cams', self.cams)
         # halo_exchange(first_row, last_row) -> (prev_row | None, next_row | None): boundary frames of the
         # neighbouring ranks, called before every iteration when the temporal term couples frames across shards
-        self.halo_exchange = halo_exchange if temporal_weight > 0 else None
+        self.halo = halo if temporal_weight > 0 else None
+        self.halo_exchange = halo_exchange if (temporal_weight > 0 and self.halo is None) else None
+        if self.halo is not None:
+            self.fb.struct.halo_buf = self.halo.buf
+            self.fb.struct.halo_peer_prev = self.halo.peer_prev
+            self.fb.struct.halo_peer_next = self.halo.peer_next
+            self.fb.struct.halo_iters = self.N
         self.theta_prev = torch.empty(B, model.NP, device=dev)
         self.verts = (out['verts'] if out.get('verts') is not None else torch.empty(B, model.V, 3, device=dev)) if return_vertices else None
         self.joints = out['joints'] if out.get('joints') is not None else torch.empty(B, model.K_full, 3, device=dev)
@@ -182,12 +202,35 @@ class FitSession(object):
             fbf.struct.flags |= _lib.F_WORLD
             self.chunks.append(fbf)
         self.kernel_launches = 0
+        if graph is None:
+            graph = os.environ.get('BODYFIT_GRAPH', '1') != '0'
+        self.use_graph = bool(graph) and self.halo_exchange is None
+        self.graph = None
+        self.gstream = None
+        self._aligned = False
 
     def set_inputs(self, kp_packed, cams):
-        """kp_packed [B,K_used,Nv,3] (x, y, effective weight; pack_keypoints) and cams [Nv,12], device tensors."""
-        assert kp_packed.shape == (self.B, self.model.K_used, self.Nv, 3) and kp_packed.is_contiguous()
-        self.fb.bind('kp', kp_packed)
-        self.fb.bind('cams', cams)
+        """kp_packed [B,K_used,Nv,3] (x, y, effective weight; pack_keypoints) and cams [Nv,12], device tensors: copied into
+        the session's static input buffers."""
+        assert kp_packed.shape == (self.B, self.model.K_used, self.Nv, 3)
+        if kp_packed.data_ptr() != self.kp.data_ptr():
+            self.kp.copy_(kp_packed)
+        if cams.data_ptr() != self.cams.data_ptr():
+            self.cams.copy_(cams)
+
+    def load_inputs(self, kp_raw, cams, poses, betas):
+        """Device tensors in the caller's layout -> the static input buffers, by two small kernels (no torch arithmetic):
+        kp_raw [B,Nv,K,3] (x, y, conf), cams [Nv,12], poses [B,>=3+nbody], betas [B,10] (smplify.py:103-128)."""
+        m = self.model
+        assert kp_raw.shape == (self.B, self.Nv, m.K_used, 3) and kp_raw.is_contiguous() and kp_raw.dtype == torch.float32
+        assert poses.is_contiguous() and betas.is_contiguous() and betas.shape == (self.B, 10)
+        L, st = _lib.lib(), _stream()
+        _lib.check(L.bf_pack_keypoints(kp_raw.data_ptr(), self.kp.data_ptr(), self.B, self.Nv, m.K_used, int(m.is_smplx), st),
+                   'bf_pack_keypoints')
+        _lib.check(L.bf_init_theta(m.struct, poses.data_ptr(), int(poses.shape[1]), betas.data_ptr(), self.theta0.data_ptr(),
+                                   self.B, st), 'bf_init_theta')
+        self.cams.copy_(cams, non_blocking=True)
+        return 2
 
     def _exchange(self):
         th = self.fb.t['theta']
@@ -200,12 +243,17 @@ class FitSession(object):
             fbf.call('bf_lbs_forward')
         return (4 if self.model.tensor_cores else 3) * len(self.chunks)     # pose, blend GEMM (+ row skinning), joints
 
-    def run(self, theta0):
+    def _body(self):
+        """Every launch of one run, on the current stream (captured once, or issued directly)."""
         fb, N = self.fb, self.N
-        fb.t['theta'].copy_(theta0)
+        fb.t['theta'].copy_(self.theta0)
         fb.t['adam_m'].zero_()
         fb.t['adam_v'].zero_()
         launches = 0
+        if self.halo is not None:
+            fb.struct.iter = 0
+            fb.call('bf_halo_begin', N)
+            launches += 1
         # kernels of one iteration: blend GEMM, per-frame loss/backward, GMM prior (pack + GEMM + select on tensor cores,
         # one FFMA kernel otherwise), blend backward GEMM, pose backward (+ next pose forward); + temporal term if on
         per_it = 4 + (3 if 'gmm_ws' in fb.t else 1) + (1 if 'tgrad' in fb.t else 0)
@@ -236,7 +284,39 @@ class FitSession(object):
         fb.call('bf_fit_step')
         launches += per_it + 1
         self.kernel_launches = launches
-        return fb.t['theta']
+
+    def _capture(self):
+        """One uncaptured run on the session's capture stream (one-time setup of kernel attributes / side streams happens
+        outside the capture), then the same launches recorded into a CUDA graph; the library's fork / join events to its
+        side stream become graph edges."""
+        dev = self.model.device
+        cur = torch.cuda.current_stream(dev)
+        self.gstream = torch.cuda.Stream(device=dev)
+        self.gstream.wait_stream(cur)
+        with torch.cuda.stream(self.gstream):
+            self._body()
+        self.gstream.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=self.gstream, capture_error_mode='thread_local'):
+            self._body()
+        cur.wait_stream(self.gstream)
+        self.graph = g
+
+    def run(self, theta0=None):
+        """N iterations from ``theta0`` ([B,NP] device tensor; None = whatever load_inputs / a previous call left in the
+        static ``theta0`` buffer)."""
+        if theta0 is not None and theta0.data_ptr() != self.theta0.data_ptr():
+            self.theta0.copy_(theta0)
+        if self.halo is not None and not self._aligned:
+            self.halo.align()
+            self._aligned = True
+        if self.use_graph:
+            if self.graph is None:
+                self._capture()
+            self.graph.replay()
+        else:
+            self._body()
+        return self.fb.t['theta']
 
     @property
     def theta(self):
@@ -295,7 +375,7 @@ class ConcurrentFitSession(object):
     Same interface as FitSession (set_inputs / run / results)."""
 
     def __init__(self, model: PreparedModel, B, Nv, num_iters, imsize=512, return_vertices=True, dense_every_iter=False,
-                 n_parts=4, trace=True, min_part=2048, lead=0, taper=0.5):
+                 n_parts=4, trace=True, min_part=2048, lead=0, taper=0.5, graph=None):
         self.model, self.B, self.Nv, self.N = model, int(B), int(Nv), int(num_iters)
         dev = model.device
         self.ranges = staggered_ranges(self.B, n_parts, min_part=min_part, lead=lead, taper=taper)
@@ -313,7 +393,7 @@ class ConcurrentFitSession(object):
             out = dict(theta=self.theta[lo:hi], joints=self.joints[lo:hi], full_pose=self.full_pose[lo:hi],
                        verts=self.verts[lo:hi] if return_vertices else None)
             self.parts.append(FitSession(model, hi - lo, Nv, num_iters, imsize=imsize, return_vertices=return_vertices,
-                                         dense_every_iter=dense_every_iter, trace=trace, out=out))
+                                         dense_every_iter=dense_every_iter, trace=trace, out=out, graph=graph))
             self.streams.append(torch.cuda.Stream(device=dev))
             self.prio_streams.append(torch.cuda.Stream(device=dev, priority=min(lowest, max(highest, highest + k))))
         self.kernel_launches = 0
@@ -323,14 +403,20 @@ class ConcurrentFitSession(object):
         for (lo, hi), p in zip(self.ranges, self.parts):
             p.set_inputs(kp_packed[lo:hi], cams)
 
-    def run(self, theta0):
+    def load_inputs(self, kp_raw, cams, poses, betas):
+        n = 0
+        for (lo, hi), p in zip(self.ranges, self.parts):
+            n += p.load_inputs(kp_raw[lo:hi], cams, poses[lo:hi], betas[lo:hi])
+        return n
+
+    def run(self, theta0=None):
         cur = torch.cuda.current_stream()
         ready = torch.cuda.Event()
         ready.record(cur)
         for (lo, hi), p, st in zip(self.ranges, self.parts, self.streams):
             st.wait_event(ready)
             with torch.cuda.stream(st):
-                p.run(theta0[lo:hi])
+                p.run(None if theta0 is None else theta0[lo:hi])
         for st in self.streams:
             cur.wait_stream(st)
         self.kernel_launches = sum(p.kernel_launches for p in self.parts)

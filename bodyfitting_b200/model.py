@@ -22,6 +22,7 @@ smplx (un-vendored) as restated in oracle/smplx_port.py.
 """
 import ctypes as C
 import os
+import warnings
 
 import numpy as np
 import torch
@@ -53,12 +54,14 @@ def load_model_data(path_or_dict, model_type=None, gender='neutral'):
         mt = model_type or 'smpl'
         base = os.path.basename(os.path.normpath(path))
         folder = path if base == mt else os.path.join(path, mt)
-        cands = [os.path.join(folder, '%s_%s.%s' % (mt.upper(), g, ext))
-                 for g in (str(gender).upper(), 'NEUTRAL') for ext in ('npz', 'pkl')]
+        want = [os.path.join(folder, '%s_%s.%s' % (mt.upper(), str(gender).upper(), ext)) for ext in ('npz', 'pkl')]
+        cands = want + [os.path.join(folder, '%s_NEUTRAL.%s' % (mt.upper(), ext)) for ext in ('npz', 'pkl')]
         found = [c for c in cands if os.path.exists(c)]
         if not found:
             raise FileNotFoundError('no %s model file under %s (tried %s)' % (mt, path, cands))
         path = found[0]
+        if path not in want:        # the reference would fail here (SMPL(gender=...) / smplx.create(gender=...)); say so loudly
+            warnings.warn('no %s model for gender %r under %s: using %s' % (mt, gender, folder, os.path.basename(path)))
     if path.endswith('.pkl'):
         import pickle
         with open(path, 'rb') as f:
@@ -72,7 +75,7 @@ class PreparedModel(object):
     """numpy tables -> device tensors -> BfModel struct (kept alive by this object)."""
 
     def __init__(self, smpl_type, data, gmm=None, J_regressor_extra=None, device='cuda', num_betas=10,
-                 num_expression=10, tensor_cores=None):
+                 num_expression=10, tensor_cores=None, gender='neutral'):
         assert smpl_type in ('smpl', 'smplx')
         self.smpl_type = smpl_type
         self.is_smplx = smpl_type == 'smplx'
@@ -80,7 +83,8 @@ class PreparedModel(object):
             tensor_cores = os.environ.get('BODYFIT_TC', '1') != '0'
         self.tensor_cores = bool(tensor_cores)
         self.device = torch.device(device)
-        data = load_model_data(data, smpl_type)
+        data = load_model_data(data, smpl_type, gender)
+        self.gender = gender
         self.faces = np.asarray(data['f']).astype(np.int64)
         vt = np.asarray(data['v_template'], dtype=np.float32)
         V = vt.shape[0]
@@ -92,7 +96,15 @@ class PreparedModel(object):
         P = (J - 1) * 9
         NB = num_betas
         NS = NB + (num_expression if self.is_smplx else 0)
-        sd = np.asarray(data['shapedirs'], dtype=np.float32)[:, :, :NS]
+        sd_all = np.asarray(data['shapedirs'], dtype=np.float32)
+        if sd_all.ndim == 2:
+            sd_all = sd_all[:, :, None]
+        if self.is_smplx and sd_all.shape[-1] >= K.SHAPE_SPACE_DIM + num_expression:
+            # official files: the expression directions follow the 300 shape directions (smplx: SHAPE_SPACE_DIM)
+            sd = np.concatenate([sd_all[:, :, :NB], sd_all[:, :, K.SHAPE_SPACE_DIM:K.SHAPE_SPACE_DIM + num_expression]], -1)
+        else:
+            sd = sd_all[:, :, :NS]                  # 10 shape (+ 10 expression) directions stored back to back
+        sd = np.ascontiguousarray(sd)
         assert sd.shape == (V, 3, NS), sd.shape
         pdirs = np.asarray(data['posedirs'], dtype=np.float32)
         PD = np.reshape(pdirs, [-1, P]).T                                   # [P, 3V]
@@ -126,7 +138,10 @@ class PreparedModel(object):
             hand_r = np.asarray(data['hands_componentsr'], dtype=np.float32)[:6]
 
         # ---- output joint table (pre-map list, then the reference's joint map) --------------------
-        extra_vids = np.asarray(data['extra_vids']).astype(np.int64)
+        # vertex-picked joints: the official files do not list them (smplx hard-codes the ids)
+        extra_vids = np.asarray(data['extra_vids'] if 'extra_vids' in data else K.EXTRA_VIDS[smpl_type]).astype(np.int64)
+        assert extra_vids.max() < V, 'vertex-picked joint ids outside the mesh'
+        self.extra_vids = extra_vids
         pre = [(0, (j, 0, 0), (1.0, 0.0, 0.0)) for j in range(J)]
         pre += [(1, (int(v), int(v), int(v)), (1.0, 0.0, 0.0)) for v in extra_vids]
         dyn_faces = dyn_bary = None

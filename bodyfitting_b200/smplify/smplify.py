@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 from .. import constants as K
-from ..engine import ConcurrentFitSession, FitSession, pack_cameras, pack_keypoints, staggered_ranges
+from ..engine import ConcurrentFitSession, FitSession, pack_cameras, pack_keypoints, staggered_ranges  # noqa: F401
 from ..model import PreparedModel
 from ..synthetic import openpose_to_keypoints
 
@@ -28,7 +28,8 @@ class SMPLify(object):
     def __init__(self, smpl_type='smpl', age='adult', step_size=1e-2, batch_size=1, num_iters=600,
                  gender='male', use_mask=False, device=torch.device('cuda'), debug=True,
                  model_data=None, gmm=None, J_regressor_extra=None, data_root='data', dense_every_iter=False,
-                 concurrent_parts=None, concurrent_min_part=2048, temporal_weight=0.0, halo_exchange=None):
+                 concurrent_parts=None, concurrent_min_part=2048, temporal_weight=0.0, halo_exchange=None, halo=None,
+                 copy_outputs=None, graph=None):
         if age != 'adult':
             raise NotImplementedError("only age='adult' is supported (kid template: smplify.py:114-115)")
         self.device = torch.device(device)
@@ -52,12 +53,19 @@ class SMPLify(object):
             fn = os.path.join(data_root, 'J_regressor_extra.npy')      # config.py:1, models/smpl.py:62
             J_regressor_extra = np.load(fn) if os.path.exists(fn) else None
         self.model = PreparedModel(smpl_type, model_data, gmm=gmm, J_regressor_extra=J_regressor_extra,
-                                   device=self.device)
+                                   device=self.device, gender=gender)
         self.smpl_faces = self.model.faces.astype(np.int32).reshape(1, -1, 3)
         self.last_trace = None
         self.dense_every_iter = dense_every_iter
         # temporal smoothness between consecutive frames of the batch (not in the reference; BASELINE config 4)
-        self.temporal_weight, self.halo_exchange = float(temporal_weight), halo_exchange
+        # halo: a sharding.HaloLink (boundary rows by in-kernel NVLink stores, graph-capturable) or halo_exchange: a host
+        # callback (sharding.exchange_halo, one NCCL send/recv pair per iteration) -- the tested fallback
+        self.temporal_weight, self.halo_exchange, self.halo = float(temporal_weight), halo_exchange, halo
+        # Results on the host: the reference returns fresh arrays.  True = always copy out of the pinned staging buffers,
+        # False = return views of them (valid until the next call with the same shapes), None = copy unless the results
+        # exceed 256 MB (a 10,000-frame SMPL-X batch holds 1.28 GB of vertices; copying it again would cost more than the fit)
+        self.copy_outputs = copy_outputs
+        self.graph = graph            # None: CUDA-graph replay of the whole fit unless BODYFIT_GRAPH=0; False: direct launches
         # batches of >= 4096 frames are fitted as up to this many staggered parts on their own streams (1 = one batch)
         if concurrent_parts is None:
             concurrent_parts = int(os.environ.get('BODYFIT_PARTS', '4'))
@@ -102,20 +110,20 @@ class SMPLify(object):
         if isinstance(sess, ConcurrentFitSession):
             return self._call_concurrent(sess, init_betas, init_poses, kp, c2ws, Ks, as_numpy)
 
-        # host -> device (pinned staging so the copies are asynchronous DMA)
-        kp_dev = self._h2d('kp', kp)
-        poses_dev = self._h2d('poses', init_poses)
-        betas_dev = self._h2d('betas', init_betas)
-        cams = self._h2d('cams', torch.from_numpy(pack_cameras(c2ws, Ks)))
-        sess.set_inputs(pack_keypoints(kp_dev, self.use_hand_face), cams)
-        # init: body pose / betas / global orient from the network, transl 0, scale 1, rest 0 (smplify.py:103-128)
-        theta0 = m.pack_theta(poses_dev[:, :3], poses_dev[:, 3:3 + m.nbody], betas_dev)
-        sess.run(theta0)
-        out = sess.results()
-        self.last_trace = sess.fb.t.get('trace')
-        self.last_loss_terms = sess.fb.t['loss_terms']
-        if as_numpy:
-            out = self._d2h(out)
+        # host -> device (pinned staging so the copies are asynchronous DMA), then two packing kernels of the library
+        with torch.cuda.device(dev):
+            kp_dev = self._h2d('kp', kp)
+            poses_dev = self._h2d('poses', init_poses)
+            betas_dev = self._h2d('betas', init_betas)
+            cams = self._h2d('cams', torch.from_numpy(pack_cameras(c2ws, Ks)))
+            # init: body pose / betas / global orient from the network, transl 0, scale 1, rest 0 (smplify.py:103-128)
+            sess.load_inputs(kp_dev, cams, poses_dev, betas_dev)
+            sess.run()
+            out = sess.results()
+            self.last_trace = sess.fb.t.get('trace')
+            self.last_loss_terms = sess.fb.t['loss_terms']
+            if as_numpy:
+                out = self._d2h(out)
         out['faces'] = self.smpl_faces[0]
         return out
 
@@ -126,38 +134,39 @@ class SMPLify(object):
         the single-batch path (frames are independent)."""
         m = self.model
         B = kp.shape[0]
-        cur = torch.cuda.current_stream()
-        cams = self._h2d('cams', torch.from_numpy(pack_cameras(c2ws, Ks)))
-        ready = torch.cuda.Event()
-        ready.record(cur)
-        host, nbytes = {}, 0
-        streams = sess.prio_streams                            # decreasing priority: parts finish in launch order
-        for k, ((lo, hi), part, st) in enumerate(zip(sess.ranges, sess.parts, streams)):
-            with torch.cuda.stream(st):
-                st.wait_event(ready)
-                kp_dev = self._h2d(('kp', k), kp[lo:hi])
-                poses_dev = self._h2d(('poses', k), init_poses[lo:hi])
-                betas_dev = self._h2d(('betas', k), init_betas[lo:hi])
-                part.set_inputs(pack_keypoints(kp_dev, self.use_hand_face), cams)
-                part.run(m.pack_theta(poses_dev[:, :3], poses_dev[:, 3:3 + m.nbody], betas_dev))
-                if as_numpy:
-                    for name, v in part.results().items():
-                        pbuf = self._pinned.get(('out', name))
-                        if pbuf is None or pbuf.shape != (B,) + tuple(v.shape[1:]):
-                            pbuf = torch.empty((B,) + tuple(v.shape[1:]), dtype=v.dtype, pin_memory=True)
-                            self._pinned[('out', name)] = pbuf
-                        host[name] = pbuf
-                        pbuf[lo:hi].copy_(v, non_blocking=True)
-                        nbytes += int(v.numel() * v.element_size())
-        if as_numpy:
-            for st in streams:
-                st.synchronize()
-            self.d2h_bytes = nbytes
-            out = {name: pbuf.squeeze(0).numpy() for name, pbuf in host.items()}
-        else:
-            for st in streams:
-                cur.wait_stream(st)
-            out = sess.results()
+        with torch.cuda.device(self.device):
+            cur = torch.cuda.current_stream()
+            cams = self._h2d('cams', torch.from_numpy(pack_cameras(c2ws, Ks)))
+            ready = torch.cuda.Event()
+            ready.record(cur)
+            host, nbytes = {}, 0
+            streams = sess.prio_streams                            # decreasing priority: parts finish in launch order
+            for k, ((lo, hi), part, st) in enumerate(zip(sess.ranges, sess.parts, streams)):
+                with torch.cuda.stream(st):
+                    st.wait_event(ready)
+                    kp_dev = self._h2d(('kp', k), kp[lo:hi])
+                    poses_dev = self._h2d(('poses', k), init_poses[lo:hi])
+                    betas_dev = self._h2d(('betas', k), init_betas[lo:hi])
+                    part.load_inputs(kp_dev, cams, poses_dev, betas_dev)
+                    part.run()
+                    if as_numpy:
+                        for name, v in part.results().items():
+                            pbuf = self._pinned.get(('out', name))
+                            if pbuf is None or pbuf.shape != (B,) + tuple(v.shape[1:]):
+                                pbuf = torch.empty((B,) + tuple(v.shape[1:]), dtype=v.dtype, pin_memory=True)
+                                self._pinned[('out', name)] = pbuf
+                            host[name] = pbuf
+                            pbuf[lo:hi].copy_(v, non_blocking=True)
+                            nbytes += int(v.numel() * v.element_size())
+            if as_numpy:
+                for st in streams:
+                    st.synchronize()
+                self.d2h_bytes = nbytes
+                out = self._host_results(host, nbytes)
+            else:
+                for st in streams:
+                    cur.wait_stream(st)
+                out = sess.results()
         self.last_trace, self.last_loss_terms = sess.trace, sess.loss_terms
         out['faces'] = self.smpl_faces[0]
         return out
@@ -261,19 +270,25 @@ class SMPLify(object):
                 self._sess = ConcurrentFitSession(self.model, B, Nv, self.num_iters, imsize=imsize, return_vertices=return_vertices,
                                                   dense_every_iter=self.dense_every_iter, n_parts=n_parts,
                                                   min_part=self.concurrent_min_part, lead=self.concurrent_lead,
-                                                  taper=self.concurrent_taper)
+                                                  taper=self.concurrent_taper, graph=self.graph)
             else:
                 self._sess = FitSession(self.model, B, Nv, self.num_iters, imsize=imsize,
                                         return_vertices=return_vertices, dense_every_iter=self.dense_every_iter,
-                                        temporal_weight=self.temporal_weight, halo_exchange=self.halo_exchange)
+                                        temporal_weight=self.temporal_weight, halo_exchange=self.halo_exchange, halo=self.halo,
+                                        graph=self.graph)
             self._sess_key = key
             self._pinned = {}
         return self._sess
 
     def _h2d(self, name, t):
+        """Host tensor -> device.  Page-locked sources (torch pinned tensors, cudaHostRegister'ed numpy arrays) are copied
+        by ONE asynchronous DMA straight from the caller's memory; pageable sources go through a pinned staging buffer
+        (re-used across calls; an event guards the previous DMA out of it)."""
         t = t.contiguous()
         if t.is_cuda:
             return t
+        if t.is_pinned():
+            return t.to(self.device, non_blocking=True)
         p = self._pinned.get(('in', name))
         if p is None or p.shape != t.shape or p.dtype != t.dtype:
             p = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
@@ -288,9 +303,16 @@ class SMPLify(object):
         self._pinned[('ev', name)] = ev
         return d
 
+    def _host_results(self, host, nbytes):
+        """Pinned staging buffers -> the arrays handed to the caller; a batch dimension of 1 is squeezed as the reference's
+        ``cpu()`` does (smplify.py:252-254).  See ``copy_outputs`` in __init__."""
+        copy = self.copy_outputs if self.copy_outputs is not None else nbytes <= (256 << 20)
+        if copy:
+            return {k: np.array(p.squeeze(0).numpy()) for k, p in host.items()}
+        return {k: p.squeeze(0).numpy() for k, p in host.items()}
+
     def _d2h(self, out):
-        """Device results -> numpy via pinned buffers (one async copy each, one sync); a batch
-        dimension of 1 is squeezed as the reference's ``cpu()`` does (smplify.py:252-254)."""
+        """Device results -> numpy via pinned buffers (one async copy each, one sync)."""
         host = {}
         nbytes = 0
         for k, v in out.items():
@@ -304,7 +326,7 @@ class SMPLify(object):
             host[k] = p
         torch.cuda.current_stream().synchronize()
         self.d2h_bytes = nbytes
-        return {k: p.squeeze(0).numpy() for k, p in host.items()}
+        return self._host_results(host, nbytes)
 
     def cpu(self, tensor):
         return tensor.detach().cpu().squeeze(0).numpy()

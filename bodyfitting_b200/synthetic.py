@@ -35,10 +35,8 @@ def _smplx_parents():
 SMPLX_PARENTS = _smplx_parents()
 
 # extra joints picked from vertices, order = face(5), feet(6), left tips(5), right tips(5)
-SMPL_EXTRA_VIDS = [332, 6260, 2800, 4071, 583, 3216, 3226, 3387, 6617, 6624, 6787,
-                   2746, 2319, 2445, 2556, 2673, 6191, 5782, 5905, 6016, 6133]
-SMPLX_EXTRA_VIDS = [9120, 9929, 9448, 616, 6, 5770, 5780, 8846, 8463, 8474, 8635,
-                    5361, 4933, 5058, 5169, 5286, 8079, 7669, 7794, 7905, 8022]
+from .constants import EXTRA_VIDS as _EXTRA_VIDS  # noqa: E402
+SMPL_EXTRA_VIDS, SMPLX_EXTRA_VIDS = _EXTRA_VIDS['smpl'], _EXTRA_VIDS['smplx']
 
 # OpenPose face (70 pts) -> model landmark order (51 inner + 17 contour), smplify/loss.py:20
 FACE_MAPPING = list(range(17, 17 + 51)) + list(range(0, 17))

@@ -40,7 +40,7 @@ extern "C" {
 #define BF_ECUDA    -2   /* a CUDA runtime call / launch failed            */
 #define BF_EARCH    -3   /* device is not sm_100 (no fallback exists)      */
 
-#define BF_ABI_VERSION 14
+#define BF_ABI_VERSION 15
 #define BF_F_WORLD 1   /* forward outputs in world space: (x + transl) * scale * constant_scale */
 #define BF_F_TC    2   /* run the blend-shape contractions on tcgen05 tensor cores (3xTF32) */
 #define BF_F_SKIN_FUSED 4  /* bf_frame_loss_backward skins the frame's live vertices itself from vposed (after bf_blend_forward) */
@@ -142,6 +142,9 @@ typedef struct BfFrames {
     float*       tloss;      /* [B]    its per-frame value */
     const float* halo_prev;  /* [NP] theta of the frame before this shard's first frame (previous rank), NULL at the sequence start */
     const float* halo_next;  /* [NP] theta of the frame after this shard's last frame (next rank), NULL at the sequence end */
+    float*       halo_buf;       /* NVLink halo (bf_halo_*): this rank's own halo buffer, or NULL = host-exchanged rows above */
+    float*       halo_peer_prev; /* the previous rank's halo buffer mapped into this process (NULL on the first rank) */
+    float*       halo_peer_next; /* the next rank's halo buffer (NULL on the last rank) */
     float*       fwd_state;  /* [B,24J] optional: full_pose, R, rest joints, chain rotations saved by the pose forward so the
                                 pose backward does not recompute them */
     float*       gmm_ws;     /* [B, n_gmm*72 + 160] workspace of the tensor-core GMM prior (y of every component | [pose|1] hi | lo), or NULL */
@@ -149,7 +152,8 @@ typedef struct BfFrames {
     int64_t      ws_floats;
     double lr_ts, lr, beta1, beta2, eps;   /* Adam hyper-parameters (python floats in the reference: smplify.py:167-174) */
     int32_t B, Nv, ld_v, iter;
-    int32_t flags, _pad0;      /* BF_F_WORLD: skin/joints forward write (x + transl) * scale * constant_scale (smplify.py:189-190) */
+    int32_t flags;             /* BF_F_WORLD: skin/joints forward write (x + transl) * scale * constant_scale (smplify.py:189-190) */
+    int32_t halo_iters;        /* NVLink halo: iterations of the run; iteration `iter` publishes its updated boundary rows iff iter + 1 < halo_iters */
     float imsize, constant_scale, sigma, w_pose, w_angle, w_shape;
     float w_temporal, _padf;   /* weight of the temporal term (0 = off; not part of the reference) */
 } BfFrames;
@@ -202,6 +206,28 @@ int bf_fit_step(const BfModel* m, const BfFrames* f, void* stream);
  * materialises all vertices into f_full->verts (the reference returns the vertices of the
  * last forward pass, smplify/smplify.py:217) */
 int bf_fit_run(const BfModel* m, const BfFrames* f, int n_iters, void* stream);
+
+
+/* ---- input packing (so that no host-framework arithmetic sits on the path) ---------------------------------
+ * detections [B,Nv,K,3] (x, y, conf) in the caller's layout -> kp [B,K,Nv,3] (x, y, effective weight): conf^2 for the body,
+ * the group's sum of conf^2 for SMPL-X hands / face (smplify/loss.py:134 with :168,:173,:179) */
+int bf_pack_keypoints(const float* kp_raw, float* kp_packed, int B, int Nv, int K, int hand_face, void* stream);
+/* network output -> initial theta rows (smplify/smplify.py:103-128): transl 0, scale 1, global_orient / body_pose from
+ * poses[b, 0:3+nbody] (row stride ld_poses), betas[b, 0:10], eye / hand parameters 0 */
+int bf_init_theta(const BfModel* m, const float* poses, int ld_poses, const float* betas, float* theta, int B, void* stream);
+
+/* ---- NVLink halo of the temporal term (BASELINE config 4; the reference has no multi-GPU path) -----------------
+ * One buffer per rank (bf_halo_bytes() bytes of cudaMalloc'ed memory, exported as a CUDA IPC handle of
+ * bf_halo_handle_bytes() bytes); neighbours map it with bf_halo_open and the optimiser kernel stores its boundary rows
+ * straight into it.  BfFrames.halo_buf / halo_peer_prev / halo_peer_next / halo_iters switch it on; bf_halo_begin starts
+ * a run (publishes the initial boundary rows).  The only calls of this library that allocate / synchronise. */
+int bf_halo_bytes(void);
+int bf_halo_handle_bytes(void);
+int bf_halo_alloc(void** buf, void* ipc_handle_out);
+int bf_halo_open(const void* ipc_handle, void** peer_buf);
+int bf_halo_close(void* peer_buf);
+int bf_halo_free(void* buf);
+int bf_halo_begin(const BfModel* m, const BfFrames* f, int n_iters, void* stream);
 
 #ifdef __cplusplus
 }

@@ -243,27 +243,32 @@ def batched_objective(w2cs, Ks, kp, model_joints, poses, betas, prior, imsize, u
 
 class FitPort(object):
     def __init__(self, smpl_type, model_data, gmm, J_regressor_extra=None, dtype=torch.float32,
-                 constant_scale=C.CONSTANT_SCALE_NO_SCAN):
+                 constant_scale=C.CONSTANT_SCALE_NO_SCAN, device='cpu'):
+        """``device='cuda'``: the same eager op sequence on the GPU (the reference's default device, smplify.py:29) --
+        bench.py's second, non-target baseline; parity is always checked with the CPU path."""
         self.smpl_type = smpl_type
         self.use_hand_face = smpl_type == 'smplx'
         self.dtype = dtype
-        self.prior = GMMPrior(gmm, dtype=dtype)
-        self.model = build_model(smpl_type, model_data, J_regressor_extra, dtype=dtype)
+        self.device = torch.device(device)
+        self.prior = GMMPrior(gmm, dtype=dtype).to(self.device)
+        self.model = build_model(smpl_type, model_data, J_regressor_extra, dtype=dtype).to(self.device)
+        if hasattr(self.model, 'joint_map'):
+            self.model.joint_map = self.model.joint_map.to(self.device)
         self.constant_scale = constant_scale
         self.faces = np.asarray(self.model.faces).astype(np.int32)
 
     # -- shared ---------------------------------------------------------------
     def _init_params(self, init_betas, init_poses, B):
-        dt = self.dtype
-        init_poses = torch.as_tensor(init_poses, dtype=dt).reshape(B, -1)
+        dt, dev = self.dtype, self.device
+        init_poses = torch.as_tensor(init_poses, dtype=dt).reshape(B, -1).to(dev)
         nb = 69 if self.smpl_type == 'smpl' else 63
         p = dict(body_pose=init_poses[:, 3:3 + nb].detach().clone(),
-                 betas=torch.as_tensor(init_betas, dtype=dt).reshape(B, -1).detach().clone(),
+                 betas=torch.as_tensor(init_betas, dtype=dt).reshape(B, -1).to(dev).detach().clone(),
                  global_orient=init_poses[:, :3].detach().clone(),
-                 global_transl=torch.zeros(B, 3, dtype=dt), body_scale=torch.ones(B, 1, dtype=dt),
-                 jaw_pose=torch.zeros(B, 1, 3, dtype=dt), leye_pose=torch.zeros(B, 1, 3, dtype=dt),
-                 reye_pose=torch.zeros(B, 1, 3, dtype=dt), left_hand_pose=torch.zeros(B, 6, dtype=dt),
-                 right_hand_pose=torch.zeros(B, 6, dtype=dt))
+                 global_transl=torch.zeros(B, 3, dtype=dt, device=dev), body_scale=torch.ones(B, 1, dtype=dt, device=dev),
+                 jaw_pose=torch.zeros(B, 1, 3, dtype=dt, device=dev), leye_pose=torch.zeros(B, 1, 3, dtype=dt, device=dev),
+                 reye_pose=torch.zeros(B, 1, 3, dtype=dt, device=dev), left_hand_pose=torch.zeros(B, 6, dtype=dt, device=dev),
+                 right_hand_pose=torch.zeros(B, 6, dtype=dt, device=dev))
         for v in p.values():
             v.requires_grad_(True)
         return p
@@ -300,7 +305,7 @@ class FitPort(object):
     def fit_frame(self, init_betas, init_poses, c2ws, Ks, views, num_iters=100, imsize=512, masks=None, mask_frames=None):
         """``masks`` [Nm,H,W] uint8 + ``mask_frames``: also the silhouette term (use_mask=True, smplify.py:137-144,196-199)."""
         p = self._init_params(init_betas, init_poses, 1)
-        w2cs = torch.inverse(torch.from_numpy(np.array(c2ws)).to(self.dtype))
+        w2cs = torch.inverse(torch.from_numpy(np.array(c2ws)).to(self.dtype).to(self.device))
         Ks = [np.asarray(k) for k in Ks]
         opt = self._optimizer(p)
         trace = []

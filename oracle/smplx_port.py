@@ -27,6 +27,13 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+# smplx.vertex_ids (hard-coded in the package; the official model files do not carry them) -- restated independently of the
+# product's copy in bodyfitting_b200/constants.py; tests/test_host.py checks that the two agree
+_EXTRA_VIDS = {
+    'smpl': [332, 6260, 2800, 4071, 583, 3216, 3226, 3387, 6617, 6624, 6787, 2746, 2319, 2445, 2556, 2673, 6191, 5782, 5905, 6016, 6133],
+    'smplx': [9120, 9929, 9448, 616, 6, 5770, 5780, 8846, 8463, 8474, 8635, 5361, 4933, 5058, 5169, 5286, 8079, 7669, 7794, 7905, 8022],
+}
+
 
 def batch_rodrigues(rot_vecs):
     """[N,3] axis-angle -> [N,3,3]; smplx.lbs.batch_rodrigues (epsilon added to the
@@ -159,7 +166,7 @@ class SMPLLayer(nn.Module):
         self.register_buffer('J_regressor', torch.tensor(np.asarray(data['J_regressor']), dtype=dtype))
         self.register_buffer('parents', _parents_from(data))
         self.register_buffer('lbs_weights', torch.tensor(np.asarray(data['weights']), dtype=dtype))
-        self.register_buffer('extra_joints_idxs', torch.tensor(np.asarray(data['extra_vids']), dtype=torch.long))
+        self.register_buffer('extra_joints_idxs', torch.tensor(np.asarray(data['extra_vids'] if 'extra_vids' in data else _EXTRA_VIDS[getattr(self, 'MODEL_TYPE', 'smpl')]), dtype=torch.long))
         self.joint_mapper = joint_mapper
         if create_transl:
             self.register_parameter('transl', nn.Parameter(torch.zeros([batch_size, 3], dtype=dtype)))
@@ -191,6 +198,7 @@ class SMPLXLayer(SMPLLayer):
     + 21 picked + 51 static + 17 dynamic landmarks = 144 joints, then ``joint_mapper``."""
     NUM_BODY_JOINTS = 21
     NECK_IDX = 12
+    MODEL_TYPE = 'smplx'
 
     def __init__(self, data, num_betas=10, num_expression_coeffs=10, num_pca_comps=6, dtype=torch.float32,
                  joint_mapper=None, use_face_contour=True, create_transl=False, batch_size=1):
@@ -198,7 +206,8 @@ class SMPLXLayer(SMPLLayer):
         super().__init__(data, num_betas=num_betas, dtype=dtype, joint_mapper=joint_mapper,
                          create_transl=create_transl, batch_size=batch_size)
         sd = np.asarray(data['shapedirs'])
-        self.register_buffer('expr_dirs', torch.tensor(sd[:, :, num_betas:num_betas + num_expression_coeffs], dtype=dtype))
+        e0 = 300 if sd.shape[-1] >= 300 + num_expression_coeffs else num_betas     # official files: 300 shape + 100 expression dirs
+        self.register_buffer('expr_dirs', torch.tensor(sd[:, :, e0:e0 + num_expression_coeffs], dtype=dtype))
         self.register_buffer('left_hand_components', torch.tensor(np.asarray(data['hands_componentsl'])[:num_pca_comps], dtype=dtype))
         self.register_buffer('right_hand_components', torch.tensor(np.asarray(data['hands_componentsr'])[:num_pca_comps], dtype=dtype))
         pose_mean = np.concatenate([np.zeros(3), np.zeros(63), np.zeros(3), np.zeros(3), np.zeros(3),
