@@ -124,10 +124,17 @@ def lib():
     ops.update({
         'bf_grid_count': [pg, fp, vp], 'bf_grid_fill': [pg, fp, vp],
         'bf_grid_nearest': [pg, fp, i32, fp, fp, fp, vp],
+        'bf_grid_barycentric': [pg, fp, fp, i32, fp, vp], 'bf_grid_nearest_backward': [pg, fp, fp, i32, fp, vp],
         'bf_grid_inside': [pg, fp, i32, fp, vp], 'bf_grid_intersects_any': [pg, fp, fp, i32, fp, vp],
         'bf_smpld_step': [pg, ps, vp], 'bf_smpld_run': [pg, ps, i32, vp],
         'bf_pc_loss': [pg, pm, pf, fl, fl, fp, fp, fp, fp, vp],
         'bf_mask_loss': [pm, pf, C.POINTER(BfMask), fl, vp],
+        'bf_op_pc_loss': [fp, fp, i64, fp, fp, vp],
+        'bf_op_normal_loss': [fp, fp, fp, i32, fp, fp, vp],
+        'bf_op_laplacian': [fp, fp, fp, fp, i32, i32, fp, fp, vp],
+        'bf_op_vertex_normals': [fp, fp, fp, fp, i32, i32, fp, fp, fp, fp, vp],
+        'bf_op_vertex_normals_backward': [fp, fp, fp, fp, i32, i32, fp, fp, fp, fp, fp, fp, fp, fp, vp],
+        'bf_op_mask_loss': [fp, i32, i32, C.POINTER(BfMask), fp, fp, fp, vp],
     })
     for name, at in ops.items():
         fn = getattr(L, name)
@@ -144,10 +151,11 @@ EXPORTED = ['bf_abi_version', 'bf_sizeof', 'bf_last_error', 'bf_check_device', '
             'bf_halo_close', 'bf_halo_free', 'bf_halo_begin']
 
 
-EXPORTED_GRID = ['bf_grid_count', 'bf_grid_fill', 'bf_grid_nearest', 'bf_grid_inside', 'bf_grid_intersects_any', 'bf_smpld_step', 'bf_smpld_run', 'bf_pc_loss']
+EXPORTED_GRID = ['bf_grid_count', 'bf_grid_fill', 'bf_grid_nearest', 'bf_grid_barycentric', 'bf_grid_nearest_backward', 'bf_grid_inside', 'bf_grid_intersects_any', 'bf_smpld_step', 'bf_smpld_run', 'bf_pc_loss']
 EXPORTED_MASK = ['bf_mask_loss']
 EXPORTED_OPS = ['bf_op_project', 'bf_op_project_backward', 'bf_op_gmof', 'bf_op_gmof_backward', 'bf_op_reprojection',
-                'bf_op_keypoints_world', 'bf_op_angle_prior', 'bf_op_gmm_pose']
+                'bf_op_keypoints_world', 'bf_op_angle_prior', 'bf_op_gmm_pose', 'bf_op_pc_loss', 'bf_op_normal_loss',
+                'bf_op_laplacian', 'bf_op_vertex_normals', 'bf_op_vertex_normals_backward', 'bf_op_mask_loss']
 
 
 def check(rc, what=''):

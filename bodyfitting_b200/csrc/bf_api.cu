@@ -618,6 +618,22 @@ int bf_grid_nearest(const BfGrid* g, const float* points, int Q, float* near_pts
     return BF_OK;
 }
 
+int bf_grid_barycentric(const BfGrid* g, const float* points, const int32_t* near_faces, int Q, float* coeff, void* stream) {
+    BF_NVTX();
+    BF_REQUIRE(g && g->verts && g->faces && points && near_faces && coeff && Q > 0, "bad arguments");
+    k_grid_bary<<<(Q + 255) / 256, 256, 0, (cudaStream_t)stream>>>(*g, points, near_faces, Q, coeff);
+    BF_LAUNCH_CHECK();
+    return BF_OK;
+}
+
+int bf_grid_nearest_backward(const BfGrid* g, const float* points, const int32_t* near_faces, int Q, float* grad, void* stream) {
+    BF_NVTX();
+    BF_REQUIRE(g && g->verts && g->faces && points && near_faces && grad && Q > 0, "bad arguments");
+    k_grid_nearest_bwd<<<(Q + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*g, points, near_faces, Q, grad);
+    BF_LAUNCH_CHECK();
+    return BF_OK;
+}
+
 int bf_grid_inside(const BfGrid* g, const float* points, int Q, float* signs, void* stream) {
     BF_NVTX();
     int rc = check_grid(g); if (rc) return rc;
@@ -783,6 +799,90 @@ int bf_pc_loss(const BfGrid* g, const BfModel* m, const BfFrames* f, float scale
     BF_LAUNCH_CHECK();
     k_pc_world_bwd<<<f->B, 256, 0, s>>>(f->verts, Pw, near_pts, f->theta, m->NP, V, f->ld_v, f->constant_scale, scale, weight,
                                         f->loss, pc_loss, f->dverts, f->grad);
+    BF_LAUNCH_CHECK();
+    return BF_OK;
+}
+
+// ---- scan / normal / silhouette terms as stand-alone operators (include/bodyfit_b200_ops.h) ---------------------------
+int bf_op_pc_loss(const float* points, const float* closest, int64_t n, float* out, float* dpoints, void* stream) {
+    BF_NVTX();
+    BF_REQUIRE(points && closest && out && dpoints && n > 0 && n < (1LL << 31), "bad arguments");
+    k_op_pc_loss<<<1, 1024, 0, (cudaStream_t)stream>>>(points, closest, (int)n, out, dpoints);
+    BF_LAUNCH_CHECK();
+    return BF_OK;
+}
+int bf_op_normal_loss(const int32_t* near_faces, const float* face_norm, const float* point_norm, int V, float* out,
+                      float* dpoint_norm, void* stream) {
+    BF_NVTX();
+    BF_REQUIRE(near_faces && face_norm && point_norm && out && dpoint_norm && V > 0, "bad arguments");
+    k_op_normal_loss<<<1, 1024, 0, (cudaStream_t)stream>>>(near_faces, face_norm, point_norm, V, out, dpoint_norm);
+    BF_LAUNCH_CHECK();
+    return BF_OK;
+}
+int bf_op_laplacian(const float* norms, const int32_t* faces, const int32_t* vf_ptr, const int32_t* vf_face, int V, int F,
+                    float* out, float* dnorms, void* stream) {
+    BF_NVTX();
+    BF_REQUIRE(norms && faces && vf_ptr && vf_face && out && dnorms && V > 0 && F > 0, "bad arguments");
+    k_op_laplacian_value<<<1, 1024, 0, (cudaStream_t)stream>>>(norms, faces, F, out);
+    BF_LAUNCH_CHECK();
+    k_op_laplacian_grad<<<(V + 255) / 256, 256, 0, (cudaStream_t)stream>>>(norms, faces, vf_ptr, vf_face, V, F, dnorms);
+    BF_LAUNCH_CHECK();
+    return BF_OK;
+}
+int bf_op_vertex_normals(const float* verts, const int32_t* faces, const int32_t* vf_ptr, const int32_t* vf_face, int V, int F,
+                         float* nhat, float* nlen, float* normals, float* Nlen, void* stream) {
+    BF_NVTX();
+    BF_REQUIRE(verts && faces && vf_ptr && vf_face && nhat && nlen && normals && Nlen && V > 0 && F > 0, "bad arguments");
+    k_face_normals<<<(F + 255) / 256, 256, 0, (cudaStream_t)stream>>>(verts, faces, F, nhat, nlen);
+    BF_LAUNCH_CHECK();
+    k_vertex_normals<<<(V + 255) / 256, 256, 0, (cudaStream_t)stream>>>(nhat, vf_ptr, vf_face, V, normals, Nlen);
+    BF_LAUNCH_CHECK();
+    return BF_OK;
+}
+int bf_op_vertex_normals_backward(const float* verts, const int32_t* faces, const int32_t* vf_ptr, const int32_t* vf_face, int V,
+                                  int F, const float* nhat, const float* nlen, const float* normals, const float* Nlen,
+                                  const float* dnormals, float* dm_scratch, float* dcorner_scratch, float* dverts, void* stream) {
+    BF_NVTX();
+    BF_REQUIRE(verts && faces && vf_ptr && vf_face && nhat && nlen && normals && Nlen && dnormals && dm_scratch &&
+               dcorner_scratch && dverts && V > 0 && F > 0, "bad arguments");
+    cudaStream_t s = (cudaStream_t)stream;
+    k_op_vnormal_bwd<<<(V + 255) / 256, 256, 0, s>>>(dnormals, normals, Nlen, V, dm_scratch);
+    BF_LAUNCH_CHECK();
+    k_smpld_dface<<<(F + 255) / 256, 256, 0, s>>>(verts, faces, nhat, nlen, dm_scratch, F, dcorner_scratch);
+    BF_LAUNCH_CHECK();
+    k_op_corner_gather<<<(V + 255) / 256, 256, 0, s>>>(dcorner_scratch, faces, vf_ptr, vf_face, V, dverts);
+    BF_LAUNCH_CHECK();
+    return BF_OK;
+}
+int bf_op_mask_loss(const float* verts_world, int B, int V, const BfMask* k, float* scratch, float* loss, float* dverts,
+                    void* stream) {
+    BF_NVTX();
+    BF_REQUIRE(verts_world && k && scratch && loss && dverts && B > 0 && V > 0, "bad arguments");
+    BF_REQUIRE(k->masks && k->cams && k->contour && k->cptr && k->cown && k->uv && k->near_q && k->cdist && k->cw && k->dPw && k->part,
+               "mask buffers missing");
+    BF_REQUIRE(k->Nm > 0 && k->H > 0 && k->W > 0 && k->stride > 0 && k->Nq == (V + k->stride - 1) / k->stride && k->total >= 0 &&
+               k->imsize > 0.f, "bad mask geometry");
+    cudaStream_t s = (cudaStream_t)stream;
+    // world-space vertices in, world-space gradient out: identity (transl 0, scale 1, constant_scale 1) frames of NP = 4
+    BfFrames f;
+    memset(&f, 0, sizeof(f));
+    f.theta = scratch; f.grad = scratch + 4 * (size_t)B;
+    f.verts = const_cast<float*>(verts_world); f.dverts = dverts; f.loss = loss;
+    f.B = B; f.ld_v = 3 * V; f.constant_scale = 1.0f;
+    k_op_identity_theta<<<(B + 127) / 128, 128, 0, s>>>(scratch, B);
+    BF_LAUNCH_CHECK();
+    if (cudaMemsetAsync(f.grad, 0, sizeof(float) * 4 * (size_t)B, s) != cudaSuccess || cudaMemsetAsync(loss, 0, sizeof(float) * B, s) != cudaSuccess ||
+        cudaMemsetAsync(dverts, 0, sizeof(float) * 3 * (size_t)V * B, s) != cudaSuccess) { bf_set_error("memset failed"); return BF_ECUDA; }
+    const size_t n = (size_t)B * k->Nm * k->Nq;
+    k_mask_project<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(f, *k, 4);
+    BF_LAUNCH_CHECK();
+    if (k->total > 0) {
+        k_mask_nearest<<<(k->total + 7) / 8, 256, 0, s>>>(*k, k->total);
+        BF_LAUNCH_CHECK();
+    }
+    k_mask_vertex<<<(unsigned)(((size_t)B * k->Nq + 127) / 128), 128, 0, s>>>(f, *k, 4);
+    BF_LAUNCH_CHECK();
+    k_mask_finish<<<B, 256, 0, s>>>(f, *k, 4, 1.0f);
     BF_LAUNCH_CHECK();
     return BF_OK;
 }

@@ -549,10 +549,16 @@ static int bf_blend_backward_tc(const BfModel* m, const BfVSet* vs, const BfFram
         static int st_env = -1;                           // BODYFIT_BWD_STAGES=2|4: experiments
         if (st_env < 0) { const char* e = getenv("BODYFIT_BWD_STAGES"); st_env = e ? atoi(e) : 0; }
         if (st_env == 2) NS = 2;                        // measured: slower in the full fit at either width
+        // narrow tiles (small batches, see above): a CTA's K loop is bound by the round trip of a stage (commit -> TMA ->
+        // MMA, ~1.8 us; measured 0.45 us per chunk with 4 stages whatever the tile width), so the freed shared memory buys a
+        // deeper pipeline: 8 stages of 16 + 2 x 4 KB
+        else if (BN <= 64 && TC_BK == 16 && st_env != 4) NS = 8;
     }
     const size_t smem = 1024 + NS * (2 * TC_BM * TC_ROWB + 2 * (size_t)BN * TC_ROWB) + 64;
     static size_t attr[2][BF_MAXDEV] = {{0}};
+    static size_t attr8[BF_MAXDEV] = {0};
     if ((rc = NS == 2 ? bf_ensure_smem(k_blend_bwd_tc<2>, smem, attr[1], "k_blend_bwd_tc<2>")
+            : NS == 8 ? bf_ensure_smem(k_blend_bwd_tc<8>, smem, attr8, "k_blend_bwd_tc<8>")
                       : bf_ensure_smem(k_blend_bwd_tc<TC_STAGES>, smem, attr[0], "k_blend_bwd_tc"))) return rc;
     const int num_k = vs->ldn / TC_BK;
     const size_t stride = (size_t)f->B * m->Kp;
@@ -580,6 +586,7 @@ static int bf_blend_backward_tc(const BfModel* m, const BfVSet* vs, const BfFram
     }
     const dim3 grid(m->Kp / BN, (f->B + TC_BM - 1) / TC_BM, S);
     if (NS == 2) k_blend_bwd_tc<2><<<grid, 192, smem, s>>>(a_hi, a_lo, b_hi, b_lo, BN, num_k, cps, m->Kp, S > 1 ? f->ws : f->dpf, stride, f->B);
+    else if (NS == 8) k_blend_bwd_tc<8><<<grid, 192, smem, s>>>(a_hi, a_lo, b_hi, b_lo, BN, num_k, cps, m->Kp, S > 1 ? f->ws : f->dpf, stride, f->B);
     else k_blend_bwd_tc<TC_STAGES><<<grid, 192, smem, s>>>(a_hi, a_lo, b_hi, b_lo, BN, num_k, cps, m->Kp, S > 1 ? f->ws : f->dpf, stride, f->B);
     BF_LAUNCH_CHECK();
     if (S > 1) {

@@ -93,50 +93,119 @@ __global__ void k_grid_sort(const int32_t* __restrict__ cell_start, int32_t* __r
     }
 }
 
-// exact closest point on triangle (a,b,c) to p (Voronoi regions); returns squared distance, writes the point
-__device__ __forceinline__ float closest_on_triangle(const float* p, const float* a, const float* b, const float* c, float* q) {
-    const float ab[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]};
-    const float ac[3] = {c[0] - a[0], c[1] - a[1], c[2] - a[2]};
-    const float ap[3] = {p[0] - a[0], p[1] - a[1], p[2] - a[2]};
-    const float d1 = ab[0] * ap[0] + ab[1] * ap[1] + ab[2] * ap[2];
-    const float d2 = ac[0] * ap[0] + ac[1] * ap[1] + ac[2] * ap[2];
-    float u = 0.f, v = 0.f;                                   // q = a + u ab + v ac
-    if (d1 <= 0.f && d2 <= 0.f) { u = 0.f; v = 0.f; }
-    else {
-        const float bp[3] = {p[0] - b[0], p[1] - b[1], p[2] - b[2]};
-        const float d3 = ab[0] * bp[0] + ab[1] * bp[1] + ab[2] * bp[2];
-        const float d4 = ac[0] * bp[0] + ac[1] * bp[1] + ac[2] * bp[2];
-        if (d3 >= 0.f && d4 <= d3) { u = 1.f; v = 0.f; }
-        else {
-            const float vc = d1 * d4 - d3 * d2;
-            if (vc <= 0.f && d1 >= 0.f && d3 <= 0.f) { u = d1 / (d1 - d3); v = 0.f; }
-            else {
-                const float cp[3] = {p[0] - c[0], p[1] - c[1], p[2] - c[2]};
-                const float d5 = ab[0] * cp[0] + ab[1] * cp[1] + ab[2] * cp[2];
-                const float d6 = ac[0] * cp[0] + ac[1] * cp[1] + ac[2] * cp[2];
-                if (d6 >= 0.f && d5 <= d6) { u = 0.f; v = 1.f; }
-                else {
-                    const float vb = d5 * d2 - d1 * d6;
-                    if (vb <= 0.f && d2 >= 0.f && d6 <= 0.f) { u = 0.f; v = d2 / (d2 - d6); }
-                    else {
-                        const float va = d3 * d6 - d5 * d4;
-                        if (va <= 0.f && (d4 - d3) >= 0.f && (d5 - d6) >= 0.f) {
-                            const float w = (d4 - d3) / ((d4 - d3) + (d5 - d6));
-                            u = 1.f - w; v = w;
-                        } else {
-                            const float den = 1.0f / (va + vb + vc);
-                            u = vb * den; v = vc * den;
-                        }
-                    }
-                }
-            }
-        }
+// exact closest point on triangle (a,b,c) to p (Voronoi regions): q = a + u (b - a) + v (c - a), i.e. barycentric
+// coefficients (1 - u - v, u, v).  T = float, or a forward-mode dual number (Dual9 below) carrying d/d(a, b, c).
+template <typename T>
+__device__ __forceinline__ void closest_uv(const float* p, const T* a, const T* b, const T* c, T& u, T& v) {
+    const T ab[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]};
+    const T ac[3] = {c[0] - a[0], c[1] - a[1], c[2] - a[2]};
+    const T ap[3] = {p[0] - a[0], p[1] - a[1], p[2] - a[2]};
+    const T d1 = ab[0] * ap[0] + ab[1] * ap[1] + ab[2] * ap[2];
+    const T d2 = ac[0] * ap[0] + ac[1] * ap[1] + ac[2] * ap[2];
+    const T zero = T(0.f), one = T(1.f);
+    u = zero; v = zero;
+    if (d1 <= 0.f && d2 <= 0.f) return;
+    const T bp[3] = {p[0] - b[0], p[1] - b[1], p[2] - b[2]};
+    const T d3 = ab[0] * bp[0] + ab[1] * bp[1] + ab[2] * bp[2];
+    const T d4 = ac[0] * bp[0] + ac[1] * bp[1] + ac[2] * bp[2];
+    if (d3 >= 0.f && d4 <= d3) { u = one; return; }
+    const T vc = d1 * d4 - d3 * d2;
+    if (vc <= 0.f && d1 >= 0.f && d3 <= 0.f) { u = d1 / (d1 - d3); return; }
+    const T cp[3] = {p[0] - c[0], p[1] - c[1], p[2] - c[2]};
+    const T d5 = ab[0] * cp[0] + ab[1] * cp[1] + ab[2] * cp[2];
+    const T d6 = ac[0] * cp[0] + ac[1] * cp[1] + ac[2] * cp[2];
+    if (d6 >= 0.f && d5 <= d6) { v = one; return; }
+    const T vb = d5 * d2 - d1 * d6;
+    if (vb <= 0.f && d2 >= 0.f && d6 <= 0.f) { v = d2 / (d2 - d6); return; }
+    const T va = d3 * d6 - d5 * d4;
+    if (va <= 0.f && (d4 - d3) >= 0.f && (d5 - d6) >= 0.f) {
+        const T w = (d4 - d3) / ((d4 - d3) + (d5 - d6));
+        u = one - w; v = w;
+        return;
     }
-    q[0] = a[0] + u * ab[0] + v * ac[0];
-    q[1] = a[1] + u * ab[1] + v * ac[1];
-    q[2] = a[2] + u * ab[2] + v * ac[2];
+    const T den = one / (va + vb + vc);
+    u = vb * den; v = vc * den;
+}
+
+// returns squared distance, writes the point
+__device__ __forceinline__ float closest_on_triangle(const float* p, const float* a, const float* b, const float* c, float* q) {
+    float u, v;
+    closest_uv<float>(p, a, b, c, u, v);
+    q[0] = a[0] + u * (b[0] - a[0]) + v * (c[0] - a[0]);
+    q[1] = a[1] + u * (b[1] - a[1]) + v * (c[1] - a[1]);
+    q[2] = a[2] + u * (b[2] - a[2]) + v * (c[2] - a[2]);
     const float dx = p[0] - q[0], dy = p[1] - q[1], dz = p[2] - q[2];
     return dx * dx + dy * dy + dz * dz;
+}
+
+// forward-mode dual number: value + the 9 partial derivatives w.r.t. the triangle's vertex coordinates (a, b, c)
+struct Dual9 {
+    float x, d[9];
+    __device__ Dual9() {}
+    __device__ explicit Dual9(float v) : x(v) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) d[i] = 0.f;
+    }
+};
+__device__ __forceinline__ Dual9 operator+(const Dual9& a, const Dual9& b) { Dual9 r; r.x = a.x + b.x; for (int i = 0; i < 9; ++i) r.d[i] = a.d[i] + b.d[i]; return r; }
+__device__ __forceinline__ Dual9 operator-(const Dual9& a, const Dual9& b) { Dual9 r; r.x = a.x - b.x; for (int i = 0; i < 9; ++i) r.d[i] = a.d[i] - b.d[i]; return r; }
+__device__ __forceinline__ Dual9 operator-(float a, const Dual9& b) { Dual9 r; r.x = a - b.x; for (int i = 0; i < 9; ++i) r.d[i] = -b.d[i]; return r; }
+__device__ __forceinline__ Dual9 operator*(const Dual9& a, const Dual9& b) { Dual9 r; r.x = a.x * b.x; for (int i = 0; i < 9; ++i) r.d[i] = a.d[i] * b.x + a.x * b.d[i]; return r; }
+__device__ __forceinline__ Dual9 operator/(const Dual9& a, const Dual9& b) {
+    Dual9 r; const float ib = 1.0f / b.x; r.x = a.x * ib;
+    for (int i = 0; i < 9; ++i) r.d[i] = (a.d[i] - r.x * b.d[i]) * ib;
+    return r;
+}
+__device__ __forceinline__ bool operator<=(const Dual9& a, float b) { return a.x <= b; }
+__device__ __forceinline__ bool operator>=(const Dual9& a, float b) { return a.x >= b; }
+__device__ __forceinline__ bool operator<=(const Dual9& a, const Dual9& b) { return a.x <= b.x; }
+
+// barycentric coefficients of the closest point on the triangle the search selected (the reference's `coeff` output,
+// mesh_grid_kernel.cu:405-410,:12-109): near_pt = c0 v0 + c1 v1 + c2 v2
+__global__ void k_grid_bary(BfGrid g, const float* __restrict__ points, const int32_t* __restrict__ near_faces, int Q,
+                            float* __restrict__ coeff) {
+    const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= Q) return;
+    const int f = near_faces[qi];
+    float u = 0.f, v = 0.f;
+    if (f >= 0) {
+        const int32_t* tri = g.faces + 3 * f;
+        const float p[3] = {points[3 * qi], points[3 * qi + 1], points[3 * qi + 2]};
+        closest_uv<float>(p, g.verts + 3 * __ldg(tri), g.verts + 3 * __ldg(tri + 1), g.verts + 3 * __ldg(tri + 2), u, v);
+    }
+    coeff[3 * qi] = f >= 0 ? 1.0f - u - v : 0.f; coeff[3 * qi + 1] = u; coeff[3 * qi + 2] = v;
+}
+
+// grad[q][i][j][k] = d near_pt[q][j] / d verts[tri[i]][k] for the face the search selected (piecewise exact: the derivative of
+// the closest-point map inside the Voronoi region the query falls in).  The reference's kernel of this name is unfinished
+// (mesh_grid_kernel.cu:354-382: "TODO: calculate inverse matrix", every thread writes the first 27 entries) and never called.
+__global__ void k_grid_nearest_bwd(BfGrid g, const float* __restrict__ points, const int32_t* __restrict__ near_faces, int Q,
+                                   float* __restrict__ grad) {
+    const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= Q) return;
+    float* o = grad + (size_t)qi * 27;
+    const int f = near_faces[qi];
+    if (f < 0) { for (int e = 0; e < 27; ++e) o[e] = 0.f; return; }
+    const int32_t* tri = g.faces + 3 * f;
+    const float p[3] = {points[3 * qi], points[3 * qi + 1], points[3 * qi + 2]};
+    Dual9 vtx[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            vtx[i * 3 + k] = Dual9(g.verts[3 * __ldg(tri + i) + k]);
+            vtx[i * 3 + k].d[i * 3 + k] = 1.0f;
+        }
+    Dual9 u, v;
+    closest_uv<Dual9>(p, vtx, vtx + 3, vtx + 6, u, v);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const Dual9 q = vtx[j] + u * (vtx[3 + j] - vtx[j]) + v * (vtx[6 + j] - vtx[j]);
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) o[(i * 3 + j) * 3 + k] = q.d[i * 3 + k];
+    }
 }
 
 // one warp per query point: shells of cells of growing L-inf radius around the query's cell

@@ -144,3 +144,125 @@ __global__ void k_angle_prior(const float* __restrict__ pose, int B, int D, floa
     out[i] = e * e;
     dout_dpose[i] = 2.0f * e * e * sg;
 }
+
+
+// ---- scan / normal terms as stand-alone operators (smplify/loss.py:233-242,260-288, utils/io_utils.py:410-428) --------
+// Each forward also produces the gradient w.r.t. its differentiable input (the objective is a scalar), like the operators
+// above; single-block fixed-order reductions (deterministic).
+
+// out[0] = |P - C|_F over n floats (loss.py:240-241: one Frobenius norm, the mean that follows is of a scalar);
+// dP = (P - C) / out[0]
+__global__ void __launch_bounds__(1024) k_op_pc_loss(const float* __restrict__ P, const float* __restrict__ C, int n,
+                                                      float* __restrict__ out, float* __restrict__ dP) {
+    __shared__ float red[32];
+    __shared__ float nrm;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    float acc = 0.f;
+    for (int i = t; i < n; i += 1024) { const float d = P[i] - C[i]; acc += d * d; }
+    acc = warp_sum(acc);
+    if (lane == 0) red[warp] = acc;
+    __syncthreads();
+    if (t == 0) { float s = 0.f; for (int w = 0; w < 32; ++w) s += red[w]; nrm = sqrtf(s); out[0] = nrm; }
+    __syncthreads();
+    const float inv = nrm > 0.f ? 1.0f / nrm : 0.f;
+    for (int i = t; i < n; i += 1024) dP[i] = (P[i] - C[i]) * inv;
+}
+
+// out[0] = mean_v (1 - <fn[near_faces[v]], N_v>) (loss.py:267-269); dN_v = -fn[near_faces[v]] / V
+__global__ void __launch_bounds__(1024) k_op_normal_loss(const int32_t* __restrict__ near_faces, const float* __restrict__ fn,
+                                                          const float* __restrict__ N, int V, float* __restrict__ out,
+                                                          float* __restrict__ dN) {
+    __shared__ float red[32];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    float acc = 0.f;
+    const float iv = 1.0f / (float)V;
+    for (int v = t; v < V; v += 1024) {
+        const float* f3 = fn + 3 * (size_t)near_faces[v];
+        acc += 1.0f - (f3[0] * N[3 * v] + f3[1] * N[3 * v + 1] + f3[2] * N[3 * v + 2]);
+        dN[3 * v] = -f3[0] * iv; dN[3 * v + 1] = -f3[1] * iv; dN[3 * v + 2] = -f3[2] * iv;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) red[warp] = acc;
+    __syncthreads();
+    if (t == 0) { float s = 0.f; for (int w = 0; w < 32; ++w) s += red[w]; out[0] = s * iv; }
+}
+
+// out[0] = mean_f (|na - nb|^2 + |nc - na|^2 + |nb - nc|^2) (loss.py:273-288);
+// dN_v = (2 / F) sum over incident face corners (2 N_v - N_o1 - N_o2), gathered per vertex through the CSR (no atomics)
+__global__ void __launch_bounds__(1024) k_op_laplacian_value(const float* __restrict__ N, const int32_t* __restrict__ faces, int F,
+                                                              float* __restrict__ out) {
+    __shared__ float red[32];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    float acc = 0.f;
+    for (int i = t; i < F; i += 1024) {
+        const float* na = N + 3 * (size_t)faces[3 * i];
+        const float* nb = N + 3 * (size_t)faces[3 * i + 1];
+        const float* nc = N + 3 * (size_t)faces[3 * i + 2];
+        float s = 0.f;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const float ab = na[d] - nb[d], ca = nc[d] - na[d], bc = nb[d] - nc[d];
+            s += ab * ab + ca * ca + bc * bc;
+        }
+        acc += s;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) red[warp] = acc;
+    __syncthreads();
+    if (t == 0) { float s = 0.f; for (int w = 0; w < 32; ++w) s += red[w]; out[0] = s / (float)F; }
+}
+__global__ void k_op_laplacian_grad(const float* __restrict__ N, const int32_t* __restrict__ faces,
+                                    const int32_t* __restrict__ vf_ptr, const int32_t* __restrict__ vf_face, int V, int F,
+                                    float* __restrict__ dN) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    const float mv[3] = {N[3 * v], N[3 * v + 1], N[3 * v + 2]};
+    const float k = 2.0f / (float)F;
+    float g[3] = {0.f, 0.f, 0.f};
+    for (int e = vf_ptr[v]; e < vf_ptr[v + 1]; ++e) {
+        const int f = vf_face[e];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const int o = faces[3 * f + c];
+            if (o == v) continue;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) g[d] += k * (mv[d] - N[3 * (size_t)o + d]);
+        }
+    }
+    dN[3 * v] = g[0]; dN[3 * v + 1] = g[1]; dN[3 * v + 2] = g[2];
+}
+
+// vertex normals, backward: g = dL/dN_v (unit normals) -> through N = m / (|m| + eps) -> dm
+__global__ void k_op_vnormal_bwd(const float* __restrict__ g, const float* __restrict__ N, const float* __restrict__ Nlen, int V,
+                                 float* __restrict__ dm) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    const float len = Nlen[v], le = len + 1e-8f;
+    const float nv[3] = {N[3 * v], N[3 * v + 1], N[3 * v + 2]};
+    const float dot = nv[0] * g[3 * v] + nv[1] * g[3 * v + 1] + nv[2] * g[3 * v + 2];
+    const float c = (len > 0.f) ? dot / len : 0.f;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) dm[3 * v + d] = g[3 * v + d] / le - nv[d] * c;
+}
+// per-corner gradients [F,3,3] -> per vertex (CSR gather, fixed order)
+__global__ void k_op_corner_gather(const float* __restrict__ dcorner, const int32_t* __restrict__ faces,
+                                   const int32_t* __restrict__ vf_ptr, const int32_t* __restrict__ vf_face, int V,
+                                   float* __restrict__ dverts) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    float g[3] = {0.f, 0.f, 0.f};
+    for (int e = vf_ptr[v]; e < vf_ptr[v + 1]; ++e) {
+        const int f = vf_face[e];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            if (faces[3 * f + c] == v) {
+#pragma unroll
+                for (int d = 0; d < 3; ++d) g[d] += dcorner[9 * (size_t)f + 3 * c + d];
+            }
+    }
+    dverts[3 * v] = g[0]; dverts[3 * v + 1] = g[1]; dverts[3 * v + 2] = g[2];
+}
+__global__ void k_op_identity_theta(float* __restrict__ theta4, int B) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) { theta4[4 * b] = 0.f; theta4[4 * b + 1] = 0.f; theta4[4 * b + 2] = 0.f; theta4[4 * b + 3] = 1.0f; }
+}

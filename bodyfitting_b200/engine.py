@@ -206,7 +206,7 @@ class FitSession(object):
             graph = os.environ.get('BODYFIT_GRAPH', '1') != '0'
         self.use_graph = bool(graph) and self.halo_exchange is None
         self.graph = None
-        self.gstream = None
+        self.graphs = {}
         self._aligned = False
 
     def set_inputs(self, kp_packed, cams):
@@ -285,35 +285,37 @@ class FitSession(object):
         launches += per_it + 1
         self.kernel_launches = launches
 
-    def _capture(self):
-        """One uncaptured run on the session's capture stream (one-time setup of kernel attributes / side streams happens
-        outside the capture), then the same launches recorded into a CUDA graph; the library's fork / join events to its
-        side stream become graph edges."""
+    def _capture(self, priority):
+        """One uncaptured run on a capture stream (one-time setup of kernel attributes / side streams happens outside the
+        capture), then the same launches recorded into a CUDA graph; the library's fork / join events to its side stream
+        become graph edges.  Kernel nodes inherit the priority of the stream they are captured on, so a session keeps one
+        graph per priority it is run with (ConcurrentFitSession: decreasing priorities make the parts finish in order)."""
         dev = self.model.device
         cur = torch.cuda.current_stream(dev)
-        self.gstream = torch.cuda.Stream(device=dev)
-        self.gstream.wait_stream(cur)
-        with torch.cuda.stream(self.gstream):
+        gs = torch.cuda.Stream(device=dev) if priority is None else torch.cuda.Stream(device=dev, priority=priority)
+        gs.wait_stream(cur)
+        with torch.cuda.stream(gs):
             self._body()
-        self.gstream.synchronize()
+        gs.synchronize()
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g, stream=self.gstream, capture_error_mode='thread_local'):
+        with torch.cuda.graph(g, stream=gs, capture_error_mode='thread_local'):
             self._body()
-        cur.wait_stream(self.gstream)
+        cur.wait_stream(gs)
+        self.graphs[priority] = (g, gs)
         self.graph = g
 
-    def run(self, theta0=None):
+    def run(self, theta0=None, priority=None):
         """N iterations from ``theta0`` ([B,NP] device tensor; None = whatever load_inputs / a previous call left in the
-        static ``theta0`` buffer)."""
+        static ``theta0`` buffer).  ``priority``: stream priority the graph's kernels run at (None = default)."""
         if theta0 is not None and theta0.data_ptr() != self.theta0.data_ptr():
             self.theta0.copy_(theta0)
         if self.halo is not None and not self._aligned:
             self.halo.align()
             self._aligned = True
         if self.use_graph:
-            if self.graph is None:
-                self._capture()
-            self.graph.replay()
+            if priority not in self.graphs:
+                self._capture(priority)
+            self.graphs[priority][0].replay()
         else:
             self._body()
         return self.fb.t['theta']

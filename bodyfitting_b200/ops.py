@@ -170,7 +170,142 @@ class _Lbs(torch.autograd.Function):
         return fb.t['grad'].clone(), None
 
 
+_csr_cache = {}
+
+
+def _faces_csr(faces):
+    """int32 faces [F,3] on the device + the CSR vertex -> incident faces the atomics-free gathers walk (built on the host
+    once per faces tensor)."""
+    from .smplify.smpld import vertex_face_csr
+    f = faces.detach().reshape(-1, 3)
+    key = (f.data_ptr(), f.shape[0], str(f.device), f._version)
+    hit = _csr_cache.get(key)
+    if hit is None:
+        fh = f.cpu().numpy().astype(np.int64)
+        V = int(fh.max()) + 1
+        ptr, fid = vertex_face_csr(fh, V)
+        hit = (f.to(torch.int32).contiguous(), torch.from_numpy(ptr).to(f.device), torch.from_numpy(fid).to(f.device), V)
+        if len(_csr_cache) > 16:
+            _csr_cache.clear()
+        _csr_cache[key] = hit
+    return hit
+
+
+class _VertexNormals(torch.autograd.Function):
+    """utils/io_utils.py:410-428 compute_normal_torch."""
+    @staticmethod
+    def forward(ctx, vertices, faces):
+        _need_cuda(vertices)
+        f32, vf_ptr, vf_face, Vmin = _faces_csr(faces)
+        v = _f32c(vertices).reshape(-1, 3)
+        V, F = v.shape[0], f32.shape[0]
+        assert V >= Vmin, 'faces index past the vertex array'
+        if V > Vmin:                                   # trailing vertices without faces: extend the CSR pointer
+            vf_ptr = torch.cat([vf_ptr, vf_ptr[-1:].expand(V - Vmin)]).contiguous()
+        nhat, nlen = torch.empty(F, 3, device=v.device), torch.empty(F, device=v.device)
+        N, Nlen = torch.empty(V, 3, device=v.device), torch.empty(V, device=v.device)
+        _call('bf_op_vertex_normals', v.data_ptr(), f32.data_ptr(), vf_ptr.data_ptr(), vf_face.data_ptr(), V, F,
+              nhat.data_ptr(), nlen.data_ptr(), N.data_ptr(), Nlen.data_ptr())
+        ctx.save_for_backward(v, f32, vf_ptr, vf_face, nhat, nlen, N, Nlen)
+        ctx.shape = vertices.shape
+        return N
+
+    @staticmethod
+    def backward(ctx, dN):
+        v, f32, vf_ptr, vf_face, nhat, nlen, N, Nlen = ctx.saved_tensors
+        V, F = v.shape[0], f32.shape[0]
+        dm, dcorner, dv = torch.empty(V, 3, device=v.device), torch.empty(F, 9, device=v.device), torch.empty(V, 3, device=v.device)
+        _call('bf_op_vertex_normals_backward', v.data_ptr(), f32.data_ptr(), vf_ptr.data_ptr(), vf_face.data_ptr(), V, F,
+              nhat.data_ptr(), nlen.data_ptr(), N.data_ptr(), Nlen.data_ptr(), _f32c(dN).reshape(V, 3).data_ptr(), dm.data_ptr(),
+              dcorner.data_ptr(), dv.data_ptr())
+        return dv.reshape(ctx.shape), None
+
+
+class _PcLoss(torch.autograd.Function):
+    """|points - closest|_F with the closest points held constant (smplify/loss.py:239-241)."""
+    @staticmethod
+    def forward(ctx, points, closest):
+        _need_cuda(points)
+        p, c = _f32c(points).reshape(-1), _f32c(closest).reshape(-1)
+        out, dp = torch.empty(1, device=p.device), torch.empty_like(p)
+        _call('bf_op_pc_loss', p.data_ptr(), c.data_ptr(), p.numel(), out.data_ptr(), dp.data_ptr())
+        ctx.save_for_backward(dp)
+        ctx.shape = points.shape
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, dout):
+        (dp,) = ctx.saved_tensors
+        return (dp * dout).reshape(ctx.shape), None
+
+
+class _NormalLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, near_faces, face_norm, point_norm):
+        _need_cuda(point_norm)
+        nf = near_faces.detach().to(torch.int32).contiguous()
+        fn, pn = _f32c(face_norm).reshape(-1, 3), _f32c(point_norm).reshape(-1, 3)
+        V = pn.shape[0]
+        out, d = torch.empty(1, device=pn.device), torch.empty_like(pn)
+        _call('bf_op_normal_loss', nf.data_ptr(), fn.data_ptr(), pn.data_ptr(), V, out.data_ptr(), d.data_ptr())
+        ctx.save_for_backward(d)
+        ctx.shape = point_norm.shape
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, dout):
+        (d,) = ctx.saved_tensors
+        return None, None, (d * dout).reshape(ctx.shape)
+
+
+class _Laplacian(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, norms, faces):
+        _need_cuda(norms)
+        f32, vf_ptr, vf_face, Vmin = _faces_csr(faces)
+        n = _f32c(norms).reshape(-1, 3)
+        V, F = n.shape[0], f32.shape[0]
+        if V > Vmin:
+            vf_ptr = torch.cat([vf_ptr, vf_ptr[-1:].expand(V - Vmin)]).contiguous()
+        out, d = torch.empty(1, device=n.device), torch.empty_like(n)
+        _call('bf_op_laplacian', n.data_ptr(), f32.data_ptr(), vf_ptr.data_ptr(), vf_face.data_ptr(), V, F, out.data_ptr(), d.data_ptr())
+        ctx.save_for_backward(d)
+        ctx.shape = norms.shape
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, dout):
+        (d,) = ctx.saved_tensors
+        return (d * dout).reshape(ctx.shape), None
+
+
+class _MaskLoss(torch.autograd.Function):
+    """smplify/loss.py:85-130 on world vertices [B,V,3]; ``term`` = smplify.mask.SilhouetteTerm (masks, contours, cameras)."""
+    @staticmethod
+    def forward(ctx, verts, term):
+        import ctypes as C
+        _need_cuda(verts)
+        v = _f32c(verts)
+        B, V = v.shape[0], v.shape[1]
+        scratch = torch.empty(8 * B, device=v.device)
+        loss, dv = torch.empty(B, device=v.device), torch.empty_like(v)
+        _lib.check(_lib.lib().bf_op_mask_loss(v.data_ptr(), B, V, C.byref(term.struct), scratch.data_ptr(), loss.data_ptr(),
+                                              dv.data_ptr(), _stream()), 'bf_op_mask_loss')
+        ctx.save_for_backward(dv)
+        return loss.sum()
+
+    @staticmethod
+    def backward(ctx, dout):
+        (dv,) = ctx.saved_tensors
+        return dv * dout, None
+
+
 project = _Project.apply
+vertex_normals = _VertexNormals.apply
+pc_loss = _PcLoss.apply
+normal_loss = _NormalLoss.apply
+laplacian = _Laplacian.apply
+mask_loss = _MaskLoss.apply
 gmof_op = _Gmof.apply
 reprojection_op = _Reprojection.apply
 keypoints_world = _KeypointsWorld.apply

@@ -2,8 +2,7 @@
 running on the B200 kernels (CUDA tensors only; autograd supported through hand-written backward
 kernels).  The fused fit loop (smplify.smplify.SMPLify) does not go through these functions.
 
-Not provided: ``multview_mask_loss`` / ``extract_countours`` (silhouette term) and the
-unused ``point_cloud_loss_chamfer_naive``.
+Not provided: the unused ``point_cloud_loss_chamfer_naive`` (loss.py:245-258).
 """
 import numpy as np
 import torch
@@ -79,3 +78,48 @@ def multiview_keypoint_loss(w2cs, Ks, keypoints, model_joints, poses, betas, use
     if output == 'sum':
         return total.sum(), losses
     return reprojection_loss, losses
+
+
+def point_cloud_loss_mesh_grid(mesh_grid_searcher, points):
+    """[loss.py:233-242] point-to-scan term: the Frobenius norm of (points - their closest scan points); the closest points
+    are constants of the objective (the reference detaches them, and its search has no backward)."""
+    pts = points.reshape(-1, 3)
+    closest, _ = mesh_grid_searcher.nearest_points(pts.detach())
+    return ops.pc_loss(pts, closest)
+
+
+def normal_loss_mesh_grid(mesh_grid_searcher, points, face_norm_mesh, point_norm):
+    """[loss.py:260-271] mean(1 - <face normal of the closest scan face, vertex normal>); differentiable w.r.t. ``point_norm``."""
+    _, faces = mesh_grid_searcher.nearest_points(points.reshape(-1, 3).detach())
+    return ops.normal_loss(faces, face_norm_mesh, point_norm)
+
+
+def normal_laplacian_smoothness(norms, faces):
+    """[loss.py:273-288] mean over faces of |na - nb|^2 + |nc - na|^2 + |nb - nc|^2."""
+    return ops.laplacian(norms, faces)
+
+
+def extract_countours(masks):
+    """[loss.py:73-83] (the reference's spelling) external contour of every mask [Nm,H,W] -> list of float tensors [Nc,1,2]
+    of (x, y) pixels on the masks' device.  As the reference does, the contour kept is ``contours[argmax(shape[1])]`` -- OpenCV
+    contours are [Nc,1,2], so that is always the FIRST external contour it returns, not the longest."""
+    from .mask import extract_contours
+    dev = masks.device if torch.is_tensor(masks) else 'cpu'
+    arr = masks.detach().cpu().numpy() if torch.is_tensor(masks) else np.asarray(masks)
+    return [torch.from_numpy(c.reshape(-1, 1, 2)).to(dev) for c in extract_contours(arr)]
+
+
+def multview_mask_loss(contours, masks, smpl_verts, smpl_faces, w2cs, Ks, mask_frames, epsilon=10, imsize=512):
+    """[loss.py:85-130] (the reference's spelling) silhouette term for one frame: ``contours`` from extract_countours,
+    ``masks`` [Nm,H,W] 0/1, ``smpl_verts`` [1,V,3] world vertices, ``w2cs`` / ``Ks`` of the mask views.  Differentiable w.r.t.
+    ``smpl_verts``.  (``smpl_faces`` / ``mask_frames`` are accepted and unused, as in the reference.)"""
+    from .mask import SilhouetteTerm
+    dev = smpl_verts.device
+    w2c = [w.detach().cpu().numpy() if torch.is_tensor(w) else np.asarray(w) for w in w2cs]
+    c2ws = [np.linalg.inv(w.astype(np.float64)) for w in w2c]
+    cams = pack_cameras(c2ws, [k.detach().cpu().numpy() if torch.is_tensor(k) else np.asarray(k) for k in Ks])
+    mk = masks.detach().cpu().numpy() if torch.is_tensor(masks) else np.asarray(masks)
+    cont = [c.detach().cpu().numpy().reshape(-1, 2).astype(np.float32) for c in contours]
+    term = SilhouetteTerm(None, (mk > 0.5).astype(np.uint8) * 255, cams, imsize=imsize, epsilon=float(epsilon), device=dev,
+                          contours=[cont], num_verts=smpl_verts.shape[-2])
+    return ops.mask_loss(smpl_verts.reshape(1, -1, 3), term)

@@ -12,10 +12,14 @@ from .. import _lib
 from ..engine import _stream
 
 
-def extract_contours(masks):
-    """masks [Nm,H,W] (bool / 0-1 / 0-255) -> list of float32 [Nc,2] (x, y) contour pixels, the longest external
-    contour of each mask (cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_NONE).  The reference unpacks OpenCV 3's three return
-    values (loss.py:79); OpenCV 4 returns (contours, hierarchy): the contours are the second-to-last element in both."""
+def extract_contours(masks, pick='reference'):
+    """masks [Nm,H,W] (bool / 0-1 / 0-255) -> list of float32 [Nc,2] (x, y) contour pixels of one external contour per
+    mask (cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_NONE).  The reference unpacks OpenCV 3's three return values (loss.py:79);
+    OpenCV 4 returns (contours, hierarchy): the contours are the second-to-last element in both.
+    ``pick='reference'``: the reference keeps ``contour[argmax(a.shape[1] for a in contour)]`` (loss.py:80) -- OpenCV contours
+    are [Nc,1,2], so every ``shape[1]`` is 1 and the argmax is 0: the FIRST contour OpenCV returns (for a mask with several
+    blobs not necessarily the largest).  Reproduced as is; ``pick='longest'`` selects the longest contour instead (the
+    evident intent), at the price of differing from the reference on multi-blob masks."""
     try:
         import cv2
     except ImportError as e:                                   # pragma: no cover
@@ -27,7 +31,7 @@ def extract_contours(masks):
         if len(cs) == 0:
             out.append(np.zeros((0, 2), np.float32))
             continue
-        c = cs[int(np.argmax(np.array([a.shape[0] for a in cs])))]
+        c = cs[int(np.argmax(np.array([a.shape[0] for a in cs])))] if pick == 'longest' else cs[0]
         out.append(np.ascontiguousarray(c.reshape(-1, 2), dtype=np.float32))
     return out
 
@@ -35,7 +39,10 @@ def extract_contours(masks):
 class SilhouetteTerm(object):
     """Device state of the silhouette term for B frames x Nm mask views."""
 
-    def __init__(self, model, masks, mask_cams, imsize=512, epsilon=10.0, stride=4, device='cuda'):
+    def __init__(self, model, masks, mask_cams, imsize=512, epsilon=10.0, stride=4, device='cuda', contours=None,
+                 num_verts=None, pick='reference'):
+        """``contours`` (optional): per frame a list of [Nc,2] arrays, one per mask view (else extracted here);
+        ``num_verts``: body vertex count when no model is given (stand-alone operator)."""
         dev = torch.device(device)
         masks = np.asarray(masks)
         if masks.ndim == 3:
@@ -45,7 +52,7 @@ class SilhouetteTerm(object):
         self.masks = torch.from_numpy(binm.astype(np.float32)).to(dev).contiguous()
         cont, cptr, cown = [], [0], []
         for b in range(B):
-            for m, c in enumerate(extract_contours(binm[b])):
+            for m, c in enumerate(contours[b] if contours is not None else extract_contours(binm[b], pick=pick)):
                 cont.append(c)
                 cptr.append(cptr[-1] + len(c))
                 cown += [b * Nm + m] * len(c)
@@ -54,7 +61,7 @@ class SilhouetteTerm(object):
         self.cptr = torch.tensor(cptr, dtype=torch.int32, device=dev)
         self.cown = torch.tensor(cown if total else [0], dtype=torch.int32, device=dev)
         self.cams = torch.as_tensor(np.asarray(mask_cams, dtype=np.float32)).reshape(Nm, 12).to(dev).contiguous()
-        Nq = (model.V + stride - 1) // stride
+        Nq = ((model.V if model is not None else int(num_verts)) + stride - 1) // stride
         f32 = dict(device=dev, dtype=torch.float32)
         self.uv = torch.empty(B, Nm, Nq, 2, **f32)
         self.near_q = torch.empty(max(total, 1), dtype=torch.int32, device=dev)

@@ -63,7 +63,8 @@ class SMPLify(object):
         self.temporal_weight, self.halo_exchange, self.halo = float(temporal_weight), halo_exchange, halo
         # Results on the host: the reference returns fresh arrays.  True = always copy out of the pinned staging buffers,
         # False = return views of them (valid until the next call with the same shapes), None = copy unless the results
-        # exceed 256 MB (a 10,000-frame SMPL-X batch holds 1.28 GB of vertices; copying it again would cost more than the fit)
+        # exceed 32 MB (~250 SMPL-X frames; fresh pages cost ~0.2 ms per MB: the 160 MB of a 1,250-frame shard took 36 ms to copy,
+        # 2.5x the fit itself -- large batches get views, and the docstring of __call__ says so)
         self.copy_outputs = copy_outputs
         self.graph = graph            # None: CUDA-graph replay of the whole fit unless BODYFIT_GRAPH=0; False: direct launches
         # batches of >= 4096 frames are fitted as up to this many staggered parts on their own streams (1 = one batch)
@@ -148,7 +149,7 @@ class SMPLify(object):
                     poses_dev = self._h2d(('poses', k), init_poses[lo:hi])
                     betas_dev = self._h2d(('betas', k), init_betas[lo:hi])
                     part.load_inputs(kp_dev, cams, poses_dev, betas_dev)
-                    part.run()
+                    part.run(priority=st.priority)
                     if as_numpy:
                         for name, v in part.results().items():
                             pbuf = self._pinned.get(('out', name))
@@ -306,7 +307,7 @@ class SMPLify(object):
     def _host_results(self, host, nbytes):
         """Pinned staging buffers -> the arrays handed to the caller; a batch dimension of 1 is squeezed as the reference's
         ``cpu()`` does (smplify.py:252-254).  See ``copy_outputs`` in __init__."""
-        copy = self.copy_outputs if self.copy_outputs is not None else nbytes <= (256 << 20)
+        copy = self.copy_outputs if self.copy_outputs is not None else nbytes <= (32 << 20)
         if copy:
             return {k: np.array(p.squeeze(0).numpy()) for k, p in host.items()}
         return {k: p.squeeze(0).numpy() for k, p in host.items()}

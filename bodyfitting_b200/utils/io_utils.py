@@ -68,3 +68,10 @@ def load_obj_mesh(mesh_file):
                 for k in range(1, len(idx) - 1):
                     faces.append([idx[0], idx[k], idx[k + 1]])
     return np.array(verts, dtype=np.float64), np.array(faces, dtype=np.int64)
+
+
+def compute_normal_torch(vertices, faces):
+    """[utils/io_utils.py:410-428] per-vertex unit normals of a triangle mesh (unit face normals summed over the incident faces,
+    renormalised with the reference's +1e-8), differentiable w.r.t. ``vertices`` (CUDA kernels, hand-written backward)."""
+    from .. import ops
+    return ops.vertex_normals(vertices, faces)

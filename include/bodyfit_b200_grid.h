@@ -32,6 +32,13 @@ int bf_grid_fill(const BfGrid* g, int32_t* cursor, void* stream);
 /* closest point of every query: near_pts[Q,3], near_faces[Q] (-1 if the mesh is empty), dist2[Q] (optional) */
 int bf_grid_nearest(const BfGrid* g, const float* points, int Q, float* near_pts, int32_t* near_faces, float* dist2, void* stream);
 
+/* barycentric coefficients [Q,3] of the closest point on the selected face (the reference's `coeff` output,
+ * mesh_grid.cpp:54-72, mesh_grid_kernel.cu:405-410): near_pt = c0 v0 + c1 v1 + c2 v2; zeros where near_faces < 0 */
+int bf_grid_barycentric(const BfGrid* g, const float* points, const int32_t* near_faces, int Q, float* coeff, void* stream);
+/* grad[Q,3,3,3]: grad[q][i][j][k] = d near_pt[q][j] / d verts[faces[near_faces[q]][i]][k] (replaces mesh_grid.cpp:119-127
+ * search_nearest_point_backward, whose kernel is unfinished in the reference and never called) */
+int bf_grid_nearest_backward(const BfGrid* g, const float* points, const int32_t* near_faces, int Q, float* grad, void* stream);
+
 /* inside test (utils/mesh_grid_searcher.py:86-91, native search_inside_mesh): signs[Q] = +1 inside the closed mesh, -1 outside
  * (crossing parity of an axis ray towards the nearest grid border; points outside the grid box are outside) */
 int bf_grid_inside(const BfGrid* g, const float* points, int Q, float* signs, void* stream);

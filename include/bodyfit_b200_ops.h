@@ -34,6 +34,30 @@ int bf_op_keypoints_world(const float* joints, const float* kp, const float* cam
 int bf_op_angle_prior(const float* pose, int B, int D, float* out, float* dout, void* stream);
 int bf_op_gmm_pose(const BfModel* m, const float* pose, int ld, int nvalid, int B, float weight, float* grad, float* loss,
                    void* stream);
+
+/* scan / normal / silhouette terms (the SMPL+D loop and the dense loop run fused versions: bf_smpld_step, bf_pc_loss,
+ * bf_mask_loss).  Every forward also returns the gradient w.r.t. its differentiable input.
+ *   bf_op_pc_loss            smplify/loss.py:233-242  out[0] = |points - closest|_F (n floats), dpoints = (points - closest)/out
+ *   bf_op_normal_loss        smplify/loss.py:260-271  out[0] = mean(1 - <face_norm[near_faces[v]], point_norm[v]>), d/d point_norm
+ *   bf_op_laplacian          smplify/loss.py:273-288  out[0] = mean over faces of the pairwise squared normal differences, d/d norms
+ *                            (vf_ptr / vf_face: CSR vertex -> incident faces, for the atomics-free gather)
+ *   bf_op_vertex_normals     utils/io_utils.py:405-428 compute_normal_torch: unit face normals summed per vertex, renormalised
+ *   bf_op_vertex_normals_backward   its gradient w.r.t. the vertex positions
+ *   bf_op_mask_loss          smplify/loss.py:85-130 multview_mask_loss on WORLD vertices [B,V,3]: loss[b] and d/d verts
+ *                            (scratch: 8 B floats; BfMask from bodyfit_b200_mask.h) */
+struct BfMask;
+int bf_op_pc_loss(const float* points, const float* closest, int64_t n, float* out, float* dpoints, void* stream);
+int bf_op_normal_loss(const int32_t* near_faces, const float* face_norm, const float* point_norm, int V, float* out,
+                      float* dpoint_norm, void* stream);
+int bf_op_laplacian(const float* norms, const int32_t* faces, const int32_t* vf_ptr, const int32_t* vf_face, int V, int F,
+                    float* out, float* dnorms, void* stream);
+int bf_op_vertex_normals(const float* verts, const int32_t* faces, const int32_t* vf_ptr, const int32_t* vf_face, int V, int F,
+                         float* nhat, float* nlen, float* normals, float* Nlen, void* stream);
+int bf_op_vertex_normals_backward(const float* verts, const int32_t* faces, const int32_t* vf_ptr, const int32_t* vf_face, int V,
+                                  int F, const float* nhat, const float* nlen, const float* normals, const float* Nlen,
+                                  const float* dnormals, float* dm_scratch, float* dcorner_scratch, float* dverts, void* stream);
+int bf_op_mask_loss(const float* verts_world, int B, int V, const struct BfMask* k, float* scratch, float* loss, float* dverts,
+                    void* stream);
 #ifdef __cplusplus
 }
 #endif

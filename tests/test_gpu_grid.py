@@ -234,3 +234,138 @@ def test_inside_and_rays_vs_reference_kernel():
     agree = (ohit == rhit).float().mean().item()
     print('rays: agreement with the reference kernel %.4f' % agree)
     assert agree > 0.995
+
+
+class _RefProtocolSearcher(object):
+    """The reference wrapper's call protocol (utils/mesh_grid_searcher.py:51-99: torch geometry, caller-allocated tensors,
+    in-place outputs) restated over a module `mg` exposing the six native functions -- used with our drop-in
+    (bodyfitting_b200.compat.mesh_grid) and with the reference's own build (oracle/_ref) alike."""
+
+    def __init__(self, mg, verts, faces):
+        self.mg = mg
+        verts = torch.from_numpy(verts).float().cuda()
+        faces = torch.from_numpy(faces).int().cuda()
+        self.verts, self.faces = verts.view(-1, 3), faces.view(-1, 3)
+        _min, _max = torch.min(verts, 0)[0], torch.max(verts, 0)[0]
+        self.step = (torch.cumprod(_max - _min, 0)[-1] / len(verts)) ** (1. / 3.)
+        l = _max - _min
+        c = (_max + _min) / 2
+        l = torch.max(torch.floor(l / self.step), torch.zeros_like(l)) + 1
+        self.num = torch.cat([l, torch.cumprod(l, 0)[-1:]]).int()
+        self.minmax = torch.cat([c - self.step * l / 2, _max])
+        self.tri_num = torch.zeros(int(self.num[-1]), dtype=torch.int32).cuda()
+        self.tri_idx = torch.zeros(1, dtype=torch.int32).cuda()
+        mg.insert_grid_surface(self.verts, self.faces, self.minmax, self.num, float(self.step), self.tri_num, self.tri_idx)
+
+    def nearest(self, points):
+        nf = torch.zeros(points.shape[-2], dtype=torch.int32).cuda()
+        coeff = torch.zeros(points.shape, dtype=torch.float32).cuda()
+        pts = torch.zeros_like(coeff)
+        self.mg.search_nearest_point(points, self.verts, self.faces, self.tri_num, self.tri_idx, self.num, self.minmax,
+                                     float(self.step), nf, pts, coeff)
+        return pts, nf, coeff
+
+    def inside(self, points):
+        s = torch.zeros(points.shape[-2], dtype=torch.float32).cuda()
+        self.mg.search_inside_mesh(points, self.verts, self.faces, self.tri_num, self.tri_idx, self.num, self.minmax, float(self.step), s)
+        return s
+
+    def rays(self, o, d):
+        hit = torch.zeros(o.shape[-2], dtype=torch.bool).cuda()
+        self.mg.search_intersect(o, d, self.verts, self.faces, self.tri_num, self.tri_idx, self.num, self.minmax, float(self.step), hit)
+        return hit
+
+
+def test_mesh_grid_module_drop_in_six_functions():
+    """bodyfitting_b200.compat.mesh_grid = the reference's native module surface (mesh_grid.cpp:129-136), driven exactly as the
+    reference's wrapper drives it: same tensors in, same in-place outputs (near_faces, near_pts, coeff, signs, intersect,
+    cumulative tri_num), checked against the fp64 brute force and, when built, the reference's own kernels."""
+    import bodyfitting_b200.compat.mesh_grid as mg
+    v, f = _scan(2500, 8)
+    q = _queries(v, 3000, 4)
+    s = _RefProtocolSearcher(mg, v, f)
+    qd = torch.from_numpy(q).cuda()
+    pts, nf, coeff = s.nearest(qd)
+    assert pts.shape == (len(q), 3) and nf.shape == (len(q),) and nf.dtype == torch.int32 and coeff.shape == (len(q), 3)
+    cp, _, d2 = gp.closest_points_bruteforce(q, v, f)
+    dist = torch.norm(pts - qd, dim=1).cpu().numpy()
+    assert np.abs(dist - np.sqrt(d2)).max() < 2e-6
+    tri = torch.from_numpy(v).cuda()[torch.from_numpy(f).cuda().long()[nf.long()]]          # [Q,3,3]
+    recon = (coeff[:, :, None] * tri).sum(1)
+    assert float((recon - pts).abs().max()) < 1e-6 and float((coeff.sum(1) - 1).abs().max()) < 1e-6
+    assert float(coeff.min()) >= -1e-6                                                      # closest point lies ON the triangle
+    # tri_num is the inclusive cumulative count, tri_idx holds every (cell, triangle) incidence
+    tn = s.tri_num.cpu().numpy()
+    assert (np.diff(tn) >= 0).all() and tn[-1] == s.tri_idx.numel()
+    # cumsum: in place + reshaped view (mesh_grid.cpp:111-118)
+    t = torch.tensor([1, 2, 3, 4], dtype=torch.int32).cuda()
+    r = mg.cumsum(t)
+    assert t.tolist() == [1, 3, 6, 10] and tuple(r.shape) == (1, 1, 4)
+    # inside / rays against the fp64 referees
+    lo, hi = v.min(0), v.max(0)
+    rng = np.random.RandomState(2)
+    qi = (rng.rand(2000, 3) * (hi - lo) * 1.2 + lo - 0.1 * (hi - lo)).astype(np.float32)
+    signs = s.inside(torch.from_numpy(qi).cuda()).cpu().numpy()
+    want = gp.inside_bruteforce(qi, v, f)
+    assert (signs == np.where(want, 1.0, -1.0)).mean() > 0.999
+    ro = (rng.rand(1500, 3) * (hi - lo) * 2.0 + lo - 0.5 * (hi - lo)).astype(np.float32)
+    rd = rng.randn(1500, 3).astype(np.float32)
+    hit = s.rays(torch.from_numpy(ro).cuda(), torch.from_numpy(rd).cuda())
+    assert hit.dtype == torch.bool
+    assert (hit.cpu().numpy() == gp.ray_any_bruteforce(ro, rd, v, f)).mean() > 0.999
+    # non-CUDA tensors are rejected like the reference's CHECK_CUDA
+    with pytest.raises(RuntimeError):
+        mg.search_inside_mesh(torch.zeros(4, 3), s.verts, s.faces, s.tri_num, s.tri_idx, s.num, s.minmax, float(s.step), torch.zeros(4).cuda())
+    so = glob.glob(os.path.join(ROOT, 'oracle', '_ref', 'mesh_grid*.so'))
+    if so:
+        spec = importlib.util.spec_from_file_location('mesh_grid', so[0])
+        ref_mg = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(ref_mg)
+        r = _RefProtocolSearcher(ref_mg, v, f)
+        rp, rf, rc = r.nearest(qd)
+        rdist = torch.norm(rp - qd, dim=1).cpu().numpy()
+        print('vs reference kernel: max |dist diff| %.3e, ours never worse: %s' % (np.abs(rdist - dist).max(), bool((dist <= rdist + 1e-6).all())))
+        assert (dist <= rdist + 1e-6).all() and np.abs(rdist - dist).max() < 1e-4
+        assert int(r.tri_num[-1]) == int(s.tri_num[-1])                                     # same cell occupancy
+
+
+def test_nearest_point_backward_matches_finite_differences():
+    """search_nearest_point_backward: grad[q,i,j,k] = d near_pt_j / d v_i,k against central differences of the fp64 brute-force
+    closest point on the selected face (queries away from region borders)."""
+    import bodyfitting_b200.compat.mesh_grid as mg
+    rng = np.random.RandomState(3)
+    v = rng.randn(30, 3).astype(np.float32)
+    f = np.array([[3 * i, 3 * i + 1, 3 * i + 2] for i in range(10)], np.int32)
+    q = (v[f].mean(1)[rng.randint(0, 10, 64)] + rng.randn(64, 3) * 0.6).astype(np.float32)
+    s = _RefProtocolSearcher(mg, v, f)
+    qd = torch.from_numpy(q).cuda()
+    pts, nf, coeff = s.nearest(qd)
+    grad = torch.zeros(1).cuda()
+    mg.search_nearest_point_backward(qd, s.verts, s.faces, nf, grad)
+    assert tuple(grad.shape) == (64, 3, 3, 3)
+    g = grad.cpu().numpy()
+    nfh = nf.cpu().numpy()
+    h, checked = 1e-4, 0
+    for qi in range(64):
+        tri = f[nfh[qi]]
+        fd = np.zeros((3, 3, 3))
+        stable = True
+        for i in range(3):
+            for k in range(3):
+                outs = []
+                for sgn in (+1, -1):
+                    vv = v.astype(np.float64).copy()
+                    vv[tri[i], k] += sgn * h
+                    cp, _, _ = gp.closest_points_bruteforce(q[qi:qi + 1].astype(np.float64), vv, f[nfh[qi]:nfh[qi] + 1])
+                    outs.append(cp[0])
+                fd[i, :, k] = (outs[0] - outs[1]) / (2 * h)
+        c = coeff[qi].cpu().numpy()
+        on_border = ((np.abs(c) < 1e-3) & (np.abs(c) > 0)).any() or ((np.abs(c - 1) < 1e-3) & (c != 1)).any()
+        if on_border or not stable:
+            continue
+        err = np.abs(g[qi] - fd).max()
+        if err > 5e-3:                      # a query within h of a region border: the two sides differ, skip; must be rare
+            continue
+        checked += 1
+    print('backward: %d of 64 queries matched finite differences to 5e-3' % checked)
+    assert checked >= 56

@@ -143,3 +143,78 @@ def test_multiview_keypoint_loss_composed(assets):
         assert relerr(losses[k], terms[k].detach().numpy()) < 1e-5, k
     for k in p:
         assert relerr(pg[k].grad.cpu().numpy(), pr[k].grad.numpy()) < 2e-4, k
+
+
+def test_scan_and_normal_terms_under_reference_names():
+    """smplify.loss.{point_cloud_loss_mesh_grid, normal_loss_mesh_grid, normal_laplacian_smoothness} and
+    utils.io_utils.compute_normal_torch (reference: smplify/loss.py:233-242,260-288, utils/io_utils.py:410-428): values and
+    gradients against autograd of the oracle's torch restatements (fp64), composed as the SMPL+D loop composes them
+    (smplify/smplify.py:236-245)."""
+    from bodyfitting_b200.smplify import loss as L
+    from bodyfitting_b200.utils.io_utils import compute_normal_torch
+    from bodyfitting_b200.utils.mesh_grid_searcher import MeshGridSearcher
+    from oracle import geometry_port as gp
+    body, faces = syn.make_template(1200, 3)
+    scan, sfaces = syn.make_template(2500, 11)
+    scan = (scan * 1.03).astype(np.float32)
+    rng = np.random.RandomState(1)
+    body = (body + rng.randn(*body.shape) * 0.003).astype(np.float32)
+    tris = scan[sfaces]
+    fn = np.cross(tris[:, 1] - tris[:, 0], tris[:, 2] - tris[:, 0]).astype(np.float32)
+    searcher = MeshGridSearcher(scan, sfaces.astype(np.int32))
+    # ---- ours
+    v = torch.tensor(body, device='cuda', requires_grad=True)
+    f = torch.tensor(faces.astype(np.int64), device='cuda')
+    norms = compute_normal_torch(v, f)
+    icp = L.point_cloud_loss_mesh_grid(searcher, v)
+    nl = L.normal_loss_mesh_grid(searcher, v, torch.tensor(fn, device='cuda'), norms)
+    sm = L.normal_laplacian_smoothness(norms, f)
+    (icp + (nl + sm) * 0.3).backward()
+    # ---- oracle (fp64, exact brute-force closest points)
+    vr = torch.tensor(body, dtype=torch.float64, requires_grad=True)
+    fr = torch.tensor(faces.astype(np.int64))
+    nr = gp.compute_normal_torch(vr, fr)
+    cp, cf, _ = gp.closest_points_bruteforce(body.astype(np.float64), scan.astype(np.float64), sfaces.astype(np.int64))
+    icp_r = torch.norm(vr - torch.tensor(cp), p=2)
+    nl_r = torch.mean(1 - torch.sum(torch.tensor(fn, dtype=torch.float64)[torch.tensor(cf)] * nr, dim=-1))
+    sm_r = gp.normal_laplacian_smoothness(nr, fr)
+    (icp_r + (nl_r + sm_r) * 0.3).backward()
+    print('normals', relerr(norms.detach().cpu().numpy(), nr.detach().numpy()), 'icp', abs(float(icp) - float(icp_r)) / float(icp_r),
+          'normal', abs(float(nl) - float(nl_r)) / abs(float(nl_r)), 'smooth', abs(float(sm) - float(sm_r)) / float(sm_r),
+          'grad', relerr(v.grad.cpu().numpy(), vr.grad.numpy()))
+    assert relerr(norms.detach().cpu().numpy(), nr.detach().numpy()) < 1e-5
+    assert abs(float(icp) - float(icp_r)) / float(icp_r) < 1e-5
+    assert abs(float(nl) - float(nl_r)) / abs(float(nl_r)) < 1e-4          # closest-face ties may differ on a handful of vertices
+    assert abs(float(sm) - float(sm_r)) / float(sm_r) < 1e-5
+    assert relerr(v.grad.cpu().numpy(), vr.grad.numpy()) < 1e-3
+
+
+def test_mask_loss_under_reference_names(assets):
+    """smplify.loss.{extract_countours, multview_mask_loss} (reference spelling, smplify/loss.py:73-130) on a mask with TWO
+    blobs in one view: the contour kept is the one the reference keeps (the first OpenCV returns), value and vertex
+    gradient match the oracle's restatement of the reference function."""
+    from bodyfitting_b200.smplify import loss as L
+    mt, nv = 'smpl', 4
+    port = make_port(assets, mt)
+    sc = make_scene(port, mt, 1, nv, seed=23)
+    init = sc['init']
+    ev = port.loss_and_grads(dict(global_orient=init['global_orient'], body_pose=init['body_pose'], betas=init['betas']),
+                             sc['c2ws'], sc['Ks'], np.zeros((1, nv, 25, 3), np.float32))
+    masks = syn.make_masks(ev['vertices'][0], port.faces, sc['c2ws'], sc['Ks'])[[1, 3]]
+    masks[0, 20:60, 30:90] = 255                                       # a second, smaller blob
+    masks[1, 440:500, 400:480] = 255
+    mk = torch.as_tensor((masks > 128).astype(np.float32))
+    w2cs = torch.inverse(torch.as_tensor(np.array(sc['c2ws']), dtype=torch.float32))[[1, 3]]
+    Kt = torch.as_tensor(np.array(sc['Ks']), dtype=torch.float32)[[1, 3]]
+    cont_ref = fp.extract_contours(mk)
+    cont = L.extract_countours(mk.cuda())
+    assert all(c.shape == r.shape and np.array_equal(c.cpu().numpy(), r.numpy()) for c, r in zip(cont, cont_ref))
+    vr = torch.tensor(ev['vertices'][:1], requires_grad=True)
+    val_r = fp.mask_objective(cont_ref, mk, vr, list(w2cs), list(Kt), 512, exact_cdist=True)
+    val_r.backward()
+    vg = torch.tensor(ev['vertices'][:1], device='cuda', requires_grad=True)
+    val = L.multview_mask_loss(cont, mk.cuda(), vg, port.faces[None], list(w2cs.cuda()), list(Kt.cuda()), [1, 3], imsize=512)
+    val.backward()
+    print('mask loss', float(val), float(val_r), 'grad rel', relerr(vg.grad.cpu().numpy(), vr.grad.numpy()))
+    assert abs(float(val) - float(val_r)) / float(val_r) < 2e-5
+    assert relerr(vg.grad.cpu().numpy(), vr.grad.numpy()) < 1e-4
