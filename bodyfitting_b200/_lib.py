@@ -130,6 +130,7 @@ def lib():
         'bf_pc_loss': [pg, pm, pf, fl, fl, fp, fp, fp, fp, vp],
         'bf_mask_loss': [pm, pf, C.POINTER(BfMask), fl, vp],
         'bf_op_pc_loss': [fp, fp, i64, fp, fp, vp],
+        'bf_op_regress_joints': [fp, fp, fp, fp, i32, i32, i32, fp, vp],
         'bf_op_normal_loss': [fp, fp, fp, i32, fp, fp, vp],
         'bf_op_laplacian': [fp, fp, fp, fp, i32, i32, fp, fp, vp],
         'bf_op_vertex_normals': [fp, fp, fp, fp, i32, i32, fp, fp, fp, fp, vp],
@@ -155,7 +156,7 @@ EXPORTED_GRID = ['bf_grid_count', 'bf_grid_fill', 'bf_grid_nearest', 'bf_grid_ba
 EXPORTED_MASK = ['bf_mask_loss']
 EXPORTED_OPS = ['bf_op_project', 'bf_op_project_backward', 'bf_op_gmof', 'bf_op_gmof_backward', 'bf_op_reprojection',
                 'bf_op_keypoints_world', 'bf_op_angle_prior', 'bf_op_gmm_pose', 'bf_op_pc_loss', 'bf_op_normal_loss',
-                'bf_op_laplacian', 'bf_op_vertex_normals', 'bf_op_vertex_normals_backward', 'bf_op_mask_loss']
+                'bf_op_laplacian', 'bf_op_vertex_normals', 'bf_op_vertex_normals_backward', 'bf_op_mask_loss', 'bf_op_regress_joints']
 
 
 def check(rc, what=''):

@@ -128,7 +128,7 @@ def search_intersect(origins, directions, verts, faces, tri_num, tri_idx, num, m
 
 def cumsum(input):
     """mesh_grid.cpp:111-118: in-place cumulative sum along dim 0, returned reshaped to [1,1,-1]."""
-    input.set_(input.cumsum(0))
+    input.copy_(input.cumsum(0))             # same storage, same dtype (an int32 cumsum comes back as int64 from torch)
     return input.reshape(1, 1, -1)
 
 

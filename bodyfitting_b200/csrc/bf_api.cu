@@ -294,7 +294,7 @@ int bf_gmm_prior(const BfModel* m, const BfFrames* f, void* stream) {
     BF_NVTX();
     int rc = check_model(m, f); if (rc) return rc;
     BF_REQUIRE(f->gmm_grad && f->gmm_loss, "gmm_grad / gmm_loss is null");
-    if ((f->flags & BF_F_TC) && m->gmm_bt_hi && m->gmm_bt_lo && f->gmm_ws && (m->n_gmm * GM_LD) % TC_BN1 == 0) {
+    if ((f->flags & BF_F_TC) && m->gmm_bt_hi && m->gmm_bt_lo && f->gmm_ws && (m->n_gmm * GM_LD) % TC_BN1 == 0 && GM_KG % TC_BK == 0) {
         // tensor-core form: pack [pose | 1] -> one 3xTF32 GEMM against [P_sym,m | -P_sym,m mu_m] -> per-frame select
         BF_REQUIRE(m->gmm_mean && m->gmm_logw && m->n_gmm > 0, "GMM tables missing");
         cudaStream_t s = (cudaStream_t)stream;
@@ -851,6 +851,15 @@ int bf_op_vertex_normals_backward(const float* verts, const int32_t* faces, cons
     k_smpld_dface<<<(F + 255) / 256, 256, 0, s>>>(verts, faces, nhat, nlen, dm_scratch, F, dcorner_scratch);
     BF_LAUNCH_CHECK();
     k_op_corner_gather<<<(V + 255) / 256, 256, 0, s>>>(dcorner_scratch, faces, vf_ptr, vf_face, V, dverts);
+    BF_LAUNCH_CHECK();
+    return BF_OK;
+}
+int bf_op_regress_joints(const float* points, const int32_t* ptr, const int32_t* idx, const float* w, int B, int N, int R,
+                         float* out, void* stream) {
+    BF_NVTX();
+    BF_REQUIRE(points && ptr && idx && w && out && B > 0 && N > 0 && R > 0, "bad arguments");
+    const size_t warps = (size_t)B * R;
+    k_op_spmm3<<<(unsigned)((warps + 7) / 8), 256, 0, (cudaStream_t)stream>>>(points, ptr, idx, w, B, N, R, out);
     BF_LAUNCH_CHECK();
     return BF_OK;
 }

@@ -266,3 +266,24 @@ __global__ void k_op_identity_theta(float* __restrict__ theta4, int B) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b < B) { theta4[4 * b] = 0.f; theta4[4 * b + 1] = 0.f; theta4[4 * b + 2] = 0.f; theta4[4 * b + 3] = 1.0f; }
 }
+
+// out[b, r, :] = sum_e w[e] x[b, idx[e], :] over the CSR row r (ptr / idx / w) -- a sparse regressor applied to [B,N,3] points:
+// joints = J_regressor @ vertices (smplx vertices2joints; models/smpl.py:85-87 get_joints_h36m) and, with the transposed
+// matrix, its backward.  One warp per (frame, row), fixed butterfly -> deterministic.
+__global__ void __launch_bounds__(256) k_op_spmm3(const float* __restrict__ x, const int32_t* __restrict__ ptr,
+                                                  const int32_t* __restrict__ idx, const float* __restrict__ w, int B, int N, int R,
+                                                  float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const size_t wi = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (wi >= (size_t)B * R) return;
+    const int b = (int)(wi / R), r = (int)(wi % R);
+    const float* xb = x + (size_t)b * N * 3;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int e = ptr[r] + lane; e < ptr[r + 1]; e += 32) {
+        const float we = __ldg(w + e);
+        const float* p = xb + 3 * (size_t)__ldg(idx + e);
+        a0 = fmaf(we, p[0], a0); a1 = fmaf(we, p[1], a1); a2 = fmaf(we, p[2], a2);
+    }
+    a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
+    if (lane == 0) { float* o = out + 3 * wi; o[0] = a0; o[1] = a1; o[2] = a2; }
+}

@@ -38,7 +38,7 @@ class SMPL(nn.Module):
     """Extension of the SMPL model to support more joints (reference: models/smpl.py:56-83)."""
 
     def __init__(self, model_path='data/smpl', batch_size=1, gender='neutral', create_transl=True, model_data=None,
-                 J_regressor_extra=None, device='cuda', **kwargs):
+                 J_regressor_extra=None, J_regressor_h36m=None, device='cuda', **kwargs):
         super().__init__()
         if model_data is None:
             model_data = model_path
@@ -52,6 +52,16 @@ class SMPL(nn.Module):
         self.prepared = PreparedModel('smpl', data, gmm=None, J_regressor_extra=J_regressor_extra, device=device)
         self.faces = self.prepared.faces
         self.joints = None
+        if J_regressor_h36m is None:
+            fn = os.path.join('data', 'J_regressor_h36m.npy')                   # config.JOINT_REGRESSOR_H36M (models/smpl.py:63)
+            J_regressor_h36m = np.load(fn) if os.path.exists(fn) else None
+        self._h36m = ops.SparseRegressor(J_regressor_h36m, self.prepared.device) if J_regressor_h36m is not None else None
+
+    def get_joints_h36m(self, vertices):
+        """models/smpl.py:85-87: the 17 Human3.6M joints regressed from the vertices [B,V,3] (differentiable)."""
+        if self._h36m is None:
+            raise FileNotFoundError('J_regressor_h36m was not given and data/J_regressor_h36m.npy does not exist')
+        return ops.regress_joints(vertices, self._h36m)
 
     def forward(self, global_orient=None, body_pose=None, betas=None, transl=None, return_full_pose=False, **kwargs):
         pm = self.prepared

@@ -300,7 +300,52 @@ class _MaskLoss(torch.autograd.Function):
         return dv * dout, None
 
 
+def _dense_to_csr(Wm):
+    """dense [R,N] numpy -> (ptr, idx, w) int32/int32/float32 numpy, entries in ascending column order"""
+    Wm = np.asarray(Wm, dtype=np.float32)
+    r, c = np.nonzero(Wm)
+    ptr = np.zeros(Wm.shape[0] + 1, dtype=np.int32)
+    np.add.at(ptr, r + 1, 1)
+    return np.cumsum(ptr).astype(np.int32), c.astype(np.int32), Wm[r, c].astype(np.float32)
+
+
+class SparseRegressor(object):
+    """A fixed joint regressor [R,N] (e.g. J_regressor_h36m) as CSR tables of W and W^T on the device."""
+
+    def __init__(self, Wm, device):
+        Wm = np.asarray(Wm, dtype=np.float32)
+        self.R, self.N = Wm.shape
+        up = lambda a: torch.from_numpy(np.ascontiguousarray(a if len(a) else np.zeros(1, a.dtype))).to(device)
+        self.fwd = tuple(up(a) for a in _dense_to_csr(Wm))
+        self.bwd = tuple(up(a) for a in _dense_to_csr(Wm.T))
+
+
+class _Regress(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, points, reg):
+        _need_cuda(points)
+        p = _f32c(points)
+        B, N = p.shape[0], p.shape[1]
+        assert N == reg.N, 'regressor is for %d vertices, got %d' % (reg.N, N)
+        out = torch.empty(B, reg.R, 3, device=p.device)
+        ptr, idx, w = reg.fwd
+        _call('bf_op_regress_joints', p.data_ptr(), ptr.data_ptr(), idx.data_ptr(), w.data_ptr(), B, N, reg.R, out.data_ptr())
+        ctx.reg = reg
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        reg = ctx.reg
+        d = _f32c(dout)
+        B = d.shape[0]
+        dp = torch.empty(B, reg.N, 3, device=d.device)
+        ptr, idx, w = reg.bwd
+        _call('bf_op_regress_joints', d.data_ptr(), ptr.data_ptr(), idx.data_ptr(), w.data_ptr(), B, reg.R, reg.N, dp.data_ptr())
+        return dp, None
+
+
 project = _Project.apply
+regress_joints = _Regress.apply
 vertex_normals = _VertexNormals.apply
 pc_loss = _PcLoss.apply
 normal_loss = _NormalLoss.apply

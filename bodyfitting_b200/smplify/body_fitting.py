@@ -3,8 +3,10 @@
 and ``fit_sequence`` -- the batched replacement of the per-frame loop of ``apps/genebody_fitting.py:183-192``:
 all frames of a sequence go through ONE SMPLify call (the model is built once, not once per frame).
 
-The HMR initialisation (``run_hmr``, a ResNet-50 regressor) is out of scope: the initial (betas, poses) are an
-argument (``net_output``), or come from a user-supplied ``init_fn(image, c2w) -> (betas[1,10], poses[1,72])``.
+The HMR network itself (``run_hmr``'s ResNet-50 regressor) is out of scope: the initial (betas, poses) are an
+argument (``net_output``), come from a user-supplied ``init_fn(image, c2w) -> (betas[1,10], poses[1,72])``, or -- keeping
+the reference's conversion step (body_fitting.py:70-73) -- from ``regressor(image) -> (rotmat[1,24,3,3], betas[1,10], cam)``
+whose root orientation is carried into world coordinates and converted to axis-angle here.
 """
 import os
 
@@ -15,7 +17,8 @@ from .smplify import SMPLify
 
 
 class BodyFitting(object):
-    def __init__(self, options=None, smpl_type=None, age='adult', use_mask=False, debug=False, init_fn=None, **smplify_kw):
+    def __init__(self, options=None, smpl_type=None, age='adult', use_mask=False, debug=False, init_fn=None, regressor=None,
+                 **smplify_kw):
         self.options = options
         self.smpl_type = smpl_type or getattr(options, 'smpl_type', 'smpl')
         self.age = getattr(options, 'age', age)
@@ -23,6 +26,7 @@ class BodyFitting(object):
         self.debug = debug
         self.use_hand_face = (self.smpl_type == 'smplx')
         self.init_fn = init_fn
+        self.regressor = regressor
         self.smplify_kw = smplify_kw
         self._smplify = {}
 
@@ -39,6 +43,10 @@ class BodyFitting(object):
     def __call__(self, images, c2ws, Ks, keypoints, gender='male', keyframe=25, use_frames=list(range(48)),
                  use_mask=False, masks=None, mask_frames=None, render_skip=12, output_folder=None, use_mesh=False,
                  meshfile=None, disp=False, net_output=None, num_iters=None, imsize=None):
+        if net_output is None and self.init_fn is None and self.regressor is not None:
+            from ..utils.geometry import world_init_from_camera_rotmat
+            pred_rotmat, pred_betas = self.regressor(images[keyframe])[:2]               # body_fitting.py:67
+            net_output = (pred_betas, world_init_from_camera_rotmat(pred_rotmat, c2ws[keyframe]))   # :70-73
         if net_output is None:
             if self.init_fn is None:
                 raise ValueError('pass net_output=(betas, poses) or construct BodyFitting(init_fn=...) '

@@ -22,6 +22,12 @@ from ..model import PreparedModel
 from ..synthetic import openpose_to_keypoints
 
 
+def _mark_event():
+    e = torch.cuda.Event(enable_timing=True)
+    e.record(torch.cuda.current_stream())
+    return e
+
+
 class SMPLify(object):
     """Implementation of multiview SMPLify (reference: smplify/smplify.py:19-82)."""
 
@@ -142,14 +148,21 @@ class SMPLify(object):
             ready.record(cur)
             host, nbytes = {}, 0
             streams = sess.prio_streams                            # decreasing priority: parts finish in launch order
+            trace_ev = [] if os.environ.get('BODYFIT_E2E_TRACE') else None      # per part: start, inputs up, fit done, results down
+            mark = (lambda: trace_ev[-1].append(_mark_event())) if trace_ev is not None else (lambda: None)
             for k, ((lo, hi), part, st) in enumerate(zip(sess.ranges, sess.parts, streams)):
                 with torch.cuda.stream(st):
                     st.wait_event(ready)
+                    if trace_ev is not None:
+                        trace_ev.append([])
+                    mark()
                     kp_dev = self._h2d(('kp', k), kp[lo:hi])
                     poses_dev = self._h2d(('poses', k), init_poses[lo:hi])
                     betas_dev = self._h2d(('betas', k), init_betas[lo:hi])
                     part.load_inputs(kp_dev, cams, poses_dev, betas_dev)
+                    mark()
                     part.run(priority=st.priority)
+                    mark()
                     if as_numpy:
                         for name, v in part.results().items():
                             pbuf = self._pinned.get(('out', name))
@@ -159,9 +172,13 @@ class SMPLify(object):
                             host[name] = pbuf
                             pbuf[lo:hi].copy_(v, non_blocking=True)
                             nbytes += int(v.numel() * v.element_size())
+                    mark()
             if as_numpy:
                 for st in streams:
                     st.synchronize()
+                if trace_ev is not None:
+                    t0 = trace_ev[0][0]
+                    self.last_e2e_timeline = [[round(t0.elapsed_time(e), 3) for e in evs] for evs in trace_ev]
                 self.d2h_bytes = nbytes
                 out = self._host_results(host, nbytes)
             else:

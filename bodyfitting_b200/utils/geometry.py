@@ -36,3 +36,14 @@ def convert_hom_to_angle(pred_rotmat, batch_size, device=None):
     if device is not None:
         R = R.to(device)
     return rotation_matrix_to_angle_axis(R).contiguous().view(batch_size, -1)
+
+
+def world_init_from_camera_rotmat(pred_rotmat, c2w):
+    """The step between the pose regressor and the fit (reference: smplify/body_fitting.py:70-73): the regressor predicts the
+    root orientation in the KEYFRAME CAMERA's frame; ``c2w[:3,:3] @ R_root`` carries it into world coordinates, then all 24
+    rotation matrices become the (1,72) axis-angle pose SMPLify starts from.  ``pred_rotmat`` (1,24,3,3) is not modified
+    (the reference overwrites it in place)."""
+    R = pred_rotmat.detach().clone()
+    c2w = torch.as_tensor(c2w, dtype=R.dtype, device=R.device)
+    R[0, 0] = c2w[:3, :3] @ R[0, 0]
+    return convert_hom_to_angle(R, R.shape[0], R.device)

@@ -44,8 +44,12 @@ int bf_op_gmm_pose(const BfModel* m, const float* pose, int ld, int nvalid, int 
  *   bf_op_vertex_normals     utils/io_utils.py:405-428 compute_normal_torch: unit face normals summed per vertex, renormalised
  *   bf_op_vertex_normals_backward   its gradient w.r.t. the vertex positions
  *   bf_op_mask_loss          smplify/loss.py:85-130 multview_mask_loss on WORLD vertices [B,V,3]: loss[b] and d/d verts
- *                            (scratch: 8 B floats; BfMask from bodyfit_b200_mask.h) */
+ *                            (scratch: 8 B floats; BfMask from bodyfit_b200_mask.h)
+ *   bf_op_regress_joints     smplx vertices2joints / models/smpl.py:85-87 get_joints_h36m: out[B,R,3] = W[R,N] @ points[B,N,3]
+ *                            with W in CSR form (ptr [R+1], idx, w); its backward is the same call with the CSR of W^T */
 struct BfMask;
+int bf_op_regress_joints(const float* points, const int32_t* ptr, const int32_t* idx, const float* w, int B, int N, int R,
+                         float* out, void* stream);
 int bf_op_pc_loss(const float* points, const float* closest, int64_t n, float* out, float* dpoints, void* stream);
 int bf_op_normal_loss(const int32_t* near_faces, const float* face_norm, const float* point_norm, int V, float* out,
                       float* dpoint_norm, void* stream);

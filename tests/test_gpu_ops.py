@@ -218,3 +218,23 @@ def test_mask_loss_under_reference_names(assets):
     print('mask loss', float(val), float(val_r), 'grad rel', relerr(vg.grad.cpu().numpy(), vr.grad.numpy()))
     assert abs(float(val) - float(val_r)) / float(val_r) < 2e-5
     assert relerr(vg.grad.cpu().numpy(), vr.grad.numpy()) < 1e-4
+
+
+def test_get_joints_h36m(assets):
+    """models/smpl.py:85-87: J_regressor_h36m @ vertices, value and gradient against the dense einsum."""
+    from bodyfitting_b200.models.smpl import SMPL
+    rng = np.random.RandomState(4)
+    Wm = np.zeros((17, 6890), np.float32)
+    for r in range(17):
+        cols = rng.choice(6890, 30, replace=False)
+        Wm[r, cols] = rng.dirichlet(np.ones(30)).astype(np.float32)
+    smpl = SMPL(model_data=assets('smpl'), J_regressor_extra=assets('jx'), J_regressor_h36m=Wm)
+    v = torch.tensor(rng.randn(3, 6890, 3).astype(np.float32), device='cuda', requires_grad=True)
+    j = smpl.get_joints_h36m(v)
+    ref_v = torch.tensor(v.detach().cpu().numpy(), dtype=torch.float64, requires_grad=True)
+    jr = torch.einsum('bik,ji->bjk', ref_v, torch.tensor(Wm, dtype=torch.float64))
+    assert j.shape == (3, 17, 3) and relerr(j.detach().cpu().numpy(), jr.detach().numpy()) < 1e-6
+    g = rng.randn(3, 17, 3).astype(np.float32)
+    (j * torch.tensor(g, device='cuda')).sum().backward()
+    (jr * torch.tensor(g, dtype=torch.float64)).sum().backward()
+    assert relerr(v.grad.cpu().numpy(), ref_v.grad.numpy()) < 1e-6

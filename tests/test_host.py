@@ -412,3 +412,89 @@ def test_reference_mesh_grid_wrapper_binds_to_our_module():
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+
+
+def test_init_conversion_matches_reference_converter():
+    """(f)3: rotmat -> axis-angle and the world transform of the root orientation against the REFERENCE'S OWN
+    utils/geometry.py:331-493 + smplify/body_fitting.py:70-73 -- committed golden (tests/golden/make_golden_aux.py) and, where
+    /root/reference exists, the live reference functions."""
+    from bodyfitting_b200.utils.geometry import convert_hom_to_angle, world_init_from_camera_rotmat
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_init_conversion.npz'))
+    R = torch.tensor(g['rotmat'])
+    pose = convert_hom_to_angle(R, 2).numpy()
+    assert pose.shape == g['pose'].shape
+    # axis-angle is unique up to fp32 conversion noise except at angle ~ pi (sign of the axis): compare as rotations
+    from scipy.spatial.transform import Rotation as Rot
+    def same_rot(a, b):
+        return np.abs(Rot.from_rotvec(a.reshape(-1, 3)).as_matrix() - Rot.from_rotvec(b.reshape(-1, 3)).as_matrix()).max()
+    assert same_rot(pose, g['pose']) < 2e-6
+    far_from_pi = np.linalg.norm(g['pose'].reshape(-1, 3), axis=1) < 3.0
+    assert np.abs(pose.reshape(-1, 3)[far_from_pi] - g['pose'].reshape(-1, 3)[far_from_pi]).max() < 2e-5
+    assert (pose.reshape(-1, 3)[0] == 0).all() and (g['pose'].reshape(-1, 3)[0] == 0).all()       # identity
+    before = R[:1].clone()
+    pw = world_init_from_camera_rotmat(R[:1], g['c2w']).numpy()
+    assert torch.equal(R[:1], before)                                  # input not modified
+    assert same_rot(pw, g['pose_world']) < 2e-6 and np.abs(pw[0, 3:] - pose[0, 3:]).max() < 1e-6   # only the root changes
+    assert np.abs(pw[0, :3] - pose[0, :3]).max() > 0.1
+    from oracle import ref_harness as rh
+    if rh.available():
+        rh.load_reference()
+        import utils.geometry as rg
+        live = rg.convert_hom_to_angle(R, 2, torch.device('cpu')).numpy()
+        assert np.array_equal(live, g['pose'])
+
+
+def test_load_openpose_on_the_reference_fixture():
+    """utils/io_utils.py:138-183 load_openpose on the reference's only real-data fixture (openpose/test.json, an OpenPose 1.3
+    output with one person and confidences > 1): same dict as the reference's own parser (committed golden)."""
+    from bodyfitting_b200.utils.io_utils import load_openpose
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+    got = load_openpose(os.path.join(here, 'openpose_test.json'))
+    want = np.load(os.path.join(here, 'reference_openpose_parse.npz'))
+    assert set(got) == set(want.files)
+    for k in want.files:
+        assert np.asarray(got[k]).shape == want[k].shape and np.allclose(np.asarray(got[k], dtype=np.float64), want[k], rtol=0, atol=1e-6), k
+
+
+def test_loader_accepts_official_model_file_layout(assets, tmp_path):
+    """Official SMPL / SMPL-X files carry no 'extra_vids' (smplx hard-codes the vertex ids of the 21 picked joints) and SMPL-X
+    stores 300 shape + 100 expression directions (expression = columns 300..309, not 10..19).  A dict / .npz laid out like
+    that must give exactly the tables of the synthetic layout, in the product loader AND in the oracle's restatement; the
+    gendered file is resolved from the data folder (a missing gender falls back to NEUTRAL with a warning, never silently)."""
+    import warnings
+    from bodyfitting_b200 import constants as K
+    from bodyfitting_b200.model import PreparedModel, load_model_data
+    from oracle import smplx_port as sp
+    for mt in ('smpl', 'smplx'):
+        d = dict(assets(mt))
+        assert list(d['extra_vids']) == K.EXTRA_VIDS[mt] == sp._EXTRA_VIDS[mt]      # product and oracle tables agree
+        off = {k: v for k, v in d.items() if k != 'extra_vids'}
+        if mt == 'smplx':
+            rng = np.random.RandomState(0)
+            sd = rng.standard_normal(d['shapedirs'].shape[:2] + (400,)).astype(np.float32)      # junk everywhere ...
+            sd[:, :, :10] = d['shapedirs'][:, :, :10]                                            # ... except the columns in use
+            sd[:, :, 300:310] = d['shapedirs'][:, :, 10:20]
+            off['shapedirs'] = sd
+        a = PreparedModel(mt, d, gmm=assets('gmm'), J_regressor_extra=assets('jx'), device='cpu', tensor_cores=False)
+        b = PreparedModel(mt, off, gmm=assets('gmm'), J_regressor_extra=assets('jx'), device='cpu', tensor_cores=False)
+        assert set(a._dev) == set(b._dev)
+        for k in a._dev:
+            assert torch.equal(a._dev[k], b._dev[k]), (mt, k)
+        # the oracle's restatement reads the same layout
+        la = sp.SMPLXLayer(d) if mt == 'smplx' else sp.SMPLLayer(d)
+        lb = sp.SMPLXLayer(off) if mt == 'smplx' else sp.SMPLLayer(off)
+        assert torch.equal(la.extra_joints_idxs, lb.extra_joints_idxs)
+        if mt == 'smplx':
+            assert torch.equal(la.expr_dirs, lb.expr_dirs)
+    # gender resolution in a reference-style data folder
+    folder = tmp_path / 'data' / 'smpl'
+    folder.mkdir(parents=True)
+    np.savez(str(folder / 'SMPL_NEUTRAL.npz'), **{k: v for k, v in assets('smpl').items() if k not in ('extra_vids', 'model_type')})
+    np.savez(str(folder / 'SMPL_FEMALE.npz'), **{k: (v * 2 if k == 'v_template' else v) for k, v in assets('smpl').items()
+                                                  if k not in ('extra_vids', 'model_type')})
+    fem = load_model_data(str(tmp_path / 'data'), 'smpl', 'female')
+    assert np.array_equal(fem['v_template'], assets('smpl')['v_template'] * 2)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter('always')
+        male = load_model_data(str(tmp_path / 'data'), 'smpl', 'male')
+    assert np.array_equal(male['v_template'], assets('smpl')['v_template']) and any('NEUTRAL' in str(x.message) for x in w)
