@@ -60,6 +60,7 @@ def parse():
     ap.add_argument('--no-dense', action='store_true')
     ap.add_argument('--no-extras', action='store_true', help='skip config4 / config5 / weak / GPU-eager legs')
     ap.add_argument('--cpu-frames', type=int, default=8)
+    ap.add_argument('--weak', action='store_true', help='at N>1 also time the weak-scaling run (--frames on every rank)')
     return ap.parse_args()
 
 
@@ -437,6 +438,11 @@ def run_ours(args):
             os.dup2(saved_fd, 1)
             os.close(saved_fd)
     host_threads(world)                                     # pinned staging / numpy of this rank may use its share of the cores
+    t_start = time.perf_counter()
+
+    def log(msg):
+        sys.stderr.write('[bench rank %d +%.1fs] %s\n' % (rank, time.perf_counter() - t_start, msg))
+        sys.stderr.flush()
     N = args.iters
     hbm_peak, peak_src = peaks()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
@@ -526,11 +532,88 @@ def run_ours(args):
     frames_done = F_total * args.steps
     value = frames_done / (ms_dev / 1e3)
     e2e = frames_done / (max(ms_e2e / 1e3, wall_e2e))
-    extras = {}
+    log('headline measured: %.0f frames/s device-resident, %.0f end to end' % (value, e2e))
 
-    # ---- config 4: temporal term, boundary rows by in-kernel NVLink stores -------------------------------------------
+    # ---- rank 0: per-kernel times, all-vertex operator, config 2 (single-GPU measurements; the other ranks wait) --------
+    line = None
+    if rank == 0:
+        plain = FitSession(pm, F, NV, N, graph=False)       # one batch on one stream: per-kernel times of one iteration
+        plain.load_inputs(pin['kp'].cuda(), sess.parts[0].cams if hasattr(sess, 'parts') else sess.cams, pin['init_pose'].cuda(),
+                          pin['init_betas'].cuda())
+        plain.run()
+        kern = kernel_breakdown(pm, plain, F, hbm_peak)
+        del plain
+        iter_ms = sum(k['ms'] * k['launches_per_iteration'] for k in kern)
+        dom = max(kern, key=lambda k: k['ms'] * k['launches_per_iteration'])
+        kp_mb = F * pm.K_used * NV * 12 / 1e6
+        state_mb = F * (2 * pm.Kp + 4 * pm.ld_act + 24 * pm.J + 4 * pm.NP) * 4 / 1e6
+        line = {
+            'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(args.warmup, 3), 'ms_per_step': ms_dev / args.steps, 'higher_is_better': True, 'scaling': args.scaling,
+            'vs_baseline': None, 'dtype': 'fp32', 'data': 'synthetic',
+            'config': {'workload': 'SMPL-X (10475 verts, 55 joints, random-init tensors) 8-view fit of ONE %d-frame sequence, '
+                                   '135 OpenPose-layout keypoints per view, %d Adam iterations (BASELINE config 3), frame-sharded over '
+                                   '%d GPU(s)' % (F_total, N, world),
+                       'frames_total': F_total, 'frames_per_gpu': F, 'views': NV, 'iters': N, 'active_vertices': int(pm.n_act),
+                       'design': 'fit loop runs blend+skinning on the %d vertices the keypoint loss can touch (exact: all other '
+                                 'vertex gradients are zero); all 10475 vertices are produced once for the returned mesh' % pm.n_act,
+                       'l2': 'L2 flushed (256 MB fill) before every timed step; per step %.0f MB of keypoints + %.0f MB of '
+                             'per-frame state per rank' % (kp_mb, state_mb),
+                       'parallelism': 'frames sharded, %d rank(s), no collective during the fit; final all_gather of parameters' % world,
+                       'streams': 'per GPU the shard runs as %d part(s), each ONE CUDA graph (N iterations + all-vertex forward) on '
+                                  'its own stream (bit-identical results); kernels[] / roofline are timed on one batch on one stream'
+                                  % (len(getattr(sess, 'ranges', [0])))},
+            'clocks': clocks,
+            'e2e': {'value': e2e, 'unit': 'frames/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
+                    'ms_per_step': 1e3 * max(ms_e2e / 1e3, wall_e2e) / args.steps,
+                    'api': 'bodyfitting_b200.smplify.smplify.SMPLify.__call__ (page-locked numpy in, numpy out incl. vertices)'},
+            'gpu_launches': int(launches),
+            'roofline': {'bound': 'hbm', 'kernel': dom['kernel'], 'achieved': dom['gbs'], 'peak': hbm_peak, 'unit': 'GB/s',
+                         'frac': dom['frac_hbm'], 'traffic': measured_traffic(dom['kernel'], F), 'peak_source': peak_src,
+                         'share_of_iteration': dom['ms'] / iter_ms},
+            'kernels': kern, 'iter_ms_sum_of_kernels': iter_ms,
+        }
+        if not args.no_dense:
+            try:
+                line['lbs_dense'] = dense_lbs_bench(0, hbm_peak)
+            except Exception as ex:                          # report, never hide
+                line['lbs_dense'] = {'error': repr(ex)}
+            try:
+                line['config2_fit'] = config2_fit_bench()
+            except Exception as ex:
+                line['config2_fit'] = {'error': repr(ex)}
+        log('rank-0 kernel / operator measurements done')
+
+    # ---- extra legs (configs 4 / 5, weak scaling).  They run under an emergency timer: if one of them blocks, rank 0 prints
+    # the line it already holds (marked) and every rank leaves -- the headline is never hostage to an extra leg.
+    extras = {}
+    printed = threading.Event()
+
+    def emit():
+        if printed.is_set():
+            return
+        printed.set()
+        if rank == 0:
+            line.update(extras)
+            sys.stdout.write(json.dumps(line) + '\n')
+            sys.stdout.flush()
+
+    def emergency():
+        import faulthandler
+        log('extra legs exceeded their time budget: printing what is there and leaving')
+        faulthandler.dump_traceback(file=sys.stderr)
+        extras['extras_timed_out'] = True
+        emit()
+        os._exit(0)
+    timer = None
     if not args.no_extras:
+        timer = threading.Timer(420.0 if world > 1 else 900.0, emergency)
+        timer.daemon = True
+        timer.start()
+        barrier()
+        # config 4: temporal term, boundary rows by in-kernel NVLink stores
         try:
+            log('config4: temporal fit, NVLink halo')
             link = HaloLink()
             fit_t, sess_t, _, _ = make_leg(F_total, lo, hi, temporal=TEMPORAL_W, halo=link)
             k4 = max(2, min(args.steps, 5))
@@ -540,10 +623,12 @@ def run_ours(args):
                   'frames_per_s': F_total * k4 / (ms_t / 1e3), 'ms_per_fit': ms_t / k4, 'graph': bool(sess_t.use_graph)}
             if world > 1:
                 # the same shards without the link (every shard its own sequence): the difference is what the halo costs
+                log('config4: same shards without the link')
                 fit_u, sess_u, _, _ = make_leg(F_total, lo, hi, temporal=TEMPORAL_W)
                 ms_u, _ = timed_region(lambda: run_sess(sess_u), k4, 2)
                 c4['ms_per_fit_without_halo'] = ms_u / k4
                 c4['halo_us_per_iteration'] = 1e3 * (ms_t - ms_u) / k4 / N
+                log('config4: host NCCL fallback')
                 fit_h, sess_h, _, _ = make_leg(F_total, lo, hi, temporal=TEMPORAL_W, halo_exchange=exchange_halo)
                 ms_h, _ = timed_region(lambda: run_sess(sess_h), 2, 1)
                 c4['host_nccl_fallback_ms_per_fit'] = ms_h / 2
@@ -552,8 +637,10 @@ def run_ours(args):
             extras['config4'] = c4
             del fit_t, sess_t
         except Exception as ex:                              # report, never hide
+            log('config4 failed: %r' % (ex,))
             extras['config4'] = {'error': repr(ex)}
         try:
+            log('config5: scan path')
             c5 = config5_bench(rank, world)
             if world > 1:
                 t = torch.tensor([c5['rank_wall_s']], device='cuda', dtype=torch.float64)
@@ -564,84 +651,46 @@ def run_ours(args):
             c5['subjects_per_s'] = c5['subjects'] / c5['wall_s_max_over_ranks']
             extras['config5'] = c5
         except Exception as ex:
+            log('config5 failed: %r' % (ex,))
             extras['config5'] = {'error': repr(ex)}
-        if world > 1 and args.scaling == 'strong':
+        if world > 1 and args.scaling == 'strong' and args.weak:
             try:                                             # weak scaling beside it: --frames frames on EVERY rank
+                log('weak leg: %d frames on every rank' % args.frames)
                 fit_w, sess_w, _, _ = make_leg(args.frames * world, rank * args.frames, (rank + 1) * args.frames)
+                log('weak leg: session ready')
                 ms_w, _ = timed_region(lambda: run_sess(sess_w), 3, 2)
                 extras['weak'] = {'frames_per_gpu': args.frames, 'value': args.frames * world * 3 / (ms_w / 1e3), 'unit': 'frames/s',
                                   'ms_per_step': ms_w / 3}
                 del fit_w, sess_w
             except Exception as ex:
+                log('weak leg failed: %r' % (ex,))
                 extras['weak'] = {'error': repr(ex)}
+        log('extra legs done')
 
+    if world > 1:
+        barrier()
+    if timer is not None:
+        timer.cancel()
     if rank != 0:
         if world > 1:
-            dist.barrier()
             dist.destroy_process_group()
         return
-    plain = FitSession(pm, F, NV, N, graph=False)           # one batch on one stream: per-kernel times of one iteration
-    plain.load_inputs(pin['kp'].cuda(), torch.zeros(NV, 12, device='cuda'), pin['init_pose'].cuda(), pin['init_betas'].cuda())
-    plain.cams.copy_(sess.parts[0].cams if hasattr(sess, 'parts') else sess.cams)
-    plain.run()
-    kern = kernel_breakdown(pm, plain, F, hbm_peak)
-    iter_ms = sum(k['ms'] * k['launches_per_iteration'] for k in kern)
-    dom = max(kern, key=lambda k: k['ms'] * k['launches_per_iteration'])
-    kp_mb = F * pm.K_used * NV * 12 / 1e6
-    state_mb = F * (2 * pm.Kp + 4 * pm.ld_act + 24 * pm.J + 4 * pm.NP) * 4 / 1e6
-    line = {
-        'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
-        'warmup': max(args.warmup, 3), 'ms_per_step': ms_dev / args.steps, 'higher_is_better': True, 'scaling': args.scaling,
-        'vs_baseline': None, 'dtype': 'fp32', 'data': 'synthetic',
-        'config': {'workload': 'SMPL-X (10475 verts, 55 joints, random-init tensors) 8-view fit of ONE %d-frame sequence, '
-                               '135 OpenPose-layout keypoints per view, %d Adam iterations (BASELINE config 3), frame-sharded over '
-                               '%d GPU(s)' % (F_total, N, world),
-                   'frames_total': F_total, 'frames_per_gpu': F, 'views': NV, 'iters': N, 'active_vertices': int(pm.n_act),
-                   'design': 'fit loop runs blend+skinning on the %d vertices the keypoint loss can touch (exact: all other '
-                             'vertex gradients are zero); all 10475 vertices are produced once for the returned mesh' % pm.n_act,
-                   'l2': 'L2 flushed (256 MB fill) before every timed step; per step %.0f MB of keypoints + %.0f MB of '
-                         'per-frame state per rank' % (kp_mb, state_mb),
-                   'parallelism': 'frames sharded, %d rank(s), no collective during the fit; final all_gather of parameters' % world,
-                   'streams': 'per GPU the shard runs as %d part(s), each ONE CUDA graph (N iterations + all-vertex forward) on '
-                              'its own stream (bit-identical results); kernels[] / roofline are timed on one batch on one stream'
-                              % (len(getattr(sess, 'ranges', [0])))},
-        'clocks': clocks,
-        'e2e': {'value': e2e, 'unit': 'frames/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
-                'ms_per_step': 1e3 * max(ms_e2e / 1e3, wall_e2e) / args.steps,
-                'api': 'bodyfitting_b200.smplify.smplify.SMPLify.__call__ (page-locked numpy in, numpy out incl. vertices)'},
-        'gpu_launches': int(launches),
-        'roofline': {'bound': 'hbm', 'kernel': dom['kernel'], 'achieved': dom['gbs'], 'peak': hbm_peak, 'unit': 'GB/s',
-                     'frac': dom['frac_hbm'], 'traffic': measured_traffic(dom['kernel'], F), 'peak_source': peak_src,
-                     'share_of_iteration': dom['ms'] / iter_ms},
-        'kernels': kern, 'iter_ms_sum_of_kernels': iter_ms,
-    }
-    line.update(extras)
-    if not args.no_dense:
-        try:
-            line['lbs_dense'] = dense_lbs_bench(0, hbm_peak)
-        except Exception as ex:                              # report, never hide
-            line['lbs_dense'] = {'error': repr(ex)}
-        try:
-            line['config2_fit'] = config2_fit_bench()
-        except Exception as ex:
-            line['config2_fit'] = {'error': repr(ex)}
     if world > 1:
-        dist.barrier()
         dist.destroy_process_group()
     if world == 1 and not args.no_extras:
         try:
             times, _ = cpu_reference_fit(2, N, warm=1, device='cuda')
-            line['gpu_eager_baseline'] = {'value': len(times) / sum(times), 'unit': 'frames/s', 'kind': 'port on device=cuda',
-                                          'sample': '2 single-frame SMPL-X 8-view %d-iteration fits after 1 warm-up: the reference\'s '
-                                                    'eager torch op sequence (oracle/fit_port.py) on the B200 -- launch-bound, not the target' % N}
+            extras['gpu_eager_baseline'] = {'value': len(times) / sum(times), 'unit': 'frames/s', 'kind': 'port on device=cuda',
+                                            'sample': '2 single-frame SMPL-X 8-view %d-iteration fits after 1 warm-up: the reference\'s '
+                                                      'eager torch op sequence (oracle/fit_port.py) on the B200 -- launch-bound, not the target' % N}
         except Exception as ex:
-            line['gpu_eager_baseline'] = {'error': repr(ex)}
+            extras['gpu_eager_baseline'] = {'error': repr(ex)}
     if world == 1 and not args.no_cpu_baseline:
         times, cores = cpu_reference_fit(args.cpu_frames, N, warm=1)
-        line['cpu_baseline'] = {'value': len(times) / sum(times), 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
-                                'sample': '%d single-frame SMPL-X 8-view %d-iteration fits after 1 warm-up (oracle/fit_port.py '
-                                          'FitPort.fit_frame, torch CPU fp32, %d host cpus)' % (len(times), N, os.cpu_count())}
-    print(json.dumps(line))
+        extras['cpu_baseline'] = {'value': len(times) / sum(times), 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
+                                  'sample': '%d single-frame SMPL-X 8-view %d-iteration fits after 1 warm-up (oracle/fit_port.py '
+                                            'FitPort.fit_frame, torch CPU fp32, %d host cpus)' % (len(times), N, os.cpu_count())}
+    emit()
 
 
 if __name__ == '__main__':

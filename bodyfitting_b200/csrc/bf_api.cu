@@ -3,6 +3,8 @@
 #include <math.h>
 #include <stdarg.h>
 #include <string.h>
+#include <stddef.h>
+#include <stdlib.h>
 
 #include "bf_common.cuh"
 #include "bf_pose.cuh"
@@ -506,25 +508,179 @@ int bf_fit_run(const BfModel* m, const BfFrames* f, int n_iters, void* stream) {
     return BF_OK;
 }
 
+// ---- model / frame-buffer construction for hosts that do not run Python ---------------------------------------------
+// A model blob is written once by bodyfitting_b200.model.PreparedModel.save_blob (the table building stays in one place);
+// loading = one file read, one cudaMalloc, one upload, pointer patching.
+struct BfModelOwned { BfModel m; void* dev; uint64_t magic; };
+#define BF_OWNED_MAGIC 0xB200F17B200F17ULL
+
+static void patch_ptrs(void** fields, int n, char* dev_base, int64_t total, int* bad) {
+    for (int i = 0; i < n; ++i) {
+        const uintptr_t v = (uintptr_t)fields[i];
+        if (v == 0) continue;
+        if ((int64_t)(v - 1) >= total) { *bad = 1; fields[i] = nullptr; continue; }
+        fields[i] = dev_base + (v - 1);
+    }
+}
+
+int bf_model_load_memory(const void* blob, int64_t nbytes, BfModel** out) {
+    BF_REQUIRE(blob && out && nbytes > 16 + (int64_t)sizeof(BfModel) + 8, "blob too small");
+    const char* p = (const char*)blob;
+    BF_REQUIRE(memcmp(p, "BFMODEL1", 8) == 0, "not a bodyfit model blob");
+    int32_t abi, sz;
+    memcpy(&abi, p + 8, 4); memcpy(&sz, p + 12, 4);
+    BF_REQUIRE(abi == BF_ABI_VERSION && sz == (int32_t)sizeof(BfModel), "model blob was written for another ABI version");
+    int64_t total;
+    memcpy(&total, p + 16 + sizeof(BfModel), 8);
+    BF_REQUIRE(total >= 0 && 16 + (int64_t)sizeof(BfModel) + 8 + total <= nbytes, "truncated model blob");
+    BfModelOwned* o = (BfModelOwned*)calloc(1, sizeof(BfModelOwned));
+    BF_REQUIRE(o, "out of host memory");
+    memcpy(&o->m, p + 16, sizeof(BfModel));
+    if (cudaMalloc(&o->dev, (size_t)(total > 0 ? total : 16)) != cudaSuccess) { free(o); bf_set_error("bf_model_load: cudaMalloc(%lld) failed", (long long)total); return BF_ECUDA; }
+    if (cudaMemcpy(o->dev, p + 16 + sizeof(BfModel) + 8, (size_t)total, cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaFree(o->dev); free(o); bf_set_error("bf_model_load: upload failed"); return BF_ECUDA;
+    }
+    int bad = 0;
+    // pointer fields: the leading block of BfModel, and of each BfVSet (layout checked against the header by static_assert)
+    patch_ptrs((void**)&o->m, (int)(offsetof(BfModel, full) / sizeof(void*)), (char*)o->dev, total, &bad);
+    patch_ptrs((void**)&o->m.full, (int)(offsetof(BfVSet, n) / sizeof(void*)), (char*)o->dev, total, &bad);
+    patch_ptrs((void**)&o->m.act, (int)(offsetof(BfVSet, n) / sizeof(void*)), (char*)o->dev, total, &bad);
+    if (bad) { cudaFree(o->dev); free(o); bf_set_error("bf_model_load: corrupt offsets"); return BF_EINVAL; }
+    o->magic = BF_OWNED_MAGIC;
+    *out = &o->m;
+    return BF_OK;
+}
+
+int bf_model_load(const char* path, BfModel** out) {
+    BF_REQUIRE(path && out, "bad arguments");
+    FILE* fp = fopen(path, "rb");
+    if (!fp) { bf_set_error("bf_model_load: cannot open %s", path); return BF_EINVAL; }
+    fseek(fp, 0, SEEK_END);
+    const long n = ftell(fp);
+    fseek(fp, 0, SEEK_SET);
+    void* buf = n > 0 ? malloc((size_t)n) : nullptr;
+    if (!buf || fread(buf, 1, (size_t)n, fp) != (size_t)n) { fclose(fp); free(buf); bf_set_error("bf_model_load: cannot read %s", path); return BF_EINVAL; }
+    fclose(fp);
+    const int rc = bf_model_load_memory(buf, n, out);
+    free(buf);
+    return rc;
+}
+
+int bf_model_destroy(BfModel* m) {
+    if (!m) return BF_OK;
+    BfModelOwned* o = (BfModelOwned*)m;                        // BfModel is the first member
+    BF_REQUIRE(o->magic == BF_OWNED_MAGIC, "model was not created by bf_model_load");
+    o->magic = 0;
+    cudaFree(o->dev);
+    free(o);
+    return BF_OK;
+}
+
+// frame buffers: one caller-owned device workspace carved into the BfFrames fields (what engine.FrameBuffers does with
+// torch tensors).  opts: 1 = all-vertex set, 2 = buffers of the backward / optimiser, 8 = temporal term.
+struct FrameCarver {
+    char* base; size_t off; bool dry;
+    void* take(size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return dry ? nullptr : (void*)(base + o); }
+};
+static void carve_frames(const BfModel* m, int B, int Nv, int opts, int n_trace, FrameCarver& c, BfFrames* f) {
+    const bool full = opts & 1, bwd = opts & 2, temporal = opts & 8;
+    const BfVSet* vs = full ? &m->full : &m->act;
+    const bool tc = vs->Bt_hi && vs->Bt_lo;
+    const size_t ld_v = full ? (size_t)3 * vs->n : (size_t)vs->ldn, F4 = sizeof(float);
+    memset(f, 0, sizeof(*f));
+    f->theta = (float*)c.take(F4 * B * m->NP);
+    f->pf = (float*)c.take(F4 * B * m->Kp);
+    if (tc) { f->pf_hi = (float*)c.take(F4 * B * m->Kp); f->pf_lo = (float*)c.take(F4 * B * m->Kp); }
+    f->A = (float*)c.take(F4 * B * m->J * 12);
+    f->Jtr = (float*)c.take(F4 * B * m->J * 3);
+    f->full_pose = (float*)c.take(F4 * B * m->J * 3);
+    f->yaw = (int32_t*)c.take(sizeof(int32_t) * B);
+    f->verts = (float*)c.take(F4 * B * ld_v);
+    f->joints = (float*)c.take(F4 * B * vs->K_out * 3);
+    f->loss = (float*)c.take(F4 * B);
+    if (Nv > 0) { f->kp = (const float*)c.take(F4 * B * m->K_used * Nv * 3); f->cams = (const float*)c.take(F4 * Nv * 12); }
+    if (bwd) {
+        f->grad = (float*)c.take(F4 * B * m->NP);
+        f->adam_m = (float*)c.take(F4 * B * m->NP);
+        f->adam_v = (float*)c.take(F4 * B * m->NP);
+        f->dpf = (float*)c.take(F4 * B * m->Kp);
+        f->dA = (float*)c.take(F4 * B * m->J * 12);
+        f->dJtr = (float*)c.take(F4 * B * m->J * 3);
+        f->vposed = (float*)c.take(F4 * B * ld_v);
+        f->dverts = (float*)c.take(F4 * B * ld_v);
+        f->dvp = (float*)c.take(F4 * B * ld_v);
+        if (tc) {
+            f->dvp_hi = (float*)c.take(F4 * B * vs->ldn);
+            f->dvp_lo = (float*)c.take(F4 * B * vs->ldn);
+            const int nsplit = (vs->ldn / TC_BK + 2048 / TC_BK - 1) / (2048 / TC_BK);
+            if (nsplit > 1) { f->ws_floats = (int64_t)nsplit * B * m->Kp; f->ws = (float*)c.take(F4 * (size_t)f->ws_floats); }
+        }
+        f->loss_terms = (float*)c.take(F4 * B * 4);
+        if (tc && m->n_gmm > 0 && (m->n_gmm * GM_LD) % TC_BN1 == 0) f->gmm_ws = (float*)c.take(F4 * B * ((size_t)m->n_gmm * GM_LD + 2 * GM_KG));
+        f->gmm_grad = (float*)c.take(F4 * B * BF_GMM_D);
+        f->gmm_loss = (float*)c.take(F4 * B);
+        f->fwd_state = (float*)c.take(F4 * B * 24 * m->J);
+        if (tc && !full && vs->lv_blk && vs->n_pad <= 512) f->blk_mask = (uint32_t*)c.take(sizeof(uint32_t) * 2 * ((B + 127) / 128));
+        if (temporal) { f->tgrad = (float*)c.take(F4 * B * m->NP); f->tloss = (float*)c.take(F4 * B); }
+    }
+    if (n_trace > 0) f->trace = (float*)c.take(F4 * (size_t)n_trace * B);
+    f->B = B; f->Nv = Nv; f->ld_v = (int)ld_v; f->iter = 0;
+    f->flags = tc ? BF_F_TC : 0;
+    // the reference's hard-coded hyper-parameters: smplify.py:160,167-174 (lr 0.1 for transl / scale, 1e-2 otherwise, Adam
+    // defaults), loss.py:139-141 (sigma 100, prior weights 4.78 / 15.2 / 5)
+    f->lr_ts = 0.1; f->lr = 1e-2; f->beta1 = 0.9; f->beta2 = 0.999; f->eps = 1e-8;
+    f->imsize = 512.f; f->constant_scale = 0.3f; f->sigma = 100.f; f->w_pose = 4.78f; f->w_angle = 15.2f; f->w_shape = 5.f;
+}
+
+int64_t bf_workspace_bytes(const BfModel* m, int B, int Nv, int opts, int n_trace) {
+    if (!m || B <= 0 || Nv < 0 || n_trace < 0) { bf_set_error("bf_workspace_bytes: bad arguments"); return BF_EINVAL; }
+    FrameCarver c{nullptr, 0, true};
+    BfFrames f;
+    carve_frames(m, B, Nv, opts, n_trace, c, &f);
+    return (int64_t)c.off;
+}
+
+int bf_frames_bind(const BfModel* m, int B, int Nv, int opts, int n_trace, void* workspace, int64_t bytes, BfFrames* out, void* stream) {
+    BF_REQUIRE(m && out && workspace && B > 0 && Nv >= 0 && n_trace >= 0, "bad arguments");
+    BF_REQUIRE(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
+    const int64_t need = bf_workspace_bytes(m, B, Nv, opts, n_trace);
+    BF_REQUIRE(bytes >= need, "workspace smaller than bf_workspace_bytes()");
+    if (cudaMemsetAsync(workspace, 0, (size_t)need, (cudaStream_t)stream) != cudaSuccess) { bf_set_error("bf_frames_bind: memset failed"); return BF_ECUDA; }
+    FrameCarver c{(char*)workspace, 0, false};
+    carve_frames(m, B, Nv, opts, n_trace, c, out);
+    return BF_OK;
+}
+
 // ---- input packing ------------------------------------------------------------------------------------------
-int bf_pack_keypoints(const float* kp_raw, float* kp_packed, int B, int Nv, int K, int hand_face, void* stream) {
+int bf_pack_keypoints(const float* kp_raw, float* kp_packed, int B, int Nv, int K, int hand_face, const int32_t* src_index,
+                      void* stream) {
     BF_NVTX();
     BF_REQUIRE(kp_raw && kp_packed && B > 0 && Nv > 0 && K > 0, "bad arguments");
     BF_REQUIRE(!hand_face || K > 67, "hand / face groups need the SMPL-X joint layout (K > 67)");
     const size_t smem = sizeof(float) * (((size_t)Nv * K * 3 + 3) / 4 * 4 + (size_t)Nv * PK_MAXG);
     BF_REQUIRE(smem <= 48 * 1024, "Nv * K too large for one frame per CTA");
-    k_pack_keypoints<<<B, 256, smem, (cudaStream_t)stream>>>(kp_raw, kp_packed, B, Nv, K, hand_face);
+    k_pack_keypoints<<<B, 256, smem, (cudaStream_t)stream>>>(kp_raw, kp_packed, B, Nv, K, hand_face, src_index);
     BF_LAUNCH_CHECK();
     return BF_OK;
 }
 
-int bf_init_theta(const BfModel* m, const float* poses, int ld_poses, const float* betas, float* theta, int B, void* stream) {
+int bf_init_theta(const BfModel* m, const float* poses, int ld_poses, const float* betas, float* theta, int B,
+                  const int32_t* src_index, void* stream) {
     BF_NVTX();
     BF_REQUIRE(m && poses && betas && theta && B > 0, "bad arguments");
     const int nb = theta_layout(m->is_smplx).nbody;
     BF_REQUIRE(ld_poses >= 3 + nb, "poses need global_orient + body_pose columns");
     const size_t n = (size_t)B * m->NP;
-    k_init_theta<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(poses, ld_poses, betas, theta, B, m->NP, nb);
+    k_init_theta<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(poses, ld_poses, betas, theta, B, m->NP, nb, src_index);
+    BF_LAUNCH_CHECK();
+    return BF_OK;
+}
+
+int bf_scatter_rows(const float* src, const int32_t* index, float* dst, int rows, int cols, void* stream) {
+    BF_NVTX();
+    BF_REQUIRE(src && dst && rows > 0 && cols > 0, "bad arguments");
+    const size_t n = (size_t)rows * cols;
+    k_scatter_rows<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, index, dst, rows, cols);
     BF_LAUNCH_CHECK();
     return BF_OK;
 }

@@ -94,17 +94,20 @@ struct Pipe {
     __device__ __forceinline__ uint8_t* stage(int s) const { return stage_base + (size_t)s * stage_bytes(); }
 };
 
+// blk_mask != ~0u (needs TC_BK == 16): the reduction runs only over the 16-vertex blocks (3 chunks of 16 coordinates each)
+// whose bit is set -- the other columns of the A operand are exactly zero for every row of this tile
 template <int NS>
 __device__ __forceinline__ void producer(const Pipe& p, const CUtensorMap* mA_hi, const CUtensorMap* mA_lo,
                                          const CUtensorMap* mB_hi, const CUtensorMap* mB_lo, int num_k, int rowA, int rowB,
-                                         int kc_begin = 0) {
+                                         int kc_begin = 0, uint32_t blk_mask = 0xFFFFFFFFu) {
     for (int kc = 0; kc < num_k; ++kc) {
         const int s = kc % NS;
         const uint32_t ph = (kc / NS) & 1;
         mbar_wait(&p.empty[s], ph ^ 1);
         mbar_expect_tx(&p.full[s], p.stage_bytes());
         uint8_t* st = p.stage(s);
-        const int c0 = (kc_begin + kc) * TC_BK;
+        const int chunk = blk_mask == 0xFFFFFFFFu ? kc_begin + kc : 3 * (int)__fns(blk_mask, 0, kc / 3 + 1) + kc % 3;
+        const int c0 = chunk * TC_BK;
         tma_load_2d(st, mA_hi, &p.full[s], c0, rowA);
         tma_load_2d(st + p.a_bytes, mA_lo, &p.full[s], c0, rowA);
         tma_load_2d(st + 2 * p.a_bytes, mB_hi, &p.full[s], c0, rowB);
@@ -326,6 +329,159 @@ k_blend_fwd_tc(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant_
     }
 }
 
+// Block-masked forward blend of the active set: per 128-frame tile only the 16-vertex blocks (48 coordinates) named by the
+// tile's mask are computed (BfFrames.blk_mask: OR over the tile's frames of the blocks their contour row needs; with the
+// frames of a batch sorted by row that is ~16 of 30 blocks).  A "virtual" N tile gathers up to four such blocks: the B operand
+// stage is assembled from four 48-row TMA boxes taken at the blocks' rows of the blend matrix (the 64-byte swizzle repeats
+// every 8 rows = 512 B, so boxes placed 48 rows apart form the same layout as one 192-row box), the MMA runs with
+// N = 48 x blocks, and the epilogue stores each 48-column group at its block's own column offset of v_posed.  Columns of
+// blocks outside the mask are not written -- no frame of the tile reads them.
+// Slot order: virtual tile index major, frame tile minor -- every frame tile has at least three virtual tiles (the static
+// blocks), so consecutive slots are almost all real and the static round-robin over the CTAs stays balanced.
+#define TC_BLK_ROWS 48
+#define TC_MAX_VT 8
+__global__ void __launch_bounds__(64 + 32 * TC_EPI_WARPS, 1)
+k_blend_fwd_tc_blk(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CUtensorMap mA_lo,
+                   const __grid_constant__ CUtensorMap mB_hi, const __grid_constant__ CUtensorMap mB_lo,
+                   int n_verts, int Kp, float* __restrict__ vposed, int B, int ld_v, int n_tiles_m,
+                   const uint32_t* __restrict__ blk_mask, int n_blocks) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    tc::Pipe p;
+    p.a_bytes = TC_BM * TC_ROWB;
+    p.b_bytes = TC_BN1 * TC_ROWB;
+    p.stage_base = base;
+    float* St = reinterpret_cast<float*>(base + TC_STAGES * p.stage_bytes());
+    uint64_t* bars = reinterpret_cast<uint64_t*>(St + TC_EPI_WARPS * TC_ST_FLOATS);
+    p.full = bars; p.empty = bars + TC_STAGES; p.tmem_full = bars + 2 * TC_STAGES;
+    uint64_t* tmem_empty = bars + 2 * TC_STAGES + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_k = Kp / TC_BK;
+    const int n_slots = n_tiles_m * TC_MAX_VT;
+    const uint32_t valid = n_blocks < 32 ? (1u << n_blocks) - 1u : 0xFFFFFFFFu;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) { tc::mbar_init(&p.full[s], 1); tc::mbar_init(&p.empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { tc::mbar_init(&p.tmem_full[s], 1); tc::mbar_init(&tmem_empty[s], TC_EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(tmem_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int it = 0;
+            for (int t = blockIdx.x; t < n_slots; t += gridDim.x) {
+                const int vt = t / n_tiles_m, fm = t - vt * n_tiles_m;
+                const uint32_t mask = __ldg(blk_mask + fm) & valid;
+                const int nb = min(4, __popc(mask) - 4 * vt);
+                if (nb <= 0) continue;
+                int rows[4];
+                for (int j = 0; j < nb; ++j) rows[j] = TC_BLK_ROWS * (int)__fns(mask, 0, 4 * vt + j + 1);
+                const int b0 = fm * TC_BM;
+                const uint32_t bytes = 2 * p.a_bytes + 2u * (uint32_t)nb * TC_BLK_ROWS * TC_ROWB;
+                for (int kc = 0; kc < num_k; ++kc, ++it) {
+                    const int s = it % TC_STAGES;
+                    const uint32_t ph = (it / TC_STAGES) & 1;
+                    tc::mbar_wait(&p.empty[s], ph ^ 1);
+                    tc::mbar_expect_tx(&p.full[s], bytes);
+                    uint8_t* st = p.stage(s);
+                    tc::tma_load_2d(st, &mA_hi, &p.full[s], kc * TC_BK, b0);
+                    tc::tma_load_2d(st + p.a_bytes, &mA_lo, &p.full[s], kc * TC_BK, b0);
+                    for (int j = 0; j < nb; ++j) {
+                        tc::tma_load_2d(st + 2 * p.a_bytes + j * TC_BLK_ROWS * TC_ROWB, &mB_hi, &p.full[s], kc * TC_BK, rows[j]);
+                        tc::tma_load_2d(st + 2 * p.a_bytes + p.b_bytes + j * TC_BLK_ROWS * TC_ROWB, &mB_lo, &p.full[s], kc * TC_BK, rows[j]);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            int it = 0, i = 0;
+            for (int t = blockIdx.x; t < n_slots; t += gridDim.x) {
+                const int vt = t / n_tiles_m, fm = t - vt * n_tiles_m;
+                const uint32_t mask = __ldg(blk_mask + fm) & valid;
+                const int nb = min(4, __popc(mask) - 4 * vt);
+                if (nb <= 0) continue;
+                const uint32_t idesc = tc::make_idesc_tf32(TC_BM, TC_BLK_ROWS * nb);
+                const int buf = i & 1;
+                tc::mbar_wait(&tmem_empty[buf], ((i >> 1) & 1) ^ 1);
+                tc::tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(buf * TC_BN1);
+                for (int kc = 0; kc < num_k; ++kc, ++it) {
+                    const int s = it % TC_STAGES;
+                    const uint32_t ph = (it / TC_STAGES) & 1;
+                    tc::mbar_wait(&p.full[s], ph);
+                    tc::tc_fence_after();
+                    uint8_t* st = p.stage(s);
+                    const uint64_t a_hi = tc::make_desc(st), a_lo = tc::make_desc(st + p.a_bytes);
+                    const uint64_t b_hi = tc::make_desc(st + 2 * p.a_bytes), b_lo = tc::make_desc(st + 2 * p.a_bytes + p.b_bytes);
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 8; ++k) {
+                        const uint64_t o = (uint64_t)(2 * k);
+                        tc::umma_tf32(tmem_d, a_hi + o, b_hi + o, idesc, (kc | k) ? 1u : 0u);
+                        tc::umma_tf32(tmem_d, a_lo + o, b_hi + o, idesc, 1u);
+                        tc::umma_tf32(tmem_d, a_hi + o, b_lo + o, idesc, 1u);
+                    }
+                    tc::umma_commit(&p.empty[s]);
+                }
+                tc::umma_commit(&p.tmem_full[buf]);
+                ++i;
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int h = (warp - 2) >> 2;
+        float* st = St + (warp - 2) * TC_ST_FLOATS;
+        int i = 0;
+        for (int t = blockIdx.x; t < n_slots; t += gridDim.x) {
+            const int vt = t / n_tiles_m, fm = t - vt * n_tiles_m;
+            const uint32_t mask = __ldg(blk_mask + fm) & valid;
+            const int nb = min(4, __popc(mask) - 4 * vt);
+            if (nb <= 0) continue;                              // warp-uniform, and the same decision in all three roles
+            const int buf = i & 1;
+            const int b0 = fm * TC_BM + 32 * q;
+            const int nrows = min(32, B - b0);
+            tc::mbar_wait(&p.tmem_full[buf], (i >> 1) & 1);
+            tc::tc_fence_after();
+            const uint32_t tmem_d = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * TC_BN1 + h * 96);
+#pragma unroll 1
+            for (int pass = 0; pass < 2; ++pass) {
+                const int j = 2 * h + pass;                     // which of the tile's (up to) four blocks
+                uint32_t r[48];
+                if (j < nb) tc::tmem_ld48(tmem_d + (uint32_t)(pass * 48), r);
+                if (pass == 1) {
+                    tc::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(&tmem_empty[buf])) : "memory");
+                }
+                if (j >= nb || nrows <= 0) continue;
+                const int vbase = 16 * (int)__fns(mask, 0, 4 * vt + j + 1);
+                if (vbase >= n_verts) continue;
+#pragma unroll
+                for (int c = 0; c < 48; ++c) st[c * TC_ST_LD + lane] = __uint_as_float(r[c]);
+                __syncwarp();
+                tc::store_rows48(st, vposed + (size_t)b0 * ld_v + 3 * vbase, (size_t)ld_v, 3 * min(16, n_verts - vbase), nrows, lane);
+                __syncwarp();
+            }
+            ++i;
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+}
+
 // dpf[b, k0 + c] = sum_n dvp[b, n] Bm[k0 + c, n]; BN = columns of this CTA (multiple of 16, <= 256); NS = pipeline stages
 // (4: one CTA per SM; 2 with BN <= 128: 67 KB and 128 TMEM columns per CTA, so three CTAs share an SM and a grid a little
 // larger than the SM count does not leave a nearly empty second wave)
@@ -335,7 +491,8 @@ __global__ void __launch_bounds__(192, 1) k_blend_bwd_tc(const __grid_constant__
                                                          const __grid_constant__ CUtensorMap mB_hi,
                                                          const __grid_constant__ CUtensorMap mB_lo,
                                                          int BN, int num_k_total, int cps, int Kp,
-                                                         float* __restrict__ out, size_t split_stride, int B) {
+                                                         float* __restrict__ out, size_t split_stride, int B,
+                                                         const uint32_t* __restrict__ blk_mask) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     tc::Pipe p;
@@ -353,7 +510,13 @@ __global__ void __launch_bounds__(192, 1) k_blend_bwd_tc(const __grid_constant__
     // split-K: this CTA reduces K chunks [kc_begin, kc_begin + num_k) and writes its own partial
     // (the tensor-core accumulator truncates, so long reductions are cut and summed in fp32 RN)
     const int kc_begin = blockIdx.z * cps;
-    const int num_k = min(cps, num_k_total - kc_begin);
+    uint32_t mask = 0xFFFFFFFFu;
+    if (blk_mask) {                                        // masked reduction (single run only): 3 chunks per set block
+        mask = blk_mask[blockIdx.y];
+        const int nblk = num_k_total / 3;
+        if (nblk < 32) mask &= (1u << nblk) - 1u;
+    }
+    const int num_k = mask == 0xFFFFFFFFu ? min(cps, num_k_total - kc_begin) : 3 * __popc(mask);
     float* dpf = out + (size_t)blockIdx.z * split_stride;
 
     if (threadIdx.x == 0) {
@@ -371,17 +534,23 @@ __global__ void __launch_bounds__(192, 1) k_blend_bwd_tc(const __grid_constant__
     const uint32_t tmem_d = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) tc::producer<NS>(p, &mA_hi, &mA_lo, &mB_hi, &mB_lo, num_k, b0, k0, kc_begin);
+        if (lane == 0 && num_k > 0) tc::producer<NS>(p, &mA_hi, &mA_lo, &mB_hi, &mB_lo, num_k, b0, k0, kc_begin, mask);
     } else if (warp == 1) {
-        if (lane == 0) tc::mma_issuer<NS>(p, num_k, tmem_d, tc::make_idesc_tf32(TC_BM, BN));
+        if (lane == 0 && num_k > 0) tc::mma_issuer<NS>(p, num_k, tmem_d, tc::make_idesc_tf32(TC_BM, BN));
     } else {
-        tc::mbar_wait(p.tmem_full, 0);
-        tc::tc_fence_after();
+        if (num_k > 0) {
+            tc::mbar_wait(p.tmem_full, 0);
+            tc::tc_fence_after();
+        }
         const int q = warp & 3;
         const int b = b0 + 32 * q + lane;
         for (int c = 0; c < BN; c += 32) {
             uint32_t r[32];
-            tc::tmem_ld32(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)c, r);
+            if (num_k > 0) tc::tmem_ld32(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)c, r);
+            else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) r[i] = 0u;                        // empty mask: the gradient rows are zero
+            }
             if (b < B) {
                 float4* o = reinterpret_cast<float4*>(dpf + (size_t)b * Kp + k0 + c);
                 const int nv = (BN - c >= 32) ? 8 : (BN - c) / 4;
@@ -474,6 +643,12 @@ static int bf_make_map_uncached(CUtensorMap* m, const float* base, uint64_t rows
     return BF_OK;
 }
 
+// BODYFIT_BLKMASK=0: the GEMMs touch every block of the active set (A/B timing, debugging)
+static inline bool bf_blk_mask_on() {
+    static int env = -1;
+    if (env < 0) { const char* e = getenv("BODYFIT_BLKMASK"); env = e ? atoi(e) : 1; }
+    return env != 0;
+}
 static inline bool bf_tc_ready_fwd(const BfVSet* vs, const BfFrames* f) {
     return (f->flags & BF_F_TC) && vs->Bt_hi && vs->Bt_lo && f->pf_hi && f->pf_lo;
 }
@@ -504,10 +679,39 @@ static int bf_gemm_forward_tc(const float* a_hi_p, const float* a_lo_p, const fl
     return BF_OK;
 }
 
+// block-masked forward of the active set (k_blend_fwd_tc_blk); returns 1 when not applicable
+static int bf_gemm_forward_tc_blk(const float* a_hi_p, const float* a_lo_p, const float* bt_hi_p, const float* bt_lo_p, int B, int Kp,
+                                  int ldn, int n_verts, float* dst, int ld_dst, const uint32_t* blk_mask, cudaStream_t s) {
+    const int n_blocks = (ldn / 3 + 15) / 16;
+    if (TC_BK != 16 || Kp % TC_BK != 0 || ldn % (3 * 16) != 0 || n_blocks > 32 || n_blocks > 4 * TC_MAX_VT) return 1;
+    CUtensorMap a_hi, a_lo, b_hi, b_lo;
+    int rc;
+    if ((rc = bf_make_map(&a_hi, a_hi_p, B, Kp, Kp, TC_BM))) return rc;
+    if ((rc = bf_make_map(&a_lo, a_lo_p, B, Kp, Kp, TC_BM))) return rc;
+    if ((rc = bf_make_map(&b_hi, bt_hi_p, ldn, Kp, Kp, TC_BLK_ROWS))) return rc;
+    if ((rc = bf_make_map(&b_lo, bt_lo_p, ldn, Kp, Kp, TC_BLK_ROWS))) return rc;
+    const size_t smem = 1024 + TC_STAGES * (2 * TC_BM * TC_ROWB + 2 * TC_BN1 * TC_ROWB) + TC_EPI_WARPS * TC_ST_FLOATS * 4 + 128;
+    static size_t attr[BF_MAXDEV] = {0};
+    if ((rc = bf_ensure_smem(k_blend_fwd_tc_blk, smem, attr, "k_blend_fwd_tc_blk"))) return rc;
+    const int num_sms = bf_num_sms();
+    const int tm = (B + TC_BM - 1) / TC_BM;
+    // at most ceil(n_blocks / 4) virtual tiles per frame tile are real; one CTA per SM, fewer when there is less work
+    const int real_max = tm * ((n_blocks + 3) / 4);
+    const int grid = real_max < num_sms ? real_max : num_sms;
+    k_blend_fwd_tc_blk<<<grid, 64 + 32 * TC_EPI_WARPS, smem, s>>>(a_hi, a_lo, b_hi, b_lo, n_verts, Kp, dst, B, ld_dst, tm, blk_mask, n_blocks);
+    BF_LAUNCH_CHECK();
+    return BF_OK;
+}
+
 // v_posed[B, ld_v] = pf @ Bm (dst = f->vposed, or any [B, ld_v] buffer)
 static int bf_gemm_forward_tc2(const float* a_hi_p, const float* a_lo_p, const float* bt_hi_p, const float* bt_lo_p, int B, int Kp,
                                int ldn, int n_verts, float* dst, int ld_dst, cudaStream_t s);      // bf_blend_tc2.cuh
 static int bf_blend_forward_tc(const BfModel* m, const BfVSet* vs, const BfFrames* f, float* dst, cudaStream_t s) {
+    if (bf_blk_mask_on() && f->blk_mask && vs->lv_blk && vs == &m->act) {
+        const int rcb = bf_gemm_forward_tc_blk(f->pf_hi, f->pf_lo, vs->Bt_hi, vs->Bt_lo, f->B, m->Kp, vs->ldn, vs->n, dst, f->ld_v,
+                                               f->blk_mask + (size_t)(f->iter & 1) * ((f->B + 127) / 128), s);
+        if (rcb != 1) return rcb;
+    }
     const int rc2 = bf_gemm_forward_tc2(f->pf_hi, f->pf_lo, vs->Bt_hi, vs->Bt_lo, f->B, m->Kp, vs->ldn, vs->n, dst, f->ld_v, s);
     if (rc2 != 1) return rc2;                              // CTA-pair kernel ran (or failed loudly); 1 = not applicable
     return bf_gemm_forward_tc(f->pf_hi, f->pf_lo, vs->Bt_hi, vs->Bt_lo, f->B, m->Kp, vs->ldn, vs->n, dst, f->ld_v, s);
@@ -585,9 +789,12 @@ static int bf_blend_backward_tc(const BfModel* m, const BfVSet* vs, const BfFram
         }
     }
     const dim3 grid(m->Kp / BN, (f->B + TC_BM - 1) / TC_BM, S);
-    if (NS == 2) k_blend_bwd_tc<2><<<grid, 192, smem, s>>>(a_hi, a_lo, b_hi, b_lo, BN, num_k, cps, m->Kp, S > 1 ? f->ws : f->dpf, stride, f->B);
-    else if (NS == 8) k_blend_bwd_tc<8><<<grid, 192, smem, s>>>(a_hi, a_lo, b_hi, b_lo, BN, num_k, cps, m->Kp, S > 1 ? f->ws : f->dpf, stride, f->B);
-    else k_blend_bwd_tc<TC_STAGES><<<grid, 192, smem, s>>>(a_hi, a_lo, b_hi, b_lo, BN, num_k, cps, m->Kp, S > 1 ? f->ws : f->dpf, stride, f->B);
+    // block mask of the active set (BfFrames.blk_mask, buffer of this iteration's parity): single-run reductions only
+    const uint32_t* mask = (bf_blk_mask_on() && f->blk_mask && vs->lv_blk && S == 1 && TC_BK == 16 && vs->n_pad <= 512 && num_k % 3 == 0)
+                               ? f->blk_mask + (size_t)(f->iter & 1) * ((f->B + 127) / 128) : nullptr;
+    if (NS == 2) k_blend_bwd_tc<2><<<grid, 192, smem, s>>>(a_hi, a_lo, b_hi, b_lo, BN, num_k, cps, m->Kp, S > 1 ? f->ws : f->dpf, stride, f->B, mask);
+    else if (NS == 8) k_blend_bwd_tc<8><<<grid, 192, smem, s>>>(a_hi, a_lo, b_hi, b_lo, BN, num_k, cps, m->Kp, S > 1 ? f->ws : f->dpf, stride, f->B, mask);
+    else k_blend_bwd_tc<TC_STAGES><<<grid, 192, smem, s>>>(a_hi, a_lo, b_hi, b_lo, BN, num_k, cps, m->Kp, S > 1 ? f->ws : f->dpf, stride, f->B, mask);
     BF_LAUNCH_CHECK();
     if (S > 1) {
         const size_t n = stride;

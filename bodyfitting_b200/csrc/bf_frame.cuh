@@ -132,14 +132,19 @@ __global__ void __launch_bounds__(FR_THREADS, 5) k_frame_loss_bwd(BfModel m, BfV
         }
     }
     // clear this frame's d(v_posed) rows: only live vertices are written below (a vertex live on another yaw row in an
-    // earlier iteration must read as zero in the blend backward GEMM)
+    // earlier iteration must read as zero in the blend backward GEMM).  With a block mask (BfFrames.blk_mask) the GEMM only
+    // reads the 16-vertex blocks (12 float4 each) its 128-frame tile needs, so only those are cleared.
     const bool split = f.dvp_hi != nullptr;
     {
+        const int ntile = (f.B + 127) >> 7;
+        const uint32_t mask = f.blk_mask ? f.blk_mask[(size_t)(f.iter & 1) * ntile + (b >> 7)] : 0xFFFFFFFFu;
+        if (f.blk_mask && t == 0 && (b & 127) == 0) f.blk_mask[(size_t)((f.iter + 1) & 1) * ntile + (b >> 7)] = 0u;   // next iteration's mask
         const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
         if (split) {
             float4* oh = reinterpret_cast<float4*>(f.dvp_hi + (size_t)b * vs.ldn);
             float4* ol = reinterpret_cast<float4*>(f.dvp_lo + (size_t)b * vs.ldn);
-            for (int i = t; i < n4; i += FR_THREADS) { oh[i] = z; ol[i] = z; }
+            for (int i = t; i < n4; i += FR_THREADS)
+                if ((mask >> min(i / 12, 31)) & 1u) { oh[i] = z; ol[i] = z; }
         } else {
             float4* o = reinterpret_cast<float4*>(f.dvp + (size_t)b * f.ld_v);
             for (int i = t; i < n4; i += FR_THREADS) o[i] = z;

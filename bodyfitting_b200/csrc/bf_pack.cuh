@@ -66,13 +66,14 @@ __global__ void __launch_bounds__(64) k_halo_begin(BfFrames f, int NP, int n_ite
 }
 
 #define PK_MAXG 4
+// src_index (optional): output frame b is input frame src_index[b] (frames sorted by contour row, engine.FitSession)
 __global__ void __launch_bounds__(256) k_pack_keypoints(const float* __restrict__ src, float* __restrict__ dst, int B, int Nv, int K,
-                                                        int hand_face) {
+                                                        int hand_face, const int32_t* __restrict__ src_index) {
     extern __shared__ float pk_sm[];                      // [Nv*K*3] the frame's detections + [Nv*PK_MAXG] group weights
     const int b = blockIdx.x, n = Nv * K * 3;
     float* raw = pk_sm;
     float* gw = pk_sm + ((n + 3) & ~3);
-    const float* s = src + (size_t)b * n;
+    const float* s = src + (size_t)(src_index ? src_index[b] : b) * n;
     for (int i = threadIdx.x; i < n; i += blockDim.x) raw[i] = s[i];
     __syncthreads();
     // hand / face groups of the SMPL-X joint order (models/utils.py:74-94): [25,46) left hand, [46,67) right hand, [67,K) face
@@ -97,13 +98,24 @@ __global__ void __launch_bounds__(256) k_pack_keypoints(const float* __restrict_
 }
 
 __global__ void __launch_bounds__(256) k_init_theta(const float* __restrict__ poses, int ldp, const float* __restrict__ betas,
-                                                    float* __restrict__ theta, int B, int NP, int nbody) {
+                                                    float* __restrict__ theta, int B, int NP, int nbody,
+                                                    const int32_t* __restrict__ src_index) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)B * NP) return;
-    const int b = (int)(i / NP), c = (int)(i % NP);
+    const int c = (int)(i % NP);
+    const int b = src_index ? src_index[i / NP] : (int)(i / NP);
     float v = 0.f;
     if (c == 3) v = 1.0f;                                                      // body_scale
     else if (c >= 4 && c < 7 + nbody) v = poses[(size_t)b * ldp + (c - 4)];    // global_orient | body_pose
     else if (c >= 7 + nbody && c < 17 + nbody) v = betas[(size_t)b * 10 + (c - 7 - nbody)];
     theta[i] = v;
+}
+
+// dst[index[r], :] = src[r, :] (index == NULL: plain copy): results of a row-sorted batch back into the caller's frame order
+__global__ void __launch_bounds__(256) k_scatter_rows(const float* __restrict__ src, const int32_t* __restrict__ index,
+                                                      float* __restrict__ dst, int rows, int cols) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)rows * cols) return;
+    const int r = (int)(i / cols), c = (int)(i % cols);
+    dst[(size_t)(index ? index[r] : r) * cols + c] = src[i];
 }

@@ -135,7 +135,8 @@ __device__ __forceinline__ void pose_forward_from_smem(const BfModel& m, PoseSme
 
 // forward outputs of frame b from the state in S: GEMM A operand (+ 3xTF32 split), joint transforms,
 // posed joints, full pose, contour-landmark row
-__device__ __forceinline__ void pose_write_outputs(const BfModel& m, const BfFrames& f, PoseSmem& S, int b, int lane) {
+// mask_par: parity of the iteration that will consume these outputs (selects the block-mask buffer, BfFrames.blk_mask)
+__device__ __forceinline__ void pose_write_outputs(const BfModel& m, const BfFrames& f, PoseSmem& S, int b, int lane, int mask_par) {
     const int J = m.J;
     if (f.fwd_state) {                       // [fp 3J | R 9J | Jr 3J | GR 9J] for the backward pass
         float* st = f.fwd_state + (size_t)b * 24 * J;
@@ -196,6 +197,9 @@ __device__ __forceinline__ void pose_write_outputs(const BfModel& m, const BfFra
             row = yi;
         }
         f.yaw[b] = row;
+        // the 16-vertex blocks of the active set this frame needs, OR-ed into its 128-frame tile's mask (order-independent)
+        if (f.blk_mask && m.act.lv_blk)
+            atomicOr(f.blk_mask + (size_t)mask_par * ((f.B + 127) >> 7) + (b >> 7), __ldg(m.act.lv_blk + (m.act.n_rows > 1 ? row : 0)));
     }
 }
 
@@ -207,7 +211,7 @@ __global__ void __launch_bounds__(128) k_pose_fwd(BfModel m, BfFrames f) {
     if (b >= f.B) return;
     PoseSmem& S = all[warp];
     pose_forward_warp(m, f.theta + (size_t)b * m.NP, S, lane);
-    pose_write_outputs(m, f, S, b, lane);
+    pose_write_outputs(m, f, S, b, lane, f.iter & 1);
 }
 
 // flags: 1 = priors, 2 = Adam, 4 = keep grad[0:4] written by the loss kernel (else zero them),
@@ -503,7 +507,7 @@ __global__ void __launch_bounds__(128) k_pose_bwd(BfModel m, BfFrames f, int fla
         if (flags & 8) {
             __syncwarp();
             pose_forward_from_smem(m, S, lane);
-            pose_write_outputs(m, f, S, b, lane);
+            pose_write_outputs(m, f, S, b, lane, (f.iter + 1) & 1);
         }
     }
 }

@@ -81,6 +81,9 @@ class FrameBuffers(object):
             buf('gmm_grad', B, 69, zero=True)
             buf('gmm_loss', B, zero=True)
             buf('fwd_state', B, 24 * J)
+            if tc and not full and model.n_act_pad <= 512:
+                # per 128-frame tile the 16-vertex blocks of the active set its frames need (two buffers: iteration parity)
+                buf('blk_mask', 2, (B + 127) // 128, zero=True, dtype=torch.int32)
             if temporal_weight > 0:
                 buf('tgrad', B, NP, zero=True)
                 buf('tloss', B, zero=True)
@@ -150,20 +153,30 @@ class FitSession(object):
 
     def __init__(self, model: PreparedModel, B, Nv, num_iters, imsize=512, return_vertices=True,
                  chunk=4096, trace=True, dense_every_iter=False, temporal_weight=0.0, halo_exchange=None, out=None,
-                 halo=None, graph=None):
+                 halo=None, graph=None, sort_frames=None):
         """``out`` (optional): externally owned result buffers for these B frames -- ``theta`` [B,NP], ``verts`` [B,V,3],
         ``joints`` [B,K_full,3], ``full_pose`` [B,3J] (contiguous row slices of a larger batch: ConcurrentFitSession).
         ``halo``: a sharding.HaloLink -- boundary rows of the temporal term travel by in-kernel NVLink stores (graph-capturable);
         ``halo_exchange``: the host-driven fallback (a callable, one NCCL send/recv pair per iteration).
         ``graph``: capture the whole run (N iterations + the all-vertex forward) in ONE CUDA graph on first use and replay it
         afterwards (default on; BODYFIT_GRAPH=0 or a host halo callback turn it off).  Inputs live in session-owned static
-        buffers (``kp``, ``cams``, ``theta0``), so the captured pointers never change."""
+        buffers (``kp``, ``cams``, ``theta0``), so the captured pointers never change.
+        ``sort_frames``: process the frames in the order of their contour (head-yaw) row at the initial pose, so that a
+        128-frame tile of the blend GEMMs holds few rows and touches ~16 of the 30 vertex blocks of the SMPL-X active set
+        (BfFrames.blk_mask).  Frames are independent fits, so the order is free; inputs are gathered and results scattered back
+        by the packing kernels, all result tensors stay in the caller's frame order.  Default: on for SMPL-X batches of more
+        than one tile without the temporal term (which couples neighbours); BODYFIT_SORT=0 turns it off."""
         self.model, self.B, self.Nv, self.N = model, int(B), int(Nv), int(num_iters)
         assert self.N >= 1
         dev = model.device
         out = out or {}
         self.fb = FrameBuffers(model, B, full=False, Nv=Nv, n_trace=(self.N if trace else 0), imsize=imsize,
-                               temporal_weight=temporal_weight, ext=dict(theta=out.get('theta')))
+                               temporal_weight=temporal_weight)
+        if sort_frames is None:
+            sort_frames = os.environ.get('BODYFIT_SORT', '1') != '0'
+        self.sort_frames = bool(sort_frames) and model.is_smplx and temporal_weight <= 0 and self.B > 128 and 'blk_mask' in self.fb.t
+        self.perm = torch.arange(B, dtype=torch.int32, device=dev) if self.sort_frames else None      # sorted position -> caller's frame
+        self.theta_out = out['theta'] if out.get('theta') is not None else torch.zeros(B, model.NP, device=dev)
         # static inputs of the captured run
         self.kp = torch.zeros(B, model.K_used, Nv, 3, device=dev)
         self.cams = torch.zeros(Nv, 12, device=dev)
@@ -213,6 +226,8 @@ class FitSession(object):
         """kp_packed [B,K_used,Nv,3] (x, y, effective weight; pack_keypoints) and cams [Nv,12], device tensors: copied into
         the session's static input buffers."""
         assert kp_packed.shape == (self.B, self.model.K_used, self.Nv, 3)
+        if self.sort_frames:                              # inputs arrive already packed: keep the caller's order
+            self.perm.copy_(torch.arange(self.B, dtype=torch.int32, device=self.perm.device))
         if kp_packed.data_ptr() != self.kp.data_ptr():
             self.kp.copy_(kp_packed)
         if cams.data_ptr() != self.cams.data_ptr():
@@ -225,12 +240,23 @@ class FitSession(object):
         assert kp_raw.shape == (self.B, self.Nv, m.K_used, 3) and kp_raw.is_contiguous() and kp_raw.dtype == torch.float32
         assert poses.is_contiguous() and betas.is_contiguous() and betas.shape == (self.B, 10)
         L, st = _lib.lib(), _stream()
-        _lib.check(L.bf_pack_keypoints(kp_raw.data_ptr(), self.kp.data_ptr(), self.B, self.Nv, m.K_used, int(m.is_smplx), st),
+        n = 2
+        perm = None
+        if self.sort_frames:
+            # contour row of every frame at its initial pose -> stable argsort -> the packing kernels gather by it
+            _lib.check(L.bf_init_theta(m.struct, poses.data_ptr(), int(poses.shape[1]), betas.data_ptr(), self.fb.t['theta'].data_ptr(),
+                                       self.B, None, st), 'bf_init_theta')
+            self.fb.struct.iter = 0
+            self.fb.call('bf_pose_forward')
+            self.perm.copy_(torch.argsort(self.fb.t['yaw'], stable=True))
+            perm = self.perm.data_ptr()
+            n += 2
+        _lib.check(L.bf_pack_keypoints(kp_raw.data_ptr(), self.kp.data_ptr(), self.B, self.Nv, m.K_used, int(m.is_smplx), perm, st),
                    'bf_pack_keypoints')
         _lib.check(L.bf_init_theta(m.struct, poses.data_ptr(), int(poses.shape[1]), betas.data_ptr(), self.theta0.data_ptr(),
-                                   self.B, st), 'bf_init_theta')
+                                   self.B, perm, st), 'bf_init_theta')
         self.cams.copy_(cams, non_blocking=True)
-        return 2
+        return n
 
     def _exchange(self):
         th = self.fb.t['theta']
@@ -249,6 +275,8 @@ class FitSession(object):
         fb.t['theta'].copy_(self.theta0)
         fb.t['adam_m'].zero_()
         fb.t['adam_v'].zero_()
+        if 'blk_mask' in fb.t:
+            fb.t['blk_mask'].zero_()
         launches = 0
         if self.halo is not None:
             fb.struct.iter = 0
@@ -260,7 +288,7 @@ class FitSession(object):
         if self.dense_every_iter:
             # materialise all V vertices in every iteration, as the reference's model call does
             for it in range(N - 1):
-                self.theta_prev.copy_(fb.t['theta'])
+                self._to_caller_order(fb.t['theta'], self.theta_prev)
                 launches += self._dense_forward()
                 fb.struct.iter = it
                 fb.call('bf_fit_step')
@@ -276,14 +304,23 @@ class FitSession(object):
             if N > 1:
                 fb.call('bf_fit_run', N - 1)
                 launches += per_it * (N - 1) + 1     # + the pose forward of the first iteration
-        self.theta_prev.copy_(fb.t['theta'])
+        self._to_caller_order(fb.t['theta'], self.theta_prev)
         launches += self._dense_forward()
         fb.struct.iter = N - 1
         if self.halo_exchange is not None:
             self._exchange()
         fb.call('bf_fit_step')
-        launches += per_it + 1
+        self._to_caller_order(fb.t['theta'], self.theta_out)
+        launches += per_it + 1 + (2 if self.sort_frames else 0)
         self.kernel_launches = launches
+
+    def _to_caller_order(self, src, dst):
+        """rows of the (possibly row-sorted) batch -> the caller's frame order: dst[perm[r]] = src[r]"""
+        if self.sort_frames:
+            _lib.check(_lib.lib().bf_scatter_rows(src.data_ptr(), self.perm.data_ptr(), dst.data_ptr(), self.B, int(src.shape[1]),
+                                                  _stream()), 'bf_scatter_rows')
+        else:
+            dst.copy_(src)
 
     def _capture(self, priority):
         """One uncaptured run on a capture stream (one-time setup of kernel attributes / side streams happens outside the
@@ -318,16 +355,32 @@ class FitSession(object):
             self.graphs[priority][0].replay()
         else:
             self._body()
-        return self.fb.t['theta']
+        return self.theta_out
 
     @property
     def theta(self):
-        return self.fb.t['theta']
+        return self.theta_out
+
+    def _unsorted(self, t, dim):
+        """per-frame rows of the sorted batch -> the caller's order (diagnostics: loss trace / loss terms)"""
+        if t is None or not self.sort_frames:
+            return t
+        out = torch.empty_like(t)
+        out.index_copy_(dim, self.perm.long(), t)
+        return out
+
+    @property
+    def trace(self):
+        return self._unsorted(self.fb.t.get('trace'), 1)
+
+    @property
+    def loss_terms(self):
+        return self._unsorted(self.fb.t['loss_terms'], 0)
 
     def results(self):
         """Device tensors with the reference's result-dict keys (smplify.py:216-226)."""
         m = self.model
-        sn = m.split_theta(self.fb.t['theta'])
+        sn = m.split_theta(self.theta_out)
         out = {}
         if self.verts is not None:
             out['vertices'] = self.verts
@@ -426,12 +479,12 @@ class ConcurrentFitSession(object):
 
     @property
     def trace(self):
-        ts = [p.fb.t.get('trace') for p in self.parts]
+        ts = [p.trace for p in self.parts]
         return None if ts[0] is None else torch.cat(ts, dim=1)
 
     @property
     def loss_terms(self):
-        return torch.cat([p.fb.t['loss_terms'] for p in self.parts], dim=0)
+        return torch.cat([p.loss_terms for p in self.parts], dim=0)
 
     def results(self):
         m = self.model

@@ -203,15 +203,24 @@ class PreparedModel(object):
         Bm_rows[:P] = PD
         Bm_rows[P:P + NS] = sd.reshape(V * 3, NS).T
         Bm_rows[P + NS] = vt.reshape(-1)
-        active = set()
+        # Active set order: first the vertices every frame uses (picked joints, static landmarks, regressed extra joints; ascending
+        # id), then the contour candidates in the order of the first yaw row that uses them.  A frame on row `a` then touches the
+        # static 16-vertex blocks plus a handful of contour blocks (the rows' vertex sets slide with the yaw angle), which is
+        # what lets the blend GEMMs skip whole blocks for frame tiles that hold few rows (lv_blk below, csrc/bf_blend_tc.cuh).
+        static, first_row = set(), {}
         for kind, src, w in self.joint_table[:K_used]:
             if kind == 1:
-                active.update(int(s) for s, ww in zip(src, w) if ww != 0.0)
-            elif kind == 2:
-                active.update(int(x) for x in dyn_faces[:, src[0], :].reshape(-1))
+                static.update(int(s) for s, ww in zip(src, w) if ww != 0.0)
             elif kind == 3:
-                active.update(int(x) for x in np.nonzero(xr[src[0]])[0])
-        self.active_vids = np.array(sorted(active), dtype=np.int64)
+                static.update(int(x) for x in np.nonzero(xr[src[0]])[0])
+        for kind, src, w in self.joint_table[:K_used]:
+            if kind == 2:
+                for a in range(dyn_faces.shape[0]):
+                    for x in dyn_faces[a, src[0], :].reshape(-1):
+                        if int(x) not in static:
+                            first_row[int(x)] = min(first_row.get(int(x), a), a)
+        self.active_vids = np.array(sorted(static) + sorted(first_row, key=lambda v: (first_row[v], v)), dtype=np.int64)
+        self.n_static = len(static)
         # joints grouped by tree level: the chain kernels walk one level at a time with lane = joint of that level
         lvl_j = np.argsort(depth, kind='stable').astype(np.int32)
         lvl_ptr = np.zeros(int(depth.max()) + 2, dtype=np.int32)
@@ -238,6 +247,7 @@ class PreparedModel(object):
         self.n_act = int(act_h['n'])
         self.n_pad_full = int(full_h['n_pad'])
         self.ld_act = 3 * int(act_h['n_pad'])
+        self.n_act_pad = int(act_h['n_pad'])
         self.K_out_act = int(act_h['K_out'])
         self._host = None
 
@@ -257,7 +267,7 @@ class PreparedModel(object):
                 setattr(vs, k, int(v))
 
     def _build_vset(self, vids, Bm_rows, W, table, build_live=False):
-        """Tables for the vertex set ``vids`` (sorted global vertex ids)."""
+        """Tables for the vertex set ``vids`` (distinct global vertex ids, in the set's column order)."""
         J = self.J
         n = len(vids)
         n_pad = _round_up(max(n, 1), 32)
@@ -409,10 +419,51 @@ class PreparedModel(object):
                 lj_w += [float(sub[x, j]) for x in nzv]
             lj_ptr[a, len(nzj):] = len(lj_vid)
         pad1 = lambda x, dt: np.array(x if len(x) else [0], dtype=dt)
+        # 16-vertex blocks a frame on row `a` needs (bit i = block i of the set); all ones where the set has > 32 blocks
+        lv_blk = np.zeros(rows, dtype=np.uint32)
+        for a in range(rows):
+            blocks = np.unique(lv_vid[a, :lv_n[a]] // 16)
+            lv_blk[a] = np.uint32(0xFFFFFFFF) if (n + 15) // 16 > 32 else np.bitwise_or.reduce((np.uint32(1) << blocks.astype(np.uint32)))
         return dict(lv_n=lv_n, lv_vid=lv_vid, lt_ptr=lt_ptr, lt_k=pad1(lt_k, np.int32), lt_w=pad1(lt_w, np.float32),
-                    lj_ptr=lj_ptr, lj_vid=pad1(lj_vid, np.int32), lj_w=pad1(lj_w, np.float32), lmax=lmax, n_rows=rows)
+                    lj_ptr=lj_ptr, lj_vid=pad1(lj_vid, np.int32), lj_w=pad1(lj_w, np.float32), lv_blk=lv_blk.view(np.int32),
+                    lmax=lmax, n_rows=rows)
 
     # ------------------------------------------------------------------------------------------
+    def save_blob(self, path):
+        """Serialise the prepared tables for hosts that do not run Python: ``bf_model_load(path, &model)`` of the C ABI maps
+        the file, uploads the array section with one copy and patches the pointers (include/bodyfit_b200.h).
+        Layout: 16-byte header ("BFMODEL1", ABI version, sizeof(BfModel)), the BfModel struct image with every pointer field
+        replaced by (offset into the array section + 1), 0 = NULL, then the array section (each array 16-byte aligned)."""
+        import struct as _st
+        img = _lib.BfModel()
+        C.memmove(C.byref(img), C.byref(self.struct), C.sizeof(_lib.BfModel))
+        blobs, off = [], 0
+
+        def put(t):
+            nonlocal off
+            a = t.detach().cpu().contiguous().numpy().tobytes()
+            pad = (-len(a)) % 16
+            blobs.append(a + b'\0' * pad)
+            o = off
+            off += len(a) + pad
+            return o + 1
+
+        def patch(st, tag):
+            for name, typ in st._fields_:
+                if typ is _lib._fp:
+                    t = self._dev.get(tag + '_' + name)
+                    setattr(st, name, put(t) if t is not None else None)
+        patch(img, 'm')
+        patch(img.full, 'full')
+        patch(img.act, 'act')
+        with open(path, 'wb') as f:
+            f.write(b'BFMODEL1' + _st.pack('<ii', _lib.ABI_VERSION, C.sizeof(_lib.BfModel)))
+            f.write(bytes(img))
+            f.write(_st.pack('<q', off))
+            for b in blobs:
+                f.write(b)
+        return path
+
     def pack_theta(self, global_orient, body_pose, betas, transl=None, scale=None, leye=None, reye=None,
                    lhand=None, rhand=None):
         """Assemble [B, NP] theta rows (layout in include/bodyfit_b200.h)."""

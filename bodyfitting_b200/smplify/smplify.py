@@ -127,8 +127,8 @@ class SMPLify(object):
             sess.load_inputs(kp_dev, cams, poses_dev, betas_dev)
             sess.run()
             out = sess.results()
-            self.last_trace = sess.fb.t.get('trace')
-            self.last_loss_terms = sess.fb.t['loss_terms']
+            self.last_trace = sess.trace
+            self.last_loss_terms = sess.loss_terms
             if as_numpy:
                 out = self._d2h(out)
         out['faces'] = self.smpl_faces[0]

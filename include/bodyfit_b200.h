@@ -40,7 +40,7 @@ extern "C" {
 #define BF_ECUDA    -2   /* a CUDA runtime call / launch failed            */
 #define BF_EARCH    -3   /* device is not sm_100 (no fallback exists)      */
 
-#define BF_ABI_VERSION 15
+#define BF_ABI_VERSION 16
 #define BF_F_WORLD 1   /* forward outputs in world space: (x + transl) * scale * constant_scale */
 #define BF_F_TC    2   /* run the blend-shape contractions on tcgen05 tensor cores (3xTF32) */
 #define BF_F_SKIN_FUSED 4  /* bf_frame_loss_backward skins the frame's live vertices itself from vposed (after bf_blend_forward) */
@@ -82,6 +82,8 @@ typedef struct BfVSet {
     const int32_t* lj_ptr;    /* [n_rows, n_nz+1] absolute offsets: skinning list of joint jv_nz[jn] restricted to live vertices */
     const int32_t* lj_vid;    /* index into the row's live list (lv_vid[a][.]) */
     const float*   lj_w;
+    const uint32_t* lv_blk;   /* [n_rows] bit i set = a frame on this row has live vertices in the 16-vertex block i of the set
+                                 (the set is ordered static vertices first, then contour candidates by first row; NULL = full set) */
     int32_t n, n_pad, ldn, nnz, K_out, n_dyn, n_extra, n_nz, lmax, n_rows;
 } BfVSet;
 
@@ -149,6 +151,9 @@ typedef struct BfFrames {
                                 pose backward does not recompute them */
     float*       gmm_ws;     /* [B, n_gmm*72 + 160] workspace of the tensor-core GMM prior (y of every component | [pose|1] hi | lo), or NULL */
     float*       ws;         /* split-K workspace of the tensor-core backward GEMM (>= ceil(ldn/2048) * B * Kp floats) or NULL */
+    uint32_t*    blk_mask;   /* [2, ceil(B/128)] (or NULL): per 128-frame tile the OR of lv_blk over its frames' yaw rows -- the
+                                16-vertex blocks of the active set the blend GEMMs have to touch for that tile.  Written by the pose
+                                forward (buffer = iteration parity), cleared by the per-frame kernel; zero before the first iteration */
     int64_t      ws_floats;
     double lr_ts, lr, beta1, beta2, eps;   /* Adam hyper-parameters (python floats in the reference: smplify.py:167-174) */
     int32_t B, Nv, ld_v, iter;
@@ -208,13 +213,34 @@ int bf_fit_step(const BfModel* m, const BfFrames* f, void* stream);
 int bf_fit_run(const BfModel* m, const BfFrames* f, int n_iters, void* stream);
 
 
+/* ---- model and frame buffers for hosts that do not run Python ---------------------------------------------------------
+ * The body-model tables (BfModel: ~60 device arrays derived from v_template / shapedirs / posedirs / J_regressor / weights /
+ * landmark tables / the GMM prior; reference: models/smpl.py:56-66, smplify/smplify.py:46-80, smplify/prior.py:127-174) are
+ * prepared once by the Python tool (bodyfitting_b200.model.PreparedModel(...).save_blob(path)) and loaded here with one
+ * upload; bf_model_destroy frees them.  bf_workspace_bytes / bf_frames_bind size and carve ONE caller-owned, 256-byte aligned
+ * device workspace into the BfFrames buffers of a B-frame batch (opts: 1 = all-vertex set, 2 = backward / optimiser buffers,
+ * 8 = temporal term; n_trace = rows of the optional per-iteration loss trace), zero it and fill in the reference's
+ * hyper-parameters.  These are the only calls besides bf_halo_* that allocate or synchronise. */
+int     bf_model_load(const char* path, BfModel** out);
+int     bf_model_load_memory(const void* blob, int64_t nbytes, BfModel** out);
+int     bf_model_destroy(BfModel* m);
+int64_t bf_workspace_bytes(const BfModel* m, int B, int Nv, int opts, int n_trace);
+int     bf_frames_bind(const BfModel* m, int B, int Nv, int opts, int n_trace, void* workspace, int64_t bytes, BfFrames* out,
+                       void* stream);
+
 /* ---- input packing (so that no host-framework arithmetic sits on the path) ---------------------------------
  * detections [B,Nv,K,3] (x, y, conf) in the caller's layout -> kp [B,K,Nv,3] (x, y, effective weight): conf^2 for the body,
  * the group's sum of conf^2 for SMPL-X hands / face (smplify/loss.py:134 with :168,:173,:179) */
-int bf_pack_keypoints(const float* kp_raw, float* kp_packed, int B, int Nv, int K, int hand_face, void* stream);
+int bf_pack_keypoints(const float* kp_raw, float* kp_packed, int B, int Nv, int K, int hand_face, const int32_t* src_index,
+                      void* stream);
 /* network output -> initial theta rows (smplify/smplify.py:103-128): transl 0, scale 1, global_orient / body_pose from
  * poses[b, 0:3+nbody] (row stride ld_poses), betas[b, 0:10], eye / hand parameters 0 */
-int bf_init_theta(const BfModel* m, const float* poses, int ld_poses, const float* betas, float* theta, int B, void* stream);
+int bf_init_theta(const BfModel* m, const float* poses, int ld_poses, const float* betas, float* theta, int B,
+                  const int32_t* src_index, void* stream);
+/* src_index (both calls above, optional): packed frame b is the caller's frame src_index[b] -- a batch whose frames are
+ * independent fits may be processed in any order (the host sorts it by contour row so that a 128-frame tile of the blend
+ * GEMMs touches few 16-vertex blocks, BfFrames.blk_mask); bf_scatter_rows puts result rows back: dst[index[r]] = src[r] */
+int bf_scatter_rows(const float* src, const int32_t* index, float* dst, int rows, int cols, void* stream);
 
 /* ---- NVLink halo of the temporal term (BASELINE config 4; the reference has no multi-GPU path) -----------------
  * One buffer per rank (bf_halo_bytes() bytes of cudaMalloc'ed memory, exported as a CUDA IPC handle of

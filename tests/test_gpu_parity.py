@@ -492,3 +492,51 @@ def test_config2_size_sampled_oracle_check(assets):
         print('   %-14s max abs diff %.3e' % (k, d))
         assert d < 2e-5, k                                    # measured <= 8.0e-7
     assert relerr(np.asarray(out['vertices'])[pick], ref['vertices']) < 1e-5
+
+
+def test_c_abi_host_without_python_tables(assets, tmp_path):
+    """The path a non-Python host takes: model blob (PreparedModel.save_blob) -> bf_model_load -> bf_workspace_bytes /
+    bf_frames_bind on one raw device allocation -> bf_pack_keypoints / bf_init_theta -> bf_fit_run.  Same parameters, bit for
+    bit, as the Python session on the same inputs."""
+    import ctypes as C
+    from bodyfitting_b200 import _lib
+    from bodyfitting_b200.engine import FitSession, pack_cameras
+    mt, nv, B, N = 'smplx', 8, 37, 9
+    port = make_port(assets, mt)
+    sc = make_scene(port, mt, B, nv, seed=55)
+    pm = _prep(assets, mt)
+    sess = FitSession(pm, B, nv, N + 1, graph=False, trace=True)
+    kp = torch.as_tensor(sc['kp']).cuda().contiguous()
+    cams = torch.from_numpy(pack_cameras(sc['c2ws'], sc['Ks'])).cuda()
+    poses, betas = torch.as_tensor(sc['init_pose']).cuda().contiguous(), torch.as_tensor(sc['init_betas']).cuda().contiguous()
+    sess.load_inputs(kp, cams, poses, betas)
+    # python path: N iterations through the library's own loop on the session's buffers
+    sess.fb.t['theta'].copy_(sess.theta0); sess.fb.t['adam_m'].zero_(); sess.fb.t['adam_v'].zero_()
+    sess.fb.struct.iter = 0
+    sess.fb.call('bf_fit_run', N)
+    torch.cuda.synchronize()
+    want = sess.fb.t['theta'].clone()
+    # C path
+    L = _lib.lib()
+    path = str(tmp_path / 'model.bfm')
+    pm.save_blob(path)
+    mptr = C.POINTER(_lib.BfModel)()
+    _lib.check(L.bf_model_load(path.encode(), C.byref(mptr)), 'bf_model_load')
+    assert mptr.contents.J == pm.J and mptr.contents.act.n == pm.n_act and mptr.contents.full.n == pm.V
+    need = L.bf_workspace_bytes(mptr, B, nv, 2, N)
+    assert need > 0
+    ws = torch.empty(need + 256, dtype=torch.uint8, device='cuda')
+    base = (ws.data_ptr() + 255) & ~255
+    fr = _lib.BfFrames()
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(L.bf_frames_bind(mptr, B, nv, 2, N, base, need, C.byref(fr), st), 'bf_frames_bind')
+    _lib.check(L.bf_pack_keypoints(kp.data_ptr(), fr.kp, B, nv, pm.K_used, 1, st), 'bf_pack_keypoints')
+    view = lambda ptr, n: ws[ptr - ws.data_ptr(): ptr - ws.data_ptr() + 4 * n].view(torch.float32)    # a field of the raw workspace
+    view(fr.cams, nv * 12).copy_(cams.reshape(-1))
+    _lib.check(L.bf_init_theta(mptr, poses.data_ptr(), poses.shape[1], betas.data_ptr(), fr.theta, B, st), 'bf_init_theta')
+    _lib.check(L.bf_fit_run(mptr, C.byref(fr), N, st), 'bf_fit_run')
+    torch.cuda.synchronize()
+    got = view(fr.theta, B * pm.NP).reshape(B, pm.NP)
+    assert torch.equal(got, want)
+    _lib.check(L.bf_model_destroy(mptr), 'bf_model_destroy')
+    assert L.bf_model_destroy(C.POINTER(_lib.BfModel)()) == 0                       # NULL is a no-op

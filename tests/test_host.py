@@ -284,7 +284,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     L = _lib.lib()
     hdr = open(os.path.join(ROOT, 'include', 'bodyfit_b200.h')).read() + open(os.path.join(ROOT, 'include', 'bodyfit_b200_ops.h')).read() + \
         open(os.path.join(ROOT, 'include', 'bodyfit_b200_grid.h')).read() + open(os.path.join(ROOT, 'include', 'bodyfit_b200_mask.h')).read()
-    declared = set(re.findall(r'^(?:int|const char\*)\s+(bf_[a-z0-9_]+)\s*\(', hdr, re.M))
+    declared = set(re.findall(r'^(?:int|int64_t|const char\*)\s+(bf_[a-z0-9_]+)\s*\(', hdr, re.M))
     assert declared, 'no declarations parsed'
     for name in sorted(declared):
         assert hasattr(L, name), 'symbol %s declared in the header but not exported' % name
