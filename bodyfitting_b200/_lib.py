@@ -10,7 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('BODYFIT_LIB') or os.path.join(_HERE, 'libbodyfit_b200.so')   # BODYFIT_LIB: A/B builds of the same ABI
-ABI_VERSION = 16
+ABI_VERSION = 17
 F_WORLD = 1
 F_TC = 2
 F_SKIN_FUSED = 4
@@ -40,7 +40,7 @@ class BfFrames(C.Structure):
     _fields_ = [(n, _fp) for n in (
         'theta', 'grad', 'adam_m', 'adam_v', 'pf', 'dpf', 'A', 'dA', 'Jtr', 'dJtr', 'full_pose', 'yaw',
         'verts', 'vposed', 'dverts', 'dvp', 'joints', 'djoints', 'kp', 'cams', 'loss', 'loss_terms', 'trace',
-        'pf_hi', 'pf_lo', 'dvp_hi', 'dvp_lo', 'gmm_grad', 'gmm_loss', 'tgrad', 'tloss', 'halo_prev', 'halo_next', 'halo_buf', 'halo_peer_prev', 'halo_peer_next', 'fwd_state', 'gmm_ws', 'ws', 'blk_mask')] + [('ws_floats', C.c_int64)] + \
+        'pf_hi', 'pf_lo', 'dvp_hi', 'dvp_lo', 'gmm_grad', 'gmm_loss', 'tgrad', 'tloss', 'halo_prev', 'halo_next', 'halo_buf', 'halo_peer_prev', 'halo_peer_next', 'fwd_state', 'gmm_ws', 'ws', 'blk_mask', 'frame_index')] + [('ws_floats', C.c_int64)] + \
         [(n, C.c_double) for n in ('lr_ts', 'lr', 'beta1', 'beta2', 'eps')] + \
         [(n, _i32) for n in ('B', 'Nv', 'ld_v', 'iter', 'flags', 'halo_iters')] + \
         [(n, C.c_float) for n in ('imsize', 'constant_scale', 'sigma', 'w_pose', 'w_angle', 'w_shape', 'w_temporal', '_padf')]
@@ -128,6 +128,8 @@ def lib():
     L.bf_workspace_bytes.argtypes = [pm, i32, i32, i32, i32]
     L.bf_frames_bind.restype = C.c_int
     L.bf_frames_bind.argtypes = [pm, i32, i32, i32, i32, C.c_void_p, C.c_int64, pf, vp]
+    L.bf_graph_set_kernel_priority.restype = C.c_int
+    L.bf_graph_set_kernel_priority.argtypes = [C.c_void_p, C.c_int]
     for name in ('bf_halo_bytes', 'bf_halo_handle_bytes'):
         getattr(L, name).restype = C.c_int
         getattr(L, name).argtypes = []
@@ -161,7 +163,7 @@ EXPORTED = ['bf_abi_version', 'bf_sizeof', 'bf_last_error', 'bf_check_device', '
             'bf_pose_backward', 'bf_gmm_prior', 'bf_temporal_prior', 'bf_fit_iteration', 'bf_frame_loss_backward', 'bf_lbs_forward', 'bf_lbs_backward', 'bf_fit_step', 'bf_fit_run',
             'bf_pack_keypoints', 'bf_init_theta', 'bf_scatter_rows', 'bf_halo_bytes', 'bf_halo_handle_bytes', 'bf_halo_alloc', 'bf_halo_open',
             'bf_halo_close', 'bf_halo_free', 'bf_halo_begin', 'bf_model_load', 'bf_model_load_memory', 'bf_model_destroy',
-            'bf_workspace_bytes', 'bf_frames_bind']
+            'bf_workspace_bytes', 'bf_frames_bind', 'bf_graph_set_kernel_priority']
 
 
 EXPORTED_GRID = ['bf_grid_count', 'bf_grid_fill', 'bf_grid_nearest', 'bf_grid_barycentric', 'bf_grid_nearest_backward', 'bf_grid_inside', 'bf_grid_intersects_any', 'bf_smpld_step', 'bf_smpld_run', 'bf_pc_loss']

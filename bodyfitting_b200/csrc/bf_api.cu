@@ -651,6 +651,32 @@ int bf_frames_bind(const BfModel* m, int B, int Nv, int opts, int n_trace, void*
     return BF_OK;
 }
 
+// Kernel nodes of a captured CUDA graph do not inherit the priority of the stream the graph is later launched on (measured:
+// four concurrently replayed part graphs all finished together whatever the priority of their streams), so the priority is
+// written into every kernel node before instantiation.  `graph` = cudaGraph_t; returns the number of kernel nodes changed.
+int bf_graph_set_kernel_priority(void* graph, int priority) {
+    BF_REQUIRE(graph, "graph is null");
+    cudaGraph_t g = (cudaGraph_t)graph;
+    size_t n = 0;
+    if (cudaGraphGetNodes(g, nullptr, &n) != cudaSuccess) { bf_set_error("cudaGraphGetNodes failed"); return BF_ECUDA; }
+    if (n == 0) return 0;
+    cudaGraphNode_t* nodes = (cudaGraphNode_t*)malloc(n * sizeof(cudaGraphNode_t));
+    BF_REQUIRE(nodes, "out of host memory");
+    int changed = 0;
+    if (cudaGraphGetNodes(g, nodes, &n) != cudaSuccess) { free(nodes); bf_set_error("cudaGraphGetNodes failed"); return BF_ECUDA; }
+    for (size_t i = 0; i < n; ++i) {
+        cudaGraphNodeType t;
+        if (cudaGraphNodeGetType(nodes[i], &t) != cudaSuccess || t != cudaGraphNodeTypeKernel) continue;
+        cudaLaunchAttributeValue v;
+        memset(&v, 0, sizeof(v));
+        v.priority = priority;
+        if (cudaGraphKernelNodeSetAttribute(nodes[i], cudaLaunchAttributePriority, &v) == cudaSuccess) ++changed;
+    }
+    free(nodes);
+    cudaGetLastError();
+    return changed;
+}
+
 // ---- input packing ------------------------------------------------------------------------------------------
 int bf_pack_keypoints(const float* kp_raw, float* kp_packed, int B, int Nv, int K, int hand_face, const int32_t* src_index,
                       void* stream) {

@@ -343,6 +343,7 @@ k_blend_fwd_tc(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant_
 __global__ void __launch_bounds__(64 + 32 * TC_EPI_WARPS, 1)
 k_blend_fwd_tc_blk(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CUtensorMap mA_lo,
                    const __grid_constant__ CUtensorMap mB_hi, const __grid_constant__ CUtensorMap mB_lo,
+                   const __grid_constant__ CUtensorMap mB4_hi, const __grid_constant__ CUtensorMap mB4_lo,
                    int n_verts, int Kp, float* __restrict__ vposed, int B, int ld_v, int n_tiles_m,
                    const uint32_t* __restrict__ blk_mask, int n_blocks) {
     extern __shared__ uint8_t smem_raw[];
@@ -386,6 +387,8 @@ k_blend_fwd_tc_blk(const __grid_constant__ CUtensorMap mA_hi, const __grid_const
                 if (nb <= 0) continue;
                 int rows[4];
                 for (int j = 0; j < nb; ++j) rows[j] = TC_BLK_ROWS * (int)__fns(mask, 0, 4 * vt + j + 1);
+                // four consecutive blocks (the static part of the set): one 192-row box instead of four 48-row ones
+                const bool run4 = nb == 4 && rows[3] == rows[0] + 3 * TC_BLK_ROWS;
                 const int b0 = fm * TC_BM;
                 const uint32_t bytes = 2 * p.a_bytes + 2u * (uint32_t)nb * TC_BLK_ROWS * TC_ROWB;
                 for (int kc = 0; kc < num_k; ++kc, ++it) {
@@ -396,9 +399,14 @@ k_blend_fwd_tc_blk(const __grid_constant__ CUtensorMap mA_hi, const __grid_const
                     uint8_t* st = p.stage(s);
                     tc::tma_load_2d(st, &mA_hi, &p.full[s], kc * TC_BK, b0);
                     tc::tma_load_2d(st + p.a_bytes, &mA_lo, &p.full[s], kc * TC_BK, b0);
-                    for (int j = 0; j < nb; ++j) {
-                        tc::tma_load_2d(st + 2 * p.a_bytes + j * TC_BLK_ROWS * TC_ROWB, &mB_hi, &p.full[s], kc * TC_BK, rows[j]);
-                        tc::tma_load_2d(st + 2 * p.a_bytes + p.b_bytes + j * TC_BLK_ROWS * TC_ROWB, &mB_lo, &p.full[s], kc * TC_BK, rows[j]);
+                    if (run4) {
+                        tc::tma_load_2d(st + 2 * p.a_bytes, &mB4_hi, &p.full[s], kc * TC_BK, rows[0]);
+                        tc::tma_load_2d(st + 2 * p.a_bytes + p.b_bytes, &mB4_lo, &p.full[s], kc * TC_BK, rows[0]);
+                    } else {
+                        for (int j = 0; j < nb; ++j) {
+                            tc::tma_load_2d(st + 2 * p.a_bytes + j * TC_BLK_ROWS * TC_ROWB, &mB_hi, &p.full[s], kc * TC_BK, rows[j]);
+                            tc::tma_load_2d(st + 2 * p.a_bytes + p.b_bytes + j * TC_BLK_ROWS * TC_ROWB, &mB_lo, &p.full[s], kc * TC_BK, rows[j]);
+                        }
                     }
                 }
             }
@@ -690,6 +698,9 @@ static int bf_gemm_forward_tc_blk(const float* a_hi_p, const float* a_lo_p, cons
     if ((rc = bf_make_map(&a_lo, a_lo_p, B, Kp, Kp, TC_BM))) return rc;
     if ((rc = bf_make_map(&b_hi, bt_hi_p, ldn, Kp, Kp, TC_BLK_ROWS))) return rc;
     if ((rc = bf_make_map(&b_lo, bt_lo_p, ldn, Kp, Kp, TC_BLK_ROWS))) return rc;
+    CUtensorMap b4_hi, b4_lo;
+    if ((rc = bf_make_map(&b4_hi, bt_hi_p, ldn, Kp, Kp, TC_BN1))) return rc;
+    if ((rc = bf_make_map(&b4_lo, bt_lo_p, ldn, Kp, Kp, TC_BN1))) return rc;
     const size_t smem = 1024 + TC_STAGES * (2 * TC_BM * TC_ROWB + 2 * TC_BN1 * TC_ROWB) + TC_EPI_WARPS * TC_ST_FLOATS * 4 + 128;
     static size_t attr[BF_MAXDEV] = {0};
     if ((rc = bf_ensure_smem(k_blend_fwd_tc_blk, smem, attr, "k_blend_fwd_tc_blk"))) return rc;
@@ -698,7 +709,7 @@ static int bf_gemm_forward_tc_blk(const float* a_hi_p, const float* a_lo_p, cons
     // at most ceil(n_blocks / 4) virtual tiles per frame tile are real; one CTA per SM, fewer when there is less work
     const int real_max = tm * ((n_blocks + 3) / 4);
     const int grid = real_max < num_sms ? real_max : num_sms;
-    k_blend_fwd_tc_blk<<<grid, 64 + 32 * TC_EPI_WARPS, smem, s>>>(a_hi, a_lo, b_hi, b_lo, n_verts, Kp, dst, B, ld_dst, tm, blk_mask, n_blocks);
+    k_blend_fwd_tc_blk<<<grid, 64 + 32 * TC_EPI_WARPS, smem, s>>>(a_hi, a_lo, b_hi, b_lo, b4_hi, b4_lo, n_verts, Kp, dst, B, ld_dst, tm, blk_mask, n_blocks);
     BF_LAUNCH_CHECK();
     return BF_OK;
 }

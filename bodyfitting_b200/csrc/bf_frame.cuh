@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(FR_THREADS, 5) k_frame_loss_bwd(BfModel m, BfV
         tc::bulk_g2s(As, f.A + (size_t)b * J * 12, a_bytes, &bars[0]);
         tc::bulk_g2s(vp, f.vposed + (size_t)b * f.ld_v, v_bytes, &bars[0]);
         tc::mbar_expect_tx(&bars[1], k_bytes);
-        tc::bulk_g2s(sm + SL.kp, f.kp + (size_t)b * K * Nv * 3, k_bytes, &bars[1]);
+        tc::bulk_g2s(sm + SL.kp, f.kp + (size_t)(f.frame_index ? f.frame_index[b] : b) * K * Nv * 3, k_bytes, &bars[1]);
     }
     const int yaw = f.yaw ? f.yaw[b] : 0;
     const int row = vs.n_rows > 1 ? yaw : 0;
@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(FR_THREADS, 5) k_frame_loss_bwd(BfModel m, BfV
         const float qx = x[0] + tx, qy = x[1] + ty, qz = x[2] + tz;
         const float X = qx * sc * cs, Y = qy * sc * cs, Z = qz * sc * cs;
         float g0 = 0.f, g1 = 0.f, g2 = 0.f, ls = 0.f;
-        const float* kpr = TMA ? kps + k * Nv * 3 : f.kp + ((size_t)b * K + k) * Nv * 3;
+        const float* kpr = TMA ? kps + k * Nv * 3 : f.kp + ((size_t)(f.frame_index ? f.frame_index[b] : b) * K + k) * Nv * 3;
         for (int v0 = 0; v0 < Nv; v0 += 4) {
             float kv[12];
             if (vec4) {

@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(256) k_keypoint_loss(BfModel m, BfVSet vs, BfF
             const float p2 = M[8] * X + M[9] * Y + M[10] * Z + M[11];
             const float iz = 1.0f / p2;
             const float u = p0 * iz, w_ = p1 * iz;
-            const float* kp = f.kp + (((size_t)b * K + k) * Nv + v) * 3;
+            const float* kp = f.kp + (((size_t)(f.frame_index ? f.frame_index[b] : b) * K + k) * Nv + v) * 3;
             const float wgt = kp[2];
             const float rx = (kp[0] - u) / coef, ry = (kp[1] - w_) / coef;
             const float rx2 = rx * rx, ry2 = ry * ry;

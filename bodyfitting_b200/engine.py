@@ -175,7 +175,17 @@ class FitSession(object):
         if sort_frames is None:
             sort_frames = os.environ.get('BODYFIT_SORT', '1') != '0'
         self.sort_frames = bool(sort_frames) and model.is_smplx and temporal_weight <= 0 and self.B > 128 and 'blk_mask' in self.fb.t
-        self.perm = torch.arange(B, dtype=torch.int32, device=dev) if self.sort_frames else None      # sorted position -> caller's frame
+        # rows move during a fit (the pose converges: ~12 rows on the synthetic workload), so the order is renewed before a few
+        # iterations: only theta / adam_m / adam_v rows are permuted, the keypoint rows stay behind `frame_index`
+        self.resort_at, self.perm = [], None
+        if self.sort_frames:
+            self.perm = torch.arange(B, dtype=torch.int32, device=dev)          # current: sorted position -> caller's frame
+            self.perm0 = self.perm.clone()                                      # order at the start of a run (initial poses)
+            want = [int(x) for x in os.environ.get('BODYFIT_RESORT', '6,16,36').split(',') if x.strip()]
+            self.resort_at = sorted(set(r for r in want if 0 < r < self.N - 1)) if not dense_every_iter else []
+            self.perm_hist = torch.zeros(len(self.resort_at) + 1, B, dtype=torch.int32, device=dev)
+            self._rows_tmp = torch.empty(B, model.NP, device=dev)
+            self.fb.bind('frame_index', self.perm)
         self.theta_out = out['theta'] if out.get('theta') is not None else torch.zeros(B, model.NP, device=dev)
         # static inputs of the captured run
         self.kp = torch.zeros(B, model.K_used, Nv, 3, device=dev)
@@ -226,8 +236,8 @@ class FitSession(object):
         """kp_packed [B,K_used,Nv,3] (x, y, effective weight; pack_keypoints) and cams [Nv,12], device tensors: copied into
         the session's static input buffers."""
         assert kp_packed.shape == (self.B, self.model.K_used, self.Nv, 3)
-        if self.sort_frames:                              # inputs arrive already packed: keep the caller's order
-            self.perm.copy_(torch.arange(self.B, dtype=torch.int32, device=self.perm.device))
+        if self.sort_frames:                              # theta0 arrives in the caller's order too
+            self.perm0.copy_(torch.arange(self.B, dtype=torch.int32, device=self.perm.device))
         if kp_packed.data_ptr() != self.kp.data_ptr():
             self.kp.copy_(kp_packed)
         if cams.data_ptr() != self.cams.data_ptr():
@@ -248,11 +258,11 @@ class FitSession(object):
                                        self.B, None, st), 'bf_init_theta')
             self.fb.struct.iter = 0
             self.fb.call('bf_pose_forward')
-            self.perm.copy_(torch.argsort(self.fb.t['yaw'], stable=True))
-            perm = self.perm.data_ptr()
+            self.perm0.copy_(torch.argsort(self.fb.t['yaw'], stable=True))
+            perm = self.perm0.data_ptr()
             n += 2
-        _lib.check(L.bf_pack_keypoints(kp_raw.data_ptr(), self.kp.data_ptr(), self.B, self.Nv, m.K_used, int(m.is_smplx), perm, st),
-                   'bf_pack_keypoints')
+        _lib.check(L.bf_pack_keypoints(kp_raw.data_ptr(), self.kp.data_ptr(), self.B, self.Nv, m.K_used, int(m.is_smplx), None, st),
+                   'bf_pack_keypoints')                   # keypoint rows stay in the caller's order (frame_index)
         _lib.check(L.bf_init_theta(m.struct, poses.data_ptr(), int(poses.shape[1]), betas.data_ptr(), self.theta0.data_ptr(),
                                    self.B, perm, st), 'bf_init_theta')
         self.cams.copy_(cams, non_blocking=True)
@@ -277,6 +287,9 @@ class FitSession(object):
         fb.t['adam_v'].zero_()
         if 'blk_mask' in fb.t:
             fb.t['blk_mask'].zero_()
+        if self.sort_frames:
+            self.perm.copy_(self.perm0)
+            self.perm_hist[0].copy_(self.perm0)
         launches = 0
         if self.halo is not None:
             fb.struct.iter = 0
@@ -300,10 +313,15 @@ class FitSession(object):
                 fb.call('bf_fit_iteration', 1 if it == 0 else 0, 1)
                 launches += per_it + (1 if it == 0 else 0)
         else:
-            fb.struct.iter = 0
-            if N > 1:
-                fb.call('bf_fit_run', N - 1)
-                launches += per_it * (N - 1) + 1     # + the pose forward of the first iteration
+            it = 0
+            for k, stop in enumerate(self.resort_at + [N - 1]):
+                if stop > it:
+                    fb.struct.iter = it
+                    fb.call('bf_fit_run', stop - it)
+                    launches += per_it * (stop - it) + 1     # + the pose forward of the segment's first iteration
+                it = stop
+                if stop != N - 1:
+                    launches += self._resort(it, k + 1)
         self._to_caller_order(fb.t['theta'], self.theta_prev)
         launches += self._dense_forward()
         fb.struct.iter = N - 1
@@ -313,6 +331,21 @@ class FitSession(object):
         self._to_caller_order(fb.t['theta'], self.theta_out)
         launches += per_it + 1 + (2 if self.sort_frames else 0)
         self.kernel_launches = launches
+
+    def _resort(self, it, k):
+        """Renew the processing order before iteration ``it``: contour rows at the current iterate (one extra pose forward),
+        stable argsort, theta / Adam rows permuted; the next segment starts with a pose forward in the new order."""
+        fb = self.fb
+        fb.struct.iter = it
+        fb.call('bf_pose_forward')
+        order = torch.argsort(fb.t['yaw'], stable=True)
+        for name in ('theta', 'adam_m', 'adam_v'):
+            torch.index_select(fb.t[name], 0, order, out=self._rows_tmp)
+            fb.t[name].copy_(self._rows_tmp)
+        self.perm.copy_(self.perm[order])
+        self.perm_hist[k].copy_(self.perm)
+        fb.t['blk_mask'][it & 1].zero_()                 # the forward above OR-ed the old order's rows into it
+        return 1
 
     def _to_caller_order(self, src, dst):
         """rows of the (possibly row-sorted) batch -> the caller's frame order: dst[perm[r]] = src[r]"""
@@ -325,8 +358,9 @@ class FitSession(object):
     def _capture(self, priority):
         """One uncaptured run on a capture stream (one-time setup of kernel attributes / side streams happens outside the
         capture), then the same launches recorded into a CUDA graph; the library's fork / join events to its side stream
-        become graph edges.  Kernel nodes inherit the priority of the stream they are captured on, so a session keeps one
-        graph per priority it is run with (ConcurrentFitSession: decreasing priorities make the parts finish in order)."""
+        become graph edges.  A session keeps one graph per priority it is run with: the priority is written into the graph's
+        kernel nodes (ConcurrentFitSession: decreasing priorities make the parts finish in order, so that the device->host
+        copy of an early part overlaps the fitting of the later ones)."""
         dev = self.model.device
         cur = torch.cuda.current_stream(dev)
         gs = torch.cuda.Stream(device=dev) if priority is None else torch.cuda.Stream(device=dev, priority=priority)
@@ -334,9 +368,15 @@ class FitSession(object):
         with torch.cuda.stream(gs):
             self._body()
         gs.synchronize()
-        g = torch.cuda.CUDAGraph()
+        g = torch.cuda.CUDAGraph(keep_graph=priority is not None)
         with torch.cuda.graph(g, stream=gs, capture_error_mode='thread_local'):
             self._body()
+        if priority is not None:
+            # the launch stream's priority does not reach the kernels of a replayed graph: write it into the kernel nodes
+            n = _lib.lib().bf_graph_set_kernel_priority(g.raw_cuda_graph(), int(priority))
+            if n < 0:
+                _lib.check(n, 'bf_graph_set_kernel_priority')
+            g.instantiate()
         cur.wait_stream(gs)
         self.graphs[priority] = (g, gs)
         self.graph = g
@@ -371,7 +411,14 @@ class FitSession(object):
 
     @property
     def trace(self):
-        return self._unsorted(self.fb.t.get('trace'), 1)
+        tr = self.fb.t.get('trace')
+        if tr is None or not self.sort_frames:
+            return tr
+        out = torch.empty_like(tr)
+        bounds = [0] + list(self.resort_at) + [self.N]           # iterations [bounds[k], bounds[k+1]) ran in order perm_hist[k]
+        for k in range(len(bounds) - 1):
+            out[bounds[k]:bounds[k + 1]].index_copy_(1, self.perm_hist[k].long(), tr[bounds[k]:bounds[k + 1]])
+        return out
 
     @property
     def loss_terms(self):
@@ -430,7 +477,7 @@ class ConcurrentFitSession(object):
     Same interface as FitSession (set_inputs / run / results)."""
 
     def __init__(self, model: PreparedModel, B, Nv, num_iters, imsize=512, return_vertices=True, dense_every_iter=False,
-                 n_parts=4, trace=True, min_part=2048, lead=0, taper=0.5, graph=None):
+                 n_parts=4, trace=True, min_part=2048, lead=0, taper=0.5, graph=None, sort_frames=None):
         self.model, self.B, self.Nv, self.N = model, int(B), int(Nv), int(num_iters)
         dev = model.device
         self.ranges = staggered_ranges(self.B, n_parts, min_part=min_part, lead=lead, taper=taper)
@@ -448,7 +495,7 @@ class ConcurrentFitSession(object):
             out = dict(theta=self.theta[lo:hi], joints=self.joints[lo:hi], full_pose=self.full_pose[lo:hi],
                        verts=self.verts[lo:hi] if return_vertices else None)
             self.parts.append(FitSession(model, hi - lo, Nv, num_iters, imsize=imsize, return_vertices=return_vertices,
-                                         dense_every_iter=dense_every_iter, trace=trace, out=out, graph=graph))
+                                         dense_every_iter=dense_every_iter, trace=trace, out=out, graph=graph, sort_frames=sort_frames))
             self.streams.append(torch.cuda.Stream(device=dev))
             self.prio_streams.append(torch.cuda.Stream(device=dev, priority=min(lowest, max(highest, highest + k))))
         self.kernel_launches = 0

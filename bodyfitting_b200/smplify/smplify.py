@@ -35,7 +35,7 @@ class SMPLify(object):
                  gender='male', use_mask=False, device=torch.device('cuda'), debug=True,
                  model_data=None, gmm=None, J_regressor_extra=None, data_root='data', dense_every_iter=False,
                  concurrent_parts=None, concurrent_min_part=2048, temporal_weight=0.0, halo_exchange=None, halo=None,
-                 copy_outputs=None, graph=None):
+                 copy_outputs=None, graph=None, sort_frames=None):
         if age != 'adult':
             raise NotImplementedError("only age='adult' is supported (kid template: smplify.py:114-115)")
         self.device = torch.device(device)
@@ -72,6 +72,7 @@ class SMPLify(object):
         # exceed 32 MB (~250 SMPL-X frames; fresh pages cost ~0.2 ms per MB: the 160 MB of a 1,250-frame shard took 36 ms to copy,
         # 2.5x the fit itself -- large batches get views, and the docstring of __call__ says so)
         self.copy_outputs = copy_outputs
+        self.sort_frames = sort_frames    # None: SMPL-X batches are processed in contour-row order (engine.FitSession), False: as given
         self.graph = graph            # None: CUDA-graph replay of the whole fit unless BODYFIT_GRAPH=0; False: direct launches
         # batches of >= 4096 frames are fitted as up to this many staggered parts on their own streams (1 = one batch)
         if concurrent_parts is None:
@@ -288,12 +289,12 @@ class SMPLify(object):
                 self._sess = ConcurrentFitSession(self.model, B, Nv, self.num_iters, imsize=imsize, return_vertices=return_vertices,
                                                   dense_every_iter=self.dense_every_iter, n_parts=n_parts,
                                                   min_part=self.concurrent_min_part, lead=self.concurrent_lead,
-                                                  taper=self.concurrent_taper, graph=self.graph)
+                                                  taper=self.concurrent_taper, graph=self.graph, sort_frames=self.sort_frames)
             else:
                 self._sess = FitSession(self.model, B, Nv, self.num_iters, imsize=imsize,
                                         return_vertices=return_vertices, dense_every_iter=self.dense_every_iter,
                                         temporal_weight=self.temporal_weight, halo_exchange=self.halo_exchange, halo=self.halo,
-                                        graph=self.graph)
+                                        graph=self.graph, sort_frames=self.sort_frames)
             self._sess_key = key
             self._pinned = {}
         return self._sess

@@ -40,7 +40,7 @@ extern "C" {
 #define BF_ECUDA    -2   /* a CUDA runtime call / launch failed            */
 #define BF_EARCH    -3   /* device is not sm_100 (no fallback exists)      */
 
-#define BF_ABI_VERSION 16
+#define BF_ABI_VERSION 17
 #define BF_F_WORLD 1   /* forward outputs in world space: (x + transl) * scale * constant_scale */
 #define BF_F_TC    2   /* run the blend-shape contractions on tcgen05 tensor cores (3xTF32) */
 #define BF_F_SKIN_FUSED 4  /* bf_frame_loss_backward skins the frame's live vertices itself from vposed (after bf_blend_forward) */
@@ -154,6 +154,9 @@ typedef struct BfFrames {
     uint32_t*    blk_mask;   /* [2, ceil(B/128)] (or NULL): per 128-frame tile the OR of lv_blk over its frames' yaw rows -- the
                                 16-vertex blocks of the active set the blend GEMMs have to touch for that tile.  Written by the pose
                                 forward (buffer = iteration parity), cleared by the per-frame kernel; zero before the first iteration */
+    const int32_t* frame_index; /* [B] (or NULL = identity): row of `kp` that belongs to frame b.  The host may process the frames
+                                   of a batch in any order (and re-order them between iterations: only theta / adam_m / adam_v rows
+                                   move); the 13 KB keypoint rows stay where they are behind this index */
     int64_t      ws_floats;
     double lr_ts, lr, beta1, beta2, eps;   /* Adam hyper-parameters (python floats in the reference: smplify.py:167-174) */
     int32_t B, Nv, ld_v, iter;
@@ -227,6 +230,10 @@ int     bf_model_destroy(BfModel* m);
 int64_t bf_workspace_bytes(const BfModel* m, int B, int Nv, int opts, int n_trace);
 int     bf_frames_bind(const BfModel* m, int B, int Nv, int opts, int n_trace, void* workspace, int64_t bytes, BfFrames* out,
                        void* stream);
+
+/* every kernel node of a captured cudaGraph_t gets launch priority `priority` (stream priority scale); returns the number of
+ * nodes changed or a negative code.  For hosts that replay several part graphs concurrently and want them to finish in order. */
+int bf_graph_set_kernel_priority(void* cuda_graph, int priority);
 
 /* ---- input packing (so that no host-framework arithmetic sits on the path) ---------------------------------
  * detections [B,Nv,K,3] (x, y, conf) in the caller's layout -> kp [B,K,Nv,3] (x, y, effective weight): conf^2 for the body,

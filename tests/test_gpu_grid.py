@@ -306,13 +306,13 @@ def test_mesh_grid_module_drop_in_six_functions():
     rng = np.random.RandomState(2)
     qi = (rng.rand(2000, 3) * (hi - lo) * 1.2 + lo - 0.1 * (hi - lo)).astype(np.float32)
     signs = s.inside(torch.from_numpy(qi).cuda()).cpu().numpy()
-    want = gp.inside_bruteforce(qi, v, f)
-    assert (signs == np.where(want, 1.0, -1.0)).mean() > 0.999
+    want, _ = gp.inside_bruteforce(qi, v, f)
+    assert (signs == want).mean() > 0.999
     ro = (rng.rand(1500, 3) * (hi - lo) * 2.0 + lo - 0.5 * (hi - lo)).astype(np.float32)
     rd = rng.randn(1500, 3).astype(np.float32)
     hit = s.rays(torch.from_numpy(ro).cuda(), torch.from_numpy(rd).cuda())
     assert hit.dtype == torch.bool
-    assert (hit.cpu().numpy() == gp.ray_any_bruteforce(ro, rd, v, f)).mean() > 0.999
+    assert (hit.cpu().numpy() == gp.ray_any_bruteforce(ro, rd, v, f)[0]).mean() > 0.999
     # non-CUDA tensors are rejected like the reference's CHECK_CUDA
     with pytest.raises(RuntimeError):
         mg.search_inside_mesh(torch.zeros(4, 3), s.verts, s.faces, s.tri_num, s.tri_idx, s.num, s.minmax, float(s.step), torch.zeros(4).cuda())
