@@ -514,7 +514,7 @@ def run_ours(args):
     def step_e2e():
         out = fit(*host_args, use_frames=list(range(NV)), imsize=512)
         if world > 1:
-            gather_frames(sess.theta, F_total)
+            gather_frames(fit.session(F, NV, 512, True, host_io=True).theta, F_total)
         return out
 
     sampler = ClockSampler(local)

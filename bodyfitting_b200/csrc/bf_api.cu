@@ -102,6 +102,8 @@ int bf_skin_forward(const BfModel* m, const BfFrames* f, int use_full, void* str
         // without a v_posed buffer (inference) the blend goes to f->verts and is skinned in place
         float* vp = f->vposed ? f->vposed : f->verts;
         rc = bf_blend_forward_tc(m, vs, f, vp, (cudaStream_t)stream); if (rc) return rc;
+        rc = bf_launch_skin_frame(0, m, vs, f, vp, f->verts, nullptr, nullptr, 0, (f->flags & BF_F_WORLD) ? 1 : 0, 0, (cudaStream_t)stream);
+        if (rc != 1) return rc;
         return bf_launch_skin_rows(0, vs, m->J, f->A, vp, f->verts, nullptr, nullptr, f->B, f->ld_v, 0,
                                    (f->flags & BF_F_WORLD) ? f->theta : nullptr, m->NP, f->constant_scale, (cudaStream_t)stream);
     }
@@ -201,8 +203,10 @@ int bf_skin_backward_parts(const BfModel* m, const BfFrames* f, int use_full, in
     }
     if ((parts & 1) && bf_tc_ready_bwd(vs, f)) {
         // tensor-core mode: only the 3xTF32 split of dvp is consumed (by the blend backward GEMM)
-        rc = bf_launch_skin_rows(1, vs, m->J, f->A, f->dverts, nullptr, f->dvp_hi, f->dvp_lo, f->B, f->ld_v, vs->ldn,
-                                 nullptr, m->NP, 0.f, s);
+        rc = bf_launch_skin_frame(1, m, vs, f, f->dverts, nullptr, f->dvp_hi, f->dvp_lo, vs->ldn, 0, 0, s);
+        if (rc == 1)
+            rc = bf_launch_skin_rows(1, vs, m->J, f->A, f->dverts, nullptr, f->dvp_hi, f->dvp_lo, f->B, f->ld_v, vs->ldn,
+                                     nullptr, m->NP, 0.f, s);
         if (rc) return rc;
     } else if (parts & 1) {
         const dim3 grid((vs->n + 255) / 256, (f->B + DV_FB - 1) / DV_FB);
@@ -399,6 +403,21 @@ int bf_pose_backward(const BfModel* m, const BfFrames* f, int flags, void* strea
 int bf_lbs_forward(const BfModel* m, const BfFrames* f, void* stream) {
     BF_NVTX();
     int rc = bf_pose_forward(m, f, stream); if (rc) return rc;
+    const BfVSet* vs = &m->full;
+    if (f->joints && bf_tc_ready_fwd(vs, f) && f->verts && f->Jtr) {
+        // blend GEMM, then ONE per-frame kernel: skinning (+ world transform) and the output joints of the frame
+        rc = check_vset(vs, f); if (rc) return rc;
+        float* vp = f->vposed ? f->vposed : f->verts;
+        rc = bf_blend_forward_tc(m, vs, f, vp, (cudaStream_t)stream); if (rc) return rc;
+        rc = bf_launch_skin_frame(0, m, vs, f, vp, f->verts, nullptr, nullptr, 0, (f->flags & BF_F_WORLD) ? 1 : 0, 1, (cudaStream_t)stream);
+        if (rc == 2) return BF_OK;                         // joints done
+        if (rc == BF_OK) return bf_joints_forward(m, f, 1, stream);
+        if (rc != 1) return rc;
+        rc = bf_launch_skin_rows(0, vs, m->J, f->A, vp, f->verts, nullptr, nullptr, f->B, f->ld_v, 0,
+                                 (f->flags & BF_F_WORLD) ? f->theta : nullptr, m->NP, f->constant_scale, (cudaStream_t)stream);
+        if (rc) return rc;
+        return bf_joints_forward(m, f, 1, stream);
+    }
     rc = bf_skin_forward(m, f, 1, stream); if (rc) return rc;
     if (f->joints) rc = bf_joints_forward(m, f, 1, stream);
     return rc;

@@ -275,9 +275,14 @@ class FitSession(object):
         self.fb.bind('halo_next', nxt)
 
     def _dense_forward(self):
+        n = 0
+        sms = torch.cuda.get_device_properties(self.model.device).multi_processor_count
         for fbf in self.chunks:
             fbf.call('bf_lbs_forward')
-        return (4 if self.model.tensor_cores else 3) * len(self.chunks)     # pose, blend GEMM (+ row skinning), joints
+            # pose, blend GEMM, per-frame skinning with the output joints fused in (a separate joints kernel when the frames
+            # alone do not fill the SMs and the vertex range is cut into slabs)
+            n += (3 if fbf.B * 1 > 2 * sms else 4) if self.model.tensor_cores else 3
+        return n
 
     def _body(self):
         """Every launch of one run, on the current stream (captured once, or issued directly)."""
