@@ -366,7 +366,7 @@ def config5_bench(rank, world, n_subjects=8, searches=100):
         vd, fd = torch.from_numpy(v).cuda(), torch.from_numpy(f).cuda()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        g = MeshGridSearcher(vd, fd)
+        g = MeshGridSearcher(vd, fd)                       # on the rank's own GPU (the tensors' device)
         torch.cuda.synchronize()
         build_ms.append(1e3 * (time.perf_counter() - t0))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -607,7 +607,7 @@ def run_ours(args):
         os._exit(0)
     timer = None
     if not args.no_extras:
-        timer = threading.Timer(420.0 if world > 1 else 900.0, emergency)
+        timer = threading.Timer(240.0 if world > 1 else 900.0, emergency)
         timer.daemon = True
         timer.start()
         barrier()

@@ -664,7 +664,7 @@ int bf_frames_bind(const BfModel* m, int B, int Nv, int opts, int n_trace, void*
     BF_REQUIRE(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
     const int64_t need = bf_workspace_bytes(m, B, Nv, opts, n_trace);
     BF_REQUIRE(bytes >= need, "workspace smaller than bf_workspace_bytes()");
-    if (cudaMemsetAsync(workspace, 0, (size_t)need, (cudaStream_t)stream) != cudaSuccess) { bf_set_error("bf_frames_bind: memset failed"); return BF_ECUDA; }
+    if (cudaMemsetAsync(workspace, 0, (size_t)need, (cudaStream_t)stream) != cudaSuccess) BF_CUDA_FAIL("memset failed");
     FrameCarver c{(char*)workspace, 0, false};
     carve_frames(m, B, Nv, opts, n_trace, c, out);
     return BF_OK;
@@ -789,7 +789,7 @@ int bf_grid_count(const BfGrid* g, int32_t* counts, void* stream) {
     int rc = check_grid(g); if (rc) return rc;
     BF_REQUIRE(counts, "counts is null");
     cudaStream_t s = (cudaStream_t)stream;
-    if (cudaMemsetAsync(counts, 0, sizeof(int32_t) * g->ncell, s) != cudaSuccess) { bf_set_error("memset failed"); return BF_ECUDA; }
+    if (cudaMemsetAsync(counts, 0, sizeof(int32_t) * g->ncell, s) != cudaSuccess) BF_CUDA_FAIL("memset failed");
     k_grid_insert<<<(g->Fs + 255) / 256, 256, 0, s>>>(*g, counts, nullptr, nullptr);
     BF_LAUNCH_CHECK();
     k_grid_scan<<<1, 1024, 0, s>>>(counts, g->cell_start, g->ncell);
@@ -802,7 +802,7 @@ int bf_grid_fill(const BfGrid* g, int32_t* cursor, void* stream) {
     int rc = check_grid(g); if (rc) return rc;
     BF_REQUIRE(cursor && g->cell_tris, "cursor / cell_tris is null");
     cudaStream_t s = (cudaStream_t)stream;
-    if (cudaMemsetAsync(cursor, 0, sizeof(int32_t) * g->ncell, s) != cudaSuccess) { bf_set_error("memset failed"); return BF_ECUDA; }
+    if (cudaMemsetAsync(cursor, 0, sizeof(int32_t) * g->ncell, s) != cudaSuccess) BF_CUDA_FAIL("memset failed");
     k_grid_insert<<<(g->Fs + 255) / 256, 256, 0, s>>>(*g, cursor, g->cell_start, g->cell_tris);
     BF_LAUNCH_CHECK();
     k_grid_sort<<<(g->ncell + 255) / 256, 256, 0, s>>>(g->cell_start, g->cell_tris, g->ncell);
@@ -886,7 +886,7 @@ int bf_smpld_step(const BfGrid* g, const BfSmpld* p, void* stream) {
     BF_LAUNCH_CHECK();
     if (p->trace) {
         if (cudaMemcpyAsync(p->trace + 4 * (size_t)p->iter, p->totals, 4 * sizeof(float), cudaMemcpyDeviceToDevice, s) != cudaSuccess) {
-            bf_set_error("trace copy failed"); return BF_ECUDA;
+            BF_CUDA_FAIL("trace copy failed");
         }
     }
     return BF_OK;
@@ -1082,7 +1082,7 @@ int bf_op_mask_loss(const float* verts_world, int B, int V, const BfMask* k, flo
     k_op_identity_theta<<<(B + 127) / 128, 128, 0, s>>>(scratch, B);
     BF_LAUNCH_CHECK();
     if (cudaMemsetAsync(f.grad, 0, sizeof(float) * 4 * (size_t)B, s) != cudaSuccess || cudaMemsetAsync(loss, 0, sizeof(float) * B, s) != cudaSuccess ||
-        cudaMemsetAsync(dverts, 0, sizeof(float) * 3 * (size_t)V * B, s) != cudaSuccess) { bf_set_error("memset failed"); return BF_ECUDA; }
+        cudaMemsetAsync(dverts, 0, sizeof(float) * 3 * (size_t)V * B, s) != cudaSuccess) BF_CUDA_FAIL("memset failed");
     const size_t n = (size_t)B * k->Nm * k->Nq;
     k_mask_project<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(f, *k, 4);
     BF_LAUNCH_CHECK();

@@ -53,6 +53,11 @@ struct BfRange {
 #define BF_REQUIRE(cond, msg)                                   \
     do { if (!(cond)) { bf_set_error("%s: %s", __func__, msg); return BF_EINVAL; } } while (0)
 
+// a failed runtime call: report it AND clear the runtime's last-error slot, so that the next launch check of an unrelated
+// call does not trip over it
+#define BF_CUDA_FAIL(msg)                                                              \
+    do { cudaError_t e_ = cudaGetLastError(); bf_set_error("%s: %s (%s)", __func__, msg, cudaGetErrorString(e_)); return BF_ECUDA; } while (0)
+
 #define BF_LAUNCH_CHECK()                                                              \
     do { cudaError_t e_ = cudaGetLastError();                                          \
          if (e_ != cudaSuccess) { bf_set_error("%s: launch failed: %s", __func__,      \

@@ -102,9 +102,19 @@ class SMPLify(object):
         assert kp.shape[0] == B, 'keypoints for %d frames, parameters for %d' % (kp.shape[0], B)
         return init_betas, init_poses, kp
 
-    def __call__(self, net_output, c2ws, Ks, keypoints, output_folder=None, use_mask=False, masks=None,
-                 use_frames=[0], mask_frames=[0], keyframe=6, imsize=512, use_mesh=False, meshfile=None,
-                 displacement=False, return_vertices=True, as_numpy=True):
+    def __call__(self, *args, **kwargs):
+        """Same signature and result dict as the reference's SMPLify.__call__ (smplify/smplify.py:84-86,216-226); see _fit.
+        Runs with ``self.device`` as the current CUDA device (the library launches on the current device's streams), whatever
+        device the caller has selected.  Host results: fresh numpy arrays, except for batches whose results exceed 32 MB,
+        which are returned as views of session-owned pinned buffers valid until the next call (``copy_outputs``)."""
+        if self.device.type == 'cuda':
+            with torch.cuda.device(self.device):
+                return self._fit(*args, **kwargs)
+        return self._fit(*args, **kwargs)
+
+    def _fit(self, net_output, c2ws, Ks, keypoints, output_folder=None, use_mask=False, masks=None,
+             use_frames=[0], mask_frames=[0], keyframe=6, imsize=512, use_mesh=False, meshfile=None,
+             displacement=False, return_vertices=True, as_numpy=True):
         if use_mask or use_mesh:
             return self._fit_dense(net_output, c2ws, Ks, keypoints, imsize, as_numpy, use_mesh=use_mesh, meshfile=meshfile,
                                    displacement=displacement, use_mask=use_mask, masks=masks, use_frames=use_frames,

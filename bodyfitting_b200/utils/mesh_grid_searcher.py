@@ -11,13 +11,17 @@ from ..engine import _stream
 
 
 class MeshGridSearcher(object):
-    def __init__(self, verts=None, faces=None, device='cuda:0'):
-        self.device = torch.device(device)
+    def __init__(self, verts=None, faces=None, device=None):
+        """``device``: where the grid lives; default = the device of ``verts`` if it is a CUDA tensor, else the CURRENT CUDA
+        device (the reference hard-codes 'cuda:0', utils/mesh_grid_searcher.py:52,56 -- wrong on every rank but the first)."""
+        self.device = None if device is None else torch.device(device)
         if verts is not None and faces is not None:
             self.set_mesh(verts, faces, device)
 
-    def set_mesh(self, verts, faces, device='cuda:0'):
+    def set_mesh(self, verts, faces, device=None):
         _lib.require_device()
+        if device is None:
+            device = verts.device if (torch.is_tensor(verts) and verts.is_cuda) else torch.device('cuda', torch.cuda.current_device())
         dev = torch.device(device)
         self.device = dev
         verts = torch.as_tensor(np.asarray(verts) if not torch.is_tensor(verts) else verts).float().to(dev).reshape(-1, 3).contiguous()

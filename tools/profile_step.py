@@ -19,15 +19,16 @@ ap.add_argument('--frames', type=int, default=10000)
 ap.add_argument('--iters', type=int, default=3)
 ap.add_argument('--dense', action='store_true', help='also run the SMPL 1024-frame dense LBS operator fwd/bwd')
 a = ap.parse_args()
-fit = SMPLify(smpl_type='smplx', num_iters=a.iters, gender='neutral', model_data=syn.make_model('smplx', 0), gmm=syn.make_gmm(0), concurrent_parts=1)
+# one batch, one stream, direct launches (no graph): every kernel of the fit appears as its own launch in the ncu list
+fit = SMPLify(smpl_type='smplx', num_iters=a.iters, gender='neutral', model_data=syn.make_model('smplx', 0), gmm=syn.make_gmm(0),
+              concurrent_parts=1, graph=False)
 pm = fit.model
 wl = bench.build_workload(pm, a.frames, seed=100)
 sess = fit.session(a.frames, 8, 512, True)
-sess.set_inputs(pack_keypoints(torch.from_numpy(wl['kp']).cuda(), True), torch.from_numpy(pack_cameras(wl['c2ws'], wl['Ks'])).cuda())
-poses = torch.from_numpy(wl['init_pose']).cuda()
-theta0 = pm.pack_theta(poses[:, :3], poses[:, 3:3 + pm.nbody], torch.from_numpy(wl['init_betas']).cuda())
+T = lambda k: torch.from_numpy(wl[k]).cuda()
+sess.load_inputs(T('kp'), torch.from_numpy(pack_cameras(wl['c2ws'], wl['Ks'])).cuda(), T('init_pose'), T('init_betas'))
 for _ in range(2):
-    sess.run(theta0)
+    sess.run()
 torch.cuda.synchronize()
 if a.dense:
     print(bench.dense_lbs_bench(0, 6457.1))
