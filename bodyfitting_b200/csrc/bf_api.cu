@@ -33,7 +33,7 @@ static int check_model(const BfModel* m, const BfFrames* f) {
     BF_REQUIRE(m && f, "null model / frames");
     BF_REQUIRE(m->J > 0 && m->J <= BF_MAXJ, "J out of range");
     BF_REQUIRE(m->NS > 0 && m->NS <= BF_MAXNS && m->NB <= m->NS, "NS/NB out of range");
-    BF_REQUIRE(m->NP == theta_layout(m->is_smplx).np && m->NP <= BF_MAXNP, "NP does not match theta layout");
+    BF_REQUIRE(m->NP == theta_layout(m->is_smplx, m->NB).np && m->NP <= BF_MAXNP, "NP does not match theta layout");
     BF_REQUIRE(m->Kp % 16 == 0 && m->Kp >= m->P + m->NS + 1, "Kp must be a multiple of 16 covering P+NS+1");
     BF_REQUIRE(m->P == (m->J - 1) * 9, "P != 9(J-1)");
     BF_REQUIRE(m->parents && m->lvl_ptr && m->lvl_j && m->child_ptr && m->child_idx, "kinematic tree tables missing");

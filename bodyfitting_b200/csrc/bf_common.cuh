@@ -67,15 +67,16 @@ struct BfRange {
 struct ThetaLayout {
     int nbody, off_betas, off_leye, off_reye, off_lh, off_rh, np;
 };
-__host__ __device__ __forceinline__ ThetaLayout theta_layout(int is_smplx) {
+// nbetas: 10, or 11 for the SMPL kid model (age='kid': the SMIL template difference is an extra shape direction)
+__host__ __device__ __forceinline__ ThetaLayout theta_layout(int is_smplx, int nbetas = 10) {
     ThetaLayout t;
     t.nbody = is_smplx ? 63 : 69;
     t.off_betas = 7 + t.nbody;
-    t.off_leye = t.off_betas + 10;
+    t.off_leye = t.off_betas + nbetas;
     t.off_reye = t.off_leye + 3;
     t.off_lh = t.off_reye + 3;
     t.off_rh = t.off_lh + 6;
-    t.np = is_smplx ? t.off_rh + 6 : t.off_betas + 10;
+    t.np = is_smplx ? t.off_rh + 6 : t.off_betas + nbetas;
     return t;
 }
 

@@ -41,7 +41,7 @@ __device__ __forceinline__ void pose_forward_from_smem(const BfModel& m, PoseSme
 
 __device__ __forceinline__ void pose_forward_warp(const BfModel& m, const float* __restrict__ theta_row,
                                                   PoseSmem& S, int lane) {
-    const int np = theta_layout(m.is_smplx).np;
+    const int np = theta_layout(m.is_smplx, m.NB).np;
     for (int i = lane; i < np; i += 32) S.th[i] = theta_row[i];
     __syncwarp();
     pose_forward_from_smem(m, S, lane);
@@ -49,7 +49,7 @@ __device__ __forceinline__ void pose_forward_warp(const BfModel& m, const float*
 
 // theta already in S.th
 __device__ __forceinline__ void pose_forward_from_smem(const BfModel& m, PoseSmem& S, int lane) {
-    const ThetaLayout L = theta_layout(m.is_smplx);
+    const ThetaLayout L = theta_layout(m.is_smplx, m.NB);
     const int J = m.J;
     // full pose
     for (int i = lane; i < 3 * J; i += 32) {
@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(128) k_pose_bwd(BfModel m, BfFrames f, int fla
     float* const drel = S.Gt;
     float* const dfp = S.fp;
     const int J = m.J;
-    const ThetaLayout L = theta_layout(m.is_smplx);
+    const ThetaLayout L = theta_layout(m.is_smplx, m.NB);
     // ---- everything this frame reads from HBM is requested up front: the saved forward state by bulk copy (TMA), the
     // loss kernel's dA / dJtr rows, the Adam moments and the GMM gradient into registers; nothing below waits on HBM again
     // (J == BF_MAXJ: the row is one contiguous block of PoseSmem; smaller skeletons take the plain loops below)
@@ -400,17 +400,20 @@ __global__ void __launch_bounds__(128) k_pose_bwd(BfModel m, BfFrames f, int fla
 
     // betas: rest-joint path + shape rows of the blend GEMM
     {
-        // lanes (l, part): 3 parts split the 3J rest-joint coordinates, combined in a fixed order
+        // lanes (l, part): 3 parts (2 when more than 10 betas: the kid model) split the 3J rest-joint coordinates, combined
+        // in a fixed order
         const int l = lane % m.NB, part = lane / m.NB;
-        const int nq = 3 * J, per = (nq + 2) / 3;
+        const int nparts = 3 * m.NB <= 32 ? 3 : 2;
+        const int nq = 3 * J, per = (nq + nparts - 1) / nparts;
         float acc = 0.f;
-        if (part < 3) {
+        if (part < nparts) {
             const int q1 = min(nq, (part + 1) * per);
 #pragma unroll 11
             for (int q = part * per; q < q1; ++q) acc += __ldg(m.Jd + q * m.NS + l) * dJr_s[q];
         }
         const float a1 = __shfl_sync(0xffffffffu, acc, (lane + m.NB) & 31);
-        const float a2 = __shfl_sync(0xffffffffu, acc, (lane + 2 * m.NB) & 31);
+        const float a2s = __shfl_sync(0xffffffffu, acc, (lane + 2 * m.NB) & 31);
+        const float a2 = nparts > 2 ? a2s : 0.f;
         if (lane < m.NB) g[L.off_betas + lane] = f.dpf[(size_t)b * m.Kp + m.P + lane] + ((acc + a1) + a2);
     }
     for (int i = lane; i < 3 + L.nbody; i += 32) g[4 + i] = dfp[i];      // global_orient + body_pose

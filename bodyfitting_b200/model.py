@@ -75,7 +75,7 @@ class PreparedModel(object):
     """numpy tables -> device tensors -> BfModel struct (kept alive by this object)."""
 
     def __init__(self, smpl_type, data, gmm=None, J_regressor_extra=None, device='cuda', num_betas=10,
-                 num_expression=10, tensor_cores=None, gender='neutral'):
+                 num_expression=10, tensor_cores=None, gender='neutral', age='adult', kid_template=None):
         assert smpl_type in ('smpl', 'smplx')
         self.smpl_type = smpl_type
         self.is_smplx = smpl_type == 'smplx'
@@ -95,10 +95,28 @@ class PreparedModel(object):
         assert all(parents[j] < j for j in range(1, J)), 'kinematic tree must be topologically sorted'
         P = (J - 1) * 9
         NB = num_betas
-        NS = NB + (num_expression if self.is_smplx else 0)
         sd_all = np.asarray(data['shapedirs'], dtype=np.float32)
         if sd_all.ndim == 2:
             sd_all = sd_all[:, :, None]
+        self.age = age
+        if age == 'kid':
+            # smplx's kid model (reference call site smplify/smplify.py:50-56: age=, kid_template_path=): the mean-centred SMIL
+            # template minus the adult template becomes an extra, 11th shape direction; betas are then [B,11]
+            assert not self.is_smplx, "age='kid' is passed to the SMPL branch only (smplify.py:50-56)"
+            if kid_template is None:
+                raise FileNotFoundError("age='kid' needs the SMIL template (kid_template= array or path; reference: config.SMIL_MODEL_DIR)")
+            kt_ = kid_template
+            if isinstance(kt_, (str, os.PathLike)):
+                kt_ = np.load(kt_, allow_pickle=True)
+                kt_ = kt_.item()['v_template'] if getattr(kt_, 'dtype', None) == object else kt_
+            kt_ = np.array(kt_, dtype=np.float32)
+            assert kt_.shape == vt.shape, 'kid template has %s vertices, model %s' % (kt_.shape, vt.shape)
+            kt_ = kt_ - kt_.mean(axis=0)
+            sd_all = np.concatenate([sd_all[:, :, :NB], (kt_ - vt)[:, :, None]], axis=2)
+            NB = NB + 1
+        elif age != 'adult':
+            raise ValueError("age must be 'adult' or 'kid'")
+        NS = NB + (num_expression if self.is_smplx else 0)
         if self.is_smplx and sd_all.shape[-1] >= K.SHAPE_SPACE_DIM + num_expression:
             # official files: the expression directions follow the 300 shape directions (smplx: SHAPE_SPACE_DIM)
             sd = np.concatenate([sd_all[:, :, :NB], sd_all[:, :, K.SHAPE_SPACE_DIM:K.SHAPE_SPACE_DIM + num_expression]], -1)
@@ -113,7 +131,7 @@ class PreparedModel(object):
         self.V, self.J, self.P, self.NB, self.NS = V, J, P, NB, NS
         self.Kdim = P + NS + 1
         self.Kp = _round_up(self.Kdim, 16)
-        self.NP = 98 if self.is_smplx else 86
+        self.NP = 7 + (63 if self.is_smplx else 69) + NB + (18 if self.is_smplx else 0)      # 98 / 86 (87 for the kid model)
         self.nbody = 63 if self.is_smplx else 69
         self.parents = parents
 
@@ -471,8 +489,11 @@ class PreparedModel(object):
         dev, dt = self.device, torch.float32
         z = lambda n: torch.zeros(B, n, device=dev, dtype=dt)
         f = lambda t, n: z(n) if t is None else t.reshape(B, n).to(device=dev, dtype=dt)
+        bt = betas.reshape(B, -1).to(device=dev, dtype=dt)
+        if bt.shape[1] < self.NB:                       # kid model: 11 betas, the network gives 10
+            bt = torch.cat([bt, torch.zeros(B, self.NB - bt.shape[1], device=dev, dtype=dt)], dim=1)
         parts = [f(transl, 3), torch.ones(B, 1, device=dev, dtype=dt) if scale is None else f(scale, 1),
-                 f(global_orient, 3), f(body_pose, self.nbody), f(betas, 10)]
+                 f(global_orient, 3), f(body_pose, self.nbody), bt]
         if self.is_smplx:
             parts += [f(leye, 3), f(reye, 3), f(lhand, 6), f(rhand, 6)]
         return torch.cat(parts, dim=1).contiguous()
@@ -480,9 +501,9 @@ class PreparedModel(object):
     def split_theta(self, theta):
         nb = self.nbody
         out = dict(transl=theta[:, 0:3], scale=theta[:, 3:4], global_orient=theta[:, 4:7],
-                   body_pose=theta[:, 7:7 + nb], betas=theta[:, 7 + nb:17 + nb])
+                   body_pose=theta[:, 7:7 + nb], betas=theta[:, 7 + nb:7 + nb + self.NB])
         if self.is_smplx:
-            o = 17 + nb
+            o = 7 + nb + self.NB
             out.update(leye_pose=theta[:, o:o + 3], reye_pose=theta[:, o + 3:o + 6],
                        left_hand_pose=theta[:, o + 6:o + 12], right_hand_pose=theta[:, o + 12:o + 18])
         return out

@@ -35,9 +35,11 @@ class SMPLify(object):
                  gender='male', use_mask=False, device=torch.device('cuda'), debug=True,
                  model_data=None, gmm=None, J_regressor_extra=None, data_root='data', dense_every_iter=False,
                  concurrent_parts=None, concurrent_min_part=2048, temporal_weight=0.0, halo_exchange=None, halo=None,
-                 copy_outputs=None, graph=None, sort_frames=None):
-        if age != 'adult':
-            raise NotImplementedError("only age='adult' is supported (kid template: smplify.py:114-115)")
+                 copy_outputs=None, graph=None, sort_frames=None, kid_template=None):
+        if age not in ('adult', 'kid'):
+            raise ValueError("age must be 'adult' or 'kid' (smplify.py:23,112-115)")
+        if age == 'kid' and smpl_type != 'smpl':
+            raise ValueError("age='kid' exists for smpl_type='smpl' only: the reference passes it to the SMPL branch (smplify.py:50-56)")
         self.device = torch.device(device)
         self.debug = debug
         self.gender = gender
@@ -58,8 +60,10 @@ class SMPLify(object):
         if smpl_type == 'smpl' and J_regressor_extra is None:
             fn = os.path.join(data_root, 'J_regressor_extra.npy')      # config.py:1, models/smpl.py:62
             J_regressor_extra = np.load(fn) if os.path.exists(fn) else None
+        if age == 'kid' and kid_template is None:
+            kid_template = os.path.join(data_root, 'smil', 'smil_web.pkl')           # config.SMIL_MODEL_DIR (config.py:5)
         self.model = PreparedModel(smpl_type, model_data, gmm=gmm, J_regressor_extra=J_regressor_extra,
-                                   device=self.device, gender=gender)
+                                   device=self.device, gender=gender, age=age, kid_template=kid_template)
         self.smpl_faces = self.model.faces.astype(np.int32).reshape(1, -1, 3)
         self.last_trace = None
         self.dense_every_iter = dense_every_iter
@@ -89,6 +93,8 @@ class SMPLify(object):
     def _pack_inputs(self, net_output, keypoints):
         init_betas, init_poses = net_output
         init_betas = torch.as_tensor(init_betas, dtype=torch.float32).reshape(-1, 10)
+        if self.age == 'kid':                                  # the kid model starts from zero betas (11 of them, smplify.py:114-115)
+            init_betas = torch.zeros_like(init_betas)
         init_poses = torch.as_tensor(init_poses, dtype=torch.float32)
         init_poses = init_poses.reshape(init_betas.shape[0], -1)
         B = init_poses.shape[0]

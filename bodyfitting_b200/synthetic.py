@@ -199,7 +199,20 @@ def write_data_dir(root, seed=0, model_types=('smpl', 'smplx')):
     for mt in model_types:
         m = make_model(mt, seed)
         save_model_npz(m, os.path.join(root, mt, '%s_NEUTRAL.npz' % mt.upper()))
+    if 'smpl' in model_types:                                  # config.SMIL_MODEL_DIR: the kid template (age='kid')
+        os.makedirs(os.path.join(root, 'smil'), exist_ok=True)
+        with open(os.path.join(root, 'smil', 'smil_web.pkl'), 'wb') as f:
+            np.save(f, make_kid_template(seed))
     return root
+
+
+def make_kid_template(seed=0):
+    """A synthetic stand-in for the SMIL infant template (smplx ``kid_template_path``): the adult SMPL template shrunk
+    and perturbed, [6890,3] float32 (smplx loads it with np.load, mean-centres it and uses its difference to the adult
+    template as an 11th shape direction)."""
+    vt = make_model('smpl', seed)['v_template']
+    rng = np.random.RandomState(seed + 77)
+    return (vt * np.array([0.55, 0.5, 0.6], np.float32) + 0.05 + rng.standard_normal(vt.shape).astype(np.float32) * 0.002).astype(np.float32)
 
 
 # --- scene --------------------------------------------------------------------

@@ -107,7 +107,7 @@ class _Cv2ThreeReturn(object):
 
 
 def run_reference_fit(data_parent, smpl_type, init_betas, init_poses, c2ws, Ks, keypoints, num_iters=100,
-                      imsize=512, record=True, masks=None, mask_frames=None):
+                      imsize=512, record=True, masks=None, mask_frames=None, age='adult'):
     """One frame through the verbatim ``SMPLify.__call__`` (smplify/smplify.py:84-250) on CPU.
     ``keypoints`` = list (per view) of OpenPose dicts.  Returns (result dict, per-iteration
     total-loss list, per-iteration loss-term dicts)."""
@@ -127,7 +127,7 @@ def run_reference_fit(data_parent, smpl_type, init_betas, init_poses, c2ws, Ks, 
         if record:
             ns.smplify.multiview_keypoint_loss = recording
         try:
-            fitter = ns.smplify.SMPLify(smpl_type=smpl_type, num_iters=num_iters, gender='neutral',
+            fitter = ns.smplify.SMPLify(smpl_type=smpl_type, num_iters=num_iters, gender='neutral', age=age,
                                         device=torch.device('cpu'), debug=False)
             nv = len(c2ws)
             extra = {}

@@ -28,10 +28,11 @@ def _find(model_path, model_type, gender):
 
 class SMPL(SMPLLayer):
     def __init__(self, model_path, batch_size=1, gender='neutral', create_transl=True, joint_mapper=None,
-                 dtype=None, **ignored):
+                 dtype=None, age='adult', kid_template_path='', **ignored):
         import torch
         super().__init__(_find(model_path, 'smpl', gender), joint_mapper=joint_mapper,
-                         create_transl=create_transl, batch_size=batch_size, dtype=dtype or torch.float32)
+                         create_transl=create_transl, batch_size=batch_size, dtype=dtype or torch.float32,
+                         age=age, kid_template_path=kid_template_path)
 
 
 class SMPLX(SMPLXLayer):

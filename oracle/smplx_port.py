@@ -153,9 +153,20 @@ class SMPLLayer(nn.Module):
     NUM_BODY_JOINTS = 23
 
     def __init__(self, data, num_betas=10, dtype=torch.float32, joint_mapper=None, create_transl=False,
-                 batch_size=1):
+                 batch_size=1, age='adult', kid_template_path=''):
         super().__init__()
         data = _load(data)
+        if age == 'kid':
+            # smplx (>= 0.1.26) kid model [recalled]: v_template_smil = np.load(kid_template_path); mean-centred; its
+            # difference to the adult template is appended to the first num_betas shape directions; num_betas += 1
+            data = dict(data)
+            smil = kid_template_path if not isinstance(kid_template_path, str) else np.load(kid_template_path, allow_pickle=True)
+            smil = np.array(smil, dtype=np.float64)
+            smil -= np.mean(smil, axis=0)
+            diff = np.expand_dims(smil - np.asarray(data['v_template'], dtype=np.float64), axis=2)
+            data['shapedirs'] = np.concatenate((np.asarray(data['shapedirs'])[:, :, :num_betas], diff), axis=2)
+            num_betas = num_betas + 1
+        self.num_betas = num_betas
         V = data['v_template'].shape[0]
         self.faces = np.asarray(data['f'])
         self.register_buffer('faces_tensor', torch.tensor(self.faces.astype(np.int64)))

@@ -585,3 +585,33 @@ def test_row_sorted_block_masked_fit_equals_plain_order(assets):
     rel = np.abs(outs[True][1][:, pick] - trace) / np.abs(trace)
     assert rel.max() < 2e-5
     assert np.abs(outs[True][0]['pose'][pick] - ref['pose']).max() < 2e-5
+
+
+def test_kid_model_fit(assets):
+    """age='kid' (smplify/smplify.py:50-56,112-115): the SMIL template difference as an 11th shape direction, 11 betas starting
+    at zero -- trajectory and results against the oracle's batched loop (itself bit-exact to the verbatim reference run with
+    age='kid', tests/test_oracle.py)."""
+    from bodyfitting_b200 import synthetic as syn
+    from bodyfitting_b200.smplify.smplify import SMPLify
+    from oracle import fit_port as fp
+    mt, nv, B, N = 'smpl', 4, 5, 40
+    kid = syn.make_kid_template(0)
+    port = fp.FitPort(mt, assets(mt), assets('gmm'), assets('jx'), age='kid', kid_template=kid)
+    sc = make_scene(make_port(assets, mt), mt, B, nv, seed=43)
+    ref, trace = port.fit_batched(sc['init_betas'], sc['init_pose'], sc['c2ws'], sc['Ks'], sc['kp'], num_iters=N)
+    fit = SMPLify(smpl_type=mt, age='kid', kid_template=kid, num_iters=N, gender='neutral', model_data=assets(mt), gmm=assets('gmm'),
+                  J_regressor_extra=assets('jx'))
+    assert fit.model.NB == 11 and fit.model.NP == 87
+    out = fit((sc['init_betas'], sc['init_pose']), list(sc['c2ws']), list(sc['Ks']), sc['kp'], None, imsize=512)
+    tr = fit.last_trace.cpu().numpy()
+    rel = np.abs(tr - trace) / np.abs(trace)
+    print('kid: loss trace max rel', rel.max())
+    assert rel.max() < 2e-5
+    assert out['betas'].shape == (B, 11) and np.abs(out['betas'][:, 10]).max() > 1e-3          # the kid direction is really fitted
+    for k in ('pose', 'betas', 'global_orient', 'global_transl', 'scale'):
+        d = np.abs(np.asarray(out[k]).reshape(B, -1) - np.asarray(ref[k]).reshape(B, -1)).max()
+        print('   kid %-14s max abs diff %.3e' % (k, d))
+        assert d < 5e-5, k
+    assert relerr(out['vertices'], ref['vertices']) < 1e-5
+    with pytest.raises(ValueError):
+        SMPLify(smpl_type='smplx', age='kid', kid_template=kid, model_data=assets('smplx'), gmm=assets('gmm'))

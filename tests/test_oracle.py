@@ -53,6 +53,27 @@ def test_port_bit_exact_vs_verbatim_reference(assets, tmp_path, mt, nv):
 
 
 @pytest.mark.skipif(not rh.available(), reason='/root/reference not present (GPU box)')
+def test_kid_model_port_bit_exact_vs_verbatim_reference(assets, tmp_path):
+    """age='kid' (smplify/smplify.py:50-56,112-115): the verbatim reference builds SMPL(age='kid', kid_template_path=
+    config.SMIL_MODEL_DIR) and starts from 11 zero betas; the restatement follows it bit for bit (the kid shape space itself is
+    smplx's, restated in oracle/smplx_port.py)."""
+    syn.write_data_dir(str(tmp_path / 'data'), seed=0, model_types=('smpl',))
+    kid = syn.make_kid_template(0)
+    port = fp.FitPort('smpl', assets('smpl'), assets('gmm'), assets('jx'), age='kid', kid_template=kid)
+    adult = make_port(assets, 'smpl')
+    sc = make_scene(adult, 'smpl', 1, 4, seed=37)
+    views = syn.keypoints_to_openpose(sc['kp'][0], 'smpl')
+    N = 15
+    res, trace, terms, _ = rh.run_reference_fit(str(tmp_path), 'smpl', sc['init_betas'][0], sc['init_pose'][0], sc['c2ws'],
+                                                sc['Ks'], views, num_iters=N, age='kid')
+    resp, trp = port.fit_frame(sc['init_betas'][0], sc['init_pose'][0], sc['c2ws'], sc['Ks'], views, num_iters=N)
+    assert res['betas'].shape == (11,) and np.abs(res['betas']).max() > 0
+    assert np.array_equal(np.asarray(trace), np.asarray(trp))
+    for k in ('pose', 'betas', 'global_orient', 'global_transl', 'scale', 'joints', 'vertices'):
+        assert np.array_equal(res[k], resp[k]), k
+
+
+@pytest.mark.skipif(not rh.available(), reason='/root/reference not present (GPU box)')
 def test_mask_term_port_bit_exact_vs_verbatim_reference(assets, tmp_path):
     """Silhouette term (use_mask=True, smplify/loss.py:73-130): the restatement run for one frame equals the verbatim
     reference bit for bit (cv2.findContours adapted to OpenCV 4's return arity in the harness)."""
