@@ -309,7 +309,28 @@ def dense_lbs_bench(assets_seed, hbm_peak):
     alg = 4 * (3 * V + 3 * Kout + 72 + 10 + 4) * B            # 83,612 B per frame
     fwd = timed(lambda: fb.call('bf_lbs_forward'))
     bwd = timed(lambda: fb.call('bf_lbs_backward'))
-    return {'config': 'SMPL 6890 verts, 1024 frames (BASELINE config 2), L2 flushed between launches',
+    # the blend GEMM alone against a TF32 peak measured the way MEASURED_PEAKS.json measures bf16 (cuBLAS, 8192^3, best of 5)
+    gemm = {}
+    try:
+        fb.call('bf_pose_forward')
+        g_ms = timed(lambda: fb.call('bf_blend_forward', 1)) if pm.tensor_cores else None
+        old = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        a, bm = torch.randn(8192, 8192, device='cuda'), torch.randn(8192, 8192, device='cuda')
+        torch.matmul(a, bm)
+        tf = max(2 * 8192 ** 3 / (t * 1e-3) / 1e12 for t in time_events(lambda: torch.matmul(a, bm), 5))
+        torch.backends.cuda.matmul.allow_tf32 = old
+        del a, bm
+        gemm = {'tf32_cublas_tflops_measured': tf}
+        if g_ms:
+            fl = 3 * 2.0 * B * pm.Kp * 3 * pm.n_pad_full            # three TF32 MMAs per product (hi*hi + lo*hi + hi*lo)
+            gemm.update(blend_gemm_ms=g_ms, blend_gemm_tf32_tflops=fl / (g_ms * 1e-3) / 1e12,
+                        blend_gemm_frac_of_tf32_peak=fl / (g_ms * 1e-3) / 1e12 / tf,
+                        note='3xTF32: the GEMM issues 3 MMAs per product, so at 100 % of the TF32 peak it would still take '
+                             '%.0f us = %.2f of the HBM roofline for this operator' % (fl / (tf * 1e12) * 1e6, alg / (fl / (tf * 1e12)) / 1e9 / hbm_peak))
+    except Exception as ex:
+        gemm = {'error': repr(ex)}
+    return {'config': 'SMPL 6890 verts, 1024 frames (BASELINE config 2), L2 flushed between launches', 'gemm': gemm,
             'alg_bytes_per_frame': alg // B, 'design': 'v_posed and dv_posed are materialised (+12V B written and read each way); '
             'achieved uses the minimal algorithmic bytes of SURVEY.md 8d',
             'fwd_ms': fwd, 'bwd_ms': bwd, 'fwd_gbs': alg / fwd / 1e6, 'bwd_gbs': alg / bwd / 1e6,
@@ -529,6 +550,29 @@ def run_ours(args):
         dist.all_reduce(t)
         h2d, d2h, launches = (int(x) for x in t.tolist())
 
+    # what the host link gives each rank while all ranks copy at once (pinned memory, 256 MB each way): the end-to-end path
+    # moves 126 KB of vertices per fitted frame, so at several ranks this -- not the GPUs -- bounds `e2e`
+    def link_gbs():
+        nb = 256 << 20
+        hbuf = torch.empty(nb, dtype=torch.uint8, pin_memory=True)
+        dbuf = torch.empty(nb, dtype=torch.uint8, device='cuda')
+        res = []
+        for src, dst in ((dbuf, hbuf), (hbuf, dbuf)):
+            dst.copy_(src, non_blocking=True)
+            barrier()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for _ in range(4):
+                dst.copy_(src, non_blocking=True)
+            e.record()
+            torch.cuda.synchronize()
+            res.append(4 * nb / (s.elapsed_time(e) / 1e3) / 1e9)
+        t = torch.tensor(res, device='cuda', dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return float(t[0]), float(t[1])
+    d2h_gbs, h2d_gbs = link_gbs()
+
     frames_done = F_total * args.steps
     value = frames_done / (ms_dev / 1e3)
     e2e = frames_done / (max(ms_e2e / 1e3, wall_e2e))
@@ -566,6 +610,8 @@ def run_ours(args):
             'clocks': clocks,
             'e2e': {'value': e2e, 'unit': 'frames/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
                     'ms_per_step': 1e3 * max(ms_e2e / 1e3, wall_e2e) / args.steps,
+                    'host_link': {'d2h_gbs_per_rank_all_ranks_copying': d2h_gbs, 'h2d_gbs_per_rank_all_ranks_copying': h2d_gbs,
+                                  'd2h_bound_frames_per_s': world * d2h_gbs * 1e9 / (d2h / max(1, world) / max(1, F)) if d2h else None},
                     'api': 'bodyfitting_b200.smplify.smplify.SMPLify.__call__ (page-locked numpy in, numpy out incl. vertices)'},
             'gpu_launches': int(launches),
             'roofline': {'bound': 'hbm', 'kernel': dom['kernel'], 'achieved': dom['gbs'], 'peak': hbm_peak, 'unit': 'GB/s',

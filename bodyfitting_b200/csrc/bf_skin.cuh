@@ -483,124 +483,150 @@ static int bf_launch_skin_rows(int mode, const BfVSet* vs, int J, const float* A
 
 
 // ---------------------------------------------------------------------------------------------
-// k_skin_frame : the same skinning with ONE FRAME per CTA and LANE = VERTEX -- the all-vertex operator's default.
+// k_skin_frame : the same skinning with FOUR FRAMES per CTA and LANE = VERTEX -- the all-vertex operator's default.
 //
 // k_skin_rows (above) keeps 32 frames' transforms in shared memory and maps lane = frame, which makes every transform read
 // a conflict-free broadcast but forces each row segment through a shared-memory transpose (42 % of its instructions) and
-// limits it to one 145 KB CTA per SM.  Here a CTA stages only its frame's J x 12 transforms (1.2 - 2.6 KB), a warp takes 32
+// limits it to one 145 KB CTA per SM.  Here a CTA stages only its four frames' J x 12 transforms (4.6 - 10.6 KB), a warp takes 32
 // consecutive vertices = 96 consecutive floats of the row (three fully coalesced 128-byte accesses, de-interleaved through a
 // 384-byte per-warp stage: stride-3 reads are conflict-free), and each lane blends its own vertex' four transforms with
-// LDS.128 (neighbouring vertices mostly share joints -> mostly broadcasts).  ~6 CTAs per SM, no transposes.  With one slab
-// per frame (gridDim.y == 1) the output joints are produced by the same CTA right after its vertices (k_joints_fwd fused).
+// LDS.128 (neighbouring vertices mostly share joints -> mostly broadcasts); the vertex' four (joint, weight) pairs are loaded once
+// and reused for the CTA's frames (one frame per CTA re-read the 32-byte table entry per frame: 226 MB of L2 traffic for 170 MB
+// of vertices), and the next frame's floats are requested before the current frame is computed.  ~6 CTAs per SM, no transposes.
+// With one slab per frame group (gridDim.y == 1) the output joints are produced by the same CTA right after its vertices.
 //   MODE 0: verts = T [v_posed; 1] (optionally -> world space);   MODE 1: dvp = T[:3,:3]^T dverts (plain and / or 3xTF32 split)
 #define SF_THREADS 256
+#define SF_FPB 4                      // frames per CTA: the skinning table of a vertex group is read once for all of them
 template <int MODE>
 __global__ void __launch_bounds__(SF_THREADS) k_skin_frame(BfModel m, BfVSet vs, BfFrames f, const float* in, float* out,
                                                            float* out_hi, float* out_lo, int ld_out, int world, int fuse_joints) {
-    __shared__ __align__(16) float As[BF_MAXJ * 12];
+    __shared__ __align__(16) float As[SF_FPB][BF_MAXJ * 12];
     __shared__ float stage[SF_THREADS / 32][96];
-    const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int b0 = blockIdx.x * SF_FPB, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int nfr = min(SF_FPB, f.B - b0);
     const int J = m.J, n = vs.n, ld_v = f.ld_v;
-    {
-        const float4* src = reinterpret_cast<const float4*>(f.A + (size_t)b * J * 12);
-        for (int i = t; i < J * 3; i += SF_THREADS) reinterpret_cast<float4*>(As)[i] = src[i];
+    for (int fr = 0; fr < nfr; ++fr) {
+        const float4* src = reinterpret_cast<const float4*>(f.A + (size_t)(b0 + fr) * J * 12);
+        for (int i = t; i < J * 3; i += SF_THREADS) reinterpret_cast<float4*>(As[fr])[i] = src[i];
     }
-    float t0 = 0.f, t1 = 0.f, t2 = 0.f, sc = 1.f;
     const float cs = f.constant_scale;
-    if (MODE == 0 && world) {
-        const float* th = f.theta + (size_t)b * m.NP;
-        t0 = th[0]; t1 = th[1]; t2 = th[2]; sc = th[3];
-    }
     __syncthreads();
-    const float* row_in = in + (size_t)b * ld_v;
     float* st = stage[warp];
     const int groups = (n + 31) >> 5;                                 // 32-vertex groups of the row
     const int g_per = (groups + gridDim.y - 1) / gridDim.y;
     const int g_end = min(groups, (int)(blockIdx.y + 1) * g_per);
     const int nnz = vs.nnz;
+    constexpr int NC = MODE == 0 ? 4 : 3;
     for (int g = blockIdx.y * g_per + warp; g < g_end; g += SF_THREADS / 32) {
         const int v0 = g << 5, nf = 3 * min(32, n - v0);              // floats of this group
-        const float* p = row_in + 3 * v0;
-#pragma unroll
-        for (int s = 0; s < 3; ++s) { const int i = lane + 32 * s; st[i] = i < nf ? p[i] : 0.f; }
-        __syncwarp();
         const int v = min(v0 + lane, n - 1);
-        const float px = st[3 * lane], py = st[3 * lane + 1], pz = st[3 * lane + 2];
-        constexpr int NC = MODE == 0 ? 4 : 3;
-        float T[3 * NC];
-#pragma unroll
-        for (int e = 0; e < 3 * NC; ++e) T[e] = 0.f;
-        if (nnz == 4) {
+        int jj[4] = {0, 0, 0, 0};
+        float ww[4] = {0.f, 0.f, 0.f, 0.f};
+        if (nnz == 4) {                                               // this vertex' influences, once for all frames of the CTA
             const int4 j4 = __ldg(reinterpret_cast<const int4*>(vs.ell_j) + v);
             const float4 w4 = __ldg(reinterpret_cast<const float4*>(vs.ell_w) + v);
-            const int jj[4] = {j4.x, j4.y, j4.z, j4.w};
-            const float ww[4] = {w4.x, w4.y, w4.z, w4.w};
+            jj[0] = j4.x; jj[1] = j4.y; jj[2] = j4.z; jj[3] = j4.w;
+            ww[0] = w4.x; ww[1] = w4.y; ww[2] = w4.z; ww[3] = w4.w;
+        }
+        // software pipeline over the frames: the next frame's 96 floats are requested before this frame is computed
+        float nx[3];
+        {
+            const float* p = in + (size_t)b0 * ld_v + 3 * v0;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const float w = ww[k];
-                const float4* Aj = reinterpret_cast<const float4*>(As + jj[k] * 12);
-                const float4 r0 = Aj[0], r1 = Aj[1], r2 = Aj[2];
-                T[0] = fmaf(w, r0.x, T[0]); T[1] = fmaf(w, r0.y, T[1]); T[2] = fmaf(w, r0.z, T[2]);
-                T[NC] = fmaf(w, r1.x, T[NC]); T[NC + 1] = fmaf(w, r1.y, T[NC + 1]); T[NC + 2] = fmaf(w, r1.z, T[NC + 2]);
-                T[2 * NC] = fmaf(w, r2.x, T[2 * NC]); T[2 * NC + 1] = fmaf(w, r2.y, T[2 * NC + 1]); T[2 * NC + 2] = fmaf(w, r2.z, T[2 * NC + 2]);
-                if (NC == 4) { T[3] = fmaf(w, r0.w, T[3]); T[7] = fmaf(w, r1.w, T[7]); T[11] = fmaf(w, r2.w, T[11]); }
-            }
-        } else {
-            const int32_t* ej = vs.ell_j + (size_t)v * nnz;
-            const float* ew = vs.ell_w + (size_t)v * nnz;
-            for (int k = 0; k < nnz; ++k) {
-                const float w = __ldg(ew + k);
-                const float4* Aj = reinterpret_cast<const float4*>(As + __ldg(ej + k) * 12);
-                const float4 r0 = Aj[0], r1 = Aj[1], r2 = Aj[2];
-                T[0] = fmaf(w, r0.x, T[0]); T[1] = fmaf(w, r0.y, T[1]); T[2] = fmaf(w, r0.z, T[2]);
-                T[NC] = fmaf(w, r1.x, T[NC]); T[NC + 1] = fmaf(w, r1.y, T[NC + 1]); T[NC + 2] = fmaf(w, r1.z, T[NC + 2]);
-                T[2 * NC] = fmaf(w, r2.x, T[2 * NC]); T[2 * NC + 1] = fmaf(w, r2.y, T[2 * NC + 1]); T[2 * NC + 2] = fmaf(w, r2.z, T[2 * NC + 2]);
-                if (NC == 4) { T[3] = fmaf(w, r0.w, T[3]); T[7] = fmaf(w, r1.w, T[7]); T[11] = fmaf(w, r2.w, T[11]); }
-            }
+            for (int s = 0; s < 3; ++s) { const int i = lane + 32 * s; nx[s] = i < nf ? p[i] : 0.f; }
         }
-        float ox, oy, oz;
-        if (MODE == 0) {
-            ox = T[0] * px + T[1] * py + T[2] * pz + T[3];
-            oy = T[4] * px + T[5] * py + T[6] * pz + T[7];
-            oz = T[8] * px + T[9] * py + T[10] * pz + T[11];
-            if (world) { ox = (ox + t0) * sc * cs; oy = (oy + t1) * sc * cs; oz = (oz + t2) * sc * cs; }
-        } else {
-            ox = T[0] * px + T[3] * py + T[6] * pz;
-            oy = T[1] * px + T[4] * py + T[7] * pz;
-            oz = T[2] * px + T[5] * py + T[8] * pz;
-        }
-        __syncwarp();
-        st[3 * lane] = ox; st[3 * lane + 1] = oy; st[3 * lane + 2] = oz;
-        __syncwarp();
-        if (out) {
-            float* q = out + (size_t)b * ld_v + 3 * v0;
+        for (int fr = 0; fr < nfr; ++fr) {
+            const int b = b0 + fr;
 #pragma unroll
-            for (int s = 0; s < 3; ++s) { const int i = lane + 32 * s; if (i < nf) q[i] = st[i]; }
-        }
-        if (MODE == 1 && out_hi) {
-            float* qh = out_hi + (size_t)b * ld_out + 3 * v0;
-            float* ql = out_lo + (size_t)b * ld_out + 3 * v0;
+            for (int s = 0; s < 3; ++s) st[lane + 32 * s] = nx[s];
+            if (fr + 1 < nfr) {
+                const float* p = in + (size_t)(b + 1) * ld_v + 3 * v0;
 #pragma unroll
-            for (int s = 0; s < 3; ++s) {
-                const int i = lane + 32 * s;
-                if (i < nf) { float h_, l_; split_tf32(st[i], h_, l_); qh[i] = h_; ql[i] = l_; }
+                for (int s = 0; s < 3; ++s) { const int i = lane + 32 * s; nx[s] = i < nf ? p[i] : 0.f; }
             }
+            __syncwarp();
+            const float px = st[3 * lane], py = st[3 * lane + 1], pz = st[3 * lane + 2];
+            float T[3 * NC];
+#pragma unroll
+            for (int e = 0; e < 3 * NC; ++e) T[e] = 0.f;
+            const float* Ab = As[fr];
+            if (nnz == 4) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float w = ww[k];
+                    const float4* Aj = reinterpret_cast<const float4*>(Ab + jj[k] * 12);
+                    const float4 r0 = Aj[0], r1 = Aj[1], r2 = Aj[2];
+                    T[0] = fmaf(w, r0.x, T[0]); T[1] = fmaf(w, r0.y, T[1]); T[2] = fmaf(w, r0.z, T[2]);
+                    T[NC] = fmaf(w, r1.x, T[NC]); T[NC + 1] = fmaf(w, r1.y, T[NC + 1]); T[NC + 2] = fmaf(w, r1.z, T[NC + 2]);
+                    T[2 * NC] = fmaf(w, r2.x, T[2 * NC]); T[2 * NC + 1] = fmaf(w, r2.y, T[2 * NC + 1]); T[2 * NC + 2] = fmaf(w, r2.z, T[2 * NC + 2]);
+                    if (NC == 4) { T[3] = fmaf(w, r0.w, T[3]); T[7] = fmaf(w, r1.w, T[7]); T[11] = fmaf(w, r2.w, T[11]); }
+                }
+            } else {
+                const int32_t* ej = vs.ell_j + (size_t)v * nnz;
+                const float* ew = vs.ell_w + (size_t)v * nnz;
+                for (int k = 0; k < nnz; ++k) {
+                    const float w = __ldg(ew + k);
+                    const float4* Aj = reinterpret_cast<const float4*>(Ab + __ldg(ej + k) * 12);
+                    const float4 r0 = Aj[0], r1 = Aj[1], r2 = Aj[2];
+                    T[0] = fmaf(w, r0.x, T[0]); T[1] = fmaf(w, r0.y, T[1]); T[2] = fmaf(w, r0.z, T[2]);
+                    T[NC] = fmaf(w, r1.x, T[NC]); T[NC + 1] = fmaf(w, r1.y, T[NC + 1]); T[NC + 2] = fmaf(w, r1.z, T[NC + 2]);
+                    T[2 * NC] = fmaf(w, r2.x, T[2 * NC]); T[2 * NC + 1] = fmaf(w, r2.y, T[2 * NC + 1]); T[2 * NC + 2] = fmaf(w, r2.z, T[2 * NC + 2]);
+                    if (NC == 4) { T[3] = fmaf(w, r0.w, T[3]); T[7] = fmaf(w, r1.w, T[7]); T[11] = fmaf(w, r2.w, T[11]); }
+                }
+            }
+            float ox, oy, oz;
+            if (MODE == 0) {
+                ox = T[0] * px + T[1] * py + T[2] * pz + T[3];
+                oy = T[4] * px + T[5] * py + T[6] * pz + T[7];
+                oz = T[8] * px + T[9] * py + T[10] * pz + T[11];
+                if (world) {
+                    const float* th = f.theta + (size_t)b * m.NP;
+                    const float sc = __ldg(th + 3);
+                    ox = (ox + __ldg(th)) * sc * cs; oy = (oy + __ldg(th + 1)) * sc * cs; oz = (oz + __ldg(th + 2)) * sc * cs;
+                }
+            } else {
+                ox = T[0] * px + T[3] * py + T[6] * pz;
+                oy = T[1] * px + T[4] * py + T[7] * pz;
+                oz = T[2] * px + T[5] * py + T[8] * pz;
+            }
+            __syncwarp();
+            st[3 * lane] = ox; st[3 * lane + 1] = oy; st[3 * lane + 2] = oz;
+            __syncwarp();
+            if (out) {
+                float* q = out + (size_t)b * ld_v + 3 * v0;
+#pragma unroll
+                for (int s = 0; s < 3; ++s) { const int i = lane + 32 * s; if (i < nf) q[i] = st[i]; }
+            }
+            if (MODE == 1 && out_hi) {
+                float* qh = out_hi + (size_t)b * ld_out + 3 * v0;
+                float* ql = out_lo + (size_t)b * ld_out + 3 * v0;
+#pragma unroll
+                for (int s = 0; s < 3; ++s) {
+                    const int i = lane + 32 * s;
+                    if (i < nf) { float h_, l_; split_tf32(st[i], h_, l_); qh[i] = h_; ql[i] = l_; }
+                }
+            }
+            __syncwarp();
         }
-        __syncwarp();
     }
     if (MODE == 0 && fuse_joints) {
         __syncthreads();                                   // this CTA's vertex stores are visible to its own threads
-        const int yaw = f.yaw ? f.yaw[b] : 0;
-        const float* Jtr_b = f.Jtr + (size_t)b * J * 3;
-        const float* verts_b = out + (size_t)b * ld_v;
-        for (int k = t; k < vs.K_out; k += SF_THREADS) {
-            float x[3];
-            joint_pos(vs, k, yaw, Jtr_b, verts_b, x);
-            if (world && __ldg(vs.kj_kind + k) == 0) {     // vertices are in world space already; chain joints are not
-                x[0] = (x[0] + t0) * sc * cs; x[1] = (x[1] + t1) * sc * cs; x[2] = (x[2] + t2) * sc * cs;
+        for (int fr = 0; fr < nfr; ++fr) {
+            const int b = b0 + fr;
+            const int yaw = f.yaw ? f.yaw[b] : 0;
+            const float* Jtr_b = f.Jtr + (size_t)b * J * 3;
+            const float* verts_b = out + (size_t)b * ld_v;
+            const float* th = f.theta + (size_t)b * m.NP;
+            for (int k = t; k < vs.K_out; k += SF_THREADS) {
+                float x[3];
+                joint_pos(vs, k, yaw, Jtr_b, verts_b, x);
+                if (world && __ldg(vs.kj_kind + k) == 0) { // vertices are in world space already; chain joints are not
+                    const float sc = __ldg(th + 3);
+                    x[0] = (x[0] + __ldg(th)) * sc * cs; x[1] = (x[1] + __ldg(th + 1)) * sc * cs; x[2] = (x[2] + __ldg(th + 2)) * sc * cs;
+                }
+                float* o = f.joints + ((size_t)b * vs.K_out + k) * 3;
+                o[0] = x[0]; o[1] = x[1]; o[2] = x[2];
             }
-            float* o = f.joints + ((size_t)b * vs.K_out + k) * 3;
-            o[0] = x[0]; o[1] = x[1]; o[2] = x[2];
         }
     }
 }
@@ -613,12 +639,13 @@ static int bf_launch_skin_frame(int mode, const BfModel* m, const BfVSet* vs, co
     if (!env) return 1;
     // slabs only while the frames alone do not fill the SMs a few times over
     const int num_sms = bf_num_sms();
-    int slabs = (4 * num_sms) / f->B;
+    const int fgroups = (f->B + SF_FPB - 1) / SF_FPB;
+    int slabs = (6 * num_sms + fgroups - 1) / fgroups;                 // ~6 CTAs of 8 warps per SM keep enough loads in flight
     const int groups = (vs->n + 31) / 32;
     if (slabs > (groups + 7) / 8) slabs = (groups + 7) / 8;
     if (slabs < 1) slabs = 1;
     if (fuse_joints && slabs > 1) fuse_joints = 0;
-    const dim3 grid(f->B, slabs);
+    const dim3 grid(fgroups, slabs);
     if (mode == 0) k_skin_frame<0><<<grid, SF_THREADS, 0, s>>>(*m, *vs, *f, in, out, out_hi, out_lo, ld_out, world, fuse_joints);
     else k_skin_frame<1><<<grid, SF_THREADS, 0, s>>>(*m, *vs, *f, in, out, out_hi, out_lo, ld_out, world, fuse_joints);
     BF_LAUNCH_CHECK();

@@ -281,7 +281,7 @@ class FitSession(object):
             fbf.call('bf_lbs_forward')
             # pose, blend GEMM, per-frame skinning with the output joints fused in (a separate joints kernel when the frames
             # alone do not fill the SMs and the vertex range is cut into slabs)
-            n += (3 if fbf.B * 1 > 2 * sms else 4) if self.model.tensor_cores else 3
+            n += (3 if fbf.B >= 24 * sms else 4) if self.model.tensor_cores else 3
         return n
 
     def _body(self):

@@ -10,3 +10,5 @@ timeout 300 python tools/dense_breakdown.py > gpurun_out/r2g_dense_breakdown.log
 BODYFIT_SKIN=rows timeout 300 python tools/dense_breakdown.py > gpurun_out/r2g_dense_breakdown_rows.log 2>&1
 timeout 900 python bench.py > gpurun_out/r2g_bench.json 2> gpurun_out/r2g_bench.err
 ls -la gpurun_out/*.ncu-rep; tail -3 gpurun_out/r2g_dense_breakdown.log; tail -3 gpurun_out/r2g_dense_breakdown_rows.log; tail -3 gpurun_out/r2g_bench.err; head -c 600 gpurun_out/r2g_bench.json
+timeout 600 python tools/e2e_sweep.py > gpurun_out/r2g_e2e_sweep.log 2>&1; grep "^{" gpurun_out/r2g_e2e_sweep.log
+timeout 1500 python -m pytest tests -m gpu -q -s -p no:cacheprovider > gpurun_out/r2g_tests.log 2>&1; echo "tests rc=$?" >> gpurun_out/r2g_tests.log; grep -E "passed|failed|FAILED" gpurun_out/r2g_tests.log | tail -5
