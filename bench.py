@@ -326,8 +326,8 @@ def dense_lbs_bench(assets_seed, hbm_peak):
             fl = 3 * 2.0 * B * pm.Kp * 3 * pm.n_pad_full            # three TF32 MMAs per product (hi*hi + lo*hi + hi*lo)
             gemm.update(blend_gemm_ms=g_ms, blend_gemm_tf32_tflops=fl / (g_ms * 1e-3) / 1e12,
                         blend_gemm_frac_of_tf32_peak=fl / (g_ms * 1e-3) / 1e12 / tf,
-                        note='3xTF32: the GEMM issues 3 MMAs per product, so at 100 % of the TF32 peak it would still take '
-                             '%.0f us = %.2f of the HBM roofline for this operator' % (fl / (tf * 1e12) * 1e6, alg / (fl / (tf * 1e12)) / 1e9 / hbm_peak))
+                        note='3xTF32: the GEMM issues 3 MMAs per product, so at 100 %% of the TF32 peak it would still take '
+                             '%.0f us, i.e. cap the forward at %.2f of the HBM roofline' % (fl / (tf * 1e12) * 1e6, alg / (fl / (tf * 1e12)) / 1e9 / hbm_peak))
     except Exception as ex:
         gemm = {'error': repr(ex)}
     return {'config': 'SMPL 6890 verts, 1024 frames (BASELINE config 2), L2 flushed between launches', 'gemm': gemm,

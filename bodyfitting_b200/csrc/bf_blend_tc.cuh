@@ -343,6 +343,8 @@ k_blend_fwd_tc(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant_
 __global__ void __launch_bounds__(64 + 32 * TC_EPI_WARPS, 1)
 k_blend_fwd_tc_blk(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CUtensorMap mA_lo,
                    const __grid_constant__ CUtensorMap mB_hi, const __grid_constant__ CUtensorMap mB_lo,
+                   const __grid_constant__ CUtensorMap mB2_hi, const __grid_constant__ CUtensorMap mB2_lo,
+                   const __grid_constant__ CUtensorMap mB3_hi, const __grid_constant__ CUtensorMap mB3_lo,
                    const __grid_constant__ CUtensorMap mB4_hi, const __grid_constant__ CUtensorMap mB4_lo,
                    int n_verts, int Kp, float* __restrict__ vposed, int B, int ld_v, int n_tiles_m,
                    const uint32_t* __restrict__ blk_mask, int n_blocks) {
@@ -387,8 +389,15 @@ k_blend_fwd_tc_blk(const __grid_constant__ CUtensorMap mA_hi, const __grid_const
                 if (nb <= 0) continue;
                 int rows[4];
                 for (int j = 0; j < nb; ++j) rows[j] = TC_BLK_ROWS * (int)__fns(mask, 0, 4 * vt + j + 1);
-                // four consecutive blocks (the static part of the set): one 192-row box instead of four 48-row ones
-                const bool run4 = nb == 4 && rows[3] == rows[0] + 3 * TC_BLK_ROWS;
+                // maximal runs of consecutive blocks (the static part of the set, and the contour blocks of a tile that holds few
+                // rows) are fetched by ONE box of 48 x run rows instead of one box per block
+                int run_len[4], n_runs = 0;
+                for (int j = 0; j < nb;) {
+                    int l = 1;
+                    while (j + l < nb && rows[j + l] == rows[j] + l * TC_BLK_ROWS) ++l;
+                    run_len[n_runs++] = l;
+                    j += l;
+                }
                 const int b0 = fm * TC_BM;
                 const uint32_t bytes = 2 * p.a_bytes + 2u * (uint32_t)nb * TC_BLK_ROWS * TC_ROWB;
                 for (int kc = 0; kc < num_k; ++kc, ++it) {
@@ -399,14 +408,12 @@ k_blend_fwd_tc_blk(const __grid_constant__ CUtensorMap mA_hi, const __grid_const
                     uint8_t* st = p.stage(s);
                     tc::tma_load_2d(st, &mA_hi, &p.full[s], kc * TC_BK, b0);
                     tc::tma_load_2d(st + p.a_bytes, &mA_lo, &p.full[s], kc * TC_BK, b0);
-                    if (run4) {
-                        tc::tma_load_2d(st + 2 * p.a_bytes, &mB4_hi, &p.full[s], kc * TC_BK, rows[0]);
-                        tc::tma_load_2d(st + 2 * p.a_bytes + p.b_bytes, &mB4_lo, &p.full[s], kc * TC_BK, rows[0]);
-                    } else {
-                        for (int j = 0; j < nb; ++j) {
-                            tc::tma_load_2d(st + 2 * p.a_bytes + j * TC_BLK_ROWS * TC_ROWB, &mB_hi, &p.full[s], kc * TC_BK, rows[j]);
-                            tc::tma_load_2d(st + 2 * p.a_bytes + p.b_bytes + j * TC_BLK_ROWS * TC_ROWB, &mB_lo, &p.full[s], kc * TC_BK, rows[j]);
-                        }
+                    for (int r = 0, j = 0; r < n_runs; j += run_len[r], ++r) {
+                        const int l = run_len[r];
+                        const CUtensorMap* mh = l == 1 ? &mB_hi : l == 2 ? &mB2_hi : l == 3 ? &mB3_hi : &mB4_hi;
+                        const CUtensorMap* ml = l == 1 ? &mB_lo : l == 2 ? &mB2_lo : l == 3 ? &mB3_lo : &mB4_lo;
+                        tc::tma_load_2d(st + 2 * p.a_bytes + j * TC_BLK_ROWS * TC_ROWB, mh, &p.full[s], kc * TC_BK, rows[j]);
+                        tc::tma_load_2d(st + 2 * p.a_bytes + p.b_bytes + j * TC_BLK_ROWS * TC_ROWB, ml, &p.full[s], kc * TC_BK, rows[j]);
                     }
                 }
             }
@@ -698,7 +705,11 @@ static int bf_gemm_forward_tc_blk(const float* a_hi_p, const float* a_lo_p, cons
     if ((rc = bf_make_map(&a_lo, a_lo_p, B, Kp, Kp, TC_BM))) return rc;
     if ((rc = bf_make_map(&b_hi, bt_hi_p, ldn, Kp, Kp, TC_BLK_ROWS))) return rc;
     if ((rc = bf_make_map(&b_lo, bt_lo_p, ldn, Kp, Kp, TC_BLK_ROWS))) return rc;
-    CUtensorMap b4_hi, b4_lo;
+    CUtensorMap b2_hi, b2_lo, b3_hi, b3_lo, b4_hi, b4_lo;
+    if ((rc = bf_make_map(&b2_hi, bt_hi_p, ldn, Kp, Kp, 2 * TC_BLK_ROWS))) return rc;
+    if ((rc = bf_make_map(&b2_lo, bt_lo_p, ldn, Kp, Kp, 2 * TC_BLK_ROWS))) return rc;
+    if ((rc = bf_make_map(&b3_hi, bt_hi_p, ldn, Kp, Kp, 3 * TC_BLK_ROWS))) return rc;
+    if ((rc = bf_make_map(&b3_lo, bt_lo_p, ldn, Kp, Kp, 3 * TC_BLK_ROWS))) return rc;
     if ((rc = bf_make_map(&b4_hi, bt_hi_p, ldn, Kp, Kp, TC_BN1))) return rc;
     if ((rc = bf_make_map(&b4_lo, bt_lo_p, ldn, Kp, Kp, TC_BN1))) return rc;
     const size_t smem = 1024 + TC_STAGES * (2 * TC_BM * TC_ROWB + 2 * TC_BN1 * TC_ROWB) + TC_EPI_WARPS * TC_ST_FLOATS * 4 + 128;
@@ -709,7 +720,7 @@ static int bf_gemm_forward_tc_blk(const float* a_hi_p, const float* a_lo_p, cons
     // at most ceil(n_blocks / 4) virtual tiles per frame tile are real; one CTA per SM, fewer when there is less work
     const int real_max = tm * ((n_blocks + 3) / 4);
     const int grid = real_max < num_sms ? real_max : num_sms;
-    k_blend_fwd_tc_blk<<<grid, 64 + 32 * TC_EPI_WARPS, smem, s>>>(a_hi, a_lo, b_hi, b_lo, b4_hi, b4_lo, n_verts, Kp, dst, B, ld_dst, tm, blk_mask, n_blocks);
+    k_blend_fwd_tc_blk<<<grid, 64 + 32 * TC_EPI_WARPS, smem, s>>>(a_hi, a_lo, b_hi, b_lo, b2_hi, b2_lo, b3_hi, b3_lo, b4_hi, b4_lo, n_verts, Kp, dst, B, ld_dst, tm, blk_mask, n_blocks);
     BF_LAUNCH_CHECK();
     return BF_OK;
 }
