@@ -639,7 +639,10 @@ static void carve_frames(const BfModel* m, int B, int Nv, int opts, int n_trace,
         f->gmm_grad = (float*)c.take(F4 * B * BF_GMM_D);
         f->gmm_loss = (float*)c.take(F4 * B);
         f->fwd_state = (float*)c.take(F4 * B * 24 * m->J);
-        if (tc && !full && vs->lv_blk && vs->n_pad <= 512) f->blk_mask = (uint32_t*)c.take(sizeof(uint32_t) * 2 * ((B + 127) / 128));
+        if (tc && !full && vs->lv_blk && vs->n_pad <= 512) {
+            f->blk_mask = (uint32_t*)c.take(sizeof(uint32_t) * 2 * ((B + 127) / 128));
+            f->dpf2 = (float*)c.take(F4 * B * m->Kp);
+        }
         if (temporal) { f->tgrad = (float*)c.take(F4 * B * m->NP); f->tloss = (float*)c.take(F4 * B); }
     }
     if (n_trace > 0) f->trace = (float*)c.take(F4 * (size_t)n_trace * B);

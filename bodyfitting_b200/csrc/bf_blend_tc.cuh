@@ -106,7 +106,8 @@ __device__ __forceinline__ void producer(const Pipe& p, const CUtensorMap* mA_hi
         mbar_wait(&p.empty[s], ph ^ 1);
         mbar_expect_tx(&p.full[s], p.stage_bytes());
         uint8_t* st = p.stage(s);
-        const int chunk = blk_mask == 0xFFFFFFFFu ? kc_begin + kc : 3 * (int)__fns(blk_mask, 0, kc / 3 + 1) + kc % 3;
+        const int kk = kc_begin + kc;                       // masked: index into the tile's list of (set block, chunk) pairs
+        const int chunk = blk_mask == 0xFFFFFFFFu ? kk : 3 * (int)__fns(blk_mask, 0, kk / 3 + 1) + kk % 3;
         const int c0 = chunk * TC_BK;
         tma_load_2d(st, mA_hi, &p.full[s], c0, rowA);
         tma_load_2d(st + p.a_bytes, mA_lo, &p.full[s], c0, rowA);
@@ -339,12 +340,11 @@ k_blend_fwd_tc(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant_
 // Slot order: virtual tile index major, frame tile minor -- every frame tile has at least three virtual tiles (the static
 // blocks), so consecutive slots are almost all real and the static round-robin over the CTAs stays balanced.
 #define TC_BLK_ROWS 48
+#define BW_SPLIT_BLOCK 8
 #define TC_MAX_VT 8
 __global__ void __launch_bounds__(64 + 32 * TC_EPI_WARPS, 1)
 k_blend_fwd_tc_blk(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CUtensorMap mA_lo,
                    const __grid_constant__ CUtensorMap mB_hi, const __grid_constant__ CUtensorMap mB_lo,
-                   const __grid_constant__ CUtensorMap mB2_hi, const __grid_constant__ CUtensorMap mB2_lo,
-                   const __grid_constant__ CUtensorMap mB3_hi, const __grid_constant__ CUtensorMap mB3_lo,
                    const __grid_constant__ CUtensorMap mB4_hi, const __grid_constant__ CUtensorMap mB4_lo,
                    int n_verts, int Kp, float* __restrict__ vposed, int B, int ld_v, int n_tiles_m,
                    const uint32_t* __restrict__ blk_mask, int n_blocks) {
@@ -389,15 +389,9 @@ k_blend_fwd_tc_blk(const __grid_constant__ CUtensorMap mA_hi, const __grid_const
                 if (nb <= 0) continue;
                 int rows[4];
                 for (int j = 0; j < nb; ++j) rows[j] = TC_BLK_ROWS * (int)__fns(mask, 0, 4 * vt + j + 1);
-                // maximal runs of consecutive blocks (the static part of the set, and the contour blocks of a tile that holds few
-                // rows) are fetched by ONE box of 48 x run rows instead of one box per block
-                int run_len[4], n_runs = 0;
-                for (int j = 0; j < nb;) {
-                    int l = 1;
-                    while (j + l < nb && rows[j + l] == rows[j] + l * TC_BLK_ROWS) ++l;
-                    run_len[n_runs++] = l;
-                    j += l;
-                }
+                // four consecutive blocks (the static part of the set): one 192-row box instead of four 48-row ones.  (Boxes of
+                // two and three blocks for shorter runs were measured and lost: 72 -> 83 us per 10,000 frames.)
+                const bool run4 = nb == 4 && rows[3] == rows[0] + 3 * TC_BLK_ROWS;
                 const int b0 = fm * TC_BM;
                 const uint32_t bytes = 2 * p.a_bytes + 2u * (uint32_t)nb * TC_BLK_ROWS * TC_ROWB;
                 for (int kc = 0; kc < num_k; ++kc, ++it) {
@@ -408,12 +402,14 @@ k_blend_fwd_tc_blk(const __grid_constant__ CUtensorMap mA_hi, const __grid_const
                     uint8_t* st = p.stage(s);
                     tc::tma_load_2d(st, &mA_hi, &p.full[s], kc * TC_BK, b0);
                     tc::tma_load_2d(st + p.a_bytes, &mA_lo, &p.full[s], kc * TC_BK, b0);
-                    for (int r = 0, j = 0; r < n_runs; j += run_len[r], ++r) {
-                        const int l = run_len[r];
-                        const CUtensorMap* mh = l == 1 ? &mB_hi : l == 2 ? &mB2_hi : l == 3 ? &mB3_hi : &mB4_hi;
-                        const CUtensorMap* ml = l == 1 ? &mB_lo : l == 2 ? &mB2_lo : l == 3 ? &mB3_lo : &mB4_lo;
-                        tc::tma_load_2d(st + 2 * p.a_bytes + j * TC_BLK_ROWS * TC_ROWB, mh, &p.full[s], kc * TC_BK, rows[j]);
-                        tc::tma_load_2d(st + 2 * p.a_bytes + p.b_bytes + j * TC_BLK_ROWS * TC_ROWB, ml, &p.full[s], kc * TC_BK, rows[j]);
+                    if (run4) {
+                        tc::tma_load_2d(st + 2 * p.a_bytes, &mB4_hi, &p.full[s], kc * TC_BK, rows[0]);
+                        tc::tma_load_2d(st + 2 * p.a_bytes + p.b_bytes, &mB4_lo, &p.full[s], kc * TC_BK, rows[0]);
+                    } else {
+                        for (int j = 0; j < nb; ++j) {
+                            tc::tma_load_2d(st + 2 * p.a_bytes + j * TC_BLK_ROWS * TC_ROWB, &mB_hi, &p.full[s], kc * TC_BK, rows[j]);
+                            tc::tma_load_2d(st + 2 * p.a_bytes + p.b_bytes + j * TC_BLK_ROWS * TC_ROWB, &mB_lo, &p.full[s], kc * TC_BK, rows[j]);
+                        }
                     }
                 }
             }
@@ -524,14 +520,30 @@ __global__ void __launch_bounds__(192, 1) k_blend_bwd_tc(const __grid_constant__
     const int tmem_cols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
     // split-K: this CTA reduces K chunks [kc_begin, kc_begin + num_k) and writes its own partial
     // (the tensor-core accumulator truncates, so long reductions are cut and summed in fp32 RN)
-    const int kc_begin = blockIdx.z * cps;
+    int kc_begin = blockIdx.z * cps;
     uint32_t mask = 0xFFFFFFFFu;
-    if (blk_mask) {                                        // masked reduction (single run only): 3 chunks per set block
+    int num_k;
+    if (blk_mask) {
+        // masked reduction: 3 chunks per set block.  With gridDim.z == 2 the reduction is cut at a FIXED block (BW_SPLIT_BLOCK:
+        // the first eight blocks are static, i.e. always set; the rest holds three static and the ~5 contour blocks of a tile),
+        // run z reduces its side of the cut and the consumer adds the two partial sums in a fixed order.  The cut does not
+        // depend on the mask, so an element's summation order -- and the result -- is the same for every batch and frame order.
         mask = blk_mask[blockIdx.y];
         const int nblk = num_k_total / 3;
         if (nblk < 32) mask &= (1u << nblk) - 1u;
+        if (gridDim.z == 2) {
+            const uint32_t low = (1u << min(BW_SPLIT_BLOCK, nblk / 2)) - 1u;
+            mask = blockIdx.z == 0 ? (mask & low) : (mask & ~low);
+            if (mask == 0xFFFFFFFFu) mask = 0xFFFFFFFEu;   // cannot happen (a half never has 32 blocks); keeps the masked path
+        }
     }
-    const int num_k = mask == 0xFFFFFFFFu ? min(cps, num_k_total - kc_begin) : 3 * __popc(mask);
+    if (blk_mask && (gridDim.z == 2 || mask != 0xFFFFFFFFu)) {
+        kc_begin = 0;
+        num_k = 3 * __popc(mask);
+    } else {
+        mask = 0xFFFFFFFFu;
+        num_k = min(cps, num_k_total - kc_begin);
+    }
     float* dpf = out + (size_t)blockIdx.z * split_stride;
 
     if (threadIdx.x == 0) {
@@ -705,11 +717,7 @@ static int bf_gemm_forward_tc_blk(const float* a_hi_p, const float* a_lo_p, cons
     if ((rc = bf_make_map(&a_lo, a_lo_p, B, Kp, Kp, TC_BM))) return rc;
     if ((rc = bf_make_map(&b_hi, bt_hi_p, ldn, Kp, Kp, TC_BLK_ROWS))) return rc;
     if ((rc = bf_make_map(&b_lo, bt_lo_p, ldn, Kp, Kp, TC_BLK_ROWS))) return rc;
-    CUtensorMap b2_hi, b2_lo, b3_hi, b3_lo, b4_hi, b4_lo;
-    if ((rc = bf_make_map(&b2_hi, bt_hi_p, ldn, Kp, Kp, 2 * TC_BLK_ROWS))) return rc;
-    if ((rc = bf_make_map(&b2_lo, bt_lo_p, ldn, Kp, Kp, 2 * TC_BLK_ROWS))) return rc;
-    if ((rc = bf_make_map(&b3_hi, bt_hi_p, ldn, Kp, Kp, 3 * TC_BLK_ROWS))) return rc;
-    if ((rc = bf_make_map(&b3_lo, bt_lo_p, ldn, Kp, Kp, 3 * TC_BLK_ROWS))) return rc;
+    CUtensorMap b4_hi, b4_lo;
     if ((rc = bf_make_map(&b4_hi, bt_hi_p, ldn, Kp, Kp, TC_BN1))) return rc;
     if ((rc = bf_make_map(&b4_lo, bt_lo_p, ldn, Kp, Kp, TC_BN1))) return rc;
     const size_t smem = 1024 + TC_STAGES * (2 * TC_BM * TC_ROWB + 2 * TC_BN1 * TC_ROWB) + TC_EPI_WARPS * TC_ST_FLOATS * 4 + 128;
@@ -720,7 +728,7 @@ static int bf_gemm_forward_tc_blk(const float* a_hi_p, const float* a_lo_p, cons
     // at most ceil(n_blocks / 4) virtual tiles per frame tile are real; one CTA per SM, fewer when there is less work
     const int real_max = tm * ((n_blocks + 3) / 4);
     const int grid = real_max < num_sms ? real_max : num_sms;
-    k_blend_fwd_tc_blk<<<grid, 64 + 32 * TC_EPI_WARPS, smem, s>>>(a_hi, a_lo, b_hi, b_lo, b2_hi, b2_lo, b3_hi, b3_lo, b4_hi, b4_lo, n_verts, Kp, dst, B, ld_dst, tm, blk_mask, n_blocks);
+    k_blend_fwd_tc_blk<<<grid, 64 + 32 * TC_EPI_WARPS, smem, s>>>(a_hi, a_lo, b_hi, b_lo, b4_hi, b4_lo, n_verts, Kp, dst, B, ld_dst, tm, blk_mask, n_blocks);
     BF_LAUNCH_CHECK();
     return BF_OK;
 }
@@ -758,7 +766,8 @@ static int bf_blend_backward_tc(const BfModel* m, const BfVSet* vs, const BfFram
     // in the same order, so the result does not depend on the tile width (bit-identical across batch sizes, tested).
     if (vs->ldn / TC_BK <= 2048 / TC_BK) {                 // single accumulation run only (the all-vertex backward is split-K)
         const int mt = (f->B + TC_BM - 1) / TC_BM;
-        while (BN > 64 && (m->Kp / BN) * mt * 2 < num_sms && m->Kp % (BN / 2) == 0 && (BN / 2) % 16 == 0) BN /= 2;
+        const int halves = (f->dpf2 && f->blk_mask && bf_blk_mask_on()) ? 2 : 1;
+        while (BN > 64 && (m->Kp / BN) * mt * halves * 2 < num_sms && m->Kp % (BN / 2) == 0 && (BN / 2) % 16 == 0) BN /= 2;
     }
     {
         static int forced = -1;                           // BODYFIT_BWD_BN=64|128|256: tile-width experiments
@@ -810,13 +819,18 @@ static int bf_blend_backward_tc(const BfModel* m, const BfVSet* vs, const BfFram
             S = (num_k + cps - 1) / cps;
         }
     }
-    const dim3 grid(m->Kp / BN, (f->B + TC_BM - 1) / TC_BM, S);
+    dim3 grid(m->Kp / BN, (f->B + TC_BM - 1) / TC_BM, S);
     // block mask of the active set (BfFrames.blk_mask, buffer of this iteration's parity): single-run reductions only
     const uint32_t* mask = (bf_blk_mask_on() && f->blk_mask && vs->lv_blk && S == 1 && TC_BK == 16 && vs->n_pad <= 512 && num_k % 3 == 0)
                                ? f->blk_mask + (size_t)(f->iter & 1) * ((f->B + 127) / 128) : nullptr;
-    if (NS == 2) k_blend_bwd_tc<2><<<grid, 192, smem, s>>>(a_hi, a_lo, b_hi, b_lo, BN, num_k, cps, m->Kp, S > 1 ? f->ws : f->dpf, stride, f->B, mask);
-    else if (NS == 8) k_blend_bwd_tc<8><<<grid, 192, smem, s>>>(a_hi, a_lo, b_hi, b_lo, BN, num_k, cps, m->Kp, S > 1 ? f->ws : f->dpf, stride, f->B, mask);
-    else k_blend_bwd_tc<TC_STAGES><<<grid, 192, smem, s>>>(a_hi, a_lo, b_hi, b_lo, BN, num_k, cps, m->Kp, S > 1 ? f->ws : f->dpf, stride, f->B, mask);
+    // two half-reductions per tile into dpf / dpf2 (summed by k_pose_bwd): halves the latency of a CTA's K loop -- what a
+    // small batch (a shard of a strong-scaled sequence) is bound by -- and evens out the last wave of a large one
+    float* out0 = S > 1 ? f->ws : f->dpf;
+    size_t out_stride = stride;
+    if (mask && f->dpf2) { grid.z = 2; out0 = f->dpf; out_stride = (size_t)(f->dpf2 - f->dpf); }
+    if (NS == 2) k_blend_bwd_tc<2><<<grid, 192, smem, s>>>(a_hi, a_lo, b_hi, b_lo, BN, num_k, cps, m->Kp, out0, out_stride, f->B, mask);
+    else if (NS == 8) k_blend_bwd_tc<8><<<grid, 192, smem, s>>>(a_hi, a_lo, b_hi, b_lo, BN, num_k, cps, m->Kp, out0, out_stride, f->B, mask);
+    else k_blend_bwd_tc<TC_STAGES><<<grid, 192, smem, s>>>(a_hi, a_lo, b_hi, b_lo, BN, num_k, cps, m->Kp, out0, out_stride, f->B, mask);
     BF_LAUNCH_CHECK();
     if (S > 1) {
         const size_t n = stride;

@@ -370,8 +370,14 @@ __global__ void __launch_bounds__(128) k_pose_bwd(BfModel m, BfFrames f, int fla
                         S.GR[p * 9 + 2 * 3 + r] * S.Gt[j * 3 + 2];
             }
             const float* dpf = f.dpf + (size_t)b * m.Kp + (j - 1) * 9;
+            if (f.dpf2) {                                  // two half-reductions of the masked blend backward GEMM
+                const float* dq = f.dpf2 + (size_t)b * m.Kp + (j - 1) * 9;
 #pragma unroll
-            for (int e = 0; e < 9; ++e) dR[e] += dpf[e];
+                for (int e = 0; e < 9; ++e) dR[e] += dpf[e] + dq[e];
+            } else {
+#pragma unroll
+                for (int e = 0; e < 9; ++e) dR[e] += dpf[e];
+            }
         }
 #pragma unroll
         for (int c = 0; c < 3; ++c) drel[j * 3 + c] = dr[c];
@@ -414,7 +420,11 @@ __global__ void __launch_bounds__(128) k_pose_bwd(BfModel m, BfFrames f, int fla
         const float a1 = __shfl_sync(0xffffffffu, acc, (lane + m.NB) & 31);
         const float a2s = __shfl_sync(0xffffffffu, acc, (lane + 2 * m.NB) & 31);
         const float a2 = nparts > 2 ? a2s : 0.f;
-        if (lane < m.NB) g[L.off_betas + lane] = f.dpf[(size_t)b * m.Kp + m.P + lane] + ((acc + a1) + a2);
+        if (lane < m.NB) {
+            float dsh = f.dpf[(size_t)b * m.Kp + m.P + lane];
+            if (f.dpf2) dsh += f.dpf2[(size_t)b * m.Kp + m.P + lane];
+            g[L.off_betas + lane] = dsh + ((acc + a1) + a2);
+        }
     }
     for (int i = lane; i < 3 + L.nbody; i += 32) g[4 + i] = dfp[i];      // global_orient + body_pose
     if (m.is_smplx) {

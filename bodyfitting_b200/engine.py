@@ -84,6 +84,7 @@ class FrameBuffers(object):
             if tc and not full and model.n_act_pad <= 512:
                 # per 128-frame tile the 16-vertex blocks of the active set its frames need (two buffers: iteration parity)
                 buf('blk_mask', 2, (B + 127) // 128, zero=True, dtype=torch.int32)
+                buf('dpf2', B, Kp, zero=True)            # second half-reduction of the masked backward GEMM
             if temporal_weight > 0:
                 buf('tgrad', B, NP, zero=True)
                 buf('tloss', B, zero=True)

@@ -40,7 +40,7 @@ extern "C" {
 #define BF_ECUDA    -2   /* a CUDA runtime call / launch failed            */
 #define BF_EARCH    -3   /* device is not sm_100 (no fallback exists)      */
 
-#define BF_ABI_VERSION 17
+#define BF_ABI_VERSION 18
 #define BF_F_WORLD 1   /* forward outputs in world space: (x + transl) * scale * constant_scale */
 #define BF_F_TC    2   /* run the blend-shape contractions on tcgen05 tensor cores (3xTF32) */
 #define BF_F_SKIN_FUSED 4  /* bf_frame_loss_backward skins the frame's live vertices itself from vposed (after bf_blend_forward) */
@@ -154,6 +154,9 @@ typedef struct BfFrames {
     uint32_t*    blk_mask;   /* [2, ceil(B/128)] (or NULL): per 128-frame tile the OR of lv_blk over its frames' yaw rows -- the
                                 16-vertex blocks of the active set the blend GEMMs have to touch for that tile.  Written by the pose
                                 forward (buffer = iteration parity), cleared by the per-frame kernel; zero before the first iteration */
+    float*       dpf2;       /* [B,Kp] (or NULL): second half-reduction of the masked blend backward GEMM; when set (together with
+                                blk_mask) the GEMM cuts every tile's reduction in two runs, dpf and dpf2, and bf_pose_backward adds
+                                them (dpf + dpf2, fixed order) */
     const int32_t* frame_index; /* [B] (or NULL = identity): row of `kp` that belongs to frame b.  The host may process the frames
                                    of a batch in any order (and re-order them between iterations: only theta / adam_m / adam_v rows
                                    move); the 13 KB keypoint rows stay where they are behind this index */
