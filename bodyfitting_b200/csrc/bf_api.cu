@@ -395,7 +395,9 @@ int bf_pose_backward(const BfModel* m, const BfFrames* f, int flags, void* strea
     static int wpb = 0;
     if (!wpb) { const char* e = getenv("BODYFIT_POSE_WPB"); wpb = e ? atoi(e) : 2; if (wpb < 1 || wpb > 4) wpb = 2; }
     const dim3 grid((f->B + wpb - 1) / wpb), block(32 * wpb);
-    k_pose_bwd<<<grid, block, wpb * sizeof(PoseSmemBwd), (cudaStream_t)stream>>>(*m, *f, flags, ad);
+    BfFrames g = *f;
+    if (!bf_bwd_two_cta(m, f)) g.dpf2 = nullptr;         // the backward GEMM added its two half-reductions itself
+    k_pose_bwd<<<grid, block, wpb * sizeof(PoseSmemBwd), (cudaStream_t)stream>>>(*m, g, flags, ad);
     BF_LAUNCH_CHECK();
     return BF_OK;
 }

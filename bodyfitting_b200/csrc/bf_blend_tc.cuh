@@ -99,10 +99,10 @@ struct Pipe {
 template <int NS>
 __device__ __forceinline__ void producer(const Pipe& p, const CUtensorMap* mA_hi, const CUtensorMap* mA_lo,
                                          const CUtensorMap* mB_hi, const CUtensorMap* mB_lo, int num_k, int rowA, int rowB,
-                                         int kc_begin = 0, uint32_t blk_mask = 0xFFFFFFFFu) {
+                                         int kc_begin = 0, uint32_t blk_mask = 0xFFFFFFFFu, int pipe0 = 0) {
     for (int kc = 0; kc < num_k; ++kc) {
-        const int s = kc % NS;
-        const uint32_t ph = (kc / NS) & 1;
+        const int s = (pipe0 + kc) % NS;                    // pipe0: chunks already sent through the pipeline by an earlier run
+        const uint32_t ph = ((pipe0 + kc) / NS) & 1;
         mbar_wait(&p.empty[s], ph ^ 1);
         mbar_expect_tx(&p.full[s], p.stage_bytes());
         uint8_t* st = p.stage(s);
@@ -117,10 +117,11 @@ __device__ __forceinline__ void producer(const Pipe& p, const CUtensorMap* mA_hi
 }
 
 template <int NS>
-__device__ __forceinline__ void mma_issuer(const Pipe& p, int num_k, uint32_t tmem_d, uint32_t idesc) {
+__device__ __forceinline__ void mma_issuer(const Pipe& p, int num_k, uint32_t tmem_d, uint32_t idesc, int pipe0 = 0,
+                                           bool last = true) {
     for (int kc = 0; kc < num_k; ++kc) {
-        const int s = kc % NS;
-        const uint32_t ph = (kc / NS) & 1;
+        const int s = (pipe0 + kc) % NS;
+        const uint32_t ph = ((pipe0 + kc) / NS) & 1;
         mbar_wait(&p.full[s], ph);
         tc_fence_after();
         uint8_t* st = p.stage(s);
@@ -135,7 +136,7 @@ __device__ __forceinline__ void mma_issuer(const Pipe& p, int num_k, uint32_t tm
         }
         umma_commit(&p.empty[s]);                        // frees the smem slot when these MMAs have read it
     }
-    umma_commit(p.tmem_full);                            // accumulator complete
+    if (last) umma_commit(p.tmem_full);                  // accumulator(s) complete
 }
 
 }  // namespace tc
@@ -503,7 +504,7 @@ __global__ void __launch_bounds__(192, 1) k_blend_bwd_tc(const __grid_constant__
                                                          const __grid_constant__ CUtensorMap mB_lo,
                                                          int BN, int num_k_total, int cps, int Kp,
                                                          float* __restrict__ out, size_t split_stride, int B,
-                                                         const uint32_t* __restrict__ blk_mask) {
+                                                         const uint32_t* __restrict__ blk_mask, int fuse_halves) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     tc::Pipe p;
@@ -517,11 +518,12 @@ __global__ void __launch_bounds__(192, 1) k_blend_bwd_tc(const __grid_constant__
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b0 = blockIdx.y * TC_BM;
     const int k0 = blockIdx.x * BN;
-    const int tmem_cols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+    const int acc_cols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+    const int tmem_cols = fuse_halves ? 2 * acc_cols : acc_cols;
     // split-K: this CTA reduces K chunks [kc_begin, kc_begin + num_k) and writes its own partial
     // (the tensor-core accumulator truncates, so long reductions are cut and summed in fp32 RN)
     int kc_begin = blockIdx.z * cps;
-    uint32_t mask = 0xFFFFFFFFu;
+    uint32_t mask = 0xFFFFFFFFu, mask2 = 0u;
     int num_k;
     if (blk_mask) {
         // masked reduction: 3 chunks per set block.  With gridDim.z == 2 the reduction is cut at a FIXED block (BW_SPLIT_BLOCK:
@@ -531,15 +533,21 @@ __global__ void __launch_bounds__(192, 1) k_blend_bwd_tc(const __grid_constant__
         mask = blk_mask[blockIdx.y];
         const int nblk = num_k_total / 3;
         if (nblk < 32) mask &= (1u << nblk) - 1u;
-        if (gridDim.z == 2) {
+        if (gridDim.z == 2 || fuse_halves) {
             const uint32_t low = (1u << min(BW_SPLIT_BLOCK, nblk / 2)) - 1u;
-            mask = blockIdx.z == 0 ? (mask & low) : (mask & ~low);
+            mask2 = mask & ~low;
+            mask = gridDim.z == 2 ? (blockIdx.z == 0 ? (mask & low) : mask2) : (mask & low);
             if (mask == 0xFFFFFFFFu) mask = 0xFFFFFFFEu;   // cannot happen (a half never has 32 blocks); keeps the masked path
         }
     }
-    if (blk_mask && (gridDim.z == 2 || mask != 0xFFFFFFFFu)) {
+    // fuse_halves: the same two half-reductions, run one after the other by ONE CTA into two TMEM accumulators that the
+    // epilogue adds -- the arithmetic of the two-CTA form (acc0 + acc1 in fp32, then the consumer's sum) without the second
+    // output buffer; the launcher picks it for large batches, where the grid fills the SMs anyway
+    int num_k2 = 0;
+    if (blk_mask && (gridDim.z == 2 || fuse_halves || mask != 0xFFFFFFFFu)) {
         kc_begin = 0;
         num_k = 3 * __popc(mask);
+        if (fuse_halves) num_k2 = 3 * __popc(mask2);
     } else {
         mask = 0xFFFFFFFFu;
         num_k = min(cps, num_k_total - kc_begin);
@@ -561,11 +569,18 @@ __global__ void __launch_bounds__(192, 1) k_blend_bwd_tc(const __grid_constant__
     const uint32_t tmem_d = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0 && num_k > 0) tc::producer<NS>(p, &mA_hi, &mA_lo, &mB_hi, &mB_lo, num_k, b0, k0, kc_begin, mask);
+        if (lane == 0) {
+            if (num_k > 0) tc::producer<NS>(p, &mA_hi, &mA_lo, &mB_hi, &mB_lo, num_k, b0, k0, kc_begin, mask);
+            if (num_k2 > 0) tc::producer<NS>(p, &mA_hi, &mA_lo, &mB_hi, &mB_lo, num_k2, b0, k0, 0, mask2, num_k);
+        }
     } else if (warp == 1) {
-        if (lane == 0 && num_k > 0) tc::mma_issuer<NS>(p, num_k, tmem_d, tc::make_idesc_tf32(TC_BM, BN));
+        if (lane == 0) {
+            const uint32_t idesc = tc::make_idesc_tf32(TC_BM, BN);
+            if (num_k > 0) tc::mma_issuer<NS>(p, num_k, tmem_d, idesc, 0, num_k2 == 0);
+            if (num_k2 > 0) tc::mma_issuer<NS>(p, num_k2, tmem_d + (uint32_t)acc_cols, idesc, num_k, true);
+        }
     } else {
-        if (num_k > 0) {
+        if (num_k + num_k2 > 0) {
             tc::mbar_wait(p.tmem_full, 0);
             tc::tc_fence_after();
         }
@@ -577,6 +592,16 @@ __global__ void __launch_bounds__(192, 1) k_blend_bwd_tc(const __grid_constant__
             else {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) r[i] = 0u;                        // empty mask: the gradient rows are zero
+            }
+            if (fuse_halves) {
+                uint32_t r2[32];
+                if (num_k2 > 0) tc::tmem_ld32(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(acc_cols + c), r2);
+                else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) r2[i] = 0u;
+                }
+#pragma unroll
+                for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(r2[i]));
             }
             if (b < B) {
                 float4* o = reinterpret_cast<float4*>(dpf + (size_t)b * Kp + k0 + c);
@@ -747,6 +772,19 @@ static int bf_blend_forward_tc(const BfModel* m, const BfVSet* vs, const BfFrame
     return bf_gemm_forward_tc(f->pf_hi, f->pf_lo, vs->Bt_hi, vs->Bt_lo, f->B, m->Kp, vs->ldn, vs->n, dst, f->ld_v, s);
 }
 
+// The masked backward GEMM always reduces a tile in two halves cut at a fixed block (BW_SPLIT_BLOCK) and adds the two
+// partial sums.  Two forms of the same arithmetic: two CTAs per tile writing dpf and dpf2 (summed by k_pose_bwd), chosen
+// when even the doubled grid is at most one wave -- the batch is small and bound by the latency of one CTA's K loop -- and
+// one CTA per tile with two TMEM accumulators added in its epilogue otherwise (no second buffer to write and re-read).
+static bool bf_bwd_two_cta(const BfModel* m, const BfFrames* f) {
+    if (!f->dpf2 || !f->blk_mask || !bf_blk_mask_on()) return false;
+    int BN = m->Kp < 256 ? m->Kp : 256;
+    while (BN > 64 && m->Kp % BN != 0) BN /= 2;
+    if (m->Kp % BN != 0) BN = m->Kp;
+    const int mt = (f->B + TC_BM - 1) / TC_BM;
+    return (m->Kp / BN) * mt * 2 <= bf_num_sms();
+}
+
 static int bf_blend_backward_tc(const BfModel* m, const BfVSet* vs, const BfFrames* f, cudaStream_t s) {
     CUtensorMap a_hi, a_lo, b_hi, b_lo;
     int rc;
@@ -766,7 +804,7 @@ static int bf_blend_backward_tc(const BfModel* m, const BfVSet* vs, const BfFram
     // in the same order, so the result does not depend on the tile width (bit-identical across batch sizes, tested).
     if (vs->ldn / TC_BK <= 2048 / TC_BK) {                 // single accumulation run only (the all-vertex backward is split-K)
         const int mt = (f->B + TC_BM - 1) / TC_BM;
-        const int halves = (f->dpf2 && f->blk_mask && bf_blk_mask_on()) ? 2 : 1;
+        const int halves = bf_bwd_two_cta(m, f) ? 2 : 1;
         while (BN > 64 && (m->Kp / BN) * mt * halves * 2 < num_sms && m->Kp % (BN / 2) == 0 && (BN / 2) % 16 == 0) BN /= 2;
     }
     {
@@ -823,14 +861,15 @@ static int bf_blend_backward_tc(const BfModel* m, const BfVSet* vs, const BfFram
     // block mask of the active set (BfFrames.blk_mask, buffer of this iteration's parity): single-run reductions only
     const uint32_t* mask = (bf_blk_mask_on() && f->blk_mask && vs->lv_blk && S == 1 && TC_BK == 16 && vs->n_pad <= 512 && num_k % 3 == 0)
                                ? f->blk_mask + (size_t)(f->iter & 1) * ((f->B + 127) / 128) : nullptr;
-    // two half-reductions per tile into dpf / dpf2 (summed by k_pose_bwd): halves the latency of a CTA's K loop -- what a
-    // small batch (a shard of a strong-scaled sequence) is bound by -- and evens out the last wave of a large one
+    // two half-reductions per tile (bf_bwd_two_cta above): by two CTAs into dpf / dpf2, or fused in one CTA
     float* out0 = S > 1 ? f->ws : f->dpf;
     size_t out_stride = stride;
-    if (mask && f->dpf2) { grid.z = 2; out0 = f->dpf; out_stride = (size_t)(f->dpf2 - f->dpf); }
-    if (NS == 2) k_blend_bwd_tc<2><<<grid, 192, smem, s>>>(a_hi, a_lo, b_hi, b_lo, BN, num_k, cps, m->Kp, out0, out_stride, f->B, mask);
-    else if (NS == 8) k_blend_bwd_tc<8><<<grid, 192, smem, s>>>(a_hi, a_lo, b_hi, b_lo, BN, num_k, cps, m->Kp, out0, out_stride, f->B, mask);
-    else k_blend_bwd_tc<TC_STAGES><<<grid, 192, smem, s>>>(a_hi, a_lo, b_hi, b_lo, BN, num_k, cps, m->Kp, out0, out_stride, f->B, mask);
+    int fuse = 0;
+    if (mask && bf_bwd_two_cta(m, f)) { grid.z = 2; out0 = f->dpf; out_stride = (size_t)(f->dpf2 - f->dpf); }
+    else if (mask) fuse = 1;
+    if (NS == 2) k_blend_bwd_tc<2><<<grid, 192, smem, s>>>(a_hi, a_lo, b_hi, b_lo, BN, num_k, cps, m->Kp, out0, out_stride, f->B, mask, fuse);
+    else if (NS == 8) k_blend_bwd_tc<8><<<grid, 192, smem, s>>>(a_hi, a_lo, b_hi, b_lo, BN, num_k, cps, m->Kp, out0, out_stride, f->B, mask, fuse);
+    else k_blend_bwd_tc<TC_STAGES><<<grid, 192, smem, s>>>(a_hi, a_lo, b_hi, b_lo, BN, num_k, cps, m->Kp, out0, out_stride, f->B, mask, fuse);
     BF_LAUNCH_CHECK();
     if (S > 1) {
         const size_t n = stride;
