@@ -10,7 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('BODYFIT_LIB') or os.path.join(_HERE, 'libbodyfit_b200.so')   # BODYFIT_LIB: A/B builds of the same ABI
-ABI_VERSION = 18
+ABI_VERSION = 19
 F_WORLD = 1
 F_TC = 2
 F_SKIN_FUSED = 4
@@ -25,6 +25,16 @@ class BfVSet(C.Structure):
         'dyn_src', 'dyn_w', 'tg_ptr', 'tg_k', 'tg_a', 'tg_w', 'xr_ptr', 'xr_vid', 'xr_w', 'Bt_hi', 'Bt_lo', 'Bm_hi', 'Bm_lo', 'dyn_k', 'jv_nz',
         'lv_n', 'lv_vid', 'lt_ptr', 'lt_k', 'lt_w', 'lj_ptr', 'lj_vid', 'lj_w', 'lv_blk')] + \
         [(n, _i32) for n in ('n', 'n_pad', 'ldn', 'nnz', 'K_out', 'n_dyn', 'n_extra', 'n_nz', 'lmax', 'n_rows')]
+
+
+class BfModelDesc(C.Structure):
+    """Raw model arrays for bf_model_create / bf_model_build_blob (include/bodyfit_b200.h)."""
+    _fields_ = [(n, _fp) for n in (
+        'v_template', 'shapedirs', 'posedirs', 'J_regressor', 'weights', 'parents', 'faces', 'hands_meanl', 'hands_meanr',
+        'hands_componentsl', 'hands_componentsr', 'lmk_faces_idx', 'lmk_bary_coords', 'dynamic_lmk_faces_idx',
+        'dynamic_lmk_bary_coords', 'extra_vids', 'J_regressor_extra', 'kid_template', 'gmm_means', 'gmm_covars', 'gmm_weights')] + \
+        [(n, _i32) for n in ('is_smplx', 'V', 'J', 'F', 'n_shape_dirs', 'num_betas', 'num_expression', 'n_lmk', 'n_dyn_rows', 'n_dyn',
+                             'n_extra_vids', 'n_regressor_extra', 'n_gmm', 'tensor_cores', '_pad0', '_pad1')]
 
 
 class BfModel(C.Structure):
@@ -124,6 +134,12 @@ def lib():
     L.bf_model_load_memory.argtypes = [C.c_void_p, C.c_int64, C.POINTER(pm)]
     L.bf_model_destroy.restype = C.c_int
     L.bf_model_destroy.argtypes = [pm]
+    L.bf_model_create.restype = C.c_int
+    L.bf_model_create.argtypes = [C.POINTER(BfModelDesc), C.POINTER(pm)]
+    L.bf_model_build_blob.restype = C.c_int
+    L.bf_model_build_blob.argtypes = [C.POINTER(BfModelDesc), C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
+    L.bf_blob_free.restype = None
+    L.bf_blob_free.argtypes = [C.c_void_p]
     L.bf_workspace_bytes.restype = C.c_int64
     L.bf_workspace_bytes.argtypes = [pm, i32, i32, i32, i32]
     L.bf_frames_bind.restype = C.c_int
@@ -163,6 +179,7 @@ EXPORTED = ['bf_abi_version', 'bf_sizeof', 'bf_last_error', 'bf_check_device', '
             'bf_pose_backward', 'bf_gmm_prior', 'bf_temporal_prior', 'bf_fit_iteration', 'bf_frame_loss_backward', 'bf_lbs_forward', 'bf_lbs_backward', 'bf_fit_step', 'bf_fit_run',
             'bf_pack_keypoints', 'bf_init_theta', 'bf_scatter_rows', 'bf_halo_bytes', 'bf_halo_handle_bytes', 'bf_halo_alloc', 'bf_halo_open',
             'bf_halo_close', 'bf_halo_free', 'bf_halo_begin', 'bf_model_load', 'bf_model_load_memory', 'bf_model_destroy',
+            'bf_model_create', 'bf_model_build_blob', 'bf_blob_free',
             'bf_workspace_bytes', 'bf_frames_bind', 'bf_graph_set_kernel_priority']
 
 
@@ -171,6 +188,11 @@ EXPORTED_MASK = ['bf_mask_loss']
 EXPORTED_OPS = ['bf_op_project', 'bf_op_project_backward', 'bf_op_gmof', 'bf_op_gmof_backward', 'bf_op_reprojection',
                 'bf_op_keypoints_world', 'bf_op_angle_prior', 'bf_op_gmm_pose', 'bf_op_pc_loss', 'bf_op_normal_loss',
                 'bf_op_laplacian', 'bf_op_vertex_normals', 'bf_op_vertex_normals_backward', 'bf_op_mask_loss', 'bf_op_regress_joints']
+
+
+def last_error():
+    msg = lib().bf_last_error()
+    return msg.decode() if msg else ''
 
 
 def check(rc, what=''):

@@ -19,6 +19,7 @@
 #include "bf_blend_tc.cuh"
 #include "bf_blend_tc2.cuh"
 #include "bf_pack.cuh"
+#include "bf_model_build.cuh"
 
 static thread_local char g_err[512] = "";
 
@@ -572,6 +573,34 @@ int bf_model_load_memory(const void* blob, int64_t nbytes, BfModel** out) {
     return BF_OK;
 }
 
+int bf_model_build_blob(const BfModelDesc* desc, void** blob, int64_t* nbytes) {
+    BF_REQUIRE(desc && blob && nbytes, "bad arguments");
+    bfb::Builder b(*desc);
+    BfModel img;
+    if (!b.run(&img)) { bf_set_error("bf_model_create: %s", b.err ? b.err : "invalid model description"); return BF_EINVAL; }
+    const int64_t total = (int64_t)b.arr.bytes.size();
+    const int64_t n = 16 + (int64_t)sizeof(BfModel) + 8 + total;
+    char* p = (char*)malloc((size_t)n);
+    BF_REQUIRE(p, "out of host memory");
+    memcpy(p, "BFMODEL1", 8);
+    const int32_t abi = BF_ABI_VERSION, sz = (int32_t)sizeof(BfModel);
+    memcpy(p + 8, &abi, 4); memcpy(p + 12, &sz, 4);
+    memcpy(p + 16, &img, sizeof(BfModel));
+    memcpy(p + 16 + sizeof(BfModel), &total, 8);
+    memcpy(p + 16 + sizeof(BfModel) + 8, b.arr.bytes.data(), (size_t)total);
+    *blob = p; *nbytes = n;
+    return BF_OK;
+}
+void bf_blob_free(void* blob) { free(blob); }
+int bf_model_create(const BfModelDesc* desc, BfModel** out) {
+    BF_REQUIRE(desc && out, "bad arguments");
+    void* blob = nullptr; int64_t n = 0;
+    int rc = bf_model_build_blob(desc, &blob, &n);
+    if (rc) return rc;
+    rc = bf_model_load_memory(blob, n, out);
+    free(blob);
+    return rc;
+}
 int bf_model_load(const char* path, BfModel** out) {
     BF_REQUIRE(path && out, "bad arguments");
     FILE* fp = fopen(path, "rb");

@@ -71,6 +71,49 @@ def load_model_data(path_or_dict, model_type=None, gender='neutral'):
     return {k: d[k] for k in d.files}
 
 
+def model_desc(smpl_type, data, gmm=None, J_regressor_extra=None, num_betas=10, num_expression=10, tensor_cores=True,
+               gender='neutral', kid_template=None):
+    """``(BfModelDesc, keepalive)`` for ``bf_model_create`` / ``bf_model_build_blob``: the raw model arrays as the C ABI
+    takes them (what a non-Python host would pass after reading the model file itself)."""
+    data = load_model_data(data, smpl_type, gender)
+    keep = []
+
+    def arr(x, dt):
+        a = np.ascontiguousarray(np.asarray(x), dtype=dt)
+        keep.append(a)
+        return a.ctypes.data
+
+    d = _lib.BfModelDesc()
+    vt = np.asarray(data['v_template'])
+    W = np.asarray(data['weights'])
+    sd = np.asarray(data['shapedirs'])
+    if sd.ndim == 2:
+        sd = sd[:, :, None]
+    faces = np.asarray(data['f'])
+    d.v_template, d.shapedirs, d.posedirs = arr(vt, np.float32), arr(sd, np.float32), arr(data['posedirs'], np.float32)
+    d.J_regressor, d.weights = arr(data['J_regressor'], np.float32), arr(W, np.float32)
+    d.parents, d.faces = arr(np.asarray(data['kintree_table'])[0].astype(np.int64), np.int32), arr(faces, np.int32)
+    d.is_smplx, d.V, d.J, d.F, d.n_shape_dirs = int(smpl_type == 'smplx'), vt.shape[0], W.shape[1], faces.shape[0], sd.shape[2]
+    d.num_betas, d.num_expression, d.tensor_cores = num_betas, num_expression, int(bool(tensor_cores))
+    if smpl_type == 'smplx':
+        d.hands_meanl, d.hands_meanr = arr(data['hands_meanl'], np.float32), arr(data['hands_meanr'], np.float32)
+        d.hands_componentsl, d.hands_componentsr = arr(data['hands_componentsl'], np.float32), arr(data['hands_componentsr'], np.float32)
+        d.lmk_faces_idx, d.lmk_bary_coords = arr(data['lmk_faces_idx'], np.int32), arr(data['lmk_bary_coords'], np.float32)
+        dyn = np.asarray(data['dynamic_lmk_faces_idx'])
+        d.dynamic_lmk_faces_idx, d.dynamic_lmk_bary_coords = arr(dyn, np.int32), arr(data['dynamic_lmk_bary_coords'], np.float32)
+        d.n_lmk, d.n_dyn_rows, d.n_dyn = len(np.asarray(data['lmk_faces_idx'])), dyn.shape[0], dyn.shape[1]
+    if 'extra_vids' in data:
+        d.extra_vids, d.n_extra_vids = arr(data['extra_vids'], np.int32), len(np.asarray(data['extra_vids']))
+    if J_regressor_extra is not None:
+        d.J_regressor_extra, d.n_regressor_extra = arr(J_regressor_extra, np.float32), np.asarray(J_regressor_extra).shape[0]
+    if kid_template is not None:
+        d.kid_template = arr(kid_template, np.float32)
+    if gmm is not None:
+        d.gmm_means, d.gmm_covars, d.gmm_weights = arr(gmm['means'], np.float32), arr(gmm['covars'], np.float32), arr(gmm['weights'], np.float32)
+        d.n_gmm = np.asarray(gmm['means']).shape[0]
+    return d, keep
+
+
 class PreparedModel(object):
     """numpy tables -> device tensors -> BfModel struct (kept alive by this object)."""
 

@@ -40,7 +40,7 @@ extern "C" {
 #define BF_ECUDA    -2   /* a CUDA runtime call / launch failed            */
 #define BF_EARCH    -3   /* device is not sm_100 (no fallback exists)      */
 
-#define BF_ABI_VERSION 18
+#define BF_ABI_VERSION 19
 #define BF_F_WORLD 1   /* forward outputs in world space: (x + transl) * scale * constant_scale */
 #define BF_F_TC    2   /* run the blend-shape contractions on tcgen05 tensor cores (3xTF32) */
 #define BF_F_SKIN_FUSED 4  /* bf_frame_loss_backward skins the frame's live vertices itself from vposed (after bf_blend_forward) */
@@ -222,11 +222,45 @@ int bf_fit_run(const BfModel* m, const BfFrames* f, int n_iters, void* stream);
 /* ---- model and frame buffers for hosts that do not run Python ---------------------------------------------------------
  * The body-model tables (BfModel: ~60 device arrays derived from v_template / shapedirs / posedirs / J_regressor / weights /
  * landmark tables / the GMM prior; reference: models/smpl.py:56-66, smplify/smplify.py:46-80, smplify/prior.py:127-174) are
- * prepared once by the Python tool (bodyfitting_b200.model.PreparedModel(...).save_blob(path)) and loaded here with one
- * upload; bf_model_destroy frees them.  bf_workspace_bytes / bf_frames_bind size and carve ONE caller-owned, 256-byte aligned
+ * built from the raw model arrays by bf_model_create (C++, no Python), or prepared once by the Python tool
+ * (bodyfitting_b200.model.PreparedModel(...).save_blob(path)) and loaded by bf_model_load with one upload; bf_model_destroy
+ * frees them.  bf_workspace_bytes / bf_frames_bind size and carve ONE caller-owned, 256-byte aligned
  * device workspace into the BfFrames buffers of a B-frame batch (opts: 1 = all-vertex set, 2 = backward / optimiser buffers,
  * 8 = temporal term; n_trace = rows of the optional per-iteration loss trace), zero it and fill in the reference's
  * hyper-parameters.  These are the only calls besides bf_halo_* that allocate or synchronise. */
+/* Raw model arrays, exactly as the reference's model files hold them (SMPL_*.pkl / SMPLX_*.npz keys of the same names; dense,
+ * row-major, float32 / int32).  Optional members may be NULL / 0.  bf_model_create builds every derived table on the host (C++,
+ * bodyfitting_b200/csrc/bf_model_build.cuh -- the same algorithm as the Python builder, compared table by table in
+ * tests/test_host.py) and uploads it; bf_model_build_blob stops before the upload and hands back the image bf_model_load_memory
+ * accepts (free it with bf_blob_free).  Reference: models/smpl.py:56-66, smplify/smplify.py:46-80, smplify/prior.py:127-174. */
+typedef struct BfModelDesc {
+    const float*   v_template;              /* [V,3] */
+    const float*   shapedirs;               /* [V,3,n_shape_dirs]; official SMPL-X files: 300 shape + 100 expression directions */
+    const float*   posedirs;                /* [V,3,(J-1)*9] */
+    const float*   J_regressor;             /* [J,V] dense */
+    const float*   weights;                 /* [V,J] skinning weights */
+    const int32_t* parents;                 /* [J] kintree_table[0]; parents[0] is ignored */
+    const int32_t* faces;                   /* [F,3] (SMPL-X: needed for the landmark tables) */
+    const float*   hands_meanl;             /* [45]   SMPL-X */
+    const float*   hands_meanr;             /* [45] */
+    const float*   hands_componentsl;       /* [>=6,45]: the first six PCA rows are used (smplx num_pca_comps=6) */
+    const float*   hands_componentsr;
+    const int32_t* lmk_faces_idx;           /* [n_lmk]   SMPL-X static face landmarks */
+    const float*   lmk_bary_coords;         /* [n_lmk,3] */
+    const int32_t* dynamic_lmk_faces_idx;   /* [n_dyn_rows,n_dyn]   SMPL-X contour landmarks per yaw row (79 x 17) */
+    const float*   dynamic_lmk_bary_coords; /* [n_dyn_rows,n_dyn,3] */
+    const int32_t* extra_vids;              /* [n_extra_vids] vertex-picked joints, or NULL = smplx.vertex_ids */
+    const float*   J_regressor_extra;       /* [n_regressor_extra,V] SMPL wrapper's extra joints (models/smpl.py:62-65), or NULL */
+    const float*   kid_template;            /* [V,3] SMIL template (age='kid', SMPL only), or NULL */
+    const float*   gmm_means;               /* [n_gmm,69]   pose prior (smplify/prior.py:127), or NULL */
+    const float*   gmm_covars;              /* [n_gmm,69,69] */
+    const float*   gmm_weights;             /* [n_gmm] */
+    int32_t is_smplx, V, J, F, n_shape_dirs, num_betas, num_expression, n_lmk, n_dyn_rows, n_dyn, n_extra_vids, n_regressor_extra,
+            n_gmm, tensor_cores, _pad0, _pad1;
+} BfModelDesc;
+int     bf_model_create(const BfModelDesc* desc, BfModel** out);
+int     bf_model_build_blob(const BfModelDesc* desc, void** blob, int64_t* nbytes);
+void    bf_blob_free(void* blob);
 int     bf_model_load(const char* path, BfModel** out);
 int     bf_model_load_memory(const void* blob, int64_t nbytes, BfModel** out);
 int     bf_model_destroy(BfModel* m);

@@ -550,6 +550,28 @@ def test_c_abi_host_without_python_tables(assets, tmp_path):
     assert torch.equal(got, want)
     _lib.check(L.bf_model_destroy(mptr), 'bf_model_destroy')
     assert L.bf_model_destroy(C.POINTER(_lib.BfModel)()) == 0                       # NULL is a no-op
+    # the same again with the tables built in C++ from the raw model arrays (bf_model_create): no Python-made table anywhere
+    from bodyfitting_b200.model import model_desc
+    desc, keep = model_desc(mt, assets(mt), gmm=assets('gmm'), tensor_cores=pm.tensor_cores)
+    mptr2 = C.POINTER(_lib.BfModel)()
+    _lib.check(L.bf_model_create(C.byref(desc), C.byref(mptr2)), 'bf_model_create')
+    assert mptr2.contents.J == pm.J and mptr2.contents.act.n == pm.n_act and mptr2.contents.NP == pm.NP
+    assert L.bf_workspace_bytes(mptr2, B, nv, 2, N) == need
+    ws.zero_()
+    fr2 = _lib.BfFrames()
+    _lib.check(L.bf_frames_bind(mptr2, B, nv, 2, N, base, need, C.byref(fr2), st), 'bf_frames_bind')
+    _lib.check(L.bf_pack_keypoints(kp.data_ptr(), fr2.kp, B, nv, pm.K_used, 1, None, st), 'bf_pack_keypoints')
+    view(fr2.cams, nv * 12).copy_(cams.reshape(-1))
+    _lib.check(L.bf_init_theta(mptr2, poses.data_ptr(), poses.shape[1], betas.data_ptr(), fr2.theta, B, None, st), 'bf_init_theta')
+    _lib.check(L.bf_fit_run(mptr2, C.byref(fr2), N, st), 'bf_fit_run')
+    torch.cuda.synchronize()
+    got2 = view(fr2.theta, B * pm.NP).reshape(B, pm.NP)
+    # identical tables (tests/test_host.py) -> identical fit; the GMM precisions are inverted in fp64 here, in fp32 by numpy
+    assert (got2 - want).abs().max().item() < 1e-5
+    print('bf_model_create fit vs Python-built tables: max |d theta| %.2e' % (got2 - want).abs().max().item())
+    _lib.check(L.bf_model_destroy(mptr2), 'bf_model_destroy')
+    bad = _lib.BfModelDesc()
+    assert L.bf_model_create(C.byref(bad), C.byref(mptr2)) != 0 and 'required' in _lib.last_error()
 
 
 def test_row_sorted_block_masked_fit_equals_plain_order(assets):

@@ -284,7 +284,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     L = _lib.lib()
     hdr = open(os.path.join(ROOT, 'include', 'bodyfit_b200.h')).read() + open(os.path.join(ROOT, 'include', 'bodyfit_b200_ops.h')).read() + \
         open(os.path.join(ROOT, 'include', 'bodyfit_b200_grid.h')).read() + open(os.path.join(ROOT, 'include', 'bodyfit_b200_mask.h')).read()
-    declared = set(re.findall(r'^(?:int|int64_t|const char\*)\s+(bf_[a-z0-9_]+)\s*\(', hdr, re.M))
+    declared = set(re.findall(r'^(?:int|int64_t|void|const char\*)\s+(bf_[a-z0-9_]+)\s*\(', hdr, re.M))
     assert declared, 'no declarations parsed'
     for name in sorted(declared):
         assert hasattr(L, name), 'symbol %s declared in the header but not exported' % name
@@ -498,3 +498,72 @@ def test_loader_accepts_official_model_file_layout(assets, tmp_path):
         warnings.simplefilter('always')
         male = load_model_data(str(tmp_path / 'data'), 'smpl', 'male')
     assert np.array_equal(male['v_template'], assets('smpl')['v_template']) and any('NEUTRAL' in str(x.message) for x in w)
+
+
+# ---- bf_model_create: the C++ table builder against the Python one --------------------------------------------------
+_FLOAT_FIELDS = {'Jt', 'Jd', 'pose_mean', 'hand_l', 'hand_r', 'gmm_mean', 'gmm_psym', 'gmm_logw', 'gmm_bt_hi', 'gmm_bt_lo',
+                 'Bm', 'ell_w', 'jv_w', 'kj_w', 'dyn_w', 'tg_w', 'xr_w', 'Bt_hi', 'Bt_lo', 'Bm_hi', 'Bm_lo', 'lt_w', 'lj_w'}
+
+
+def _parse_blob(raw):
+    """blob bytes -> (BfModel image, {'m_x' / 'full_x' / 'act_x': raw bytes of the array, padding included})"""
+    assert raw[:8] == b'BFMODEL1'
+    abi, sz = np.frombuffer(raw[8:16], np.int32)
+    assert abi == _lib.ABI_VERSION and sz == ctypes.sizeof(_lib.BfModel)
+    img = _lib.BfModel.from_buffer_copy(raw[16:16 + sz])
+    total = int(np.frombuffer(raw[16 + sz:24 + sz], np.int64)[0])
+    sec = raw[24 + sz:24 + sz + total]
+    offs = {}
+    for tag, st in (('m', img), ('full', img.full), ('act', img.act)):
+        for name, typ in st._fields_:
+            if typ is _lib._fp and getattr(st, name):
+                offs[tag + '_' + name] = getattr(st, name) - 1
+    ends = sorted(set(offs.values()) | {total})
+    return img, {k: sec[o:ends[ends.index(o) + 1]] for k, o in offs.items()}
+
+
+@pytest.mark.parametrize('case', ['smpl', 'smplx', 'smpl_kid', 'smpl_plain'])
+def test_bf_model_create_tables_match_python_builder(assets, case, tmp_path):
+    """include/bodyfit_b200.h: bf_model_build_blob (what bf_model_create uploads) builds the SAME tables from the raw model
+    arrays as bodyfitting_b200.model.PreparedModel: index tables bit for bit; folded / inverted float tables to rounding."""
+    mt = 'smplx' if case == 'smplx' else 'smpl'
+    kw = {}
+    if case == 'smpl_kid':
+        kw = dict(kid_template=syn.make_kid_template(0))
+    jx = assets('jx') if case in ('smpl', 'smpl_kid') else None
+    gmm = None if case == 'smpl_plain' else assets('gmm')
+    pm = PreparedModel(mt, assets(mt), gmm=gmm, J_regressor_extra=jx, device='cpu', tensor_cores=True,
+                       age='kid' if case == 'smpl_kid' else 'adult', **kw)
+    path = pm.save_blob(str(tmp_path / 'py.blob'))
+    img_p, arr_p = _parse_blob(open(path, 'rb').read())
+    from bodyfitting_b200.model import model_desc
+    d, keep = model_desc(mt, assets(mt), gmm=gmm, J_regressor_extra=jx, tensor_cores=True, **kw)
+    blob, n = ctypes.c_void_p(), ctypes.c_int64()
+    rc = _lib.lib().bf_model_build_blob(ctypes.byref(d), ctypes.byref(blob), ctypes.byref(n))
+    assert rc == 0, _lib.last_error()
+    raw = ctypes.string_at(blob, n.value)
+    _lib.lib().bf_blob_free(blob)
+    img_c, arr_c = _parse_blob(raw)
+    # scalar members
+    for tag, a, b in (('m', img_p, img_c), ('full', img_p.full, img_c.full), ('act', img_p.act, img_c.act)):
+        for name, typ in a._fields_:
+            if typ is _lib._i32 and not name.startswith('_pad'):
+                assert getattr(a, name) == getattr(b, name), (tag, name)
+    assert set(arr_p) == set(arr_c), set(arr_p) ^ set(arr_c)
+    worst = {}
+    for key in sorted(arr_p):
+        a, b = arr_p[key], arr_c[key]
+        assert len(a) == len(b), (key, len(a), len(b))
+        name = key.split('_', 1)[1]
+        if name in _FLOAT_FIELDS:
+            fa, fb = np.frombuffer(a, np.float32), np.frombuffer(b, np.float32)
+            scale = max(1e-30, float(np.abs(fa).max()))
+            worst[key] = float(np.abs(fa - fb).max()) / scale
+        else:
+            assert a == b, key
+    # float tables: identical except where a reduction is folded (fp64 accumulation order) or a matrix inverted
+    # (numpy inverts the float32 covariances in float32, the C++ builder in float64): measured <= 2e-7 / 3e-5
+    loose = {k for k in worst if 'gmm' in k}
+    assert max([v for k, v in worst.items() if k not in loose] + [0.0]) < 1e-6, {k: v for k, v in worst.items() if v > 0}
+    assert max([worst[k] for k in loose] + [0.0]) < 1e-3, {k: worst[k] for k in loose}
+    print(case, 'largest relative differences:', {k: '%.1e' % v for k, v in worst.items() if v > 0})
