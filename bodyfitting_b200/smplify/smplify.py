@@ -315,10 +315,18 @@ class SMPLify(object):
             n_parts = 1 if self.temporal_weight > 0 else self.concurrent_parts
             if not host_io and 'BODYFIT_PARTS' not in os.environ:
                 n_parts = min(n_parts, self.device_parts)
-            if n_parts > 1 and len(staggered_ranges(B, n_parts, min_part=self.concurrent_min_part)) > 1:
+            # host results: even a small batch (one rank's shard of a strong-scaled sequence) is cut into parts, because the
+            # copy of its vertices is the expensive step there -- eight ranks share ~90 GB/s of host ingest (measured:
+            # the end-to-end overhead over the device time is ~14 ms for 10,000 frames whether 1 or 8 GPUs produce them), so a
+            # shard's copy takes as long as its fit and has to overlap it.  Single process, 1,250 frames: 17.4 ms as one part,
+            # 16.4 ms as four (profiles/r2_e2e_parts_sweep.log).
+            min_part = self.concurrent_min_part
+            if host_io and 'BODYFIT_MIN_PART' not in os.environ:
+                min_part = min(min_part, 256)
+            if n_parts > 1 and len(staggered_ranges(B, n_parts, min_part=min_part)) > 1:
                 cache[key] = ConcurrentFitSession(self.model, B, Nv, self.num_iters, imsize=imsize, return_vertices=return_vertices,
                                                   dense_every_iter=self.dense_every_iter, n_parts=n_parts,
-                                                  min_part=self.concurrent_min_part, lead=self.concurrent_lead,
+                                                  min_part=min_part, lead=self.concurrent_lead,
                                                   taper=self.concurrent_taper, graph=self.graph, sort_frames=self.sort_frames)
             else:
                 cache[key] = FitSession(self.model, B, Nv, self.num_iters, imsize=imsize,

@@ -587,7 +587,8 @@ def test_row_sorted_block_masked_fit_equals_plain_order(assets):
     sc['init_pose'][:, :66] += rng.randn(B, 66).astype(np.float32) * 0.15          # spread the head yaw: many contour rows per tile
     outs = {}
     for sort in (True, False):
-        fit = SMPLify(smpl_type=mt, num_iters=N, gender='neutral', model_data=assets(mt), gmm=assets('gmm'), sort_frames=sort)
+        fit = SMPLify(smpl_type=mt, num_iters=N, gender='neutral', model_data=assets(mt), gmm=assets('gmm'), sort_frames=sort,
+                      concurrent_parts=1)              # one session: its frame order and block masks are inspected below
         o = fit((sc['init_betas'], sc['init_pose']), list(sc['c2ws']), list(sc['Ks']), sc['kp'], None, imsize=512)
         sess = fit.session(B, nv, 512, True)
         assert sess.sort_frames == sort and (len(sess.resort_at) == 2) == sort                     # default schedule 6, 16 (36 > N)
