@@ -467,8 +467,16 @@ int bf_frame_loss_backward(const BfModel* m, const BfFrames* f, void* stream) {
     BF_REQUIRE(smem <= 48 * 1024, "active vertex set too large for the fused per-frame kernel");
     BfFrames g = *f;
     if (!bf_tc_ready_bwd(vs, f)) { g.dvp_hi = nullptr; g.dvp_lo = nullptr; }
-    if (tma) k_frame_loss_bwd<1><<<f->B, FR_THREADS, smem, (cudaStream_t)stream>>>(*m, *vs, g, skin_here);
-    else k_frame_loss_bwd<0><<<f->B, FR_THREADS, smem, (cudaStream_t)stream>>>(*m, *vs, g, skin_here);
+    static int nt = 0;
+    if (!nt) { const char* e = getenv("BODYFIT_FRAME_THREADS"); const int v = e ? atoi(e) : 0; nt = v == 256 ? v : FR_THREADS; }
+    const cudaStream_t s_ = (cudaStream_t)stream;
+    if (tma) {
+        if (nt == 224) k_frame_loss_bwd<1, 224><<<f->B, 224, smem, s_>>>(*m, *vs, g, skin_here);
+        else k_frame_loss_bwd<1, 256><<<f->B, 256, smem, s_>>>(*m, *vs, g, skin_here);
+    } else {
+        if (nt == 224) k_frame_loss_bwd<0, 224><<<f->B, 224, smem, s_>>>(*m, *vs, g, skin_here);
+        else k_frame_loss_bwd<0, 256><<<f->B, 256, smem, s_>>>(*m, *vs, g, skin_here);
+    }
     BF_LAUNCH_CHECK();
     return BF_OK;
 }

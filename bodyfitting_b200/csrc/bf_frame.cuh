@@ -15,7 +15,7 @@
 #include "bf_common.cuh"
 #include "bf_loss.cuh"
 
-#define FR_THREADS 256
+#define FR_THREADS 224      // default launch shape (BODYFIT_FRAME_THREADS=256: the previous one, A/B timing)
 
 // Dynamic shared-memory layout of k_frame_loss_bwd (float offsets, every region 16-byte aligned); host and device use the
 // same function.  TMA = 1 adds the frame's keypoint row and two mbarriers.
@@ -86,8 +86,13 @@ __device__ __forceinline__ void blend_transform(const BfVSet& vs, const float* A
 // TMA = 1: the frame's transforms, v_posed row and keypoint row (J*48 + 12*n + 12*K*Nv bytes, each one contiguous in
 // HBM) are fetched by three bulk copies issued by one thread at kernel entry; the keypoints land while the vertices are
 // being skinned, so the loss loop reads them from shared memory instead of waiting on HBM.
-template <int TMA>
-__global__ void __launch_bounds__(FR_THREADS, 5) k_frame_loss_bwd(BfModel m, BfVSet vs, BfFrames f, int skin_here) {
+// NT threads per CTA: 224 = seven warps cover the <= 224 live vertices of a row in one pass and leave two warps idle in the loss
+// loop (135 joints = five warps) instead of three; with five CTAs per SM the register budget is 56 instead of 48.  Measured in
+// one session, interleaved, 10,000 frames: 191.8 us with 256 threads, 188.9 us with 224, 215.7 us with 192 (two passes over the
+// vertices); the full carve-out attribute makes no difference.  Six CTAs of 224 threads (skinned vertices kept per live vertex
+// so that six 37 KB frames fit) need <= 40 registers and measured 191 us: not kept (profiles/r2_frame_kernel_experiments.md).
+template <int TMA, int NT>
+__global__ void __launch_bounds__(NT, 5) k_frame_loss_bwd(BfModel m, BfVSet vs, BfFrames f, int skin_here) {
     extern __shared__ __align__(16) float sm[];
     const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int K = m.K_used, Nv = f.Nv, J = m.J;
@@ -118,17 +123,17 @@ __global__ void __launch_bounds__(FR_THREADS, 5) k_frame_loss_bwd(BfModel m, BfV
     const int row = vs.n_rows > 1 ? yaw : 0;
     const int L = __ldg(vs.lv_n + row);
     const int32_t* lv = vs.lv_vid + (size_t)row * vs.lmax;
-    for (int i = t; i < Nv * 12; i += FR_THREADS) cam[i] = f.cams[i];
+    for (int i = t; i < Nv * 12; i += NT) cam[i] = f.cams[i];
     {
         if (!TMA) {
             const float4* src = reinterpret_cast<const float4*>(f.A + (size_t)b * J * 12);
-            for (int i = t; i < J * 3; i += FR_THREADS) reinterpret_cast<float4*>(As)[i] = src[i];
+            for (int i = t; i < J * 3; i += NT) reinterpret_cast<float4*>(As)[i] = src[i];
             const float4* vsrc = reinterpret_cast<const float4*>(f.vposed + (size_t)b * f.ld_v);
-            for (int i = t; i < n4; i += FR_THREADS) reinterpret_cast<float4*>(vp)[i] = vsrc[i];
+            for (int i = t; i < n4; i += NT) reinterpret_cast<float4*>(vp)[i] = vsrc[i];
         }
         if (!skin_here) {
             const float4* wsrc = reinterpret_cast<const float4*>(f.verts + (size_t)b * f.ld_v);
-            for (int i = t; i < n4; i += FR_THREADS) reinterpret_cast<float4*>(dv)[i] = wsrc[i];
+            for (int i = t; i < n4; i += NT) reinterpret_cast<float4*>(dv)[i] = wsrc[i];
         }
     }
     // clear this frame's d(v_posed) rows: only live vertices are written below (a vertex live on another yaw row in an
@@ -143,11 +148,11 @@ __global__ void __launch_bounds__(FR_THREADS, 5) k_frame_loss_bwd(BfModel m, BfV
         if (split) {
             float4* oh = reinterpret_cast<float4*>(f.dvp_hi + (size_t)b * vs.ldn);
             float4* ol = reinterpret_cast<float4*>(f.dvp_lo + (size_t)b * vs.ldn);
-            for (int i = t; i < n4; i += FR_THREADS)
+            for (int i = t; i < n4; i += NT)
                 if ((mask >> min(i / 12, 31)) & 1u) { oh[i] = z; ol[i] = z; }
         } else {
             float4* o = reinterpret_cast<float4*>(f.dvp + (size_t)b * f.ld_v);
-            for (int i = t; i < n4; i += FR_THREADS) o[i] = z;
+            for (int i = t; i < n4; i += NT) o[i] = z;
         }
     }
     __syncthreads();
@@ -161,7 +166,7 @@ __global__ void __launch_bounds__(FR_THREADS, 5) k_frame_loss_bwd(BfModel m, BfV
     const float invNv = 1.0f / (float)Nv;
 
     if (skin_here) {                                 // skin the live vertices: verts = (sum_k w_k A_jk) [v_posed; 1]
-        for (int i = t; i < L; i += FR_THREADS) {
+        for (int i = t; i < L; i += NT) {
             const int v = __ldg(lv + i);
             float T[12];
             blend_transform<4>(vs, As, v, T);
@@ -181,7 +186,7 @@ __global__ void __launch_bounds__(FR_THREADS, 5) k_frame_loss_bwd(BfModel m, BfV
     float acc5[5] = {0.f, 0.f, 0.f, 0.f, 0.f};               // loss, d/d transl (3), d/d scale
     const bool vec4 = (Nv & 3) == 0;
     if (TMA) fr_wait(&bars[1]);                      // keypoint row (in flight since kernel entry)
-    for (int k = t; k < K; k += FR_THREADS) {
+    for (int k = t; k < K; k += NT) {
         float x[3];                                  // joint position (model space) + translation: q = x + T
         joint_pos(vs, k, yaw, Jtr_b, dv, x);
         const float qx = x[0] + tx, qy = x[1] + ty, qz = x[2] + tz;
@@ -249,7 +254,7 @@ __global__ void __launch_bounds__(FR_THREADS, 5) k_frame_loss_bwd(BfModel m, BfV
     }
     // joint gradients -> chain joints (static gather by target; the threads at the top of the block, idle below)
     float* dJtr_b = f.dJtr + (size_t)b * J * 3;
-    for (int i = FR_THREADS - 1 - t; i < J; i += FR_THREADS) {
+    for (int i = NT - 1 - t; i < J; i += NT) {
         float a0 = 0.f, a1 = 0.f, a2 = 0.f;
         const int e0 = __ldg(vs.tg_ptr + i), e1 = __ldg(vs.tg_ptr + i + 1);
         for (int e = e0; e < e1; ++e) {
@@ -261,7 +266,7 @@ __global__ void __launch_bounds__(FR_THREADS, 5) k_frame_loss_bwd(BfModel m, BfV
     // live vertices: gather d(vertex) from the joints it feeds (per-row lists) and back-propagate it through the skinning
     // right away -- d(verts) stays in registers: dvp = (sum_k w_k A_jk)[:3,:3]^T dverts
     const int32_t* ltp = vs.lt_ptr + (size_t)row * (vs.lmax + 1);
-    for (int i = t; i < L; i += FR_THREADS) {
+    for (int i = t; i < L; i += NT) {
         float gx_ = 0.f, gy_ = 0.f, gz_ = 0.f;
         {
             const int e0 = __ldg(ltp + i), e1 = __ldg(ltp + i + 1);
@@ -299,14 +304,14 @@ __global__ void __launch_bounds__(FR_THREADS, 5) k_frame_loss_bwd(BfModel m, BfV
     float* dAb = f.dA + (size_t)b * J * 12;
     if (vs.n_nz < J) {                                 // joints without live vertices keep zero rows (16-byte stores)
         const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int i = t; i < J * 3; i += FR_THREADS) reinterpret_cast<float4*>(dAb)[i] = z;
+        for (int i = t; i < J * 3; i += NT) reinterpret_cast<float4*>(dAb)[i] = z;
     }
     __syncthreads();
     // 4 lanes per joint (the live skinning lists are short), 8 joints per warp at a time; the 12 (padded 16) partial sums
     // are reduced over the 4 lanes with a multi-value butterfly (8 + 4 shuffles), after which lane l of the group holds
     // elements 4l .. 4l+3 = one row of dA[j] -> one 16-byte store
     const int32_t* ljp = vs.lj_ptr + (size_t)row * (vs.n_nz + 1);
-    for (int jn0 = 0; jn0 < vs.n_nz; jn0 += 8 * (FR_THREADS / 32)) {
+    for (int jn0 = 0; jn0 < vs.n_nz; jn0 += 8 * (NT / 32)) {
         if (jn0 + warp * 8 >= vs.n_nz) break;                  // warp-uniform
         const int jn = jn0 + warp * 8 + (lane >> 2);
         const bool jv_ = jn < vs.n_nz;
