@@ -522,22 +522,32 @@ def _parse_blob(raw):
     return img, {k: sec[o:ends[ends.index(o) + 1]] for k, o in offs.items()}
 
 
-@pytest.mark.parametrize('case', ['smpl', 'smplx', 'smpl_kid', 'smpl_plain'])
+@pytest.mark.parametrize('case', ['smpl', 'smplx', 'smpl_kid', 'smpl_plain', 'smplx_official'])
 def test_bf_model_create_tables_match_python_builder(assets, case, tmp_path):
     """include/bodyfit_b200.h: bf_model_build_blob (what bf_model_create uploads) builds the SAME tables from the raw model
     arrays as bodyfitting_b200.model.PreparedModel: index tables bit for bit; folded / inverted float tables to rounding."""
-    mt = 'smplx' if case == 'smplx' else 'smpl'
+    mt = 'smplx' if case.startswith('smplx') else 'smpl'
+    model = assets(mt)
+    if case == 'smplx_official':
+        # the layout of the official files: no 'extra_vids' key (smplx hard-codes the ids), 300 shape + 100 expression directions
+        model = {k: v for k, v in model.items() if k != 'extra_vids'}
+        sd = np.asarray(model['shapedirs'], np.float32)
+        wide = np.zeros(sd.shape[:2] + (400,), np.float32)
+        wide[:, :, :10], wide[:, :, 300:310] = sd[:, :, :10], sd[:, :, 10:20]
+        wide[:, :, 10:300] = 1e-3                                      # directions the fit must not pick up
+        model['shapedirs'] = wide
     kw = {}
     if case == 'smpl_kid':
         kw = dict(kid_template=syn.make_kid_template(0))
     jx = assets('jx') if case in ('smpl', 'smpl_kid') else None
     gmm = None if case == 'smpl_plain' else assets('gmm')
-    pm = PreparedModel(mt, assets(mt), gmm=gmm, J_regressor_extra=jx, device='cpu', tensor_cores=True,
+    pm = PreparedModel(mt, model, gmm=gmm, J_regressor_extra=jx, device='cpu', tensor_cores=True,
                        age='kid' if case == 'smpl_kid' else 'adult', **kw)
     path = pm.save_blob(str(tmp_path / 'py.blob'))
     img_p, arr_p = _parse_blob(open(path, 'rb').read())
     from bodyfitting_b200.model import model_desc
-    d, keep = model_desc(mt, assets(mt), gmm=gmm, J_regressor_extra=jx, tensor_cores=True, **kw)
+    d, keep = model_desc(mt, model, gmm=gmm, J_regressor_extra=jx, tensor_cores=True, **kw)
+    assert (d.extra_vids is None) == (case == 'smplx_official')
     blob, n = ctypes.c_void_p(), ctypes.c_int64()
     rc = _lib.lib().bf_model_build_blob(ctypes.byref(d), ctypes.byref(blob), ctypes.byref(n))
     assert rc == 0, _lib.last_error()
