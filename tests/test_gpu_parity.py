@@ -574,6 +574,66 @@ def test_c_abi_host_without_python_tables(assets, tmp_path):
     assert L.bf_model_create(C.byref(bad), C.byref(mptr2)) != 0 and 'required' in _lib.last_error()
 
 
+def test_c_host_program(assets, tmp_path):
+    """tests/c_host/fit_host.cpp -- a C++ program that includes only include/bodyfit_b200.h -- is built with nvcc, reads a dump of
+    the raw model arrays and the inputs, builds the model tables itself (bf_model_create) and runs the fit; the parameters it
+    writes equal the Python session's bit for bit."""
+    import ctypes as C, shutil, struct, subprocess
+    from bodyfitting_b200 import _lib
+    from bodyfitting_b200.engine import FitSession, pack_cameras
+    from bodyfitting_b200.model import model_desc
+    if shutil.which('nvcc') is None:
+        pytest.skip('nvcc not on PATH')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / 'fit_host')
+    libdir = os.path.join(root, 'bodyfitting_b200')
+    r = subprocess.run(['nvcc', '-std=c++17', '-O2', '-I', os.path.join(root, 'include'), '-o', exe,
+                        os.path.join(root, 'tests', 'c_host', 'fit_host.cpp'), '-L', libdir, '-lbodyfit_b200',
+                        '-Xlinker', '-rpath', '-Xlinker', libdir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    mt, nv, B, N = 'smplx', 4, 21, 12
+    port = make_port(assets, mt)
+    sc = make_scene(port, mt, B, nv, seed=91)
+    pm = _prep(assets, mt)
+    kp = np.ascontiguousarray(sc['kp'], np.float32)
+    cams = pack_cameras(sc['c2ws'], sc['Ks']).astype(np.float32)
+    poses, betas = np.ascontiguousarray(sc['init_pose'], np.float32), np.ascontiguousarray(sc['init_betas'], np.float32)
+    # python session, same library loop
+    sess = FitSession(pm, B, nv, N + 1, graph=False, trace=True)
+    sess.load_inputs(torch.from_numpy(kp).cuda(), torch.from_numpy(cams).cuda(), torch.from_numpy(poses).cuda(), torch.from_numpy(betas).cuda())
+    sess.fb.t['theta'].copy_(sess.theta0); sess.fb.t['adam_m'].zero_(); sess.fb.t['adam_v'].zero_()
+    sess.fb.struct.iter = 0
+    sess.fb.call('bf_fit_run', N)
+    torch.cuda.synchronize()
+    perm = sess.perm0.cpu().numpy() if getattr(sess, 'sort_frames', False) else np.arange(B)
+    want = np.empty((B, pm.NP), np.float32)
+    want[perm] = sess.fb.t['theta'].cpu().numpy()                # the session processes frames in contour-row order
+    # dump for the C++ host: raw model arrays (BfModelDesc members in order) + inputs
+    desc, keep = model_desc(mt, assets(mt), gmm=assets('gmm'), tensor_cores=pm.tensor_cores)
+    by_ptr = {a.ctypes.data: a for a in keep}
+    path = str(tmp_path / 'in.bin')
+    with open(path, 'wb') as f:
+        f.write(struct.pack('<I', 0xB200C057))
+        for name, typ in _lib.BfModelDesc._fields_:
+            if typ is _lib._fp:
+                a = by_ptr.get(getattr(desc, name))
+                f.write(struct.pack('<q', a.nbytes if a is not None else 0))
+                if a is not None:
+                    f.write(a.tobytes())
+        f.write(struct.pack('<16i', *[getattr(desc, name) for name, typ in _lib.BfModelDesc._fields_ if typ is _lib._i32]))
+        f.write(struct.pack('<6i', B, nv, pm.K_used, poses.shape[1], N, 1))
+        for a in (kp, cams, poses, betas):
+            f.write(a.tobytes())
+    out = str(tmp_path / 'theta.bin')
+    r = subprocess.run([exe, path, out], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-2000:]
+    print(r.stdout.strip())
+    got = np.fromfile(out, np.float32).reshape(B, pm.NP)
+    d = np.abs(got - want).max()
+    print('C++ host vs Python session: max |d theta| %.2e' % d)
+    assert d < 1e-5                                                # identical tables -> identical fit (0 measured)
+
+
 def test_row_sorted_block_masked_fit_equals_plain_order(assets):
     """SMPL-X batches are processed in contour-row order, re-sorted during the fit, and the blend GEMMs skip the 16-vertex
     blocks a 128-frame tile does not need (BfFrames.blk_mask).  None of that may change a single bit: same results and the
