@@ -468,14 +468,28 @@ int bf_frame_loss_backward(const BfModel* m, const BfFrames* f, void* stream) {
     BfFrames g = *f;
     if (!bf_tc_ready_bwd(vs, f)) { g.dvp_hi = nullptr; g.dvp_lo = nullptr; }
     static int nt = 0;
-    if (!nt) { const char* e = getenv("BODYFIT_FRAME_THREADS"); const int v = e ? atoi(e) : 0; nt = v == 256 ? v : FR_THREADS; }
+    if (!nt) { const char* e = getenv("BODYFIT_FRAME_THREADS"); const int v = e ? atoi(e) : 0; nt = (v == 256 || v == 224) ? v : FR_THREADS; }
     const cudaStream_t s_ = (cudaStream_t)stream;
-    if (tma) {
-        if (nt == 224) k_frame_loss_bwd<1, 224><<<f->B, 224, smem, s_>>>(*m, *vs, g, skin_here);
-        else k_frame_loss_bwd<1, 256><<<f->B, 256, smem, s_>>>(*m, *vs, g, skin_here);
+    if (tma && nt == 160) {
+        // keypoints from global memory: 27 KB of shared memory per frame; the full carve-out makes room for eight CTAs per SM
+        const size_t smem2 = bf_frame_smem(m, vs, f->Nv, 2);
+        static bool carve[BF_MAXDEV] = {false};
+        const int dev = bf_cur_dev();
+        {
+            std::lock_guard<std::mutex> lk(g_bf_mu);
+            if (!carve[dev]) {
+                cudaFuncSetAttribute(k_frame_loss_bwd<2, 160>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+                cudaGetLastError();
+                carve[dev] = true;
+            }
+        }
+        k_frame_loss_bwd<2, 160><<<f->B, 160, smem2, s_>>>(*m, *vs, g, skin_here);
+    } else if (tma) {
+        if (nt == 256) k_frame_loss_bwd<1, 256><<<f->B, 256, smem, s_>>>(*m, *vs, g, skin_here);
+        else k_frame_loss_bwd<1, 224><<<f->B, 224, smem, s_>>>(*m, *vs, g, skin_here);
     } else {
-        if (nt == 224) k_frame_loss_bwd<0, 224><<<f->B, 224, smem, s_>>>(*m, *vs, g, skin_here);
-        else k_frame_loss_bwd<0, 256><<<f->B, 256, smem, s_>>>(*m, *vs, g, skin_here);
+        if (nt == 256) k_frame_loss_bwd<0, 256><<<f->B, 256, smem, s_>>>(*m, *vs, g, skin_here);
+        else k_frame_loss_bwd<0, 224><<<f->B, 224, smem, s_>>>(*m, *vs, g, skin_here);
     }
     BF_LAUNCH_CHECK();
     return BF_OK;

@@ -15,7 +15,7 @@
 #include "bf_common.cuh"
 #include "bf_loss.cuh"
 
-#define FR_THREADS 224      // default launch shape (BODYFIT_FRAME_THREADS=256: the previous one, A/B timing)
+#define FR_THREADS 160      // default launch shape (BODYFIT_FRAME_THREADS=224 / 256: the others, A/B timing)
 
 // Dynamic shared-memory layout of k_frame_loss_bwd (float offsets, every region 16-byte aligned); host and device use the
 // same function.  TMA = 1 adds the frame's keypoint row and two mbarriers.
@@ -33,7 +33,7 @@ __host__ __device__ __forceinline__ FrameSmem frame_smem_layout(int K, int Nv, i
     L.vp = L.dv + ldn;                          // [ldn] v_posed
     L.outb = L.vp + ldn;                        // [lmax*12] blended transforms, later d(verts) (x) [v_posed; 1]
     L.kp = L.outb + 12 * lmax;                  // [K*Nv*3] keypoint row (TMA only)
-    L.bars = L.kp + (tma ? ((K * Nv * 3 + 3) & ~3) : 0);
+    L.bars = L.kp + (tma == 1 ? ((K * Nv * 3 + 3) & ~3) : 0);       // tma == 2: transforms + v_posed by bulk copy, keypoints from global
     L.total = L.bars + (tma ? 4 : 0);
     return L;
 }
@@ -86,13 +86,18 @@ __device__ __forceinline__ void blend_transform(const BfVSet& vs, const float* A
 // TMA = 1: the frame's transforms, v_posed row and keypoint row (J*48 + 12*n + 12*K*Nv bytes, each one contiguous in
 // HBM) are fetched by three bulk copies issued by one thread at kernel entry; the keypoints land while the vertices are
 // being skinned, so the loss loop reads them from shared memory instead of waiting on HBM.
-// NT threads per CTA: 224 = seven warps cover the <= 224 live vertices of a row in one pass and leave two warps idle in the loss
-// loop (135 joints = five warps) instead of three; with five CTAs per SM the register budget is 56 instead of 48.  Measured in
-// one session, interleaved, 10,000 frames: 191.8 us with 256 threads, 188.9 us with 224, 215.7 us with 192 (two passes over the
-// vertices); the full carve-out attribute makes no difference.  Six CTAs of 224 threads (skinned vertices kept per live vertex
-// so that six 37 KB frames fit) need <= 40 registers and measured 191 us: not kept (profiles/r2_frame_kernel_experiments.md).
+// Launch shape.  The kernel is bound by the latency of a frame's dependent phases, so what counts is how many frames an SM holds:
+//   NT = 160, TMA = 2 (default): five warps per frame -- exactly the 135 joints of the loss loop, the kernel's longest phase; the live
+//     vertices take two passes -- and the keypoint row is read from global memory instead of being staged (13 KB less shared memory):
+//     27 KB per frame = EIGHT frames per SM at 48 registers.  Measured, 10,000 frames: 181.1 us; whole fit 48.1 ms.
+//   NT = 224, TMA = 1: seven warps, keypoints staged by a third bulk copy, five frames per SM, 56 registers: 189.0 us; fit 48.9 ms.
+//   NT = 256, TMA = 1: the round-1 shape, 48 registers: 191.8 us.
+// Not kept (profiles/r2_frame_kernel_experiments.md): 192 threads (staged keypoints, five frames: 215.7 us; global keypoints, six frames
+// at 56 registers: 208 us);
+// six frames of 224 threads with the skinned vertices kept per live vertex (<= 40 registers, spills: 191 us); persistent CTAs with
+// next-frame prefetch (203 us); a packed-fp32 (FFMA2) loss loop (197-232 us).
 template <int TMA, int NT>
-__global__ void __launch_bounds__(NT, 5) k_frame_loss_bwd(BfModel m, BfVSet vs, BfFrames f, int skin_here) {
+__global__ void __launch_bounds__(NT, NT == 160 ? 8 : 5) k_frame_loss_bwd(BfModel m, BfVSet vs, BfFrames f, int skin_here) {
     extern __shared__ __align__(16) float sm[];
     const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int K = m.K_used, Nv = f.Nv, J = m.J;
@@ -116,8 +121,15 @@ __global__ void __launch_bounds__(NT, 5) k_frame_loss_bwd(BfModel m, BfVSet vs, 
         tc::mbar_expect_tx(&bars[0], a_bytes + v_bytes);
         tc::bulk_g2s(As, f.A + (size_t)b * J * 12, a_bytes, &bars[0]);
         tc::bulk_g2s(vp, f.vposed + (size_t)b * f.ld_v, v_bytes, &bars[0]);
-        tc::mbar_expect_tx(&bars[1], k_bytes);
-        tc::bulk_g2s(sm + SL.kp, f.kp + (size_t)(f.frame_index ? f.frame_index[b] : b) * K * Nv * 3, k_bytes, &bars[1]);
+        if (TMA == 1) {
+            tc::mbar_expect_tx(&bars[1], k_bytes);
+            tc::bulk_g2s(sm + SL.kp, f.kp + (size_t)(f.frame_index ? f.frame_index[b] : b) * K * Nv * 3, k_bytes, &bars[1]);
+        }
+    }
+    if (TMA == 2 && t < K) {
+        // keypoints are read from global memory in the loss loop: pull this thread's row (Nv x 12 bytes) into L2 now
+        const char* kr = reinterpret_cast<const char*>(f.kp + ((size_t)(f.frame_index ? f.frame_index[b] : b) * K + t) * Nv * 3);
+        for (int o = 0; o < Nv * 12; o += 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(kr + o));
     }
     const int yaw = f.yaw ? f.yaw[b] : 0;
     const int row = vs.n_rows > 1 ? yaw : 0;
@@ -185,14 +197,14 @@ __global__ void __launch_bounds__(NT, 5) k_frame_loss_bwd(BfModel m, BfVSet vs, 
     // and the joint-major keypoint rows ([B,K,Nv,3]) are read as 16-byte vectors, four views at a time
     float acc5[5] = {0.f, 0.f, 0.f, 0.f, 0.f};               // loss, d/d transl (3), d/d scale
     const bool vec4 = (Nv & 3) == 0;
-    if (TMA) fr_wait(&bars[1]);                      // keypoint row (in flight since kernel entry)
+    if (TMA == 1) fr_wait(&bars[1]);                 // keypoint row (in flight since kernel entry)
     for (int k = t; k < K; k += NT) {
         float x[3];                                  // joint position (model space) + translation: q = x + T
         joint_pos(vs, k, yaw, Jtr_b, dv, x);
         const float qx = x[0] + tx, qy = x[1] + ty, qz = x[2] + tz;
         const float X = qx * sc * cs, Y = qy * sc * cs, Z = qz * sc * cs;
         float g0 = 0.f, g1 = 0.f, g2 = 0.f, ls = 0.f;
-        const float* kpr = TMA ? kps + k * Nv * 3 : f.kp + ((size_t)(f.frame_index ? f.frame_index[b] : b) * K + k) * Nv * 3;
+        const float* kpr = TMA == 1 ? kps + k * Nv * 3 : f.kp + ((size_t)(f.frame_index ? f.frame_index[b] : b) * K + k) * Nv * 3;
         for (int v0 = 0; v0 < Nv; v0 += 4) {
             float kv[12];
             if (vec4) {
