@@ -111,6 +111,7 @@ __global__ void __launch_bounds__(NT, NT == 160 ? 8 : 5) k_frame_loss_bwd(BfMode
     float4* outb = reinterpret_cast<float4*>(sm + SL.outb);
     const float* kps = sm + SL.kp;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + SL.bars);
+    const bool skin = skin_here != 0;
     const int n4 = (3 * vs.n + 3) / 4;                                  // float4s of a v_posed row; ld_v % 4 == 0 (checked on the host)
     if (TMA && t == 0) {
         tc::mbar_init(&bars[0], 1);
@@ -127,7 +128,8 @@ __global__ void __launch_bounds__(NT, NT == 160 ? 8 : 5) k_frame_loss_bwd(BfMode
         }
     }
     if (TMA == 2 && t < K) {
-        // keypoints are read from global memory in the loss loop: pull this thread's row (Nv x 12 bytes) into L2 now
+        // keypoints are read from global memory in the loss loop: pull this thread's row (Nv x 12 bytes) towards L2 now (measured:
+        // within noise either way -- eight resident frames hide the first touch)
         const char* kr = reinterpret_cast<const char*>(f.kp + ((size_t)(f.frame_index ? f.frame_index[b] : b) * K + t) * Nv * 3);
         for (int o = 0; o < Nv * 12; o += 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(kr + o));
     }
@@ -143,7 +145,7 @@ __global__ void __launch_bounds__(NT, NT == 160 ? 8 : 5) k_frame_loss_bwd(BfMode
             const float4* vsrc = reinterpret_cast<const float4*>(f.vposed + (size_t)b * f.ld_v);
             for (int i = t; i < n4; i += NT) reinterpret_cast<float4*>(vp)[i] = vsrc[i];
         }
-        if (!skin_here) {
+        if (!skin) {
             const float4* wsrc = reinterpret_cast<const float4*>(f.verts + (size_t)b * f.ld_v);
             for (int i = t; i < n4; i += NT) reinterpret_cast<float4*>(dv)[i] = wsrc[i];
         }
@@ -177,7 +179,7 @@ __global__ void __launch_bounds__(NT, NT == 160 ? 8 : 5) k_frame_loss_bwd(BfMode
     const float* Jtr_b = f.Jtr + (size_t)b * J * 3;
     const float invNv = 1.0f / (float)Nv;
 
-    if (skin_here) {                                 // skin the live vertices: verts = (sum_k w_k A_jk) [v_posed; 1]
+    if (skin) {                                 // skin the live vertices: verts = (sum_k w_k A_jk) [v_posed; 1]
         for (int i = t; i < L; i += NT) {
             const int v = __ldg(lv + i);
             float T[12];
@@ -289,7 +291,7 @@ __global__ void __launch_bounds__(NT, NT == 160 ? 8 : 5) k_frame_loss_bwd(BfMode
         }
         const int v = __ldg(lv + i);
         float T[9];
-        if (skin_here) {                               // blended transform saved by the forward skinning above
+        if (skin) {                               // blended transform saved by the forward skinning above
             const float4 r0 = outb[3 * i], r1 = outb[3 * i + 1], r2 = outb[3 * i + 2];
             T[0] = r0.x; T[1] = r0.y; T[2] = r0.z; T[3] = r1.x; T[4] = r1.y; T[5] = r1.z; T[6] = r2.x; T[7] = r2.y; T[8] = r2.z;
         } else {
