@@ -467,8 +467,13 @@ int bf_frame_loss_backward(const BfModel* m, const BfFrames* f, void* stream) {
     BF_REQUIRE(smem <= 48 * 1024, "active vertex set too large for the fused per-frame kernel");
     BfFrames g = *f;
     if (!bf_tc_ready_bwd(vs, f)) { g.dvp_hi = nullptr; g.dvp_lo = nullptr; }
-    static int nt = 0;
-    if (!nt) { const char* e = getenv("BODYFIT_FRAME_THREADS"); const int v = e ? atoi(e) : 0; nt = (v == 256 || v == 224) ? v : FR_THREADS; }
+    // Launch shape (bf_frame.cuh): eight resident frames of 160 threads win once the batch covers their 8 x SMs slots about twice
+    // (10,000 frames: 189 -> 181 us); a 1,250-frame shard is ONE wave of the 224-thread shape's slots plus a half, but one wave of
+    // the 160-thread shape plus 66 frames (37.8 vs 32.0 us), so small batches keep 224 x 5.  Both shapes run the same per-frame
+    // arithmetic in the same order (bit-identical; tests/test_gpu_parity.py::test_full_size_batch_properties crosses them).
+    static int nt_env = -1;
+    if (nt_env < 0) { const char* e = getenv("BODYFIT_FRAME_THREADS"); const int v = e ? atoi(e) : 0; nt_env = (v == 256 || v == 224 || v == 160) ? v : 0; }
+    const int nt = nt_env ? nt_env : (f->B >= 2048 ? 160 : 224);
     const cudaStream_t s_ = (cudaStream_t)stream;
     if (tma && nt == 160) {
         // keypoints from global memory: 27 KB of shared memory per frame; the full carve-out makes room for eight CTAs per SM

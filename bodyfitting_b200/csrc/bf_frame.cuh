@@ -15,7 +15,7 @@
 #include "bf_common.cuh"
 #include "bf_loss.cuh"
 
-#define FR_THREADS 160      // default launch shape (BODYFIT_FRAME_THREADS=224 / 256: the others, A/B timing)
+#define FR_THREADS 160      // launch shape of large batches (small ones: 224; BODYFIT_FRAME_THREADS=160 / 224 / 256 forces one)
 
 // Dynamic shared-memory layout of k_frame_loss_bwd (float offsets, every region 16-byte aligned); host and device use the
 // same function.  TMA = 1 adds the frame's keypoint row and two mbarriers.
@@ -87,10 +87,11 @@ __device__ __forceinline__ void blend_transform(const BfVSet& vs, const float* A
 // HBM) are fetched by three bulk copies issued by one thread at kernel entry; the keypoints land while the vertices are
 // being skinned, so the loss loop reads them from shared memory instead of waiting on HBM.
 // Launch shape.  The kernel is bound by the latency of a frame's dependent phases, so what counts is how many frames an SM holds:
-//   NT = 160, TMA = 2 (default): five warps per frame -- exactly the 135 joints of the loss loop, the kernel's longest phase; the live
+//   NT = 160, TMA = 2 (batches of >= 2048 frames): five warps per frame -- exactly the 135 joints of the loss loop, the kernel's longest phase; the live
 //     vertices take two passes -- and the keypoint row is read from global memory instead of being staged (13 KB less shared memory):
 //     27 KB per frame = EIGHT frames per SM at 48 registers.  Measured, 10,000 frames: 181.1 us; whole fit 48.1 ms.
-//   NT = 224, TMA = 1: seven warps, keypoints staged by a third bulk copy, five frames per SM, 56 registers: 189.0 us; fit 48.9 ms.
+//   NT = 224, TMA = 1 (smaller batches): seven warps, keypoints staged by a third bulk copy, five frames per SM, 56 registers:
+//     189.0 us; fit 48.9 ms; at 1,250 frames 32.0 us against 37.8 us for the 160-thread shape (one wave of 1,184 + 66 frames).
 //   NT = 256, TMA = 1: the round-1 shape, 48 registers: 191.8 us.
 // Not kept (profiles/r2_frame_kernel_experiments.md): 192 threads (staged keypoints, five frames: 215.7 us; global keypoints, six frames
 // at 56 registers: 208 us);
