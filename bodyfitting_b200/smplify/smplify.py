@@ -34,7 +34,7 @@ class SMPLify(object):
     def __init__(self, smpl_type='smpl', age='adult', step_size=1e-2, batch_size=1, num_iters=600,
                  gender='male', use_mask=False, device=torch.device('cuda'), debug=True,
                  model_data=None, gmm=None, J_regressor_extra=None, data_root='data', dense_every_iter=False,
-                 concurrent_parts=None, concurrent_min_part=2048, temporal_weight=0.0, halo_exchange=None, halo=None,
+                 concurrent_parts=None, concurrent_min_part=512, temporal_weight=0.0, halo_exchange=None, halo=None,
                  copy_outputs=None, graph=None, sort_frames=None, kid_template=None):
         if age not in ('adult', 'kid'):
             raise ValueError("age must be 'adult' or 'kid' (smplify.py:23,112-115)")
