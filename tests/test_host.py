@@ -577,3 +577,49 @@ def test_bf_model_create_tables_match_python_builder(assets, case, tmp_path):
     assert max([v for k, v in worst.items() if k not in loose] + [0.0]) < 1e-6, {k: v for k, v in worst.items() if v > 0}
     assert max([worst[k] for k in loose] + [0.0]) < 1e-3, {k: worst[k] for k in loose}
     print(case, 'largest relative differences:', {k: '%.1e' % v for k, v in worst.items() if v > 0})
+
+
+def test_bf_model_create_rejects_bad_descriptions(assets):
+    """bf_model_build_blob fails loudly (negative code + bf_last_error) instead of building tables from inconsistent input."""
+    from bodyfitting_b200.model import model_desc
+    L = _lib.lib()
+
+    def build(d):
+        blob, n = ctypes.c_void_p(), ctypes.c_int64()
+        rc = L.bf_model_build_blob(ctypes.byref(d), ctypes.byref(blob), ctypes.byref(n))
+        if rc == 0:
+            L.bf_blob_free(blob)
+        return rc, _lib.last_error()
+
+    rc, msg = build(_lib.BfModelDesc())
+    assert rc != 0 and 'required' in msg
+    # kinematic tree out of order
+    d, keep = model_desc('smpl', assets('smpl'))
+    par = np.ascontiguousarray(np.asarray(assets('smpl')['kintree_table'])[0].astype(np.int32))
+    par[3] = 7
+    d.parents = par.ctypes.data
+    rc, msg = build(d)
+    assert rc != 0 and 'topologically' in msg
+    # SMPL-X without its landmark tables
+    d, keep = model_desc('smplx', assets('smplx'))
+    d.lmk_faces_idx = None
+    rc, msg = build(d)
+    assert rc != 0 and 'landmark' in msg
+    # vertex-picked joint outside the mesh
+    d, keep = model_desc('smpl', assets('smpl'))
+    bad = np.full(21, 10 ** 6, np.int32)
+    d.extra_vids, d.n_extra_vids = bad.ctypes.data, 21
+    rc, msg = build(d)
+    assert rc != 0 and 'outside the mesh' in msg
+    # a covariance that is not positive definite
+    g = {k: np.array(v, dtype=np.float32) for k, v in assets('gmm').items()}
+    g['covars'][0] = -np.eye(69, dtype=np.float32)
+    d, keep = model_desc('smpl', assets('smpl'), gmm=g)
+    rc, msg = build(d)
+    assert rc != 0 and 'positive definite' in msg
+    # the kid template belongs to SMPL
+    d, keep = model_desc('smplx', assets('smplx'))
+    kid = np.zeros((d.V, 3), np.float32)
+    d.kid_template = kid.ctypes.data
+    rc, msg = build(d)
+    assert rc != 0 and 'SMPL only' in msg
