@@ -420,6 +420,13 @@ struct Builder {
         std::vector<int> jmap;
         if (smplx) {
             if (!d.faces || !d.lmk_faces_idx || !d.lmk_bary_coords || !d.dynamic_lmk_faces_idx || !d.dynamic_lmk_bary_coords) { err = "SMPL-X needs faces and the landmark tables"; return false; }
+            if (d.F <= 0 || d.n_lmk < 0 || d.n_dyn_rows <= 0 || d.n_dyn <= 0) { err = "SMPL-X needs F, n_dyn_rows, n_dyn > 0"; return false; }
+            for (int i = 0; i < d.n_lmk; ++i)
+                if (d.lmk_faces_idx[i] < 0 || d.lmk_faces_idx[i] >= d.F) { err = "lmk_faces_idx outside the face list"; return false; }
+            for (size_t i = 0; i < (size_t)d.n_dyn_rows * d.n_dyn; ++i)
+                if (d.dynamic_lmk_faces_idx[i] < 0 || d.dynamic_lmk_faces_idx[i] >= d.F) { err = "dynamic_lmk_faces_idx outside the face list"; return false; }
+            for (size_t i = 0; i < (size_t)d.F * 3; ++i)
+                if (d.faces[i] < 0 || d.faces[i] >= V) { err = "faces reference a vertex outside the mesh"; return false; }
             for (int i = 0; i < d.n_lmk; ++i) {
                 const int32_t* fc = d.faces + 3 * (size_t)d.lmk_faces_idx[i];
                 const float* b = d.lmk_bary_coords + 3 * (size_t)i;

@@ -605,6 +605,13 @@ def test_bf_model_create_rejects_bad_descriptions(assets):
     d.lmk_faces_idx = None
     rc, msg = build(d)
     assert rc != 0 and 'landmark' in msg
+    # a landmark face index beyond the face list
+    d, keep = model_desc('smplx', assets('smplx'))
+    lf = np.ascontiguousarray(np.asarray(assets('smplx')['lmk_faces_idx']).astype(np.int32))
+    lf[5] = d.F
+    d.lmk_faces_idx = lf.ctypes.data
+    rc, msg = build(d)
+    assert rc != 0 and 'outside the face list' in msg
     # vertex-picked joint outside the mesh
     d, keep = model_desc('smpl', assets('smpl'))
     bad = np.full(21, 10 ** 6, np.int32)
